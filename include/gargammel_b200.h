@@ -1,0 +1,174 @@
+/*
+ * gargammel_b200.h -- C-ABI of the B200-native gargammel hot path
+ * (fragSim -> deamSim -> adptSim per-fragment pipeline).
+ *
+ * The reference (grenaud/gargammel) has no library / FFI interface: the boundary
+ * of this path is the process CLI of three executables called by gargammel.pl
+ * (gargammel.pl:71-84,232-248).  This header is the thin C boundary between the
+ * C++11 host side (bin/fragSim, bin/deamSim, bin/adptSim, bin/gargammel-b200,
+ * the Python harness) and the hand-written sm_100a kernels.  Every entry point
+ * cites the reference code it replaces.  Plain pointers and sizes only; no C++
+ * or torch types cross this boundary; no exception crosses it.
+ *
+ * All functions return GG_OK (0) or a negative gg_status.  gg_last_error(ctx)
+ * returns a human-readable message for the last failure on that context.
+ * A context is bound to one CUDA device and one stream and is not thread-safe.
+ * There is NO CPU fallback: every gg_run_* launches CUDA kernels or fails.
+ */
+#ifndef GARGAMMEL_B200_H
+#define GARGAMMEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+
+typedef enum gg_status {
+    GG_OK            =  0,
+    GG_ERR_ARG       = -1,  /* bad argument / inconsistent tables            */
+    GG_ERR_CUDA      = -2,  /* CUDA runtime error (message has the detail)    */
+    GG_ERR_NOMEM     = -3,  /* host or device allocation failed               */
+    GG_ERR_STATE     = -4,  /* call order: tables/plan/genome missing         */
+    GG_ERR_PARSE     = -5,  /* malformed FASTA record stream                  */
+    GG_ERR_GIVEUP    = -6,  /* a fragment exhausted GG_MAX_ATTEMPTS attempts  */
+    GG_ERR_CAPACITY  = -7   /* caller buffer too small                        */
+} gg_status;
+
+/* Rejection loop bound per fragment (fragSim.cpp:1361 loops forever on an all-N genome). */
+#define GG_MAX_ATTEMPTS 65536u
+
+/* ---- fragment length model: selectFragmentLength, fragSim.cpp:137-187 ---- */
+typedef enum gg_size_mode {
+    GG_SIZE_FIXED = 0,   /* -l L              fragSim.cpp:181      */
+    GG_SIZE_LIST  = 1,   /* -s file           fragSim.cpp:149-152  */
+    GG_SIZE_FREQ  = 2    /* -f file           fragSim.cpp:156-178  */
+} gg_size_mode;
+
+/* ---- deamination model per damage slot ---- */
+typedef enum gg_damage_mode {
+    GG_DMG_NONE   = 0,
+    GG_DMG_MATRIX = 1,   /* -matfile / -profile    deamSim.cpp:1794-1930 */
+    GG_DMG_BRIGGS = 2,   /* -damage v,l,d,s        deamSim.cpp:1477-1613 */
+    GG_DMG_SINGLE = 3,   /* -mat single / -mapdamage f single  deamSim.cpp:1941-1971 */
+    GG_DMG_DOUBLE = 4    /* -mat double / -mapdamage f double  deamSim.cpp:1973-2002 */
+} gg_damage_mode;
+#define GG_MAX_DAMAGE_SLOTS 4
+
+/* ---- what the last stage writes ---- */
+typedef enum gg_emit_mode {
+    GG_EMIT_FRAG    = 0, /* fragSim record  ">def\nFRAG\n"             fragSim.cpp:1603      */
+    GG_EMIT_DEAM    = 1, /* deamSim record  "ID\nSEQ\n"                deamSim.cpp:2038      */
+    GG_EMIT_STDOUT4 = 2, /* adptSim default "ID\nF\nID_r\nR\n"         adptSim.cpp:408       */
+    GG_EMIT_ARTS    = 3, /* adptSim -arts   "ID\nF\n"                  adptSim.cpp:402       */
+    GG_EMIT_ARTP    = 4, /* adptSim -artp   "ID\nF revcomp(R)\n"       adptSim.cpp:403-406   */
+    GG_EMIT_FR      = 5, /* adptSim -fr     "ID\nF\n"                  adptSim.cpp:397       */
+    GG_EMIT_RR      = 6  /* adptSim -rr     "ID_r\nR\n"                adptSim.cpp:398       */
+} gg_emit_mode;
+
+/* One line of a samtools .fai index (faidx1_t, fragSim.cpp:61-65,249-259). */
+typedef struct gg_fai_entry {
+    const char* name;        /* NUL-terminated contig name                    */
+    int64_t     len;         /* bases                                         */
+    uint64_t    offset;      /* byte offset of the first base in the FASTA    */
+    int32_t     line_blen;   /* bases per line                                */
+    int32_t     line_len;    /* bytes per line incl. newline                  */
+} gg_fai_entry;
+
+/* One contiguous run of fragment ids drawn from one genome file: replaces one
+ * `fragSim -tag T -n N file` invocation of gargammel.pl:1476-1683 and the choice
+ * of deamination for that source (gargammel.pl:640-648,1698-1830). */
+typedef struct gg_range {
+    uint64_t first_id;       /* global fragment id of the first fragment      */
+    uint64_t count;          /* number of fragments                           */
+    int32_t  genome;         /* id returned by gg_genome_upload               */
+    int32_t  damage_slot;    /* 0..GG_MAX_DAMAGE_SLOTS-1, or -1 = no damage   */
+    char     tag[24];        /* NUL-terminated -tag string appended to defline (fragSim.cpp:1505-1507) */
+} gg_range;
+
+/* Result of a gg_run_*: a device-resident byte stream. */
+typedef struct gg_out {
+    void*    dev_ptr;        /* device pointer to the first output byte (owned by ctx) */
+    uint64_t bytes;          /* bytes produced                                */
+    uint64_t records;        /* fragments / records processed                 */
+    uint64_t attempts;       /* sampling attempts incl. rejected (fused/frag) */
+    uint64_t gather_bytes;   /* algorithmic genome-gather bytes: sum ceil(L/4)+ceil(L/8) */
+    uint64_t in_bytes;       /* input record bytes (stand-alone deam/adpt)    */
+    double   device_ms;      /* CUDA-event time of the kernels of this run    */
+    int32_t  launches;       /* kernels launched by this run                  */
+    int32_t  reserved;
+} gg_out;
+
+typedef struct gg_ctx gg_ctx;
+
+/* ---- lifetime ---- */
+int  gg_abi_version(void);
+int  gg_ctx_create(int device, uint64_t seed, gg_ctx** out);
+int  gg_ctx_destroy(gg_ctx* ctx);
+int  gg_ctx_set_seed(gg_ctx* ctx, uint64_t seed);
+const char* gg_last_error(gg_ctx* ctx);
+/* the CUDA stream the kernels run on (cudaStream_t as void*), for external event timing */
+void* gg_ctx_stream(gg_ctx* ctx);
+
+/* ---- genome: replaces IndexedGenome (mmap + fetchSeq), fragSim.cpp:192-331,1148-1166 ----
+ * fasta/n: host bytes of ONE plain FASTA file (caller-owned, may be freed after return);
+ * fai: its index.  Bases are upper-cased (fragSim.cpp:315), 2-bit packed + 1-bit non-ACGT mask,
+ * and stay resident in HBM.  Contigs are concatenated in lexicographic name order like the
+ * reference's std::map (fragSim.cpp:215,1152-1166). */
+int  gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n,
+                      const gg_fai_entry* fai, int n_chr, int* genome_id_out);
+int  gg_genome_count(gg_ctx* ctx);
+/* debug/parity helper: unpack `len` bases of contig `chr` (index in the caller's fai order) from `start` into ASCII (N for masked) */
+int  gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len, char* dst);
+
+/* ---- tables ---- */
+/* fragSim -l / -s / -f, -m, -M (fragSim.cpp:137-187,719-784,1375-1381).
+ * FREQ: len[i], cum[i] = running sum exactly as fragSim.cpp:765-768 accumulates it. */
+int  gg_tables_set_sizes(gg_ctx* ctx, int mode, const int32_t* len, const double* cum, int n,
+                         int fixed_len, int minlen, int maxlen);
+int  gg_tables_set_norev(gg_ctx* ctx, int norev);   /* --norev, fragSim.cpp:1463-1467 */
+/* deamSim -matfile/-profile (deamSim.cpp:956-1241): sub5[r][12], sub3[r][12] with index 0 = terminal base
+ * (i.e. AFTER the 3' reversal of deamSim.cpp:1236); clamp_last = !(-last) (deamSim.cpp:1811-1817). */
+int  gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5,
+                          const double* sub3, int rows3, int clamp_last);
+/* deamSim -mat single|double / -mapdamage (deamSim.cpp:1941-2002); protocol = GG_DMG_SINGLE or GG_DMG_DOUBLE */
+int  gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const double* sub5, int rows5,
+                                const double* sub3, int rows3);
+/* deamSim -damage v,l,d,s (deamSim.cpp:285-306,1477-1613) */
+int  gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, double s);
+int  gg_tables_clear_damage(gg_ctx* ctx, int slot);
+/* adptSim -f -s -l (adptSim.cpp:28-31,131-147) */
+int  gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int read_len);
+
+/* ---- plan: which fragment id comes from which genome with which tag/damage ---- */
+int  gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n);
+
+/* ---- runs ---- */
+/* fragment ids [first, first+count) of the plan; fused frag->deam->adpt in ONE kernel; emit selects the
+ * last stage's dialect (GG_EMIT_FRAG = fragSim only; GG_EMIT_DEAM = fragSim|deamSim; others add adptSim). */
+int  gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* out);
+/* stand-alone stages over a HOST byte stream of 2-line FASTA records (what the previous stage wrote):
+ * deamSim main loop deamSim.cpp:1300-2042; adptSim main loop adptSim.cpp:263-420.
+ * first_id = fragment id of the first record (0 for the reference CLI). */
+int  gg_run_deam(gg_ctx* ctx, const uint8_t* recs, size_t n, int slot, uint64_t first_id, gg_out* out);
+int  gg_run_adpt(gg_ctx* ctx, const uint8_t* recs, size_t n, int emit, uint64_t first_id, gg_out* out);
+/* same, with the record stream already resident on the device (used for device-timed benchmarks) */
+int  gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, gg_out* out);
+int  gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, gg_out* out);
+
+/* copy a run's bytes to the host (pinned staging inside; blocking) */
+int  gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n);
+/* CUDA-event time (ms) of the kernels of the last gg_run_* on this context */
+double gg_last_device_ms(gg_ctx* ctx);
+/* upper bound of output bytes per fragment for the current tables/plan and emit mode (0 on error) */
+uint64_t gg_max_record_bytes(gg_ctx* ctx, int emit);
+/* write 1<<log2_bytes bytes of scratch to evict L2 between timed iterations */
+int  gg_flush_l2(gg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARGAMMEL_B200_H */

@@ -1,0 +1,501 @@
+/*
+ * gg_oracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A single-threaded C++ restatement of the reference's per-fragment algorithm
+ * (grenaud/gargammel: src/fragSim.cpp, src/deamSim.cpp, src/adptSim.cpp), written from
+ * the reference's behaviour, with every random draw taken from the counter-based
+ * Philox4x32-10 stream specified in DESIGN.md ("Draw specification") instead of the
+ * reference's rand()/libgab helpers.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (gargammel_b200/csrc) never links or calls it.
+ *
+ * PARITY STATUS: the deterministic transforms (reverse complement, trimming, record grammar,
+ * matrix row selection, cumulative-probability pick) are pinned against the reference sources
+ * compiled with our shim (oracle/_ref, see oracle/Makefile) by tests/test_oracle_vs_ref.py;
+ * everything stochastic is pinned STATISTICALLY against those binaries (the reference is
+ * time-seeded and its uniform helpers live in un-vendored libgab: bit-level parity of the
+ * random stream is unpinnable).
+ *
+ * It reads bases THROUGH the FASTA line structure exactly like IndexedGenome::fetchSeq
+ * (fragSim.cpp:305-329); the product instead packs the genome to 2 bits once.  The two
+ * implementations share no code.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdio.h>
+#include <ctype.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <map>
+
+#include "../include/gargammel_b200.h"   /* struct layouts + enums only (gg_fai_entry, gg_range, modes) */
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+/* Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3" (SC'11). */
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                 uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* stream ids (counter word 3) -- DESIGN.md "Draw specification" */
+enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4 };
+
+struct Rng {
+    uint32_t k0, k1;
+    void block(uint64_t id, uint32_t blk, uint32_t stream, uint32_t out[4]) const {
+        philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), blk, stream, k0, k1, out);
+    }
+    /* word w of the stream: block w/4, lane w%4 */
+    uint32_t word(uint64_t id, uint32_t stream, uint32_t w) const {
+        uint32_t o[4]; block(id, w >> 2, stream, o); return o[w & 3];
+    }
+};
+/* the uniform in (0,1) used wherever the reference calls randomProb(): 31 bits, never 0 or 1 */
+static inline double u01(uint32_t x) { return ((double)(x >> 1) + 0.5) * (1.0 / 2147483648.0); }
+
+/* ------------------------------------------------------------------ helpers (libgab semantics inferred from call sites) */
+static inline bool isResolvedDNA(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+static inline int  base2int(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+static inline char complementBase(char c) {
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+}
+static std::string reverseComplement(const std::string& s) {
+    std::string r(s.size(), 'N');
+    for (size_t i = 0; i < s.size(); i++) r[i] = complementBase(s[s.size() - 1 - i]);
+    return r;
+}
+
+/* ------------------------------------------------------------------ state */
+struct Chr { std::string name; int64_t len; uint64_t offset; int32_t line_blen, line_len; uint64_t start, end; /* 1-based concatenated, fragSim.cpp:1160-1162 */ };
+struct Genome { std::vector<uint8_t> fasta; std::vector<Chr> chrs; /* name-sorted like std::map */ uint64_t G; };
+struct Damage {
+    int mode; int clamp_last;
+    std::vector<double> sub5, sub3;  /* rows x 12 */
+    double v, l, d, s;
+    Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0) {}
+};
+struct orc_ctx {
+    Rng rng;
+    std::vector<Genome> genomes;
+    int size_mode, fixed_len, minlen, maxlen, norev;
+    std::vector<int32_t> size_len; std::vector<double> size_cum;
+    Damage dmg[GG_MAX_DAMAGE_SLOTS];
+    std::string adF, adS; int read_len;
+    std::vector<gg_range> plan;
+    std::string err;
+    uint64_t attempts, gather_bytes;
+    orc_ctx() : size_mode(GG_SIZE_FIXED), fixed_len(20), minlen(0), maxlen(1000), norev(0),
+        adF("AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"),   /* adptSim.cpp:28 */
+        adS("AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"),         /* adptSim.cpp:29 */
+        read_len(100), attempts(0), gather_bytes(0) {}
+};
+
+/* ------------------------------------------------------------------ fragSim */
+/* IndexedGenome::fetchSeq, fragSim.cpp:305-329 (uppercase branch).  Positions that run past the
+ * file are returned as '\0' (the reference would read past the mmap: undefined). */
+static std::string fetchSeq(const Genome& g, const Chr& c, int64_t index, int n) {
+    std::string s; s.reserve(n);
+    int64_t index2 = index;
+    for (int j = 0; j < n; j++) {
+        uint64_t pos = c.offset + (uint64_t)(index2 / c.line_blen) * c.line_len + (uint64_t)(index2 % c.line_blen);
+        char ch = pos < g.fasta.size() ? (char)toupper(g.fasta[pos]) : '\0';
+        s += ch;
+        index2++;
+    }
+    return s;
+}
+
+/* selectFragmentLength, fragSim.cpp:137-187.  x0 = length word, x1 = fallback word (bits 31..1). */
+static int selectFragmentLength(const orc_ctx* c, uint32_t x0, uint32_t x1) {
+    if (c->size_mode == GG_SIZE_LIST) {                      /* :149-152  randomInt(0,n-1) */
+        uint64_t n = c->size_len.size();
+        return c->size_len[(size_t)(((uint64_t)x0 * n) >> 32)];
+    }
+    if (c->size_mode == GG_SIZE_FREQ) {                      /* :156-178 */
+        double p = u01(x0);
+        for (size_t i = 0; i < c->size_cum.size(); i++)
+            if (0.0 <= p && p <= c->size_cum[i]) return c->size_len[i];   /* cProbLower stays 0.0 (:159,:163) */
+        uint64_t n = c->size_len.size();                     /* :176 fallback: uniform row */
+        return c->size_len[(size_t)(((uint64_t)(x1 >> 1) * n) >> 31)];
+    }
+    return c->fixed_len;                                     /* :181 */
+}
+
+struct FragResult { const Chr* chr; uint64_t idx; int length; bool plus; std::string frag; };
+
+/* One fragment = the first accepted attempt; mirrors the while-loop body fragSim.cpp:1361-1507
+ * with distFromEnd == 0 (no --comp: fragSim.cpp:1019-1021), no --circ, no -gc. */
+static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, FragResult* out) {
+    for (uint32_t attempt = 0; attempt < GG_MAX_ATTEMPTS; attempt++) {
+        uint32_t x[4];
+        c->rng.block(id, attempt, ST_FRAG, x);
+        c->attempts++;
+        int length = selectFragmentLength(c, x[0], x[1]);
+        if (length < 0) continue;                            /* :1375 with distFromEnd 0 */
+        if (length < c->minlen) continue;                    /* :1377 */
+        if (length > c->maxlen) continue;                    /* :1380 */
+        /* randGenomicCoord, fragSim.cpp:80-93: uniform in [0,G).  (multiply-shift instead of %: DESIGN.md) */
+        uint64_t r64 = ((uint64_t)x[3] << 32) | x[2];
+        uint64_t coord = (uint64_t)(((unsigned __int128)r64 * g.G) >> 64);
+        /* chromosome scan fragSim.cpp:1397-1403: first chr with start <= coord <= end+1 */
+        const Chr* found = NULL;
+        for (size_t i = 0; i < g.chrs.size(); i++) {
+            if (g.chrs[i].start <= coord && coord <= g.chrs[i].end + 1) { found = &g.chrs[i]; break; }
+        }
+        if (!found) continue;   /* coord == 0: the reference redraws only the coordinate (:1390); we redraw the attempt */
+        uint64_t idx = coord - found->start;                 /* :1404 */
+        std::string temp;
+        if (idx + (uint64_t)length > (uint64_t)found->len) {
+            /* run-off: the reference fetches past the contig and always hits '\n', '>' or EOF, so
+             * isResolvedDNAstring rejects it (:1472).  Same outcome, stated directly. */
+            continue;
+        }
+        temp = fetchSeq(g, *found, (int64_t)idx, length);    /* :1443 */
+        bool plus = c->norev ? true : ((x[1] & 1u) != 0);    /* :1462-1467 randomBool */
+        bool resolved = true;                                /* :1472 isResolvedDNAstring */
+        for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
+        if (!resolved) continue;
+        if (!plus) temp = reverseComplement(temp);           /* :1484 */
+        out->chr = found; out->idx = idx; out->length = length; out->plus = plus; out->frag = temp;
+        c->gather_bytes += (uint64_t)((length + 3) / 4 + (length + 7) / 8);
+        return 0;
+    }
+    return GG_ERR_GIVEUP;
+}
+
+static std::string u64str(uint64_t v) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)v); return b; }
+
+/* defline, fragSim.cpp:1489/1498 + tag without separator :1505-1507; printed with '>' :1603 */
+static std::string fragDefline(const FragResult& f, const char* tag) {
+    return ">" + f.chr->name + ":" + (f.plus ? "+" : "-") + ":" + u64str(f.idx) + ":" + u64str(f.idx + f.length) + ":" + u64str(f.length) + tag;
+}
+
+/* ------------------------------------------------------------------ deamSim */
+/* cumulative table of a geometric_distribution<int>(p) (support 0,1,...; deamSim.cpp:297): CDF(k) = 1-(1-p)^(k+1),
+ * accumulated as a running product so that product and oracle can build it identically on the host. */
+static std::vector<double> geomCdf(double p, int n) {
+    std::vector<double> cdf(n); double q = 1.0;
+    for (int k = 0; k < n; k++) { q *= (1.0 - p); cdf[k] = 1.0 - q; }
+    return cdf;
+}
+static int geomDraw(const std::vector<double>& cdf, uint32_t x) {
+    double p = u01(x);
+    for (size_t k = 0; k < cdf.size(); k++) if (p <= cdf[k]) return (int)k;
+    return (int)cdf.size();
+}
+#define GEOM_TABLE 4096
+
+/* -matfile loop, deamSim.cpp:1794-1930 */
+static void deamMatrix(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+    int n5 = (int)(D.sub5.size() / 12), n3 = (int)(D.sub3.size() / 12);
+    int len = (int)seq.size();
+    for (int i = 0; i < len; i++) {
+        if (!isResolvedDNA(seq[i])) continue;                       /* :1795 */
+        double sumProb[5], _sumProb[5];
+        sumProb[0] = 0.0; _sumProb[0] = 0.0;
+        const double* row;
+        if (i < len / 2) {                                          /* :1805  5p */
+            int r = i;
+            if (r >= n5) { if (D.clamp_last) r = n5 - 1; else continue; }   /* :1811-1817 */
+            row = &D.sub5[(size_t)r * 12];
+        } else {                                                    /* :1868  3p */
+            int r = len - i - 1;                                    /* :1873 */
+            if (r >= n3) { if (D.clamp_last) r = n3 - 1; else continue; }   /* :1874-1880 */
+            row = &D.sub3[(size_t)r * 12];
+        }
+        int b = base2int(seq[i]);
+        double sum = 0.0;
+        for (int a = 0; a < 4; a++) {                               /* :1820-1830 */
+            if (a == b) continue;
+            int idx = (a < b) ? b * 3 + a : b * 3 + (a - 1);
+            sum += row[idx];
+            _sumProb[a + 1] = row[idx];
+        }
+        _sumProb[b + 1] = 1.0 - sum;                                /* :1831 */
+        double s = 0;
+        for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }   /* :1833-1837 */
+        double p = u01(c->rng.word(id, ST_DEAM, (uint32_t)i));      /* :1847 one uniform per resolved base */
+        for (int a = 0; a < 4; a++) {                               /* :1849-1863 */
+            if (sumProb[a] <= p && sumProb[a + 1] >= p) { seq[i] = "ACGT"[a]; break; }
+        }
+    }
+}
+
+/* -damage v,l,d,s loop, deamSim.cpp:1477-1613.  Draw layout: DEAM words 0,1,2 = 5' overhang, 3' overhang,
+ * nick position (geometric: first success of the per-base Bernoulli(v) scan :1503-1507); per-base word 4+i. */
+static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+    int len = (int)seq.size();
+    std::vector<double> cdfL = geomCdf(D.l, GEOM_TABLE), cdfV = geomCdf(D.v, GEOM_TABLE);
+    uint32_t h[4]; c->rng.block(id, 0, ST_DEAM, h);
+    int overhang5p = geomDraw(cdfL, h[0]);                          /* :1478 */
+    int overhang3p = geomDraw(cdfL, h[1]);                          /* :1479 */
+    if (overhang5p + overhang3p >= len) {                           /* :1483 all single strand */
+        for (int i = 0; i < len; i++)
+            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i)) < D.s) seq[i] = 'T';   /* :1486-1494 */
+        return;
+    }
+    int indexNick = geomDraw(cdfV, h[2]);                           /* first i with randomProb()<v, :1503-1507 */
+    for (int i = 0; i < len; i++) {
+        bool placedNick = (indexNick <= i);                         /* nick applies from its own position on (:1510) */
+        double p = u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i));
+        if ((i + 1) <= overhang5p) {                                /* :1513 / :1557 */
+            if (seq[i] == 'C' && p < D.s) seq[i] = 'T';
+        } else if ((len - i) <= overhang3p) {                       /* :1527 / :1571 */
+            if (seq[i] == 'G' && p < D.s) seq[i] = 'A';
+        } else if (placedNick) {                                    /* :1542 */
+            if (seq[i] == 'G' && p < D.d) seq[i] = 'A';
+        } else {                                                    /* :1586 */
+            if (seq[i] == 'C' && p < D.d) seq[i] = 'T';
+        }
+    }
+}
+
+/* -mat single|double / -mapdamage loops, deamSim.cpp:1941-2002.  Row index clamped to the last row
+ * (the reference indexes out of bounds for len > rows: DESIGN.md deviation). */
+static void deamSingleDouble(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+    int n5 = (int)(D.sub5.size() / 12), n3 = (int)(D.sub3.size() / 12);
+    int len = (int)seq.size();
+    for (int i = 0; i < len; i++) {                                 /* :1944-1954 / :1976-1986 */
+        if (seq[i] == 'C') {
+            int r = std::min(i, n5 - 1);
+            if (u01(c->rng.word(id, ST_DEAM, (uint32_t)i)) < D.sub5[(size_t)r * 12 + 5]) seq[i] = 'T';
+        }
+    }
+    for (int i = 0; i < len; i++) {
+        int r = std::min(len - i - 1, n3 - 1);
+        if (D.mode == GG_DMG_SINGLE) {                              /* :1957-1967 */
+            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 5]) seq[i] = 'T';
+        } else {                                                    /* :1989-2000 */
+            if (seq[i] == 'G' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 6]) seq[i] = 'A';
+        }
+    }
+}
+
+static void deaminate(const orc_ctx* c, int slot, uint64_t id, std::string& seq) {
+    for (size_t i = 0; i < seq.size(); i++) seq[i] = (char)toupper(seq[i]);   /* deamSim.cpp:1319-1321 */
+    if (slot < 0) return;
+    const Damage& D = c->dmg[slot];
+    switch (D.mode) {
+        case GG_DMG_MATRIX: deamMatrix(c, D, id, seq); break;
+        case GG_DMG_BRIGGS: deamBriggs(c, D, id, seq); break;
+        case GG_DMG_SINGLE: case GG_DMG_DOUBLE: deamSingleDouble(c, D, id, seq); break;
+        default: break;
+    }
+}
+
+/* ------------------------------------------------------------------ adptSim */
+/* randomDNASeq(n) (libgab): n uniform bases; word q/16 of the stream, 2 bits each */
+static std::string randomDNASeq(const orc_ctx* c, uint64_t id, uint32_t stream, int n) {
+    std::string s(n, 'A');
+    for (int q = 0; q < n; q++) {
+        uint32_t w = c->rng.word(id, stream, (uint32_t)(q >> 4));
+        s[q] = "ACGT"[(w >> (2 * (q & 15))) & 3];
+    }
+    return s;
+}
+/* adptSim.cpp:288-322 */
+static void adaptReads(const orc_ctx* c, uint64_t id, const std::string& seq_in, std::string& seqf, std::string& seqr) {
+    seqf = seq_in;
+    for (size_t i = 0; i < seqf.size(); i++) seqf[i] = (char)toupper(seqf[i]);       /* :288 */
+    seqr = reverseComplement(seqf);                                                   /* :289 */
+    int L = c->read_len;
+    if ((int)seqf.size() < L) { seqf = seqf + c->adF; seqf = seqf.substr(0, L); }      /* :298-301 */
+    else seqf = seqf.substr(0, L);                                                    /* :303 */
+    if ((int)seqf.size() < L) seqf = seqf + randomDNASeq(c, id, ST_ADPT_F, L - (int)seqf.size());   /* :307-310 */
+    if ((int)seqr.size() < L) { seqr = seqr + c->adS; seqr = seqr.substr(0, L); }      /* :313-315 */
+    else seqr = seqr.substr(0, L);                                                    /* :317 */
+    if ((int)seqr.size() < L) seqr = seqr + randomDNASeq(c, id, ST_ADPT_R, L - (int)seqr.size());   /* :320-322 */
+}
+/* adptSim.cpp:396-411 */
+static void emitAdpt(int emit, const std::string& namef, const std::string& seqf, const std::string& seqr, std::string& out) {
+    std::string namer = namef + "_r";                                                 /* :286 */
+    switch (emit) {
+        case GG_EMIT_STDOUT4: out += namef + "\n" + seqf + "\n" + namer + "\n" + seqr + "\n"; break;   /* :408 */
+        case GG_EMIT_ARTS: case GG_EMIT_FR: out += namef + "\n" + seqf + "\n"; break;                  /* :402 / :397 */
+        case GG_EMIT_RR: out += namer + "\n" + seqr + "\n"; break;                                     /* :398 */
+        case GG_EMIT_ARTP: out += namef + "\n" + seqf + reverseComplement(seqr) + "\n"; break;         /* :404-405 */
+        default: break;
+    }
+}
+
+/* ------------------------------------------------------------------ extern "C" surface (mirrors include/gargammel_b200.h with orc_ prefix) */
+extern "C" {
+
+int orc_ctx_create(uint64_t seed, orc_ctx** out) {
+    orc_ctx* c = new orc_ctx(); c->rng.k0 = (uint32_t)seed; c->rng.k1 = (uint32_t)(seed >> 32); *out = c; return 0;
+}
+int orc_ctx_destroy(orc_ctx* c) { delete c; return 0; }
+int orc_ctx_set_seed(orc_ctx* c, uint64_t seed) { c->rng.k0 = (uint32_t)seed; c->rng.k1 = (uint32_t)(seed >> 32); return 0; }
+const char* orc_last_error(orc_ctx* c) { return c->err.c_str(); }
+
+void orc_philox(uint64_t seed, uint64_t id, uint32_t blk, uint32_t stream, uint32_t* out4) {
+    Rng r; r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32); r.block(id, blk, stream, out4);
+}
+void orc_philox_raw(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+    philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4);
+}
+
+int orc_genome_upload(orc_ctx* c, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int* id_out) {
+    Genome g; g.fasta.assign(fasta, fasta + n);
+    std::map<std::string, Chr> byname;                      /* std::map ordering, fragSim.cpp:215 */
+    for (int i = 0; i < n_chr; i++) {
+        Chr ch; ch.name = fai[i].name; ch.len = fai[i].len; ch.offset = fai[i].offset;
+        ch.line_blen = fai[i].line_blen; ch.line_len = fai[i].line_len; ch.start = ch.end = 0;
+        if (ch.len <= 0 || ch.line_blen <= 0 || ch.line_len < ch.line_blen) { c->err = "bad fai entry"; return GG_ERR_ARG; }
+        byname.insert(std::make_pair(ch.name, ch));         /* duplicates: first wins, like map::insert (:266) */
+    }
+    uint64_t G = 0;
+    for (std::map<std::string, Chr>::iterator it = byname.begin(); it != byname.end(); ++it) {   /* :1152-1166 */
+        Chr ch = it->second; ch.start = G + 1; ch.end = G + (uint64_t)ch.len; G += (uint64_t)ch.len;
+        g.chrs.push_back(ch);
+    }
+    g.G = G;
+    c->genomes.push_back(g);
+    if (id_out) *id_out = (int)c->genomes.size() - 1;
+    return 0;
+}
+
+int orc_tables_set_sizes(orc_ctx* c, int mode, const int32_t* len, const double* cum, int n, int fixed_len, int minlen, int maxlen) {
+    c->size_mode = mode; c->fixed_len = fixed_len; c->minlen = minlen; c->maxlen = maxlen;
+    c->size_len.clear(); c->size_cum.clear();
+    if (mode != GG_SIZE_FIXED) {
+        if (n <= 0) { c->err = "empty size table"; return GG_ERR_ARG; }
+        c->size_len.assign(len, len + n);
+        if (mode == GG_SIZE_FREQ) c->size_cum.assign(cum, cum + n);
+    }
+    return 0;
+}
+int orc_tables_set_norev(orc_ctx* c, int norev) { c->norev = norev; return 0; }
+int orc_tables_set_matrix(orc_ctx* c, int slot, const double* sub5, int rows5, const double* sub3, int rows3, int clamp_last) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || rows5 <= 0 || rows3 <= 0) return GG_ERR_ARG;
+    Damage& D = c->dmg[slot]; D.mode = GG_DMG_MATRIX; D.clamp_last = clamp_last;
+    D.sub5.assign(sub5, sub5 + (size_t)rows5 * 12); D.sub3.assign(sub3, sub3 + (size_t)rows3 * 12);
+    return 0;
+}
+int orc_tables_set_singledouble(orc_ctx* c, int slot, int protocol, const double* sub5, int rows5, const double* sub3, int rows3) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || rows5 <= 0 || rows3 <= 0) return GG_ERR_ARG;
+    if (protocol != GG_DMG_SINGLE && protocol != GG_DMG_DOUBLE) return GG_ERR_ARG;
+    Damage& D = c->dmg[slot]; D.mode = protocol; D.clamp_last = 1;
+    D.sub5.assign(sub5, sub5 + (size_t)rows5 * 12); D.sub3.assign(sub3, sub3 + (size_t)rows3 * 12);
+    return 0;
+}
+int orc_tables_set_briggs(orc_ctx* c, int slot, double v, double l, double d, double s) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
+    Damage& D = c->dmg[slot]; D.mode = GG_DMG_BRIGGS; D.v = v; D.l = l; D.d = d; D.s = s; return 0;
+}
+int orc_tables_clear_damage(orc_ctx* c, int slot) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
+    c->dmg[slot] = Damage(); return 0;
+}
+int orc_tables_set_adapters(orc_ctx* c, const char* fwd, const char* rev, int read_len) {
+    c->adF = fwd; c->adS = rev; c->read_len = read_len; return 0;
+}
+int orc_plan_set(orc_ctx* c, const gg_range* r, int n) { c->plan.assign(r, r + n); return 0; }
+
+/* fused: for each id: fragSim record -> deamSim -> adptSim, i.e. the literal composition of the three loops */
+int orc_run_fused(orc_ctx* c, uint64_t first, uint64_t count, int emit, uint8_t* dst, size_t cap, size_t* n_out, gg_out* info) {
+    std::string out;
+    c->attempts = 0; c->gather_bytes = 0;
+    for (uint64_t id = first; id < first + count; id++) {
+        const gg_range* rg = NULL;
+        for (size_t k = 0; k < c->plan.size(); k++)
+            if (id >= c->plan[k].first_id && id < c->plan[k].first_id + c->plan[k].count) { rg = &c->plan[k]; break; }
+        if (!rg) { c->err = "fragment id outside the plan"; return GG_ERR_STATE; }
+        if (rg->genome < 0 || rg->genome >= (int)c->genomes.size()) { c->err = "bad genome id"; return GG_ERR_ARG; }
+        FragResult f;
+        int rc = sampleFragment(c, c->genomes[rg->genome], id, &f);
+        if (rc) { c->err = "fragment exhausted its attempts"; return rc; }
+        std::string name = fragDefline(f, rg->tag);
+        std::string seq = f.frag;
+        if (emit == GG_EMIT_FRAG) { out += name + "\n" + seq + "\n"; continue; }      /* fragSim.cpp:1603 */
+        deaminate(c, rg->damage_slot, id, seq);
+        if (emit == GG_EMIT_DEAM) { out += name + "\n" + seq + "\n"; continue; }      /* deamSim.cpp:2038 */
+        std::string seqf, seqr;
+        adaptReads(c, id, seq, seqf, seqr);
+        emitAdpt(emit, name, seqf, seqr, out);
+    }
+    if (info) { memset(info, 0, sizeof *info); info->bytes = out.size(); info->records = count; info->attempts = c->attempts; info->gather_bytes = c->gather_bytes; }
+    *n_out = out.size();
+    if (out.size() > cap) return GG_ERR_CAPACITY;
+    memcpy(dst, out.data(), out.size());
+    return 0;
+}
+
+/* split a 2-line FASTA record stream (what fragSim/deamSim write; FastQParser(file,true) in deamSim.cpp:1288) */
+static int splitRecords(orc_ctx* c, const uint8_t* in, size_t n, std::vector<std::pair<std::string, std::string> >& recs) {
+    size_t p = 0;
+    while (p < n) {
+        const uint8_t* e = (const uint8_t*)memchr(in + p, '\n', n - p);
+        size_t le = e ? (size_t)(e - in) : n;
+        std::string id((const char*)in + p, le - p);
+        p = le + 1;
+        if (id.empty() && p >= n) break;
+        if (id.empty() || id[0] != '>') { c->err = "record does not start with '>'"; return GG_ERR_PARSE; }
+        if (p > n) p = n;
+        e = p < n ? (const uint8_t*)memchr(in + p, '\n', n - p) : NULL;
+        le = e ? (size_t)(e - in) : n;
+        std::string seq((const char*)in + p, le - p);
+        p = le + 1;
+        recs.push_back(std::make_pair(id, seq));
+    }
+    return 0;
+}
+
+int orc_run_deam(orc_ctx* c, const uint8_t* in, size_t n, int slot, uint64_t first_id, uint8_t* dst, size_t cap, size_t* n_out, gg_out* info) {
+    std::vector<std::pair<std::string, std::string> > recs;
+    int rc = splitRecords(c, in, n, recs); if (rc) return rc;
+    std::string out;
+    for (size_t r = 0; r < recs.size(); r++) {
+        std::string seq = recs[r].second;
+        deaminate(c, slot, first_id + r, seq);
+        out += recs[r].first + "\n" + seq + "\n";                                     /* deamSim.cpp:2038 */
+    }
+    if (info) { memset(info, 0, sizeof *info); info->bytes = out.size(); info->records = recs.size(); info->in_bytes = n; }
+    *n_out = out.size();
+    if (out.size() > cap) return GG_ERR_CAPACITY;
+    memcpy(dst, out.data(), out.size());
+    return 0;
+}
+
+int orc_run_adpt(orc_ctx* c, const uint8_t* in, size_t n, int emit, uint64_t first_id, uint8_t* dst, size_t cap, size_t* n_out, gg_out* info) {
+    std::vector<std::pair<std::string, std::string> > recs;
+    int rc = splitRecords(c, in, n, recs); if (rc) return rc;
+    std::string out;
+    for (size_t r = 0; r < recs.size(); r++) {
+        std::string seqf, seqr;
+        adaptReads(c, first_id + r, recs[r].second, seqf, seqr);
+        emitAdpt(emit, recs[r].first, seqf, seqr, out);
+    }
+    if (info) { memset(info, 0, sizeof *info); info->bytes = out.size(); info->records = recs.size(); info->in_bytes = n; }
+    *n_out = out.size();
+    if (out.size() > cap) return GG_ERR_CAPACITY;
+    memcpy(dst, out.data(), out.size());
+    return 0;
+}
+
+/* deterministic transforms exposed one by one for level-2 parity tests */
+int orc_revcomp(const char* in, int n, char* out) {
+    std::string r = reverseComplement(std::string(in, n)); memcpy(out, r.data(), n); return 0;
+}
+int orc_fetch(orc_ctx* c, int genome, int chr_sorted, int64_t start, int len, char* dst) {
+    if (genome < 0 || genome >= (int)c->genomes.size()) return GG_ERR_ARG;
+    const Genome& g = c->genomes[genome];
+    if (chr_sorted < 0 || chr_sorted >= (int)g.chrs.size()) return GG_ERR_ARG;
+    std::string s = fetchSeq(g, g.chrs[chr_sorted], start, len); memcpy(dst, s.data(), len); return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,2 @@
+/* api/BamMultiReader.h -- SHIM, see api/BamAux.h */
+#include "BamAux.h"

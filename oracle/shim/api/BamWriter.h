@@ -1,0 +1,2 @@
+/* api/BamWriter.h -- SHIM, see api/BamAux.h */
+#include "BamAux.h"

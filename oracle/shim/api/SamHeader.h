@@ -1,0 +1,2 @@
+/* api/SamHeader.h -- SHIM, see api/BamAux.h */
+#include "BamAux.h"
