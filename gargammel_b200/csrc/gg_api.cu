@@ -1,0 +1,762 @@
+// gg_api.cu -- implementation of the C-ABI in include/gargammel_b200.h.
+// Host side of the device path: owns the CUDA context state (stream, events, HBM-resident genomes and tables),
+// turns the reference's floating-point tables into exact integer thresholds, sizes shared memory, launches the
+// kernels in gg_kernels.cu.  There is no CPU fallback: without a CUDA device every gg_run_* fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/gargammel_b200.h"
+#include "gg_kernels.cuh"
+
+using namespace ggk;
+
+namespace {
+
+struct DBuf {                       // grow-only device buffer
+    void* p; size_t cap;
+    DBuf() : p(nullptr), cap(0) {}
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + (n >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cudaGetLastError(); e = cudaMalloc(&p, n); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct HostContig { std::string name; uint64_t len, offset; int32_t blen, llen; uint64_t gbase, cum_end; int fai_index; };
+struct HostGenome {
+    std::vector<HostContig> contigs;      // name-sorted (std::map order, fragSim.cpp:215,1152)
+    std::vector<int> fai2sorted;
+    uint64_t G, n_units;
+    uint32_t* d_seq2; uint32_t* d_nmask;
+    int first_contig;
+};
+struct HostDamage {
+    int mode, rows5, rows3, clamp_last;
+    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd;
+    DBuf d_thr, d_sd5, d_sd3, d_geoL, d_geoV;
+    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0) {}
+};
+
+const int GEO_TABLE = 4096;          // geometric inverse-CDF table length (overhangs / nick position)
+const int MAX_FRAG_LEN = 4095;
+
+// p = (u31 + 0.5) / 2^31.   number of u31 with p <= c   (cum[a] <= p <= cum[a+1] picks, deamSim.cpp:1850; p <= cProb, fragSim.cpp:165)
+uint32_t thr_le(double c) {
+    if (!(c == c)) return 0;
+    const double y = c * 2147483648.0 - 0.5;
+    if (y < 0.0) return 0;
+    const double k = floor(y) + 1.0;
+    return k >= 2147483648.0 ? 2147483648u : (uint32_t)k;
+}
+// number of u31 with p < c   (randomProb() < rate, deamSim.cpp:1488-1587,1948-1993)
+uint32_t thr_lt(double c) {
+    if (!(c == c)) return 0;
+    const double y = c * 2147483648.0 - 0.5;
+    if (y <= 0.0) return 0;
+    const double k = ceil(y);
+    return k >= 2147483648.0 ? 2147483648u : (uint32_t)k;
+}
+
+} // namespace
+
+struct gg_ctx {
+    int device; cudaStream_t st; cudaEvent_t ev0, ev1;
+    uint64_t seed; std::string err;
+    int sm_count; size_t smem_optin;
+    // genomes
+    std::vector<HostGenome> genomes;
+    DBuf d_cum_end, d_gbase, d_clen, d_name_off, d_name_len, d_names, d_genomes;
+    bool ctab_dirty;
+    int n_contigs_total;
+    // sizes
+    int size_mode, fixed_len, minlen, maxlen, norev;
+    std::vector<int32_t> size_len; std::vector<uint32_t> size_thr;
+    DBuf d_size_len, d_size_thr;
+    bool sizes_set;
+    // damage
+    HostDamage dmg[GG_MAX_DAMAGE_SLOTS];
+    // adapters
+    std::string adF, adS; int read_len;
+    DBuf d_adF2, d_adS2, d_rcS2, d_adF, d_adS;
+    bool ad_dirty;
+    // plan
+    std::vector<gg_range> plan; DBuf d_ranges; bool plan_dirty;
+    // run state
+    DBuf d_out, d_out2, d_tile_state, d_ticket_stats, d_in, d_nl, d_scan, d_sizes, d_flush;
+    void* h_pinned; size_t h_pinned_cap;
+    double last_ms;
+
+    int fail(int code, const std::string& msg) { err = msg; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e); cudaGetLastError(); return GG_ERR_CUDA;
+    }
+};
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); } while (0)
+
+namespace {
+
+template <typename T> int upload_vec(gg_ctx* ctx, DBuf& b, const std::vector<T>& v, size_t slack_elems = 0) {
+    const size_t bytes = (v.size() + slack_elems) * sizeof(T);
+    CK(b.ensure(bytes ? bytes : sizeof(T)));
+    if (slack_elems) CK(cudaMemsetAsync(b.p, 0, bytes, ctx->st));
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));     // v may be a temporary
+    return GG_OK;
+}
+
+std::vector<uint32_t> pack2(const std::string& s) {
+    std::vector<uint32_t> w((s.size() + 15) / 16, 0u);
+    for (size_t i = 0; i < s.size(); i++) {
+        uint32_t c = s[i] == 'A' ? 0u : s[i] == 'C' ? 1u : s[i] == 'G' ? 2u : 3u;
+        w[i >> 4] |= c << (2 * (i & 15));
+    }
+    return w;
+}
+std::string revcomp(const std::string& s) {
+    std::string r(s.size(), 'N');
+    for (size_t i = 0; i < s.size(); i++) {
+        char c = s[s.size() - 1 - i];
+        r[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    }
+    return r;
+}
+
+int sync_contig_tables(gg_ctx* ctx) {
+    if (!ctx->ctab_dirty) return GG_OK;
+    std::vector<uint64_t> cum_end, gbase; std::vector<uint32_t> clen, name_off; std::vector<uint16_t> name_len; std::vector<char> names;
+    std::vector<GenomeDev> gd;
+    for (size_t g = 0; g < ctx->genomes.size(); g++) {
+        HostGenome& H = ctx->genomes[g];
+        H.first_contig = (int)cum_end.size();
+        for (size_t i = 0; i < H.contigs.size(); i++) {
+            const HostContig& c = H.contigs[i];
+            cum_end.push_back(c.cum_end); gbase.push_back(c.gbase); clen.push_back((uint32_t)c.len);
+            name_off.push_back((uint32_t)names.size()); name_len.push_back((uint16_t)c.name.size());
+            names.insert(names.end(), c.name.begin(), c.name.end());
+        }
+        GenomeDev d; d.seq2 = H.d_seq2; d.nmask = H.d_nmask; d.G = H.G; d.first_contig = H.first_contig; d.n_contigs = (int)H.contigs.size();
+        gd.push_back(d);
+    }
+    ctx->n_contigs_total = (int)cum_end.size();
+    int rc;
+    if ((rc = upload_vec(ctx, ctx->d_cum_end, cum_end))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_gbase, gbase))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_clen, clen))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_name_off, name_off))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_name_len, name_len))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_names, names, 16))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_genomes, gd))) return rc;
+    ctx->ctab_dirty = false;
+    return GG_OK;
+}
+
+int sync_adapters(gg_ctx* ctx) {
+    if (!ctx->ad_dirty) return GG_OK;
+    int rc;
+    if ((rc = upload_vec(ctx, ctx->d_adF2, pack2(ctx->adF), 3))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_adS2, pack2(ctx->adS), 3))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_rcS2, pack2(revcomp(ctx->adS)), 3))) return rc;
+    std::vector<uint8_t> f(ctx->adF.begin(), ctx->adF.end()), s(ctx->adS.begin(), ctx->adS.end());
+    if ((rc = upload_vec(ctx, ctx->d_adF, f, 16))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_adS, s, 16))) return rc;
+    ctx->ad_dirty = false;
+    return GG_OK;
+}
+
+int sync_plan(gg_ctx* ctx) {
+    if (!ctx->plan_dirty) return GG_OK;
+    std::vector<RangeDev> r(ctx->plan.size());
+    for (size_t i = 0; i < r.size(); i++) {
+        memset(&r[i], 0, sizeof(RangeDev));
+        r[i].first_id = ctx->plan[i].first_id; r[i].count = ctx->plan[i].count;
+        r[i].genome = ctx->plan[i].genome; r[i].slot = ctx->plan[i].damage_slot;
+        r[i].tag_len = (int)strnlen(ctx->plan[i].tag, sizeof(ctx->plan[i].tag) - 1);
+        memcpy(r[i].tag, ctx->plan[i].tag, r[i].tag_len);
+    }
+    int rc = upload_vec(ctx, ctx->d_ranges, r);
+    if (rc) return rc;
+    ctx->plan_dirty = false;
+    return GG_OK;
+}
+
+void fill_damage_dev(const HostDamage& H, ggd::DamageDev* D) {
+    memset(D, 0, sizeof *D);
+    D->mode = H.mode; D->rows5 = H.rows5; D->rows3 = H.rows3; D->clamp_last = H.clamp_last;
+    D->thr = H.d_thr.as<uint4>(); D->sd5 = H.d_sd5.as<uint32_t>(); D->sd3 = H.d_sd3.as<uint32_t>();
+    D->Ks = H.Ks; D->Kd = H.Kd; D->geoL = H.d_geoL.as<uint32_t>(); D->geoV = H.d_geoV.as<uint32_t>(); D->n_geo = GEO_TABLE;
+}
+
+int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
+
+// largest fragment length the size model can emit
+int max_frag_len(const gg_ctx* ctx) {
+    if (ctx->size_mode == GG_SIZE_FIXED) return ctx->fixed_len;
+    int m = 0;
+    for (size_t i = 0; i < ctx->size_len.size(); i++)
+        if (ctx->size_len[i] >= ctx->minlen && ctx->size_len[i] <= ctx->maxlen) m = std::max(m, ctx->size_len[i]);
+    return m;
+}
+int emit_lines(int emit) { return emit == GG_EMIT_STDOUT4 ? 2 : 1; }
+int emit_seqlen(int emit, int L, int RL) { return emit <= GG_EMIT_DEAM ? L : (emit == GG_EMIT_ARTP ? 2 * RL : RL); }
+
+// upper bounds over the current plan: header bytes, record bytes
+void plan_bounds(const gg_ctx* ctx, int emit, int Lmax, int* hdr_max, uint64_t* rec_max) {
+    size_t name = 1, tag = 0; uint64_t clen = 1;
+    for (size_t i = 0; i < ctx->plan.size(); i++) {
+        const gg_range& r = ctx->plan[i];
+        tag = std::max(tag, strnlen(r.tag, sizeof(r.tag) - 1));
+        if (r.genome >= 0 && r.genome < (int)ctx->genomes.size())
+            for (size_t c = 0; c < ctx->genomes[r.genome].contigs.size(); c++) {
+                name = std::max(name, ctx->genomes[r.genome].contigs[c].name.size());
+                clen = std::max(clen, ctx->genomes[r.genome].contigs[c].len);
+            }
+    }
+    const int h = 1 + (int)name + 3 + digits10(clen) + 1 + digits10(clen) + 1 + digits10((uint64_t)std::max(Lmax, 1)) + (int)tag;
+    *hdr_max = h;
+    const int S = emit_seqlen(emit, Lmax, ctx->read_len);
+    uint64_t b = 0;
+    for (int ln = 0; ln < emit_lines(emit); ln++) b += (uint64_t)h + 2 + 1 + (uint64_t)S + 1;   // +2: "_r"
+    *rec_max = b;
+}
+
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// shared-memory carve-up for F fragments per tile
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups) {
+    SmemLayout s; int o = 0;
+    s.lut = o; o += 1024;
+    o += 16;                                   // readable slack before staging
+    s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 32;
+    s.gpos = o; o += 8 * F;
+    s.meta = o; o += 4 * F;
+    s.recoff = o; o += 4 * F;
+    s.dwords = o; o += 4 * (F * max_chunks + 4);
+    s.hdr = o; o += 2 * F;
+    s.cstart = o; o += 2 * F;
+    s.gstart = o; o += 2 * F;
+    s.cmap = o; o += F * max_chunks;
+    s.gmap = o; o += F * max_groups;
+    s.total = align_up(o, 16);
+    return s;
+}
+
+} // namespace
+
+extern "C" {
+
+int gg_abi_version(void) { return GG_ABI_VERSION; }
+
+int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
+    if (!out) return GG_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return GG_ERR_CUDA; }   // no GPU: fail loudly, never fall back
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GG_ERR_CUDA; }
+    gg_ctx* ctx = new gg_ctx();
+    ctx->device = device; ctx->seed = seed; ctx->st = nullptr; ctx->ev0 = ctx->ev1 = nullptr;
+    ctx->ctab_dirty = true; ctx->n_contigs_total = 0;
+    ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false;
+    ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
+    ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
+    ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true;                  // adptSim.cpp:31
+    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { cudaGetLastError(); delete ctx; return GG_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return GG_OK;
+}
+
+int gg_ctx_destroy(gg_ctx* ctx) {
+    if (!ctx) return GG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); }
+    DBuf* bufs[] = {&ctx->d_cum_end, &ctx->d_gbase, &ctx->d_clen, &ctx->d_name_off, &ctx->d_name_len, &ctx->d_names, &ctx->d_genomes,
+                    &ctx->d_size_len, &ctx->d_size_thr, &ctx->d_adF2, &ctx->d_adS2, &ctx->d_rcS2, &ctx->d_adF, &ctx->d_adS, &ctx->d_ranges,
+                    &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
+    for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
+    for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
+        ctx->dmg[s].d_thr.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release();
+    }
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->st);
+    delete ctx;
+    return GG_OK;
+}
+
+int gg_ctx_set_seed(gg_ctx* ctx, uint64_t seed) { if (!ctx) return GG_ERR_ARG; ctx->seed = seed; return GG_OK; }
+const char* gg_last_error(gg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* gg_ctx_stream(gg_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+double gg_last_device_ms(gg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+
+// ------------------------------------------------------------------------------------------------ genome
+int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int* genome_id_out) {
+    if (!ctx || !fasta || !fai || n_chr <= 0) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_upload: bad arguments") : GG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    HostGenome H; H.d_seq2 = H.d_nmask = nullptr; H.first_contig = 0;
+    std::vector<HostContig> cs;
+    for (int i = 0; i < n_chr; i++) {
+        HostContig c; c.name = fai[i].name ? fai[i].name : "";
+        if (fai[i].len <= 0 || fai[i].line_blen <= 0 || fai[i].line_len < fai[i].line_blen) return ctx->fail(GG_ERR_ARG, "gg_genome_upload: bad .fai entry for " + c.name);
+        if ((uint64_t)fai[i].len > 0xFFFFFFFFull) return ctx->fail(GG_ERR_ARG, "gg_genome_upload: contig longer than 2^32-1 bases: " + c.name);
+        if (c.name.size() > 4096) return ctx->fail(GG_ERR_ARG, "gg_genome_upload: contig name too long");
+        c.len = (uint64_t)fai[i].len; c.offset = fai[i].offset; c.blen = fai[i].line_blen; c.llen = fai[i].line_len; c.fai_index = i;
+        c.gbase = c.cum_end = 0;
+        cs.push_back(c);
+    }
+    // std::map<string,...>::insert keeps the first of duplicate names and iterates in lexicographic order (fragSim.cpp:215,266,1152)
+    std::stable_sort(cs.begin(), cs.end(), [](const HostContig& a, const HostContig& b) { return a.name < b.name; });
+    H.fai2sorted.assign(n_chr, -1);
+    uint64_t G = 0, gb = 64;                 // 64 guard bases so that reverse-strand windows never index below 0
+    for (size_t i = 0; i < cs.size(); i++) {
+        if (i && cs[i].name == cs[i - 1].name) continue;
+        HostContig c = cs[i];
+        G += c.len; c.cum_end = G; c.gbase = gb; gb += (c.len + 63) / 64 * 64;
+        H.fai2sorted[c.fai_index] = (int)H.contigs.size();
+        H.contigs.push_back(c);
+    }
+    H.G = G; H.n_units = gb / 32 + 2;
+    // device: raw FASTA (temporary), contig descriptors (temporary), packed arrays (resident)
+    const size_t nc = H.contigs.size();
+    std::vector<uint64_t> off(nc), gbase(nc); std::vector<uint32_t> len(nc); std::vector<int32_t> blen(nc), llen(nc);
+    for (size_t i = 0; i < nc; i++) { off[i] = H.contigs[i].offset; gbase[i] = H.contigs[i].gbase; len[i] = (uint32_t)H.contigs[i].len; blen[i] = H.contigs[i].blen; llen[i] = H.contigs[i].llen; }
+    uint8_t* d_fa = nullptr; uint64_t* d_off = nullptr; uint64_t* d_gb = nullptr; uint32_t* d_len = nullptr; int32_t* d_bl = nullptr; int32_t* d_ll = nullptr;
+    cudaError_t e = cudaSuccess;
+#define TRY(x) if (e == cudaSuccess) e = (x)
+    TRY(cudaMalloc(&d_fa, n + 16));
+    TRY(cudaMalloc(&d_off, nc * 8)); TRY(cudaMalloc(&d_gb, nc * 8)); TRY(cudaMalloc(&d_len, nc * 4)); TRY(cudaMalloc(&d_bl, nc * 4)); TRY(cudaMalloc(&d_ll, nc * 4));
+    TRY(cudaMalloc(&H.d_seq2, (H.n_units * 2 + 4) * 4)); TRY(cudaMalloc(&H.d_nmask, (H.n_units + 4) * 4));
+    TRY(cudaMemsetAsync(H.d_seq2, 0, (H.n_units * 2 + 4) * 4, ctx->st)); TRY(cudaMemsetAsync(H.d_nmask, 0xFF, (H.n_units + 4) * 4, ctx->st));
+    TRY(cudaMemcpyAsync(d_fa, fasta, n, cudaMemcpyHostToDevice, ctx->st));
+    TRY(cudaMemcpyAsync(d_off, off.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
+    TRY(cudaMemcpyAsync(d_gb, gbase.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
+    TRY(cudaMemcpyAsync(d_len, len.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
+    TRY(cudaMemcpyAsync(d_bl, blen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
+    TRY(cudaMemcpyAsync(d_ll, llen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
+    TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, nullptr, (int)nc, H.n_units, H.d_seq2, H.d_nmask, ctx->st));
+    TRY(cudaStreamSynchronize(ctx->st));
+#undef TRY
+    cudaFree(d_fa); cudaFree(d_off); cudaFree(d_gb); cudaFree(d_len); cudaFree(d_bl); cudaFree(d_ll);
+    if (e != cudaSuccess) { cudaFree(H.d_seq2); cudaFree(H.d_nmask); return ctx->cuda_fail(e, "gg_genome_upload"); }
+    ctx->genomes.push_back(H);
+    ctx->ctab_dirty = true;
+    if (genome_id_out) *genome_id_out = (int)ctx->genomes.size() - 1;
+    return GG_OK;
+}
+int gg_genome_count(gg_ctx* ctx) { return ctx ? (int)ctx->genomes.size() : 0; }
+
+int gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len, char* dst) {
+    if (!ctx || genome_id < 0 || genome_id >= (int)ctx->genomes.size() || !dst || len < 0) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_fetch: bad arguments") : GG_ERR_ARG;
+    const HostGenome& H = ctx->genomes[genome_id];
+    if (chr < 0 || chr >= (int)H.fai2sorted.size() || H.fai2sorted[chr] < 0) return ctx->fail(GG_ERR_ARG, "gg_genome_fetch: bad contig");
+    const HostContig& c = H.contigs[H.fai2sorted[chr]];
+    if (start < 0 || (uint64_t)start + (uint64_t)len > c.len) return ctx->fail(GG_ERR_ARG, "gg_genome_fetch: range outside contig");
+    if (len == 0) return GG_OK;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t b0 = c.gbase + (uint64_t)start, b1 = b0 + (uint64_t)len - 1;
+    const uint64_t w0 = b0 >> 4, w1 = b1 >> 4, m0 = b0 >> 5, m1 = b1 >> 5;
+    std::vector<uint32_t> w(w1 - w0 + 1), m(m1 - m0 + 1);
+    CK(cudaMemcpyAsync(w.data(), H.d_seq2 + w0, w.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(m.data(), H.d_nmask + m0, m.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i < len; i++) {
+        const uint64_t b = b0 + (uint64_t)i;
+        const bool bad = (m[(b >> 5) - m0] >> (b & 31)) & 1u;
+        dst[i] = bad ? 'N' : "ACGT"[(w[(b >> 4) - w0] >> (2 * (b & 15))) & 3u];
+    }
+    return GG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+int gg_tables_set_sizes(gg_ctx* ctx, int mode, const int32_t* len, const double* cum, int n, int fixed_len, int minlen, int maxlen) {
+    if (!ctx) return GG_ERR_ARG;
+    if (mode != GG_SIZE_FIXED && mode != GG_SIZE_LIST && mode != GG_SIZE_FREQ) return ctx->fail(GG_ERR_ARG, "gg_tables_set_sizes: unknown mode");
+    if (mode != GG_SIZE_FIXED && (n <= 0 || !len || (mode == GG_SIZE_FREQ && !cum))) return ctx->fail(GG_ERR_ARG, "gg_tables_set_sizes: empty size table");
+    CK(cudaSetDevice(ctx->device));
+    ctx->size_mode = mode; ctx->fixed_len = fixed_len; ctx->minlen = minlen; ctx->maxlen = maxlen;
+    ctx->size_len.clear(); ctx->size_thr.clear();
+    if (mode != GG_SIZE_FIXED) {
+        ctx->size_len.assign(len, len + n);
+        if (mode == GG_SIZE_FREQ) {
+            ctx->size_thr.resize(n);
+            uint32_t prev = 0;
+            for (int i = 0; i < n; i++) {      // p <= cProb[i], fragSim.cpp:163-165; a non-increasing cum entry can never be the first match
+                uint32_t t = thr_le(cum[i]); if (t < prev) t = prev; ctx->size_thr[i] = t; prev = t;
+            }
+        }
+    }
+    if (max_frag_len(ctx) > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_tables_set_sizes: fragment lengths above 4095 are not supported");
+    int rc;
+    if ((rc = upload_vec(ctx, ctx->d_size_len, ctx->size_len))) return rc;
+    if ((rc = upload_vec(ctx, ctx->d_size_thr, ctx->size_thr))) return rc;
+    ctx->sizes_set = true;
+    return GG_OK;
+}
+int gg_tables_set_norev(gg_ctx* ctx, int norev) { if (!ctx) return GG_ERR_ARG; ctx->norev = norev ? 1 : 0; return GG_OK; }
+
+static int check_rates(gg_ctx* ctx, const double* sub, int rows, const char* what) {
+    for (int r = 0; r < rows; r++)
+        for (int b = 0; b < 4; b++) {
+            double sum = 0.0;
+            for (int a = 0; a < 3; a++) {
+                const double v = sub[(size_t)r * 12 + b * 3 + a];
+                if (!(v >= 0.0)) return ctx->fail(GG_ERR_ARG, std::string(what) + ": negative or NaN substitution rate");
+                sum += v;
+            }
+            if (sum > 1.0) return ctx->fail(GG_ERR_ARG, std::string(what) + ": the sum of the substitution probabilities exceeds 1");   // deamSim.cpp:1154-1157
+        }
+    return GG_OK;
+}
+
+int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, const double* sub3, int rows3, int clamp_last) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || !sub5 || !sub3 || rows5 <= 0 || rows3 <= 0) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: bad arguments");
+    int rc;
+    if ((rc = check_rates(ctx, sub5, rows5, "gg_tables_set_matrix"))) return rc;
+    if ((rc = check_rates(ctx, sub3, rows3, "gg_tables_set_matrix"))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    HostDamage& H = ctx->dmg[slot];
+    H.mode = GG_DMG_MATRIX; H.rows5 = rows5; H.rows3 = rows3; H.clamp_last = clamp_last ? 1 : 0;
+    H.thr.assign((size_t)(rows5 + rows3) * 4, make_uint4(0, 0, 0, 0));
+    for (int r = 0; r < rows5 + rows3; r++) {
+        const double* row = r < rows5 ? sub5 + (size_t)r * 12 : sub3 + (size_t)(r - rows5) * 12;
+        for (int b = 0; b < 4; b++) {
+            // cumulative table exactly as deamSim.cpp:1797-1837 builds it (same operation order, fp64)
+            double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
+            double sum = 0.0;
+            for (int a = 0; a < 4; a++) {
+                if (a == b) continue;
+                const int idx = a < b ? b * 3 + a : b * 3 + (a - 1);
+                sum += row[idx]; _sumProb[a + 1] = row[idx];
+            }
+            _sumProb[b + 1] = 1.0 - sum;
+            double s = 0;
+            for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }
+            uint32_t k[4], prev = 0;
+            for (int a = 0; a < 4; a++) { uint32_t t = thr_le(sumProb[a + 1]); if (t < prev) t = prev; k[a] = t; prev = t; }
+            H.thr[(size_t)r * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
+        }
+    }
+    return upload_vec(ctx, H.d_thr, H.thr);
+}
+
+int gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const double* sub5, int rows5, const double* sub3, int rows3) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || !sub5 || !sub3 || rows5 <= 0 || rows3 <= 0 ||
+        (protocol != GG_DMG_SINGLE && protocol != GG_DMG_DOUBLE)) return ctx->fail(GG_ERR_ARG, "gg_tables_set_singledouble: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    HostDamage& H = ctx->dmg[slot];
+    H.mode = protocol; H.rows5 = rows5; H.rows3 = rows3; H.clamp_last = 1;
+    H.sd5.resize(rows5); H.sd3.resize(rows3);
+    for (int r = 0; r < rows5; r++) H.sd5[r] = thr_lt(sub5[(size_t)r * 12 + 5]);                                      // C->T, deamSim.cpp:1948
+    for (int r = 0; r < rows3; r++) H.sd3[r] = thr_lt(sub3[(size_t)r * 12 + (protocol == GG_DMG_SINGLE ? 5 : 6)]);    // deamSim.cpp:1961 / :1993
+    int rc;
+    if ((rc = upload_vec(ctx, H.d_sd5, H.sd5))) return rc;
+    return upload_vec(ctx, H.d_sd3, H.sd3);
+}
+
+int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, double s) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_tables_set_briggs: bad slot");
+    if (!(v >= 0 && v <= 1)) return ctx->fail(GG_ERR_ARG, "Nick frequency must be between 0 and 1");                          // deamSim.cpp:298-301
+    if (!(l >= 0 && l <= 1)) return ctx->fail(GG_ERR_ARG, "Geometric parameter for overhang must be between 0 and 1");
+    if (!(d >= 0 && d <= 1)) return ctx->fail(GG_ERR_ARG, "double-strand deamination prob. must be between 0 and 1");
+    if (!(s >= 0 && s <= 1)) return ctx->fail(GG_ERR_ARG, "single-strand deamination prob. must be between 0 and 1");
+    CK(cudaSetDevice(ctx->device));
+    HostDamage& H = ctx->dmg[slot];
+    H.mode = GG_DMG_BRIGGS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
+    H.Ks = thr_lt(s); H.Kd = thr_lt(d);
+    H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
+    // inverse-CDF tables of geometric_distribution<int>(p): CDF(k) = 1-(1-p)^(k+1) as a running product (deamSim.cpp:297,1478-1479,1503-1507)
+    double q = 1.0; uint32_t prev = 0;
+    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoL[k] = t; prev = t; }
+    q = 1.0; prev = 0;
+    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - v); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoV[k] = t; prev = t; }
+    int rc;
+    if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
+    return upload_vec(ctx, H.d_geoV, H.geoV);
+}
+int gg_tables_clear_damage(gg_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
+    ctx->dmg[slot].mode = GG_DMG_NONE; return GG_OK;
+}
+int gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int read_len) {
+    if (!ctx || !fwd || !rev) return ctx ? ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: bad arguments") : GG_ERR_ARG;
+    if (read_len < 1 || read_len > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: read length must be in [1,4095]");
+    std::string f(fwd), s(rev);
+    for (size_t i = 0; i < f.size(); i++) if (!strchr("ACGT", f[i])) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be upper-case ACGT");
+    for (size_t i = 0; i < s.size(); i++) if (!strchr("ACGT", s[i])) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be upper-case ACGT");
+    ctx->adF = f; ctx->adS = s; ctx->read_len = read_len; ctx->ad_dirty = true;
+    return GG_OK;
+}
+
+int gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n) {
+    if (!ctx || n < 0 || (n > 0 && !ranges)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_plan_set: bad arguments") : GG_ERR_ARG;
+    uint64_t next = n ? ranges[0].first_id : 0;
+    for (int i = 0; i < n; i++) {
+        if (ranges[i].first_id != next) return ctx->fail(GG_ERR_ARG, "gg_plan_set: ranges must be contiguous and ascending in fragment id");
+        if (ranges[i].genome < 0 || ranges[i].genome >= (int)ctx->genomes.size()) return ctx->fail(GG_ERR_ARG, "gg_plan_set: unknown genome id");
+        if (ranges[i].damage_slot < -1 || ranges[i].damage_slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad damage slot");
+        if (ranges[i].count == 0) return ctx->fail(GG_ERR_ARG, "gg_plan_set: empty range");
+        next += ranges[i].count;
+    }
+    ctx->plan.assign(ranges, ranges + n);
+    ctx->plan_dirty = true;
+    return GG_OK;
+}
+
+uint64_t gg_max_record_bytes(gg_ctx* ctx, int emit) {
+    if (!ctx || emit < GG_EMIT_FRAG || emit > GG_EMIT_RR) return 0;
+    int h; uint64_t r; plan_bounds(ctx, emit, max_frag_len(ctx), &h, &r); return r;
+}
+
+// ------------------------------------------------------------------------------------------------ fused run
+int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* out) {
+    if (!ctx || !out) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_fused: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (emit < GG_EMIT_FRAG || emit > GG_EMIT_RR) return ctx->fail(GG_ERR_ARG, "gg_run_fused: unknown emit mode");
+    if (ctx->plan.empty() || ctx->genomes.empty()) return ctx->fail(GG_ERR_STATE, "gg_run_fused: no plan / genome");
+    const uint64_t p0 = ctx->plan.front().first_id, p1 = ctx->plan.back().first_id + ctx->plan.back().count;
+    if (first < p0 || first + count > p1) return ctx->fail(GG_ERR_ARG, "gg_run_fused: fragment ids outside the plan");
+    for (size_t i = 0; i < ctx->plan.size(); i++) {
+        const int s = ctx->plan[i].damage_slot;
+        if (emit != GG_EMIT_FRAG && s >= 0 && ctx->dmg[s].mode == GG_DMG_NONE) return ctx->fail(GG_ERR_STATE, "gg_run_fused: plan references an unset damage slot");
+        if (ctx->genomes[ctx->plan[i].genome].G < 2) return ctx->fail(GG_ERR_ARG, "gg_run_fused: genome too small");
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_contig_tables(ctx)) || (rc = sync_adapters(ctx)) || (rc = sync_plan(ctx))) return rc;
+    if (count == 0) { out->dev_ptr = ctx->d_out.p; ctx->last_ms = 0; return GG_OK; }
+
+    const int Lmax = max_frag_len(ctx);
+    if (Lmax <= 0 || Lmax > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_run_fused: no admissible fragment length (check -l/-s/-f against -m/-M)");
+    int hdr_max; uint64_t rec_max; plan_bounds(ctx, emit, Lmax, &hdr_max, &rec_max);
+    const int Smax = emit_seqlen(emit, Lmax, ctx->read_len);
+    const int max_chunks = (Lmax + 15) / 16, max_groups = emit_lines(emit) * ((Smax + 15) / 16 + 1);
+
+    // fragments per tile: the largest F <= 256 whose tile fits the shared memory of `ctas` co-resident CTAs
+    const size_t sm_budget = 227 * 1024;
+    int F = 0, ctas = 0;
+    const char* envF = getenv("GG_FUSED_F"); const char* envC = getenv("GG_FUSED_CTAS");
+    for (int t = envC ? atoi(envC) : 3; t >= 1 && F == 0; t--) {
+        const size_t per_cta = std::min(sm_budget / (size_t)t - 1024, ctx->smem_optin);
+        int f = envF ? atoi(envF) : FUSED_THREADS;
+        f = std::max(1, std::min(f, FUSED_THREADS));
+        while (f >= 1 && (size_t)make_layout(f, rec_max, max_chunks, max_groups).total > per_cta) f = (f > 32) ? f - 16 : f - 1;
+        if (f >= (t > 1 ? 128 : 1)) { F = f; ctas = t; }
+    }
+    if (F < 1) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
+    while ((uint64_t)F * (uint64_t)max_chunks > 60000ull || (uint64_t)F * (uint64_t)max_groups > 60000ull) F--;
+    const SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups);
+    const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
+    if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
+    const int n_tiles = (int)n_tiles64;
+
+    const uint64_t out_cap = count * rec_max + 64;
+    CK(ctx->d_out.ensure(out_cap));
+    CK(ctx->d_tile_state.ensure((size_t)n_tiles * 8));
+    CK(ctx->d_ticket_stats.ensure(256));
+
+    FusedParams P; memset(&P, 0, sizeof P);
+    P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev;
+    P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
+    P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
+    P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();
+    P.ctab.cum_end = ctx->d_cum_end.as<uint64_t>(); P.ctab.gbase = ctx->d_gbase.as<uint64_t>(); P.ctab.len = ctx->d_clen.as<uint32_t>();
+    P.ctab.name_off = ctx->d_name_off.as<uint32_t>(); P.ctab.name_len = ctx->d_name_len.as<uint16_t>(); P.ctab.names = ctx->d_names.as<char>();
+    P.size_mode = ctx->size_mode; P.fixed_len = ctx->fixed_len; P.minlen = ctx->minlen; P.maxlen = ctx->maxlen; P.n_sizes = (int)ctx->size_len.size();
+    P.size_thr = ctx->d_size_thr.as<uint32_t>(); P.size_len = ctx->d_size_len.as<int32_t>();
+    for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
+    P.ad.adF2 = ctx->d_adF2.as<uint32_t>(); P.ad.adS2 = ctx->d_adS2.as<uint32_t>(); P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>();
+    P.ad.lenF = (int)ctx->adF.size(); P.ad.lenS = (int)ctx->adS.size(); P.ad.read_len = ctx->read_len;
+    P.out = ctx->d_out.as<uint8_t>(); P.out_cap = out_cap;
+    P.tile_state = ctx->d_tile_state.as<unsigned long long>();
+    P.ticket = ctx->d_ticket_stats.as<unsigned int>();
+    P.stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
+    P.sm = sm;
+
+    int bps = 0;
+    CK(fused_occupancy(sm.total, &bps));
+    if (bps < 1) return ctx->fail(GG_ERR_CUDA, "gg_run_fused: kernel does not fit on an SM");
+    bps = std::min(bps, std::max(ctas, 1));
+    const int grid = (int)std::min<uint64_t>((uint64_t)n_tiles, (uint64_t)bps * (uint64_t)ctx->sm_count);
+
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles * 8, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
+    CK(launch_fused(P, grid, ctx->st));
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    unsigned long long stats[ST_N];
+    CK(cudaMemcpyAsync(stats, P.stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    out->dev_ptr = ctx->d_out.p; out->bytes = stats[ST_TOTAL]; out->records = count;
+    out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = 1;
+    if (stats[ST_ERR] & ERRF_GIVEUP) return ctx->fail(GG_ERR_GIVEUP, "gg_run_fused: a fragment exhausted its sampling attempts (genome without an admissible window?)");
+    if (stats[ST_ERR] & ERRF_OVERFLOW) return ctx->fail(GG_ERR_CAPACITY, "gg_run_fused: internal staging/output overflow");
+    return GG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone stages
+namespace {
+// stand-alone stages may be chained on the device (input = a previous run's output): write to the other slab
+DBuf& pick_out(gg_ctx* ctx, const void* input) {
+    const uint8_t* in = (const uint8_t*)input; const uint8_t* o = ctx->d_out.as<uint8_t>();
+    return (o && in >= o && in < o + ctx->d_out.cap) ? ctx->d_out2 : ctx->d_out;
+}
+// newline index of a device-resident record stream; returns n_rec and the RecStream
+int index_records(gg_ctx* ctx, const uint8_t* d_in, size_t n, RecStream* R, int* launches) {
+    R->in = d_in; R->n = n; R->nl = nullptr; R->n_nl = 0; R->n_rec = 0;
+    if (n == 0) return GG_OK;
+    const int nb = (int)((n + NL_BLOCK_BYTES - 1) / NL_BLOCK_BYTES);
+    CK(ctx->d_scan.ensure(((size_t)nb + (nb + 2047) / 2048 + 16) * 8));
+    unsigned long long* counts = ctx->d_scan.as<unsigned long long>();
+    unsigned long long* scratch = counts + nb;
+    unsigned long long* total = scratch + (nb + 2047) / 2048 + 1;
+    CK(launch_count_newlines(d_in, n, counts, nb, ctx->st));
+    CK(launch_exclusive_scan(counts, (uint64_t)nb, scratch, total, ctx->st));
+    unsigned long long h_total = 0; uint8_t last = 0;
+    CK(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&last, d_in + n - 1, 1, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx->d_nl.ensure((size_t)(h_total + 2) * 8));
+    CK(launch_fill_newlines(d_in, n, counts, ctx->d_nl.as<uint64_t>(), nb, ctx->st));
+    *launches += 5;
+    const uint64_t n_lines = h_total + (last != '\n' ? 1 : 0);
+    if (n_lines & 1) return ctx->fail(GG_ERR_PARSE, "record stream has an odd number of lines (expected ID line + sequence line per record)");
+    R->nl = ctx->d_nl.as<uint64_t>(); R->n_nl = h_total; R->n_rec = n_lines / 2;
+    return GG_OK;
+}
+}
+
+int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, gg_out* out) {
+    if (!ctx || !out || (n && !recs_dev)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_deam: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (slot < -1 || slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_run_deam: bad damage slot");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_ticket_stats.ensure(256));
+    unsigned long long* d_stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
+    RecStream R; int launches = 0;
+    int rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches);
+    if (rc) return rc;
+    const uint64_t out_bytes = n ? (R.n_nl == 2 * R.n_rec ? n : n + 1) : 0;
+    DBuf& ob = pick_out(ctx, recs_dev);
+    CK(ob.ensure(out_bytes + 64));
+    ggd::DamageDev D; memset(&D, 0, sizeof D);
+    const int has = (slot >= 0 && ctx->dmg[slot].mode != GG_DMG_NONE) ? 1 : 0;
+    if (has) fill_damage_dev(ctx->dmg[slot], &D);
+    ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
+    CK(launch_deam_records(R, ob.as<uint8_t>(), D, has, key, first_id, d_stats, ctx->st));
+    launches += 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    unsigned long long stats[ST_N];
+    CK(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    out->dev_ptr = ob.p; out->bytes = out_bytes; out->records = R.n_rec; out->in_bytes = n; out->device_ms = ms; out->launches = launches;
+    if (stats[ST_ERR] & ERRF_PARSE) return ctx->fail(GG_ERR_PARSE, "gg_run_deam: a record does not start with '>'");
+    return GG_OK;
+}
+
+int gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, gg_out* out) {
+    if (!ctx || !out || (n && !recs_dev)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_adpt: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (emit < GG_EMIT_STDOUT4 || emit > GG_EMIT_RR) return ctx->fail(GG_ERR_ARG, "gg_run_adpt: emit mode must be an adptSim dialect");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_adapters(ctx))) return rc;
+    CK(ctx->d_ticket_stats.ensure(256));
+    unsigned long long* d_stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
+    RecStream R; int launches = 0;
+    if ((rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches))) return rc;
+    unsigned long long h_total = 0;
+    DBuf& ob = pick_out(ctx, recs_dev);
+    if (R.n_rec) {
+        const uint64_t nb = (R.n_rec + 2047) / 2048;
+        CK(ctx->d_sizes.ensure((size_t)(R.n_rec + nb + 16) * 8));
+        unsigned long long* sizes = ctx->d_sizes.as<unsigned long long>();
+        unsigned long long* scratch = sizes + R.n_rec;
+        unsigned long long* total = scratch + nb + 1;
+        CK(launch_adpt_sizes(R, emit, ctx->read_len, sizes, d_stats, ctx->st));
+        CK(launch_exclusive_scan(sizes, R.n_rec, scratch, total, ctx->st));
+        CK(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(ob.ensure(h_total + 64));
+        Adapters ad; memset(&ad, 0, sizeof ad);
+        ad.lenF = (int)ctx->adF.size(); ad.lenS = (int)ctx->adS.size(); ad.read_len = ctx->read_len;
+        ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
+        CK(launch_adpt_records(R, sizes, ob.as<uint8_t>(), emit, ad, ctx->d_adF.as<uint8_t>(), ctx->d_adS.as<uint8_t>(), key, first_id, ctx->st));
+        launches += 5;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    unsigned long long stats[ST_N];
+    CK(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    out->dev_ptr = ob.p; out->bytes = h_total; out->records = R.n_rec; out->in_bytes = n; out->device_ms = ms; out->launches = launches;
+    if (stats[ST_ERR] & ERRF_PARSE) return ctx->fail(GG_ERR_PARSE, "gg_run_adpt: a record does not start with '>'");
+    return GG_OK;
+}
+
+static int upload_input(gg_ctx* ctx, const uint8_t* recs, size_t n) {
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_in.ensure(n + 64));
+    if (n) CK(cudaMemcpyAsync(ctx->d_in.p, recs, n, cudaMemcpyHostToDevice, ctx->st));
+    return GG_OK;
+}
+int gg_run_deam(gg_ctx* ctx, const uint8_t* recs, size_t n, int slot, uint64_t first_id, gg_out* out) {
+    if (!ctx || (n && !recs)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_deam: bad arguments") : GG_ERR_ARG;
+    int rc = upload_input(ctx, recs, n); if (rc) return rc;
+    return gg_run_deam_dev(ctx, ctx->d_in.p, n, slot, first_id, out);
+}
+int gg_run_adpt(gg_ctx* ctx, const uint8_t* recs, size_t n, int emit, uint64_t first_id, gg_out* out) {
+    if (!ctx || (n && !recs)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_adpt: bad arguments") : GG_ERR_ARG;
+    int rc = upload_input(ctx, recs, n); if (rc) return rc;
+    return gg_run_adpt_dev(ctx, ctx->d_in.p, n, emit, first_id, out);
+}
+
+int gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n) {
+    if (!ctx || !out || (!host_dst && out->bytes)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_out_fetch: bad arguments") : GG_ERR_ARG;
+    if (n) *n = (size_t)out->bytes;
+    if (out->bytes > cap) return ctx->fail(GG_ERR_CAPACITY, "gg_out_fetch: destination too small");
+    if (out->bytes == 0) return GG_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host_dst, out->dev_ptr, out->bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GG_OK;
+}
+
+int gg_flush_l2(gg_ctx* ctx) {
+    if (!ctx) return GG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = 256ull << 20;          // > 126 MB L2
+    CK(ctx->d_flush.ensure(bytes));
+    CK(launch_l2_flush(ctx->d_flush.as<uint4>(), bytes / 16, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return GG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,139 @@
+// gg_device.cuh -- device-side building blocks shared by the sm_100a kernels:
+// Philox4x32-10 counter RNG, 2-bit genome access, per-base damage models.
+// Draw layout and threshold semantics: DESIGN.md "Draw specification".
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace ggd {
+
+// stream ids (Philox counter word 3)
+enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4 };
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+struct Key { uint32_t k0, k1; };
+__device__ __forceinline__ uint4 rng_block(const Key& k, uint64_t id, uint32_t blk, uint32_t stream) {
+    return philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), blk, stream, k.k0, k.k1);
+}
+__device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+__device__ __forceinline__ uint32_t rng_word(const Key& k, uint64_t id, uint32_t stream, uint32_t w) {
+    return pick(rng_block(k, id, w >> 2, stream), (int)(w & 3));
+}
+
+// ---------------------------------------------------------------- 2-bit sequence helpers (A=0 C=1 G=2 T=3; 16 bases per u32, base k at bits 2k)
+// 16 bases starting at base index `pos` of a packed array (reads words pos/16 and pos/16+1)
+__device__ __forceinline__ uint32_t fetch16(const uint32_t* __restrict__ w, int64_t pos) {
+    const int64_t wi = pos >> 4;
+    const uint32_t sh = ((uint32_t)pos & 15u) * 2u;
+    return __funnelshift_r(__ldg(w + wi), __ldg(w + wi + 1), sh);
+}
+__device__ __forceinline__ uint32_t fetch16_smem(const uint32_t* w, int pos) {
+    const int wi = pos >> 4;
+    const uint32_t sh = ((uint32_t)pos & 15u) * 2u;
+    return __funnelshift_r(w[wi], w[wi + 1], sh);
+}
+// reverse the order of the sixteen 2-bit fields and complement each (A<->T, C<->G is 3-v == ~v)
+__device__ __forceinline__ uint32_t revcomp16(uint32_t x) {
+    uint32_t y = __brev(x);
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    return ~y;
+}
+// mask with the low n 2-bit fields set, n in [0,16]
+__device__ __forceinline__ uint32_t lowfields(int n) { return n >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u); }
+
+// ---------------------------------------------------------------- damage model tables (device view)
+struct DamageDev {
+    int mode;            // gg_damage_mode
+    int rows5, rows3;    // matrix / single-double rows
+    int clamp_last;      // matrix: clamp to last row (default) or skip (-last)
+    // MATRIX: thr[(r*4+b)] = {K1,K2,K3,K4}: new base = first a with u31 < K[a+1], else unchanged; rows5 entries then rows3
+    const uint4* thr;
+    // SINGLE/DOUBLE: sd5[r] (C->T 5'), sd3[r] (C->T single / G->A double)
+    const uint32_t* sd5; const uint32_t* sd3;
+    // BRIGGS: Ks,Kd strict thresholds (u31 < K); geometric tables (u31 < cdf_thr[k] first k) of n_geo entries
+    uint32_t Ks, Kd; const uint32_t* geoL; const uint32_t* geoV; int n_geo;
+};
+
+// first k with u < thr[k], thr ascending; returns n if none
+__device__ __forceinline__ int first_below(const uint32_t* __restrict__ thr, int n, uint32_t u) {
+    int lo = 0, hi = n;            // invariant: answer in [lo,hi]
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(thr + mid)) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// -matfile, one base (deamSim.cpp:1794-1930): i = position, L = fragment length, b = code, x = raw Philox word
+__device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x) {
+    int r;
+    if (i < (L >> 1)) {
+        r = i;
+        if (r >= D.rows5) { if (!D.clamp_last) return b; r = D.rows5 - 1; }
+    } else {
+        r = L - 1 - i;
+        if (r >= D.rows3) { if (!D.clamp_last) return b; r = D.rows3 - 1; }
+        r += D.rows5;
+    }
+    const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
+    const uint32_t u = x >> 1;
+    return u < T.x ? 0u : u < T.y ? 1u : u < T.z ? 2u : u < T.w ? 3u : b;
+}
+// Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
+struct BriggsHdr { int o5, o3, nick; };
+__device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const uint4& h) {
+    BriggsHdr B;
+    B.o5 = first_below(D.geoL, D.n_geo, h.x >> 1);
+    B.o3 = first_below(D.geoL, D.n_geo, h.y >> 1);
+    B.nick = first_below(D.geoV, D.n_geo, h.z >> 1);
+    return B;
+}
+// -damage, one base (deamSim.cpp:1483-1594)
+__device__ __forceinline__ uint32_t dmg_briggs_base(const DamageDev& D, const BriggsHdr& B, int i, int L, uint32_t b, uint32_t x) {
+    const uint32_t u = x >> 1;
+    if (B.o5 + B.o3 >= L) return (b == 1u && u < D.Ks) ? 3u : b;          // all single-stranded: C->T at s
+    if (i + 1 <= B.o5)    return (b == 1u && u < D.Ks) ? 3u : b;          // 5' overhang: C->T at s
+    if (L - i <= B.o3)    return (b == 2u && u < D.Ks) ? 0u : b;          // 3' overhang: G->A at s
+    if (B.nick <= i)      return (b == 2u && u < D.Kd) ? 0u : b;          // after the nick: G->A at d
+    return (b == 1u && u < D.Kd) ? 3u : b;                                 // before the nick: C->T at d
+}
+// -mat single|double / -mapdamage, one base, both passes (deamSim.cpp:1941-2002); x1 pass-1 word, x2 pass-2 word
+__device__ __forceinline__ uint32_t dmg_sd_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x1, uint32_t x2) {
+    const int r5 = min(i, D.rows5 - 1), r3 = min(L - 1 - i, D.rows3 - 1);
+    if (b == 1u && (x1 >> 1) < __ldg(D.sd5 + r5)) b = 3u;                  // pass 1: C->T by 5' row
+    if (D.mode == 3 /*SINGLE*/) { if (b == 1u && (x2 >> 1) < __ldg(D.sd3 + r3)) b = 3u; }
+    else                        { if (b == 2u && (x2 >> 1) < __ldg(D.sd3 + r3)) b = 0u; }
+    return b;
+}
+
+// ASCII <-> code
+__device__ __forceinline__ int ascii2code(uint8_t c) {   // upper-case input; -1 = unresolved
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+}
+__device__ __forceinline__ uint8_t code2ascii(uint32_t b) { return (uint8_t)(0x54474341u >> (8 * b)); }
+__device__ __forceinline__ uint8_t upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+__device__ __forceinline__ uint8_t complement_ascii(uint8_t c) {
+    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+}
+
+// decimal digits
+// (coordinates are < 2^33: contig lengths are u32 and fragment lengths <= 4095)
+__device__ __forceinline__ int ndigits(uint64_t v) {
+    return 1 + (v >= 10ull) + (v >= 100ull) + (v >= 1000ull) + (v >= 10000ull) + (v >= 100000ull) +
+           (v >= 1000000ull) + (v >= 10000000ull) + (v >= 100000000ull) + (v >= 1000000000ull) +
+           (v >= 10000000000ull);
+}
+
+} // namespace ggd

@@ -1,0 +1,411 @@
+// gg_host.cpp -- file-format layer + fragment apportioning (host, C++11, no CUDA).
+#include "gg_host.h"
+#include <zlib.h>
+#include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <math.h>
+#include <errno.h>
+#include <algorithm>
+#include <map>
+
+namespace ggh {
+
+bool read_file(const std::string& path, std::vector<uint8_t>& out, std::string& err) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) { err = "Unable to open file " + path; return false; }
+    gzbuffer(f, 1 << 20);
+    out.clear();
+    std::vector<uint8_t> buf(1 << 22);
+    while (true) {
+        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n < 0) { err = "Read error in " + path; gzclose(f); return false; }
+        if (n == 0) break;
+        out.insert(out.end(), buf.begin(), buf.begin() + n);
+    }
+    gzclose(f);
+    return true;
+}
+
+std::vector<std::string> all_tokens(const std::string& s, char delim) {
+    std::vector<std::string> out; std::string cur;
+    for (size_t i = 0; i < s.size(); i++) { if (s[i] == delim) { out.push_back(cur); cur.clear(); } else cur += s[i]; }
+    out.push_back(cur);
+    return out;
+}
+
+static void split_lines(const std::vector<uint8_t>& b, std::vector<std::string>& lines) {
+    size_t p = 0;
+    while (p < b.size()) {
+        const uint8_t* e = (const uint8_t*)memchr(b.data() + p, '\n', b.size() - p);
+        size_t le = e ? (size_t)(e - b.data()) : b.size();
+        lines.push_back(std::string((const char*)b.data() + p, le - p));
+        p = le + 1;
+    }
+}
+// destringify<T> of the reference = operator>> on an istringstream: leading blanks skipped, trailing junk ignored
+static bool to_double(const std::string& s, double* v) { char* e; errno = 0; *v = strtod(s.c_str(), &e); return e != s.c_str(); }
+static bool to_i64(const std::string& s, long long* v) { char* e; errno = 0; *v = strtoll(s.c_str(), &e, 10); return e != s.c_str(); }
+
+bool parse_fai(const std::string& path, std::vector<FaiEntry>& out, std::string& err) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = "Cannot open faidx: " + path; return false; }
+    std::vector<std::string> lines; split_lines(b, lines);
+    out.clear();
+    for (size_t i = 0; i < lines.size(); i++) {
+        const std::string& line = lines[i];
+        if (line.empty()) continue;                                   // fragSim.cpp:239
+        if (line.find('\t') == std::string::npos) continue;           // fragSim.cpp:243
+        std::vector<std::string> t = all_tokens(line, '\t');
+        if (t.size() != 5) { err = "Parse error in " + line; return false; }   // fragSim.cpp:250-253
+        FaiEntry e; long long a, o, bl, ll;
+        if (!to_i64(t[1], &a) || !to_i64(t[2], &o) || !to_i64(t[3], &bl) || !to_i64(t[4], &ll)) { err = "Parse error in " + line; return false; }
+        e.name = t[0]; e.len = a; e.offset = (uint64_t)o; e.line_blen = (int32_t)bl; e.line_len = (int32_t)ll;
+        out.push_back(e);
+    }
+    if (out.empty()) { err = "Empty faidx: " + path; return false; }
+    return true;
+}
+
+bool build_fai(const std::vector<uint8_t>& fa, std::vector<FaiEntry>& out, std::string& err) {
+    out.clear();
+    size_t p = 0, n = fa.size();
+    FaiEntry cur; bool have = false; int64_t seen_short = 0;
+    while (p < n) {
+        const uint8_t* e = (const uint8_t*)memchr(fa.data() + p, '\n', n - p);
+        size_t le = e ? (size_t)(e - fa.data()) : n;
+        size_t llen = le - p + (e ? 1 : 0);
+        size_t blen = le - p;
+        if (blen && fa[le - 1] == '\r') blen--;
+        if (fa[p] == '>') {
+            if (have) out.push_back(cur);
+            size_t q = p + 1; while (q < le && !isspace(fa[q])) q++;
+            cur = FaiEntry(); cur.name = std::string((const char*)fa.data() + p + 1, q - p - 1);
+            cur.len = 0; cur.offset = le + 1; cur.line_blen = 0; cur.line_len = 0; have = true; seen_short = 0;
+        } else if (have && blen) {
+            if (cur.line_blen == 0) { cur.line_blen = (int32_t)blen; cur.line_len = (int32_t)llen; }
+            else {
+                if (seen_short) { err = "build_fai: different line length in sequence " + cur.name; return false; }
+                if ((int32_t)blen != cur.line_blen) { if ((int32_t)blen > cur.line_blen) { err = "build_fai: different line length in sequence " + cur.name; return false; } seen_short = 1; }
+            }
+            cur.len += (int64_t)blen;
+        }
+        p = le + 1;
+    }
+    if (have) out.push_back(cur);
+    if (out.empty()) { err = "build_fai: no sequence found"; return false; }
+    return true;
+}
+
+bool load_size_list(const std::string& path, std::vector<int32_t>& len, std::string& err) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = "Unable to open size distribution file " + path; return false; }   // fragSim.cpp:742
+    std::vector<std::string> lines; split_lines(b, lines);
+    len.clear();
+    for (size_t i = 0; i < lines.size(); i++) {
+        if (all_tokens(lines[i], '\t').size() != 1) { err = "The following line " + lines[i] + " in file " + path + " does not have 1 field"; return false; }   // :730-733
+        long long t;
+        if (!to_i64(lines[i], &t)) { err = "The following line " + lines[i] + " in file " + path + " is not a number"; return false; }
+        if (t >= 1) len.push_back((int32_t)t);                        // :736-737
+    }
+    if (len.empty()) { err = "Size distribution file " + path + " holds no usable length"; return false; }
+    return true;
+}
+
+bool load_size_freq(const std::string& path, std::vector<int32_t>& len, std::vector<double>& cum, std::string& err) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = "Unable to open size frequency file " + path; return false; }      // fragSim.cpp:774
+    std::vector<std::string> lines; split_lines(b, lines);
+    len.clear(); cum.clear();
+    double cumul = 0.0;
+    for (size_t i = 0; i < lines.size(); i++) {
+        std::vector<std::string> f = all_tokens(lines[i], '\t');
+        if (f.size() != 2) { err = "The following line " + lines[i] + " in file " + path + " does not have 2 fields"; return false; }   // :760-763
+        double fr; long long l;
+        if (!to_double(f[1], &fr) || !to_i64(f[0], &l)) { err = "The following line " + lines[i] + " in file " + path + " cannot be parsed"; return false; }
+        cumul += fr;                                                  // :765
+        len.push_back((int32_t)l); cum.push_back(cumul);              // :766-769
+    }
+    if (cumul < 0.99 || cumul > 1.01) {                               // :778-782
+        char t[64]; snprintf(t, sizeof t, "%g", cumul);
+        err = "Problem in file: " + path + ", the sum of frequencies does not sum to 1, sum=" + t; return false;
+    }
+    return true;
+}
+
+// one .dat/.prof file: header line skipped; per line: tab fields (dropping the first `skip` columns), token before ' ' -> double
+static bool load_rate_file(const std::string& path, int skip, Rates& sub, std::string& err, const char* which) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = std::string("Unable to open ") + which + " deamination file " + path; return false; }   // deamSim.cpp:1165-1168
+    std::vector<std::string> lines; split_lines(b, lines);
+    if (lines.empty()) { err = std::string("Parsing error for ") + which + " deamination file " + path; return false; }          // :1121-1124
+    sub.clear();
+    for (size_t i = 1; i < lines.size(); i++) {
+        std::vector<std::string> fields = all_tokens(lines[i], '\t');
+        std::vector<std::string> first;
+        for (size_t k = (size_t)skip; k < fields.size(); k++) first.push_back(all_tokens(fields[k], ' ')[0]);   // :1127-1132
+        if (first.size() != 12) { char t[32]; snprintf(t, sizeof t, "%zu", first.size()); err = "line from deamination does not have 12 fields " + lines[i] + " " + t; return false; }   // :1134-1137
+        double r[12];
+        for (int k = 0; k < 12; k++) if (!to_double(first[k], &r[k])) { err = "cannot parse rate \"" + first[k] + "\" in " + path; return false; }
+        for (int bb = 0; bb < 4; bb++) {                                 // :1148-1158
+            double sum = 0.0;
+            for (int a = 0; a < 3; a++) sum += r[bb * 3 + a];
+            if (sum > 1.0) { err = "Problem with line " + lines[i] + " in file " + path + " the sum of the substitution probabilities exceeds 1"; return false; }
+        }
+        sub.insert(sub.end(), r, r + 12);
+    }
+    if (sub.empty()) { err = std::string("No rows in ") + which + " deamination file " + path; return false; }
+    return true;
+}
+static void reverse_rows(Rates& s) {
+    const size_t rows = s.size() / 12;
+    for (size_t i = 0; i < rows / 2; i++) for (int k = 0; k < 12; k++) std::swap(s[i * 12 + k], s[(rows - 1 - i) * 12 + k]);
+}
+bool load_matrix_dat(const std::string& prefix, Rates& sub5, Rates& sub3, std::string& err) {
+    if (!load_rate_file(prefix + "5.dat", 1, sub5, err, "5p")) return false;     // deamSim.cpp:1102
+    if (!load_rate_file(prefix + "3.dat", 1, sub3, err, "3p")) return false;     // :1103
+    reverse_rows(sub3);                                                           // :1236
+    return true;
+}
+bool load_profile(const std::string& prefix, Rates& sub5, Rates& sub3, std::string& err) {
+    if (!load_rate_file(prefix + "5p.prof", 0, sub5, err, "5p")) return false;   // deamSim.cpp:960
+    if (!load_rate_file(prefix + "3p.prof", 0, sub3, err, "3p")) return false;   // :961  (not reversed, :1090)
+    return true;
+}
+
+bool load_mapdamage(const std::string& path, Rates& sub5, Rates& sub3, std::string& err) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = "Unable to open misincorporation file " + path; return false; }    // deamSim.cpp:611-613
+    std::vector<std::string> lines; split_lines(b, lines);
+    if (lines.size() < 4) { err = "Parsing error for misincorporation file " + path; return false; }        // :471-481
+    std::vector<std::string> hdr = all_tokens(lines[3], '\t');
+    if (hdr.size() < 21) { err = "Parsing error for misincorporation file " + path; return false; }
+    int map12[12];
+    for (int i = 0; i < 12; i++) {                                      // :486-536
+        const std::string& h = hdr[9 + i];
+        if (h.size() != 3 || h[1] != '>') { err = "Parsing error for misincorporation file " + path + " wrong header field " + h; return false; }
+        const char* B = "ACGT";
+        const char* f = strchr(B, h[0]); const char* t = strchr(B, h[2]);
+        if (!f || !t || !h[0] || !h[2] || f == t) { err = "Parsing error for misincorporation file " + path; return false; }
+        const int from = (int)(f - B), to = (int)(t - B);
+        map12[i] = from * 3 + (to < from ? to : to - 1);
+    }
+    struct Cnt { double sub[12]; double base[4]; };
+    std::vector<Cnt> c5, c3; bool first5 = true, first3 = true;
+    for (size_t li = 4; li < lines.size(); li++) {                      // :539-609
+        if (lines[li].empty() && li + 1 == lines.size()) break;
+        std::vector<std::string> f = all_tokens(lines[li], '\t');
+        if (f.size() < 21) { err = "line from misincorporation.txt does not have a 5p or 3p in the 2nd column: " + lines[li]; return false; }
+        const bool is3 = f[1] == "3p", is5 = f[1] == "5p";
+        if (!is3 && !is5) { err = "line from misincorporation.txt does not have a 5p or 3p in the 2nd column: " + lines[li]; return false; }   // :604
+        std::vector<Cnt>& C = is3 ? c3 : c5; bool& first = is3 ? first3 : first5;
+        if (first && f[2] == "-") first = false;                        // :544-546 / :576-578
+        long long v;
+        if (first) {
+            Cnt c; memset(&c, 0, sizeof c);
+            for (int i = 0; i < 4; i++) { if (!to_i64(f[4 + i], &v)) { err = "bad count in " + lines[li]; return false; } c.base[i] = (double)(uint32_t)v; }
+            for (int i = 0; i < 12; i++) { if (!to_i64(f[9 + i], &v)) { err = "bad count in " + lines[li]; return false; } c.sub[map12[i]] = (double)(uint32_t)v; }
+            C.push_back(c);
+        } else {
+            long long pos; if (!to_i64(f[3], &pos) || pos < 1 || (size_t)pos > C.size()) { err = "bad position in " + lines[li]; return false; }
+            Cnt& c = C[(size_t)pos - 1];                                // :561 / :592
+            for (int i = 0; i < 4; i++) { if (!to_i64(f[4 + i], &v)) { err = "bad count in " + lines[li]; return false; } c.base[i] = (double)(uint32_t)((uint32_t)c.base[i] + (uint32_t)v); }
+            for (int i = 0; i < 12; i++) { if (!to_i64(f[9 + i], &v)) { err = "bad count in " + lines[li]; return false; } c.sub[map12[i]] = (double)(uint32_t)((uint32_t)c.sub[map12[i]] + (uint32_t)v); }
+        }
+    }
+    if (c5.size() != c3.size()) { err = "Error in misincorporation file " + path + " the number of defined bases for the 5' and 3' ends differ"; return false; }   // :616-619
+    sub5.clear(); sub3.clear();
+    for (size_t i = 0; i < c5.size(); i++) for (int bb = 0; bb < 4; bb++) for (int a = 0; a < 3; a++) sub5.push_back(c5[i].sub[bb * 3 + a] / c5[i].base[bb]);   // :622-632
+    for (size_t i = 0; i < c3.size(); i++) for (int bb = 0; bb < 4; bb++) for (int a = 0; a < 3; a++) sub3.push_back(c3[i].sub[bb * 3 + a] / c3[i].base[bb]);   // :641-649
+    if (sub5.empty()) { err = "Parsing error for misincorporation file " + path; return false; }
+    return true;
+}
+
+bool load_bact_list(const std::string& path, std::vector<std::string>& names, std::vector<double>& w, std::string& err) {
+    std::vector<uint8_t> b;
+    if (!read_file(path, b, err)) { err = "List file " + path + " does not exist"; return false; }
+    std::vector<std::string> lines; split_lines(b, lines);
+    names.clear(); w.clear();
+    double sum = 0;
+    for (size_t i = 0; i < lines.size(); i++) {
+        // /^(\S+)\s+(\S+)$/   gargammel.pl:870
+        const std::string& l = lines[i];
+        size_t a = 0; while (a < l.size() && !isspace((unsigned char)l[a])) a++;
+        size_t c = a; while (c < l.size() && isspace((unsigned char)l[c])) c++;
+        size_t d = c; while (d < l.size() && !isspace((unsigned char)l[d])) d++;
+        double v;
+        if (a == 0 || c == a || d == c || d != l.size() || !to_double(l.substr(c, d - c), &v)) { err = "Cannot parse line from bacterial list: " + path + " line:" + l; return false; }
+        names.push_back(l.substr(0, a)); w.push_back(v); sum += v;
+    }
+    if (sum < 0.99 || sum > 1.01) { char t[64]; snprintf(t, sizeof t, "%g", sum); err = "Problem from bacterial list: " + path + " sum is not 1, found: " + t; return false; }   // gargammel.pl:887
+    return true;
+}
+
+// ---------------------------------------------------------------- apportioning
+// host-side Philox4x32-10 (same generator as the device path; used for the per-source counts only)
+static void philox(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t key, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct UStream {                        // uniform doubles in (0,1), 53 bits
+    uint64_t seed, stream, n; uint32_t buf[4]; int have;
+    UStream(uint64_t s, uint64_t st) : seed(s), stream(st), n(0), have(0) {}
+    double next() {
+        if (have < 2) { philox(n++, stream | (0xA5ull << 56), seed, buf); have = 4; }
+        uint64_t v = ((uint64_t)buf[have - 1] << 32) | buf[have - 2]; have -= 2;
+        return ((double)(v >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    }
+};
+static double stirling_tail(double k) {   // log(k!) - [ (k+0.5)log(k+1) - (k+1) + 0.5 log(2 pi) ]
+    static const double t[] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509, 0.0166446911898211,
+                               0.0138761288230707, 0.0118967099458917, 0.0104112652619720, 0.00925546218271273, 0.00833056343336287};
+    if (k <= 9) return t[(int)k];
+    const double kp1sq = (k + 1) * (k + 1);
+    return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / (k + 1);
+}
+static uint64_t binomial_stream(uint64_t n, double p, UStream& U) {
+    if (n == 0 || p <= 0.0) return 0;
+    if (p >= 1.0) return n;
+    if (p > 0.5) return n - binomial_stream(n, 1.0 - p, U);
+    const double nd = (double)n;
+    if (nd * p < 10.0) {                 // inversion by sequential search
+        const double q = 1.0 - p, s = p / q;
+        double f = pow(q, nd), u = U.next(); uint64_t k = 0;
+        while (u > f && k < n) { u -= f; k++; f *= s * (nd - (double)k + 1.0) / (double)k; if (f <= 0) break; }
+        return k;
+    }
+    // BTRS: Hormann (1993) transformed rejection with squeeze
+    const double spq = sqrt(nd * p * (1 - p)), b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * p, c = nd * p + 0.5;
+    const double vr = 0.92 - 4.2 / b, alpha = (2.83 + 5.1 / b) * spq, r = p / (1 - p), m = floor((nd + 1) * p);
+    while (true) {
+        const double u = U.next() - 0.5; double v = U.next();
+        const double us = 0.5 - fabs(u), k = floor((2 * a / us + b) * u + c);
+        if (k < 0 || k > nd) continue;
+        if (us >= 0.07 && v <= vr) return (uint64_t)k;
+        v = log(v * alpha / (a / (us * us) + b));
+        const double ub = (m + 0.5) * log((m + 1) / (r * (nd - m + 1))) + (nd + 1) * log((nd - m + 1) / (nd - k + 1)) +
+                          (k + 0.5) * log(r * (nd - k + 1) / (k + 1)) + stirling_tail(m) + stirling_tail(nd - m) - stirling_tail(k) - stirling_tail(nd - k);
+        if (v <= ub) return (uint64_t)k;
+    }
+}
+uint64_t binomial_draw(uint64_t n, double p, uint64_t seed, uint64_t stream) { UStream U(seed, stream); return binomial_stream(n, p, U); }
+
+// Multinomial(n, w/sum w) by conditional binomials: the law of n iid categorical draws (gargammel.pl:1322-1348, 1421-1431)
+static void multinomial(uint64_t n, const std::vector<double>& w, UStream& U, std::vector<uint64_t>& out) {
+    out.assign(w.size(), 0);
+    double rest = 0; for (size_t i = 0; i < w.size(); i++) rest += w[i];
+    uint64_t left = n;
+    for (size_t i = 0; i < w.size() && left > 0; i++) {
+        if (i + 1 == w.size() || rest <= w[i]) { out[i] = left; left = 0; break; }
+        const uint64_t k = binomial_stream(left, w[i] / rest, U);
+        out[i] = k; left -= k; rest -= w[i];
+    }
+}
+
+bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err) {
+    if (fabs(in.compB + in.compC + in.compE - 1.0) > 1e-9) {           // gargammel.pl:773 (exact != 1 there; tolerance here)
+        char t[64]; snprintf(t, sizeof t, "%g", in.compB + in.compC + in.compE);
+        err = std::string("The --comp option must have 3 comma-delimited numbers that sum up to 1, current sum ") + t; return false;
+    }
+    if (in.n_endo != 1 && in.n_endo != 2 && in.compE > 0) { err = "The endogenous directory must have 1 (haploid) or 2 (diploid) files"; return false; }
+    out.nC = (uint64_t)((double)in.n_fragments * in.compC);             // gargammel.pl:1261-1263  int()
+    out.nB = (uint64_t)((double)in.n_fragments * in.compB);
+    out.nE = (uint64_t)((double)in.n_fragments * in.compE);
+    if (out.nC && in.cont_len.empty()) { err = "If you want contamination, please have at least one file in the cont/ directory"; return false; }
+    if (out.nB && in.bact_w.empty()) { err = "If you want bacterial contamination, please have at least one file in the bact/ directory"; return false; }
+    UStream U(in.seed, 1);
+    out.endo.assign(in.n_endo > 0 ? in.n_endo : 1, 0);
+    if (in.n_endo == 2) {                                               // gargammel.pl:1272-1279: nE coin flips
+        out.endo[0] = binomial_stream(out.nE, 0.5, U); out.endo[1] = out.nE - out.endo[0];
+    } else out.endo[0] = out.nE;
+    multinomial(out.nB, in.bact_w, U, out.bact);                        // gargammel.pl:1322-1348 (a miss redraws: weights are renormalised)
+    // contaminant: randC = int(rand(sumC)); first j with randC <= cumulative length (gargammel.pl:1421-1431)
+    std::vector<double> cw(in.cont_len.size());
+    uint64_t sumC = 0; for (size_t j = 0; j < in.cont_len.size(); j++) sumC += in.cont_len[j];
+    uint64_t prev_hi = 0, run = 0;   // integers r in [0,sumC) with r <= SL[j] not taken by an earlier j
+    for (size_t j = 0; j < in.cont_len.size(); j++) {
+        run += in.cont_len[j];
+        const uint64_t hi = std::min(run + 1, sumC);   // r in [0, SL[j]] -> SL[j]+1 values, capped by sumC
+        cw[j] = (double)(hi - prev_hi); prev_hi = hi;
+    }
+    multinomial(out.nC, cw, U, out.cont);
+    return true;
+}
+
+bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err) {
+    g.path = fasta_path;
+    if (!read_file(fasta_path, g.bytes, err)) return false;            // .gz is inflated in memory (the reference writes a temp file, fragSim.cpp:1108-1147)
+    std::string e2;
+    if (!parse_fai(fasta_path + ".fai", g.fai, e2)) {
+        const bool gz = fasta_path.size() > 3 && fasta_path.compare(fasta_path.size() - 3, 3, ".gz") == 0;
+        if (gz) { err = e2; return false; }
+        if (!build_fai(g.bytes, g.fai, err)) return false;             // samtools faidx equivalent (gargammel.pl:900-903)
+    }
+    g.total_len = 0;
+    for (size_t i = 0; i < g.fai.size(); i++) g.total_len += (uint64_t)g.fai[i].len;
+    return true;
+}
+int upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out) {
+    std::vector<gg_fai_entry> f(g.fai.size());
+    for (size_t i = 0; i < f.size(); i++) { f[i].name = g.fai[i].name.c_str(); f[i].len = g.fai[i].len; f[i].offset = g.fai[i].offset; f[i].line_blen = g.fai[i].line_blen; f[i].line_len = g.fai[i].line_len; }
+    return gg_genome_upload(ctx, g.bytes.data(), g.bytes.size(), f.data(), (int)f.size(), id_out);
+}
+
+} // namespace ggh
+
+// ---------------------------------------------------------------- C exports (Python harness)
+static int set_err(char* err, int cap, const std::string& m) { if (err && cap > 0) { snprintf(err, cap, "%s", m.c_str()); } return -1; }
+extern "C" {
+int ggh_load_size_freq(const char* path, int32_t* len, double* cum, int cap, int* n, char* err, int errcap) {
+    std::vector<int32_t> l; std::vector<double> c; std::string e;
+    if (!ggh::load_size_freq(path, l, c, e)) return set_err(err, errcap, e);
+    *n = (int)l.size(); if ((int)l.size() > cap) return set_err(err, errcap, "buffer too small");
+    memcpy(len, l.data(), l.size() * 4); memcpy(cum, c.data(), c.size() * 8); return 0;
+}
+int ggh_load_size_list(const char* path, int32_t* len, int cap, int* n, char* err, int errcap) {
+    std::vector<int32_t> l; std::string e;
+    if (!ggh::load_size_list(path, l, e)) return set_err(err, errcap, e);
+    *n = (int)l.size(); if ((int)l.size() > cap) return set_err(err, errcap, "buffer too small");
+    memcpy(len, l.data(), l.size() * 4); return 0;
+}
+int ggh_load_rates(const char* path, int kind, double* sub5, int cap5, int* rows5, double* sub3, int cap3, int* rows3, char* err, int errcap) {
+    ggh::Rates a, b; std::string e; bool ok;
+    if (kind == 0) ok = ggh::load_matrix_dat(path, a, b, e); else if (kind == 1) ok = ggh::load_profile(path, a, b, e); else ok = ggh::load_mapdamage(path, a, b, e);
+    if (!ok) return set_err(err, errcap, e);
+    *rows5 = (int)(a.size() / 12); *rows3 = (int)(b.size() / 12);
+    if (*rows5 > cap5 || *rows3 > cap3) return set_err(err, errcap, "buffer too small");
+    memcpy(sub5, a.data(), a.size() * 8); memcpy(sub3, b.data(), b.size() * 8); return 0;
+}
+int ggh_fai_load(const char* path, int from_fasta, void** handle, int* n, char* err, int errcap) {
+    std::vector<ggh::FaiEntry>* v = new std::vector<ggh::FaiEntry>(); std::string e; bool ok;
+    if (from_fasta) { std::vector<uint8_t> b; ok = ggh::read_file(path, b, e) && ggh::build_fai(b, *v, e); } else ok = ggh::parse_fai(path, *v, e);
+    if (!ok) { delete v; return set_err(err, errcap, e); }
+    *handle = v; *n = (int)v->size(); return 0;
+}
+int ggh_fai_get(void* handle, int i, char* name, int namecap, int64_t* len, uint64_t* offset, int32_t* blen, int32_t* llen) {
+    std::vector<ggh::FaiEntry>* v = (std::vector<ggh::FaiEntry>*)handle;
+    if (!v || i < 0 || i >= (int)v->size()) return -1;
+    snprintf(name, namecap, "%s", (*v)[i].name.c_str()); *len = (*v)[i].len; *offset = (*v)[i].offset; *blen = (*v)[i].line_blen; *llen = (*v)[i].line_len; return 0;
+}
+void ggh_fai_free(void* handle) { delete (std::vector<ggh::FaiEntry>*)handle; }
+int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_endo, const uint64_t* cont_len, int n_cont,
+                  const double* bact_w, int n_bact, uint64_t seed, uint64_t* totals3, uint64_t* endo, uint64_t* cont, uint64_t* bact,
+                  char* err, int errcap) {
+    ggh::ApportionIn in; in.n_fragments = n; in.compB = compB; in.compC = compC; in.compE = compE; in.n_endo = n_endo; in.seed = seed;
+    in.cont_len.assign(cont_len, cont_len + n_cont); in.bact_w.assign(bact_w, bact_w + n_bact);
+    ggh::ApportionOut out; std::string e;
+    if (!ggh::apportion(in, out, e)) return set_err(err, errcap, e);
+    totals3[0] = out.nE; totals3[1] = out.nC; totals3[2] = out.nB;
+    for (size_t i = 0; i < out.endo.size(); i++) endo[i] = out.endo[i];
+    for (size_t i = 0; i < out.cont.size(); i++) cont[i] = out.cont[i];
+    for (size_t i = 0; i < out.bact.size(); i++) bact[i] = out.bact[i];
+    return 0;
+}
+uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream) { return ggh::binomial_draw(n, p, seed, stream); }
+}

@@ -1,0 +1,77 @@
+// gg_host.h -- host-side (C++11) file-format layer and fragment apportioning of the gargammel hot path.
+// Parsers follow the reference's loaders line by line (cited at each function); no CUDA here.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/gargammel_b200.h"
+
+namespace ggh {
+
+struct FaiEntry { std::string name; int64_t len; uint64_t offset; int32_t line_blen, line_len; };
+
+// whole file into memory; transparently inflates gzip (zlib gzread)
+bool read_file(const std::string& path, std::vector<uint8_t>& out, std::string& err);
+// split on a delimiter keeping empty tokens (libgab allTokens semantics as used by the reference)
+std::vector<std::string> all_tokens(const std::string& s, char delim);
+
+// samtools .fai, 5 tab-separated columns (fragSim.cpp:231-269)
+bool parse_fai(const std::string& path, std::vector<FaiEntry>& out, std::string& err);
+// build a .fai from FASTA bytes (the driver runs `samtools faidx` when it is missing, gargammel.pl:900-903)
+bool build_fai(const std::vector<uint8_t>& fasta, std::vector<FaiEntry>& out, std::string& err);
+
+// -s file: one length per line, keep t >= 1 (fragSim.cpp:720-745)
+bool load_size_list(const std::string& path, std::vector<int32_t>& len, std::string& err);
+// -f file: "length<TAB>freq", running cumulative sum, require 0.99 <= sum <= 1.01 (fragSim.cpp:751-784)
+bool load_size_freq(const std::string& path, std::vector<int32_t>& len, std::vector<double>& cum, std::string& err);
+
+typedef std::vector<double> Rates;   // rows x 12, idx = from*3 + (to<from ? to : to-1), bases A,C,G,T
+// -matfile prefix: <prefix>5.dat / <prefix>3.dat; first column dropped, "value [lo..hi]" -> value; per-base sums <= 1;
+// the 3' file is reversed so that row 0 is the terminal base (deamSim.cpp:1098-1241)
+bool load_matrix_dat(const std::string& prefix, Rates& sub5, Rates& sub3, std::string& err);
+// -profile prefix: <prefix>5p.prof / <prefix>3p.prof, 12 columns from field 0, 3' NOT reversed (deamSim.cpp:956-1094)
+bool load_profile(const std::string& prefix, Rates& sub5, Rates& sub3, std::string& err);
+// -mapdamage misincorporation.txt: header-driven column remap, counts summed over chromosomes/strands (deamSim.cpp:453-668)
+bool load_mapdamage(const std::string& path, Rates& sub5, Rates& sub3, std::string& err);
+
+// bact/list: "name<TAB>weight" (select_random_speciesftp.py:66-70; gargammel.pl:1040-1105)
+bool load_bact_list(const std::string& path, std::vector<std::string>& names, std::vector<double>& w, std::string& err);
+
+// ---- apportioning (gargammel.pl:1256-1283,1320-1349,1421-1431) ----
+struct ApportionIn {
+    uint64_t n_fragments;                  // -n
+    double compB, compC, compE;            // --comp B,C,E
+    int n_endo;                            // 1 (haploid) or 2 (diploid)
+    std::vector<uint64_t> cont_len;        // contaminant file lengths (bp)
+    std::vector<double> bact_w;            // bacterial weights (sum ~ 1)
+    uint64_t seed;
+};
+struct ApportionOut {
+    uint64_t nE, nC, nB;                   // int(n*comp)  (gargammel.pl:1261-1263)
+    std::vector<uint64_t> endo, cont, bact;
+};
+bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err);
+// exact Binomial(n,p) draw from a Philox-fed uniform stream (inversion for small n*p, BTRS otherwise)
+uint64_t binomial_draw(uint64_t n, double p, uint64_t seed, uint64_t stream);
+
+// ---- one genome file ready for upload ----
+struct GenomeFile { std::string path; std::vector<uint8_t> bytes; std::vector<FaiEntry> fai; uint64_t total_len; };
+bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err);
+int  upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out);
+
+} // namespace ggh
+
+// C exports for the Python harness (ctypes); caller-provided buffers, 0 on success, message in err
+extern "C" {
+int ggh_load_size_freq(const char* path, int32_t* len, double* cum, int cap, int* n, char* err, int errcap);
+int ggh_load_size_list(const char* path, int32_t* len, int cap, int* n, char* err, int errcap);
+/* kind: 0 = -matfile (.dat), 1 = -profile (.prof), 2 = -mapdamage (path is the file) */
+int ggh_load_rates(const char* path, int kind, double* sub5, int cap5, int* rows5, double* sub3, int cap3, int* rows3, char* err, int errcap);
+int ggh_fai_load(const char* path, int from_fasta, void** handle, int* n, char* err, int errcap);
+int ggh_fai_get(void* handle, int i, char* name, int namecap, int64_t* len, uint64_t* offset, int32_t* blen, int32_t* llen);
+void ggh_fai_free(void* handle);
+int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_endo, const uint64_t* cont_len, int n_cont,
+                  const double* bact_w, int n_bact, uint64_t seed, uint64_t* totals3, uint64_t* endo, uint64_t* cont, uint64_t* bact,
+                  char* err, int errcap);
+uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
+}

@@ -1,0 +1,97 @@
+// gg_kernels.cuh -- parameter blocks shared by the host API (gg_api.cu) and the kernels (gg_kernels.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "gg_device.cuh"
+
+namespace ggk {
+
+struct GenomeDev {           // one uploaded FASTA file, packed (DESIGN.md "Data layout in HBM")
+    const uint32_t* seq2;    // 2-bit codes, 16 bases per word
+    const uint32_t* nmask;   // 1 bit per base, 1 = not A/C/G/T, 32 bases per word
+    uint64_t G;              // sum of contig lengths = size of the sampling space (fragSim.cpp:1163)
+    int first_contig;        // index of this genome's first contig in the (name-sorted) contig table
+    int n_contigs;
+};
+struct ContigTab {           // struct-of-arrays over all contigs of all genomes
+    const uint64_t* cum_end; // inclusive running end within its genome, name-sorted order (fragSim.cpp:1160-1163)
+    const uint64_t* gbase;   // first base of the contig in seq2/nmask base space (64-aligned)
+    const uint32_t* len;
+    const uint32_t* name_off;
+    const uint16_t* name_len;
+    const char*     names;
+};
+struct RangeDev {            // one `fragSim -tag T -n N file` of the plan
+    uint64_t first_id, count;
+    int genome, slot, tag_len, pad;
+    char tag[24];
+};
+struct Adapters {
+    const uint32_t* adF2;    // forward adapter, 2-bit packed (+slack)
+    const uint32_t* adS2;    // second adapter
+    const uint32_t* rcS2;    // reverse complement of the second adapter
+    int lenF, lenS, read_len, pad;
+};
+struct SmemLayout {          // byte offsets into dynamic shared memory, computed by the host
+    int stage, stage_bytes;  // output staging (16 B of readable slack before and after)
+    int gpos, meta, recoff, hdr, cstart, gstart;   // per-fragment descriptors
+    int dwords, cmap, gmap, lut, total;
+};
+struct FusedParams {
+    // work
+    uint64_t first, count;   // fragment ids [first, first+count)
+    int F;                   // fragments per tile
+    int n_tiles;
+    int emit;                // gg_emit_mode
+    int norev;
+    ggd::Key key;
+    // plan + genomes
+    const RangeDev* ranges; int n_ranges;
+    const GenomeDev* genomes; int n_genomes;
+    ContigTab ctab;
+    // fragment lengths
+    int size_mode, fixed_len, minlen, maxlen, n_sizes;
+    const uint32_t* size_thr;   // FREQ: u31 < size_thr[i]  <=>  p <= cum[i]
+    const int32_t*  size_len;
+    // damage + adapters
+    ggd::DamageDev dmg[4];
+    Adapters ad;
+    // output
+    uint8_t* out; uint64_t out_cap;
+    unsigned long long* tile_state;   // decoupled look-back: [63:62] status, [61:0] bytes
+    unsigned int* ticket;
+    unsigned long long* stats;        // [0] total bytes [1] attempts [2] gather bytes [3] error flags
+    SmemLayout sm;
+};
+
+enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
+enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
+
+constexpr int FUSED_THREADS = 256;
+
+// ---- launchers (gg_kernels.cu) ----
+cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
+                               const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
+                               const uint64_t* unit_start, int n_contigs, uint64_t n_units,
+                               uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
+cudaError_t launch_fused(const FusedParams& P, int grid, cudaStream_t st);
+cudaError_t fused_occupancy(int smem_bytes, int* blocks_per_sm);
+
+// stand-alone record-stream kernels
+struct RecStream {
+    const uint8_t* in; uint64_t n;        // input bytes
+    const uint64_t* nl; uint64_t n_nl;    // positions of '\n' (an implicit one at n if the stream lacks it)
+    uint64_t n_rec;
+};
+cudaError_t launch_count_newlines(const uint8_t* in, uint64_t n, unsigned long long* block_counts, int n_blocks, cudaStream_t st);
+cudaError_t launch_fill_newlines(const uint8_t* in, uint64_t n, const unsigned long long* block_base, uint64_t* nl, int n_blocks, cudaStream_t st);
+cudaError_t launch_exclusive_scan(unsigned long long* data, uint64_t n, unsigned long long* scratch, unsigned long long* total, cudaStream_t st);
+cudaError_t launch_deam_records(const RecStream& R, uint8_t* out, const ggd::DamageDev& D, int has_damage, ggd::Key key,
+                                uint64_t first_id, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_adpt_sizes(const RecStream& R, int emit, int read_len, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_adpt_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, int emit, Adapters ad,
+                                const uint8_t* adF, const uint8_t* adS, ggd::Key key, uint64_t first_id, cudaStream_t st);
+cudaError_t launch_l2_flush(uint4* buf, uint64_t n16, cudaStream_t st);
+constexpr int NL_BLOCK_BYTES = 1 << 16;
+
+} // namespace ggk

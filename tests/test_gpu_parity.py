@@ -1,0 +1,201 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) must be BIT-EXACT against the CPU oracle on the
+same seeded inputs -- integer/byte work, so no tolerance anywhere."""
+import numpy as np
+import pytest
+
+from gargammel_b200 import api, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+ALL_EMITS = [api.EMIT_FRAG, api.EMIT_DEAM, api.EMIT_STDOUT4, api.EMIT_ARTS, api.EMIT_ARTP, api.EMIT_FR, api.EMIT_RR]
+
+
+@pytest.fixture(scope="module")
+def genomes():
+    return util.tiny_genomes()
+
+
+def _pair(oracle_mod, genomes, seed=42, **kw):
+    g = api.Context(0, seed)
+    o = oracle_mod.OracleContext(seed)
+    ids = util.configure(g, genomes, **kw)
+    assert util.configure(o, genomes, **kw) == ids
+    return g, o, ids
+
+
+def test_pack_genome_matches_fasta(genomes):
+    """k_pack_genome vs the FASTA bytes read through the line structure (fetchSeq, fragSim.cpp:305-329)."""
+    with api.Context(0, 1) as g:
+        for fa, fai in genomes:
+            gid = g.upload_genome(fa, fai)
+            for ci, e in enumerate(fai):
+                raw = fa[e.offset:e.offset + e.len + e.len // e.line_blen + 1].replace(b"\n", b"")[:e.len].upper()
+                want = bytes(c if c in b"ACGT" else ord("N") for c in raw)
+                assert g.genome_fetch(gid, ci, 0, e.len) == want
+                assert g.genome_fetch(gid, ci, e.len // 3, min(77, e.len - e.len // 3)) == want[e.len // 3:e.len // 3 + 77]
+
+
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double"])
+@pytest.mark.parametrize("sizes", ["freq", "list", "fixed"])
+def test_fused_bit_exact(oracle_mod, genomes, damage, sizes):
+    g, o, ids = _pair(oracle_mod, genomes, sizes=sizes, damage=damage)
+    plan = util.plan3(ids)
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in ALL_EMITS:
+        a, ia = g.run_fused(0, 1200, emit)
+        b, ib = o.run_fused(0, 1200, emit)
+        util.assert_same(a, b, "emit=%d damage=%s sizes=%s" % (emit, damage, sizes))
+        assert (ia.bytes, ia.records, ia.attempts, ia.gather_bytes) == (ib.bytes, ib.records, ib.attempts, ib.gather_bytes)
+    g.close(); o.close()
+
+
+def test_fused_id_ranges_and_seeds(oracle_mod, genomes):
+    """Any id sub-range gives the corresponding slice (disjoint Philox counters = multi-GPU sharding); seeds differ."""
+    g, o, ids = _pair(oracle_mod, genomes, seed=2024)
+    plan = util.plan3(ids, counts=(1000, 700, 900))
+    g.set_plan(plan); o.set_plan(plan)
+    full, _ = g.run_fused(0, 2600, api.EMIT_ARTP)
+    util.assert_same(full, o.run_fused(0, 2600, api.EMIT_ARTP)[0], "full")
+    cuts = [0, 1, 255, 256, 257, 999, 1000, 1700, 2599, 2600]
+    parts = [g.run_fused(a, b - a, api.EMIT_ARTP)[0] for a, b in zip(cuts[:-1], cuts[1:])]
+    assert b"".join(parts) == full
+    g.set_seed(2025); o.set_seed(2025)
+    other, _ = g.run_fused(0, 2600, api.EMIT_ARTP)
+    assert other != full
+    util.assert_same(other, o.run_fused(0, 2600, api.EMIT_ARTP)[0], "seed 2025")
+    empty, info = g.run_fused(5, 0, api.EMIT_ARTP)
+    assert empty == b"" and info.bytes == 0
+
+
+@pytest.mark.parametrize("read_len,adF,adS", [(30, "ACGTTGCA", "TTGGCC"), (75, api.DEFAULT_ADAPTER_F, api.DEFAULT_ADAPTER_S),
+                                              (200, api.DEFAULT_ADAPTER_F, api.DEFAULT_ADAPTER_S), (16, "A", "C"), (1, "G", "T")])
+def test_fused_adapters_trim_and_pad(oracle_mod, genomes, read_len, adF, adS):
+    """Read shorter than, equal to and longer than fragment+adapter: trimming, adapter append, random padding (adptSim.cpp:298-322)."""
+    g, o, ids = _pair(oracle_mod, genomes, read_len=read_len, adapters=(adF, adS), damage="matrix")
+    plan = util.plan3(ids)
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in ALL_EMITS[2:]:
+        util.assert_same(g.run_fused(0, 1200, emit)[0], o.run_fused(0, 1200, emit)[0], "RL=%d emit=%d" % (read_len, emit))
+
+
+@pytest.mark.parametrize("kw", [dict(sizes="fixed", fixed_len=1), dict(sizes="fixed", fixed_len=16), dict(sizes="fixed", fixed_len=17),
+                                dict(sizes="fixed", fixed_len=191), dict(sizes="fixed", fixed_len=700, maxlen=1000), dict(minlen=60, maxlen=90),
+                                dict(norev=True), dict(clamp_last=False, sizes="fixed", fixed_len=191), dict(matrix="double-")])
+def test_fused_edge_configs(oracle_mod, genomes, kw):
+    g, o, ids = _pair(oracle_mod, genomes, **kw)
+    plan = util.plan3(ids, counts=(300, 200, 250))
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in (api.EMIT_FRAG, api.EMIT_DEAM, api.EMIT_ARTP, api.EMIT_STDOUT4):
+        util.assert_same(g.run_fused(0, 750, emit)[0], o.run_fused(0, 750, emit)[0], "%r emit=%d" % (kw, emit))
+
+
+def test_fused_many_contigs_and_long_names(oracle_mod):
+    """Draft-assembly style input: hundreds of short contigs, long names, contig ends everywhere (run-off rejection)."""
+    rng = np.random.default_rng(11)
+    contigs = [("scaffold_%04d_len_with_a_rather_long_name|x" % i, synth.random_contig(rng, int(rng.integers(40, 400)), 0.02, (3, 30))) for i in range(300)]
+    fa, fai = synth.fasta_bytes(contigs, width=70)
+    g = api.Context(0, 9); o = oracle_mod.OracleContext(9)
+    for c in (g, o):
+        gid = c.upload_genome(fa, fai)
+        c.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq())
+        util.set_damage(c, 0, "briggs")
+        c.set_adapters(read_len=75)
+        c.set_plan([api.Range(100, 3000, gid, 0, "b1000")])
+    for emit in (api.EMIT_FRAG, api.EMIT_ARTP):
+        a, ia = g.run_fused(100, 3000, emit); b, ib = o.run_fused(100, 3000, emit)
+        util.assert_same(a, b, "many contigs emit=%d" % emit)
+        assert ia.attempts == ib.attempts and ia.attempts > 3000
+
+
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double", "none"])
+def test_standalone_stages_bit_exact(oracle_mod, genomes, damage):
+    """deamSim / adptSim as separate stages over the record stream the previous stage wrote, and fused == composition."""
+    g, o, ids = _pair(oracle_mod, genomes, damage=damage)
+    slot = 0 if damage != "none" else -1
+    plan = [api.Range(0, 900, ids[1], slot, "e")]
+    g.set_plan(plan); o.set_plan(plan)
+    frag, _ = g.run_fused(0, 900, api.EMIT_FRAG)
+    d_g, info = g.run_deam(frag, slot, 0)
+    util.assert_same(d_g, o.run_deam(frag, slot, 0)[0], "deam " + damage)
+    assert info.records == 900 and info.in_bytes == len(frag)
+    util.assert_same(d_g, g.run_fused(0, 900, api.EMIT_DEAM)[0], "fused vs fragSim|deamSim")
+    util.assert_same(g.run_deam(frag, slot, 12345)[0], o.run_deam(frag, slot, 12345)[0], "deam first_id")
+    for emit in ALL_EMITS[2:]:
+        a_g, _ = g.run_adpt(d_g, emit, 0)
+        util.assert_same(a_g, o.run_adpt(d_g, emit, 0)[0], "adpt emit=%d" % emit)
+        util.assert_same(a_g, g.run_fused(0, 900, emit)[0], "fused vs composition emit=%d" % emit)
+
+
+def test_standalone_odd_inputs(oracle_mod):
+    """Empty stream, missing final newline, lower case, N and IUPAC bases, 1-base and long sequences, long ids."""
+    g = api.Context(0, 77); o = oracle_mod.OracleContext(77)
+    for c in (g, o):
+        util.set_damage(c, 0, "matrix"); util.set_damage(c, 1, "briggs"); util.set_damage(c, 2, "double")
+        c.set_adapters("ACGTACGTAC", "TTTTGGGGCC", 40)
+    rng = np.random.default_rng(5)
+    recs = [b">only_one_base\nC\n", b">lower:+:1:9:8\nacgtnacg\n", b">iupac\nACGTRYKMNNacgtCCCCGGGG\n",
+            b">" + b"x" * 300 + b"\n" + synth._BASES[rng.integers(0, 4, 3000)].tobytes() + b"\n", b">empty_seq\n\n"]
+    recs += [b">r%d\n%s\n" % (i, synth._BASES[rng.integers(0, 4, int(rng.integers(1, 120)))].tobytes()) for i in range(500)]
+    stream = b"".join(recs)
+    for data in (b"", stream, stream[:-1], recs[0], recs[0][:-1]):
+        for slot in (0, 1, 2, -1):
+            util.assert_same(g.run_deam(data, slot)[0], o.run_deam(data, slot)[0], "deam slot=%d n=%d" % (slot, len(data)))
+        for emit in ALL_EMITS[2:]:
+            util.assert_same(g.run_adpt(data, emit)[0], o.run_adpt(data, emit)[0], "adpt emit=%d n=%d" % (emit, len(data)))
+    with pytest.raises(api.GGError):
+        g.run_deam(b">a\nACGT\n>b\n", 0)          # odd number of lines
+    with pytest.raises(api.GGError):
+        g.run_deam(b"a\nACGT\n", 0)               # no '>'
+
+
+def test_errors_are_loud(genomes):
+    g = api.Context(0, 1)
+    with pytest.raises(api.GGError):
+        g.run_fused(0, 10, api.EMIT_FRAG)                       # no plan
+    fa, fai = synth.fasta_bytes([("allN", np.full(5000, ord("N"), dtype=np.uint8))])
+    gid = g.upload_genome(fa, fai)
+    g.set_sizes(api.SIZE_FIXED, fixed_len=40)
+    g.set_plan([api.Range(0, 10, gid, -1, "")])
+    with pytest.raises(api.GGError) as e:
+        g.run_fused(0, 10, api.EMIT_FRAG)                       # fragSim.cpp:1361 would spin forever
+    assert e.value.code == -6
+    with pytest.raises(api.GGError):
+        g.set_plan([api.Range(0, 10, 99, -1, "")])
+    with pytest.raises(api.GGError):
+        g.set_sizes(api.SIZE_FIXED, fixed_len=5000, maxlen=10000)
+    with pytest.raises(api.GGError):
+        g.set_adapters("ACGU", "ACGT", 75)
+    with pytest.raises(api.GGError):
+        g.set_briggs(0, 1.5, 0.4, 0.01, 0.3)
+
+
+def test_large_run_properties(oracle_mod):
+    """A BASELINE-shaped run (C2 at 1/25 scale: 2 Mb sources, 400k fragments, --comp 0,0.08,0.92, sizefreq, single- matrix,
+    2x75 artp): sampled id windows are bit-exact vs the oracle; the whole stream obeys the size-independent invariants."""
+    srcs = [synth.make_genome(100 + i, 1 + i % 3, 2_000_000, prefix="s%d_" % i) for i in range(3)]
+    g = api.Context(0, 42); o = oracle_mod.OracleContext(42)
+    n = 400_000
+    nC, nE = int(n * 0.08), int(n * 0.92)
+    for c in (g, o):
+        ids = [c.upload_genome(fa, fai) for fa, fai in srcs]
+        c.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq())
+        util.set_damage(c, 0, "matrix")
+        c.set_adapters(read_len=75)
+        c.set_plan([api.Range(0, nE // 2, ids[0], 0, "e1_0"), api.Range(nE // 2, nE - nE // 2, ids[1], 0, "e2_0"), api.Range(nE, nC, ids[2], -1, "c1")])
+    tot = nE + nC
+    out, info = g.run_fused(0, tot, api.EMIT_ARTP)
+    assert info.records == tot and info.bytes == len(out) and info.launches == 1
+    lines = out.split(b"\n")
+    assert lines[-1] == b"" and len(lines) == 2 * tot + 1
+    seqlen = np.array([len(x) for x in lines[1:-1:2]])
+    assert (seqlen == 150).all()
+    assert all(h.startswith(b">s") for h in lines[0:-1:2][:5000])
+    for first, cnt in ((0, 3000), (nE // 2 - 1500, 3000), (nE - 1500, 3000), (tot - 3000, 3000)):
+        want, _ = o.run_fused(first, cnt, api.EMIT_ARTP)
+        got = b"\n".join(lines[2 * first:2 * (first + cnt)]) + b"\n"
+        util.assert_same(got, want, "window %d" % first)
+    # fragSim-only stream: record grammar + composition
+    frag, _ = g.run_fused(0, tot, api.EMIT_FRAG)
+    hdrs = frag.split(b"\n")[0:-1:2]
+    assert sum(h.endswith(b"c1") for h in hdrs) == nC and sum(h.endswith(b"e1_0") for h in hdrs) == nE // 2

@@ -1,0 +1,189 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every symbol of include/gargammel_b200.h,
+the C++ parsers agree with the oracle parsers and the golden tables, apportioning follows gargammel.pl."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gargammel_b200 import api, synth
+from oracle import parsers
+from tests.conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    hdr = open(os.path.join(ROOT, "include", "gargammel_b200.h")).read()
+    names = set(re.findall(r"\b(gg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+    lib.gg_abi_version.restype = C.c_int
+    assert lib.gg_abi_version() == 1
+
+
+def test_no_cuda_device_fails_loudly():
+    """Without a GPU the context cannot be created: there is no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.GGError):
+        api.Context(0, 1)
+
+
+def _load_rates(path, kind):
+    lib = api.load_library()
+    s5 = np.zeros((4096, 12)); s3 = np.zeros((4096, 12))
+    r5, r3 = C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = lib.ggh_load_rates(path.encode(), kind, s5.ctypes.data_as(C.POINTER(C.c_double)), 4096, C.byref(r5),
+                            s3.ctypes.data_as(C.POINTER(C.c_double)), 4096, C.byref(r3), err, 512)
+    if rc:
+        raise ValueError(err.value.decode())
+    return s5[:r5.value], s3[:r3.value]
+
+
+def test_matrix_dat_parser(tmp_path, golden):
+    for name in ("single-", "double-"):
+        s5, s3 = synth.golden_matrix(name)
+        synth.write_matrix_dat(str(tmp_path / name), s5, s3)
+        g5, g3 = _load_rates(str(tmp_path / name), 0)
+        assert np.array_equal(g5, s5) and np.array_equal(g3, s3)       # incl. the 3' reversal (deamSim.cpp:1236)
+        o5, o3 = parsers.load_matrix_dat(str(tmp_path / name))
+        assert np.array_equal(np.array(o5), g5) and np.array_equal(np.array(o3), g3)
+    # sum > 1 is rejected (deamSim.cpp:1148-1158)
+    bad = s5.copy(); bad[3, 3:6] = 0.4
+    synth.write_matrix_dat(str(tmp_path / "bad-"), bad, s3)
+    with pytest.raises(ValueError, match="Problem with line"):
+        _load_rates(str(tmp_path / "bad-"), 0)
+    with pytest.raises(ValueError, match="Unable to open"):
+        _load_rates(str(tmp_path / "missing-"), 0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/matrices"), reason="reference tree not mounted")
+def test_parsers_on_reference_files(golden):
+    for name in ("single-", "double-"):
+        g5, g3 = _load_rates("/root/reference/src/matrices/" + name, 0)
+        s5, s3 = synth.golden_matrix(name)
+        assert np.array_equal(g5, s5) and np.array_equal(g3, s3)
+    g5, g3 = _load_rates("/root/reference/examplesMapDamage/results_LaBrana/misincorporation.txt", 2)
+    md = golden["mapdamage_LaBrana"]
+    assert g5.shape == (70, 12) and np.allclose(g5[0], md["sub5_row0"], rtol=0, atol=0, equal_nan=True)
+    assert np.allclose(g3[0], md["sub3_row0"], rtol=0, atol=0, equal_nan=True) and np.allclose(g5[69], md["sub5_row69"], rtol=0, atol=0, equal_nan=True)
+    lens, cum = _size_freq("/root/reference/src/sizefreq.size.gz")
+    ol, oc = synth.golden_sizefreq()
+    assert lens == ol and cum == oc
+    assert _size_list("/root/reference/src/sizedist.size.gz")[:32] == golden["sizedist_first32"]
+
+
+def test_mapdamage_parser(golden):
+    p = os.path.join(ROOT, "tests", "golden", "mapdamage_sample.txt")
+    g5, g3 = _load_rates(p, 2)
+    assert np.array_equal(g5, np.array(golden["mapdamage_sample"]["sub5"])) and np.array_equal(g3, np.array(golden["mapdamage_sample"]["sub3"]))
+    o5, o3 = parsers.load_mapdamage(p)
+    assert np.array_equal(np.array(o5), g5)
+    # header order of mapDamage: G>A C>T A>G T>C A>C A>T C>G C>A T>G T>A G>C G>T -> canonical index (deamSim.cpp:483-536)
+    first = open(p).read().split("\n")[4].split("\t")
+    assert first[1] == "3p" and first[3] == "1"
+
+
+def _size_freq(path):
+    lib = api.load_library()
+    ln = np.zeros(100000, dtype=np.int32); cm = np.zeros(100000)
+    n = C.c_int(); err = C.create_string_buffer(512)
+    rc = lib.ggh_load_size_freq(path.encode(), ln.ctypes.data_as(C.POINTER(C.c_int32)), cm.ctypes.data_as(C.POINTER(C.c_double)), 100000, C.byref(n), err, 512)
+    if rc:
+        raise ValueError(err.value.decode())
+    return ln[:n.value].tolist(), cm[:n.value].tolist()
+
+
+def _size_list(path):
+    lib = api.load_library()
+    ln = np.zeros(100000, dtype=np.int32)
+    n = C.c_int(); err = C.create_string_buffer(512)
+    rc = lib.ggh_load_size_list(path.encode(), ln.ctypes.data_as(C.POINTER(C.c_int32)), 100000, C.byref(n), err, 512)
+    if rc:
+        raise ValueError(err.value.decode())
+    return ln[:n.value].tolist()
+
+
+def test_size_parsers(tmp_path):
+    p = str(tmp_path / "sf.size")
+    synth.write_sizefreq(p)
+    lens, cum = _size_freq(p)
+    ol, oc = synth.golden_sizefreq()
+    assert lens == ol and cum == oc and (lens, cum) == tuple(map(list, parsers.load_size_freq(p)))
+    import gzip
+    with gzip.open(p + ".gz", "wt") as f:
+        f.write(open(p).read())
+    assert _size_freq(p + ".gz") == (lens, cum)                         # igzstream reads gz or plain (fragSim.cpp:753)
+    with open(p, "w") as f:
+        f.write("40\t0.5\n41\t0.3\n")
+    with pytest.raises(ValueError, match="does not sum to 1"):
+        _size_freq(p)
+    with open(p, "w") as f:
+        f.write("40\n0\n-3\n77\n")
+    assert _size_list(p) == [40, 77]                                   # keep t >= 1 (fragSim.cpp:736)
+
+
+def test_fai_parse_and_build(tmp_path):
+    fa, fai = synth.make_genome(3, 4, 5000, width=50, lower_frac=0.1)
+    p = str(tmp_path / "g.fa")
+    open(p, "wb").write(fa)
+    synth.write_fai(p + ".fai", fai)
+    lib = api.load_library()
+    for from_fasta, path in ((0, p + ".fai"), (1, p)):
+        h = C.c_void_p(); n = C.c_int(); err = C.create_string_buffer(512)
+        assert lib.ggh_fai_load(path.encode(), from_fasta, C.byref(h), C.byref(n), err, 512) == 0, err.value
+        assert n.value == len(fai)
+        for i, e in enumerate(fai):
+            name = C.create_string_buffer(256); ln = C.c_int64(); off = C.c_uint64(); bl = C.c_int32(); ll = C.c_int32()
+            assert lib.ggh_fai_get(h, i, name, 256, C.byref(ln), C.byref(off), C.byref(bl), C.byref(ll)) == 0
+            assert (name.value.decode(), ln.value, off.value) == (e.name, e.len, e.offset)
+            if e.len > e.line_blen:
+                assert (bl.value, ll.value) == (e.line_blen, e.line_len)
+        lib.ggh_fai_free(h)
+
+
+def _apportion(n, comp, n_endo, cont_len, bact_w, seed):
+    lib = api.load_library()
+    tot = (C.c_uint64 * 3)(); e = (C.c_uint64 * 2)(); c = (C.c_uint64 * max(1, len(cont_len)))(); b = (C.c_uint64 * max(1, len(bact_w)))()
+    err = C.create_string_buffer(512)
+    rc = lib.ggh_apportion(C.c_uint64(n), C.c_double(comp[0]), C.c_double(comp[1]), C.c_double(comp[2]), n_endo,
+                           (C.c_uint64 * max(1, len(cont_len)))(*cont_len), len(cont_len), (C.c_double * max(1, len(bact_w)))(*bact_w), len(bact_w),
+                           C.c_uint64(seed), tot, e, c, b, err, 512)
+    if rc:
+        raise ValueError(err.value.decode())
+    return list(tot), list(e)[:n_endo], list(c)[:len(cont_len)], list(b)[:len(bact_w)]
+
+
+def test_apportion_follows_gargammel_pl():
+    """gargammel.pl:1256-1283 (int(n*comp), diploid coin flips), :1320-1349 (bacterial multinomial), :1421-1431 (contaminant by length)."""
+    w = np.random.default_rng(0).lognormal(size=10); w /= w.sum()
+    tot, e, c, b = _apportion(10_000_000, (0.9, 0.02, 0.08), 2, [30_000_000, 10_000_000], w.tolist(), 42)
+    assert tot == [int(10_000_000 * 0.08), int(10_000_000 * 0.02), int(10_000_000 * 0.9)]
+    assert sum(e) == tot[0] and sum(c) == tot[1] and sum(b) == tot[2]
+    assert abs(e[0] - tot[0] / 2) < 5 * (tot[0] / 4) ** 0.5                              # Binomial(nE, 1/2)
+    assert abs(c[0] / tot[1] - 0.75) < 5 * (0.75 * 0.25 / tot[1]) ** 0.5                 # by genome length
+    z = (np.array(b) - tot[2] * w) / np.sqrt(tot[2] * w * (1 - w))
+    assert np.abs(z).max() < 5
+    # deterministic in the seed, different across seeds
+    assert _apportion(10_000_000, (0.9, 0.02, 0.08), 2, [30_000_000, 10_000_000], w.tolist(), 42) == (tot, e, c, b)
+    assert _apportion(10_000_000, (0.9, 0.02, 0.08), 2, [30_000_000, 10_000_000], w.tolist(), 43)[1] != e
+    with pytest.raises(ValueError, match="sum up to 1"):
+        _apportion(1000, (0.5, 0.2, 0.2), 1, [10], [1.0], 1)
+    tot, e, c, b = _apportion(1000, (0, 0.08, 0.92), 1, [5000], [], 1)                   # README example composition
+    assert tot == [920, 80, 0] and e == [920] and c == [80]
+
+
+def test_binomial_sampler_moments():
+    lib = api.load_library()
+    lib.ggh_binomial.restype = C.c_uint64
+    for n, p in ((50, 0.1), (1000, 0.3), (10 ** 9, 0.37), (10 ** 6, 1e-7), (10 ** 7, 0.999)):
+        x = np.array([lib.ggh_binomial(C.c_uint64(n), C.c_double(p), C.c_uint64(7), C.c_uint64(k)) for k in range(4000)], dtype=np.float64)
+        m, s = n * p, (n * p * (1 - p)) ** 0.5
+        assert abs(x.mean() - m) < 5 * s / 4000 ** 0.5 + 1e-9
+        if s > 0.5:
+            assert abs(x.std() / s - 1) < 0.08
+        assert x.min() >= 0 and x.max() <= n

@@ -1,0 +1,79 @@
+"""Shared scaffolding of the parity tests: build the same state in a product Context and an oracle Context."""
+import numpy as np
+
+from gargammel_b200 import api, synth
+
+
+def tiny_genomes(seed=7, n_files=3):
+    """A few small multi-contig genomes with N runs, lower-case stretches and awkward line widths."""
+    out = []
+    for g in range(n_files):
+        fa, fai = synth.make_genome(seed * 100 + g, n_contigs=3 + g, total_len=6000 + 2500 * g, prefix="c%dx" % g,
+                                    width=[60, 37, 80][g % 3], n_frac=0.03, n_run=(5, 120), lower_frac=0.2)
+        out.append((fa, fai))
+    return out
+
+
+def configure(ctx, genomes, sizes="freq", damage="matrix", read_len=75, minlen=0, maxlen=1000, norev=False,
+              adapters=(api.DEFAULT_ADAPTER_F, api.DEFAULT_ADAPTER_S), fixed_len=40, clamp_last=True, matrix="single-"):
+    ids = [ctx.upload_genome(fa, fai) for fa, fai in genomes]
+    if sizes == "freq":
+        lens, cum = synth.golden_sizefreq()
+        ctx.set_sizes(api.SIZE_FREQ, lens, cum, minlen=minlen, maxlen=maxlen)
+    elif sizes == "list":
+        ctx.set_sizes(api.SIZE_LIST, synth.golden_sizelist(), minlen=minlen, maxlen=maxlen)
+    else:
+        ctx.set_sizes(api.SIZE_FIXED, fixed_len=fixed_len, minlen=minlen, maxlen=maxlen)
+    ctx.set_norev(norev)
+    set_damage(ctx, 0, damage, clamp_last=clamp_last, matrix=matrix)
+    ctx.set_adapters(adapters[0], adapters[1], read_len)
+    return ids
+
+
+def set_damage(ctx, slot, damage, clamp_last=True, matrix="single-"):
+    s5, s3 = synth.golden_matrix(matrix)
+    if damage == "matrix":
+        ctx.set_matrix(slot, s5, s3, clamp_last=clamp_last)
+    elif damage == "briggs":
+        ctx.set_briggs(slot, 0.03, 0.4, 0.01, 0.3)
+    elif damage == "single":
+        ctx.set_singledouble(slot, api.DMG_SINGLE, s5, s3)
+    elif damage == "double":
+        ctx.set_singledouble(slot, api.DMG_DOUBLE, s5, s3)
+    elif damage == "none":
+        ctx.clear_damage(slot)
+    else:
+        raise ValueError(damage)
+
+
+def plan3(ids, counts=(400, 300, 500), tags=("e1_0", "b1", "c1"), slots=(0, 0, -1)):
+    """endo / bact / cont ranges in the reference's output order with its tag grammar (gargammel.pl:1476,1600,1648)."""
+    out, first = [], 0
+    for g, n, t, s in zip(ids, counts, tags, slots):
+        out.append(api.Range(first, n, g, s, t))
+        first += n
+    return out
+
+
+def records(data: bytes):
+    lines = data.split(b"\n")
+    assert lines[-1] == b""
+    lines = lines[:-1]
+    assert len(lines) % 2 == 0
+    return [(lines[i], lines[i + 1]) for i in range(0, len(lines), 2)]
+
+
+def first_diff(a: bytes, b: bytes):
+    n = min(len(a), len(b))
+    aa, bb = np.frombuffer(a[:n], dtype=np.uint8), np.frombuffer(b[:n], dtype=np.uint8)
+    d = np.nonzero(aa != bb)[0]
+    if len(d) == 0:
+        return None if len(a) == len(b) else n
+    return int(d[0])
+
+
+def assert_same(a: bytes, b: bytes, what=""):
+    i = first_diff(a, b)
+    if i is not None:
+        lo = max(0, i - 60)
+        raise AssertionError("%s: outputs differ at byte %d (lens %d vs %d)\n cuda  : %r\n oracle: %r" % (what, i, len(a), len(b), a[lo:i + 60], b[lo:i + 60]))
