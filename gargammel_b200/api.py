@@ -115,14 +115,23 @@ class Context:
     def set_seed(self, seed):
         self._ck(self._f("ctx_set_seed")(self._h, C.c_uint64(seed)))
 
-    def upload_genome(self, fasta: bytes, fai):
+    def genome_clear(self):
+        self._ck(self._f("genome_clear")(self._h))
+
+    def upload_genome(self, fasta, fai):
+        """fasta: bytes, or any object with data_ptr()/numel() (a pinned torch uint8 tensor), or a numpy uint8 array."""
         arr = (_Fai * len(fai))()
         for i, e in enumerate(fai):
             arr[i].name = e.name.encode()
             arr[i].len, arr[i].offset, arr[i].line_blen, arr[i].line_len = e.len, e.offset, e.line_blen, e.line_len
         gid = C.c_int(-1)
-        buf = (C.c_uint8 * len(fasta)).from_buffer_copy(fasta) if len(fasta) else (C.c_uint8 * 1)()
-        self._ck(self._f("genome_upload")(self._h, buf, C.c_size_t(len(fasta)), arr, C.c_int(len(fai)), C.byref(gid)))
+        if hasattr(fasta, "data_ptr"):
+            ptr, n = C.c_void_p(fasta.data_ptr()), int(fasta.numel())
+        elif hasattr(fasta, "ctypes"):
+            ptr, n = C.c_void_p(fasta.ctypes.data), int(fasta.size)
+        else:
+            ptr, n = C.cast(C.c_char_p(fasta), C.c_void_p), len(fasta)
+        self._ck(self._f("genome_upload")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.byref(gid)))
         return gid.value
 
     def genome_fetch(self, genome, chr_index, start, length):
@@ -181,6 +190,14 @@ class Context:
             return buf.raw[:n.value], _info(o)
         self._ck(self._f("run_fused")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.byref(o)))
         return (self._fetch(o) if fetch else None), _info(o)
+
+    def run_fused_into(self, first, count, emit, host_ptr, cap):
+        """run + D2H into caller memory (e.g. a pinned torch tensor's data_ptr()); returns RunInfo."""
+        o = _Out()
+        self._ck(self._f("run_fused")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.byref(o)))
+        n = C.c_size_t(0)
+        self._ck(self._f("out_fetch")(self._h, C.byref(o), C.c_void_p(host_ptr), C.c_size_t(cap), C.byref(n)))
+        return _info(o)
 
     def _fetch(self, o):
         buf = C.create_string_buffer(max(int(o.bytes), 1))

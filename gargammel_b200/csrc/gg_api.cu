@@ -360,6 +360,14 @@ int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_e
     return GG_OK;
 }
 int gg_genome_count(gg_ctx* ctx) { return ctx ? (int)ctx->genomes.size() : 0; }
+int gg_genome_clear(gg_ctx* ctx) {
+    if (!ctx) return GG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); }
+    ctx->genomes.clear(); ctx->plan.clear(); ctx->ctab_dirty = true; ctx->plan_dirty = true;
+    return GG_OK;
+}
 
 int gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len, char* dst) {
     if (!ctx || genome_id < 0 || genome_id >= (int)ctx->genomes.size() || !dst || len < 0) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_fetch: bad arguments") : GG_ERR_ARG;
@@ -433,24 +441,36 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_MATRIX; H.rows5 = rows5; H.rows3 = rows3; H.clamp_last = clamp_last ? 1 : 0;
-    H.thr.assign((size_t)(rows5 + rows3) * 4, make_uint4(0, 0, 0, 0));
-    for (int r = 0; r < rows5 + rows3; r++) {
-        const double* row = r < rows5 ? sub5 + (size_t)r * 12 : sub3 + (size_t)(r - rows5) * 12;
-        for (int b = 0; b < 4; b++) {
-            // cumulative table exactly as deamSim.cpp:1797-1837 builds it (same operation order, fp64)
-            double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
-            double sum = 0.0;
-            for (int a = 0; a < 4; a++) {
-                if (a == b) continue;
-                const int idx = a < b ? b * 3 + a : b * 3 + (a - 1);
-                sum += row[idx]; _sumProb[a + 1] = row[idx];
+    // device layout: rows5 real rows + sentinel, rows3 real rows + sentinel.  The sentinel is the last row when clamping
+    // (deamSim.cpp:1811-1813) or an identity row (base unchanged) with -last (deamSim.cpp:1814-1816).
+    H.thr.assign((size_t)(rows5 + rows3 + 2) * 4, make_uint4(0, 0, 0, 0));
+    for (int e = 0; e < 2; e++) {
+        const double* sub = e == 0 ? sub5 : sub3; const int rows = e == 0 ? rows5 : rows3; const size_t base = e == 0 ? 0 : (size_t)rows5 + 1;
+        for (int r = 0; r <= rows; r++) {
+            const double* row = sub + (size_t)std::min(r, rows - 1) * 12;
+            for (int b = 0; b < 4; b++) {
+                uint32_t k[4];
+                if (r == rows && !H.clamp_last) {            // identity: u >= K for every a < b, u < K for a >= b
+                    for (int a = 0; a < 4; a++) k[a] = a < b ? 0u : 2147483648u;
+                } else {
+                    // cumulative table exactly as deamSim.cpp:1797-1837 builds it (same operation order, fp64)
+                    double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
+                    double sum = 0.0;
+                    for (int a = 0; a < 4; a++) {
+                        if (a == b) continue;
+                        const int idx = a < b ? b * 3 + a : b * 3 + (a - 1);
+                        sum += row[idx]; _sumProb[a + 1] = row[idx];
+                    }
+                    _sumProb[b + 1] = 1.0 - sum;
+                    double s = 0;
+                    for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }
+                    uint32_t prev = 0;
+                    for (int a = 0; a < 4; a++) { uint32_t t = thr_le(sumProb[a + 1]); if (t < prev) t = prev; k[a] = t; prev = t; }
+                    // the device picks (u>=K1)+(u>=K2)+(u>=K3): exact iff the last cumulative value covers every u31
+                    if (k[3] != 2147483648u) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: cumulative probabilities of a row do not reach 1");
+                }
+                H.thr[(base + (size_t)r) * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
             }
-            _sumProb[b + 1] = 1.0 - sum;
-            double s = 0;
-            for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }
-            uint32_t k[4], prev = 0;
-            for (int a = 0; a < 4; a++) { uint32_t t = thr_le(sumProb[a + 1]); if (t < prev) t = prev; k[a] = t; prev = t; }
-            H.thr[(size_t)r * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
         }
     }
     return upload_vec(ctx, H.d_thr, H.thr);

@@ -54,14 +54,18 @@ __device__ __forceinline__ uint32_t revcomp16(uint32_t x) {
     return ~y;
 }
 // mask with the low n 2-bit fields set, n in [0,16]
-__device__ __forceinline__ uint32_t lowfields(int n) { return n >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u); }
+// (PTX shl.b32 clamps shift amounts above 31, so n == 16 gives (1<<32)-1 == 0xFFFFFFFF without a compare)
+__device__ __forceinline__ uint32_t lowfields(int n) {
+    uint32_t r; asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(2 * n)); return r - 1u;
+}
 
 // ---------------------------------------------------------------- damage model tables (device view)
 struct DamageDev {
     int mode;            // gg_damage_mode
     int rows5, rows3;    // matrix / single-double rows
     int clamp_last;      // matrix: clamp to last row (default) or skip (-last)
-    // MATRIX: thr[(r*4+b)] = {K1,K2,K3,K4}: new base = first a with u31 < K[a+1], else unchanged; rows5 entries then rows3
+    // MATRIX: thr[(r*4+b)] = {K1,K2,K3,K4}: new base = first a with u31 < K[a+1] (K4 == 2^31 always, checked on the host).
+    // Layout: rows5 real 5' rows, one sentinel row (= last row when clamping, identity when -last), rows3 real 3' rows, sentinel.
     const uint4* thr;
     // SINGLE/DOUBLE: sd5[r] (C->T 5'), sd3[r] (C->T single / G->A double)
     const uint32_t* sd5; const uint32_t* sd3;
@@ -78,18 +82,10 @@ __device__ __forceinline__ int first_below(const uint32_t* __restrict__ thr, int
 
 // -matfile, one base (deamSim.cpp:1794-1930): i = position, L = fragment length, b = code, x = raw Philox word
 __device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x) {
-    int r;
-    if (i < (L >> 1)) {
-        r = i;
-        if (r >= D.rows5) { if (!D.clamp_last) return b; r = D.rows5 - 1; }
-    } else {
-        r = L - 1 - i;
-        if (r >= D.rows3) { if (!D.clamp_last) return b; r = D.rows3 - 1; }
-        r += D.rows5;
-    }
+    const int r = (i < (L >> 1)) ? min(i, D.rows5) : D.rows5 + 1 + min(L - 1 - i, D.rows3);   // sentinel rows absorb the clamp / -last cases
     const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
     const uint32_t u = x >> 1;
-    return u < T.x ? 0u : u < T.y ? 1u : u < T.z ? 2u : u < T.w ? 3u : b;
+    return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z);
 }
 // Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
 struct BriggsHdr { int o5, o3, nick; };

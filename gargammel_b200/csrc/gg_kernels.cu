@@ -114,8 +114,8 @@ __device__ __forceinline__ uint32_t fetch_run_glob(const uint32_t* __restrict__ 
 }
 // group-relative mask of [lo,hi) clipped to [0,16)
 __device__ __forceinline__ uint32_t run_mask(int lo, int hi) {
-    lo = max(lo, 0); hi = min(hi, 16);
-    return hi > lo ? (lowfields(hi) & ~lowfields(lo)) : 0u;
+    lo = min(max(lo, 0), 16); hi = min(max(hi, 0), 16);
+    return lowfields(hi) & ~lowfields(lo);          // empty when hi <= lo
 }
 
 // 16 output codes for positions j0..j0+15 of sequence line `line` of one fragment
@@ -148,6 +148,7 @@ __device__ __forceinline__ uint32_t line_codes(const FusedParams& P, const uint3
             const int nS = min(mAd, P.ad.lenS);             // adapter bases
             const int nP = mAd - nS;                        // pad bases
             // [RL, RL+nP): complement of padR reversed
+            if (nP > 0)
             for (int t = max(RL - j0, 0); t < min(RL + nP - j0, 16); t++) {
                 const int q = nP - 1 - (j0 + t - RL);
                 const uint32_t c = (rng_word(P.key, id, ST_ADPT_R, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
@@ -181,7 +182,10 @@ __device__ __forceinline__ uint32_t line_codes(const FusedParams& P, const uint3
 }
 
 __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) {
-    for (int k = nd - 1; k >= 0; k--) { const uint64_t q = v / 10ull; p[k] = (uint8_t)('0' + (uint32_t)(v - q * 10ull)); v = q; }
+    int k = nd - 1;
+    for (; v > 0xFFFFFFFFull; k--) { const uint64_t q = v / 10ull; p[k] = (uint8_t)('0' + (uint32_t)(v - q * 10ull)); v = q; }
+    uint32_t w = (uint32_t)v;
+    for (; k >= 0; k--) { const uint32_t q = w / 10u; p[k] = (uint8_t)('0' + (w - q * 10u)); w = q; }
     return p + nd;
 }
 
@@ -423,8 +427,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
             if (jlo == j0 && jhi == j0 + 16) {
                 *(uint4*)dst = a;
             } else {
+                // boundary group: merge under a byte mask.  Headers were written before the barrier; two sequence lines are
+                // always >= 12 bytes apart (newline + a header), so no other thread touches these 4-byte words in this pass.
+                const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
+                uint32_t* d4 = (uint32_t*)dst;
                 const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-                for (int t = jlo - j0; t < jhi - j0; t++) dst[t] = (uint8_t)(aw[t >> 2] >> (8 * (t & 3)));
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int lo = min(max(t0 - 4 * w, 0), 4), hi = min(max(t1 - 4 * w, 0), 4);
+                    uint32_t mh, ml;
+                    asm("shl.b32 %0, 1, %1;" : "=r"(mh) : "r"(8 * hi));
+                    asm("shl.b32 %0, 1, %1;" : "=r"(ml) : "r"(8 * lo));
+                    const uint32_t m = (mh - 1u) & ~(ml - 1u);
+                    if (m == 0xFFFFFFFFu) d4[w] = aw[w];
+                    else if (m) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                }
             }
         }
 

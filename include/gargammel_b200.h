@@ -121,6 +121,8 @@ void* gg_ctx_stream(gg_ctx* ctx);
 int  gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n,
                       const gg_fai_entry* fai, int n_chr, int* genome_id_out);
 int  gg_genome_count(gg_ctx* ctx);
+/* drop every uploaded genome and the plan (tables stay) */
+int  gg_genome_clear(gg_ctx* ctx);
 /* debug/parity helper: unpack `len` bases of contig `chr` (index in the caller's fai order) from `start` into ASCII (N for masked) */
 int  gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len, char* dst);
 
