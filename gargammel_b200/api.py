@@ -40,7 +40,8 @@ class _Out(C.Structure):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgargammel_b200.so")
+    # GG_LIB selects an experimental build of the same library (tuning only)
+    return os.environ.get("GG_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgargammel_b200.so")
 
 
 _LIB = None

@@ -117,11 +117,12 @@ template <typename T> int upload_vec(gg_ctx* ctx, DBuf& b, const std::vector<T>&
     return GG_OK;
 }
 
+// 2-bit packing with one guard word in front (device pointers are taken at word 1)
 std::vector<uint32_t> pack2(const std::string& s) {
-    std::vector<uint32_t> w((s.size() + 15) / 16, 0u);
+    std::vector<uint32_t> w(1 + (s.size() + 15) / 16, 0u);
     for (size_t i = 0; i < s.size(); i++) {
         uint32_t c = s[i] == 'A' ? 0u : s[i] == 'C' ? 1u : s[i] == 'G' ? 2u : 3u;
-        w[i >> 4] |= c << (2 * (i & 15));
+        w[1 + (i >> 4)] |= c << (2 * (i & 15));
     }
     return w;
 }
@@ -235,18 +236,23 @@ void plan_bounds(const gg_ctx* ctx, int emit, int Lmax, int* hdr_max, uint64_t* 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // shared-memory carve-up for F fragments per tile
-SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups) {
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words) {
     SmemLayout s; int o = 0;
     s.lut = o; o += 1024;
     o += 16;                                   // readable slack before staging
-    s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 32;
+    s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
     s.gpos = o; o += 8 * F;
+    s.idx = o; o += 8 * F;
+    s.ci = o; o += 4 * F;
     s.meta = o; o += 4 * F;
     s.recoff = o; o += 4 * F;
+    o += 4;                                    // guard word in front of the damaged-fragment words
     s.dwords = o; o += 4 * (F * max_chunks + 4);
+    s.lwords = o; o += 4 * (F * line_words + 4);
     s.hdr = o; o += 2 * F;
     s.cstart = o; o += 2 * F;
     s.gstart = o; o += 2 * F;
+    s.rg = o; o += 2 * F;
     s.cmap = o; o += F * max_chunks;
     s.gmap = o; o += F * max_groups;
     s.total = align_up(o, 16);
@@ -528,6 +534,7 @@ int gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int re
 
 int gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n) {
     if (!ctx || n < 0 || (n > 0 && !ranges)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_plan_set: bad arguments") : GG_ERR_ARG;
+    if (n > 65535) return ctx->fail(GG_ERR_ARG, "gg_plan_set: at most 65535 ranges");
     uint64_t next = n ? ranges[0].first_id : 0;
     for (int i = 0; i < n; i++) {
         if (ranges[i].first_id != next) return ctx->fail(GG_ERR_ARG, "gg_plan_set: ranges must be contiguous and ascending in fragment id");
@@ -569,6 +576,16 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int hdr_max; uint64_t rec_max; plan_bounds(ctx, emit, Lmax, &hdr_max, &rec_max);
     const int Smax = emit_seqlen(emit, Lmax, ctx->read_len);
     const int max_chunks = (Lmax + 15) / 16, max_groups = emit_lines(emit) * ((Smax + 15) / 16 + 1);
+    const int line_words = emit >= GG_EMIT_STDOUT4 ? emit_lines(emit) * ((Smax + 15) / 16 + 2) : 0;   // packed line images (adptSim dialects)
+    // whole-group stores need >= 13 header bytes between two sequence lines: name + tag + 9 >= 13
+    size_t min_name_tag = 1000;
+    for (size_t i = 0; i < ctx->plan.size(); i++) {
+        size_t nm = 1000;
+        const HostGenome& HG = ctx->genomes[ctx->plan[i].genome];
+        for (size_t c = 0; c < HG.contigs.size(); c++) nm = std::min(nm, HG.contigs[c].name.size());
+        min_name_tag = std::min(min_name_tag, nm + strnlen(ctx->plan[i].tag, sizeof(ctx->plan[i].tag) - 1));
+    }
+    const int fast_boundary = (min_name_tag >= 4 && !getenv("GG_FUSED_NOFAST")) ? 1 : 0;
 
     // fragments per tile: the largest F <= 256 whose tile fits the shared memory of `ctas` co-resident CTAs
     const size_t sm_budget = 227 * 1024;
@@ -578,12 +595,12 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
         const size_t per_cta = std::min(sm_budget / (size_t)t - 1024, ctx->smem_optin);
         int f = envF ? atoi(envF) : FUSED_THREADS;
         f = std::max(1, std::min(f, FUSED_THREADS));
-        while (f >= 1 && (size_t)make_layout(f, rec_max, max_chunks, max_groups).total > per_cta) f = (f > 32) ? f - 16 : f - 1;
+        while (f >= 1 && (size_t)make_layout(f, rec_max, max_chunks, max_groups, line_words).total > per_cta) f = (f > 32) ? f - 16 : f - 1;
         if (f >= (t > 1 ? 128 : 1)) { F = f; ctas = t; }
     }
     if (F < 1) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
     while ((uint64_t)F * (uint64_t)max_chunks > 60000ull || (uint64_t)F * (uint64_t)max_groups > 60000ull) F--;
-    const SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups);
+    const SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words);
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
     const int n_tiles = (int)n_tiles64;
@@ -594,7 +611,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(ctx->d_ticket_stats.ensure(256));
 
     FusedParams P; memset(&P, 0, sizeof P);
-    P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev;
+    P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary;
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();
@@ -603,7 +620,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.size_mode = ctx->size_mode; P.fixed_len = ctx->fixed_len; P.minlen = ctx->minlen; P.maxlen = ctx->maxlen; P.n_sizes = (int)ctx->size_len.size();
     P.size_thr = ctx->d_size_thr.as<uint32_t>(); P.size_len = ctx->d_size_len.as<int32_t>();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
-    P.ad.adF2 = ctx->d_adF2.as<uint32_t>(); P.ad.adS2 = ctx->d_adS2.as<uint32_t>(); P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>();
+    P.ad.adF2 = ctx->d_adF2.as<uint32_t>() + 1; P.ad.adS2 = ctx->d_adS2.as<uint32_t>() + 1; P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>() + 1;
     P.ad.lenF = (int)ctx->adF.size(); P.ad.lenS = (int)ctx->adS.size(); P.ad.read_len = ctx->read_len;
     P.out = ctx->d_out.as<uint8_t>(); P.out_cap = out_cap;
     P.tile_state = ctx->d_tile_state.as<unsigned long long>();

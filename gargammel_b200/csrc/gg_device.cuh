@@ -87,6 +87,17 @@ __device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, i
     const uint32_t u = x >> 1;
     return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z);
 }
+// same, returning the new base already placed in its 2-bit field: (new base) * unit with unit = 1 << 2j
+__device__ __forceinline__ uint32_t dmg_matrix_base_shifted(const DamageDev& D, int i, int L, uint32_t b, uint32_t x, uint32_t unit) {
+    const int r = (i < (L >> 1)) ? min(i, D.rows5) : D.rows5 + 1 + min(L - 1 - i, D.rows3);
+    const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
+    const uint32_t u = x >> 1;
+    uint32_t v = 0;
+    if (u >= T.x) v += unit;
+    if (u >= T.y) v += unit;
+    if (u >= T.z) v += unit;
+    return v;
+}
 // Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
 struct BriggsHdr { int o5, o3, nick; };
 __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const uint4& h) {

@@ -105,80 +105,59 @@ __device__ __forceinline__ int emit_seqlen(int emit, int L, int RL) {
 // "_r" suffix on line `line`?   RR: line 0; STDOUT4: line 1  (adptSim.cpp:286)
 __device__ __forceinline__ int emit_suffix(int emit, int line) { return (emit == 6 || (emit == 2 && line == 1)) ? 2 : 0; }
 
-// positions p..p+15 of a packed smem source; positions < 0 read as garbage-free zeros
-__device__ __forceinline__ uint32_t fetch_run_smem(const uint32_t* src, int p) {
-    return p >= 0 ? fetch16_smem(src, p) : (fetch16_smem(src, 0) << (2 * (-p)));
-}
-__device__ __forceinline__ uint32_t fetch_run_glob(const uint32_t* __restrict__ src, int p) {
-    return p >= 0 ? fetch16(src, p) : (fetch16(src, 0) << (2 * (-p)));
-}
+// positions p..p+15 of a packed source, p >= -16.  Every source has one readable guard word in front of it, so a
+// window that starts before the source simply carries garbage in fields that the caller's run mask removes.
+__device__ __forceinline__ uint32_t fetch_run_smem(const uint32_t* src, int p) { return fetch16_smem(src - 1, p + 16); }
+__device__ __forceinline__ uint32_t fetch_run_glob(const uint32_t* __restrict__ src, int p) { return fetch16(src - 1, (int64_t)(p + 16)); }
 // group-relative mask of [lo,hi) clipped to [0,16)
 __device__ __forceinline__ uint32_t run_mask(int lo, int hi) {
     lo = min(max(lo, 0), 16); hi = min(max(hi, 0), 16);
     return lowfields(hi) & ~lowfields(lo);          // empty when hi <= lo
 }
 
-// 16 output codes for positions j0..j0+15 of sequence line `line` of one fragment
-// (adptSim.cpp:288-322,396-411 restated as runs over 2-bit sources; D = damaged fragment in smem)
-__device__ __forceinline__ uint32_t line_codes(const FusedParams& P, const uint32_t* D, int L, int line, int j0,
-                                               uint64_t id) {
-    const int emit = P.emit, RL = P.ad.read_len;
-    if (emit <= 1) return fetch_run_smem(D, j0);                           // FRAG / DEAM: the fragment itself
-    uint32_t out = 0;
-    const bool second = (emit == 6) || (emit == 2 && line == 1);           // the reverse read line (RR, STDOUT4 line 1)
-    if (!second) {
-        // forward read S1 = (frag + adapterF)[0:RL] + pad      adptSim.cpp:298-310
-        const int nD = min(L, RL);
-        uint32_t m = run_mask(0 - j0, nD - j0);
-        if (m) out |= fetch_run_smem(D, j0) & m;
-        const int nA = min(max(RL - L, 0), P.ad.lenF);
-        m = run_mask(L - j0, L + nA - j0);
-        if (m) out |= fetch_run_glob(P.ad.adF2, j0 - L) & m;
-        const int padStart = L + nA;                                        // random tail, adptSim.cpp:307-310
-        if (padStart < RL) {
-            for (int t = max(padStart - j0, 0); t < min(RL - j0, 16); t++) {
-                const int q = j0 + t - padStart;
-                const uint32_t c = (rng_word(P.key, id, ST_ADPT_F, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
-                out |= c << (2 * t);
-            }
-        }
-        if (emit == 4) {
-            // ARTP second half = revcomp(SR), positions RL..2RL-1      adptSim.cpp:404-405
-            const int mAd = max(RL - L, 0);                 // adapter+pad bases of SR
-            const int nS = min(mAd, P.ad.lenS);             // adapter bases
-            const int nP = mAd - nS;                        // pad bases
-            // [RL, RL+nP): complement of padR reversed
-            if (nP > 0)
-            for (int t = max(RL - j0, 0); t < min(RL + nP - j0, 16); t++) {
-                const int q = nP - 1 - (j0 + t - RL);
-                const uint32_t c = (rng_word(P.key, id, ST_ADPT_R, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
-                out |= (3u - c) << (2 * t);
-            }
-            // [RL+nP, RL+mAd): suffix of revcomp(adapterS)
-            m = run_mask(RL + nP - j0, RL + mAd - j0);
-            if (m) out |= fetch_run_glob(P.ad.rcS2, j0 - (RL + nP) + (P.ad.lenS - nS)) & m;
-            // [RL+mAd, 2RL): fragment forward from max(L-RL,0)
-            m = run_mask(RL + mAd - j0, 2 * RL - j0);
-            if (m) out |= fetch_run_smem(D, j0 - (RL + mAd) + max(L - RL, 0)) & m;
-        }
-    } else {
-        // reverse read SR = (revcomp(frag) + adapterS)[0:RL] + pad      adptSim.cpp:313-322
-        const int nD = min(L, RL);
-        uint32_t m = run_mask(0 - j0, nD - j0);
-        if (m) out |= revcomp16(fetch_run_smem(D, L - 16 - j0)) & m;
-        const int nA = min(max(RL - L, 0), P.ad.lenS);
-        m = run_mask(L - j0, L + nA - j0);
-        if (m) out |= fetch_run_glob(P.ad.adS2, j0 - L) & m;
-        const int padStart = L + nA;
-        if (padStart < RL) {
-            for (int t = max(padStart - j0, 0); t < min(RL - j0, 16); t++) {
-                const int q = j0 + t - padStart;
-                const uint32_t c = (rng_word(P.key, id, ST_ADPT_R, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
-                out |= c << (2 * t);
-            }
-        }
+// ---- line image: the 2-bit packed sequence line(s) of one record, assembled once per fragment by its owner thread
+// (adptSim.cpp:288-322,396-411 restated as a concatenation of runs over 2-bit sources; D = damaged fragment in smem)
+struct BitAppender {
+    uint32_t* out; uint64_t acc; int fill;
+    __device__ __forceinline__ void put(uint32_t x, int n) {        // n fields (1..16); fields of x above n are zero
+        acc |= (uint64_t)x << fill; fill += 2 * n;
+        if (fill >= 32) { *out++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
     }
-    return out;
+    __device__ __forceinline__ void flush() { if (fill > 0) *out++ = (uint32_t)acc; }
+};
+__device__ __forceinline__ void put_run_smem(BitAppender& A, const uint32_t* src, int start, int len) {
+    for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(fetch_run_smem(src, start + o) & lowfields(n), n); }
+}
+__device__ __forceinline__ void put_run_glob(BitAppender& A, const uint32_t* __restrict__ src, int start, int len) {
+    for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(fetch_run_glob(src, start + o) & lowfields(n), n); }
+}
+// first `len` bases of revcomp(D[0:L])
+__device__ __forceinline__ void put_rc_run(BitAppender& A, const uint32_t* D, int L, int len) {
+    for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(revcomp16(fetch_run_smem(D, L - 16 - o)) & lowfields(n), n); }
+}
+__device__ __forceinline__ uint32_t pad_base(const FusedParams& P, uint64_t id, uint32_t stream, int q) {   // randomDNASeq base q
+    return (rng_word(P.key, id, stream, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
+}
+// forward read S1 = (frag + adapterF)[0:RL] + random tail      adptSim.cpp:298-310
+__device__ __forceinline__ void put_forward_read(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+    const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenF);
+    put_run_smem(A, D, 0, nD);
+    put_run_glob(A, P.ad.adF2, 0, nA);
+    for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_F, q), 1);
+}
+// reverse read SR = (revcomp(frag) + adapterS)[0:RL] + random tail      adptSim.cpp:289,313-322
+__device__ __forceinline__ void put_reverse_read(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+    const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenS);
+    put_rc_run(A, D, L, nD);
+    put_run_glob(A, P.ad.adS2, 0, nA);
+    for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_R, q), 1);
+}
+// revcomp(SR): complemented random tail reversed, suffix of revcomp(adapterS), the last min(L,RL) fragment bases   adptSim.cpp:404
+__device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+    const int RL = P.ad.read_len, nD = min(L, RL), mAd = RL - nD, nS = min(mAd, P.ad.lenS), nP = mAd - nS;
+    for (int t = 0; t < nP; t++) A.put(3u - pad_base(P, id, ST_ADPT_R, nP - 1 - t), 1);
+    put_run_glob(A, P.ad.rcS2, P.ad.lenS - nS, nS);
+    put_run_smem(A, D, L - nD, nD);
 }
 
 __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) {
@@ -189,7 +168,13 @@ __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) 
     return p + nd;
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constant__ FusedParams P) {
+#ifndef GG_FUSED_MINB
+#define GG_FUSED_MINB 3
+#endif
+// FASTB: every header is >= 13 bytes, so a partial 16-byte group of one sequence line can never reach another line's
+// sequence bytes: groups are stored whole and the headers/newlines are written afterwards (no read-modify-write).
+template <bool FASTB>
+__global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t*  const s_stage  = smem + P.sm.stage;
     uint64_t* const s_gpos   = (uint64_t*)(smem + P.sm.gpos);
@@ -198,13 +183,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
     uint16_t* const s_hdr    = (uint16_t*)(smem + P.sm.hdr);
     uint16_t* const s_cstart = (uint16_t*)(smem + P.sm.cstart);
     uint16_t* const s_gstart = (uint16_t*)(smem + P.sm.gstart);
+    uint64_t* const s_idx    = (uint64_t*)(smem + P.sm.idx);
+    uint32_t* const s_ci     = (uint32_t*)(smem + P.sm.ci);
+    uint16_t* const s_rg     = (uint16_t*)(smem + P.sm.rg);
     uint32_t* const s_dwords = (uint32_t*)(smem + P.sm.dwords);
     uint8_t*  const s_cmap   = smem + P.sm.cmap;
     uint8_t*  const s_gmap   = smem + P.sm.gmap;
+    uint32_t* const s_lwords = (uint32_t*)(smem + P.sm.lwords);   // line images (adptSim dialects only)
     uint32_t* const s_lut    = (uint32_t*)(smem + P.sm.lut);     // 256 x 4 ASCII bytes
     __shared__ unsigned long long s_warp_tot[FUSED_THREADS / 32];
     __shared__ unsigned long long s_excl;
     __shared__ int s_tile;
+    __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int emit = P.emit, RL = P.ad.read_len;
@@ -217,6 +207,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
         for (int k = 0; k < 4; k++) w |= (uint32_t)code2ascii((v >> (2 * k)) & 3) << (8 * k);
         s_lut[v] = w;
     }
+    if (P.size_mode == 2)
+        for (int q = tid; q < 1024; q += FUSED_THREADS) s_guide[q] = (uint16_t)first_below(P.size_thr, P.n_sizes, (uint32_t)q << 21);
     unsigned long long my_attempts = 0, my_gather = 0;
     uint32_t my_err = 0;
 
@@ -229,9 +221,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
         const int nf = (int)min((uint64_t)P.F, P.count - tile_first);
 
         // ------------------------------------------------------------ pass A: sample (thread per fragment)
-        uint64_t idx = 0; int L = 0, ci = 0, hdr = 0, tag_len = 0; uint32_t plus = 1; const char* tag = nullptr;
         unsigned long long pk = 0;
         if (tid < nf) {
+            uint64_t idx = 0; int L = 0, ci = 0, hdr = 0, tag_len = 0; uint32_t plus = 1;
             const uint64_t id = P.first + tile_first + (uint64_t)tid;
             int lo = 0, hi = P.n_ranges - 1;                    // last range with first_id <= id
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.ranges[mid].first_id <= id) lo = mid; else hi = mid - 1; }
@@ -246,7 +238,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
                 if (P.size_mode == 0) L = P.fixed_len;
                 else if (P.size_mode == 1) L = __ldg(P.size_len + __umulhi(x.x, (uint32_t)P.n_sizes));
                 else {
-                    int k = first_below(P.size_thr, P.n_sizes, x.x >> 1);
+                    const uint32_t u = x.x >> 1;
+                    int k = s_guide[u >> 21];                                       // first i with p <= cProb[i] (fragSim.cpp:162-171)
+                    while (k < P.n_sizes && u >= __ldg(P.size_thr + k)) k++;
                     if (k == P.n_sizes) k = (int)(((uint64_t)(x.y >> 1) * (uint64_t)P.n_sizes) >> 31);   // fragSim.cpp:176
                     L = __ldg(P.size_len + k);
                 }
@@ -279,7 +273,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
             }
             if (!ok) { my_err |= ERRF_GIVEUP; L = 0; idx = 0; }
             my_gather += (unsigned long long)((L + 3) / 4 + (L + 7) / 8);
-            tag = rg->tag; tag_len = rg->tag_len;
+            tag_len = rg->tag_len;
             const int nlen = __ldg(P.ctab.name_len + ci);
             hdr = 1 + nlen + 3 + ndigits(idx) + 1 + ndigits(idx + (uint64_t)L) + 1 + ndigits((uint64_t)L) + tag_len;
             const int S = emit_seqlen(emit, L, RL);
@@ -291,6 +285,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
             s_gpos[tid] = gpos;
             s_meta[tid] = META(L, plus, rg->slot, rg->genome);
             s_hdr[tid] = (uint16_t)hdr;
+            s_idx[tid] = idx; s_ci[tid] = (uint32_t)ci; s_rg[tid] = (uint16_t)lo;   // parked for pass B2 (keeps registers free in passes C/D)
         }
         // block exclusive scan of pk
         unsigned long long incl = warp_scan_u64(pk, lane);
@@ -307,145 +302,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
         }
         const bool overflow = T > (uint32_t)P.sm.stage_bytes;    // host sizing bug guard: never write past staging
 
-        // ------------------------------------------------------------ pass B: headers + work maps (owner thread)
+        // ------------------------------------------------------------ pass B1: work maps (owner thread)
         if (tid < nf && !overflow) {
             const uint32_t roff = PK_BYTES(excl), c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
             s_recoff[tid] = roff; s_cstart[tid] = (uint16_t)c0; s_gstart[tid] = (uint16_t)g0;
             const uint32_t nch = PK_CHUNKS(pk), ngr = PK_GROUPS(pk);
             for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)tid;
             for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)tid;
-            const int S = emit_seqlen(emit, L, RL);
-            const char* nm = P.ctab.names + __ldg(P.ctab.name_off + ci);
-            const int nlen = __ldg(P.ctab.name_len + ci);
-            uint8_t* p = s_stage + roff;
-            for (int ln = 0; ln < nlines; ln++) {
-                // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
-                *p++ = '>';
-                for (int k = 0; k < nlen; k++) *p++ = (uint8_t)__ldg(nm + k);
-                *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
-                p = put_decimal(p, idx, ndigits(idx)); *p++ = ':';
-                p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L)); *p++ = ':';
-                p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L));
-                for (int k = 0; k < tag_len; k++) *p++ = (uint8_t)tag[k];
-                if (emit_suffix(emit, ln)) { *p++ = '_'; *p++ = 'r'; }
-                *p++ = '\n';
-                p += S;
-                *p++ = '\n';
-            }
         }
         __syncthreads();
 
-        // ------------------------------------------------------------ pass C: gather + damage (thread per 16-base chunk)
-        if (!overflow)
-        for (uint32_t e = tid; e < n_chunks; e += FUSED_THREADS) {
-            const int f = s_cmap[e];
-            const int k = (int)e - (int)s_cstart[f];
-            const uint32_t meta = s_meta[f];
-            const int fl = META_L(meta), slot = META_SLOT(meta);
-            const uint64_t gp = s_gpos[f];
-            const uint32_t* seq2 = P.genomes[META_GEN(meta)].seq2;
-            const int n = min(16, fl - 16 * k);
-            uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
-                                         : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
-            W &= lowfields(n);
-            if (slot >= 0 && emit != 0) {
-                const DamageDev& D = P.dmg[slot];
-                const uint64_t id = P.first + tile_first + (uint64_t)f;
-                if (D.mode == 1) {                                   // -matfile: one uniform per base (deamSim.cpp:1847,1911)
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                if (j < n) Wn |= dmg_matrix_base(D, 16 * k + j, fl, (W >> (2 * j)) & 3u, pick(x, jj)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                } else if (D.mode == 2) {                            // Briggs: header block 0, per-base word 4+i
-                    const BriggsHdr B = dmg_briggs_hdr(D, rng_block(P.key, id, 0u, ST_DEAM));
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                if (j < n) Wn |= dmg_briggs_base(D, B, 16 * k + j, fl, (W >> (2 * j)) & 3u, pick(x, jj)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                } else if (D.mode == 3 || D.mode == 4) {             // single / double: two passes, two streams
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x1 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
-                            const uint4 x2 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM2);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                if (j < n) Wn |= dmg_sd_base(D, 16 * k + j, fl, (W >> (2 * j)) & 3u, pick(x1, jj), pick(x2, jj)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                }
-            }
-            s_dwords[e] = W;
-        }
-        __syncthreads();
-
-        // ------------------------------------------------------------ pass D: adapters + ASCII (thread per 16-byte staging group)
-        if (!overflow)
-        for (uint32_t e = tid; e < n_groups; e += FUSED_THREADS) {
-            const int f = s_gmap[e];
-            const uint32_t meta = s_meta[f];
-            const int fl = META_L(meta);
-            const int S = emit_seqlen(emit, fl, RL);
-            const int gpl = ((S + 15) >> 4) + 1;                    // group slots per line
-            int g = (int)e - (int)s_gstart[f];
-            const int line = g >= gpl ? 1 : 0;
-            g -= line * gpl;
-            const int h = s_hdr[f];
-            // staging offset of the first sequence byte of this line
-            const int ls = (int)s_recoff[f] + line * (h + 1 + S + 1) + h + emit_suffix(emit, line) + 1;
-            const int sigma = ls & 15;
-            const int j0 = 16 * g - sigma;
-            const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
-            if (jhi <= jlo) continue;
-            const uint32_t codes = line_codes(P, s_dwords + s_cstart[f], fl, line, j0, P.first + tile_first + (uint64_t)f);
-            uint4 a;
-            a.x = s_lut[codes & 0xFFu]; a.y = s_lut[(codes >> 8) & 0xFFu];
-            a.z = s_lut[(codes >> 16) & 0xFFu]; a.w = s_lut[codes >> 24];
-            uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
-            if (jlo == j0 && jhi == j0 + 16) {
-                *(uint4*)dst = a;
-            } else {
-                // boundary group: merge under a byte mask.  Headers were written before the barrier; two sequence lines are
-                // always >= 12 bytes apart (newline + a header), so no other thread touches these 4-byte words in this pass.
-                const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
-                uint32_t* d4 = (uint32_t*)dst;
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int lo = min(max(t0 - 4 * w, 0), 4), hi = min(max(t1 - 4 * w, 0), 4);
-                    uint32_t mh, ml;
-                    asm("shl.b32 %0, 1, %1;" : "=r"(mh) : "r"(8 * hi));
-                    asm("shl.b32 %0, 1, %1;" : "=r"(ml) : "r"(8 * lo));
-                    const uint32_t m = (mh - 1u) & ~(ml - 1u);
-                    if (m == 0xFFFFFFFFu) d4[w] = aw[w];
-                    else if (m) d4[w] = (d4[w] & ~m) | (aw[w] & m);
-                }
-            }
-        }
-
-        // ------------------------------------------------------------ look-back: global byte offset of this tile
+        // ------------------------------------------------------------ look-back (warp 0, overlapped with pass C of the other warps):
+        // global byte offset of this tile.  The inclusive prefix is published here, right after sampling, so successors
+        // rarely have to walk back further than a few tiles.
         if (warp == 0) {
             unsigned long long ex = 0;
             if (tile > 0) {
@@ -467,42 +336,196 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
                 if (tile == P.n_tiles - 1) P.stats[ST_TOTAL] = ex + (unsigned long long)T;
             }
         }
+
+        // ------------------------------------------------------------ pass C: gather + damage (thread per 16-base chunk)
+        if (!overflow)
+        for (uint32_t e = tid; e < n_chunks; e += FUSED_THREADS) {
+            const int f = s_cmap[e];
+            const int k = (int)e - (int)s_cstart[f];
+            const uint32_t meta = s_meta[f];
+            const int fl = META_L(meta), slot = META_SLOT(meta);
+            const uint64_t gp = s_gpos[f];
+            const uint32_t* seq2 = P.genomes[META_GEN(meta)].seq2;
+            const int n = min(16, fl - 16 * k);
+            uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
+                                         : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
+            if (slot >= 0 && emit != 0) {
+                // All 16 fields are processed without per-base branches; fields at or beyond the fragment end hold
+                // neighbouring genome bases, index sentinel/clamped rows, and are masked off below.
+                const uint64_t id = P.first + tile_first + (uint64_t)f;
+                const int mode = P.dmg[slot].mode;
+                const int i0 = 16 * k;
+                if (mode == 1) {                                     // -matfile: one uniform per base (deamSim.cpp:1847,1911)
+                    const int R5 = P.dmg[slot].rows5, R3 = P.dmg[slot].rows3;
+                    const uint4* __restrict__ thr5 = P.dmg[slot].thr;
+                    const uint4* __restrict__ thr3 = thr5 + 4 * (R5 + 1);
+                    const int c5 = (fl >> 1) - i0;                    // fields j < c5 are on the 5' side (deamSim.cpp:1805)
+                    const uint32_t d3 = (uint32_t)(fl - 1 - i0);      // distance of field 0 from the 3' end
+                    uint32_t Wn = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (4 * q < n) {
+                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = 4 * q + jj;
+                                const uint32_t b = (W >> (2 * j)) & 3u;
+                                const uint4* row = (j < c5) ? thr5 + 4 * min(i0 + j, R5) : thr3 + 4 * (int)min(d3 - (uint32_t)j, (uint32_t)R3);
+                                const uint4 T = __ldg(row + b);
+                                const uint32_t u = pick(x, jj) >> 1;
+                                Wn += ((uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z)) << (2 * j);
+                            }
+                        }
+                    }
+                    W = Wn;
+                } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i
+                    const DamageDev& D = P.dmg[slot];
+                    const BriggsHdr B = dmg_briggs_hdr(D, rng_block(P.key, id, 0u, ST_DEAM));
+                    uint32_t Wn = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (4 * q < n) {
+                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = 4 * q + jj;
+                                Wn |= dmg_briggs_base(D, B, i0 + j, fl, (W >> (2 * j)) & 3u, pick(x, jj)) << (2 * j);
+                            }
+                        }
+                    }
+                    W = Wn;
+                } else if (mode == 3 || mode == 4) {                 // single / double: two passes, two streams
+                    const DamageDev& D = P.dmg[slot];
+                    uint32_t Wn = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (4 * q < n) {
+                            const uint4 x1 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
+                            const uint4 x2 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM2);
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = 4 * q + jj;
+                                Wn |= dmg_sd_base(D, min(i0 + j, fl - 1), fl, (W >> (2 * j)) & 3u, pick(x1, jj), pick(x2, jj)) << (2 * j);
+                            }
+                        }
+                    }
+                    W = Wn;
+                }
+            }
+            s_dwords[e] = W & lowfields(n);
+        }
         __syncthreads();
 
-        // ------------------------------------------------------------ copy-out: staging -> global, 16-byte aligned vector stores
-        if (!overflow) {
-            const unsigned long long B = s_excl;
-            if (B + T > P.out_cap) { my_err |= ERRF_OVERFLOW; }
+        // ------------------------------------------------------------ pass C2: line images (owner thread; adptSim dialects only)
+        const int S_ad = emit == 4 ? 2 * RL : RL;                       // sequence-line length of the adptSim dialects
+        const int LWL = ((S_ad + 15) >> 4) + 2;                          // words per line image: guard + data + read slack
+        if (emit >= 2 && tid < nf && !overflow) {
+            const int L = META_L(s_meta[tid]);
+            const uint64_t id = P.first + tile_first + (uint64_t)tid;
+            const uint32_t* D = s_dwords + s_cstart[tid];
+            uint32_t* lw = s_lwords + tid * (nlines * LWL);
+            BitAppender A; A.out = lw + 1; A.acc = 0; A.fill = 0;
+            if (emit == 6) put_reverse_read(A, P, D, L, id);            // -rr
             else {
-                uint8_t* const gout = P.out + B;
-                const int pad = (int)((uintptr_t)gout & 15);            // misalignment of the tile's first byte
-                // aligned global chunk c covers staging bytes [16c - pad, 16c - pad + 16)
-                const int nchunks = (int)((T + pad + 15) >> 4);
-                const int sh = (16 - pad) & 15;                          // staging byte offset within its aligned 16 B
+                put_forward_read(A, P, D, L, id);                       // -arts / -fr / first line / first half of -artp
+                if (emit == 4) put_reverse_read_rc(A, P, D, L, id);     // -artp: ++ revcomp(reverse read)
+            }
+            A.flush();
+            if (emit == 2) {                                            // default 4-line output: second line = reverse read
+                A.out = lw + LWL + 1; A.acc = 0; A.fill = 0;
+                put_reverse_read(A, P, D, L, id);
+                A.flush();
+            }
+        }
+        const unsigned long long gofs = s_excl;                         // (published by warp 0 before the barrier above)
+        const int pad = (int)((uintptr_t)(P.out + gofs) & 15);          // the tile is staged with its global misalignment
+        if (emit >= 2) __syncthreads();
+
+        // ------------------------------------------------------------ pass B2 (before D unless FASTB): headers + newlines (owner thread)
+        auto write_headers = [&]() {
+            if (tid < nf && !overflow) {
+                const uint32_t meta = s_meta[tid];
+                const int L = META_L(meta); const uint32_t plus = META_PLUS(meta);
+                const uint64_t idx = s_idx[tid]; const int ci = (int)s_ci[tid];
+                const RangeDev* rg = P.ranges + s_rg[tid];
+                const char* tag = rg->tag; const int tag_len = rg->tag_len;
+                const int S = emit_seqlen(emit, L, RL);
+                const char* nm = P.ctab.names + __ldg(P.ctab.name_off + ci);
+                const int nlen = __ldg(P.ctab.name_len + ci);
+                uint8_t* p = s_stage + pad + s_recoff[tid];
+                for (int ln = 0; ln < nlines; ln++) {
+                    // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
+                    *p++ = '>';
+                    for (int k = 0; k < nlen; k++) *p++ = (uint8_t)__ldg(nm + k);
+                    *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
+                    p = put_decimal(p, idx, ndigits(idx)); *p++ = ':';
+                    p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L)); *p++ = ':';
+                    p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L));
+                    for (int k = 0; k < tag_len; k++) *p++ = (uint8_t)tag[k];
+                    if (emit_suffix(emit, ln)) { *p++ = '_'; *p++ = 'r'; }
+                    *p++ = '\n';
+                    p += S;
+                    *p++ = '\n';
+                }
+            }
+        };
+        if (!FASTB) { write_headers(); __syncthreads(); }
+
+        // ------------------------------------------------------------ pass D: ASCII (thread per 16-byte staging group)
+        if (!overflow)
+        for (uint32_t e = tid; e < n_groups; e += FUSED_THREADS) {
+            const int f = s_gmap[e];
+            const int fl = META_L(s_meta[f]);
+            const int S = emit_seqlen(emit, fl, RL);
+            const int gpl = ((S + 15) >> 4) + 1;                    // group slots per line
+            int g = (int)e - (int)s_gstart[f];
+            const int line = g >= gpl ? 1 : 0;
+            g -= line * gpl;
+            const int h = s_hdr[f];
+            // staging offset of the first sequence byte of this line
+            const int ls = pad + (int)s_recoff[f] + line * (h + 1 + S + 1) + h + emit_suffix(emit, line) + 1;
+            const int sigma = ls & 15;
+            const int j0 = 16 * g - sigma;
+            const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
+            if (jhi <= jlo) continue;
+            const uint32_t* src = emit <= 1 ? s_dwords + s_cstart[f] : s_lwords + f * (nlines * LWL) + line * LWL + 1;
+            const uint32_t codes = fetch_run_smem(src, j0);
+            uint4 a;
+            a.x = s_lut[codes & 0xFFu]; a.y = s_lut[(codes >> 8) & 0xFFu];
+            a.z = s_lut[(codes >> 16) & 0xFFu]; a.w = s_lut[codes >> 24];
+            uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
+            if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
+                *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
+            } else {
+                // boundary group: merge under a byte mask.  Headers were written before the barrier; two sequence lines are
+                // always >= 12 bytes apart (newline + a header), so no other thread touches these 4-byte words in this pass.
+                const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
+                const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
+                uint32_t* d4 = (uint32_t*)dst;
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t nib = (V >> (4 * w)) & 0xFu;
+                    const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
+                    if (nib == 0xFu) d4[w] = aw[w];
+                    else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                }
+            }
+        }
+        __syncthreads();
+        if (FASTB) { write_headers(); __syncthreads(); }
+
+        // ------------------------------------------------------------ copy-out: staging -> global, aligned 16-byte vector stores
+        if (!overflow) {
+            if (gofs + T > P.out_cap) { my_err |= ERRF_OVERFLOW; }
+            else {
+                uint8_t* const gal = P.out + gofs - pad;                 // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+T)
+                const int end = pad + (int)T;
+                const int nchunks = (end + 15) >> 4;
                 for (int c = tid; c < nchunks; c += FUSED_THREADS) {
-                    const int s0 = 16 * c - pad;
-                    uint8_t* gdst = gout + s0;
-                    if (s0 >= 0 && s0 + 16 <= (int)T) {
-                        uint4 v;
-                        if (sh == 0) v = *(const uint4*)(s_stage + s0);
-                        else {
-                            const uint4 lo4 = *(const uint4*)(s_stage + s0 - sh), hi4 = *(const uint4*)(s_stage + s0 - sh + 16);
-                            const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                            const int ws = sh >> 2; const uint32_t bs = (uint32_t)(sh & 3) * 8u;
-                            uint32_t r[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                uint32_t a0 = 0, a1 = 0;
-#pragma unroll
-                                for (int q = 0; q < 4; q++) if (ws == q) { a0 = w[q + k]; a1 = w[q + k + 1 < 8 ? q + k + 1 : 7]; }
-                                r[k] = __funnelshift_r(a0, a1, bs);
-                            }
-                            v = make_uint4(r[0], r[1], r[2], r[3]);
-                        }
-                        st_global_v4(gdst, v);
-                    } else {
-                        for (int t = max(s0, 0); t < min(s0 + 16, (int)T); t++) gout[t] = s_stage[t];
-                    }
+                    const int s0 = 16 * c;
+                    if (s0 >= pad && s0 + 16 <= end) st_global_v4(gal + s0, *(const uint4*)(s_stage + s0));
+                    else for (int t = max(s0, pad); t < min(s0 + 16, end); t++) gal[t] = s_stage[t];
                 }
             }
         }
@@ -522,14 +545,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) k_fused(const __grid_constan
 }
 
 cudaError_t fused_occupancy(int smem_bytes, int* blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_fused, FUSED_THREADS, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_fused<false>, FUSED_THREADS, smem_bytes);
 }
 cudaError_t launch_fused(const FusedParams& P, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm.total);
-    if (e != cudaSuccess) return e;
-    k_fused<<<grid, FUSED_THREADS, P.sm.total, st>>>(P);
+    if (P.fast_boundary) k_fused<true><<<grid, FUSED_THREADS, P.sm.total, st>>>(P);
+    else                 k_fused<false><<<grid, FUSED_THREADS, P.sm.total, st>>>(P);
     return cudaGetLastError();
 }
 

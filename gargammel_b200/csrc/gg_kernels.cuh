@@ -35,7 +35,8 @@ struct Adapters {
 struct SmemLayout {          // byte offsets into dynamic shared memory, computed by the host
     int stage, stage_bytes;  // output staging (16 B of readable slack before and after)
     int gpos, meta, recoff, hdr, cstart, gstart;   // per-fragment descriptors
-    int dwords, cmap, gmap, lut, total;
+    int idx, ci, rg;                               // per-fragment header state parked between passes
+    int dwords, lwords, cmap, gmap, lut, total;
 };
 struct FusedParams {
     // work
@@ -44,6 +45,7 @@ struct FusedParams {
     int n_tiles;
     int emit;                // gg_emit_mode
     int norev;
+    int fast_boundary;       // every header >= 13 bytes: whole-group stores, headers written afterwards
     ggd::Key key;
     // plan + genomes
     const RangeDev* ranges; int n_ranges;

@@ -199,3 +199,23 @@ def test_large_run_properties(oracle_mod):
     frag, _ = g.run_fused(0, tot, api.EMIT_FRAG)
     hdrs = frag.split(b"\n")[0:-1:2]
     assert sum(h.endswith(b"c1") for h in hdrs) == nC and sum(h.endswith(b"e1_0") for h in hdrs) == nE // 2
+
+
+def test_fused_short_headers(oracle_mod):
+    """One-letter contig names and no tag: headers shorter than 13 bytes take the masked read-modify-write path of the
+    emit pass (two sequence lines may share a 16-byte group)."""
+    rng = np.random.default_rng(3)
+    fa, fai = synth.fasta_bytes([("a", synth.random_contig(rng, 900, 0.02, (3, 20))), ("b", synth.random_contig(rng, 700, 0.0))], width=50)
+    for sizes, kw in (("fixed", dict(fixed_len=1)), ("fixed", dict(fixed_len=3)), ("fixed", dict(fixed_len=20)), ("freq", {})):
+        g = api.Context(0, 5); o = oracle_mod.OracleContext(5)
+        for c in (g, o):
+            gid = c.upload_genome(fa, fai)
+            if sizes == "fixed":
+                c.set_sizes(api.SIZE_FIXED, **kw)
+            else:
+                c.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq())
+            util.set_damage(c, 0, "matrix")
+            c.set_adapters("ACGT", "TTGCA", 9)
+            c.set_plan([api.Range(0, 2000, gid, 0, "")])
+        for emit in ALL_EMITS:
+            util.assert_same(g.run_fused(0, 2000, emit)[0], o.run_fused(0, 2000, emit)[0], "short headers %s %r emit=%d" % (sizes, kw, emit))
