@@ -1,0 +1,65 @@
+// bin/adptSim -- drop-in for the reference's src/adptSim (adptSim.cpp): same flags, last argv is the FASTA (plain or gz);
+// stdout 4-line records, -arts/-artp plain files, -fr/-rr gz files; same final stderr line.  GPU through the C-ABI.
+#include "cli_common.h"
+using namespace cli;
+
+int main(int argc, char** argv) {
+    std::string adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
+    std::string adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
+    int desiredLength = 100; std::string outArt, fwd, rev = "/dev/null"; bool arts = false, artp = false, fa = false;
+    uint64_t seed = time_seed();
+    const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds adapters / trims to the read length (B200 build)\n\n" +
+        "\t\t-arts\t[out]\t\tOutput single-end reads as ART (unzipped fasta)\n\t\t-artp\t[out]\t\tOutput reads as ART (unzipped fasta) with wrap-around for paired-end mode\n" +
+        "\t\t-fr\t[out fwdr]\tOutput forward read as zipped fasta\n\t\t-rr\t[out rwdr]\tOutput reverse read as zipped fasta\n" +
+        "\t-f\t[seq]\t\t\tAdapter that is observed after the forward read\n\t-s\t[seq]\t\t\tAdapter that is observed after the reverse read\n\t-l\t[length]\t\tDesired read length  (Default:  100)\n" +
+        "\tNot in this build: -bs -bp -u -name -tag\n";
+    if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // adptSim.cpp:82-90
+    for (int i = 1; i < argc - 1; i++) {                                            // adptSim.cpp:92-177
+        const std::string a = argv[i];
+        if (a == "-arts") { outArt = argv[++i]; arts = true; continue; }
+        if (a == "-artp") { outArt = argv[++i]; artp = true; continue; }
+        if (a == "-l") { desiredLength = (int)to_ll(argv[++i], "-l"); continue; }
+        if (a == "-f") { adF = argv[++i]; continue; }
+        if (a == "-s") { adS = argv[++i]; continue; }
+        if (a == "-fr") { fwd = argv[++i]; fa = true; continue; }
+        if (a == "-rr") { rev = argv[++i]; fa = true; continue; }
+        if (a == "--seed") { seed = (uint64_t)to_ll(argv[++i], "--seed"); continue; }    // extension: the reference pads from an unseeded rand()
+        if (a == "-bs" || a == "-bp" || a == "-u" || a == "-name" || a == "-tag") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        return die("Error: unknown option " + a);                                   // adptSim.cpp:175-176
+    }
+    if (fa && fwd.empty()) return die("Error: need to specify the output forward read ");                  // :179-182
+    if (fa && (arts || artp)) return die("Error: cannot produce both fastq and ART output");               // :189-192
+    const std::string infileName = argv[argc - 1];                                  // adptSim.cpp:199
+
+    gg_ctx* ctx = NULL;
+    if (open_ctx(seed, &ctx)) return 1;
+    if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), desiredLength) != GG_OK) return gg_fail(ctx, "adapters");
+    std::string err; std::vector<uint8_t> recs; uint64_t nrec = 0;
+    if (!read_records(infileName, recs, &nrec, err)) return die(err);
+    std::vector<Chunk> chunks = chunk_records(recs, 256u << 20);
+    std::vector<uint8_t> host;
+    // one pass per output file: -fr and -rr are two streams (adptSim.cpp:397-398)
+    struct Pass { int emit; Sink sink; };
+    std::vector<Pass> passes;
+    if (fa) {
+        Pass p1; p1.emit = GG_EMIT_FR; if (!p1.sink.open_gz(fwd)) return die("Cannot write to file " + fwd); passes.push_back(p1);
+        Pass p2; p2.emit = GG_EMIT_RR; if (!p2.sink.open_gz(rev)) return die("Cannot write to file " + rev); passes.push_back(p2);
+    } else if (arts || artp) {
+        Pass p; p.emit = artp ? GG_EMIT_ARTP : GG_EMIT_ARTS; if (!p.sink.open_plain(outArt)) return die("Cannot write to file " + outArt); passes.push_back(p);
+    } else { Pass p; p.emit = GG_EMIT_STDOUT4; p.sink.open_stdout(); passes.push_back(p); }
+    for (size_t k = 0; k < passes.size(); k++) {
+        uint64_t first = 0;
+        for (size_t c = 0; c < chunks.size(); c++) {
+            gg_out o;
+            if (gg_run_adpt(ctx, recs.data() + chunks[c].off, chunks[c].bytes, passes[k].emit, first, &o) != GG_OK) return gg_fail(ctx, "adptSim kernel");
+            host.resize(o.bytes); size_t n = 0;
+            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+            if (!passes[k].sink.write(host.data(), n)) return die("Error: write failed");
+            first += chunks[c].recs;
+        }
+        if (!passes[k].sink.close()) return die("Error: write failed");
+    }
+    gg_ctx_destroy(ctx);
+    std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nrec << " sequences" << std::endl;   // adptSim.cpp:437
+    return 0;
+}

@@ -1,0 +1,132 @@
+// cli_common.h -- shared plumbing of the drop-in executables (bin/fragSim, bin/deamSim, bin/adptSim, bin/gargammel-b200).
+// Host side in C++11 above the C-ABI (include/gargammel_b200.h); mirrors the reference's CLI conventions:
+// options over argv[1..argc-2], last argv is the input, errors on stderr + exit 1 (fragSim.cpp:463-471,622-623).
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <sys/time.h>
+#include <unistd.h>
+#include <limits.h>
+#include <string>
+#include <vector>
+#include <iostream>
+#include "gg_host.h"
+
+namespace cli {
+
+inline bool is_help(int argc, char** argv) {
+    return argc == 1 || (argc == 2 && (!strcmp(argv[1], "-h") || !strcmp(argv[1], "-help") || !strcmp(argv[1], "--help")));
+}
+inline int die(const std::string& msg) { std::cerr << msg << std::endl; return 1; }
+inline int unsupported(const std::string& opt, const char* why) {
+    std::cerr << "Error: option " << opt << " is not supported by the B200 build (" << why << ")" << std::endl;
+    return 1;
+}
+// destringify<T>(argv) of the reference: exit(1) on garbage
+inline long long to_ll(const char* s, const char* opt) {
+    char* e; long long v = strtoll(s, &e, 10);
+    if (e == s) { std::cerr << "Error: cannot convert \"" << s << "\" for option " << opt << std::endl; exit(1); }
+    return v;
+}
+inline double to_d(const char* s, const char* opt) {
+    char* e; double v = strtod(s, &e);
+    if (e == s) { std::cerr << "Error: cannot convert \"" << s << "\" for option " << opt << std::endl; exit(1); }
+    return v;
+}
+inline uint64_t time_seed() {       // the reference seeds from the clock when --seed is absent (fragSim.cpp:713-715)
+    timeval t; gettimeofday(&t, NULL);
+    return (uint64_t)t.tv_sec * 1000000ull + (uint64_t)t.tv_usec;
+}
+inline std::string exe_dir(const char* argv0) {     // getCWD(argv[0]) of libgab: directory of the executable, trailing '/'
+    char buf[PATH_MAX]; std::string p;
+    ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+    if (n > 0) { buf[n] = 0; p = buf; } else p = argv0;
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? std::string("./") : p.substr(0, k + 1);
+}
+
+// output sink: stdout, a plain file, or a gzip file (ogzstream of the reference)
+struct Sink {
+    FILE* f; gzFile gz; bool own;
+    Sink() : f(NULL), gz(NULL), own(false) {}
+    bool open_stdout() { f = stdout; own = false; setvbuf(stdout, NULL, _IOFBF, 1 << 22); return true; }
+    bool open_plain(const std::string& p) { f = fopen(p.c_str(), "wb"); own = true; if (f) setvbuf(f, NULL, _IOFBF, 1 << 22); return f != NULL; }
+    bool open_gz(const std::string& p, bool append = false) { gz = gzopen(p.c_str(), append ? "ab1" : "wb1"); if (gz) gzbuffer(gz, 1 << 20); return gz != NULL; }
+    bool write(const void* d, size_t n) {
+        if (gz) { const char* p = (const char*)d; while (n) { unsigned c = n > (1u << 30) ? (1u << 30) : (unsigned)n; if (gzwrite(gz, p, c) != (int)c) return false; p += c; n -= c; } return true; }
+        return fwrite(d, 1, n, f) == n;
+    }
+    bool close() { bool ok = true; if (gz) { ok = gzclose(gz) == Z_OK; gz = NULL; } if (f) { ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; } return ok; }
+};
+
+// Read a FASTA record stream as the reference's FastQParser(file, true) does (gz or plain) and normalise it to
+// 2-line records "ID\nSEQ\n" (multi-line sequences are joined).  Returns false on error.
+inline bool read_records(const std::string& path, std::vector<uint8_t>& out, uint64_t* n_rec, std::string& err) {
+    std::vector<uint8_t> raw;
+    if (!ggh::read_file(path, raw, err)) return false;
+    *n_rec = 0;
+    // fast path: already strictly 2-line
+    bool two_line = true; size_t p = 0, lines = 0;
+    while (p < raw.size()) {
+        const uint8_t* e = (const uint8_t*)memchr(raw.data() + p, '\n', raw.size() - p);
+        size_t le = e ? (size_t)(e - raw.data()) : raw.size();
+        const bool hdr = raw[p] == '>';
+        if ((lines & 1) == 0 ? !hdr : hdr) { two_line = false; break; }
+        if (le > p && raw[le - 1] == '\r') { two_line = false; break; }
+        lines++; p = le + 1;
+    }
+    if (two_line && (lines & 1) == 0) {
+        if (!raw.empty() && raw.back() != '\n') raw.push_back('\n');
+        out.swap(raw); *n_rec = lines / 2; return true;
+    }
+    out.clear(); out.reserve(raw.size() + 1);
+    p = 0; bool have = false, in_seq = false;
+    while (p < raw.size()) {
+        const uint8_t* e = (const uint8_t*)memchr(raw.data() + p, '\n', raw.size() - p);
+        size_t le = e ? (size_t)(e - raw.data()) : raw.size();
+        size_t l1 = le; if (l1 > p && raw[l1 - 1] == '\r') l1--;
+        if (l1 > p && raw[p] == '>') {
+            if (have) { if (!in_seq) {} out.push_back('\n'); }
+            out.insert(out.end(), raw.begin() + p, raw.begin() + l1); out.push_back('\n');
+            have = true; in_seq = true; (*n_rec)++;
+        } else if (l1 > p) {
+            if (!have) { err = "input does not start with a '>' record: " + path; return false; }
+            out.insert(out.end(), raw.begin() + p, raw.begin() + l1);
+        }
+        p = le + 1;
+    }
+    if (have) out.push_back('\n');
+    return true;
+}
+
+// split a normalised 2-line stream into chunks of at most `max_bytes` on record boundaries; returns (offset, bytes, records)
+struct Chunk { size_t off, bytes; uint64_t recs; };
+inline std::vector<Chunk> chunk_records(const std::vector<uint8_t>& s, size_t max_bytes) {
+    std::vector<Chunk> out; size_t start = 0, p = 0; uint64_t recs = 0, lines = 0;
+    while (p < s.size()) {
+        const uint8_t* e = (const uint8_t*)memchr(s.data() + p, '\n', s.size() - p);
+        p = e ? (size_t)(e - s.data()) + 1 : s.size();
+        if ((++lines & 1) == 0) {
+            recs++;
+            if (p - start >= max_bytes) { Chunk c = {start, p - start, recs}; out.push_back(c); start = p; recs = 0; }
+        }
+    }
+    if (p > start) { Chunk c = {start, p - start, recs}; out.push_back(c); }
+    return out;
+}
+
+inline int gg_fail(gg_ctx* ctx, const char* what) {
+    std::cerr << "Error: " << what << ": " << gg_last_error(ctx) << std::endl; return 1;
+}
+inline int open_ctx(uint64_t seed, gg_ctx** ctx) {
+    int dev = 0; const char* d = getenv("GG_DEVICE"); if (d) dev = atoi(d);
+    if (gg_ctx_create(dev, seed, ctx) != GG_OK) {
+        std::cerr << "Error: cannot open CUDA device " << dev << " (this build has no CPU fallback)" << std::endl; return 1;
+    }
+    return 0;
+}
+
+} // namespace cli

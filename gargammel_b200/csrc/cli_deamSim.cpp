@@ -1,0 +1,91 @@
+// bin/deamSim -- drop-in for the reference's src/deamSim (deamSim.cpp): same flags, last argv is the FASTA (plain or gz),
+// "ID\nSEQ\n" records on stdout / -o gz, same final stderr line.  The per-base damage runs on the GPU through the C-ABI.
+#include "cli_common.h"
+using namespace cli;
+
+int main(int argc, char** argv) {
+    std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix;
+    bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false;
+    double v = 0, l = 0, d = 0, s = 0; uint64_t seed = 0;
+    const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds deamination according to a certain model (B200 build)\n\n" +
+        "\t\t-o\t[fasta out]\t\t\tWrite fasta output as a zipped fasta\n\t\t-last\t\t\t\t\tdo not use the last matrix row beyond the matrix\n\t\t--seed\t[int]\n\n" +
+        "\t\t-mapdamage  [mis.txt] [protocol]\n\t\t-profile  [prof file prefix]\n\t\t-matfile  [matrix file prefix]\n\t\t-mat      [single|double]\n\t\t-damage     [v,l,d,s]\n" +
+        "\tNot in this build: -b -u -name -damagess -matfilemeth -matfilenonmeth\n";
+    if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // deamSim.cpp:199-207
+    for (int i = 1; i < argc - 1; i++) {                                            // deamSim.cpp:213-378
+        const std::string a = argv[i];
+        if (a == "-mat") {
+            matrix = argv[++i];
+            if (matrix != "single" && matrix != "double") return die("Specify either \"single\" or \"double\" (without quotes), you entered " + matrix);
+            matrixSpecified = true; continue;
+        }
+        if (a == "--seed") { seed = (uint64_t)to_ll(argv[++i], "--seed"); seedSpecified = true; continue; }
+        if (a == "-profile") { profFile = argv[++i]; continue; }
+        if (a == "-matfile") { matrixFile = argv[++i]; continue; }
+        if (a == "-mapdamage") {
+            if (i + 2 >= argc) return die("Error: -mapdamage needs a file and a protocol");
+            mapdamageFile = argv[++i]; mapdamageProtocol = argv[++i];
+            if (mapdamageProtocol != "single" && mapdamageProtocol != "double") return die("The protocol specified should be 'single' or 'double' without the quotes, got: " + mapdamageProtocol);
+            continue;
+        }
+        if (a == "-damage") {
+            const std::string p = argv[++i]; useBriggs = true;
+            std::vector<std::string> t = ggh::all_tokens(p, ',');
+            if (t.size() != 4) return die("Specify 4 comma-separated values for the Briggs model, you entered:" + p);
+            v = to_d(t[0].c_str(), "-damage"); l = to_d(t[1].c_str(), "-damage"); d = to_d(t[2].c_str(), "-damage"); s = to_d(t[3].c_str(), "-damage");
+            if (v < 0 || v > 1) return die("Nick frequency must be between 0 and 1, entered:" + t[0]);
+            if (l < 0 || l > 1) return die("Geometric parameter for overhang must be between 0 and 1, entered:" + t[1]);
+            if (d < 0 || d > 1) return die("double-strand deamination prob. must be between 0 and 1, entered:" + t[2]);
+            if (s < 0 || s > 1) return die("single-strand deamination prob. must be between 0 and 1, entered:" + t[3]);
+            continue;
+        }
+        if (a == "-o") { outGz = argv[++i]; continue; }
+        if (a == "-last") { lastRowMatrix = false; continue; }
+        if (a == "-v") continue;                                                    // per-read log on stderr: not produced
+        if (a == "-name" || a == "-b" || a == "-u" || a == "-damagess" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377
+    }
+    const bool mapd = !mapdamageFile.empty();
+    if (useBriggs && (matrixSpecified || mapd)) return die("Error: cannot specify both a file and Briggs parameter model");        // :380-383
+    if (!useBriggs && !matrixSpecified && matrixFile.empty() && !mapd && profFile.empty())
+        return die("Please specify the matrix to use or use the Briggs parameter model");                                          // :395-405
+    if (!profFile.empty() && !matrixFile.empty()) return die("Please specify damage profile or substitution matrix");              // :407-412
+    if (!seedSpecified) seed = time_seed();
+    const std::string inputFile = argv[argc - 1];                                   // deamSim.cpp:436
+
+    gg_ctx* ctx = NULL;
+    if (open_ctx(seed, &ctx)) return 1;
+    std::string err; ggh::Rates s5, s3;
+    if (useBriggs) { if (gg_tables_set_briggs(ctx, 0, v, l, d, s) != GG_OK) return gg_fail(ctx, "-damage"); }
+    else if (mapd) {                                                                // deamSim.cpp:453-668
+        if (!ggh::load_mapdamage(mapdamageFile, s5, s3, err)) return die(err);
+        if (gg_tables_set_singledouble(ctx, 0, mapdamageProtocol == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mapdamage");
+    } else if (!profFile.empty()) {                                                 // :956-1094
+        if (!ggh::load_profile(profFile, s5, s3, err)) return die(err);
+        if (gg_tables_set_matrix(ctx, 0, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12), lastRowMatrix) != GG_OK) return gg_fail(ctx, "-profile");
+    } else if (!matrixFile.empty()) {                                               // :1098-1241
+        if (!ggh::load_matrix_dat(matrixFile, s5, s3, err)) return die(err);
+        if (gg_tables_set_matrix(ctx, 0, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12), lastRowMatrix) != GG_OK) return gg_fail(ctx, "-matfile");
+    } else {                                                                        // -mat single|double: <exe dir>/matrices/<m>-{5,3}.dat (:1105-1106)
+        if (!ggh::load_matrix_dat(exe_dir(argv[0]) + "matrices/" + matrix + "-", s5, s3, err)) return die(err);
+        if (gg_tables_set_singledouble(ctx, 0, matrix == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mat");
+    }
+    std::vector<uint8_t> recs; uint64_t nrec = 0;
+    if (!read_records(inputFile, recs, &nrec, err)) return die(err);
+    Sink out;
+    if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); } else out.open_stdout();
+    std::vector<Chunk> chunks = chunk_records(recs, 512u << 20);
+    std::vector<uint8_t> host; uint64_t first = 0;
+    for (size_t c = 0; c < chunks.size(); c++) {
+        gg_out o;
+        if (gg_run_deam(ctx, recs.data() + chunks[c].off, chunks[c].bytes, 0, first, &o) != GG_OK) return gg_fail(ctx, "deamSim kernel");
+        host.resize(o.bytes); size_t n = 0;
+        if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+        if (!out.write(host.data(), n)) return die("Error: write failed");
+        first += chunks[c].recs;
+    }
+    if (!out.close()) return die("Error: write failed");
+    gg_ctx_destroy(ctx);
+    std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nrec << " sequences" << std::endl;   // deamSim.cpp:2053
+    return 0;
+}

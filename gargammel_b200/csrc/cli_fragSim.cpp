@@ -1,0 +1,85 @@
+// bin/fragSim -- drop-in for the reference's src/fragSim (fragSim.cpp): same flags, last argv is the FASTA, same
+// record grammar on stdout / -o gz, same final stderr line.  The sampling runs on the GPU through the C-ABI.
+#include "cli_common.h"
+using namespace cli;
+
+int main(int argc, char** argv) {
+    int sizeFragments = 20; uint64_t nFragments = 10; int minLen = 0, maxLen = 1000;
+    bool noRev = false, seedSpecified = false, specifiedLength = false; uint64_t seed = 0;
+    std::string sizeList, sizeFreq, outGz, tag;
+    const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
+        " aDNA fragments according to a certain distribution (B200 build)\n\n " + argv[0] + " [options]  [chromosome fasta] \n\n" +
+        "\t\t-n\t[number]\t\t\tGenerate [number] fragments (default: 10)\n\t\t--norev\t\t\t\t\tDo not reverse complement (default: rev. comp half of seqs.)\n" +
+        "\t\t--seed\t[int]\t\t\t\tUse [seed] as seed for the random number generator (default random seed each execution)\n" +
+        "\t\t-o\t[fasta out]\t\t\tWrite output as a zipped fasta (default: fasta in STDOUT)\n\t\t-tag\t[tag]\t\t\t\tAppend this string to deflines\n" +
+        "\t\t-m\t[length]\t\t\tMinimum fragments length (default: 0)\n\t\t-M\t[length]\t\t\tMaximum fragments length (default: 1000)\n" +
+        "\t\t-l\t[length]\t\t\tGenerate fragments of fixed length  (default: 20)\n\t\t-s\t[file]\t\t\t\tOpen file with size distribution (one fragment length per line)\n" +
+        "\t\t-f\t[file]\t\t\t\tOpen file with size frequency: length[TAB]freq\n" +
+        "\tNot in this build: --comp --dist -gc --circ --case --fq --trim5p --loc --scale -uniq -b -u\n";
+    if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
+    for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
+        const std::string a = argv[i];
+        if (a == "-n") { nFragments = (uint64_t)to_ll(argv[++i], "-n"); continue; }
+        if (a == "-l") { sizeFragments = (int)to_ll(argv[++i], "-l"); specifiedLength = true; continue; }
+        if (a == "-s") { sizeList = argv[++i]; continue; }
+        if (a == "-f") { sizeFreq = argv[++i]; continue; }
+        if (a == "-m") { minLen = (int)to_ll(argv[++i], "-m"); continue; }
+        if (a == "-M") { maxLen = (int)to_ll(argv[++i], "-M"); continue; }
+        if (a == "--norev") { noRev = true; continue; }
+        if (a == "--seed") { seed = (uint64_t)to_ll(argv[++i], "--seed"); seedSpecified = true; continue; }
+        if (a == "-o") { outGz = argv[++i]; continue; }
+        if (a == "-tag") { tag = argv[++i]; continue; }
+        if (a == "-tmp") { ++i; continue; }                                         // gz inputs are inflated in memory
+        if (a == "--comp" || a == "--dist" || a == "-gc" || a == "--circ" || a == "--trim5p" || a == "--loc" || a == "--scale" || a == "-b")
+            return unsupported(a, "SURVEY.md 8f-3");
+        if (a == "--case" || a == "--fq" || a == "-uniq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
+        return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
+    }
+    if (specifiedLength && sizeFragments > maxLen)                                   // fragSim.cpp:638-643
+        return die("Error: specified size " + std::to_string(sizeFragments) + " is longer than the maximum allowed fragment size " + std::to_string(maxLen) + ", use option -M to change this.");
+    if (!sizeList.empty() && !sizeFreq.empty()) return die("Error: cannot specify -s with -f");          // :682-685
+    if (specifiedLength && !sizeList.empty()) return die("Error: cannot specify -l and -s");             // :688-691
+    if (specifiedLength && !sizeFreq.empty()) return die("Error: cannot specify -l and -f");             // :693-696
+    if (tag.size() > 23) return die("Error: -tag longer than 23 characters");
+    if (!seedSpecified) seed = time_seed();
+    const std::string inFile = argv[argc - 1];                                      // fragSim.cpp:1026
+
+    std::string err;
+    std::vector<int32_t> lens; std::vector<double> cum;
+    if (!sizeList.empty() && !ggh::load_size_list(sizeList, lens, err)) return die(err);
+    if (!sizeFreq.empty() && !ggh::load_size_freq(sizeFreq, lens, cum, err)) return die(err);
+    ggh::GenomeFile G;
+    if (!ggh::load_genome(inFile, G, err)) return die(err);
+    std::cerr << "Mapped " << inFile << " into memory" << std::endl;                // fragSim.cpp:1149
+
+    gg_ctx* ctx = NULL;
+    if (open_ctx(seed, &ctx)) return 1;
+    int gid = -1;
+    if (ggh::upload_genome(ctx, G, &gid) != GG_OK) return gg_fail(ctx, "genome upload");
+    std::vector<uint8_t>().swap(G.bytes);
+    const int mode = !sizeList.empty() ? GG_SIZE_LIST : !sizeFreq.empty() ? GG_SIZE_FREQ : GG_SIZE_FIXED;
+    if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), sizeFragments, minLen, maxLen) != GG_OK) return gg_fail(ctx, "size tables");
+    gg_tables_set_norev(ctx, noRev ? 1 : 0);
+    if (nFragments) {
+        gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1;
+        snprintf(r.tag, sizeof r.tag, "%s", tag.c_str());
+        if (gg_plan_set(ctx, &r, 1) != GG_OK) return gg_fail(ctx, "plan");
+    }
+    Sink out;
+    if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); }       // fragSim.cpp:1297-1303
+    else out.open_stdout();
+    const uint64_t chunk = 4u << 20;
+    std::vector<uint8_t> host;
+    for (uint64_t first = 0; first < nFragments; first += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
+        gg_out o;
+        if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
+        host.resize(o.bytes); size_t n = 0;
+        if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+        if (!out.write(host.data(), n)) return die("Error: write failed");
+    }
+    if (!out.close()) return die("Error: write failed");
+    gg_ctx_destroy(ctx);
+    std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nFragments << " sequences" << std::endl;   // fragSim.cpp:1785
+    return 0;
+}

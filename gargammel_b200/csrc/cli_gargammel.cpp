@@ -1,0 +1,227 @@
+// bin/gargammel-b200 -- fused driver for the middle of gargammel.pl: scans <dir>/{endo,cont,bact},
+// apportions the fragments across the sources (gargammel.pl:1256-1283,1320-1349,1421-1431), and runs
+// fragSim -> deamSim -> adptSim as ONE kernel per GPU instead of ~N process launches, 3 gzip and 2 gunzip hops.
+// Writes <prefix>_a.fa (what adptSim -artp/-arts writes for ART, gargammel.pl:1838-1848); with --keep also the
+// intermediate <prefix>.{e,b,c}.fa.gz and <prefix>_d.fa.gz of the reference.  ART stays on the host (north_star).
+#include "cli_common.h"
+#include <dirent.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <thread>
+#include <math.h>
+using namespace cli;
+
+static bool ends_with(const std::string& s, const char* suf) { size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+// listdirFa, gargammel.pl:156-183 (sorted here: readdir order is not portable)
+static std::vector<std::string> list_fa(const std::string& dir) {
+    std::vector<std::string> out; DIR* d = opendir(dir.c_str());
+    if (!d) return out;
+    while (dirent* e = readdir(d)) {
+        std::string n = e->d_name;
+        if (n == "." || n == "..") continue;
+        struct stat st; if (stat((dir + n).c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;
+        if (ends_with(n, ".fa") || ends_with(n, ".fa.gz") || ends_with(n, ".fna") || ends_with(n, ".fasta") || ends_with(n, ".fasta.gz")) out.push_back(dir + n);
+    }
+    closedir(d); std::sort(out.begin(), out.end());
+    return out;
+}
+struct DamageSpec { std::string matfile, briggs, mapd_file, mapd_proto; bool any() const { return !matfile.empty() || !briggs.empty() || !mapd_file.empty(); } };
+
+static int set_damage(gg_ctx* ctx, int slot, const DamageSpec& d) {
+    std::string err; ggh::Rates s5, s3;
+    if (!d.matfile.empty()) {
+        if (!ggh::load_matrix_dat(d.matfile, s5, s3, err)) return die(err);
+        if (gg_tables_set_matrix(ctx, slot, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12), 1) != GG_OK) return gg_fail(ctx, "-matfile");
+    } else if (!d.briggs.empty()) {
+        std::vector<std::string> t = ggh::all_tokens(d.briggs, ',');
+        if (t.size() != 4) return die("Specify 4 comma-separated values for the Briggs model, you entered:" + d.briggs);
+        if (gg_tables_set_briggs(ctx, slot, to_d(t[0].c_str(), "-damage"), to_d(t[1].c_str(), "-damage"), to_d(t[2].c_str(), "-damage"), to_d(t[3].c_str(), "-damage")) != GG_OK) return gg_fail(ctx, "-damage");
+    } else if (!d.mapd_file.empty()) {
+        if (d.mapd_proto != "single" && d.mapd_proto != "double") return die("The protocol specified should be 'single' or 'double' without the quotes, got: " + d.mapd_proto);
+        if (!ggh::load_mapdamage(d.mapd_file, s5, s3, err)) return die(err);
+        if (gg_tables_set_singledouble(ctx, slot, d.mapd_proto == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mapdamage");
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    double compB = 0, compC = 0, compE = 1; std::string comp = "0,0,1";
+    uint64_t n = 1000; double coverage = -1; int fraglength = 35, minsize = 0, maxsize = 1000, rl = 75, gpus = 1;
+    std::string sizeList, sizeFreq, prefix, adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";   // gargammel.pl:255-257
+    bool se = false, keep = false, n_given = false, seedSpecified = false; uint64_t seed = 0;
+    DamageSpec dAll, dE, dB, dC;
+    const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
+        "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
+        "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t--seed [int]\t--gpus [N]\t--keep\n";
+    if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }
+    for (int i = 1; i < argc - 1; i++) {
+        std::string a = argv[i]; if (a.size() > 2 && a[0] == '-' && a[1] == '-') a = a.substr(1);      // Getopt::Long takes -x and --x
+        auto next = [&]() -> const char* { if (i + 1 >= argc - 1 + 1) { std::cerr << "Error: option " << a << " needs a value" << std::endl; exit(1); } return argv[++i]; };
+        if (a == "-comp") { comp = next(); continue; }
+        if (a == "-o") { prefix = next(); continue; }
+        if (a == "-n") { n = (uint64_t)to_ll(next(), "-n"); n_given = true; continue; }
+        if (a == "-c") { coverage = to_d(next(), "-c"); continue; }
+        if (a == "-l") { fraglength = (int)to_ll(next(), "-l"); continue; }
+        if (a == "-s") { sizeList = next(); continue; }
+        if (a == "-f") { sizeFreq = next(); continue; }
+        if (a == "-minsize") { minsize = (int)to_ll(next(), "-minsize"); continue; }
+        if (a == "-maxsize") { maxsize = (int)to_ll(next(), "-maxsize"); continue; }
+        if (a == "-matfile") { dAll.matfile = next(); continue; }
+        if (a == "-damage") { dAll.briggs = next(); continue; }
+        if (a == "-mapdamage") { dAll.mapd_file = next(); dAll.mapd_proto = next(); continue; }
+        if (a == "-matfilee") { dE.matfile = next(); continue; }  if (a == "-damagee") { dE.briggs = next(); continue; }
+        if (a == "-matfileb") { dB.matfile = next(); continue; }  if (a == "-damageb") { dB.briggs = next(); continue; }
+        if (a == "-matfilec") { dC.matfile = next(); continue; }  if (a == "-damagec") { dC.briggs = next(); continue; }
+        if (a == "-mapdamagee") { dE.mapd_file = next(); dE.mapd_proto = next(); continue; }
+        if (a == "-mapdamageb") { dB.mapd_file = next(); dB.mapd_proto = next(); continue; }
+        if (a == "-mapdamagec") { dC.mapd_file = next(); dC.mapd_proto = next(); continue; }
+        if (a == "-fa") { adF = next(); continue; }  if (a == "-sa") { adS = next(); continue; }
+        if (a == "-rl") { rl = (int)to_ll(next(), "-rl"); continue; }
+        if (a == "-se") { se = true; continue; }
+        if (a == "-seed") { seed = (uint64_t)to_ll(next(), "--seed"); seedSpecified = true; continue; }
+        if (a == "-gpus") { gpus = (int)to_ll(next(), "--gpus"); continue; }
+        if (a == "-keep") { keep = true; continue; }
+        if (a == "-mock" || a == "-methyl" || a == "-uniq" || a == "-ss" || a == "-distmis" || a == "-misince" || a == "-misincb" || a == "-misincc" ||
+            a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-loc" || a == "-scale" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
+        return die("Unknown option: " + a);
+    }
+    if (coverage >= 0 && n_given) return die("Must use the -c or -n but not both");                    // gargammel.pl:753-756
+    std::vector<std::string> c3 = ggh::all_tokens(comp, ',');
+    if (c3.size() != 3) return die("the --comp option must have 3 comma-delimited fields, found " + std::to_string(c3.size()));   // :748-751
+    compB = to_d(c3[0].c_str(), "--comp"); compC = to_d(c3[1].c_str(), "--comp"); compE = to_d(c3[2].c_str(), "--comp");
+    if (coverage >= 0 && compE == 0) return die("Cannot use the endogenous coverage -c and not specify some level of endogenous content.");   // :778-780
+    if (dAll.any()) {                                                              // -matfile/-damage/-mapdamage => endogenous + bacterial only (gargammel.pl:619-648)
+        if (dE.any() || dB.any() || dC.any()) return die("Specify either patterns for endogenous and bacterial using either -matfile or -damage but do not specify other parameters");
+        dE = dAll; dB = dAll;
+    }
+    for (size_t i = 0; i < adF.size(); i++) adF[i] = (char)toupper(adF[i]);         // uc(), gargammel.pl:469-475
+    for (size_t i = 0; i < adS.size(); i++) adS[i] = (char)toupper(adS[i]);
+    if (!seedSpecified) seed = time_seed();
+    std::string dir = argv[argc - 1]; if (dir.empty() || dir[dir.size() - 1] != '/') dir += "/";
+    if (prefix.empty()) prefix = dir + "simadna";                                   // gargammel.pl usage
+    std::string err;
+
+    // ---- scan the three directories (gargammel.pl:817-1181)
+    std::vector<std::string> fE = list_fa(dir + "endo/"), fC = list_fa(dir + "cont/"), fB = list_fa(dir + "bact/");
+    if (compE > 0 && fE.size() != 1 && fE.size() != 2) return die("The endogenous directory must have 1 (haploid) or 2 (diploid) files, found: " + std::to_string(fE.size()));
+    if (compC > 0 && fC.empty()) return die("If you want contamination, please have at least one file in the cont/ directory");
+    std::vector<double> bw;
+    if (compB > 0) {
+        if (fB.empty()) return die("If you want bacterial contamination, please have at least one file in the bact/ directory");
+        std::vector<std::string> names; std::vector<double> w;
+        if (!ggh::load_bact_list(dir + "bact/list", names, w, err)) return die(err);
+        bw.assign(fB.size(), 0.0); std::vector<int> seen(names.size(), 0);
+        for (size_t j = 0; j < fB.size(); j++)
+            for (size_t k = 0; k < names.size(); k++) if (dir + "bact/" + names[k] == fB[j]) { bw[j] = w[k]; seen[k]++; }   // counts go to the file NAMED in the list (DESIGN.md deviation from gargammel.pl:1343)
+        for (size_t k = 0; k < names.size(); k++) {
+            if (seen[k] == 0) return die("Fasta  " + names[k] + " was not found in the directory but it was found in the list");
+            if (seen[k] > 1) return die("Fasta  " + names[k] + " was found twice in the list");
+        }
+    }
+    // ---- load genomes (only the sources that get fragments)
+    struct Src { std::string path; ggh::GenomeFile g; char kind; int idx; };
+    std::vector<Src> srcs;
+    auto add = [&](const std::vector<std::string>& files, char kind, bool wanted) -> bool {
+        for (size_t i = 0; i < files.size(); i++) {
+            Src s; s.path = files[i]; s.kind = kind; s.idx = (int)i;
+            if (wanted) { if (!ggh::load_genome(files[i], s.g, err)) return false; std::cerr << "Found " << (kind == 'e' ? "endogenous" : kind == 'c' ? "contaminant" : "bacterial") << " file " << files[i] << " (" << s.g.total_len << " bp)" << std::endl; }
+            else s.g.total_len = 0;
+            srcs.push_back(s);
+        }
+        return true;
+    };
+    if (!add(fE, 'e', compE > 0) || !add(fB, 'b', compB > 0) || !add(fC, 'c', compC > 0)) return die(err);
+    uint64_t sumE = 0; std::vector<uint64_t> contLen;
+    for (size_t i = 0; i < srcs.size(); i++) { if (srcs[i].kind == 'e') sumE += srcs[i].g.total_len; if (srcs[i].kind == 'c') contLen.push_back(srcs[i].g.total_len); }
+
+    // ---- size model + average size (gargammel.pl:1185-1229)
+    std::vector<int32_t> lens; std::vector<double> cum; double avg = fraglength;
+    if (!sizeList.empty()) { if (!ggh::load_size_list(sizeList, lens, err)) return die(err); double t = 0; for (size_t i = 0; i < lens.size(); i++) t += lens[i]; avg = t / lens.size(); }
+    else if (!sizeFreq.empty()) { if (!ggh::load_size_freq(sizeFreq, lens, cum, err)) return die(err); double t = 0, prev = 0; for (size_t i = 0; i < lens.size(); i++) { t += lens[i] * (cum[i] - prev); prev = cum[i]; } avg = t / cum.back(); }
+    // ---- number of fragments (gargammel.pl:1236-1266)
+    ggh::ApportionIn in; in.compB = compB; in.compC = compC; in.compE = compE; in.n_endo = (int)std::max<size_t>(fE.size(), 1); in.cont_len = contLen; in.bact_w = bw; in.seed = seed;
+    if (coverage >= 0) {
+        double use = avg; if (se) { if (rl < avg) use = rl; } else if (2 * rl < avg) use = 2 * rl;
+        const double sumEeff = fE.size() == 2 ? sumE / 2.0 : (double)sumE;
+        const uint64_t nE = (uint64_t)(coverage * (sumEeff / use));
+        n = (uint64_t)((double)nE / compE);
+    }
+    in.n_fragments = n;
+    ggh::ApportionOut ap;
+    if (!ggh::apportion(in, ap, err)) return die(err);
+    const uint64_t total = ap.nE + ap.nB + ap.nC;
+    std::cerr << "We will generate: \n\n" << total << "\ttotal fragments\n" << ap.nE << "\tendogenous fragments\n" << ap.nC << "\tcontaminant fragments\n" << ap.nB << "\tbacterial fragments\n";
+
+    // ---- plan in the reference's output order e, b, c with its tag grammar (gargammel.pl:1476,1521,1554,1600,1648; 1698-1830)
+    struct PlanItem { size_t src; uint64_t count; std::string tag; int slot; };
+    std::vector<PlanItem> items;
+    for (size_t i = 0; i < srcs.size(); i++) {
+        const Src& s = srcs[i]; PlanItem it; it.src = i; it.count = 0; it.slot = -1;
+        if (s.kind == 'e') { it.count = ap.endo[s.idx]; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; }
+        if (s.kind == 'b') { it.count = ap.bact[s.idx]; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; }
+        if (s.kind == 'c') { it.count = ap.cont[s.idx]; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; }
+        if (it.count) items.push_back(it);
+    }
+    if (gpus < 1) gpus = 1;
+    const int emit = se ? GG_EMIT_ARTS : GG_EMIT_ARTP;
+    // ---- one worker per GPU: rank r takes the r-th contiguous slice of the id space; outputs are concatenated in rank order
+    std::vector<std::string> shard(gpus), shard_err(gpus); std::vector<int> rcs(gpus, 0);
+    std::vector<std::vector<std::string> > shard_keep(gpus, std::vector<std::string>(4));
+    auto worker = [&](int r) {
+        gg_ctx* ctx = NULL;
+        if (gg_ctx_create(r, seed, &ctx) != GG_OK) { shard_err[r] = "cannot open CUDA device " + std::to_string(r) + " (no CPU fallback)"; rcs[r] = 1; return; }
+        auto fail = [&](const char* what) { shard_err[r] = std::string(what) + ": " + gg_last_error(ctx); rcs[r] = 1; gg_ctx_destroy(ctx); };
+        std::vector<gg_range> plan; uint64_t first = 0;
+        for (size_t k = 0; k < items.size(); k++) {
+            int gid = -1;
+            if (ggh::upload_genome(ctx, srcs[items[k].src].g, &gid) != GG_OK) return fail("genome upload");
+            gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot;
+            snprintf(rg.tag, sizeof rg.tag, "%s", items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;
+        }
+        const int mode = !sizeList.empty() ? GG_SIZE_LIST : !sizeFreq.empty() ? GG_SIZE_FREQ : GG_SIZE_FIXED;
+        if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
+        if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) { rcs[r] = 1; gg_ctx_destroy(ctx); return; }
+        if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), rl) != GG_OK) return fail("adapters");
+        if (!plan.empty() && gg_plan_set(ctx, plan.data(), (int)plan.size()) != GG_OK) return fail("plan");
+        const uint64_t lo = total * (uint64_t)r / (uint64_t)gpus, hi = total * (uint64_t)(r + 1) / (uint64_t)gpus;
+        const uint64_t chunk = 8u << 20;
+        int emits[3] = {emit, GG_EMIT_FRAG, GG_EMIT_DEAM};
+        for (int pass = 0; pass < (keep ? 3 : 1); pass++)
+            for (uint64_t a = lo; a < hi; a += chunk) {
+                const uint64_t cnt = std::min<uint64_t>(chunk, hi - a);
+                gg_out o;
+                if (gg_run_fused(ctx, a, cnt, emits[pass], &o) != GG_OK) return fail("fused kernel");
+                std::string& dst = pass == 0 ? shard[r] : shard_keep[r][pass];
+                const size_t old = dst.size(); dst.resize(old + o.bytes); size_t got = 0;
+                if (gg_out_fetch(ctx, &o, &dst[old], o.bytes, &got) != GG_OK) return fail("fetch");
+            }
+        gg_ctx_destroy(ctx);
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < gpus; r++) th.push_back(std::thread(worker, r));
+    for (int r = 0; r < gpus; r++) th[r].join();
+    for (int r = 0; r < gpus; r++) if (rcs[r]) return die("Error: " + shard_err[r]);
+    Sink out;
+    if (!out.open_plain(prefix + "_a.fa")) return die("Cannot write to file " + prefix + "_a.fa");
+    for (int r = 0; r < gpus; r++) if (!out.write(shard[r].data(), shard[r].size())) return die("Error: write failed");
+    if (!out.close()) return die("Error: write failed");
+    if (keep) {
+        // <prefix>_d.fa.gz = deamSim output in e,b,c order; <prefix>.{e,b,c}.fa.gz = the fragSim outputs per source class
+        Sink d; if (!d.open_gz(prefix + "_d.fa.gz")) return die("Cannot write to file " + prefix + "_d.fa.gz");
+        for (int r = 0; r < gpus; r++) d.write(shard_keep[r][2].data(), shard_keep[r][2].size());
+        d.close();
+        std::string all; for (int r = 0; r < gpus; r++) all += shard_keep[r][1];
+        Sink se_, sb_, sc_;
+        if (!se_.open_gz(prefix + ".e.fa.gz") || !sb_.open_gz(prefix + ".b.fa.gz") || !sc_.open_gz(prefix + ".c.fa.gz")) return die("Cannot write intermediate files for prefix " + prefix);
+        size_t p = 0; uint64_t rec = 0;
+        while (p < all.size()) {                                   // records are in e,b,c order: split by count
+            size_t e1 = all.find('\n', p); size_t e2 = e1 == std::string::npos ? e1 : all.find('\n', e1 + 1);
+            if (e2 == std::string::npos) break;
+            Sink& s = rec < ap.nE ? se_ : rec < ap.nE + ap.nB ? sb_ : sc_;
+            s.write(all.data() + p, e2 + 1 - p); p = e2 + 1; rec++;
+        }
+        se_.close(); sb_.close(); sc_.close();
+    }
+    std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << total << " sequences to " << prefix << "_a.fa" << std::endl;
+    return 0;
+}

@@ -39,7 +39,7 @@ struct HostGenome {
     std::vector<HostContig> contigs;      // name-sorted (std::map order, fragSim.cpp:215,1152)
     std::vector<int> fai2sorted;
     uint64_t G, n_units;
-    uint32_t* d_seq2; uint32_t* d_nmask;
+    uint32_t* d_seq2; uint32_t* d_nmask; size_t seq2_bytes, nmask_bytes;
     int first_contig;
 };
 struct HostDamage {
@@ -94,6 +94,8 @@ struct gg_ctx {
     // plan
     std::vector<gg_range> plan; DBuf d_ranges; bool plan_dirty;
     // run state
+    std::vector<std::pair<void*, size_t> > pool;     // device blocks of cleared genomes, reused by the next uploads
+    DBuf d_tmp_fa, d_tmp_desc;                       // upload staging (raw FASTA bytes, contig descriptors)
     DBuf d_out, d_out2, d_tile_state, d_ticket_stats, d_in, d_nl, d_scan, d_sizes, d_flush;
     void* h_pinned; size_t h_pinned_cap;
     double last_ms;
@@ -235,6 +237,20 @@ void plan_bounds(const gg_ctx* ctx, int emit, int Lmax, int* hdr_max, uint64_t* 
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// best-fit block from the context's pool of cleared genome storage, else cudaMalloc (cudaFree/cudaMalloc cost tens of ms)
+cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].second >= bytes && (best < 0 || ctx->pool[i].second < ctx->pool[best].second)) best = (int)i;
+    if (best >= 0 && ctx->pool[best].second <= 2 * bytes + (1u << 20)) {
+        *p = ctx->pool[best].first; *got = ctx->pool[best].second;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return cudaSuccess;
+    }
+    *got = bytes;
+    return cudaMalloc(p, bytes);
+}
+
 // shared-memory carve-up for F fragments per tile
 SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words) {
     SmemLayout s; int o = 0;
@@ -295,11 +311,12 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); }
     DBuf* bufs[] = {&ctx->d_cum_end, &ctx->d_gbase, &ctx->d_clen, &ctx->d_name_off, &ctx->d_name_len, &ctx->d_names, &ctx->d_genomes,
                     &ctx->d_size_len, &ctx->d_size_thr, &ctx->d_adF2, &ctx->d_adS2, &ctx->d_rcS2, &ctx->d_adF, &ctx->d_adS, &ctx->d_ranges,
-                    &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
+                    &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
         ctx->dmg[s].d_thr.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release();
     }
+    for (size_t i = 0; i < ctx->pool.size(); i++) cudaFree(ctx->pool[i].first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -342,24 +359,31 @@ int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_e
     const size_t nc = H.contigs.size();
     std::vector<uint64_t> off(nc), gbase(nc); std::vector<uint32_t> len(nc); std::vector<int32_t> blen(nc), llen(nc);
     for (size_t i = 0; i < nc; i++) { off[i] = H.contigs[i].offset; gbase[i] = H.contigs[i].gbase; len[i] = (uint32_t)H.contigs[i].len; blen[i] = H.contigs[i].blen; llen[i] = H.contigs[i].llen; }
-    uint8_t* d_fa = nullptr; uint64_t* d_off = nullptr; uint64_t* d_gb = nullptr; uint32_t* d_len = nullptr; int32_t* d_bl = nullptr; int32_t* d_ll = nullptr;
-    cudaError_t e = cudaSuccess;
+    // staging (reused across uploads): raw FASTA bytes + contig descriptors
+    const size_t desc_bytes = nc * (8 + 8 + 4 + 4 + 4) + 64;
+    CK(ctx->d_tmp_fa.ensure(n + 16));
+    CK(ctx->d_tmp_desc.ensure(desc_bytes));
+    uint8_t* d_fa = ctx->d_tmp_fa.as<uint8_t>();
+    uint64_t* d_off = ctx->d_tmp_desc.as<uint64_t>(); uint64_t* d_gb = d_off + nc;
+    uint32_t* d_len = (uint32_t*)(d_gb + nc); int32_t* d_bl = (int32_t*)(d_len + nc); int32_t* d_ll = d_bl + nc;
+    void* p1 = nullptr; void* p2 = nullptr;
+    cudaError_t e = pool_alloc(ctx, (H.n_units * 2 + 4) * 4, &p1, &H.seq2_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (H.n_units + 4) * 4, &p2, &H.nmask_bytes);
+    H.d_seq2 = (uint32_t*)p1; H.d_nmask = (uint32_t*)p2;
 #define TRY(x) if (e == cudaSuccess) e = (x)
-    TRY(cudaMalloc(&d_fa, n + 16));
-    TRY(cudaMalloc(&d_off, nc * 8)); TRY(cudaMalloc(&d_gb, nc * 8)); TRY(cudaMalloc(&d_len, nc * 4)); TRY(cudaMalloc(&d_bl, nc * 4)); TRY(cudaMalloc(&d_ll, nc * 4));
-    TRY(cudaMalloc(&H.d_seq2, (H.n_units * 2 + 4) * 4)); TRY(cudaMalloc(&H.d_nmask, (H.n_units + 4) * 4));
-    TRY(cudaMemsetAsync(H.d_seq2, 0, (H.n_units * 2 + 4) * 4, ctx->st)); TRY(cudaMemsetAsync(H.d_nmask, 0xFF, (H.n_units + 4) * 4, ctx->st));
     TRY(cudaMemcpyAsync(d_fa, fasta, n, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_off, off.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_gb, gbase.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_len, len.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_bl, blen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_ll, llen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
+    // every unit (incl. the guard units in front and the slack behind) is written by the pack kernel
     TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, nullptr, (int)nc, H.n_units, H.d_seq2, H.d_nmask, ctx->st));
+    TRY(cudaMemsetAsync(H.d_seq2 + H.n_units * 2, 0, 16, ctx->st));
+    TRY(cudaMemsetAsync(H.d_nmask + H.n_units, 0xFF, 16, ctx->st));
     TRY(cudaStreamSynchronize(ctx->st));
 #undef TRY
-    cudaFree(d_fa); cudaFree(d_off); cudaFree(d_gb); cudaFree(d_len); cudaFree(d_bl); cudaFree(d_ll);
-    if (e != cudaSuccess) { cudaFree(H.d_seq2); cudaFree(H.d_nmask); return ctx->cuda_fail(e, "gg_genome_upload"); }
+    if (e != cudaSuccess) { if (p1) cudaFree(p1); if (p2) cudaFree(p2); return ctx->cuda_fail(e, "gg_genome_upload"); }
     ctx->genomes.push_back(H);
     ctx->ctab_dirty = true;
     if (genome_id_out) *genome_id_out = (int)ctx->genomes.size() - 1;
@@ -370,7 +394,10 @@ int gg_genome_clear(gg_ctx* ctx) {
     if (!ctx) return GG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->st));
-    for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); }
+    for (size_t g = 0; g < ctx->genomes.size(); g++) {
+        ctx->pool.push_back(std::make_pair((void*)ctx->genomes[g].d_seq2, ctx->genomes[g].seq2_bytes));
+        ctx->pool.push_back(std::make_pair((void*)ctx->genomes[g].d_nmask, ctx->genomes[g].nmask_bytes));
+    }
     ctx->genomes.clear(); ctx->plan.clear(); ctx->ctab_dirty = true; ctx->plan_dirty = true;
     return GG_OK;
 }

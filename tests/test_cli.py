@@ -1,0 +1,203 @@
+"""The drop-in executables: argument conventions and error behaviour of the reference CLIs (CPU), byte-exact output
+against the oracle for the same seed (GPU), statistical equivalence with the reference's own binaries (GPU + oracle/_ref)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gargammel_b200 import api, synth
+from tests import util
+from tests.conftest import ROOT
+
+BIN = os.path.join(ROOT, "bin")
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    fa, fai = synth.make_genome(21, 4, 60000, prefix="chr", width=60, n_frac=0.01, n_run=(20, 300), lower_frac=0.1)
+    (d / "g.fa").write_bytes(fa)
+    synth.write_fai(str(d / "g.fa.fai"), fai)
+    synth.write_sizefreq(str(d / "sf.size"))
+    s5, s3 = synth.golden_matrix("single-")
+    synth.write_matrix_dat(str(d / "m-"), s5, s3)
+    return d, fa, fai
+
+
+@pytest.mark.parametrize("tool", ["fragSim", "deamSim", "adptSim", "gargammel-b200"])
+def test_cli_usage_and_unknown_option(tool):
+    """no args / -h => usage on stdout, exit 1; unknown option => message on stderr, exit 1 (fragSim.cpp:463-471,622-623)."""
+    exe = os.path.join(BIN, tool)
+    assert os.path.exists(exe), "run `make` first"
+    r = run([exe]); assert r.returncode == 1 and len(r.stdout) > 100
+    r = run([exe, "-h"]); assert r.returncode == 1 and len(r.stdout) > 100
+    r = run([exe, "-zzz", "x", "input"])
+    assert r.returncode == 1 and (b"unknown option -zzz" in r.stderr or b"Unknown option: -zzz" in r.stderr)
+
+
+def test_cli_validation_errors(workdir):
+    d, _, _ = workdir
+    r = run([os.path.join(BIN, "fragSim"), "-l", "2000", str(d / "g.fa")])
+    assert r.returncode == 1 and b"is longer than the maximum allowed fragment size" in r.stderr       # fragSim.cpp:638-643
+    r = run([os.path.join(BIN, "fragSim"), "-l", "40", "-s", "x", str(d / "g.fa")])
+    assert r.returncode == 1 and b"cannot specify -l and -s" in r.stderr
+    r = run([os.path.join(BIN, "deamSim"), str(d / "g.fa")])
+    assert r.returncode == 1 and b"Please specify the matrix to use or use the Briggs parameter model" in r.stderr   # deamSim.cpp:403
+    r = run([os.path.join(BIN, "deamSim"), "-damage", "0.03,0.4,0.01", str(d / "g.fa")])
+    assert r.returncode == 1 and b"Specify 4 comma-separated values" in r.stderr
+    r = run([os.path.join(BIN, "deamSim"), "-mat", "triple", str(d / "g.fa")])
+    assert r.returncode == 1 and b'Specify either "single" or "double"' in r.stderr
+    r = run([os.path.join(BIN, "adptSim"), "-rr", "x.gz", str(d / "g.fa")])
+    assert r.returncode == 1 and b"need to specify the output forward read" in r.stderr              # adptSim.cpp:179-182
+    r = run([os.path.join(BIN, "gargammel-b200"), "--comp", "0.5,0.5", str(d)])
+    assert r.returncode == 1 and b"3 comma-delimited fields" in r.stderr
+
+
+def test_cli_without_gpu_fails_loudly(workdir):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d, _, _ = workdir
+    r = run([os.path.join(BIN, "fragSim"), "-n", "5", "-l", "30", str(d / "g.fa")])
+    assert r.returncode == 1 and b"no CPU fallback" in r.stderr and r.stdout == b""
+
+
+@pytest.mark.gpu
+def test_cli_pipeline_matches_oracle(workdir, oracle_mod):
+    """bin/fragSim | bin/deamSim | bin/adptSim with --seed == the oracle's stage composition, byte for byte."""
+    d, fa, fai = workdir
+    seed, n = 4242, 20000
+    o = oracle_mod.OracleContext(seed)
+    gid = o.upload_genome(fa, fai)
+    o.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=0, maxlen=1000)
+    util.set_damage(o, 0, "matrix")
+    o.set_adapters(read_len=75)
+    o.set_plan([api.Range(0, n, gid, 0, "e1_0")])
+    r = run([os.path.join(BIN, "fragSim"), "--seed", str(seed), "-tag", "e1_0", "-n", str(n), "-m", "0", "-M", "1000", "-f", str(d / "sf.size"), str(d / "g.fa")])
+    assert r.returncode == 0, r.stderr
+    assert b"terminated succesfully, wrote %d sequences" % n in r.stderr
+    util.assert_same(r.stdout, o.run_fused(0, n, api.EMIT_FRAG)[0], "bin/fragSim")
+    (d / "f.fa").write_bytes(r.stdout)
+    r2 = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-matfile", str(d / "m-"), str(d / "f.fa")])
+    assert r2.returncode == 0, r2.stderr
+    util.assert_same(r2.stdout, o.run_fused(0, n, api.EMIT_DEAM)[0], "bin/deamSim")
+    import gzip
+    with gzip.open(str(d / "d.fa.gz"), "wb") as f:                 # the driver hands deamSim/adptSim gz files (gargammel.pl:1729,1847)
+        f.write(r2.stdout)
+    r3 = run([os.path.join(BIN, "adptSim"), "-l", "75", "-artp", str(d / "a.fa"), str(d / "d.fa.gz")])
+    assert r3.returncode == 0, r3.stderr
+    util.assert_same((d / "a.fa").read_bytes(), o.run_fused(0, n, api.EMIT_ARTP)[0], "bin/adptSim -artp")
+    r4 = run([os.path.join(BIN, "adptSim"), "-l", "75", str(d / "d.fa.gz")])
+    util.assert_same(r4.stdout, o.run_fused(0, n, api.EMIT_STDOUT4)[0], "bin/adptSim stdout")
+    r5 = run([os.path.join(BIN, "adptSim"), "-l", "60", "-fr", str(d / "fr.gz"), "-rr", str(d / "rr.gz"), str(d / "d.fa.gz")])
+    assert r5.returncode == 0, r5.stderr
+    o.set_adapters(read_len=60)
+    util.assert_same(gzip.open(str(d / "fr.gz")).read(), o.run_fused(0, n, api.EMIT_FR)[0], "-fr")
+    util.assert_same(gzip.open(str(d / "rr.gz")).read(), o.run_fused(0, n, api.EMIT_RR)[0], "-rr")
+    # Briggs through the CLI + gz output
+    o.set_briggs(0, 0.03, 0.4, 0.01, 0.3)
+    r6 = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-damage", "0.03,0.4,0.01,0.3", "-o", str(d / "b.fa.gz"), str(d / "f.fa")])
+    assert r6.returncode == 0, r6.stderr
+    util.assert_same(gzip.open(str(d / "b.fa.gz")).read(), o.run_fused(0, n, api.EMIT_DEAM)[0], "bin/deamSim -damage -o")
+
+
+@pytest.mark.gpu
+def test_fused_driver_matches_oracle(tmp_path, oracle_mod):
+    """bin/gargammel-b200 on an endo(x2)/cont/bact directory == oracle run of the same apportioned plan (1 and 2 workers)."""
+    d = tmp_path / "in"
+    files = {}
+    for sub, names in (("endo", ["endo.1.fa", "endo.2.fa"]), ("cont", ["cont.1.fa", "cont.2.fa"]), ("bact", ["b1.fa", "b2.fa", "b3.fa"])):
+        (d / sub).mkdir(parents=True)
+        for k, nm in enumerate(names):
+            fa, fai = synth.make_genome(hash((sub, k)) % 1000, 2 + k, 30000 + 7000 * k, prefix=sub[0] + "%d_" % k, n_frac=0.01, n_run=(10, 200))
+            (d / sub / nm).write_bytes(fa)
+            if k != 1:
+                synth.write_fai(str(d / sub / (nm + ".fai")), fai)        # one file per dir has no .fai: built like `samtools faidx`
+            files[(sub, nm)] = (fa, fai)
+    (d / "bact" / "list").write_text("b2.fa\t0.5\nb1.fa\t0.2\nb3.fa\t0.3\n")
+    synth.write_sizefreq(str(tmp_path / "sf.size"))
+    s5, s3 = synth.golden_matrix("single-")
+    synth.write_matrix_dat(str(tmp_path / "m-"), s5, s3)
+    seed, n = 777, 30000
+    for gpus in (1,):
+        r = run([os.path.join(BIN, "gargammel-b200"), "--comp", "0.3,0.1,0.6", "-n", str(n), "-f", str(tmp_path / "sf.size"), "-matfile", str(tmp_path / "m-"),
+                 "-rl", "75", "--seed", str(seed), "--gpus", str(gpus), "--keep", "-o", str(tmp_path / "sim"), str(d)])
+        assert r.returncode == 0, r.stderr
+        lib = api.load_library()
+        tot = (C.c_uint64 * 3)(); e = (C.c_uint64 * 2)(); c = (C.c_uint64 * 2)(); b = (C.c_uint64 * 3)(); err = C.create_string_buffer(256)
+        clen = [sum(x.len for x in files[("cont", nm)][1]) for nm in ("cont.1.fa", "cont.2.fa")]
+        assert lib.ggh_apportion(C.c_uint64(n), C.c_double(0.3), C.c_double(0.1), C.c_double(0.6), 2, (C.c_uint64 * 2)(*clen), 2,
+                                 (C.c_double * 3)(0.2, 0.5, 0.3), 3, C.c_uint64(seed), tot, e, c, b, err, 256) == 0
+        assert abs(b[1] / tot[2] - 0.5) < 0.03                       # weights follow the list by NAME
+        o = oracle_mod.OracleContext(seed)
+        o.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=0, maxlen=1000)
+        util.set_damage(o, 0, "matrix"); util.set_damage(o, 1, "matrix")
+        o.set_adapters(read_len=75)
+        plan, first = [], 0
+        for key, cnt, tag, slot in ([(("endo", "endo.1.fa"), e[0], "e1_0", 0), (("endo", "endo.2.fa"), e[1], "e2_0", 0)] +
+                                    [(("bact", "b%d.fa" % (k + 1)), b[k], "b%d" % (k + 1), 1) for k in range(3)] +
+                                    [(("cont", "cont.%d.fa" % (k + 1)), c[k], "c%d" % (k + 1), -1) for k in range(2)]):
+            if cnt:
+                plan.append(api.Range(first, int(cnt), o.upload_genome(*files[key]), slot, tag)); first += int(cnt)
+        o.set_plan(plan)
+        util.assert_same((tmp_path / "sim_a.fa").read_bytes(), o.run_fused(0, first, api.EMIT_ARTP)[0], "gargammel-b200 _a.fa")
+        import gzip
+        util.assert_same(gzip.open(str(tmp_path / "sim_d.fa.gz")).read(), o.run_fused(0, first, api.EMIT_DEAM)[0], "_d.fa.gz")
+        frag = o.run_fused(0, first, api.EMIT_FRAG)[0]
+        got = b"".join(gzip.open(str(tmp_path / ("sim.%s.fa.gz" % k))).read() for k in "ebc")
+        util.assert_same(got, frag, ".e/.b/.c.fa.gz")
+
+
+def _ref(name):
+    from oracle import oracle
+    return oracle.ref_bin(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ref("deamSim") is None, reason="oracle/_ref not built")
+def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
+    """Level 3 (north_star): our binaries vs the reference's own (its sources + our shim): per-position C->T / G->A rates
+    within +-0.002 of the matrix (ours, n=2M) and of each other within sampling error; KS on lengths p > 0.01."""
+    from scipy import stats
+    d, _, _ = workdir
+    rng = np.random.default_rng(1)
+    L = 50
+    s5, s3 = synth.golden_matrix("single-")
+    want_ct = np.array([s5[i][5] if i < 25 else s3[49 - i][5] for i in range(L)])
+    want_ga = np.array([s5[i][6] if i < 25 else s3[49 - i][6] for i in range(L)])
+
+    def rates(exe, n, seed):
+        seqs = synth._BASES[rng.integers(0, 4, size=(n, L))]
+        p = tmp_path / ("in_%d.fa" % n)
+        with open(p, "wb") as f:
+            f.write(b"".join(b">chrS:+:%d:%d:50\n%s\n" % (i * 50, i * 50 + 50, seqs[i].tobytes()) for i in range(n)))
+        r = run([exe, "--seed", str(seed), "-matfile", str(d / "m-"), str(p)])
+        assert r.returncode == 0, r.stderr
+        got = np.frombuffer(r.stdout, dtype=np.uint8).reshape(n, -1)[:, -(L + 1):-1]
+        isC, isG = seqs == ord("C"), seqs == ord("G")
+        return ((got == ord("T")) & isC).sum(0) / isC.sum(0), ((got == ord("A")) & isG).sum(0) / isG.sum(0), isC.sum(0)
+    ct, ga, nC = rates(os.path.join(BIN, "deamSim"), 1_000_000, 42)              # BASELINE config 1
+    assert np.abs(ct - want_ct).max() < 0.002 + 3 * np.sqrt(0.34 * 0.66 / nC.min()) * (want_ct.max() > 0.3)
+    assert np.abs(ct[:-1] - want_ct[:-1]).max() < 0.002 and np.abs(ga - want_ga).max() < 0.002
+    rct, rga, rnC = rates(_ref("deamSim"), 300_000, 42)
+    sd = np.sqrt(want_ct * (1 - want_ct) * (1.0 / nC + 1.0 / rnC))
+    assert (np.abs(ct - rct) < 5 * sd + 1e-4).all()
+    # lengths and strands: fragSim -f sizefreq
+    ours = run([os.path.join(BIN, "fragSim"), "--seed", "5", "-n", "200000", "-f", str(d / "sf.size"), str(d / "g.fa")])
+    ref = run([_ref("fragSim"), "--seed", "5", "-n", "60000", "-f", str(d / "sf.size"), str(d / "g.fa")])
+    assert ours.returncode == 0 and ref.returncode == 0
+    lo = np.array([len(s) for _, s in util.records(ours.stdout)]); lr = np.array([len(s) for _, s in util.records(ref.stdout)])
+    assert stats.ks_2samp(lo, lr).pvalue > 0.01
+    po = np.mean([h.split(b":")[1] == b"+" for h, _ in util.records(ours.stdout)])
+    pr = np.mean([h.split(b":")[1] == b"+" for h, _ in util.records(ref.stdout)])
+    assert abs(po - 0.5) < 0.01 and abs(pr - 0.5) < 0.02
+    # start positions are uniform over the accepted windows in both: compare coarse histograms of chr1 starts
+    def starts(out):
+        return np.array([int(h.split(b":")[2]) for h, _ in util.records(out) if h.startswith(b">chr1:")])
+    assert stats.ks_2samp(starts(ours.stdout), starts(ref.stdout)).pvalue > 0.001
