@@ -251,17 +251,16 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
     return cudaMalloc(p, bytes);
 }
 
-// shared-memory carve-up for F fragments per tile
-SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words) {
+// shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared LUT
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes) {
     SmemLayout s; int o = 0;
-    s.lut = o; o += 1024;
     o += 16;                                   // readable slack before staging
     s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
     s.gpos = o; o += 8 * F;
     s.idx = o; o += 8 * F;
-    s.ci = o; o += 4 * F;
     s.meta = o; o += 4 * F;
     s.recoff = o; o += 4 * F;
+    s.ci = o; o += 4 * F;
     o += 4;                                    // guard word in front of the damaged-fragment words
     s.dwords = o; o += 4 * (F * max_chunks + 4);
     s.lwords = o; o += 4 * (F * line_words + 4);
@@ -271,7 +270,10 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.rg = o; o += 2 * F;
     s.cmap = o; o += F * max_chunks;
     s.gmap = o; o += F * max_groups;
-    s.total = align_up(o, 16);
+    s.warp_bytes = align_up(o, 16);
+    s.lut = 0; s.thr = 1024; s.thr_bytes = thr_bytes; s.warp0 = 1024 + align_up(thr_bytes, 16);
+    for (int i = 0; i < 4; i++) s.thr_slot[i] = -1;
+    s.total = s.warp0 + warps * s.warp_bytes;
     return s;
 }
 
@@ -614,20 +616,34 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     }
     const int fast_boundary = (min_name_tag >= 4 && !getenv("GG_FUSED_NOFAST")) ? 1 : 0;
 
-    // fragments per tile: the largest F <= 256 whose tile fits the shared memory of `ctas` co-resident CTAs
-    const size_t sm_budget = 227 * 1024;
-    int F = 0, ctas = 0;
-    const char* envF = getenv("GG_FUSED_F"); const char* envC = getenv("GG_FUSED_CTAS");
-    for (int t = envC ? atoi(envC) : 3; t >= 1 && F == 0; t--) {
-        const size_t per_cta = std::min(sm_budget / (size_t)t - 1024, ctx->smem_optin);
-        int f = envF ? atoi(envF) : FUSED_THREADS;
-        f = std::max(1, std::min(f, FUSED_THREADS));
-        while (f >= 1 && (size_t)make_layout(f, rec_max, max_chunks, max_groups, line_words).total > per_cta) f = (f > 32) ? f - 16 : f - 1;
-        if (f >= (t > 1 ? 128 : 1)) { F = f; ctas = t; }
+    // One warp per tile of F = 32 fragments (fewer only if 32 maximal records do not fit one warp's shared memory);
+    // warps per CTA chosen to fill the SM: limited by shared memory, registers and the kernel's launch bound.
+    const size_t sm_budget = std::min<size_t>(227 * 1024, ctx->smem_optin) - 2304;   // static: length guide table
+    int dmode = 1;                                   // matrix-only specialisation unless some used slot is Briggs / single / double
+    for (size_t i = 0; i < ctx->plan.size(); i++) { const int sl = ctx->plan[i].damage_slot; if (sl >= 0 && ctx->dmg[sl].mode != GG_DMG_MATRIX && ctx->dmg[sl].mode != GG_DMG_NONE) dmode = 0; }
+    // matrix-only plans keep their threshold tables in shared memory (L1 is only a few KB at this carve-out)
+    int thr_bytes = 0, thr_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
+    if (dmode == 1 && emit != GG_EMIT_FRAG) {
+        bool used[GG_MAX_DAMAGE_SLOTS] = {false, false, false, false};
+        for (size_t i = 0; i < ctx->plan.size(); i++) if (ctx->plan[i].damage_slot >= 0) used[ctx->plan[i].damage_slot] = true;
+        for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++)
+            if (used[sl] && ctx->dmg[sl].mode == GG_DMG_MATRIX) { thr_slot[sl] = thr_bytes / 16; thr_bytes += 64 * (ctx->dmg[sl].rows5 + ctx->dmg[sl].rows3 + 2); }
+        if (thr_bytes > 48 * 1024) { dmode = 0; thr_bytes = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) thr_slot[sl] = -1; }   // huge matrices: read them from global
     }
-    if (F < 1) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
-    while ((uint64_t)F * (uint64_t)max_chunks > 60000ull || (uint64_t)F * (uint64_t)max_groups > 60000ull) F--;
-    const SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words);
+    int regs = 96, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, 32, 4096, &bps0, &regs));
+    const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
+    int F = 32;
+    while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).total > sm_budget) F >>= 1;
+    if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
+    const int ctas = envC ? std::max(1, atoi(envC)) : 1;
+    const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).warp_bytes;
+    int warps = (int)((sm_budget / (size_t)ctas - 1024 - (size_t)thr_bytes) / per_warp);
+    warps = std::min(warps, 65536 / (regs * 32) / ctas);
+    warps = std::min(warps, 640 / 32);
+    if (envW) warps = std::min(warps, std::max(1, atoi(envW)));
+    warps = std::max(warps, 1);
+    SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes);
+    for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) sm.thr_slot[i] = thr_slot[i];
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
     const int n_tiles = (int)n_tiles64;
@@ -638,7 +654,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(ctx->d_ticket_stats.ensure(256));
 
     FusedParams P; memset(&P, 0, sizeof P);
-    P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary;
+    P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary; P.dmode = dmode;
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();
@@ -656,15 +672,16 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.sm = sm;
 
     int bps = 0;
-    CK(fused_occupancy(sm.total, &bps));
+    CK(fused_prepare(fast_boundary, dmode, warps * 32, sm.total, &bps, &regs));
     if (bps < 1) return ctx->fail(GG_ERR_CUDA, "gg_run_fused: kernel does not fit on an SM");
-    bps = std::min(bps, std::max(ctas, 1));
-    const int grid = (int)std::min<uint64_t>((uint64_t)n_tiles, (uint64_t)bps * (uint64_t)ctx->sm_count);
+    bps = std::min(bps, ctas);
+    const uint64_t want_ctas = (n_tiles64 + (uint64_t)warps - 1) / (uint64_t)warps;
+    const int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)bps * (uint64_t)ctx->sm_count);
 
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles * 8, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
-    CK(launch_fused(P, grid, ctx->st));
+    CK(launch_fused(P, grid, warps * 32, ctx->st));
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long stats[ST_N];
     CK(cudaMemcpyAsync(stats, P.stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));

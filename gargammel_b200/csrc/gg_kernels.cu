@@ -1,11 +1,11 @@
 // gg_kernels.cu -- hand-written sm_100a kernels of the gargammel hot path.
 //
 //   k_pack_genome   FASTA bytes -> 2-bit codes + non-ACGT mask (replaces mmap + per-char fetchSeq, fragSim.cpp:305-329)
-//   k_fused         fragSim -> deamSim -> adptSim for a tile of fragments per CTA iteration, ONE kernel:
-//                   thread-per-fragment rejection sampling (fragSim.cpp:1361-1507), thread-per-16-base-chunk damage
-//                   (deamSim.cpp:1477-1613,1794-2002), thread-per-16-byte-group adapter/emit (adptSim.cpp:281-411), records
-//                   staged in shared memory, global byte offsets from a decoupled look-back scan over tiles, and
-//                   16-byte vector stores of the final FASTA byte stream.
+//   k_fused         fragSim -> deamSim -> adptSim, ONE kernel of persistent, autonomous warps.  Each warp takes tiles of 32
+//                   fragments: lane-per-fragment rejection sampling (fragSim.cpp:1361-1507), lane-per-16-base-chunk damage
+//                   (deamSim.cpp:1477-1613,1794-2002), lane-per-fragment 2-bit line image + lane-per-16-byte-group ASCII
+//                   (adptSim.cpp:281-411), records staged in the warp's shared memory, global byte offsets from a decoupled
+//                   look-back over warp tiles, and 16-byte vector stores of the final FASTA byte stream.
 //   k_deam_records / k_adpt_records   the stand-alone stages over a 2-line FASTA record stream (for the drop-in CLIs)
 //
 // HBM-bound integer/byte work: no tensor cores.  Layout and byte accounting: DESIGN.md.
@@ -126,13 +126,16 @@ struct BitAppender {
     __device__ __forceinline__ void flush() { if (fill > 0) *out++ = (uint32_t)acc; }
 };
 __device__ __forceinline__ void put_run_smem(BitAppender& A, const uint32_t* src, int start, int len) {
+#pragma unroll 1
     for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(fetch_run_smem(src, start + o) & lowfields(n), n); }
 }
 __device__ __forceinline__ void put_run_glob(BitAppender& A, const uint32_t* __restrict__ src, int start, int len) {
+#pragma unroll 1
     for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(fetch_run_glob(src, start + o) & lowfields(n), n); }
 }
 // first `len` bases of revcomp(D[0:L])
 __device__ __forceinline__ void put_rc_run(BitAppender& A, const uint32_t* D, int L, int len) {
+#pragma unroll 1
     for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(revcomp16(fetch_run_smem(D, L - 16 - o)) & lowfields(n), n); }
 }
 __device__ __forceinline__ uint32_t pad_base(const FusedParams& P, uint64_t id, uint32_t stream, int q) {   // randomDNASeq base q
@@ -143,6 +146,7 @@ __device__ __forceinline__ void put_forward_read(BitAppender& A, const FusedPara
     const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenF);
     put_run_smem(A, D, 0, nD);
     put_run_glob(A, P.ad.adF2, 0, nA);
+#pragma unroll 1
     for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_F, q), 1);
 }
 // reverse read SR = (revcomp(frag) + adapterS)[0:RL] + random tail      adptSim.cpp:289,313-322
@@ -150,11 +154,13 @@ __device__ __forceinline__ void put_reverse_read(BitAppender& A, const FusedPara
     const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenS);
     put_rc_run(A, D, L, nD);
     put_run_glob(A, P.ad.adS2, 0, nA);
+#pragma unroll 1
     for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_R, q), 1);
 }
 // revcomp(SR): complemented random tail reversed, suffix of revcomp(adapterS), the last min(L,RL) fragment bases   adptSim.cpp:404
 __device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
     const int RL = P.ad.read_len, nD = min(L, RL), mAd = RL - nD, nS = min(mAd, P.ad.lenS), nP = mAd - nS;
+#pragma unroll 1
     for (int t = 0; t < nP; t++) A.put(3u - pad_base(P, id, ST_ADPT_R, nP - 1 - t), 1);
     put_run_glob(A, P.ad.rcS2, P.ad.lenS - nS, nS);
     put_run_smem(A, D, L - nD, nD);
@@ -162,8 +168,10 @@ __device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedP
 
 __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) {
     int k = nd - 1;
+#pragma unroll 1
     for (; v > 0xFFFFFFFFull; k--) { const uint64_t q = v / 10ull; p[k] = (uint8_t)('0' + (uint32_t)(v - q * 10ull)); v = q; }
     uint32_t w = (uint32_t)v;
+#pragma unroll 1
     for (; k >= 0; k--) { const uint32_t q = w / 10u; p[k] = (uint8_t)('0' + (w - q * 10u)); w = q; }
     return p + nd;
 }
@@ -171,60 +179,147 @@ __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) 
 #ifndef GG_FUSED_MINB
 #define GG_FUSED_MINB 3
 #endif
+// One packed sequence line: kind 0 = forward read, 1 = reverse read, 2 = forward read ++ revcomp(reverse read) (-artp).
+// Deliberately not inlined: it is called from two places and the kernel's code size matters (asynchronous warps).
+__device__ __noinline__ void build_line_image(const FusedParams& P, const uint32_t* D, int L, uint64_t id, int kind, uint32_t* out) {
+    BitAppender A; A.out = out; A.acc = 0; A.fill = 0;
+    if (kind == 1) put_reverse_read(A, P, D, L, id);
+    else {
+        put_forward_read(A, P, D, L, id);
+        if (kind == 2) put_reverse_read_rc(A, P, D, L, id);
+    }
+    A.flush();
+}
+
+// Damage of one 16-base chunk (fields 0..15 of W = fragment positions 16k..16k+15, n of them inside the fragment).
+// All fields of a 4-base group are processed without per-base branches; fields at or beyond the fragment end hold
+// neighbouring genome bases, index sentinel/clamped rows, and are masked off by the caller.  The group loop is NOT
+// unrolled: the kernel's warps run asynchronously, so code size (instruction cache) matters more than loop overhead.
+// DMODE: 1 = every damage slot of the plan is a -matfile matrix (only that code is compiled in), 0 = any mix.
+template <int DMODE>
+__device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const DamageDev& D, const uint4* thr_sm, uint64_t id, int k, int fl, int n, uint32_t W) {
+    const int mode = DMODE == 1 ? 1 : D.mode;
+    const int i0 = 16 * k;
+    const int nq = (n + 3) >> 2;
+    uint32_t Wn = 0;
+    if (mode == 1) {                                     // -matfile: one uniform per base (deamSim.cpp:1847,1911)
+        const int R5 = D.rows5;
+        const uint32_t R3 = (uint32_t)D.rows3, r3base = (uint32_t)R5 + 1u;
+        const uint4* thr = DMODE == 1 ? thr_sm : D.thr;   // rows5 + sentinel, rows3 + sentinel; shared-memory copy in the matrix-only kernel
+        const int half = fl >> 1;                         // positions i < half are on the 5' side (deamSim.cpp:1805)
+#pragma unroll 1
+        for (int q = 0; q < nq; q++) {
+            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
+            const uint32_t Wq = W >> (8 * q);
+            const int i4 = i0 + 4 * q;
+            uint32_t nb = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int i = i4 + jj;
+                const uint32_t b = (Wq >> (2 * jj)) & 3u;
+                const uint32_t r = (i < half) ? (uint32_t)min(i, R5) : r3base + min((uint32_t)(fl - 1 - i), R3);
+                const uint4 Tq = DMODE == 1 ? thr[r * 4u + b] : __ldg(thr + (r * 4u + b));
+                const uint32_t u = pick(x, jj) >> 1;
+                nb += ((uint32_t)(u >= Tq.x) + (uint32_t)(u >= Tq.y) + (uint32_t)(u >= Tq.z)) << (2 * jj);
+            }
+            Wn |= nb << (8 * q);
+        }
+    } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i
+        const BriggsHdr B = dmg_briggs_hdr(D, rng_block(P.key, id, 0u, ST_DEAM));
+#pragma unroll 1
+        for (int q = 0; q < nq; q++) {
+            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
+            const uint32_t Wq = W >> (8 * q);
+            uint32_t nb = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
+            Wn |= nb << (8 * q);
+        }
+    } else {                                             // single / double: two passes, two streams
+#pragma unroll 1
+        for (int q = 0; q < nq; q++) {
+            const uint4 x1 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
+            const uint4 x2 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM2);
+            const uint32_t Wq = W >> (8 * q);
+            uint32_t nb = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) nb |= dmg_sd_base(D, min(i0 + 4 * q + jj, fl - 1), fl, (Wq >> (2 * jj)) & 3u, pick(x1, jj), pick(x2, jj)) << (2 * jj);
+            Wn |= nb << (8 * q);
+        }
+    }
+    return Wn;
+}
+
+// One warp owns one tile of up to 32 fragments from sampling to the global store; warps never wait for each other
+// (no CTA barrier inside the loop).  Byte offsets come from a decoupled look-back over per-warp-tile states.
+//
 // FASTB: every header is >= 13 bytes, so a partial 16-byte group of one sequence line can never reach another line's
 // sequence bytes: groups are stored whole and the headers/newlines are written afterwards (no read-modify-write).
-template <bool FASTB>
-__global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __grid_constant__ FusedParams P) {
+#ifndef GG_FUSED_MAXT
+#define GG_FUSED_MAXT 640
+#endif
+template <bool FASTB, int DMODE>
+__global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t*  const s_stage  = smem + P.sm.stage;
-    uint64_t* const s_gpos   = (uint64_t*)(smem + P.sm.gpos);
-    uint32_t* const s_meta   = (uint32_t*)(smem + P.sm.meta);
-    uint32_t* const s_recoff = (uint32_t*)(smem + P.sm.recoff);
-    uint16_t* const s_hdr    = (uint16_t*)(smem + P.sm.hdr);
-    uint16_t* const s_cstart = (uint16_t*)(smem + P.sm.cstart);
-    uint16_t* const s_gstart = (uint16_t*)(smem + P.sm.gstart);
-    uint64_t* const s_idx    = (uint64_t*)(smem + P.sm.idx);
-    uint32_t* const s_ci     = (uint32_t*)(smem + P.sm.ci);
-    uint16_t* const s_rg     = (uint16_t*)(smem + P.sm.rg);
-    uint32_t* const s_dwords = (uint32_t*)(smem + P.sm.dwords);
-    uint8_t*  const s_cmap   = smem + P.sm.cmap;
-    uint8_t*  const s_gmap   = smem + P.sm.gmap;
-    uint32_t* const s_lwords = (uint32_t*)(smem + P.sm.lwords);   // line images (adptSim dialects only)
-    uint32_t* const s_lut    = (uint32_t*)(smem + P.sm.lut);     // 256 x 4 ASCII bytes
-    __shared__ unsigned long long s_warp_tot[FUSED_THREADS / 32];
-    __shared__ unsigned long long s_excl;
-    __shared__ int s_tile;
     __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
+    uint32_t* const s_lut = (uint32_t*)(smem + P.sm.lut);     // 256 x 4 ASCII bytes (CTA-shared)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int emit = P.emit, RL = P.ad.read_len;
     const int nlines = emit_lines(emit);
 
     // 4 bases (one byte of codes) -> 4 ASCII chars
-    for (int v = tid; v < 256; v += FUSED_THREADS) {
+    for (int v = tid; v < 256; v += blockDim.x) {
         uint32_t w = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) w |= (uint32_t)code2ascii((v >> (2 * k)) & 3) << (8 * k);
         s_lut[v] = w;
     }
+    const uint4* const s_thr = (const uint4*)(smem + P.sm.thr);
+    if (DMODE == 1)                                   // matrix thresholds of the used slots: global -> shared, once per CTA
+        for (int slot = 0; slot < 4; slot++)
+            if (P.dmg[slot].mode == 1 && P.sm.thr_slot[slot] >= 0)
+                for (int q = tid; q < 4 * (P.dmg[slot].rows5 + P.dmg[slot].rows3 + 2); q += blockDim.x)
+                    ((uint4*)(smem + P.sm.thr))[P.sm.thr_slot[slot] + q] = __ldg(P.dmg[slot].thr + q);
     if (P.size_mode == 2)
-        for (int q = tid; q < 1024; q += FUSED_THREADS) s_guide[q] = (uint16_t)first_below(P.size_thr, P.n_sizes, (uint32_t)q << 21);
+        for (int q = tid; q < 1024; q += blockDim.x) s_guide[q] = (uint16_t)first_below(P.size_thr, P.n_sizes, (uint32_t)q << 21);
+    __syncthreads();                                  // the only CTA barrier
+
+    // this warp's private shared memory
+    uint8_t*  const wb       = smem + P.sm.warp0 + (size_t)warp * P.sm.warp_bytes;
+    uint8_t*  const s_stage  = wb + P.sm.stage;
+    uint64_t* const s_gpos   = (uint64_t*)(wb + P.sm.gpos);
+    uint64_t* const s_idx    = (uint64_t*)(wb + P.sm.idx);
+    uint32_t* const s_meta   = (uint32_t*)(wb + P.sm.meta);
+    uint32_t* const s_recoff = (uint32_t*)(wb + P.sm.recoff);
+    uint32_t* const s_ci     = (uint32_t*)(wb + P.sm.ci);
+    uint16_t* const s_hdr    = (uint16_t*)(wb + P.sm.hdr);
+    uint16_t* const s_cstart = (uint16_t*)(wb + P.sm.cstart);
+    uint16_t* const s_gstart = (uint16_t*)(wb + P.sm.gstart);
+    uint16_t* const s_rg     = (uint16_t*)(wb + P.sm.rg);
+    uint32_t* const s_dwords = (uint32_t*)(wb + P.sm.dwords);
+    uint32_t* const s_lwords = (uint32_t*)(wb + P.sm.lwords);   // line images (adptSim dialects only)
+    uint8_t*  const s_cmap   = wb + P.sm.cmap;
+    uint8_t*  const s_gmap   = wb + P.sm.gmap;
+
     unsigned long long my_attempts = 0, my_gather = 0;
     uint32_t my_err = 0;
+    const int S_ad = emit == 4 ? 2 * RL : RL;                       // sequence-line length of the adptSim dialects
+    const int LWL = ((S_ad + 15) >> 4) + 2;                          // words per line image: guard + data + read slack
 
     while (true) {
-        if (tid == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
-        __syncthreads();
-        const int tile = s_tile;
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= P.n_tiles) break;
         const uint64_t tile_first = (uint64_t)tile * (uint64_t)P.F;
         const int nf = (int)min((uint64_t)P.F, P.count - tile_first);
 
-        // ------------------------------------------------------------ pass A: sample (thread per fragment)
+        // ------------------------------------------------------------ pass A: sample (lane per fragment)
         unsigned long long pk = 0;
-        if (tid < nf) {
+        if (lane < nf) {
             uint64_t idx = 0; int L = 0, ci = 0, hdr = 0, tag_len = 0; uint32_t plus = 1;
-            const uint64_t id = P.first + tile_first + (uint64_t)tid;
+            const uint64_t id = P.first + tile_first + (uint64_t)lane;
             int lo = 0, hi = P.n_ranges - 1;                    // last range with first_id <= id
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.ranges[mid].first_id <= id) lo = mid; else hi = mid - 1; }
             const RangeDev* rg = P.ranges + lo;
@@ -260,6 +355,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
                     const uint64_t e = gpos + (uint64_t)L - 1;
                     const uint64_t w0 = gpos >> 5, w1 = e >> 5;
                     uint32_t any = 0;
+#pragma unroll 1
                     for (uint64_t w = w0; w <= w1; w++) {
                         uint32_t m = __ldg(G.nmask + w);
                         if (w == w0) m &= 0xFFFFFFFFu << (gpos & 31);
@@ -282,64 +378,40 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
             const uint32_t chunks = (L + 15) >> 4;
             const uint32_t groups = nlines * (((S + 15) >> 4) + 1);
             pk = PK(bytes, chunks, groups);
-            s_gpos[tid] = gpos;
-            s_meta[tid] = META(L, plus, rg->slot, rg->genome);
-            s_hdr[tid] = (uint16_t)hdr;
-            s_idx[tid] = idx; s_ci[tid] = (uint32_t)ci; s_rg[tid] = (uint16_t)lo;   // parked for pass B2 (keeps registers free in passes C/D)
+            s_gpos[lane] = gpos;
+            s_meta[lane] = META(L, plus, rg->slot, rg->genome);
+            s_hdr[lane] = (uint16_t)hdr;
+            s_idx[lane] = idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
         }
-        // block exclusive scan of pk
-        unsigned long long incl = warp_scan_u64(pk, lane);
-        if (lane == 31) s_warp_tot[warp] = incl;
-        __syncthreads();
-        unsigned long long woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < FUSED_THREADS / 32; w++) { const unsigned long long t = s_warp_tot[w]; if (w < warp) woff += t; tot += t; }
-        const unsigned long long excl = woff + incl - pk;
+        // warp exclusive scan of pk
+        const unsigned long long incl = warp_scan_u64(pk, lane);
+        const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long excl = incl - pk;
         const uint32_t T = PK_BYTES(tot), n_chunks = PK_CHUNKS(tot), n_groups = PK_GROUPS(tot);
-        if (tid == 0) {   // publish this tile's byte count for the look-back
-            st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
-            if (T > (uint32_t)P.sm.stage_bytes) my_err |= ERRF_OVERFLOW;
-        }
         const bool overflow = T > (uint32_t)P.sm.stage_bytes;    // host sizing bug guard: never write past staging
+        if (lane == 0) {   // publish this tile's byte count for the look-back
+            st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
+            if (overflow) my_err |= ERRF_OVERFLOW;
+        }
 
-        // ------------------------------------------------------------ pass B1: work maps (owner thread)
-        if (tid < nf && !overflow) {
+        // ------------------------------------------------------------ pass B1: work maps (owner lane)
+        if (lane < nf && !overflow) {
             const uint32_t roff = PK_BYTES(excl), c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
-            s_recoff[tid] = roff; s_cstart[tid] = (uint16_t)c0; s_gstart[tid] = (uint16_t)g0;
+            s_recoff[lane] = roff; s_cstart[lane] = (uint16_t)c0; s_gstart[lane] = (uint16_t)g0;
             const uint32_t nch = PK_CHUNKS(pk), ngr = PK_GROUPS(pk);
-            for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)tid;
-            for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)tid;
+#pragma unroll 1
+            for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)lane;
+#pragma unroll 1
+            for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)lane;
         }
-        __syncthreads();
+        // first look-back probe, issued now and consumed after the damage pass (its latency overlaps pass C)
+        unsigned long long lb = 2ull << 62;
+        if (tile > 0 && tile - 1 - lane >= 0) lb = ld_volatile_u64(P.tile_state + (tile - 1 - lane));
+        __syncwarp();
 
-        // ------------------------------------------------------------ look-back (warp 0, overlapped with pass C of the other warps):
-        // global byte offset of this tile.  The inclusive prefix is published here, right after sampling, so successors
-        // rarely have to walk back further than a few tiles.
-        if (warp == 0) {
-            unsigned long long ex = 0;
-            if (tile > 0) {
-                int look = tile - 1;
-                while (true) {
-                    const int i = look - lane;
-                    unsigned long long v;
-                    do { v = i >= 0 ? ld_volatile_u64(P.tile_state + i) : (2ull << 62); } while (__any_sync(0xffffffffu, (v >> 62) == 0));
-                    const uint32_t inc = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-                    const int first_inc = inc ? (__ffs(inc) - 1) : 32;
-                    ex += warp_sum_u64(lane <= first_inc ? (v & 0x3FFFFFFFFFFFFFFFull) : 0ull);
-                    if (inc) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_volatile_u64(P.tile_state + tile, (2ull << 62) | (ex + (unsigned long long)T));
-            }
-            if (lane == 0) {
-                s_excl = ex;
-                if (tile == P.n_tiles - 1) P.stats[ST_TOTAL] = ex + (unsigned long long)T;
-            }
-        }
-
-        // ------------------------------------------------------------ pass C: gather + damage (thread per 16-base chunk)
+        // ------------------------------------------------------------ pass C: gather + damage (lane per 16-base chunk)
         if (!overflow)
-        for (uint32_t e = tid; e < n_chunks; e += FUSED_THREADS) {
+        for (uint32_t e = lane; e < n_chunks; e += 32) {
             const int f = s_cmap[e];
             const int k = (int)e - (int)s_cstart[f];
             const uint32_t meta = s_meta[f];
@@ -349,118 +421,65 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
             const int n = min(16, fl - 16 * k);
             uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
                                          : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
-            if (slot >= 0 && emit != 0) {
-                // All 16 fields are processed without per-base branches; fields at or beyond the fragment end hold
-                // neighbouring genome bases, index sentinel/clamped rows, and are masked off below.
-                const uint64_t id = P.first + tile_first + (uint64_t)f;
-                const int mode = P.dmg[slot].mode;
-                const int i0 = 16 * k;
-                if (mode == 1) {                                     // -matfile: one uniform per base (deamSim.cpp:1847,1911)
-                    const int R5 = P.dmg[slot].rows5, R3 = P.dmg[slot].rows3;
-                    const uint4* __restrict__ thr5 = P.dmg[slot].thr;
-                    const uint4* __restrict__ thr3 = thr5 + 4 * (R5 + 1);
-                    const int c5 = (fl >> 1) - i0;                    // fields j < c5 are on the 5' side (deamSim.cpp:1805)
-                    const uint32_t d3 = (uint32_t)(fl - 1 - i0);      // distance of field 0 from the 3' end
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                const uint32_t b = (W >> (2 * j)) & 3u;
-                                const uint4* row = (j < c5) ? thr5 + 4 * min(i0 + j, R5) : thr3 + 4 * (int)min(d3 - (uint32_t)j, (uint32_t)R3);
-                                const uint4 T = __ldg(row + b);
-                                const uint32_t u = pick(x, jj) >> 1;
-                                Wn += ((uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i
-                    const DamageDev& D = P.dmg[slot];
-                    const BriggsHdr B = dmg_briggs_hdr(D, rng_block(P.key, id, 0u, ST_DEAM));
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                Wn |= dmg_briggs_base(D, B, i0 + j, fl, (W >> (2 * j)) & 3u, pick(x, jj)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                } else if (mode == 3 || mode == 4) {                 // single / double: two passes, two streams
-                    const DamageDev& D = P.dmg[slot];
-                    uint32_t Wn = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * q < n) {
-                            const uint4 x1 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
-                            const uint4 x2 = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM2);
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * q + jj;
-                                Wn |= dmg_sd_base(D, min(i0 + j, fl - 1), fl, (W >> (2 * j)) & 3u, pick(x1, jj), pick(x2, jj)) << (2 * j);
-                            }
-                        }
-                    }
-                    W = Wn;
-                }
-            }
+            if (slot >= 0 && emit != 0)
+                W = damage_chunk<DMODE>(P, P.dmg[slot], s_thr + P.sm.thr_slot[slot], P.first + tile_first + (uint64_t)f, k, fl, n, W);
             s_dwords[e] = W & lowfields(n);
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ------------------------------------------------------------ pass C2: line images (owner thread; adptSim dialects only)
-        const int S_ad = emit == 4 ? 2 * RL : RL;                       // sequence-line length of the adptSim dialects
-        const int LWL = ((S_ad + 15) >> 4) + 2;                          // words per line image: guard + data + read slack
-        if (emit >= 2 && tid < nf && !overflow) {
-            const int L = META_L(s_meta[tid]);
-            const uint64_t id = P.first + tile_first + (uint64_t)tid;
-            const uint32_t* D = s_dwords + s_cstart[tid];
-            uint32_t* lw = s_lwords + tid * (nlines * LWL);
-            BitAppender A; A.out = lw + 1; A.acc = 0; A.fill = 0;
-            if (emit == 6) put_reverse_read(A, P, D, L, id);            // -rr
-            else {
-                put_forward_read(A, P, D, L, id);                       // -arts / -fr / first line / first half of -artp
-                if (emit == 4) put_reverse_read_rc(A, P, D, L, id);     // -artp: ++ revcomp(reverse read)
-            }
-            A.flush();
-            if (emit == 2) {                                            // default 4-line output: second line = reverse read
-                A.out = lw + LWL + 1; A.acc = 0; A.fill = 0;
-                put_reverse_read(A, P, D, L, id);
-                A.flush();
-            }
+        // ------------------------------------------------------------ pass C2: line images (owner lane; adptSim dialects only)
+        if (emit >= 2 && lane < nf && !overflow) {
+            const int L = META_L(s_meta[lane]);
+            const uint64_t id = P.first + tile_first + (uint64_t)lane;
+            const uint32_t* D = s_dwords + s_cstart[lane];
+            uint32_t* lw = s_lwords + lane * (nlines * LWL);
+            // -rr: reverse read; -artp: forward ++ revcomp(reverse); otherwise the forward read (first line)
+            build_line_image(P, D, L, id, emit == 6 ? 1 : emit == 4 ? 2 : 0, lw + 1);
+            if (emit == 2) build_line_image(P, D, L, id, 1, lw + LWL + 1);     // default 4-line output: second line = reverse read
         }
-        const unsigned long long gofs = s_excl;                         // (published by warp 0 before the barrier above)
-        const int pad = (int)((uintptr_t)(P.out + gofs) & 15);          // the tile is staged with its global misalignment
-        if (emit >= 2) __syncthreads();
 
-        // ------------------------------------------------------------ pass B2 (before D unless FASTB): headers + newlines (owner thread)
+        // ------------------------------------------------------------ look-back: global byte offset of this tile
+        unsigned long long gofs = 0;
+        if (tile > 0) {
+            int look = tile - 1;
+            while (true) {
+                const int i = look - lane;
+                while (__any_sync(0xffffffffu, (lb >> 62) == 0)) { if ((lb >> 62) == 0) lb = ld_volatile_u64(P.tile_state + i); }
+                const uint32_t inc = __ballot_sync(0xffffffffu, (lb >> 62) == 2ull);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+                gofs += warp_sum_u64(lane <= first_inc ? (lb & 0x3FFFFFFFFFFFFFFFull) : 0ull);
+                if (inc) break;
+                look -= 32;
+                lb = (look - lane >= 0) ? ld_volatile_u64(P.tile_state + (look - lane)) : (2ull << 62);
+            }
+            if (lane == 0) st_volatile_u64(P.tile_state + tile, (2ull << 62) | (gofs + (unsigned long long)T));
+        }
+        if (lane == 0 && tile == P.n_tiles - 1) P.stats[ST_TOTAL] = gofs + (unsigned long long)T;
+        const int pad = (int)((uintptr_t)(P.out + gofs) & 15);          // the tile is staged with its global misalignment
+        __syncwarp();
+
+        // ------------------------------------------------------------ pass B2 (before D unless FASTB): headers + newlines (owner lane)
         auto write_headers = [&]() {
-            if (tid < nf && !overflow) {
-                const uint32_t meta = s_meta[tid];
+            if (lane < nf && !overflow) {
+                const uint32_t meta = s_meta[lane];
                 const int L = META_L(meta); const uint32_t plus = META_PLUS(meta);
-                const uint64_t idx = s_idx[tid]; const int ci = (int)s_ci[tid];
-                const RangeDev* rg = P.ranges + s_rg[tid];
+                const uint64_t idx = s_idx[lane]; const int ci = (int)s_ci[lane];
+                const RangeDev* rg = P.ranges + s_rg[lane];
                 const char* tag = rg->tag; const int tag_len = rg->tag_len;
                 const int S = emit_seqlen(emit, L, RL);
                 const char* nm = P.ctab.names + __ldg(P.ctab.name_off + ci);
                 const int nlen = __ldg(P.ctab.name_len + ci);
-                uint8_t* p = s_stage + pad + s_recoff[tid];
+                uint8_t* p = s_stage + pad + s_recoff[lane];
                 for (int ln = 0; ln < nlines; ln++) {
                     // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
                     *p++ = '>';
+#pragma unroll 1
                     for (int k = 0; k < nlen; k++) *p++ = (uint8_t)__ldg(nm + k);
                     *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
                     p = put_decimal(p, idx, ndigits(idx)); *p++ = ':';
                     p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L)); *p++ = ':';
                     p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L));
+#pragma unroll 1
                     for (int k = 0; k < tag_len; k++) *p++ = (uint8_t)tag[k];
                     if (emit_suffix(emit, ln)) { *p++ = '_'; *p++ = 'r'; }
                     *p++ = '\n';
@@ -469,11 +488,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
                 }
             }
         };
-        if (!FASTB) { write_headers(); __syncthreads(); }
+        if (!FASTB) { write_headers(); __syncwarp(); }
 
-        // ------------------------------------------------------------ pass D: ASCII (thread per 16-byte staging group)
+        // ------------------------------------------------------------ pass D: ASCII (lane per 16-byte staging group)
         if (!overflow)
-        for (uint32_t e = tid; e < n_groups; e += FUSED_THREADS) {
+        for (uint32_t e = lane; e < n_groups; e += 32) {
             const int f = s_gmap[e];
             const int fl = META_L(s_meta[f]);
             const int S = emit_seqlen(emit, fl, RL);
@@ -497,8 +516,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
             if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
                 *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
             } else {
-                // boundary group: merge under a byte mask.  Headers were written before the barrier; two sequence lines are
-                // always >= 12 bytes apart (newline + a header), so no other thread touches these 4-byte words in this pass.
+                // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
+                // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
                 const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
                 const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
                 uint32_t* d4 = (uint32_t*)dst;
@@ -512,8 +531,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
                 }
             }
         }
-        __syncthreads();
-        if (FASTB) { write_headers(); __syncthreads(); }
+        __syncwarp();
+        if (FASTB) { write_headers(); __syncwarp(); }
 
         // ------------------------------------------------------------ copy-out: staging -> global, aligned 16-byte vector stores
         if (!overflow) {
@@ -522,17 +541,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
                 uint8_t* const gal = P.out + gofs - pad;                 // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+T)
                 const int end = pad + (int)T;
                 const int nchunks = (end + 15) >> 4;
-                for (int c = tid; c < nchunks; c += FUSED_THREADS) {
+                for (int c = lane; c < nchunks; c += 32) {
                     const int s0 = 16 * c;
                     if (s0 >= pad && s0 + 16 <= end) st_global_v4(gal + s0, *(const uint4*)(s_stage + s0));
-                    else for (int t = max(s0, pad); t < min(s0 + 16, end); t++) gal[t] = s_stage[t];
+                    else {
+#pragma unroll 1
+                        for (int t = max(s0, pad); t < min(s0 + 16, end); t++) gal[t] = s_stage[t];
+                    }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // per-CTA statistics
+    // per-warp statistics
     my_attempts = warp_sum_u64(my_attempts); my_gather = warp_sum_u64(my_gather);
     uint32_t e = my_err;
 #pragma unroll
@@ -544,15 +566,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, GG_FUSED_MINB) k_fused(const __
     }
 }
 
-cudaError_t fused_occupancy(int smem_bytes, int* blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_fused<false>, FUSED_THREADS, smem_bytes);
+typedef void (*fused_fn)(const FusedParams);
+static fused_fn fused_variant(int fast, int dmode) {
+    if (fast) return dmode == 1 ? k_fused<true, 1> : k_fused<true, 0>;
+    return dmode == 1 ? k_fused<false, 1> : k_fused<false, 0>;
 }
-cudaError_t launch_fused(const FusedParams& P, int grid, cudaStream_t st) {
-    if (P.fast_boundary) k_fused<true><<<grid, FUSED_THREADS, P.sm.total, st>>>(P);
-    else                 k_fused<false><<<grid, FUSED_THREADS, P.sm.total, st>>>(P);
+cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs) {
+    fused_fn f = fused_variant(fast, dmode);
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes a; e = cudaFuncGetAttributes(&a, f);
+    if (e != cudaSuccess) return e;
+    *regs = a.numRegs;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, threads, smem_bytes);
+}
+cudaError_t launch_fused(const FusedParams& P, int grid, int threads, cudaStream_t st) {
+    fused_variant(P.fast_boundary, P.dmode)<<<grid, threads, P.sm.total, st>>>(P);
     return cudaGetLastError();
 }
 

@@ -33,19 +33,24 @@ struct Adapters {
     int lenF, lenS, read_len, pad;
 };
 struct SmemLayout {          // byte offsets into dynamic shared memory, computed by the host
-    int stage, stage_bytes;  // output staging (16 B of readable slack before and after)
+    int lut;                 // CTA-shared: 4-bases -> 4-ASCII table
+    int thr, thr_bytes;      // CTA-shared copy of the matrix thresholds of the used damage slots (DMODE 1)
+    int thr_slot[4];         // uint4 index of each slot's table inside that copy
+    int warp0, warp_bytes;   // per-warp regions start at warp0 + warp * warp_bytes; the offsets below are relative to a region
+    int stage, stage_bytes;  // output staging (readable slack before and after)
     int gpos, meta, recoff, hdr, cstart, gstart;   // per-fragment descriptors
     int idx, ci, rg;                               // per-fragment header state parked between passes
-    int dwords, lwords, cmap, gmap, lut, total;
+    int dwords, lwords, cmap, gmap, total;
 };
 struct FusedParams {
     // work
     uint64_t first, count;   // fragment ids [first, first+count)
-    int F;                   // fragments per tile
+    int F;                   // fragments per warp tile (32 unless a record needs more shared memory)
     int n_tiles;
     int emit;                // gg_emit_mode
     int norev;
     int fast_boundary;       // every header >= 13 bytes: whole-group stores, headers written afterwards
+    int dmode;               // 1: every damage slot used by the plan is a matrix (specialised kernel), 0: any mix
     ggd::Key key;
     // plan + genomes
     const RangeDev* ranges; int n_ranges;
@@ -69,15 +74,14 @@ struct FusedParams {
 enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
 enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
 
-constexpr int FUSED_THREADS = 256;
 
 // ---- launchers (gg_kernels.cu) ----
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
                                const uint64_t* unit_start, int n_contigs, uint64_t n_units,
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
-cudaError_t launch_fused(const FusedParams& P, int grid, cudaStream_t st);
-cudaError_t fused_occupancy(int smem_bytes, int* blocks_per_sm);
+cudaError_t launch_fused(const FusedParams& P, int grid, int threads, cudaStream_t st);
+cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs);
 
 // stand-alone record-stream kernels
 struct RecStream {
