@@ -365,7 +365,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": count * world * e_steps / float(te.item()), "unit": "fragments/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(ei.bytes), "steps": e_steps,
-               "what": "per step: gg_genome_upload x3 from pinned host + gg_run_fused + gg_out_fetch to pinned host"}
+               "what": "per step: gg_genome_upload x3 from pinned host + gg_run_fused + gg_out_fetch to pinned host (PCIe-bound: the D2H of the FASTA stream)"}
         # cheap end-to-end sanity on what reached the host
         head = bytes(host_out[:64].numpy().tobytes())
         assert head.startswith(b">chr"), head

@@ -200,6 +200,13 @@ class Context:
         self._ck(self._f("out_fetch")(self._h, C.byref(o), C.c_void_p(host_ptr), C.c_size_t(cap), C.byref(n)))
         return _info(o)
 
+    def run_fused_to_host(self, first, count, emit, host_ptr, cap, chunk=0):
+        """chunked run with the D2H copies overlapped (gg_run_fused_to_host); host_ptr should be pinned memory."""
+        o = _Out()
+        self._ck(self._f("run_fused_to_host")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.c_void_p(host_ptr),
+                                              C.c_size_t(cap), C.c_uint64(chunk), C.byref(o)))
+        return _info(o)
+
     def _fetch(self, o):
         buf = C.create_string_buffer(max(int(o.bytes), 1))
         n = C.c_size_t(0)

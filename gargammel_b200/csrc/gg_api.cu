@@ -73,6 +73,8 @@ uint32_t thr_lt(double c) {
 
 struct gg_ctx {
     int device; cudaStream_t st; cudaEvent_t ev0, ev1;
+    cudaStream_t st_copy; cudaEvent_t ev_k[2], ev_c[2];     // egress pipeline of gg_run_fused_to_host
+    int out_slab;                                          // which of d_out/d_out2 the next fused run writes
     uint64_t seed; std::string err;
     int sm_count; size_t smem_optin;
     // genomes
@@ -252,7 +254,7 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
 }
 
 // shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared LUT
-SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes) {
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords) {
     SmemLayout s; int o = 0;
     o += 16;                                   // readable slack before staging
     s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
@@ -261,8 +263,12 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.meta = o; o += 4 * F;
     s.recoff = o; o += 4 * F;
     s.ci = o; o += 4 * F;
-    o += 4;                                    // guard word in front of the damaged-fragment words
-    s.dwords = o; o += 4 * (F * max_chunks + 4);
+    if (alias_dwords && s.stage_bytes >= 4 * (F * max_chunks + 4)) {
+        s.dwords = s.stage;                    // adptSim dialects: the damaged words are dead once the line images exist, before staging is written
+    } else {
+        o += 4;                                // guard word in front of the damaged-fragment words
+        s.dwords = o; o += 4 * (F * max_chunks + 4);
+    }
     s.lwords = o; o += 4 * (F * line_words + 4);
     s.hdr = o; o += 2 * F;
     s.cstart = o; o += 2 * F;
@@ -291,7 +297,8 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return GG_ERR_CUDA; }   // no GPU: fail loudly, never fall back
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GG_ERR_CUDA; }
     gg_ctx* ctx = new gg_ctx();
-    ctx->device = device; ctx->seed = seed; ctx->st = nullptr; ctx->ev0 = ctx->ev1 = nullptr;
+    ctx->device = device; ctx->seed = seed; ctx->st = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->st_copy = nullptr; ctx->out_slab = 0;
+    for (int i = 0; i < 2; i++) ctx->ev_k[i] = ctx->ev_c[i] = nullptr;
     ctx->ctab_dirty = true; ctx->n_contigs_total = 0;
     ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false;
     ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
@@ -300,7 +307,9 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { cudaGetLastError(); delete ctx; return GG_ERR_CUDA; }
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_k[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_k[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_c[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_c[1], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); delete ctx; return GG_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
     *out = ctx;
     return GG_OK;
@@ -320,7 +329,9 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     }
     for (size_t i = 0; i < ctx->pool.size(); i++) cudaFree(ctx->pool[i].first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->st);
+    cudaStreamSynchronize(ctx->st_copy);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_k[i]); cudaEventDestroy(ctx->ev_c[i]); }
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_copy);
     delete ctx;
     return GG_OK;
 }
@@ -633,23 +644,24 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int regs = 96, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
     int F = 32;
-    while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).total > sm_budget) F >>= 1;
-    if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
+    while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) F >>= 1;
+    if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
     const int ctas = envC ? std::max(1, atoi(envC)) : 1;
-    const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes).warp_bytes;
+    const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).warp_bytes;
     int warps = (int)((sm_budget / (size_t)ctas - 1024 - (size_t)thr_bytes) / per_warp);
     warps = std::min(warps, 65536 / (regs * 32) / ctas);
-    warps = std::min(warps, 640 / 32);
+    warps = std::min(warps, GG_FUSED_MAXT / 32);
     if (envW) warps = std::min(warps, std::max(1, atoi(envW)));
     warps = std::max(warps, 1);
-    SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes);
+    SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4);
     for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) sm.thr_slot[i] = thr_slot[i];
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
     const int n_tiles = (int)n_tiles64;
 
     const uint64_t out_cap = count * rec_max + 64;
-    CK(ctx->d_out.ensure(out_cap));
+    DBuf& oslab = ctx->out_slab ? ctx->d_out2 : ctx->d_out;
+    CK(oslab.ensure(out_cap));
     CK(ctx->d_tile_state.ensure((size_t)n_tiles * 8));
     CK(ctx->d_ticket_stats.ensure(256));
 
@@ -665,7 +677,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
     P.ad.adF2 = ctx->d_adF2.as<uint32_t>() + 1; P.ad.adS2 = ctx->d_adS2.as<uint32_t>() + 1; P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>() + 1;
     P.ad.lenF = (int)ctx->adF.size(); P.ad.lenS = (int)ctx->adS.size(); P.ad.read_len = ctx->read_len;
-    P.out = ctx->d_out.as<uint8_t>(); P.out_cap = out_cap;
+    P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;
     P.tile_state = ctx->d_tile_state.as<unsigned long long>();
     P.ticket = ctx->d_ticket_stats.as<unsigned int>();
     P.stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
@@ -688,7 +700,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(cudaStreamSynchronize(ctx->st));
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
-    out->dev_ptr = ctx->d_out.p; out->bytes = stats[ST_TOTAL]; out->records = count;
+    out->dev_ptr = oslab.p; out->bytes = stats[ST_TOTAL]; out->records = count;
     out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = 1;
     if (stats[ST_ERR] & ERRF_GIVEUP) return ctx->fail(GG_ERR_GIVEUP, "gg_run_fused: a fragment exhausted its sampling attempts (genome without an admissible window?)");
     if (stats[ST_ERR] & ERRF_OVERFLOW) return ctx->fail(GG_ERR_CAPACITY, "gg_run_fused: internal staging/output overflow");
@@ -817,6 +829,34 @@ int gg_run_adpt(gg_ctx* ctx, const uint8_t* recs, size_t n, int emit, uint64_t f
     if (!ctx || (n && !recs)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_adpt: bad arguments") : GG_ERR_ARG;
     int rc = upload_input(ctx, recs, n); if (rc) return rc;
     return gg_run_adpt_dev(ctx, ctx->d_in.p, n, emit, first_id, out);
+}
+
+int gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* host_dst, size_t cap, uint64_t chunk, gg_out* out) {
+    if (!ctx || !out || (!host_dst && count)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_fused_to_host: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (chunk == 0) chunk = 1u << 20;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* dst = (uint8_t*)host_dst; size_t used = 0; int rc = GG_OK;
+    for (uint64_t a = 0, i = 0; a < count; a += chunk, i++) {
+        const int slab = (int)(i & 1);
+        if (i >= 2) CK(cudaEventSynchronize(ctx->ev_c[slab]));          // the copy that last read this slab has finished
+        ctx->out_slab = slab;
+        gg_out o;
+        rc = gg_run_fused(ctx, first + a, std::min<uint64_t>(chunk, count - a), emit, &o);   // syncs the compute stream, returns the byte count
+        if (rc != GG_OK) break;
+        if (used + o.bytes > cap) { rc = ctx->fail(GG_ERR_CAPACITY, "gg_run_fused_to_host: destination too small"); break; }
+        CK(cudaMemcpyAsync(dst + used, o.dev_ptr, o.bytes, cudaMemcpyDeviceToHost, ctx->st_copy));   // overlaps the next chunk's kernel
+        CK(cudaEventRecord(ctx->ev_c[slab], ctx->st_copy));
+        used += o.bytes; out->bytes += o.bytes; out->records += o.records; out->attempts += o.attempts; out->gather_bytes += o.gather_bytes;
+        out->device_ms += o.device_ms; out->launches += o.launches;
+    }
+    ctx->out_slab = 0;
+    cudaError_t e = cudaStreamSynchronize(ctx->st_copy);
+    if (rc != GG_OK) return rc;
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "gg_run_fused_to_host: copy");
+    out->dev_ptr = nullptr;
+    ctx->last_ms = out->device_ms;
+    return GG_OK;
 }
 
 int gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n) {

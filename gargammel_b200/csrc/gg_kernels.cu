@@ -255,9 +255,6 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
 //
 // FASTB: every header is >= 13 bytes, so a partial 16-byte group of one sequence line can never reach another line's
 // sequence bytes: groups are stored whole and the headers/newlines are written afterwards (no read-modify-write).
-#ifndef GG_FUSED_MAXT
-#define GG_FUSED_MAXT 640
-#endif
 template <bool FASTB, int DMODE>
 __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];

@@ -71,6 +71,9 @@ struct FusedParams {
     SmemLayout sm;
 };
 
+#ifndef GG_FUSED_MAXT
+#define GG_FUSED_MAXT 640      // launch bound of k_fused: 20 warps, 96 registers (measured best of 640/672/704)
+#endif
 enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
 enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
 

@@ -161,6 +161,11 @@ int  gg_run_adpt(gg_ctx* ctx, const uint8_t* recs, size_t n, int emit, uint64_t 
 int  gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, gg_out* out);
 int  gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, gg_out* out);
 
+/* gg_run_fused + egress in one call: the id range is processed in chunks of `chunk` fragments (0 = default) through two
+ * device slabs, and each chunk's bytes are copied to host_dst while the next chunk is being generated (second stream).
+ * host_dst should be pinned memory for the copies to overlap.  out->device_ms = sum of the kernels' event times. */
+int  gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* host_dst, size_t cap,
+                          uint64_t chunk, gg_out* out);
 /* copy a run's bytes to the host (pinned staging inside; blocking) */
 int  gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n);
 /* CUDA-event time (ms) of the kernels of the last gg_run_* on this context */

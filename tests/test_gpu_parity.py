@@ -219,3 +219,23 @@ def test_fused_short_headers(oracle_mod):
             c.set_plan([api.Range(0, 2000, gid, 0, "")])
         for emit in ALL_EMITS:
             util.assert_same(g.run_fused(0, 2000, emit)[0], o.run_fused(0, 2000, emit)[0], "short headers %s %r emit=%d" % (sizes, kw, emit))
+
+
+def test_run_fused_to_host_chunked(oracle_mod, genomes):
+    """gg_run_fused_to_host (chunks through two device slabs, D2H overlapped) == one gg_run_fused call."""
+    import ctypes as C
+    g, o, ids = _pair(oracle_mod, genomes, damage="matrix")
+    plan = util.plan3(ids, counts=(3000, 2500, 2000))
+    g.set_plan(plan)
+    full, info = g.run_fused(0, 7500, api.EMIT_ARTP)
+    cap = len(full) + 100
+    buf = C.create_string_buffer(cap)
+    for chunk in (0, 7500, 1000, 777, 1):
+        if chunk == 1:
+            i2 = g.run_fused_to_host(100, 50, api.EMIT_ARTP, C.addressof(buf), cap, 1)
+            assert buf.raw[:i2.bytes] == g.run_fused(100, 50, api.EMIT_ARTP)[0]
+            continue
+        i2 = g.run_fused_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), cap, chunk)
+        assert i2.bytes == len(full) and buf.raw[:i2.bytes] == full and i2.records == 7500 and i2.attempts == info.attempts
+    with pytest.raises(api.GGError):
+        g.run_fused_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), 1000, 1000)
