@@ -5,7 +5,8 @@ using namespace cli;
 
 int main(int argc, char** argv) {
     int sizeFragments = 20; uint64_t nFragments = 10; int minLen = 0, maxLen = 1000;
-    bool noRev = false, seedSpecified = false, specifiedLength = false; uint64_t seed = 0;
+    bool noRev = false, seedSpecified = false, specifiedLength = false, specifiedLoc = false, specifiedScale = false; uint64_t seed = 0;
+    double location = -1, scale = -1;
     std::string sizeList, sizeFreq, outGz, tag;
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
         " aDNA fragments according to a certain distribution (B200 build)\n\n " + argv[0] + " [options]  [chromosome fasta] \n\n" +
@@ -15,7 +16,8 @@ int main(int argc, char** argv) {
         "\t\t-m\t[length]\t\t\tMinimum fragments length (default: 0)\n\t\t-M\t[length]\t\t\tMaximum fragments length (default: 1000)\n" +
         "\t\t-l\t[length]\t\t\tGenerate fragments of fixed length  (default: 20)\n\t\t-s\t[file]\t\t\t\tOpen file with size distribution (one fragment length per line)\n" +
         "\t\t-f\t[file]\t\t\t\tOpen file with size frequency: length[TAB]freq\n" +
-        "\tNot in this build: --comp --dist -gc --circ --case --fq --trim5p --loc --scale -uniq -b -u\n";
+        "\t\t--loc\t[float] --scale\t[float]\tlog-normal fragment lengths\n" +
+        "\tNot in this build: --comp --dist -gc --circ --case --fq --trim5p -uniq -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -30,13 +32,23 @@ int main(int argc, char** argv) {
         if (a == "-o") { outGz = argv[++i]; continue; }
         if (a == "-tag") { tag = argv[++i]; continue; }
         if (a == "-tmp") { ++i; continue; }                                         // gz inputs are inflated in memory
-        if (a == "--comp" || a == "--dist" || a == "-gc" || a == "--circ" || a == "--trim5p" || a == "--loc" || a == "--scale" || a == "-b")
+        if (a == "--loc") { location = to_d(argv[++i], "--loc"); specifiedLoc = true; continue; }
+        if (a == "--scale") { scale = to_d(argv[++i], "--scale"); specifiedScale = true; continue; }
+        if (a == "--comp" || a == "--dist" || a == "-gc" || a == "--circ" || a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
         if (a == "--case" || a == "--fq" || a == "-uniq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
     }
     if (specifiedLength && sizeFragments > maxLen)                                   // fragSim.cpp:638-643
         return die("Error: specified size " + std::to_string(sizeFragments) + " is longer than the maximum allowed fragment size " + std::to_string(maxLen) + ", use option -M to change this.");
+    if (specifiedLoc && !specifiedScale) return die("Error: cannot specify --loc without --scale");      // fragSim.cpp:645-653
+    if (specifiedScale && !specifiedLoc) return die("Error: cannot specify --scale without --loc");
+    if (specifiedScale && specifiedLoc) {                                                                // :655-669
+        if (specifiedLength) return die("Error: cannot specify --scale and --loc with -l");
+        if (!sizeList.empty()) return die("Error: cannot specify --scale and --loc with -s");
+        if (!sizeFreq.empty()) return die("Error: cannot specify --scale and --loc with -f");
+        if (!(scale > 0)) return die("Error: --scale must be positive");
+    }
     if (!sizeList.empty() && !sizeFreq.empty()) return die("Error: cannot specify -s with -f");          // :682-685
     if (specifiedLength && !sizeList.empty()) return die("Error: cannot specify -l and -s");             // :688-691
     if (specifiedLength && !sizeFreq.empty()) return die("Error: cannot specify -l and -f");             // :693-696
@@ -48,6 +60,7 @@ int main(int argc, char** argv) {
     std::vector<int32_t> lens; std::vector<double> cum;
     if (!sizeList.empty() && !ggh::load_size_list(sizeList, lens, err)) return die(err);
     if (!sizeFreq.empty() && !ggh::load_size_freq(sizeFreq, lens, cum, err)) return die(err);
+    if (specifiedLoc) { if (maxLen > 4095) maxLen = 4095; ggh::lognormal_table(location, scale, 4095, lens, cum); }   // int(lognormal(loc,scale)), fragSim.cpp:184
     ggh::GenomeFile G;
     if (!ggh::load_genome(inFile, G, err)) return die(err);
     std::cerr << "Mapped " << inFile << " into memory" << std::endl;                // fragSim.cpp:1149
@@ -57,7 +70,7 @@ int main(int argc, char** argv) {
     int gid = -1;
     if (ggh::upload_genome(ctx, G, &gid) != GG_OK) return gg_fail(ctx, "genome upload");
     std::vector<uint8_t>().swap(G.bytes);
-    const int mode = !sizeList.empty() ? GG_SIZE_LIST : !sizeFreq.empty() ? GG_SIZE_FREQ : GG_SIZE_FIXED;
+    const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || specifiedLoc) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
     if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), sizeFragments, minLen, maxLen) != GG_OK) return gg_fail(ctx, "size tables");
     gg_tables_set_norev(ctx, noRev ? 1 : 0);
     if (nFragments) {

@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
     double compB = 0, compC = 0, compE = 1; std::string comp = "0,0,1";
     uint64_t n = 1000; double coverage = -1; int fraglength = 35, minsize = 0, maxsize = 1000, rl = 75, gpus = 1;
     std::string sizeList, sizeFreq, prefix, adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";   // gargammel.pl:255-257
-    bool se = false, keep = false, n_given = false, seedSpecified = false; uint64_t seed = 0;
+    bool se = false, keep = false, n_given = false, seedSpecified = false, lognorm = false; uint64_t seed = 0; double loc = 0, scale = 0;
     DamageSpec dAll, dE, dB, dC;
     const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
         "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
@@ -64,6 +64,8 @@ int main(int argc, char** argv) {
         if (a == "-l") { fraglength = (int)to_ll(next(), "-l"); continue; }
         if (a == "-s") { sizeList = next(); continue; }
         if (a == "-f") { sizeFreq = next(); continue; }
+        if (a == "-loc") { loc = to_d(next(), "-loc"); lognorm = true; continue; }
+        if (a == "-scale") { scale = to_d(next(), "-scale"); lognorm = true; continue; }
         if (a == "-minsize") { minsize = (int)to_ll(next(), "-minsize"); continue; }
         if (a == "-maxsize") { maxsize = (int)to_ll(next(), "-maxsize"); continue; }
         if (a == "-matfile") { dAll.matfile = next(); continue; }
@@ -82,7 +84,7 @@ int main(int argc, char** argv) {
         if (a == "-gpus") { gpus = (int)to_ll(next(), "--gpus"); continue; }
         if (a == "-keep") { keep = true; continue; }
         if (a == "-mock" || a == "-methyl" || a == "-uniq" || a == "-ss" || a == "-distmis" || a == "-misince" || a == "-misincb" || a == "-misincc" ||
-            a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-loc" || a == "-scale" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
+            a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
         return die("Unknown option: " + a);
     }
     if (coverage >= 0 && n_given) return die("Must use the -c or -n but not both");                    // gargammel.pl:753-756
@@ -138,6 +140,7 @@ int main(int argc, char** argv) {
     std::vector<int32_t> lens; std::vector<double> cum; double avg = fraglength;
     if (!sizeList.empty()) { if (!ggh::load_size_list(sizeList, lens, err)) return die(err); double t = 0; for (size_t i = 0; i < lens.size(); i++) t += lens[i]; avg = t / lens.size(); }
     else if (!sizeFreq.empty()) { if (!ggh::load_size_freq(sizeFreq, lens, cum, err)) return die(err); double t = 0, prev = 0; for (size_t i = 0; i < lens.size(); i++) { t += lens[i] * (cum[i] - prev); prev = cum[i]; } avg = t / cum.back(); }
+    else if (lognorm) { if (!(scale > 0)) return die("-scale must be positive"); if (maxsize > 4095) maxsize = 4095; ggh::lognormal_table(loc, scale, 4095, lens, cum); avg = exp(loc + scale * scale / 2); }   // gargammel.pl:1221-1222
     // ---- number of fragments (gargammel.pl:1236-1266)
     ggh::ApportionIn in; in.compB = compB; in.compC = compC; in.compE = compE; in.n_endo = (int)std::max<size_t>(fE.size(), 1); in.cont_len = contLen; in.bact_w = bw; in.seed = seed;
     if (coverage >= 0) {
@@ -178,7 +181,7 @@ int main(int argc, char** argv) {
             gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot;
             snprintf(rg.tag, sizeof rg.tag, "%s", items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;
         }
-        const int mode = !sizeList.empty() ? GG_SIZE_LIST : !sizeFreq.empty() ? GG_SIZE_FREQ : GG_SIZE_FIXED;
+        const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
         if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
         if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) { rcs[r] = 1; gg_ctx_destroy(ctx); return; }
         if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), rl) != GG_OK) return fail("adapters");

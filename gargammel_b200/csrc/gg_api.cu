@@ -208,10 +208,10 @@ int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n
 
 // largest fragment length the size model can emit
 int max_frag_len(const gg_ctx* ctx) {
-    if (ctx->size_mode == GG_SIZE_FIXED) return ctx->fixed_len;
-    int m = 0;
+    if (ctx->size_mode == GG_SIZE_FIXED) return (ctx->fixed_len >= ctx->minlen && ctx->fixed_len <= ctx->maxlen) ? ctx->fixed_len : -1;
+    int m = -1;                                  // -1: no admissible length at all
     for (size_t i = 0; i < ctx->size_len.size(); i++)
-        if (ctx->size_len[i] >= ctx->minlen && ctx->size_len[i] <= ctx->maxlen) m = std::max(m, ctx->size_len[i]);
+        if (ctx->size_len[i] >= 0 && ctx->size_len[i] >= ctx->minlen && ctx->size_len[i] <= ctx->maxlen) m = std::max(m, ctx->size_len[i]);
     return m;
 }
 int emit_lines(int emit) { return emit == GG_EMIT_STDOUT4 ? 2 : 1; }
@@ -612,7 +612,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (count == 0) { out->dev_ptr = ctx->d_out.p; ctx->last_ms = 0; return GG_OK; }
 
     const int Lmax = max_frag_len(ctx);
-    if (Lmax <= 0 || Lmax > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_run_fused: no admissible fragment length (check -l/-s/-f against -m/-M)");
+    if (Lmax < 0 || Lmax > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_run_fused: no admissible fragment length (check -l/-s/-f against -m/-M)");
     int hdr_max; uint64_t rec_max; plan_bounds(ctx, emit, Lmax, &hdr_max, &rec_max);
     const int Smax = emit_seqlen(emit, Lmax, ctx->read_len);
     const int max_chunks = (Lmax + 15) / 16, max_groups = emit_lines(emit) * ((Smax + 15) / 16 + 1);

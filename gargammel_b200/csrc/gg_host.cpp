@@ -133,6 +133,15 @@ bool load_size_freq(const std::string& path, std::vector<int32_t>& len, std::vec
     return true;
 }
 
+void lognormal_table(double loc, double scale, int cap, std::vector<int32_t>& len, std::vector<double>& cum) {
+    len.clear(); cum.clear();
+    for (int l = 0; l <= cap; l++) {
+        const double z = (log((double)l + 1.0) - loc) / scale;
+        len.push_back(l); cum.push_back(0.5 * erfc(-z * 0.70710678118654752440));
+    }
+    len.push_back(cap + 1); cum.push_back(1.0);
+}
+
 // one .dat/.prof file: header line skipped; per line: tab fields (dropping the first `skip` columns), token before ' ' -> double
 static bool load_rate_file(const std::string& path, int skip, Rates& sub, std::string& err, const char* which) {
     std::vector<uint8_t> b;
@@ -408,4 +417,8 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
     return 0;
 }
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream) { return ggh::binomial_draw(n, p, seed, stream); }
+int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum) {
+    std::vector<int32_t> l; std::vector<double> c; ggh::lognormal_table(loc, scale, cap, l, c);
+    memcpy(len, l.data(), l.size() * 4); memcpy(cum, c.data(), c.size() * 8); return (int)l.size();
+}
 }

@@ -25,6 +25,10 @@ bool load_size_list(const std::string& path, std::vector<int32_t>& len, std::str
 // -f file: "length<TAB>freq", running cumulative sum, require 0.99 <= sum <= 1.01 (fragSim.cpp:751-784)
 bool load_size_freq(const std::string& path, std::vector<int32_t>& len, std::vector<double>& cum, std::string& err);
 
+// --loc/--scale: length = int(lognormal(loc, scale)) (fragSim.cpp:184,671) as an inverse-CDF table over lengths 0..cap:
+// cum[l] = P(length <= l) = Phi((ln(l+1) - loc) / scale); a last row `cap+1` with cum 1 holds the tail (rejected by -M).
+void lognormal_table(double loc, double scale, int cap, std::vector<int32_t>& len, std::vector<double>& cum);
+
 typedef std::vector<double> Rates;   // rows x 12, idx = from*3 + (to<from ? to : to-1), bases A,C,G,T
 // -matfile prefix: <prefix>5.dat / <prefix>3.dat; first column dropped, "value [lo..hi]" -> value; per-base sums <= 1;
 // the 3' file is reversed so that row 0 is the terminal base (deamSim.cpp:1098-1241)
@@ -74,4 +78,5 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
                   const double* bact_w, int n_bact, uint64_t seed, uint64_t* totals3, uint64_t* endo, uint64_t* cont, uint64_t* bact,
                   char* err, int errcap);
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
+int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum);   /* cap+2 rows */
 }

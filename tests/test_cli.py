@@ -197,6 +197,12 @@ def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
     po = np.mean([h.split(b":")[1] == b"+" for h, _ in util.records(ours.stdout)])
     pr = np.mean([h.split(b":")[1] == b"+" for h, _ in util.records(ref.stdout)])
     assert abs(po - 0.5) < 0.01 and abs(pr - 0.5) < 0.02
+    # --loc/--scale: ours (inverse-CDF table) vs the reference's std::lognormal_distribution
+    ours_ln = run([os.path.join(BIN, "fragSim"), "--seed", "6", "-n", "100000", "--loc", "4.1", "--scale", "0.35", str(d / "g.fa")])
+    ref_ln = run([_ref("fragSim"), "--seed", "6", "-n", "50000", "--loc", "4.1", "--scale", "0.35", str(d / "g.fa")])
+    assert ours_ln.returncode == 0 and ref_ln.returncode == 0, ours_ln.stderr
+    a = np.array([len(s) for _, s in util.records(ours_ln.stdout)]); b = np.array([len(s) for _, s in util.records(ref_ln.stdout)])
+    assert stats.ks_2samp(a, b).pvalue > 0.01 and abs(a.mean() - np.exp(4.1 + 0.35 ** 2 / 2) + 0.5) < 1.0
     # start positions are uniform over the accepted windows in both: compare coarse histograms of chr1 starts
     def starts(out):
         return np.array([int(h.split(b":")[2]) for h, _ in util.records(out) if h.startswith(b">chr1:")])

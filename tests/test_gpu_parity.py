@@ -37,7 +37,7 @@ def test_pack_genome_matches_fasta(genomes):
 
 
 @pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double"])
-@pytest.mark.parametrize("sizes", ["freq", "list", "fixed"])
+@pytest.mark.parametrize("sizes", ["freq", "list", "fixed", "lognormal"])
 def test_fused_bit_exact(oracle_mod, genomes, damage, sizes):
     g, o, ids = _pair(oracle_mod, genomes, sizes=sizes, damage=damage)
     plan = util.plan3(ids)
@@ -79,7 +79,7 @@ def test_fused_adapters_trim_and_pad(oracle_mod, genomes, read_len, adF, adS):
         util.assert_same(g.run_fused(0, 1200, emit)[0], o.run_fused(0, 1200, emit)[0], "RL=%d emit=%d" % (read_len, emit))
 
 
-@pytest.mark.parametrize("kw", [dict(sizes="fixed", fixed_len=1), dict(sizes="fixed", fixed_len=16), dict(sizes="fixed", fixed_len=17),
+@pytest.mark.parametrize("kw", [dict(sizes="fixed", fixed_len=0), dict(sizes="fixed", fixed_len=1), dict(sizes="fixed", fixed_len=16), dict(sizes="fixed", fixed_len=17),
                                 dict(sizes="fixed", fixed_len=191), dict(sizes="fixed", fixed_len=700, maxlen=1000), dict(minlen=60, maxlen=90),
                                 dict(norev=True), dict(clamp_last=False, sizes="fixed", fixed_len=191), dict(matrix="double-")])
 def test_fused_edge_configs(oracle_mod, genomes, kw):

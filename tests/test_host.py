@@ -187,3 +187,15 @@ def test_binomial_sampler_moments():
         if s > 0.5:
             assert abs(x.std() / s - 1) < 0.08
         assert x.min() >= 0 and x.max() <= n
+
+
+def test_lognormal_table_matches_scipy():
+    """fragSim --loc/--scale: length = int(lognormal(loc, scale)) (fragSim.cpp:184) as an inverse-CDF table."""
+    from scipy import stats
+    from tests import util
+    for loc, scale in ((4.1, 0.35), (3.7, 0.6), (5.0, 0.2)):
+        lens, cum = util.lognormal_table(loc, scale)
+        assert lens[:3] == [0, 1, 2] and lens[-1] == 4096 and cum[-1] == 1.0
+        want = stats.lognorm.cdf(np.arange(1, 4097), s=scale, scale=np.exp(loc))       # P(int(X) <= l) = F(l+1)
+        assert np.abs(np.array(cum[:-1]) - want).max() < 1e-12
+        assert all(b >= a for a, b in zip(cum[:-1], cum[1:]))

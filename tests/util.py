@@ -20,6 +20,9 @@ def configure(ctx, genomes, sizes="freq", damage="matrix", read_len=75, minlen=0
     if sizes == "freq":
         lens, cum = synth.golden_sizefreq()
         ctx.set_sizes(api.SIZE_FREQ, lens, cum, minlen=minlen, maxlen=maxlen)
+    elif sizes == "lognormal":
+        lens, cum = lognormal_table(4.1, 0.35)
+        ctx.set_sizes(api.SIZE_FREQ, lens, cum, minlen=minlen, maxlen=min(maxlen, 4095))
     elif sizes == "list":
         ctx.set_sizes(api.SIZE_LIST, synth.golden_sizelist(), minlen=minlen, maxlen=maxlen)
     else:
@@ -28,6 +31,16 @@ def configure(ctx, genomes, sizes="freq", damage="matrix", read_len=75, minlen=0
     set_damage(ctx, 0, damage, clamp_last=clamp_last, matrix=matrix)
     ctx.set_adapters(adapters[0], adapters[1], read_len)
     return ids
+
+
+def lognormal_table(loc, scale, cap=4095):
+    """--loc/--scale lengths through the host library's inverse-CDF table (ggh::lognormal_table)."""
+    import ctypes as C
+    lib = api.load_library()
+    ln = np.zeros(cap + 2, dtype=np.int32); cm = np.zeros(cap + 2)
+    n = lib.ggh_lognormal_table(C.c_double(loc), C.c_double(scale), C.c_int(cap), ln.ctypes.data_as(C.POINTER(C.c_int32)), cm.ctypes.data_as(C.POINTER(C.c_double)))
+    assert n == cap + 2
+    return ln.tolist(), cm.tolist()
 
 
 def set_damage(ctx, slot, damage, clamp_last=True, matrix="single-"):
