@@ -366,6 +366,26 @@ def main():
         e2e = {"value": count * world * e_steps / float(te.item()), "unit": "fragments/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(ei.bytes), "steps": e_steps,
                "what": "per step: gg_genome_upload x3 from pinned host + gg_run_fused + gg_out_fetch to pinned host (PCIe-bound: the D2H of the FASTA stream)"}
+        # the same with host BGZF of the byte stream on all host threads (north_star: with and without gzip/BGZF output)
+        try:
+            import ctypes as C
+            lib = api.load_library()
+            zcap = int(ei.bytes) + int(ei.bytes) // 200 + (1 << 20)
+            zbuf = torch.empty(zcap, dtype=torch.uint8)
+            zn = C.c_size_t(0)
+            barrier()
+            tz0 = time.perf_counter()
+            ei = e2e_step()
+            rcz = lib.ggh_bgzf_compress(C.c_void_p(host_out.data_ptr()), C.c_size_t(int(ei.bytes)), 0, 1, 1, C.c_void_p(zbuf.data_ptr()), C.c_size_t(zcap), C.byref(zn))
+            barrier()
+            tz = torch.tensor([time.perf_counter() - tz0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tz, op=dist.ReduceOp.MAX)
+            if rcz == 0:
+                e2e["with_bgzf"] = {"value": count * world / float(tz.item()), "unit": "fragments/s", "host_threads": host_cores(), "level": 1,
+                                    "compressed_bytes_per_step": int(zn.value), "steps": 1}
+        except Exception as ex:
+            e2e["with_bgzf"] = {"value": None, "error": repr(ex)}
         # cheap end-to-end sanity on what reached the host
         head = bytes(host_out[:64].numpy().tobytes())
         assert head.startswith(b">chr"), head

@@ -48,18 +48,39 @@ inline std::string exe_dir(const char* argv0) {     // getCWD(argv[0]) of libgab
     return k == std::string::npos ? std::string("./") : p.substr(0, k + 1);
 }
 
-// output sink: stdout, a plain file, or a gzip file (ogzstream of the reference)
+// output sink: stdout, a plain file, or a gzip file (ogzstream of the reference).  gz output is written as BGZF
+// (blocked gzip: any gzip reader inflates it, htslib can index it), deflated on all host threads.
 struct Sink {
-    FILE* f; gzFile gz; bool own;
-    Sink() : f(NULL), gz(NULL), own(false) {}
+    FILE* f; bool own, bgzf; std::vector<uint8_t> pend;
+    Sink() : f(NULL), own(false), bgzf(false) {}
     bool open_stdout() { f = stdout; own = false; setvbuf(stdout, NULL, _IOFBF, 1 << 22); return true; }
     bool open_plain(const std::string& p) { f = fopen(p.c_str(), "wb"); own = true; if (f) setvbuf(f, NULL, _IOFBF, 1 << 22); return f != NULL; }
-    bool open_gz(const std::string& p, bool append = false) { gz = gzopen(p.c_str(), append ? "ab1" : "wb1"); if (gz) gzbuffer(gz, 1 << 20); return gz != NULL; }
-    bool write(const void* d, size_t n) {
-        if (gz) { const char* p = (const char*)d; while (n) { unsigned c = n > (1u << 30) ? (1u << 30) : (unsigned)n; if (gzwrite(gz, p, c) != (int)c) return false; p += c; n -= c; } return true; }
-        return fwrite(d, 1, n, f) == n;
+    bool open_gz(const std::string& p, bool append = false) { f = fopen(p.c_str(), append ? "ab" : "wb"); own = true; bgzf = true; return f != NULL; }
+    bool flush_blocks(bool final) {
+        const size_t B = 0xff00, whole = final ? pend.size() : pend.size() / B * B;
+        if (whole) {
+            std::vector<uint8_t> z; std::string e;
+            if (!ggh::bgzf_compress(pend.data(), whole, 0, 1, z, false, e)) return false;
+            if (fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
+            pend.erase(pend.begin(), pend.begin() + whole);
+        }
+        if (final) {
+            std::vector<uint8_t> z; std::string e;
+            if (!ggh::bgzf_compress(NULL, 0, 1, 1, z, true, e)) return false;     // EOF marker block
+            if (fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
+        }
+        return true;
     }
-    bool close() { bool ok = true; if (gz) { ok = gzclose(gz) == Z_OK; gz = NULL; } if (f) { ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; } return ok; }
+    bool write(const void* d, size_t n) {
+        if (!bgzf) return fwrite(d, 1, n, f) == n;
+        pend.insert(pend.end(), (const uint8_t*)d, (const uint8_t*)d + n);
+        return pend.size() >= (8u << 20) ? flush_blocks(false) : true;
+    }
+    bool close() {
+        bool ok = true;
+        if (f) { if (bgzf) ok = flush_blocks(true); ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; }
+        return ok;
+    }
 };
 
 // Read a FASTA record stream as the reference's FastQParser(file, true) does (gz or plain) and normalise it to

@@ -8,6 +8,7 @@
 #include <errno.h>
 #include <algorithm>
 #include <map>
+#include <thread>
 
 namespace ggh {
 
@@ -347,6 +348,53 @@ bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err) {
     return true;
 }
 
+// one BGZF block: gzip member with the 'BC' extra field holding the block size (SAM spec 4.1)
+static bool bgzf_block(const uint8_t* in, size_t n, int level, std::vector<uint8_t>& out) {
+    out.resize(18 + compressBound((uLong)n) + 8);
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    zs.next_in = (Bytef*)in; zs.avail_in = (uInt)n; zs.next_out = out.data() + 18; zs.avail_out = (uInt)(out.size() - 18 - 8);
+    const int rc = deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    if (rc != Z_STREAM_END) return false;
+    const size_t total = 18 + clen + 8;
+    if (total > 65536) return false;
+    static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(out.data(), hdr, 16);
+    out[16] = (uint8_t)((total - 1) & 0xff); out[17] = (uint8_t)((total - 1) >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)n), isz = (uint32_t)n;
+    uint8_t* t = out.data() + 18 + clen;
+    for (int k = 0; k < 4; k++) { t[k] = (uint8_t)(crc >> (8 * k)); t[4 + k] = (uint8_t)(isz >> (8 * k)); }
+    out.resize(total);
+    return true;
+}
+bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vector<uint8_t>& out, bool eof_marker, std::string& err) {
+    const size_t B = 0xff00;
+    const size_t nb = (n + B - 1) / B;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(nb, 1));
+    std::vector<std::vector<uint8_t> > blocks(nb);
+    std::vector<int> ok(threads, 1);
+    auto work = [&](int t) {
+        for (size_t b = (size_t)t; b < nb; b += (size_t)threads)
+            if (!bgzf_block(in + b * B, std::min(B, n - b * B), level, blocks[b])) { ok[t] = 0; return; }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.push_back(std::thread(work, t));
+    work(0);
+    for (size_t t = 0; t < th.size(); t++) th[t].join();
+    for (int t = 0; t < threads; t++) if (!ok[t]) { err = "bgzf_compress: deflate failed"; return false; }
+    size_t tot = 0; for (size_t b = 0; b < nb; b++) tot += blocks[b].size();
+    out.clear(); out.reserve(tot + 28);
+    for (size_t b = 0; b < nb; b++) out.insert(out.end(), blocks[b].begin(), blocks[b].end());
+    if (eof_marker) {
+        static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        out.insert(out.end(), eof, eof + 28);
+    }
+    return true;
+}
+
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err) {
     g.path = fasta_path;
     if (!read_file(fasta_path, g.bytes, err)) return false;            // .gz is inflated in memory (the reference writes a temp file, fragSim.cpp:1108-1147)
@@ -417,6 +465,13 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
     return 0;
 }
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream) { return ggh::binomial_draw(n, p, seed, stream); }
+int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int eof_marker, uint8_t* out, size_t cap, size_t* out_n) {
+    std::vector<uint8_t> o; std::string e;
+    if (!ggh::bgzf_compress(in, n, threads, level, o, eof_marker != 0, e)) return -1;
+    *out_n = o.size();
+    if (o.size() > cap) return -2;
+    memcpy(out, o.data(), o.size()); return 0;
+}
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum) {
     std::vector<int32_t> l; std::vector<double> c; ggh::lognormal_table(loc, scale, cap, l, c);
     memcpy(len, l.data(), l.size() * 4); memcpy(cum, c.data(), c.size() * 8); return (int)l.size();

@@ -58,6 +58,10 @@ bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err);
 // exact Binomial(n,p) draw from a Philox-fed uniform stream (inversion for small n*p, BTRS otherwise)
 uint64_t binomial_draw(uint64_t n, double p, uint64_t seed, uint64_t stream);
 
+// ---- parallel BGZF (blocked gzip, readable by zcat/gzstream/htslib) of an output stream ----
+// Splits `in` into 65280-byte blocks, deflates them on `threads` host threads (0 = all), concatenates in order.
+bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vector<uint8_t>& out, bool eof_marker, std::string& err);
+
 // ---- one genome file ready for upload ----
 struct GenomeFile { std::string path; std::vector<uint8_t> bytes; std::vector<FaiEntry> fai; uint64_t total_len; };
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err);
@@ -78,5 +82,7 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
                   const double* bact_w, int n_bact, uint64_t seed, uint64_t* totals3, uint64_t* endo, uint64_t* cont, uint64_t* bact,
                   char* err, int errcap);
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
+/* returns 0 and the compressed size in *out_n; out needs n + n/255 + 64 KiB */
+int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int eof_marker, uint8_t* out, size_t cap, size_t* out_n);
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum);   /* cap+2 rows */
 }

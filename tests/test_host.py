@@ -199,3 +199,25 @@ def test_lognormal_table_matches_scipy():
         want = stats.lognorm.cdf(np.arange(1, 4097), s=scale, scale=np.exp(loc))       # P(int(X) <= l) = F(l+1)
         assert np.abs(np.array(cum[:-1]) - want).max() < 1e-12
         assert all(b >= a for a, b in zip(cum[:-1], cum[1:]))
+
+
+def test_bgzf_writer_roundtrip():
+    """Parallel BGZF (blocked gzip) used for every .gz output: inflates with a plain gzip reader, carries the BC block
+    sizes and the 28-byte EOF marker of the SAM spec."""
+    import gzip
+    lib = api.load_library()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 65279, 65280, 65281, 1_000_003):
+        data = (b">chr1:+:%d:%d:40e1\n" % (n, n + 40)) * 3 + synth._BASES[rng.integers(0, 4, n)].tobytes()
+        out = C.create_string_buffer(len(data) + len(data) // 200 + 70000)
+        m = C.c_size_t()
+        assert lib.ggh_bgzf_compress(data, C.c_size_t(len(data)), 3, 1, 1, out, C.c_size_t(len(out)), C.byref(m)) == 0
+        z = out.raw[:m.value]
+        assert gzip.decompress(z) == data
+        assert z[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+        # walk the blocks through their BSIZE fields
+        p, blocks = 0, 0
+        while p < len(z):
+            assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 12:p + 14] == b"BC"
+            p += (z[p + 16] | (z[p + 17] << 8)) + 1; blocks += 1
+        assert p == len(z) and blocks == (len(data) + 65279) // 65280 + 1
