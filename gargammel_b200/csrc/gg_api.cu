@@ -260,6 +260,7 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
     s.gpos = o; o += 8 * F;
     s.idx = o; o += 8 * F;
+    s.bh = o; o += 8 * F;
     s.meta = o; o += 4 * F;
     s.recoff = o; o += 4 * F;
     s.ci = o; o += 4 * F;
@@ -630,8 +631,14 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     // One warp per tile of F = 32 fragments (fewer only if 32 maximal records do not fit one warp's shared memory);
     // warps per CTA chosen to fill the SM: limited by shared memory, registers and the kernel's launch bound.
     const size_t sm_budget = std::min<size_t>(227 * 1024, ctx->smem_optin) - 2304;   // static: length guide table
-    int dmode = 1;                                   // matrix-only specialisation unless some used slot is Briggs / single / double
-    for (size_t i = 0; i < ctx->plan.size(); i++) { const int sl = ctx->plan[i].damage_slot; if (sl >= 0 && ctx->dmg[sl].mode != GG_DMG_MATRIX && ctx->dmg[sl].mode != GG_DMG_NONE) dmode = 0; }
+    // specialised kernels: 1 = every used damage slot is a matrix, 2 = every used slot is Briggs, 0 = any mix
+    bool has_matrix = false, has_briggs = false, has_other = false;
+    for (size_t i = 0; i < ctx->plan.size(); i++) {
+        const int sl = ctx->plan[i].damage_slot; if (sl < 0) continue;
+        const int m = ctx->dmg[sl].mode;
+        if (m == GG_DMG_MATRIX) has_matrix = true; else if (m == GG_DMG_BRIGGS) has_briggs = true; else if (m != GG_DMG_NONE) has_other = true;
+    }
+    int dmode = has_other || (has_matrix && has_briggs) ? 0 : has_briggs ? 2 : 1;
     // matrix-only plans keep their threshold tables in shared memory (L1 is only a few KB at this carve-out)
     int thr_bytes = 0, thr_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
     if (dmode == 1 && emit != GG_EMIT_FRAG) {

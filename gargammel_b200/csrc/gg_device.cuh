@@ -80,6 +80,20 @@ __device__ __forceinline__ int first_below(const uint32_t* __restrict__ thr, int
     return lo;
 }
 
+// same result, for draws that are usually tiny (geometric tables): probe the first entries, then gallop, then bisect
+__device__ __forceinline__ int first_below_gallop(const uint32_t* __restrict__ thr, int n, uint32_t u) {
+#pragma unroll 1
+    for (int k = 0; k < 4 && k < n; k++) if (u < __ldg(thr + k)) return k;
+    int lo = 4, hi = 8;
+#pragma unroll 1
+    while (hi < n && u >= __ldg(thr + hi)) { lo = hi + 1; hi <<= 1; }
+    hi = min(hi, n);
+    if (lo > hi) return hi;
+#pragma unroll 1
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < __ldg(thr + mid)) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
 // -matfile, one base (deamSim.cpp:1794-1930): i = position, L = fragment length, b = code, x = raw Philox word
 __device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x) {
     const int r = (i < (L >> 1)) ? min(i, D.rows5) : D.rows5 + 1 + min(L - 1 - i, D.rows3);   // sentinel rows absorb the clamp / -last cases
@@ -102,19 +116,23 @@ __device__ __forceinline__ uint32_t dmg_matrix_base_shifted(const DamageDev& D, 
 struct BriggsHdr { int o5, o3, nick; };
 __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const uint4& h) {
     BriggsHdr B;
-    B.o5 = first_below(D.geoL, D.n_geo, h.x >> 1);
-    B.o3 = first_below(D.geoL, D.n_geo, h.y >> 1);
-    B.nick = first_below(D.geoV, D.n_geo, h.z >> 1);
+    B.o5 = first_below_gallop(D.geoL, D.n_geo, h.x >> 1);
+    B.o3 = first_below_gallop(D.geoL, D.n_geo, h.y >> 1);
+    B.nick = first_below_gallop(D.geoV, D.n_geo, h.z >> 1);
     return B;
 }
-// -damage, one base (deamSim.cpp:1483-1594)
+// -damage, one base (deamSim.cpp:1483-1594), branch-free:
+//   C->T at s  if all single-stranded, or inside the 5' overhang            (:1486-1494, :1513-1523, :1557-1567)
+//   G->A at s  inside the 3' overhang                                       (:1527-1537, :1571-1581)
+//   G->A at d  in the double-stranded part at/after the nick, C->T at d before it   (:1542-1548, :1586-1592)
 __device__ __forceinline__ uint32_t dmg_briggs_base(const DamageDev& D, const BriggsHdr& B, int i, int L, uint32_t b, uint32_t x) {
     const uint32_t u = x >> 1;
-    if (B.o5 + B.o3 >= L) return (b == 1u && u < D.Ks) ? 3u : b;          // all single-stranded: C->T at s
-    if (i + 1 <= B.o5)    return (b == 1u && u < D.Ks) ? 3u : b;          // 5' overhang: C->T at s
-    if (L - i <= B.o3)    return (b == 2u && u < D.Ks) ? 0u : b;          // 3' overhang: G->A at s
-    if (B.nick <= i)      return (b == 2u && u < D.Kd) ? 0u : b;          // after the nick: G->A at d
-    return (b == 1u && u < D.Kd) ? 3u : b;                                 // before the nick: C->T at d
+    const bool ss5 = (B.o5 + B.o3 >= L) || (i + 1 <= B.o5);
+    const bool ss3 = !ss5 && (L - i <= B.o3);
+    const bool ct = ss5 || (!ss3 && B.nick > i);
+    const uint32_t K = (ss5 || ss3) ? D.Ks : D.Kd;
+    const uint32_t from = ct ? 1u : 2u, to = ct ? 3u : 0u;
+    return (b == from && u < K) ? to : b;
 }
 // -mat single|double / -mapdamage, one base, both passes (deamSim.cpp:1941-2002); x1 pass-1 word, x2 pass-2 word
 __device__ __forceinline__ uint32_t dmg_sd_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x1, uint32_t x2) {

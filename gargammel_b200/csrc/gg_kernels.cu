@@ -195,10 +195,10 @@ __device__ __noinline__ void build_line_image(const FusedParams& P, const uint32
 // All fields of a 4-base group are processed without per-base branches; fields at or beyond the fragment end hold
 // neighbouring genome bases, index sentinel/clamped rows, and are masked off by the caller.  The group loop is NOT
 // unrolled: the kernel's warps run asynchronously, so code size (instruction cache) matters more than loop overhead.
-// DMODE: 1 = every damage slot of the plan is a -matfile matrix (only that code is compiled in), 0 = any mix.
+// DMODE: 1 = every damage slot of the plan is a -matfile matrix, 2 = every slot is Briggs (only that code is compiled in), 0 = any mix.
 template <int DMODE>
-__device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const DamageDev& D, const uint4* thr_sm, uint64_t id, int k, int fl, int n, uint32_t W) {
-    const int mode = DMODE == 1 ? 1 : D.mode;
+__device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const DamageDev& D, const uint4* thr_sm, unsigned long long bh, uint64_t id, int k, int fl, int n, uint32_t W) {
+    const int mode = DMODE != 0 ? DMODE : D.mode;
     const int i0 = 16 * k;
     const int nq = (n + 3) >> 2;
     uint32_t Wn = 0;
@@ -225,7 +225,7 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
             Wn |= nb << (8 * q);
         }
     } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i
-        const BriggsHdr B = dmg_briggs_hdr(D, rng_block(P.key, id, 0u, ST_DEAM));
+        BriggsHdr B; B.o5 = (int)(bh & 0xFFFFu); B.o3 = (int)((bh >> 16) & 0xFFFFu); B.nick = (int)((bh >> 32) & 0xFFFFu);   // drawn once per fragment in pass A
 #pragma unroll 1
         for (int q = 0; q < nq; q++) {
             const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint8_t*  const s_stage  = wb + P.sm.stage;
     uint64_t* const s_gpos   = (uint64_t*)(wb + P.sm.gpos);
     uint64_t* const s_idx    = (uint64_t*)(wb + P.sm.idx);
+    unsigned long long* const s_bh = (unsigned long long*)(wb + P.sm.bh);
     uint32_t* const s_meta   = (uint32_t*)(wb + P.sm.meta);
     uint32_t* const s_recoff = (uint32_t*)(wb + P.sm.recoff);
     uint32_t* const s_ci     = (uint32_t*)(wb + P.sm.ci);
@@ -379,6 +380,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             s_meta[lane] = META(L, plus, rg->slot, rg->genome);
             s_hdr[lane] = (uint16_t)hdr;
             s_idx[lane] = idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
+            if (DMODE != 1 && emit != 0 && rg->slot >= 0 && (DMODE == 2 || P.dmg[rg->slot].mode == 2)) {   // Briggs: overhangs + nick, once per fragment (deamSim.cpp:1478-1507)
+                const BriggsHdr B = dmg_briggs_hdr(P.dmg[rg->slot], rng_block(P.key, id, 0u, ST_DEAM));
+                s_bh[lane] = (unsigned long long)B.o5 | ((unsigned long long)B.o3 << 16) | ((unsigned long long)B.nick << 32);
+            }
         }
         // warp exclusive scan of pk
         const unsigned long long incl = warp_scan_u64(pk, lane);
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
                                          : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
             if (slot >= 0 && emit != 0)
-                W = damage_chunk<DMODE>(P, P.dmg[slot], s_thr + P.sm.thr_slot[slot], P.first + tile_first + (uint64_t)f, k, fl, n, W);
+                W = damage_chunk<DMODE>(P, P.dmg[slot], s_thr + P.sm.thr_slot[slot], DMODE == 1 ? 0ull : s_bh[f], P.first + tile_first + (uint64_t)f, k, fl, n, W);
             s_dwords[e] = W & lowfields(n);
         }
         __syncwarp();
@@ -565,8 +570,8 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
 
 typedef void (*fused_fn)(const FusedParams);
 static fused_fn fused_variant(int fast, int dmode) {
-    if (fast) return dmode == 1 ? k_fused<true, 1> : k_fused<true, 0>;
-    return dmode == 1 ? k_fused<false, 1> : k_fused<false, 0>;
+    if (fast) return dmode == 1 ? k_fused<true, 1> : dmode == 2 ? k_fused<true, 2> : k_fused<true, 0>;
+    return dmode == 1 ? k_fused<false, 1> : dmode == 2 ? k_fused<false, 2> : k_fused<false, 0>;
 }
 cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs) {
     fused_fn f = fused_variant(fast, dmode);

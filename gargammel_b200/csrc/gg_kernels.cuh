@@ -40,6 +40,7 @@ struct SmemLayout {          // byte offsets into dynamic shared memory, compute
     int stage, stage_bytes;  // output staging (readable slack before and after)
     int gpos, meta, recoff, hdr, cstart, gstart;   // per-fragment descriptors
     int idx, ci, rg;                               // per-fragment header state parked between passes
+    int bh;                                        // per-fragment Briggs header draws (overhangs, nick), u64 each
     int dwords, lwords, cmap, gmap, total;
 };
 struct FusedParams {
