@@ -13,7 +13,7 @@ DEFAULT_ADAPTER_F = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTC
 DEFAULT_ADAPTER_S = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"         # adptSim.cpp:29
 
 FaiEntry = namedtuple("FaiEntry", "name len offset line_blen line_len")
-Range = namedtuple("Range", "first_id count genome damage_slot tag")
+Range = namedtuple("Range", "first_id count genome damage_slot tag comp_slot", defaults=(-1,))
 RunInfo = namedtuple("RunInfo", "bytes records attempts gather_bytes in_bytes device_ms launches")
 
 
@@ -30,7 +30,7 @@ class _Fai(C.Structure):
 
 class _Range(C.Structure):
     _fields_ = [("first_id", C.c_uint64), ("count", C.c_uint64), ("genome", C.c_int32),
-                ("damage_slot", C.c_int32), ("tag", C.c_char * 24)]
+                ("damage_slot", C.c_int32), ("comp_slot", C.c_int32), ("reserved", C.c_int32), ("tag", C.c_char * 24)]
 
 
 class _Out(C.Structure):
@@ -164,6 +164,13 @@ class Context:
         self._ck(self._f("tables_set_singledouble")(self._h, C.c_int(slot), C.c_int(protocol), p5, C.c_int(a5.size // 12),
                                                     p3, C.c_int(a3.size // 12)))
 
+    def set_composition(self, slot, dist, s5p, s5m, s3p, s3m):
+        a = [_darr(x) for x in (s5p, s5m, s3p, s3m)]
+        self._ck(self._f("tables_set_composition")(self._h, C.c_int(slot), C.c_int(dist), a[0][1], a[1][1], a[2][1], a[3][1]))
+
+    def clear_composition(self, slot):
+        self._ck(self._f("tables_clear_composition")(self._h, C.c_int(slot)))
+
     def set_briggs(self, slot, v, l, d, s):
         self._ck(self._f("tables_set_briggs")(self._h, C.c_int(slot), C.c_double(v), C.c_double(l), C.c_double(d), C.c_double(s)))
 
@@ -177,6 +184,7 @@ class Context:
         arr = (_Range * max(len(ranges), 1))()
         for i, r in enumerate(ranges):
             arr[i].first_id, arr[i].count, arr[i].genome, arr[i].damage_slot = r.first_id, r.count, r.genome, r.damage_slot
+            arr[i].comp_slot = r.comp_slot
             arr[i].tag = (r.tag or "").encode()
         self._ck(self._f("plan_set")(self._h, arr, C.c_int(len(ranges))))
 

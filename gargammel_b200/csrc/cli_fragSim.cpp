@@ -7,6 +7,7 @@ int main(int argc, char** argv) {
     int sizeFragments = 20; uint64_t nFragments = 10; int minLen = 0, maxLen = 1000;
     bool noRev = false, seedSpecified = false, specifiedLength = false, specifiedLoc = false, specifiedScale = false; uint64_t seed = 0;
     double location = -1, scale = -1;
+    std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
         " aDNA fragments according to a certain distribution (B200 build)\n\n " + argv[0] + " [options]  [chromosome fasta] \n\n" +
@@ -17,7 +18,8 @@ int main(int argc, char** argv) {
         "\t\t-l\t[length]\t\t\tGenerate fragments of fixed length  (default: 20)\n\t\t-s\t[file]\t\t\t\tOpen file with size distribution (one fragment length per line)\n" +
         "\t\t-f\t[file]\t\t\t\tOpen file with size frequency: length[TAB]freq\n" +
         "\t\t--loc\t[float] --scale\t[float]\tlog-normal fragment lengths\n" +
-        "\tNot in this build: --comp --dist -gc --circ --case --fq --trim5p -uniq -b -u\n";
+        "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
+        "\tNot in this build: -gc --circ --case --fq --trim5p -uniq -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -34,7 +36,9 @@ int main(int argc, char** argv) {
         if (a == "-tmp") { ++i; continue; }                                         // gz inputs are inflated in memory
         if (a == "--loc") { location = to_d(argv[++i], "--loc"); specifiedLoc = true; continue; }
         if (a == "--scale") { scale = to_d(argv[++i], "--scale"); specifiedScale = true; continue; }
-        if (a == "--comp" || a == "--dist" || a == "-gc" || a == "--circ" || a == "--trim5p" || a == "-b")
+        if (a == "--comp") { compFile = argv[++i]; continue; }
+        if (a == "--dist") { distFromEnd = (int)to_ll(argv[++i], "--dist"); continue; }
+        if (a == "-gc" || a == "--circ" || a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
         if (a == "--case" || a == "--fq" || a == "-uniq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
@@ -73,8 +77,13 @@ int main(int argc, char** argv) {
     const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || specifiedLoc) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
     if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), sizeFragments, minLen, maxLen) != GG_OK) return gg_fail(ctx, "size tables");
     gg_tables_set_norev(ctx, noRev ? 1 : 0);
+    if (!compFile.empty()) {                                                        // --comp / --dist, fragSim.cpp:798-1021
+        ggh::CompTables ct;
+        if (!ggh::load_dnacomp(compFile, distFromEnd, ct, err)) return die(err);
+        if (gg_tables_set_composition(ctx, 0, ct.dist, ct.s5p.data(), ct.s5m.data(), ct.s3p.data(), ct.s3m.data()) != GG_OK) return gg_fail(ctx, "--comp");
+    }
     if (nFragments) {
-        gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1;
+        gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1; r.comp_slot = compFile.empty() ? -1 : 0;
         snprintf(r.tag, sizeof r.tag, "%s", tag.c_str());
         if (gg_plan_set(ctx, &r, 1) != GG_OK) return gg_fail(ctx, "plan");
     }

@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
     std::string sizeList, sizeFreq, prefix, adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";   // gargammel.pl:255-257
     bool se = false, keep = false, n_given = false, seedSpecified = false, lognorm = false; uint64_t seed = 0; double loc = 0, scale = 0;
     DamageSpec dAll, dE, dB, dC;
+    std::string misE, misB, misC; int distmis = 1;                                  // --misince/--misincb/--misincc/--distmis (gargammel.pl:300-303)
     const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
         "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
         "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t--seed [int]\t--gpus [N]\t--keep\n";
@@ -77,13 +78,15 @@ int main(int argc, char** argv) {
         if (a == "-mapdamagee") { dE.mapd_file = next(); dE.mapd_proto = next(); continue; }
         if (a == "-mapdamageb") { dB.mapd_file = next(); dB.mapd_proto = next(); continue; }
         if (a == "-mapdamagec") { dC.mapd_file = next(); dC.mapd_proto = next(); continue; }
+        if (a == "-misince") { misE = next(); continue; }  if (a == "-misincb") { misB = next(); continue; }  if (a == "-misincc") { misC = next(); continue; }
+        if (a == "-distmis") { distmis = (int)to_ll(next(), "-distmis"); continue; }
         if (a == "-fa") { adF = next(); continue; }  if (a == "-sa") { adS = next(); continue; }
         if (a == "-rl") { rl = (int)to_ll(next(), "-rl"); continue; }
         if (a == "-se") { se = true; continue; }
         if (a == "-seed") { seed = (uint64_t)to_ll(next(), "--seed"); seedSpecified = true; continue; }
         if (a == "-gpus") { gpus = (int)to_ll(next(), "--gpus"); continue; }
         if (a == "-keep") { keep = true; continue; }
-        if (a == "-mock" || a == "-methyl" || a == "-uniq" || a == "-ss" || a == "-distmis" || a == "-misince" || a == "-misincb" || a == "-misincc" ||
+        if (a == "-mock" || a == "-methyl" || a == "-uniq" || a == "-ss" ||
             a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
         return die("Unknown option: " + a);
     }
@@ -156,13 +159,13 @@ int main(int argc, char** argv) {
     std::cerr << "We will generate: \n\n" << total << "\ttotal fragments\n" << ap.nE << "\tendogenous fragments\n" << ap.nC << "\tcontaminant fragments\n" << ap.nB << "\tbacterial fragments\n";
 
     // ---- plan in the reference's output order e, b, c with its tag grammar (gargammel.pl:1476,1521,1554,1600,1648; 1698-1830)
-    struct PlanItem { size_t src; uint64_t count; std::string tag; int slot; };
+    struct PlanItem { size_t src; uint64_t count; std::string tag; int slot; int comp; };
     std::vector<PlanItem> items;
     for (size_t i = 0; i < srcs.size(); i++) {
-        const Src& s = srcs[i]; PlanItem it; it.src = i; it.count = 0; it.slot = -1;
-        if (s.kind == 'e') { it.count = ap.endo[s.idx]; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; }
-        if (s.kind == 'b') { it.count = ap.bact[s.idx]; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; }
-        if (s.kind == 'c') { it.count = ap.cont[s.idx]; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; }
+        const Src& s = srcs[i]; PlanItem it; it.src = i; it.count = 0; it.slot = -1; it.comp = -1;
+        if (s.kind == 'e') { it.count = ap.endo[s.idx]; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0; }
+        if (s.kind == 'b') { it.count = ap.bact[s.idx]; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; it.comp = misB.empty() ? -1 : 1; }
+        if (s.kind == 'c') { it.count = ap.cont[s.idx]; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; it.comp = misC.empty() ? -1 : 2; }
         if (it.count) items.push_back(it);
     }
     if (gpus < 1) gpus = 1;
@@ -178,12 +181,18 @@ int main(int argc, char** argv) {
         for (size_t k = 0; k < items.size(); k++) {
             int gid = -1;
             if (ggh::upload_genome(ctx, srcs[items[k].src].g, &gid) != GG_OK) return fail("genome upload");
-            gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot;
+            gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot; rg.comp_slot = items[k].comp;
             snprintf(rg.tag, sizeof rg.tag, "%s", items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;
         }
         const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
         if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
         if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) { rcs[r] = 1; gg_ctx_destroy(ctx); return; }
+        const std::string* mis[3] = {&misE, &misB, &misC};
+        for (int m = 0; m < 3; m++) if (!mis[m]->empty()) {                        // fragSim --comp F --dist D per source (gargammel.pl:1492-1495,1615-1618,1664-1667)
+            ggh::CompTables ct; std::string e2;
+            if (!ggh::load_dnacomp(*mis[m], distmis, ct, e2)) { shard_err[r] = e2; rcs[r] = 1; gg_ctx_destroy(ctx); return; }
+            if (gg_tables_set_composition(ctx, m, ct.dist, ct.s5p.data(), ct.s5m.data(), ct.s3p.data(), ct.s3m.data()) != GG_OK) return fail("--misinc");
+        }
         if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), rl) != GG_OK) return fail("adapters");
         if (!plan.empty() && gg_plan_set(ctx, plan.data(), (int)plan.size()) != GG_OK) return fail("plan");
         const uint64_t lo = total * (uint64_t)r / (uint64_t)gpus, hi = total * (uint64_t)(r + 1) / (uint64_t)gpus;

@@ -89,6 +89,8 @@ struct gg_ctx {
     bool sizes_set;
     // damage
     HostDamage dmg[GG_MAX_DAMAGE_SLOTS];
+    // base composition (fragSim --comp)
+    struct HostComp { int dist; double maxP, maxM; DBuf d_tab; } comp[GG_MAX_COMP_SLOTS];
     // adapters
     std::string adF, adS; int read_len;
     DBuf d_adF2, d_adS2, d_rcS2, d_adF, d_adS;
@@ -188,6 +190,7 @@ int sync_plan(gg_ctx* ctx) {
         memset(&r[i], 0, sizeof(RangeDev));
         r[i].first_id = ctx->plan[i].first_id; r[i].count = ctx->plan[i].count;
         r[i].genome = ctx->plan[i].genome; r[i].slot = ctx->plan[i].damage_slot;
+        r[i].comp = (ctx->plan[i].comp_slot >= 0 && ctx->comp[ctx->plan[i].comp_slot].dist > 0) ? ctx->plan[i].comp_slot : -1;
         r[i].tag_len = (int)strnlen(ctx->plan[i].tag, sizeof(ctx->plan[i].tag) - 1);
         memcpy(r[i].tag, ctx->plan[i].tag, r[i].tag_len);
     }
@@ -306,6 +309,7 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
     ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true;                  // adptSim.cpp:31
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
+    for (int i = 0; i < GG_MAX_COMP_SLOTS; i++) { ctx->comp[i].dist = 0; ctx->comp[i].maxP = ctx->comp[i].maxM = 1.0; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
@@ -325,6 +329,7 @@ int gg_ctx_destroy(gg_ctx* ctx) {
                     &ctx->d_size_len, &ctx->d_size_thr, &ctx->d_adF2, &ctx->d_adS2, &ctx->d_rcS2, &ctx->d_adF, &ctx->d_adS, &ctx->d_ranges,
                     &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
+    for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
         ctx->dmg[s].d_thr.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release();
     }
@@ -559,6 +564,29 @@ int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, do
     if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
     return upload_vec(ctx, H.d_geoV, H.geoV);
 }
+int gg_tables_set_composition(gg_ctx* ctx, int slot, int dist, const double* s5p, const double* s5m, const double* s3p, const double* s3m) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_COMP_SLOTS || dist < 1 || dist > GG_MAX_COMP_DIST || !s5p || !s5m || !s3p || !s3m) return ctx->fail(GG_ERR_ARG, "gg_tables_set_composition: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)2 * dist * 4;
+    std::vector<double> t; t.insert(t.end(), s5p, s5p + n); t.insert(t.end(), s5m, s5m + n); t.insert(t.end(), s3p, s3p + n); t.insert(t.end(), s3m, s3m + n);
+    // maxProb exactly as fragSim.cpp:1030-1047 multiplies it (5p+ / 5p- first, then 3p+ / 3p-)
+    double maxP = 1.0, maxM = 1.0;
+    for (int i = 0; i < 2 * dist; i++) maxP = maxP * *std::max_element(s5p + 4 * i, s5p + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxM = maxM * *std::max_element(s5m + 4 * i, s5m + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxP = maxP * *std::max_element(s3p + 4 * i, s3p + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxM = maxM * *std::max_element(s3m + 4 * i, s3m + 4 * i + 4);
+    if (!(maxP > 0.0) || !(maxM > 0.0)) return ctx->fail(GG_ERR_ARG, "gg_tables_set_composition: non-positive composition table");
+    int rc = upload_vec(ctx, ctx->comp[slot].d_tab, t);
+    if (rc) return rc;
+    ctx->comp[slot].dist = dist; ctx->comp[slot].maxP = maxP; ctx->comp[slot].maxM = maxM;
+    ctx->plan_dirty = true;
+    return GG_OK;
+}
+int gg_tables_clear_composition(gg_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= GG_MAX_COMP_SLOTS) return GG_ERR_ARG;
+    ctx->comp[slot].dist = 0; ctx->plan_dirty = true; return GG_OK;
+}
 int gg_tables_clear_damage(gg_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
     ctx->dmg[slot].mode = GG_DMG_NONE; return GG_OK;
@@ -581,6 +609,7 @@ int gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n) {
         if (ranges[i].first_id != next) return ctx->fail(GG_ERR_ARG, "gg_plan_set: ranges must be contiguous and ascending in fragment id");
         if (ranges[i].genome < 0 || ranges[i].genome >= (int)ctx->genomes.size()) return ctx->fail(GG_ERR_ARG, "gg_plan_set: unknown genome id");
         if (ranges[i].damage_slot < -1 || ranges[i].damage_slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad damage slot");
+        if (ranges[i].comp_slot < -1 || ranges[i].comp_slot >= GG_MAX_COMP_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad composition slot");
         if (ranges[i].count == 0) return ctx->fail(GG_ERR_ARG, "gg_plan_set: empty range");
         next += ranges[i].count;
     }
@@ -682,6 +711,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.size_mode = ctx->size_mode; P.fixed_len = ctx->fixed_len; P.minlen = ctx->minlen; P.maxlen = ctx->maxlen; P.n_sizes = (int)ctx->size_len.size();
     P.size_thr = ctx->d_size_thr.as<uint32_t>(); P.size_len = ctx->d_size_len.as<int32_t>();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
+    for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) { P.comp[s].dist = ctx->comp[s].dist; P.comp[s].tab = ctx->comp[s].d_tab.as<double>(); P.comp[s].maxP = ctx->comp[s].maxP; P.comp[s].maxM = ctx->comp[s].maxM; }
     P.ad.adF2 = ctx->d_adF2.as<uint32_t>() + 1; P.ad.adS2 = ctx->d_adS2.as<uint32_t>() + 1; P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>() + 1;
     P.ad.lenF = (int)ctx->adF.size(); P.ad.lenS = (int)ctx->adS.size(); P.ad.read_len = ctx->read_len;
     P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;

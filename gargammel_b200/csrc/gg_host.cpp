@@ -143,6 +143,43 @@ void lognormal_table(double loc, double scale, int cap, std::vector<int32_t>& le
     len.push_back(cap + 1); cum.push_back(1.0);
 }
 
+bool load_dnacomp(const std::string& path, int dist, CompTables& out, std::string& err) {
+    std::vector<uint8_t> b;
+    if (dist < 1 || dist > GG_MAX_COMP_DIST) { err = "--dist must be between 1 and 32"; return false; }
+    if (!read_file(path, b, err)) { err = "Unable to open composition file " + path; return false; }       // fragSim.cpp:1014
+    std::vector<std::string> lines; split_lines(b, lines);
+    out.dist = dist; out.s5p.clear(); out.s5m.clear(); out.s3p.clear(); out.s3m.clear();
+    int first[4] = {-1000, -1000, -1000, -1000};                        // sub5pPlusi, sub5pMinusi, sub3pPlusi, sub3pMinusi (:793-796)
+    unsigned int tot[5] = {0, 0, 0, 0, 0};
+    for (size_t li = 0; li < lines.size(); li++) {
+        const std::string& line = lines[li];
+        if (line.compare(0, 1, "#") == 0 || line.compare(0, 3, "Chr") == 0) continue;          // :817-819
+        std::vector<std::string> f = all_tokens(line, '\t');
+        if (f.size() <= 7) continue;                                     // :825
+        if (f.size() < 9) { err = "Parse error in composition file " + path + ": " + line; return false; }
+        long long d, c[5];
+        if (!to_i64(f[3], &d)) { err = "Parse error in composition file " + path + ": " + line; return false; }
+        for (int k = 0; k < 5; k++) if (!to_i64(f[4 + k], &c[k])) { err = "Parse error in composition file " + path + ": " + line; return false; }
+        if (llabs(d) <= dist) {                                          // :837
+            const bool is3 = f[1] == "3p", is5 = f[1] == "5p", plus = f[2] == "+", minus = f[2] == "-";
+            if (!(is3 || is5) || !(plus || minus)) continue;
+            const int which = (is5 ? 0 : 2) + (plus ? 0 : 1);
+            if (first[which] == -1000) first[which] = (int)d;
+            else if (d < first[which]) { err = "Parse error, wrong order of distance to fragment end  for line " + line; return false; }   // :846-849
+            std::vector<double>& v = which == 0 ? out.s5p : which == 1 ? out.s5m : which == 2 ? out.s3p : out.s3m;
+            for (int k = 0; k < 4; k++) v.push_back((double)(unsigned int)c[k] / (double)(unsigned int)c[4]);      // :853-857
+        } else for (int k = 0; k < 5; k++) tot[k] += (unsigned int)c[k];  // background, :922-929
+    }
+    const size_t need = (size_t)2 * dist * 4;
+    if (out.s5p.size() != need || out.s5m.size() != need || out.s3p.size() != need || out.s3m.size() != need) {
+        err = "Composition file " + path + " does not hold " + std::to_string(2 * dist) + " positions within --dist of every end/strand"; return false;
+    }
+    double bg[4]; for (int k = 0; k < 4; k++) bg[k] = (double)tot[k] / (double)tot[4];             // :937-940
+    std::vector<double>* all[4] = {&out.s5p, &out.s5m, &out.s3p, &out.s3m};
+    for (int t = 0; t < 4; t++) for (size_t i = 0; i < need; i++) { const double x = (*all[t])[i] - bg[i & 3]; (*all[t])[i] = 0.25 + x; }   // :948-1008
+    return true;
+}
+
 // one .dat/.prof file: header line skipped; per line: tab fields (dropping the first `skip` columns), token before ' ' -> double
 static bool load_rate_file(const std::string& path, int skip, Rates& sub, std::string& err, const char* which) {
     std::vector<uint8_t> b;
@@ -471,6 +508,12 @@ int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int e
     *out_n = o.size();
     if (o.size() > cap) return -2;
     memcpy(out, o.data(), o.size()); return 0;
+}
+int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, double* s3p, double* s3m, char* err, int errcap) {
+    ggh::CompTables t; std::string e;
+    if (!ggh::load_dnacomp(path, dist, t, e)) return set_err(err, errcap, e);
+    const size_t n = (size_t)2 * dist * 4 * 8;
+    memcpy(s5p, t.s5p.data(), n); memcpy(s5m, t.s5m.data(), n); memcpy(s3p, t.s3p.data(), n); memcpy(s3m, t.s3m.data(), n); return 0;
 }
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum) {
     std::vector<int32_t> l; std::vector<double> c; ggh::lognormal_table(loc, scale, cap, l, c);

@@ -29,6 +29,10 @@ bool load_size_freq(const std::string& path, std::vector<int32_t>& len, std::vec
 // cum[l] = P(length <= l) = Phi((ln(l+1) - loc) / scale); a last row `cap+1` with cum 1 holds the tail (rejected by -M).
 void lognormal_table(double loc, double scale, int cap, std::vector<int32_t>& len, std::vector<double>& cum);
 
+// --comp file (mapDamage dnacomp.txt) with --dist d: four [2d][4] tables of "frequency - background + 0.25" (fragSim.cpp:798-1012)
+struct CompTables { int dist; std::vector<double> s5p, s5m, s3p, s3m; };
+bool load_dnacomp(const std::string& path, int dist, CompTables& out, std::string& err);
+
 typedef std::vector<double> Rates;   // rows x 12, idx = from*3 + (to<from ? to : to-1), bases A,C,G,T
 // -matfile prefix: <prefix>5.dat / <prefix>3.dat; first column dropped, "value [lo..hi]" -> value; per-base sums <= 1;
 // the 3' file is reversed so that row 0 is the terminal base (deamSim.cpp:1098-1241)
@@ -84,5 +88,6 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
 /* returns 0 and the compressed size in *out_n; out needs n + n/255 + 64 KiB */
 int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int eof_marker, uint8_t* out, size_t cap, size_t* out_n);
+int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, double* s3p, double* s3m, char* err, int errcap);   /* each [2*dist][4] */
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum);   /* cap+2 rows */
 }

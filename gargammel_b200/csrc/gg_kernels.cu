@@ -191,6 +191,35 @@ __device__ __noinline__ void build_line_image(const FusedParams& P, const uint32
     A.flush();
 }
 
+// fragSim --comp acceptance (fragSim.cpp:1609-1759): product of 4*dist position-specific base frequencies over the
+// fragment ends and their flanks, in the reference's multiplication order and in IEEE fp64 (no contraction), divided by
+// the maximum attainable product; accept iff uniform < product.  temp[t] = fragment-orientation window incl. flanks.
+__device__ __noinline__ bool comp_accept(const FusedParams& P, const CompDev& C, const uint32_t* __restrict__ seq2, uint64_t gpos, int L,
+                                         uint32_t plus, uint64_t id, uint32_t attempt) {
+    const int d = C.dist, W = L + 2 * d;
+    const uint64_t w0 = gpos - (uint64_t)d;
+    auto temp = [&](int t) -> uint32_t {
+        const uint64_t p = plus ? w0 + (uint64_t)t : w0 + (uint64_t)(W - 1 - t);
+        const uint32_t c = (__ldg(seq2 + (p >> 4)) >> (2 * (p & 15))) & 3u;
+        return plus ? c : 3u - c;
+    };
+    const double* s5 = C.tab + (plus ? 0 : 1) * (2 * d * 4);
+    const double* s3 = C.tab + (plus ? 2 : 3) * (2 * d * 4);
+    double acc = 1.0;
+#pragma unroll 1
+    for (int i = 0; i < d; i++) acc = __dmul_rn(acc, __ldg(s5 + i * 4 + temp(i)));                    // 5p before frag
+#pragma unroll 1
+    for (int i = 0; i < d; i++) acc = __dmul_rn(acc, __ldg(s5 + (i + d) * 4 + temp(d + i)));          // 5p in frag
+#pragma unroll 1
+    for (int i = 0; i < d; i++) acc = __dmul_rn(acc, __ldg(s3 + i * 4 + temp(L + i)));                // 3p in frag: frag[L-d+i] = temp[L+i]
+#pragma unroll 1
+    for (int i = 0; i < d; i++) acc = __dmul_rn(acc, __ldg(s3 + (i + d) * 4 + temp(L + d + i)));      // 3p after frag
+    acc = __ddiv_rn(acc, plus ? C.maxP : C.maxM);
+    const uint4 y = rng_block(P.key, id, attempt, ST_FRAG2);
+    const double p = __dmul_rn((double)(y.x >> 1) + 0.5, 1.0 / 2147483648.0);
+    return p < acc;
+}
+
 // Damage of one 16-base chunk (fields 0..15 of W = fragment positions 16k..16k+15, n of them inside the fragment).
 // All fields of a 4-base group are processed without per-base branches; fields at or beyond the fragment end hold
 // neighbouring genome bases, index sentinel/clamped rows, and are masked off by the caller.  The group loop is NOT
@@ -323,6 +352,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const RangeDev* rg = P.ranges + lo;
             const GenomeDev G = P.genomes[rg->genome];
             const uint64_t* cum = P.ctab.cum_end + G.first_contig;
+            const int d = rg->comp >= 0 ? P.comp[rg->comp].dist : 0;       // distFromEnd: 0 without --comp (fragSim.cpp:1019-1021)
             uint64_t gpos = 0; bool ok = false;
             for (uint32_t attempt = 0; attempt < 65536u; attempt++) {
                 const uint4 x = rng_block(P.key, id, attempt, ST_FRAG);
@@ -337,36 +367,39 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     if (k == P.n_sizes) k = (int)(((uint64_t)(x.y >> 1) * (uint64_t)P.n_sizes) >> 31);   // fragSim.cpp:176
                     L = __ldg(P.size_len + k);
                 }
-                if (L < 0 || L < P.minlen || L > P.maxlen) continue;                 // fragSim.cpp:1375-1381
+                if (L < d || L < P.minlen || L > P.maxlen) continue;                 // fragSim.cpp:1375-1381
                 const uint64_t r64 = ((uint64_t)x.w << 32) | x.z;
                 const uint64_t coord = __umul64hi(r64, G.G);                           // randGenomicCoord, fragSim.cpp:80-93
                 if (coord == 0) continue;                                              // never matches a chromosome (starts are 1-based)
                 const uint64_t cp = coord - 1;
-                int a = 0, b = G.n_contigs - 1;                                        // first contig with cp <= cum_end (fragSim.cpp:1397-1403)
-                while (a < b) { int mid = (a + b) >> 1; if (cp <= __ldg(cum + mid)) b = mid; else a = mid + 1; }
+                // first contig with start+d <= coord <= end-d+1 (fragSim.cpp:1397-1403); for d == 0 that is the first with cp <= cum_end
+                const uint64_t key = d ? coord : cp;
+                int a = 0, b = G.n_contigs - 1;
+                while (a < b) { int mid = (a + b) >> 1; if (key <= __ldg(cum + mid)) b = mid; else a = mid + 1; }
                 ci = G.first_contig + a;
                 const uint64_t clen = __ldg(P.ctab.len + ci);
                 idx = cp - (__ldg(cum + a) - clen);                                    // coord - startIndexChr, fragSim.cpp:1404
-                if (idx + (uint64_t)L > clen) continue;                                // run-off past the contig end is always rejected (fragSim.cpp:1472)
+                if (idx < (uint64_t)d || idx + (uint64_t)L + (uint64_t)d > clen) continue;   // outside [start+d, end-d+1], or run-off past the contig end (always rejected, fragSim.cpp:1472)
                 gpos = __ldg(P.ctab.gbase + ci) + idx;
-                if (L > 0) {                                                           // isResolvedDNAstring, fragSim.cpp:333-339,1472
-                    const uint64_t e = gpos + (uint64_t)L - 1;
-                    const uint64_t w0 = gpos >> 5, w1 = e >> 5;
+                if (L + 2 * d > 0) {                                                   // isResolvedDNAstring over the window incl. the flanks, fragSim.cpp:333-339,1472
+                    const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1;
+                    const uint64_t w0 = s0 >> 5, w1 = e >> 5;
                     uint32_t any = 0;
 #pragma unroll 1
                     for (uint64_t w = w0; w <= w1; w++) {
                         uint32_t m = __ldg(G.nmask + w);
-                        if (w == w0) m &= 0xFFFFFFFFu << (gpos & 31);
+                        if (w == w0) m &= 0xFFFFFFFFu << (s0 & 31);
                         if (w == w1) m &= 0xFFFFFFFFu >> (31 - (e & 31));
                         any |= m;
                     }
                     if (any) continue;
                 }
                 plus = P.norev ? 1u : (x.y & 1u);                                      // randomBool, fragSim.cpp:1462-1467
+                if (d && !comp_accept(P, P.comp[rg->comp], G.seq2, gpos, L, plus, id, attempt)) continue;   // --comp, fragSim.cpp:1609-1759
                 ok = true; break;
             }
             if (!ok) { my_err |= ERRF_GIVEUP; L = 0; idx = 0; }
-            my_gather += (unsigned long long)((L + 3) / 4 + (L + 7) / 8);
+            my_gather += (unsigned long long)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
             const int nlen = __ldg(P.ctab.name_len + ci);
             hdr = 1 + nlen + 3 + ndigits(idx) + 1 + ndigits(idx + (uint64_t)L) + 1 + ndigits((uint64_t)L) + tag_len;

@@ -23,8 +23,13 @@ struct ContigTab {           // struct-of-arrays over all contigs of all genomes
 };
 struct RangeDev {            // one `fragSim -tag T -n N file` of the plan
     uint64_t first_id, count;
-    int genome, slot, tag_len, pad;
+    int genome, slot, tag_len, comp;
     char tag[24];
+};
+struct CompDev {             // fragSim --comp tables of one slot (fp64: the acceptance product must round like the reference)
+    int dist, pad;
+    const double* tab;       // [4 tables: 5p+,5p-,3p+,3p-][2*dist][4]
+    double maxP, maxM;       // fragSim.cpp:1030-1047
 };
 struct Adapters {
     const uint32_t* adF2;    // forward adapter, 2-bit packed (+slack)
@@ -63,6 +68,7 @@ struct FusedParams {
     const int32_t*  size_len;
     // damage + adapters
     ggd::DamageDev dmg[4];
+    CompDev comp[4];
     Adapters ad;
     // output
     uint8_t* out; uint64_t out_cap;

@@ -119,3 +119,21 @@ def write_sizefreq(path):
     with open(path, "w") as f:
         for a, b in golden()["sizefreq"]:
             f.write("%d\t%s\n" % (a, b))
+
+
+def write_dnacomp(path, seed=3, max_pos=8):
+    """A mapDamage-style dnacomp.txt (Chr End Std Pos A C G T Total) with position-specific base counts."""
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as f:
+        f.write("# table produced by synth.write_dnacomp\n# comment\nChr\tEnd\tStd\tPos\tA\tC\tG\tT\tTotal\n")
+        for end in ("3p", "5p"):
+            for std in ("+", "-"):
+                for pos in list(range(-max_pos, 0)) + list(range(1, max_pos + 1)):
+                    w = np.array([0.3, 0.2, 0.2, 0.3]) if abs(pos) > 2 else rng.dirichlet([3, 3, 3, 3])
+                    c = rng.multinomial(500000, w)
+                    f.write("21\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\n" % (end, std, pos, c[0], c[1], c[2], c[3], c.sum()))
+
+
+def golden_dnacomp():
+    """The reference's src/dnacomp.txt parsed with --dist 2: [5p+, 5p-, 3p+, 3p-] x [4 positions][4 bases]."""
+    return [np.array(t, dtype=np.float64) for t in golden()["dnacomp_dist2"]]

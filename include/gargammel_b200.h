@@ -57,6 +57,8 @@ typedef enum gg_damage_mode {
     GG_DMG_DOUBLE = 4    /* -mat double / -mapdamage f double  deamSim.cpp:1973-2002 */
 } gg_damage_mode;
 #define GG_MAX_DAMAGE_SLOTS 4
+#define GG_MAX_COMP_SLOTS 4
+#define GG_MAX_COMP_DIST 32
 
 /* ---- what the last stage writes ---- */
 typedef enum gg_emit_mode {
@@ -86,6 +88,8 @@ typedef struct gg_range {
     uint64_t count;          /* number of fragments                           */
     int32_t  genome;         /* id returned by gg_genome_upload               */
     int32_t  damage_slot;    /* 0..GG_MAX_DAMAGE_SLOTS-1, or -1 = no damage   */
+    int32_t  comp_slot;      /* base-composition table (fragSim --comp), 0..GG_MAX_COMP_SLOTS-1, or -1 = none */
+    int32_t  reserved;
     char     tag[24];        /* NUL-terminated -tag string appended to defline (fragSim.cpp:1505-1507) */
 } gg_range;
 
@@ -132,6 +136,11 @@ int  gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len
 int  gg_tables_set_sizes(gg_ctx* ctx, int mode, const int32_t* len, const double* cum, int n,
                          int fixed_len, int minlen, int maxlen);
 int  gg_tables_set_norev(gg_ctx* ctx, int norev);   /* --norev, fragSim.cpp:1463-1467 */
+/* fragSim --comp/--dist (fragSim.cpp:798-1047,1609-1759): base-composition acceptance.  Each table is [2*dist][4] (A,C,G,T) and
+ * already holds "frequency - background + 0.25" (fragSim.cpp:948-1012): s5p = 5' end on the + strand, s5m on the - strand, s3p/s3m the
+ * 3' end; rows 0..dist-1 are the positions outside the fragment on the 5' side / inside on the 3' side (reference order). */
+int  gg_tables_set_composition(gg_ctx* ctx, int slot, int dist, const double* s5p, const double* s5m, const double* s3p, const double* s3m);
+int  gg_tables_clear_composition(gg_ctx* ctx, int slot);
 /* deamSim -matfile/-profile (deamSim.cpp:956-1241): sub5[r][12], sub3[r][12] with index 0 = terminal base
  * (i.e. AFTER the 3' reversal of deamSim.cpp:1236); clamp_last = !(-last) (deamSim.cpp:1811-1817). */
 int  gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5,

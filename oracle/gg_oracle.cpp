@@ -12,7 +12,7 @@
  *
  * PARITY STATUS: the deterministic transforms (reverse complement, trimming, record grammar,
  * matrix row selection, cumulative-probability pick) are pinned against the reference sources
- * compiled with our shim (oracle/_ref, see oracle/Makefile) by tests/test_oracle_vs_ref.py;
+ * compiled with our shim (oracle/_ref, see oracle/Makefile) by tests/test_cli.py;
  * everything stochastic is pinned STATISTICALLY against those binaries (the reference is
  * time-seeded and its uniform helpers live in un-vendored libgab: bit-level parity of the
  * random stream is unpinnable).
@@ -52,7 +52,7 @@ static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
 }
 
 /* stream ids (counter word 3) -- DESIGN.md "Draw specification" */
-enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4 };
+enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4, ST_FRAG2 = 5 };
 
 struct Rng {
     uint32_t k0, k1;
@@ -88,8 +88,10 @@ struct Damage {
     double v, l, d, s;
     Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0) {}
 };
+struct Comp { int dist; std::vector<double> s5p, s5m, s3p, s3m; double maxP, maxM; Comp() : dist(0), maxP(1), maxM(1) {} };
 struct orc_ctx {
     Rng rng;
+    Comp comp[GG_MAX_COMP_SLOTS];
     std::vector<Genome> genomes;
     int size_mode, fixed_len, minlen, maxlen, norev;
     std::vector<int32_t> size_len; std::vector<double> size_cum;
@@ -139,39 +141,54 @@ struct FragResult { const Chr* chr; uint64_t idx; int length; bool plus; std::st
 
 /* One fragment = the first accepted attempt; mirrors the while-loop body fragSim.cpp:1361-1507
  * with distFromEnd == 0 (no --comp: fragSim.cpp:1019-1021), no --circ, no -gc. */
-static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, FragResult* out) {
+static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slot, FragResult* out) {
+    const Comp* cp = (comp_slot >= 0 && c->comp[comp_slot].dist > 0) ? &c->comp[comp_slot] : NULL;
+    const int d = cp ? cp->dist : 0;                         /* distFromEnd: 0 without --comp (fragSim.cpp:1019-1021) */
     for (uint32_t attempt = 0; attempt < GG_MAX_ATTEMPTS; attempt++) {
         uint32_t x[4];
         c->rng.block(id, attempt, ST_FRAG, x);
         c->attempts++;
         int length = selectFragmentLength(c, x[0], x[1]);
-        if (length < 0) continue;                            /* :1375 with distFromEnd 0 */
+        if (length < d) continue;                            /* :1375 */
         if (length < c->minlen) continue;                    /* :1377 */
         if (length > c->maxlen) continue;                    /* :1380 */
         /* randGenomicCoord, fragSim.cpp:80-93: uniform in [0,G).  (multiply-shift instead of %: DESIGN.md) */
         uint64_t r64 = ((uint64_t)x[3] << 32) | x[2];
         uint64_t coord = (uint64_t)(((unsigned __int128)r64 * g.G) >> 64);
-        /* chromosome scan fragSim.cpp:1397-1403: first chr with start <= coord <= end+1 */
+        /* chromosome scan fragSim.cpp:1397-1403: first chr with start+d <= coord <= end-d+1 */
         const Chr* found = NULL;
         for (size_t i = 0; i < g.chrs.size(); i++) {
-            if (g.chrs[i].start <= coord && coord <= g.chrs[i].end + 1) { found = &g.chrs[i]; break; }
+            if (g.chrs[i].start + (uint64_t)d <= coord && coord + (uint64_t)d <= g.chrs[i].end + 1) { found = &g.chrs[i]; break; }
         }
-        if (!found) continue;   /* coord == 0: the reference redraws only the coordinate (:1390); we redraw the attempt */
+        if (!found) continue;   /* the reference redraws only the coordinate (:1390); we redraw the attempt */
         uint64_t idx = coord - found->start;                 /* :1404 */
-        std::string temp;
-        if (idx + (uint64_t)length > (uint64_t)found->len) {
+        if (idx + (uint64_t)length + (uint64_t)d > (uint64_t)found->len) {
             /* run-off: the reference fetches past the contig and always hits '\n', '>' or EOF, so
              * isResolvedDNAstring rejects it (:1472).  Same outcome, stated directly. */
             continue;
         }
-        temp = fetchSeq(g, *found, (int64_t)idx, length);    /* :1443 */
+        std::string temp = fetchSeq(g, *found, (int64_t)idx - d, length + 2 * d);    /* :1443 */
         bool plus = c->norev ? true : ((x[1] & 1u) != 0);    /* :1462-1467 randomBool */
         bool resolved = true;                                /* :1472 isResolvedDNAstring */
         for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
         if (!resolved) continue;
         if (!plus) temp = reverseComplement(temp);           /* :1484 */
-        out->chr = found; out->idx = idx; out->length = length; out->plus = plus; out->frag = temp;
-        c->gather_bytes += (uint64_t)((length + 3) / 4 + (length + 7) / 8);
+        std::string preFrag = temp.substr(0, d), frag = temp.substr(d, length), posFrag = temp.substr(length + d, d);   /* :1485-1496 */
+        if (cp) {                                            /* --comp acceptance, fragSim.cpp:1609-1759 */
+            const std::vector<double>& s5 = plus ? cp->s5p : cp->s5m;
+            const std::vector<double>& s3 = plus ? cp->s3p : cp->s3m;
+            double probAcc = 1.0;
+            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)i * 4 + base2int(preFrag[i])];                 /* :1614-1616 */
+            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)(i + d) * 4 + base2int(frag[i])];              /* :1619-1621 */
+            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)i * 4 + base2int(frag[length - d + i])];       /* :1624-1626 */
+            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)(i + d) * 4 + base2int(posFrag[i])];           /* :1629-1631 */
+            probAcc = probAcc / (plus ? cp->maxP : cp->maxM);                                                 /* :1633 */
+            uint32_t y[4]; c->rng.block(id, attempt, ST_FRAG2, y);
+            if (!(u01(y[0]) < probAcc)) continue;                                                             /* :1639 */
+        }
+        out->chr = found; out->idx = idx; out->length = length; out->plus = plus; out->frag = frag;
+        const int w = length + 2 * d;
+        c->gather_bytes += (uint64_t)((w + 3) / 4 + (w + 7) / 8);
         return 0;
     }
     return GG_ERR_GIVEUP;
@@ -393,6 +410,21 @@ int orc_tables_set_singledouble(orc_ctx* c, int slot, int protocol, const double
     D.sub5.assign(sub5, sub5 + (size_t)rows5 * 12); D.sub3.assign(sub3, sub3 + (size_t)rows3 * 12);
     return 0;
 }
+/* maxProb as fragSim.cpp:1030-1047 */
+int orc_tables_set_composition(orc_ctx* c, int slot, int dist, const double* s5p, const double* s5m, const double* s3p, const double* s3m) {
+    if (slot < 0 || slot >= GG_MAX_COMP_SLOTS || dist < 1 || dist > GG_MAX_COMP_DIST) return GG_ERR_ARG;
+    Comp& C = c->comp[slot]; C.dist = dist;
+    const size_t n = (size_t)2 * dist * 4;
+    C.s5p.assign(s5p, s5p + n); C.s5m.assign(s5m, s5m + n); C.s3p.assign(s3p, s3p + n); C.s3m.assign(s3m, s3m + n);
+    double maxP = 1.0, maxM = 1.0;
+    for (int i = 0; i < 2 * dist; i++) maxP = maxP * *std::max_element(s5p + 4 * i, s5p + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxM = maxM * *std::max_element(s5m + 4 * i, s5m + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxP = maxP * *std::max_element(s3p + 4 * i, s3p + 4 * i + 4);
+    for (int i = 0; i < 2 * dist; i++) maxM = maxM * *std::max_element(s3m + 4 * i, s3m + 4 * i + 4);
+    C.maxP = maxP; C.maxM = maxM;
+    return 0;
+}
+int orc_tables_clear_composition(orc_ctx* c, int slot) { if (slot < 0 || slot >= GG_MAX_COMP_SLOTS) return GG_ERR_ARG; c->comp[slot] = Comp(); return 0; }
 int orc_tables_set_briggs(orc_ctx* c, int slot, double v, double l, double d, double s) {
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
     Damage& D = c->dmg[slot]; D.mode = GG_DMG_BRIGGS; D.v = v; D.l = l; D.d = d; D.s = s; return 0;
@@ -417,7 +449,7 @@ int orc_run_fused(orc_ctx* c, uint64_t first, uint64_t count, int emit, uint8_t*
         if (!rg) { c->err = "fragment id outside the plan"; return GG_ERR_STATE; }
         if (rg->genome < 0 || rg->genome >= (int)c->genomes.size()) { c->err = "bad genome id"; return GG_ERR_ARG; }
         FragResult f;
-        int rc = sampleFragment(c, c->genomes[rg->genome], id, &f);
+        int rc = sampleFragment(c, c->genomes[rg->genome], id, rg->comp_slot, &f);
         if (rc) { c->err = "fragment exhausted its attempts"; return rc; }
         std::string name = fragDefline(f, rg->tag);
         std::string seq = f.frag;

@@ -109,3 +109,31 @@ def load_mapdamage(path):
     def rates(c):
         return [[(sub[b * 3 + a] / base[b]) if base[b] else float("nan") for b in range(4) for a in range(3)] for base, sub in c]
     return rates(cnt["5p"]), rates(cnt["3p"])
+
+
+def load_dnacomp(path, dist):
+    """fragSim.cpp:798-1012: mapDamage dnacomp.txt -> four [2*dist][4] tables of frequency - background + 0.25
+    (5p+, 5p-, 3p+, 3p-), positions within `dist` of the fragment end in file order; everything else is background."""
+    tabs = {("5p", "+"): [], ("5p", "-"): [], ("3p", "+"): [], ("3p", "-"): []}
+    tot = [0, 0, 0, 0, 0]
+    for line in _lines(path):
+        if line.startswith("#") or line.startswith("Chr"):
+            continue
+        f = line.split("\t")
+        if len(f) <= 7:
+            continue
+        d = int(f[3]); c = [int(x) for x in f[4:9]]
+        if abs(d) <= dist:
+            if (f[1], f[2]) in tabs:
+                tabs[(f[1], f[2])].append([c[k] / c[4] for k in range(4)])
+        else:
+            for k in range(5):
+                tot[k] += c[k]
+    bg = [tot[k] / tot[4] for k in range(4)]
+    out = []
+    for key in (("5p", "+"), ("5p", "-"), ("3p", "+"), ("3p", "-")):
+        rows = tabs[key]
+        if len(rows) != 2 * dist:
+            raise ValueError("composition file does not hold 2*dist positions for %s %s" % key)
+        out.append([[0.25 + (r[k] - bg[k]) for k in range(4)] for r in rows])
+    return out

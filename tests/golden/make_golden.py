@@ -41,6 +41,7 @@ def main():
         f.write("\n".join(keep) + "\n")
     s5, s3 = parsers.load_mapdamage(os.path.join(HERE, "mapdamage_sample.txt"))
     out["mapdamage_sample"] = {"sub5": s5, "sub3": s3}
+    out["dnacomp_dist2"] = parsers.load_dnacomp(os.path.join(REF, "src", "dnacomp.txt"), 2)     # 5p+,5p-,3p+,3p- x [4][4]
     with open(os.path.join(HERE, "ref_tables.json"), "w") as f:
         json.dump(out, f, indent=0, separators=(",", ":"))
     print("wrote ref_tables.json:", {k: (len(v) if hasattr(v, "__len__") else v) for k, v in out.items()})

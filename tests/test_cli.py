@@ -203,6 +203,19 @@ def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
     assert ours_ln.returncode == 0 and ref_ln.returncode == 0, ours_ln.stderr
     a = np.array([len(s) for _, s in util.records(ours_ln.stdout)]); b = np.array([len(s) for _, s in util.records(ref_ln.stdout)])
     assert stats.ks_2samp(a, b).pvalue > 0.01 and abs(a.mean() - np.exp(4.1 + 0.35 ** 2 / 2) + 0.5) < 1.0
+    # --comp/--dist: base composition at the fragment ends, ours vs the reference (chi-square homogeneity of the first/last base)
+    synth.write_dnacomp(str(d / "dnacomp.txt"), seed=11)
+    oc = run([os.path.join(BIN, "fragSim"), "--seed", "8", "-n", "120000", "-l", "40", "--comp", str(d / "dnacomp.txt"), "--dist", "2", str(d / "g.fa")])
+    rc = run([_ref("fragSim"), "--seed", "8", "-n", "40000", "-l", "40", "--comp", str(d / "dnacomp.txt"), "--dist", "2", str(d / "g.fa")])
+    assert oc.returncode == 0 and rc.returncode == 0, oc.stderr + rc.stderr
+    for pos in (0, 1, -2, -1):
+        ta = np.array([[s[pos] == c for c in b"ACGT"] for _, s in util.records(oc.stdout)]).sum(0)
+        tb = np.array([[s[pos] == c for c in b"ACGT"] for _, s in util.records(rc.stdout)]).sum(0)
+        assert stats.chi2_contingency(np.array([ta, tb]))[1] > 0.001, (pos, ta, tb)
+    plain = run([os.path.join(BIN, "fragSim"), "--seed", "8", "-n", "120000", "-l", "40", str(d / "g.fa")])
+    t0 = np.array([[s[0] == c for c in b"ACGT"] for _, s in util.records(plain.stdout)]).sum(0)
+    t1 = np.array([[s[0] == c for c in b"ACGT"] for _, s in util.records(oc.stdout)]).sum(0)
+    assert stats.chi2_contingency(np.array([t0, t1]))[1] < 1e-6            # the composition file really changes the ends
     # start positions are uniform over the accepted windows in both: compare coarse histograms of chr1 starts
     def starts(out):
         return np.array([int(h.split(b":")[2]) for h, _ in util.records(out) if h.startswith(b">chr1:")])

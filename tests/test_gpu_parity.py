@@ -239,3 +239,23 @@ def test_run_fused_to_host_chunked(oracle_mod, genomes):
         assert i2.bytes == len(full) and buf.raw[:i2.bytes] == full and i2.records == 7500 and i2.attempts == info.attempts
     with pytest.raises(api.GGError):
         g.run_fused_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), 1000, 1000)
+
+
+@pytest.mark.parametrize("dist", [1, 2, 5])
+def test_fused_base_composition(oracle_mod, genomes, tmp_path, dist):
+    """fragSim --comp/--dist (fragSim.cpp:1609-1759): fp64 acceptance product over the fragment ends and their flanks."""
+    from oracle import parsers
+    p = str(tmp_path / "dnacomp.txt")
+    synth.write_dnacomp(p, seed=dist)
+    tabs = [np.array(t) for t in parsers.load_dnacomp(p, dist)]
+    g, o, ids = _pair(oracle_mod, genomes, damage="matrix")
+    for c in (g, o):
+        c.set_composition(1, dist, *tabs)
+    plan = [api.Range(0, 700, ids[0], 0, "e1_0", 1), api.Range(700, 500, ids[1], 0, "b1", -1), api.Range(1200, 600, ids[2], -1, "c1", 1)]
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in (api.EMIT_FRAG, api.EMIT_ARTP):
+        a, ia = g.run_fused(0, 1800, emit); b, ib = o.run_fused(0, 1800, emit)
+        util.assert_same(a, b, "--comp dist=%d emit=%d" % (dist, emit))
+        assert (ia.attempts, ia.gather_bytes) == (ib.attempts, ib.gather_bytes) and ia.attempts > 1.3 * 1800
+    g.clear_composition(1); o.clear_composition(1)
+    util.assert_same(g.run_fused(0, 1800, api.EMIT_FRAG)[0], o.run_fused(0, 1800, api.EMIT_FRAG)[0], "composition cleared")

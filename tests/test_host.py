@@ -221,3 +221,32 @@ def test_bgzf_writer_roundtrip():
             assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 12:p + 14] == b"BC"
             p += (z[p + 16] | (z[p + 17] << 8)) + 1; blocks += 1
         assert p == len(z) and blocks == (len(data) + 65279) // 65280 + 1
+
+
+def _load_dnacomp(path, dist):
+    lib = api.load_library()
+    t = [np.zeros((2 * dist, 4)) for _ in range(4)]
+    err = C.create_string_buffer(512)
+    rc = lib.ggh_load_dnacomp(path.encode(), dist, *[x.ctypes.data_as(C.POINTER(C.c_double)) for x in t], err, 512)
+    if rc:
+        raise ValueError(err.value.decode())
+    return t
+
+
+def test_dnacomp_parser(tmp_path, golden):
+    """fragSim --comp/--dist loader (fragSim.cpp:798-1012) vs the Python restatement and the golden table of src/dnacomp.txt."""
+    p = str(tmp_path / "dnacomp.txt")
+    synth.write_dnacomp(p)
+    for dist in (1, 2, 3):
+        got = _load_dnacomp(p, dist)
+        want = parsers.load_dnacomp(p, dist)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, np.array(b))
+            assert np.allclose(a.sum(1), 1.0, atol=1e-9)            # frequency - background + 0.25 still sums to 1
+    with pytest.raises(ValueError):
+        _load_dnacomp(p, 9)                                         # the file only holds +-8
+    if os.path.exists("/root/reference/src/dnacomp.txt"):
+        got = _load_dnacomp("/root/reference/src/dnacomp.txt", 2)
+        for a, b in zip(got, synth.golden_dnacomp()):
+            assert np.array_equal(a, b)
+    assert len(golden["dnacomp_dist2"]) == 4 and len(golden["dnacomp_dist2"][0]) == 4
