@@ -180,6 +180,12 @@ class Context:
     def set_adapters(self, fwd=DEFAULT_ADAPTER_F, rev=DEFAULT_ADAPTER_S, read_len=100):
         self._ck(self._f("tables_set_adapters")(self._h, fwd.encode(), rev.encode(), C.c_int(read_len)))
 
+    def set_deam_naming(self, on=True):
+        self._ck(self._f("tables_set_deam_naming")(self._h, C.c_int(1 if on else 0)))
+
+    def set_adpt_naming(self, add_in_name=False, tag=""):
+        self._ck(self._f("tables_set_adpt_naming")(self._h, C.c_int(1 if add_in_name else 0), (tag or "").encode()))
+
     def set_plan(self, ranges):
         arr = (_Range * max(len(ranges), 1))()
         for i, r in enumerate(ranges):

@@ -7,12 +7,12 @@ int main(int argc, char** argv) {
     std::string adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
     std::string adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
     int desiredLength = 100; std::string outArt, fwd, rev = "/dev/null"; bool arts = false, artp = false, fa = false;
-    uint64_t seed = time_seed();
+    uint64_t seed = time_seed(); bool addInName = false; std::string tag;
     const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds adapters / trims to the read length (B200 build)\n\n" +
         "\t\t-arts\t[out]\t\tOutput single-end reads as ART (unzipped fasta)\n\t\t-artp\t[out]\t\tOutput reads as ART (unzipped fasta) with wrap-around for paired-end mode\n" +
         "\t\t-fr\t[out fwdr]\tOutput forward read as zipped fasta\n\t\t-rr\t[out rwdr]\tOutput reverse read as zipped fasta\n" +
         "\t-f\t[seq]\t\t\tAdapter that is observed after the forward read\n\t-s\t[seq]\t\t\tAdapter that is observed after the reverse read\n\t-l\t[length]\t\tDesired read length  (Default:  100)\n" +
-        "\tNot in this build: -bs -bp -u -name -tag\n";
+        "\t-name\t\t\t\tAppend _adpt/_rand to deflines if adapters / random bases are added\n\t-tag\t[tag]\t\t\tAppend this string to deflines\n\tNot in this build: -bs -bp -u\n";
     if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // adptSim.cpp:82-90
     for (int i = 1; i < argc - 1; i++) {                                            // adptSim.cpp:92-177
         const std::string a = argv[i];
@@ -24,7 +24,9 @@ int main(int argc, char** argv) {
         if (a == "-fr") { fwd = argv[++i]; fa = true; continue; }
         if (a == "-rr") { rev = argv[++i]; fa = true; continue; }
         if (a == "--seed") { seed = (uint64_t)to_ll(argv[++i], "--seed"); continue; }    // extension: the reference pads from an unseeded rand()
-        if (a == "-bs" || a == "-bp" || a == "-u" || a == "-name" || a == "-tag") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        if (a == "-name") { addInName = true; continue; }                           // adptSim.cpp:163-166
+        if (a == "-tag") { tag = argv[++i]; continue; }                              // adptSim.cpp:168-173
+        if (a == "-bs" || a == "-bp" || a == "-u") return unsupported(a, "SURVEY.md 8f-4");
         return die("Error: unknown option " + a);                                   // adptSim.cpp:175-176
     }
     if (fa && fwd.empty()) return die("Error: need to specify the output forward read ");                  // :179-182
@@ -34,6 +36,7 @@ int main(int argc, char** argv) {
     gg_ctx* ctx = NULL;
     if (open_ctx(seed, &ctx)) return 1;
     if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), desiredLength) != GG_OK) return gg_fail(ctx, "adapters");
+    if (gg_tables_set_adpt_naming(ctx, addInName ? 1 : 0, tag.c_str()) != GG_OK) return gg_fail(ctx, "-tag");
     std::string err; std::vector<uint8_t> recs; uint64_t nrec = 0;
     if (!read_records(infileName, recs, &nrec, err)) return die(err);
     std::vector<Chunk> chunks = chunk_records(recs, 256u << 20);

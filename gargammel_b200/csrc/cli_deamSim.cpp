@@ -5,12 +5,12 @@ using namespace cli;
 
 int main(int argc, char** argv) {
     std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix;
-    bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false;
+    bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false, putDeamInName = false;
     double v = 0, l = 0, d = 0, s = 0; uint64_t seed = 0;
     const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds deamination according to a certain model (B200 build)\n\n" +
         "\t\t-o\t[fasta out]\t\t\tWrite fasta output as a zipped fasta\n\t\t-last\t\t\t\t\tdo not use the last matrix row beyond the matrix\n\t\t--seed\t[int]\n\n" +
         "\t\t-mapdamage  [mis.txt] [protocol]\n\t\t-profile  [prof file prefix]\n\t\t-matfile  [matrix file prefix]\n\t\t-mat      [single|double]\n\t\t-damage     [v,l,d,s]\n" +
-        "\tNot in this build: -b -u -name -damagess -matfilemeth -matfilenonmeth\n";
+        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\tNot in this build: -b -u -damagess -matfilemeth -matfilenonmeth\n";
     if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // deamSim.cpp:199-207
     for (int i = 1; i < argc - 1; i++) {                                            // deamSim.cpp:213-378
         const std::string a = argv[i];
@@ -42,7 +42,8 @@ int main(int argc, char** argv) {
         if (a == "-o") { outGz = argv[++i]; continue; }
         if (a == "-last") { lastRowMatrix = false; continue; }
         if (a == "-v") continue;                                                    // per-read log on stderr: not produced
-        if (a == "-name" || a == "-b" || a == "-u" || a == "-damagess" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        if (a == "-name") { putDeamInName = true; continue; }                        // deamSim.cpp:342-345
+        if (a == "-b" || a == "-u" || a == "-damagess" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
         return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377
     }
     const bool mapd = !mapdamageFile.empty();
@@ -70,6 +71,7 @@ int main(int argc, char** argv) {
         if (!ggh::load_matrix_dat(exe_dir(argv[0]) + "matrices/" + matrix + "-", s5, s3, err)) return die(err);
         if (gg_tables_set_singledouble(ctx, 0, matrix == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mat");
     }
+    gg_tables_set_deam_naming(ctx, putDeamInName ? 1 : 0);
     std::vector<uint8_t> recs; uint64_t nrec = 0;
     if (!read_records(inputFile, recs, &nrec, err)) return die(err);
     Sink out;

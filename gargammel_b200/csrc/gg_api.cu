@@ -95,6 +95,7 @@ struct gg_ctx {
     std::string adF, adS; int read_len;
     DBuf d_adF2, d_adS2, d_rcS2, d_adF, d_adS;
     bool ad_dirty;
+    AdptNaming naming; int deam_name;
     // plan
     std::vector<gg_range> plan; DBuf d_ranges; bool plan_dirty;
     // run state
@@ -307,7 +308,7 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false;
     ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
-    ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true;                  // adptSim.cpp:31
+    ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
     for (int i = 0; i < GG_MAX_COMP_SLOTS; i++) { ctx->comp[i].dist = 0; ctx->comp[i].maxP = ctx->comp[i].maxM = 1.0; }
     cudaDeviceProp prop;
@@ -601,6 +602,17 @@ int gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int re
     return GG_OK;
 }
 
+int gg_tables_set_deam_naming(gg_ctx* ctx, int on) { if (!ctx) return GG_ERR_ARG; ctx->deam_name = on ? 1 : 0; return GG_OK; }
+int gg_tables_set_adpt_naming(gg_ctx* ctx, int add_in_name, const char* tag) {
+    if (!ctx) return GG_ERR_ARG;
+    const size_t n = tag ? strlen(tag) : 0;
+    if (n > sizeof(ctx->naming.tag) - 1) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adpt_naming: -tag longer than 23 characters");
+    memset(&ctx->naming, 0, sizeof ctx->naming);
+    ctx->naming.add_in_name = add_in_name ? 1 : 0; ctx->naming.tag_len = (int)n;
+    if (n) memcpy(ctx->naming.tag, tag, n);
+    return GG_OK;
+}
+
 int gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n) {
     if (!ctx || n < 0 || (n > 0 && !ranges)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_plan_set: bad arguments") : GG_ERR_ARG;
     if (n > 65535) return ctx->fail(GG_ERR_ARG, "gg_plan_set: at most 65535 ranges");
@@ -788,15 +800,34 @@ int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint6
     RecStream R; int launches = 0;
     int rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches);
     if (rc) return rc;
-    const uint64_t out_bytes = n ? (R.n_nl == 2 * R.n_rec ? n : n + 1) : 0;
+    uint64_t out_bytes = n ? (R.n_nl == 2 * R.n_rec ? n : n + 1) : 0;
     DBuf& ob = pick_out(ctx, recs_dev);
-    CK(ob.ensure(out_bytes + 64));
     ggd::DamageDev D; memset(&D, 0, sizeof D);
     const int has = (slot >= 0 && ctx->dmg[slot].mode != GG_DMG_NONE) ? 1 : 0;
     if (has) fill_damage_dev(ctx->dmg[slot], &D);
     ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
-    CK(launch_deam_records(R, ob.as<uint8_t>(), D, has, key, first_id, d_stats, ctx->st));
-    launches += 1;
+    if (ctx->deam_name && has && R.n_rec) {
+        // -name: record sizes depend on the damage -> sizes, scan, write (the draws are counter-based, so both passes agree)
+        const uint64_t nbk = (R.n_rec + 1 + 2047) / 2048;
+        CK(ctx->d_sizes.ensure((size_t)(R.n_rec + 1 + nbk + 16) * 8));
+        unsigned long long* sizes = ctx->d_sizes.as<unsigned long long>();
+        unsigned long long* scratch = sizes + R.n_rec + 1;
+        unsigned long long* total = scratch + nbk + 1;
+        CK(cudaMemsetAsync(sizes + R.n_rec, 0, 8, ctx->st));                        // sentinel so that off[r+1] exists for the last record
+        CK(launch_deam_name_sizes(R, D, key, first_id, sizes, d_stats, ctx->st));
+        CK(launch_exclusive_scan(sizes, R.n_rec + 1, scratch, total, ctx->st));
+        unsigned long long h_total = 0;
+        CK(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        out_bytes = h_total;
+        CK(ob.ensure(out_bytes + 64));
+        CK(launch_deam_name_records(R, sizes, ob.as<uint8_t>(), D, key, first_id, ctx->st));
+        launches += 5;
+    } else {
+        CK(ob.ensure(out_bytes + 64));
+        CK(launch_deam_records(R, ob.as<uint8_t>(), D, has, key, first_id, d_stats, ctx->st));
+        launches += 1;
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long stats[ST_N];
     CK(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));
@@ -829,15 +860,15 @@ int gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint6
         unsigned long long* sizes = ctx->d_sizes.as<unsigned long long>();
         unsigned long long* scratch = sizes + R.n_rec;
         unsigned long long* total = scratch + nb + 1;
-        CK(launch_adpt_sizes(R, emit, ctx->read_len, sizes, d_stats, ctx->st));
+        Adapters ad; memset(&ad, 0, sizeof ad);
+        ad.lenF = (int)ctx->adF.size(); ad.lenS = (int)ctx->adS.size(); ad.read_len = ctx->read_len;
+        CK(launch_adpt_sizes(R, emit, ad, ctx->naming, sizes, d_stats, ctx->st));
         CK(launch_exclusive_scan(sizes, R.n_rec, scratch, total, ctx->st));
         CK(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         CK(ob.ensure(h_total + 64));
-        Adapters ad; memset(&ad, 0, sizeof ad);
-        ad.lenF = (int)ctx->adF.size(); ad.lenS = (int)ctx->adS.size(); ad.read_len = ctx->read_len;
         ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
-        CK(launch_adpt_records(R, sizes, ob.as<uint8_t>(), emit, ad, ctx->d_adF.as<uint8_t>(), ctx->d_adS.as<uint8_t>(), key, first_id, ctx->st));
+        CK(launch_adpt_records(R, sizes, ob.as<uint8_t>(), emit, ad, ctx->d_adF.as<uint8_t>(), ctx->d_adS.as<uint8_t>(), ctx->naming, key, first_id, ctx->st));
         launches += 5;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->st));

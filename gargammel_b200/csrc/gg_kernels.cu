@@ -777,6 +777,111 @@ __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t
         if (lane == 0) out[p.se] = '\n';
     }
 }
+// ---- deamSim -name: "_DEAM:p1,p2,..." appended to the ID of every damaged record (deamSim.cpp:2029-2037).
+// Position lists follow the reference's push order: matrix: i ascending, +(i+1) in the 5' half, -(len-i) in the 3' half
+// (:1857,1919); Briggs: +(i+1) (:1489-1589); single/double: all pass-1 hits +(i+1), then all pass-2 hits -(len-i) (:1949-1994).
+struct DeamEvt { uint32_t nb; int v0, v1; };     // new base; list-0 value (0 = none); list-1 value (0 = none)
+__device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int i, int L, int code) {
+    DeamEvt e; e.nb = (uint32_t)code; e.v0 = 0; e.v1 = 0;
+    const uint32_t b = (uint32_t)code;
+    if (D.mode == 1) {
+        e.nb = dmg_matrix_base(D, i, L, b, rng_word(key, id, ST_DEAM, (uint32_t)i));
+        if (e.nb != b) e.v0 = (i < (L >> 1)) ? i + 1 : -(L - i);
+    } else if (D.mode == 2) {
+        e.nb = dmg_briggs_base(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
+        if (e.nb != b) e.v0 = i + 1;
+    } else {
+        const uint32_t x1 = rng_word(key, id, ST_DEAM, (uint32_t)i), x2 = rng_word(key, id, ST_DEAM2, (uint32_t)i);
+        const int r5 = min(i, D.rows5 - 1), r3 = min(L - 1 - i, D.rows3 - 1);
+        uint32_t c = b;
+        if (c == 1u && (x1 >> 1) < __ldg(D.sd5 + r5)) { c = 3u; e.v0 = i + 1; }
+        if (D.mode == 3) { if (c == 1u && (x2 >> 1) < __ldg(D.sd3 + r3)) { c = 3u; e.v1 = -(L - i); } }
+        else             { if (c == 2u && (x2 >> 1) < __ldg(D.sd3 + r3)) { c = 0u; e.v1 = -(L - i); } }
+        e.nb = c;
+    }
+    return e;
+}
+__device__ __forceinline__ int evt_text_len(int v) { return v == 0 ? 0 : 1 + (v < 0 ? 1 : 0) + ndigits((uint64_t)(v < 0 ? -v : v)); }   // separator + sign + digits
+
+// pass 1: output bytes per record
+__global__ void __launch_bounds__(256) k_deam_name_sizes(const RecStream R, const DamageDev D, Key key, uint64_t first_id,
+                                                         unsigned long long* __restrict__ sizes, unsigned long long* stats) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < R.n_rec; r += nw) {
+        const RecPos p = rec_pos(R, r);
+        const uint64_t id = first_id + r;
+        if (lane == 0 && (p.ide <= p.ids || R.in[p.ids] != '>')) atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
+        const int L = (int)(p.se - p.ss);
+        BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+        if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        unsigned long long txt = 0;
+        for (int i = lane; i < L; i += 32) {
+            const int code = ascii2code(upper(R.in[p.ss + i]));
+            if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code); txt += (unsigned long long)(evt_text_len(e.v0) + evt_text_len(e.v1)); }
+        }
+        txt = warp_sum_u64(txt);
+        if (lane == 0) sizes[r] = (p.ide - p.ids) + (txt ? 5ull + txt : 0ull) + 1ull + (unsigned long long)L + 1ull;
+    }
+}
+// pass 2: write "ID[_DEAM:list]\nSEQ\n"
+__global__ void __launch_bounds__(256) k_deam_name_records(const RecStream R, const unsigned long long* __restrict__ out_off, uint8_t* __restrict__ out,
+                                                           const DamageDev D, Key key, uint64_t first_id) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < R.n_rec; r += nw) {
+        const RecPos p = rec_pos(R, r);
+        const uint64_t id = first_id + r;
+        const int L = (int)(p.se - p.ss);
+        const uint64_t idlen = p.ide - p.ids;
+        uint8_t* o = out + out_off[r];
+        for (uint64_t i = lane; i < idlen; i += 32) o[i] = R.in[p.ids + i];
+        BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+        if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        const uint64_t total = out_off[r + 1] - out_off[r];                       // sizes array has a sentinel entry
+        uint8_t* seqo = o + (total - (uint64_t)L - 1);                            // sequence start
+        const bool any = total > idlen + 1 + (uint64_t)L + 1;
+        if (any && lane < 5) o[idlen + lane] = (uint8_t)"_DEAM"[lane];
+        uint32_t cur = (uint32_t)idlen + 5;                                        // next text offset within the record
+        for (int list = 0; list < 2; list++) {
+            if (list == 1 && D.mode != 3 && D.mode != 4) break;
+            for (int i0 = 0; i0 < L; i0 += 32) {
+                const int i = i0 + lane;
+                int v = 0; uint32_t nb = 0; int code = -1; uint8_t ch = 0;
+                if (i < L) {
+                    ch = upper(R.in[p.ss + i]); code = ascii2code(ch);
+                    if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code); v = list == 0 ? e.v0 : e.v1; nb = e.nb; }
+                    if (list == 0) seqo[i] = code >= 0 ? code2ascii(nb) : ch;   // sequence bytes written once
+                }
+                const int len = evt_text_len(v);
+                int inc = len;
+                for (int s2 = 1; s2 < 32; s2 <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, s2); if (lane >= s2) inc += t; }
+                const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                if (len) {
+                    uint8_t* q = o + cur + (uint32_t)(inc - len);
+                    *q++ = (cur + (uint32_t)(inc - len) == (uint32_t)idlen + 5) ? ':' : ',';   // first event overall follows "_DEAM"
+                    if (v < 0) *q++ = '-';
+                    uint32_t a = (uint32_t)(v < 0 ? -v : v); const int nd = ndigits((uint64_t)a);
+                    for (int k = nd - 1; k >= 0; k--) { q[k] = (uint8_t)('0' + a % 10u); a /= 10u; }
+                }
+                cur += (uint32_t)tot;
+            }
+        }
+        if (lane == 0) { seqo[-1] = '\n'; seqo[L] = '\n'; }
+    }
+}
+cudaError_t launch_deam_name_sizes(const RecStream& R, const DamageDev& D, Key key, uint64_t first_id, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st) {
+    if (R.n_rec == 0) return cudaSuccess;
+    const uint64_t want = (R.n_rec + 7) / 8;
+    k_deam_name_sizes<<<(unsigned)(want < 148ull * 16 ? want : 148ull * 16), 256, 0, st>>>(R, D, key, first_id, sizes, stats);
+    return cudaGetLastError();
+}
+cudaError_t launch_deam_name_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, const DamageDev& D, Key key, uint64_t first_id, cudaStream_t st) {
+    if (R.n_rec == 0) return cudaSuccess;
+    const uint64_t want = (R.n_rec + 7) / 8;
+    k_deam_name_records<<<(unsigned)(want < 148ull * 16 ? want : 148ull * 16), 256, 0, st>>>(R, out_off, out, D, key, first_id);
+    return cudaGetLastError();
+}
 cudaError_t launch_deam_records(const RecStream& R, uint8_t* out, const DamageDev& D, int has_damage, Key key,
                                 uint64_t first_id, unsigned long long* stats, cudaStream_t st) {
     if (R.n_rec == 0) return cudaSuccess;
@@ -786,6 +891,13 @@ cudaError_t launch_deam_records(const RecStream& R, uint8_t* out, const DamageDe
     return cudaGetLastError();
 }
 
+// "_adpt" if the forward read got adapter bases, "_rand" if it also got random bases (flags come from the forward read
+// only, adptSim.cpp:294-310,378-386), then the -tag string
+__device__ __forceinline__ int adpt_name_extra(const AdptNaming& nm, const Adapters& ad, int L) {
+    int x = nm.tag_len;
+    if (nm.add_in_name) { if (L < ad.read_len) x += 5; if (L + ad.lenF < ad.read_len) x += 5; }
+    return x;
+}
 __device__ __forceinline__ uint64_t adpt_rec_bytes(int emit, uint64_t idlen, int RL) {
     switch (emit) {
         case 2: return (idlen + 1 + RL + 1) + (idlen + 2 + 1 + RL + 1);     // STDOUT4
@@ -795,23 +907,23 @@ __device__ __forceinline__ uint64_t adpt_rec_bytes(int emit, uint64_t idlen, int
         default: return 0;
     }
 }
-__global__ void __launch_bounds__(256) k_adpt_sizes(const RecStream R, int emit, int RL, unsigned long long* __restrict__ sizes, unsigned long long* stats) {
+__global__ void __launch_bounds__(256) k_adpt_sizes(const RecStream R, int emit, Adapters ad, AdptNaming nm, unsigned long long* __restrict__ sizes, unsigned long long* stats) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R.n_rec) return;
     const RecPos p = rec_pos(R, r);
     if (p.ide <= p.ids || R.in[p.ids] != '>') atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
-    sizes[r] = adpt_rec_bytes(emit, p.ide - p.ids, RL);
+    sizes[r] = adpt_rec_bytes(emit, (p.ide - p.ids) + (uint64_t)adpt_name_extra(nm, ad, (int)(p.se - p.ss)), ad.read_len);
 }
-cudaError_t launch_adpt_sizes(const RecStream& R, int emit, int read_len, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st) {
+cudaError_t launch_adpt_sizes(const RecStream& R, int emit, Adapters ad, AdptNaming nm, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st) {
     if (R.n_rec == 0) return cudaSuccess;
-    k_adpt_sizes<<<(unsigned)((R.n_rec + 255) / 256), 256, 0, st>>>(R, emit, read_len, sizes, stats);
+    k_adpt_sizes<<<(unsigned)((R.n_rec + 255) / 256), 256, 0, st>>>(R, emit, ad, nm, sizes, stats);
     return cudaGetLastError();
 }
 
 // stand-alone adptSim main loop (adptSim.cpp:263-420): warp per record, ASCII in/out
 __global__ void __launch_bounds__(256) k_adpt_records(const RecStream R, const unsigned long long* __restrict__ out_off, uint8_t* __restrict__ out,
                                                       int emit, Adapters ad, const uint8_t* __restrict__ adF, const uint8_t* __restrict__ adS,
-                                                      Key key, uint64_t first_id) {
+                                                      AdptNaming nm, Key key, uint64_t first_id) {
     const int lane = threadIdx.x & 31;
     const int RL = ad.read_len;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -828,6 +940,10 @@ __global__ void __launch_bounds__(256) k_adpt_records(const RecStream R, const u
             for (uint64_t i = lane; i < idlen; i += 32) o[i] = R.in[p.ids + i];
             o += idlen;
             if (second) { if (lane == 0) { o[0] = '_'; o[1] = 'r'; } o += 2; }       // namer = namef + "_r", adptSim.cpp:286
+            if (nm.add_in_name && L < RL) { if (lane < 5) o[lane] = (uint8_t)"_adpt"[lane]; o += 5; }                    // adptSim.cpp:378-379,383-384
+            if (nm.add_in_name && L + ad.lenF < RL) { if (lane < 5) o[lane] = (uint8_t)"_rand"[lane]; o += 5; }          // adptSim.cpp:380-381,385-386
+            if (lane < nm.tag_len) o[lane] = (uint8_t)nm.tag[lane];                                                      // adptSim.cpp:389-392
+            o += nm.tag_len;
             if (lane == 0) o[0] = '\n';
             o += 1;
             const int S = emit == 4 ? 2 * RL : RL;
@@ -859,11 +975,11 @@ __global__ void __launch_bounds__(256) k_adpt_records(const RecStream R, const u
     }
 }
 cudaError_t launch_adpt_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, int emit, Adapters ad,
-                                const uint8_t* adF, const uint8_t* adS, Key key, uint64_t first_id, cudaStream_t st) {
+                                const uint8_t* adF, const uint8_t* adS, AdptNaming nm, Key key, uint64_t first_id, cudaStream_t st) {
     if (R.n_rec == 0) return cudaSuccess;
     const uint64_t want = (R.n_rec + 7) / 8;
     const unsigned grid = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
-    k_adpt_records<<<grid, 256, 0, st>>>(R, out_off, out, emit, ad, adF, adS, key, first_id);
+    k_adpt_records<<<grid, 256, 0, st>>>(R, out_off, out, emit, ad, adF, adS, nm, key, first_id);
     return cudaGetLastError();
 }
 

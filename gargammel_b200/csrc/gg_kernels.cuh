@@ -31,6 +31,9 @@ struct CompDev {             // fragSim --comp tables of one slot (fp64: the acc
     const double* tab;       // [4 tables: 5p+,5p-,3p+,3p-][2*dist][4]
     double maxP, maxM;       // fragSim.cpp:1030-1047
 };
+struct AdptNaming {           // adptSim -name / -tag (adptSim.cpp:375-393)
+    int add_in_name, tag_len; char tag[24];
+};
 struct Adapters {
     const uint32_t* adF2;    // forward adapter, 2-bit packed (+slack)
     const uint32_t* adS2;    // second adapter
@@ -104,9 +107,11 @@ cudaError_t launch_fill_newlines(const uint8_t* in, uint64_t n, const unsigned l
 cudaError_t launch_exclusive_scan(unsigned long long* data, uint64_t n, unsigned long long* scratch, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_deam_records(const RecStream& R, uint8_t* out, const ggd::DamageDev& D, int has_damage, ggd::Key key,
                                 uint64_t first_id, unsigned long long* stats, cudaStream_t st);
-cudaError_t launch_adpt_sizes(const RecStream& R, int emit, int read_len, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_deam_name_sizes(const RecStream& R, const ggd::DamageDev& D, ggd::Key key, uint64_t first_id, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
+cudaError_t launch_deam_name_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, const ggd::DamageDev& D, ggd::Key key, uint64_t first_id, cudaStream_t st);
+cudaError_t launch_adpt_sizes(const RecStream& R, int emit, Adapters ad, AdptNaming nm, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
 cudaError_t launch_adpt_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, int emit, Adapters ad,
-                                const uint8_t* adF, const uint8_t* adS, ggd::Key key, uint64_t first_id, cudaStream_t st);
+                                const uint8_t* adF, const uint8_t* adS, AdptNaming nm, ggd::Key key, uint64_t first_id, cudaStream_t st);
 cudaError_t launch_l2_flush(uint4* buf, uint64_t n16, cudaStream_t st);
 constexpr int NL_BLOCK_BYTES = 1 << 16;
 

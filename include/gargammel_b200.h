@@ -151,8 +151,12 @@ int  gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const doubl
 /* deamSim -damage v,l,d,s (deamSim.cpp:285-306,1477-1613) */
 int  gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, double s);
 int  gg_tables_clear_damage(gg_ctx* ctx, int slot);
+/* deamSim -name (deamSim.cpp:342-345,2029-2037): append "_DEAM:p1,p2,..." to the ID of damaged records; stand-alone deamSim stage only */
+int  gg_tables_set_deam_naming(gg_ctx* ctx, int put_deam_in_name);
 /* adptSim -f -s -l (adptSim.cpp:28-31,131-147) */
 int  gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int read_len);
+/* adptSim -name / -tag (adptSim.cpp:163-173,375-393), stand-alone adptSim stage only; tag may be NULL */
+int  gg_tables_set_adpt_naming(gg_ctx* ctx, int add_in_name, const char* tag);
 
 /* ---- plan: which fragment id comes from which genome with which tag/damage ---- */
 int  gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n);

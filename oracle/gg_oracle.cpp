@@ -97,13 +97,14 @@ struct orc_ctx {
     std::vector<int32_t> size_len; std::vector<double> size_cum;
     Damage dmg[GG_MAX_DAMAGE_SLOTS];
     std::string adF, adS; int read_len;
+    int add_in_name; std::string adpt_tag; int deam_name;
     std::vector<gg_range> plan;
     std::string err;
     uint64_t attempts, gather_bytes;
     orc_ctx() : size_mode(GG_SIZE_FIXED), fixed_len(20), minlen(0), maxlen(1000), norev(0),
         adF("AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"),   /* adptSim.cpp:28 */
         adS("AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"),         /* adptSim.cpp:29 */
-        read_len(100), attempts(0), gather_bytes(0) {}
+        read_len(100), add_in_name(0), deam_name(0), attempts(0), gather_bytes(0) {}
 };
 
 /* ------------------------------------------------------------------ fragSim */
@@ -217,7 +218,7 @@ static int geomDraw(const std::vector<double>& cdf, uint32_t x) {
 #define GEOM_TABLE 4096
 
 /* -matfile loop, deamSim.cpp:1794-1930 */
-static void deamMatrix(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+static void deamMatrix(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
     int n5 = (int)(D.sub5.size() / 12), n3 = (int)(D.sub3.size() / 12);
     int len = (int)seq.size();
     for (int i = 0; i < len; i++) {
@@ -247,14 +248,18 @@ static void deamMatrix(const orc_ctx* c, const Damage& D, uint64_t id, std::stri
         for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }   /* :1833-1837 */
         double p = u01(c->rng.word(id, ST_DEAM, (uint32_t)i));      /* :1847 one uniform per resolved base */
         for (int a = 0; a < 4; a++) {                               /* :1849-1863 */
-            if (sumProb[a] <= p && sumProb[a + 1] >= p) { seq[i] = "ACGT"[a]; break; }
+            if (sumProb[a] <= p && sumProb[a + 1] >= p) {
+                seq[i] = "ACGT"[a];
+                if (a != b && deamPos) deamPos->push_back(i < len / 2 ? i + 1 : -(len - i));          /* :1856-1859, :1918-1921 */
+                break;
+            }
         }
     }
 }
 
 /* -damage v,l,d,s loop, deamSim.cpp:1477-1613.  Draw layout: DEAM words 0,1,2 = 5' overhang, 3' overhang,
  * nick position (geometric: first success of the per-base Bernoulli(v) scan :1503-1507); per-base word 4+i. */
-static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
     int len = (int)seq.size();
     std::vector<double> cdfL = geomCdf(D.l, GEOM_TABLE), cdfV = geomCdf(D.v, GEOM_TABLE);
     uint32_t h[4]; c->rng.block(id, 0, ST_DEAM, h);
@@ -262,7 +267,7 @@ static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::stri
     int overhang3p = geomDraw(cdfL, h[1]);                          /* :1479 */
     if (overhang5p + overhang3p >= len) {                           /* :1483 all single strand */
         for (int i = 0; i < len; i++)
-            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i)) < D.s) seq[i] = 'T';   /* :1486-1494 */
+            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i)) < D.s) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }   /* :1486-1494 */
         return;
     }
     int indexNick = geomDraw(cdfV, h[2]);                           /* first i with randomProb()<v, :1503-1507 */
@@ -270,46 +275,46 @@ static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::stri
         bool placedNick = (indexNick <= i);                         /* nick applies from its own position on (:1510) */
         double p = u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i));
         if ((i + 1) <= overhang5p) {                                /* :1513 / :1557 */
-            if (seq[i] == 'C' && p < D.s) seq[i] = 'T';
+            if (seq[i] == 'C' && p < D.s) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
         } else if ((len - i) <= overhang3p) {                       /* :1527 / :1571 */
-            if (seq[i] == 'G' && p < D.s) seq[i] = 'A';
+            if (seq[i] == 'G' && p < D.s) { seq[i] = 'A'; if (deamPos) deamPos->push_back(i + 1); }
         } else if (placedNick) {                                    /* :1542 */
-            if (seq[i] == 'G' && p < D.d) seq[i] = 'A';
+            if (seq[i] == 'G' && p < D.d) { seq[i] = 'A'; if (deamPos) deamPos->push_back(i + 1); }
         } else {                                                    /* :1586 */
-            if (seq[i] == 'C' && p < D.d) seq[i] = 'T';
+            if (seq[i] == 'C' && p < D.d) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
         }
     }
 }
 
 /* -mat single|double / -mapdamage loops, deamSim.cpp:1941-2002.  Row index clamped to the last row
  * (the reference indexes out of bounds for len > rows: DESIGN.md deviation). */
-static void deamSingleDouble(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq) {
+static void deamSingleDouble(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
     int n5 = (int)(D.sub5.size() / 12), n3 = (int)(D.sub3.size() / 12);
     int len = (int)seq.size();
     for (int i = 0; i < len; i++) {                                 /* :1944-1954 / :1976-1986 */
         if (seq[i] == 'C') {
             int r = std::min(i, n5 - 1);
-            if (u01(c->rng.word(id, ST_DEAM, (uint32_t)i)) < D.sub5[(size_t)r * 12 + 5]) seq[i] = 'T';
+            if (u01(c->rng.word(id, ST_DEAM, (uint32_t)i)) < D.sub5[(size_t)r * 12 + 5]) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
         }
     }
     for (int i = 0; i < len; i++) {
         int r = std::min(len - i - 1, n3 - 1);
         if (D.mode == GG_DMG_SINGLE) {                              /* :1957-1967 */
-            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 5]) seq[i] = 'T';
+            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 5]) { seq[i] = 'T'; if (deamPos) deamPos->push_back(-(len - i)); }
         } else {                                                    /* :1989-2000 */
-            if (seq[i] == 'G' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 6]) seq[i] = 'A';
+            if (seq[i] == 'G' && u01(c->rng.word(id, ST_DEAM2, (uint32_t)i)) < D.sub3[(size_t)r * 12 + 6]) { seq[i] = 'A'; if (deamPos) deamPos->push_back(-(len - i)); }
         }
     }
 }
 
-static void deaminate(const orc_ctx* c, int slot, uint64_t id, std::string& seq) {
+static void deaminate(const orc_ctx* c, int slot, uint64_t id, std::string& seq, std::vector<int>* deamPos = NULL) {
     for (size_t i = 0; i < seq.size(); i++) seq[i] = (char)toupper(seq[i]);   /* deamSim.cpp:1319-1321 */
     if (slot < 0) return;
     const Damage& D = c->dmg[slot];
     switch (D.mode) {
-        case GG_DMG_MATRIX: deamMatrix(c, D, id, seq); break;
-        case GG_DMG_BRIGGS: deamBriggs(c, D, id, seq); break;
-        case GG_DMG_SINGLE: case GG_DMG_DOUBLE: deamSingleDouble(c, D, id, seq); break;
+        case GG_DMG_MATRIX: deamMatrix(c, D, id, seq, deamPos); break;
+        case GG_DMG_BRIGGS: deamBriggs(c, D, id, seq, deamPos); break;
+        case GG_DMG_SINGLE: case GG_DMG_DOUBLE: deamSingleDouble(c, D, id, seq, deamPos); break;
         default: break;
     }
 }
@@ -325,21 +330,23 @@ static std::string randomDNASeq(const orc_ctx* c, uint64_t id, uint32_t stream, 
     return s;
 }
 /* adptSim.cpp:288-322 */
-static void adaptReads(const orc_ctx* c, uint64_t id, const std::string& seq_in, std::string& seqf, std::string& seqr) {
+static void adaptReads(const orc_ctx* c, uint64_t id, const std::string& seq_in, std::string& seqf, std::string& seqr, bool* addedAdapter = NULL, bool* addedRandom = NULL) {
     seqf = seq_in;
     for (size_t i = 0; i < seqf.size(); i++) seqf[i] = (char)toupper(seqf[i]);       /* :288 */
     seqr = reverseComplement(seqf);                                                   /* :289 */
     int L = c->read_len;
-    if ((int)seqf.size() < L) { seqf = seqf + c->adF; seqf = seqf.substr(0, L); }      /* :298-301 */
+    if (addedAdapter) *addedAdapter = false;
+    if (addedRandom) *addedRandom = false;
+    if ((int)seqf.size() < L) { seqf = seqf + c->adF; seqf = seqf.substr(0, L); if (addedAdapter) *addedAdapter = true; }      /* :298-301 */
     else seqf = seqf.substr(0, L);                                                    /* :303 */
-    if ((int)seqf.size() < L) seqf = seqf + randomDNASeq(c, id, ST_ADPT_F, L - (int)seqf.size());   /* :307-310 */
+    if ((int)seqf.size() < L) { seqf = seqf + randomDNASeq(c, id, ST_ADPT_F, L - (int)seqf.size()); if (addedRandom) *addedRandom = true; }   /* :307-310 */
     if ((int)seqr.size() < L) { seqr = seqr + c->adS; seqr = seqr.substr(0, L); }      /* :313-315 */
     else seqr = seqr.substr(0, L);                                                    /* :317 */
     if ((int)seqr.size() < L) seqr = seqr + randomDNASeq(c, id, ST_ADPT_R, L - (int)seqr.size());   /* :320-322 */
 }
 /* adptSim.cpp:396-411 */
-static void emitAdpt(int emit, const std::string& namef, const std::string& seqf, const std::string& seqr, std::string& out) {
-    std::string namer = namef + "_r";                                                 /* :286 */
+static void emitAdpt(int emit, const std::string& name_in, const std::string& seqf, const std::string& seqr, std::string& out, const std::string& suffix = "") {
+    std::string namef = name_in + suffix, namer = name_in + "_r" + suffix;             /* :286, :375-393 */
     switch (emit) {
         case GG_EMIT_STDOUT4: out += namef + "\n" + seqf + "\n" + namer + "\n" + seqr + "\n"; break;   /* :408 */
         case GG_EMIT_ARTS: case GG_EMIT_FR: out += namef + "\n" + seqf + "\n"; break;                  /* :402 / :397 */
@@ -436,6 +443,8 @@ int orc_tables_clear_damage(orc_ctx* c, int slot) {
 int orc_tables_set_adapters(orc_ctx* c, const char* fwd, const char* rev, int read_len) {
     c->adF = fwd; c->adS = rev; c->read_len = read_len; return 0;
 }
+int orc_tables_set_deam_naming(orc_ctx* c, int on) { c->deam_name = on; return 0; }
+int orc_tables_set_adpt_naming(orc_ctx* c, int add_in_name, const char* tag) { c->add_in_name = add_in_name; c->adpt_tag = tag ? tag : ""; return 0; }
 int orc_plan_set(orc_ctx* c, const gg_range* r, int n) { c->plan.assign(r, r + n); return 0; }
 
 /* fused: for each id: fragSim record -> deamSim -> adptSim, i.e. the literal composition of the three loops */
@@ -493,8 +502,14 @@ int orc_run_deam(orc_ctx* c, const uint8_t* in, size_t n, int slot, uint64_t fir
     std::string out;
     for (size_t r = 0; r < recs.size(); r++) {
         std::string seq = recs[r].second;
-        deaminate(c, slot, first_id + r, seq);
-        out += recs[r].first + "\n" + seq + "\n";                                     /* deamSim.cpp:2038 */
+        std::vector<int> deamPos;
+        deaminate(c, slot, first_id + r, seq, &deamPos);
+        std::string idl = recs[r].first;
+        if (c->deam_name && !deamPos.empty()) {                                       /* deamSim.cpp:2035-2036: ID + "_DEAM:" + vectorToString(deamPos) */
+            idl += "_DEAM:";
+            for (size_t k = 0; k < deamPos.size(); k++) { if (k) idl += ","; char b[16]; snprintf(b, sizeof b, "%d", deamPos[k]); idl += b; }
+        }
+        out += idl + "\n" + seq + "\n";                                              /* deamSim.cpp:2038 */
     }
     if (info) { memset(info, 0, sizeof *info); info->bytes = out.size(); info->records = recs.size(); info->in_bytes = n; }
     *n_out = out.size();
@@ -508,9 +523,12 @@ int orc_run_adpt(orc_ctx* c, const uint8_t* in, size_t n, int emit, uint64_t fir
     int rc = splitRecords(c, in, n, recs); if (rc) return rc;
     std::string out;
     for (size_t r = 0; r < recs.size(); r++) {
-        std::string seqf, seqr;
-        adaptReads(c, first_id + r, recs[r].second, seqf, seqr);
-        emitAdpt(emit, recs[r].first, seqf, seqr, out);
+        std::string seqf, seqr; bool aA, aR;
+        adaptReads(c, first_id + r, recs[r].second, seqf, seqr, &aA, &aR);
+        std::string suffix;                                                           /* adptSim.cpp:375-393 */
+        if (c->add_in_name) { if (aA) suffix += "_adpt"; if (aR) suffix += "_rand"; }
+        suffix += c->adpt_tag;
+        emitAdpt(emit, recs[r].first, seqf, seqr, out, suffix);
     }
     if (info) { memset(info, 0, sizeof *info); info->bytes = out.size(); info->records = recs.size(); info->in_bytes = n; }
     *n_out = out.size();

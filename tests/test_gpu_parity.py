@@ -259,3 +259,40 @@ def test_fused_base_composition(oracle_mod, genomes, tmp_path, dist):
         assert (ia.attempts, ia.gather_bytes) == (ib.attempts, ib.gather_bytes) and ia.attempts > 1.3 * 1800
     g.clear_composition(1); o.clear_composition(1)
     util.assert_same(g.run_fused(0, 1800, api.EMIT_FRAG)[0], o.run_fused(0, 1800, api.EMIT_FRAG)[0], "composition cleared")
+
+
+def test_adpt_name_and_tag(oracle_mod):
+    """adptSim -name (_adpt/_rand flags from the forward read) and -tag (adptSim.cpp:375-393), all dialects."""
+    g = api.Context(0, 3); o = oracle_mod.OracleContext(3)
+    rng = np.random.default_rng(8)
+    recs = b"".join(b">f%d:+:1:2:3\n%s\n" % (i, synth._BASES[rng.integers(0, 4, int(rng.integers(1, 70)))].tobytes()) for i in range(400))
+    for c in (g, o):
+        c.set_adapters("ACGTACGTACGTAC", "TTGCA", 40)           # L < 26: adapter + random; 26 <= L < 40: adapter only; else neither
+    for name, tag in ((True, ""), (False, "XY"), (True, "_lib7")):
+        g.set_adpt_naming(name, tag); o.set_adpt_naming(name, tag)
+        for emit in ALL_EMITS[2:]:
+            a = g.run_adpt(recs, emit)[0]; b = o.run_adpt(recs, emit)[0]
+            util.assert_same(a, b, "adpt naming %r %r emit=%d" % (name, tag, emit))
+    out = g.run_adpt(b">x\nACGT\n>y\n" + b"A" * 30 + b"\n>z\n" + b"C" * 50 + b"\n", api.EMIT_STDOUT4)[0].split(b"\n")
+    assert out[0] == b">x_adpt_rand_lib7" and out[2] == b">x_r_adpt_rand_lib7" and out[4] == b">y_adpt_lib7" and out[8] == b">z_lib7"
+
+
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double"])
+def test_deam_name_tags(oracle_mod, damage):
+    """deamSim -name: "_DEAM:" + positions in the reference's push order (deamSim.cpp:1857,1919,1949-1994,2035)."""
+    g = api.Context(0, 31); o = oracle_mod.OracleContext(31)
+    rng = np.random.default_rng(9)
+    recs = b"".join(b">f%d:-:10:20:%d\n%s\n" % (i, i, synth._BASES[rng.integers(0, 4, int(rng.integers(1, 260)))].tobytes()) for i in range(600))
+    recs += b">allN\nNNNNNNNN\n>one\nC\n"
+    for c in (g, o):
+        util.set_damage(c, 0, damage); c.set_deam_naming(True)
+    a, info = g.run_deam(recs, 0, 5)
+    b, _ = o.run_deam(recs, 0, 5)
+    util.assert_same(a, b, "deamSim -name " + damage)
+    tagged = [h for h, _ in util.records(a) if b"_DEAM:" in h]
+    assert len(tagged) > 100 and info.records == 602
+    if damage in ("single", "double"):
+        assert any(b",-" in h and h.split(b"_DEAM:")[1].split(b",")[0][:1] != b"-" for h in tagged)      # pass-1 hits listed before pass-2 hits
+    for c in (g, o):
+        c.set_deam_naming(False)
+    util.assert_same(g.run_deam(recs, 0, 5)[0], o.run_deam(recs, 0, 5)[0], "naming off")
