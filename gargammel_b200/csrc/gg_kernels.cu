@@ -249,7 +249,7 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
                 const uint32_t r = (i < half) ? (uint32_t)min(i, R5) : r3base + min((uint32_t)(fl - 1 - i), R3);
                 const uint4 Tq = DMODE == 1 ? thr[r * 4u + b] : __ldg(thr + (r * 4u + b));
                 const uint32_t u = pick(x, jj) >> 1;
-                nb += ((uint32_t)(u >= Tq.x) + (uint32_t)(u >= Tq.y) + (uint32_t)(u >= Tq.z)) << (2 * jj);
+                nb += (u >= Tq.z ? 3u : u >= Tq.y ? 2u : u >= Tq.x ? 1u : 0u) << (2 * jj);      // thresholds ascend: number of them <= u
             }
             Wn |= nb << (8 * q);
         }
