@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <iostream>
+#include <unordered_map>
 #include "gg_host.h"
 
 namespace cli {
@@ -138,6 +139,32 @@ inline std::vector<Chunk> chunk_records(const std::vector<uint8_t>& s, size_t ma
     if (p > start) { Chunk c = {start, p - start, recs}; out.push_back(c); }
     return out;
 }
+
+// fragSim -uniq (fragSim.cpp:119-135,1579-1584): every defline gets "_<k>" where k counts how often that exact defline has
+// been produced so far, then "_<tag>" if a tag was given.  Like the reference this is a host-side map over all deflines
+// ("note: this might not be practical for large datasets", fragSim.cpp:429-430); it runs over the byte stream the GPU wrote
+// (2-line records whose deflines carry no tag).
+struct UniqSuffixer {
+    std::unordered_map<std::string, unsigned int> seen; std::string tag; bool tagb;
+    UniqSuffixer() : tagb(false) {}
+    void reset(const std::string& t, bool has_tag) { seen.clear(); tag = t; tagb = has_tag; }
+    // rewrites `in` (whole records) into out; header lines are those at even line index
+    void apply(const char* in, size_t n, std::string& out) {
+        size_t p = 0; bool hdr = true;
+        while (p < n) {
+            const char* e = (const char*)memchr(in + p, '\n', n - p);
+            const size_t le = e ? (size_t)(e - in) : n;
+            if (hdr) {
+                std::string key(in + p + 1, le - p - 1);                 // defline without '>'
+                unsigned int& c = seen[key]; c++;
+                out.append(in + p, le - p); out += '_'; out += std::to_string(c);
+                if (tagb) { out += '_'; out += tag; }
+                out += '\n';
+            } else { out.append(in + p, le - p); out += '\n'; }
+            hdr = !hdr; p = le + 1;
+        }
+    }
+};
 
 inline int gg_fail(gg_ctx* ctx, const char* what) {
     std::cerr << "Error: " << what << ": " << gg_last_error(ctx) << std::endl; return 1;

@@ -7,6 +7,7 @@ int main(int argc, char** argv) {
     int sizeFragments = 20; uint64_t nFragments = 10; int minLen = 0, maxLen = 1000;
     bool noRev = false, seedSpecified = false, specifiedLength = false, specifiedLoc = false, specifiedScale = false; uint64_t seed = 0;
     double location = -1, scale = -1;
+    bool uniqTags = false, tagb = false;
     std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
@@ -19,7 +20,8 @@ int main(int argc, char** argv) {
         "\t\t-f\t[file]\t\t\t\tOpen file with size frequency: length[TAB]freq\n" +
         "\t\t--loc\t[float] --scale\t[float]\tlog-normal fragment lengths\n" +
         "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
-        "\tNot in this build: -gc --circ --case --fq --trim5p -uniq -b -u\n";
+        "\t\t-uniq\t\t\t\t\tMake the fragment names unique by appending a counter (host-side pass, like the reference)\n" +
+        "\tNot in this build: -gc --circ --case --fq --trim5p -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -32,7 +34,8 @@ int main(int argc, char** argv) {
         if (a == "--norev") { noRev = true; continue; }
         if (a == "--seed") { seed = (uint64_t)to_ll(argv[++i], "--seed"); seedSpecified = true; continue; }
         if (a == "-o") { outGz = argv[++i]; continue; }
-        if (a == "-tag") { tag = argv[++i]; continue; }
+        if (a == "-tag") { tag = argv[++i]; tagb = true; continue; }
+        if (a == "-uniq") { uniqTags = true; continue; }                              // fragSim.cpp:481-484
         if (a == "-tmp") { ++i; continue; }                                         // gz inputs are inflated in memory
         if (a == "--loc") { location = to_d(argv[++i], "--loc"); specifiedLoc = true; continue; }
         if (a == "--scale") { scale = to_d(argv[++i], "--scale"); specifiedScale = true; continue; }
@@ -40,7 +43,7 @@ int main(int argc, char** argv) {
         if (a == "--dist") { distFromEnd = (int)to_ll(argv[++i], "--dist"); continue; }
         if (a == "-gc" || a == "--circ" || a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
-        if (a == "--case" || a == "--fq" || a == "-uniq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
+        if (a == "--case" || a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
     }
     if (specifiedLength && sizeFragments > maxLen)                                   // fragSim.cpp:638-643
@@ -84,21 +87,22 @@ int main(int argc, char** argv) {
     }
     if (nFragments) {
         gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1; r.comp_slot = compFile.empty() ? -1 : 0;
-        snprintf(r.tag, sizeof r.tag, "%s", tag.c_str());
+        snprintf(r.tag, sizeof r.tag, "%s", uniqTags ? "" : tag.c_str());        // with -uniq the tag goes after the count (fragSim.cpp:1505,131-133)
         if (gg_plan_set(ctx, &r, 1) != GG_OK) return gg_fail(ctx, "plan");
     }
     Sink out;
     if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); }       // fragSim.cpp:1297-1303
     else out.open_stdout();
     const uint64_t chunk = 4u << 20;
-    std::vector<uint8_t> host;
+    std::vector<uint8_t> host; UniqSuffixer uniq; uniq.reset(tag, tagb); std::string renamed;
     for (uint64_t first = 0; first < nFragments; first += chunk) {
         const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
         gg_out o;
         if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
         host.resize(o.bytes); size_t n = 0;
         if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
-        if (!out.write(host.data(), n)) return die("Error: write failed");
+        if (uniqTags) { renamed.clear(); uniq.apply((const char*)host.data(), n, renamed); if (!out.write(renamed.data(), renamed.size())) return die("Error: write failed"); }
+        else if (!out.write(host.data(), n)) return die("Error: write failed");
     }
     if (!out.close()) return die("Error: write failed");
     gg_ctx_destroy(ctx);

@@ -48,6 +48,7 @@ int main(int argc, char** argv) {
     double compB = 0, compC = 0, compE = 1; std::string comp = "0,0,1";
     uint64_t n = 1000; double coverage = -1; int fraglength = 35, minsize = 0, maxsize = 1000, rl = 75, gpus = 1;
     std::string sizeList, sizeFreq, prefix, adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";   // gargammel.pl:255-257
+    bool uniq = false;
     bool se = false, keep = false, n_given = false, seedSpecified = false, lognorm = false; uint64_t seed = 0; double loc = 0, scale = 0;
     DamageSpec dAll, dE, dB, dC;
     std::string misE, misB, misC; int distmis = 1;                                  // --misince/--misincb/--misincc/--distmis (gargammel.pl:300-303)
@@ -86,7 +87,8 @@ int main(int argc, char** argv) {
         if (a == "-seed") { seed = (uint64_t)to_ll(next(), "--seed"); seedSpecified = true; continue; }
         if (a == "-gpus") { gpus = (int)to_ll(next(), "--gpus"); continue; }
         if (a == "-keep") { keep = true; continue; }
-        if (a == "-mock" || a == "-methyl" || a == "-uniq" || a == "-ss" ||
+        if (a == "-uniq") { uniq = true; continue; }                                // fragSim -uniq for every source (gargammel.pl:1506-1507,1544,1628,1675)
+        if (a == "-mock" || a == "-methyl" || a == "-ss" ||
             a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
         return die("Unknown option: " + a);
     }
@@ -182,7 +184,7 @@ int main(int argc, char** argv) {
             int gid = -1;
             if (ggh::upload_genome(ctx, srcs[items[k].src].g, &gid) != GG_OK) return fail("genome upload");
             gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot; rg.comp_slot = items[k].comp;
-            snprintf(rg.tag, sizeof rg.tag, "%s", items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;
+            snprintf(rg.tag, sizeof rg.tag, "%s", uniq ? "" : items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;   // -uniq: "_<count>_<tag>" is appended on the host
         }
         const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
         if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
@@ -213,9 +215,26 @@ int main(int argc, char** argv) {
     for (int r = 0; r < gpus; r++) th.push_back(std::thread(worker, r));
     for (int r = 0; r < gpus; r++) th[r].join();
     for (int r = 0; r < gpus; r++) if (rcs[r]) return die("Error: " + shard_err[r]);
+    // -uniq: one defline counter per source file, exactly one fragSim invocation each in the reference
+    auto uniq_pass = [&](std::vector<std::string>& parts) {
+        std::string all; for (size_t r = 0; r < parts.size(); r++) { all += parts[r]; std::string().swap(parts[r]); }
+        std::string out2; out2.reserve(all.size() + all.size() / 16);
+        UniqSuffixer u; size_t p = 0;
+        for (size_t k = 0; k < items.size(); k++) {
+            u.reset(items[k].tag, true);
+            size_t q = p; uint64_t lines = 0;
+            while (q < all.size() && lines < 2 * items[k].count) { const char* e = (const char*)memchr(all.data() + q, '\n', all.size() - q); q = e ? (size_t)(e - all.data()) + 1 : all.size(); lines++; }
+            u.apply(all.data() + p, q - p, out2); p = q;
+        }
+        parts.assign(1, out2);
+    };
+    if (uniq) {
+        uniq_pass(shard);
+        if (keep) for (int pass = 1; pass < 3; pass++) { std::vector<std::string> v; for (int r = 0; r < gpus; r++) v.push_back(shard_keep[r][pass]); uniq_pass(v); for (int r = 0; r < gpus; r++) shard_keep[r][pass] = r == 0 ? v[0] : std::string(); }
+    }
     Sink out;
     if (!out.open_plain(prefix + "_a.fa")) return die("Cannot write to file " + prefix + "_a.fa");
-    for (int r = 0; r < gpus; r++) if (!out.write(shard[r].data(), shard[r].size())) return die("Error: write failed");
+    for (size_t r = 0; r < shard.size(); r++) if (!out.write(shard[r].data(), shard[r].size())) return die("Error: write failed");
     if (!out.close()) return die("Error: write failed");
     if (keep) {
         // <prefix>_d.fa.gz = deamSim output in e,b,c order; <prefix>.{e,b,c}.fa.gz = the fragSim outputs per source class

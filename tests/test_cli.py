@@ -100,6 +100,16 @@ def test_cli_pipeline_matches_oracle(workdir, oracle_mod):
     o.set_adapters(read_len=60)
     util.assert_same(gzip.open(str(d / "fr.gz")).read(), o.run_fused(0, n, api.EMIT_FR)[0], "-fr")
     util.assert_same(gzip.open(str(d / "rr.gz")).read(), o.run_fused(0, n, api.EMIT_RR)[0], "-rr")
+    # -uniq: "_<count>" after every defline, then "_<tag>" (fragSim.cpp:119-135); the GPU stream carries no tag in this mode
+    r7 = run([os.path.join(BIN, "fragSim"), "--seed", str(seed), "-tag", "e1_0", "-uniq", "-n", "3000", "-l", "25", "--norev", str(d / "g.fa")])
+    assert r7.returncode == 0, r7.stderr
+    o.set_sizes(api.SIZE_FIXED, fixed_len=25); o.set_norev(True); o.set_plan([api.Range(0, 3000, gid, -1, "")])
+    seen, want = {}, []
+    for h, s_ in util.records(o.run_fused(0, 3000, api.EMIT_FRAG)[0]):
+        seen[h] = seen.get(h, 0) + 1
+        want.append(h + b"_%d_e1_0\n" % seen[h] + s_ + b"\n")
+    util.assert_same(r7.stdout, b"".join(want), "bin/fragSim -uniq")
+    o.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=0, maxlen=1000); o.set_norev(False); o.set_plan([api.Range(0, n, gid, 0, "e1_0")])
     # Briggs through the CLI + gz output
     o.set_briggs(0, 0.03, 0.4, 0.01, 0.3)
     r6 = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-damage", "0.03,0.4,0.01,0.3", "-o", str(d / "b.fa.gz"), str(d / "f.fa")])
@@ -152,6 +162,18 @@ def test_fused_driver_matches_oracle(tmp_path, oracle_mod):
         frag = o.run_fused(0, first, api.EMIT_FRAG)[0]
         got = b"".join(gzip.open(str(tmp_path / ("sim.%s.fa.gz" % k))).read() for k in "ebc")
         util.assert_same(got, frag, ".e/.b/.c.fa.gz")
+        # -uniq: "<defline>_<count>_<tag>" with one counter per source file (gargammel.pl:1506-1507; fragSim.cpp:119-135)
+        r = run([os.path.join(BIN, "gargammel-b200"), "--comp", "0.3,0.1,0.6", "-n", str(n), "-f", str(tmp_path / "sf.size"), "-matfile", str(tmp_path / "m-"),
+                 "-rl", "75", "--seed", str(seed), "-uniq", "-o", str(tmp_path / "simu"), str(d)])
+        assert r.returncode == 0, r.stderr
+        import re
+        plain = util.records((tmp_path / "sim_a.fa").read_bytes()); uq = util.records((tmp_path / "simu_a.fa").read_bytes())
+        assert len(plain) == len(uq)
+        seen = {}
+        for (h0, s0), (h1, s1) in zip(plain, uq):
+            m = re.match(rb"^(>.*:\d+)(e1_0|e2_0|b\d+|c\d+)$", h0)
+            key = (m.group(2), m.group(1)); seen[key] = seen.get(key, 0) + 1
+            assert s0 == s1 and h1 == m.group(1) + b"_%d_" % seen[key] + m.group(2)
 
 
 def _ref(name):
