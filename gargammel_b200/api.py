@@ -13,7 +13,7 @@ DEFAULT_ADAPTER_F = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTC
 DEFAULT_ADAPTER_S = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"         # adptSim.cpp:29
 
 FaiEntry = namedtuple("FaiEntry", "name len offset line_blen line_len")
-Range = namedtuple("Range", "first_id count genome damage_slot tag comp_slot", defaults=(-1,))
+Range = namedtuple("Range", "first_id count genome damage_slot tag comp_slot gc_slot", defaults=(-1, -1))
 RunInfo = namedtuple("RunInfo", "bytes records attempts gather_bytes in_bytes device_ms launches")
 
 
@@ -30,7 +30,7 @@ class _Fai(C.Structure):
 
 class _Range(C.Structure):
     _fields_ = [("first_id", C.c_uint64), ("count", C.c_uint64), ("genome", C.c_int32),
-                ("damage_slot", C.c_int32), ("comp_slot", C.c_int32), ("reserved", C.c_int32), ("tag", C.c_char * 24)]
+                ("damage_slot", C.c_int32), ("comp_slot", C.c_int32), ("gc_slot", C.c_int32), ("tag", C.c_char * 24)]
 
 
 class _Out(C.Structure):
@@ -171,6 +171,14 @@ class Context:
     def clear_composition(self, slot):
         self._ck(self._f("tables_clear_composition")(self._h, C.c_int(slot)))
 
+    def set_gcbias(self, slot, genome, comp_dist, gc_bias):
+        m, sd = C.c_double(), C.c_double()
+        self._ck(self._f("tables_set_gcbias")(self._h, C.c_int(slot), C.c_int(genome), C.c_int(comp_dist), C.c_double(gc_bias), C.byref(m), C.byref(sd)))
+        return m.value, sd.value
+
+    def clear_gcbias(self, slot):
+        self._ck(self._f("tables_clear_gcbias")(self._h, C.c_int(slot)))
+
     def set_briggs(self, slot, v, l, d, s):
         self._ck(self._f("tables_set_briggs")(self._h, C.c_int(slot), C.c_double(v), C.c_double(l), C.c_double(d), C.c_double(s)))
 
@@ -191,6 +199,7 @@ class Context:
         for i, r in enumerate(ranges):
             arr[i].first_id, arr[i].count, arr[i].genome, arr[i].damage_slot = r.first_id, r.count, r.genome, r.damage_slot
             arr[i].comp_slot = r.comp_slot
+            arr[i].gc_slot = r.gc_slot
             arr[i].tag = (r.tag or "").encode()
         self._ck(self._f("plan_set")(self._h, arr, C.c_int(len(ranges))))
 

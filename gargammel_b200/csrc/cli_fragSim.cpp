@@ -7,7 +7,7 @@ int main(int argc, char** argv) {
     int sizeFragments = 20; uint64_t nFragments = 10; int minLen = 0, maxLen = 1000;
     bool noRev = false, seedSpecified = false, specifiedLength = false, specifiedLoc = false, specifiedScale = false; uint64_t seed = 0;
     double location = -1, scale = -1;
-    bool uniqTags = false, tagb = false;
+    bool uniqTags = false, tagb = false, gcBiasB = false; double gcBias = 0;
     std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
         "\t\t--loc\t[float] --scale\t[float]\tlog-normal fragment lengths\n" +
         "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
         "\t\t-uniq\t\t\t\t\tMake the fragment names unique by appending a counter (host-side pass, like the reference)\n" +
-        "\tNot in this build: -gc --circ --case --fq --trim5p -b -u\n";
+        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\tNot in this build: --circ --case --fq --trim5p -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -41,7 +41,8 @@ int main(int argc, char** argv) {
         if (a == "--scale") { scale = to_d(argv[++i], "--scale"); specifiedScale = true; continue; }
         if (a == "--comp") { compFile = argv[++i]; continue; }
         if (a == "--dist") { distFromEnd = (int)to_ll(argv[++i], "--dist"); continue; }
-        if (a == "-gc" || a == "--circ" || a == "--trim5p" || a == "-b")
+        if (a == "-gc") { gcBias = to_d(argv[++i], "-gc"); gcBiasB = true; continue; }      // fragSim.cpp:589-594
+        if (a == "--circ" || a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
         if (a == "--case" || a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
@@ -85,8 +86,14 @@ int main(int argc, char** argv) {
         if (!ggh::load_dnacomp(compFile, distFromEnd, ct, err)) return die(err);
         if (gg_tables_set_composition(ctx, 0, ct.dist, ct.s5p.data(), ct.s5m.data(), ct.s3p.data(), ct.s3m.data()) != GG_OK) return gg_fail(ctx, "--comp");
     }
+    if (gcBiasB) {                                                                  // fragSim.cpp:1190-1269
+        std::cerr << "Computing average GC content" << std::endl;
+        double m = 0, sd = 0;
+        if (gg_tables_set_gcbias(ctx, 0, gid, compFile.empty() ? 0 : distFromEnd, gcBias, &m, &sd) != GG_OK) return gg_fail(ctx, "-gc");
+        std::cerr << "GC content: mean:" << m << " stdev:" << sd << std::endl;
+    }
     if (nFragments) {
-        gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1; r.comp_slot = compFile.empty() ? -1 : 0;
+        gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1; r.comp_slot = compFile.empty() ? -1 : 0; r.gc_slot = gcBiasB ? 0 : -1;
         snprintf(r.tag, sizeof r.tag, "%s", uniqTags ? "" : tag.c_str());        // with -uniq the tag goes after the count (fragSim.cpp:1505,131-133)
         if (gg_plan_set(ctx, &r, 1) != GG_OK) return gg_fail(ctx, "plan");
     }

@@ -183,7 +183,7 @@ int main(int argc, char** argv) {
         for (size_t k = 0; k < items.size(); k++) {
             int gid = -1;
             if (ggh::upload_genome(ctx, srcs[items[k].src].g, &gid) != GG_OK) return fail("genome upload");
-            gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot; rg.comp_slot = items[k].comp;
+            gg_range rg; memset(&rg, 0, sizeof rg); rg.first_id = first; rg.count = items[k].count; rg.genome = gid; rg.damage_slot = items[k].slot; rg.comp_slot = items[k].comp; rg.gc_slot = -1;
             snprintf(rg.tag, sizeof rg.tag, "%s", uniq ? "" : items[k].tag.c_str()); plan.push_back(rg); first += items[k].count;   // -uniq: "_<count>_<tag>" is appended on the host
         }
         const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;

@@ -91,6 +91,8 @@ struct gg_ctx {
     HostDamage dmg[GG_MAX_DAMAGE_SLOTS];
     // base composition (fragSim --comp)
     struct HostComp { int dist; double maxP, maxM; DBuf d_tab; } comp[GG_MAX_COMP_SLOTS];
+    // GC bias (fragSim -gc)
+    struct HostGc { bool on; int dist, genome, wmax; double bias, mean, sd; DBuf d_thr; } gc[GG_MAX_GC_SLOTS];
     // adapters
     std::string adF, adS; int read_len;
     DBuf d_adF2, d_adS2, d_rcS2, d_adF, d_adS;
@@ -191,6 +193,7 @@ int sync_plan(gg_ctx* ctx) {
         memset(&r[i], 0, sizeof(RangeDev));
         r[i].first_id = ctx->plan[i].first_id; r[i].count = ctx->plan[i].count;
         r[i].genome = ctx->plan[i].genome; r[i].slot = ctx->plan[i].damage_slot;
+        r[i].gc = (ctx->plan[i].gc_slot >= 0 && ctx->gc[ctx->plan[i].gc_slot].on) ? ctx->plan[i].gc_slot : -1;
         r[i].comp = (ctx->plan[i].comp_slot >= 0 && ctx->comp[ctx->plan[i].comp_slot].dist > 0) ? ctx->plan[i].comp_slot : -1;
         r[i].tag_len = (int)strnlen(ctx->plan[i].tag, sizeof(ctx->plan[i].tag) - 1);
         memcpy(r[i].tag, ctx->plan[i].tag, r[i].tag_len);
@@ -310,6 +313,7 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
     ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
+    for (int i = 0; i < GG_MAX_GC_SLOTS; i++) { ctx->gc[i].on = false; ctx->gc[i].wmax = -1; }
     for (int i = 0; i < GG_MAX_COMP_SLOTS; i++) { ctx->comp[i].dist = 0; ctx->comp[i].maxP = ctx->comp[i].maxM = 1.0; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
@@ -331,6 +335,7 @@ int gg_ctx_destroy(gg_ctx* ctx) {
                     &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
+    for (int s = 0; s < GG_MAX_GC_SLOTS; s++) ctx->gc[s].d_thr.release();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
         ctx->dmg[s].d_thr.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release();
     }
@@ -588,6 +593,62 @@ int gg_tables_clear_composition(gg_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= GG_MAX_COMP_SLOTS) return GG_ERR_ARG;
     ctx->comp[slot].dist = 0; ctx->plan_dirty = true; return GG_OK;
 }
+// survival thresholds for every window length W <= wmax and G/C count g <= W: survive iff rP <= pSurv (fragSim.cpp:1524-1529)
+static int build_gc_table(gg_ctx* ctx, int slot, int wmax) {
+    gg_ctx::HostGc& H = ctx->gc[slot];
+    std::vector<uint32_t> thr((size_t)(wmax + 1) * (size_t)(wmax + 2) / 2);
+    static const double inv_sqrt_2pi = 0.3989422804014327;                                // pdfNorm, fragSim.cpp:96-102
+    const double maxNorm = inv_sqrt_2pi / H.sd * exp(-0.5 * ((H.mean - H.mean) / H.sd) * ((H.mean - H.mean) / H.sd));
+    for (int W = 0; W <= wmax; W++)
+        for (int g = 0; g <= W; g++) {
+            uint32_t t = 2147483648u;                                                     // W == 0: gcContent is NaN, rP > NaN is false: never killed
+            if (W > 0) {
+                const double gcContent = double(g) / double(W);
+                double pSurv = 1 / (1 + exp(H.bias * (gcContent - H.mean)));
+                const double a = (gcContent - H.mean) / H.sd;
+                pSurv = pSurv * ((inv_sqrt_2pi / H.sd * exp(-0.5 * a * a)) / maxNorm);
+                t = thr_le(pSurv);
+            }
+            thr[(size_t)W * (W + 1) / 2 + g] = t;
+        }
+    int rc = upload_vec(ctx, H.d_thr, thr);
+    if (rc) return rc;
+    H.wmax = wmax;
+    return GG_OK;
+}
+int gg_tables_set_gcbias(gg_ctx* ctx, int slot, int genome_id, int comp_dist, double gc_bias, double* mean_out, double* sd_out) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_GC_SLOTS || genome_id < 0 || genome_id >= (int)ctx->genomes.size() || comp_dist < 0 || comp_dist > GG_MAX_COMP_DIST)
+        return ctx->fail(GG_ERR_ARG, "gg_tables_set_gcbias: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_contig_tables(ctx))) return rc;
+    CK(ctx->d_ticket_stats.ensure(256));
+    unsigned long long* d_sums = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 128);
+    CK(cudaMemsetAsync(d_sums, 0, 24, ctx->st));
+    const HostGenome& HG = ctx->genomes[genome_id];
+    GenomeDev G; G.seq2 = HG.d_seq2; G.nmask = HG.d_nmask; G.G = HG.G; G.first_contig = HG.first_contig; G.n_contigs = (int)HG.contigs.size();
+    ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
+    CK(launch_gc_probe(G, ctx->d_cum_end.as<uint64_t>(), ctx->d_gbase.as<uint64_t>(), ctx->d_clen.as<uint32_t>(), comp_dist, key, d_sums, ctx->st));
+    unsigned long long sums[3];
+    CK(cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (sums[2]) return ctx->fail(GG_ERR_GIVEUP, "gg_tables_set_gcbias: a GC probe exhausted its attempts (genome without a resolved 50-bp window?)");
+    gg_ctx::HostGc& H = ctx->gc[slot];
+    const double n = (double)GG_GC_PROBES, w = (double)(GG_GC_PROBE_LEN + 2 * comp_dist);
+    H.mean = (double)sums[0] / (n * w);
+    const double var = (double)sums[1] / (n * w * w) - H.mean * H.mean;
+    H.sd = sqrt(var > 0 ? var : 0);
+    H.bias = gc_bias; H.dist = comp_dist; H.genome = genome_id; H.on = true; H.wmax = -1;
+    if (mean_out) *mean_out = H.mean;
+    if (sd_out) *sd_out = H.sd;
+    ctx->plan_dirty = true;
+    return GG_OK;
+}
+int gg_tables_clear_gcbias(gg_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= GG_MAX_GC_SLOTS) return GG_ERR_ARG;
+    ctx->gc[slot].on = false; ctx->plan_dirty = true; return GG_OK;
+}
 int gg_tables_clear_damage(gg_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
     ctx->dmg[slot].mode = GG_DMG_NONE; return GG_OK;
@@ -622,6 +683,7 @@ int gg_plan_set(gg_ctx* ctx, const gg_range* ranges, int n) {
         if (ranges[i].genome < 0 || ranges[i].genome >= (int)ctx->genomes.size()) return ctx->fail(GG_ERR_ARG, "gg_plan_set: unknown genome id");
         if (ranges[i].damage_slot < -1 || ranges[i].damage_slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad damage slot");
         if (ranges[i].comp_slot < -1 || ranges[i].comp_slot >= GG_MAX_COMP_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad composition slot");
+        if (ranges[i].gc_slot < -1 || ranges[i].gc_slot >= GG_MAX_GC_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_plan_set: bad GC-bias slot");
         if (ranges[i].count == 0) return ctx->fail(GG_ERR_ARG, "gg_plan_set: empty range");
         next += ranges[i].count;
     }
@@ -723,6 +785,10 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.size_mode = ctx->size_mode; P.fixed_len = ctx->fixed_len; P.minlen = ctx->minlen; P.maxlen = ctx->maxlen; P.n_sizes = (int)ctx->size_len.size();
     P.size_thr = ctx->d_size_thr.as<uint32_t>(); P.size_len = ctx->d_size_len.as<int32_t>();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
+    for (int s = 0; s < GG_MAX_GC_SLOTS; s++) {
+        if (ctx->gc[s].on && ctx->gc[s].wmax < Lmax + 2 * ctx->gc[s].dist) { int rc2 = build_gc_table(ctx, s, Lmax + 2 * ctx->gc[s].dist); if (rc2) return rc2; }
+        P.gc[s].thr = ctx->gc[s].d_thr.as<uint32_t>(); P.gc[s].wmax = ctx->gc[s].wmax; P.gc[s].on = ctx->gc[s].on ? 1 : 0;
+    }
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) { P.comp[s].dist = ctx->comp[s].dist; P.comp[s].tab = ctx->comp[s].d_tab.as<double>(); P.comp[s].maxP = ctx->comp[s].maxP; P.comp[s].maxM = ctx->comp[s].maxM; }
     P.ad.adF2 = ctx->d_adF2.as<uint32_t>() + 1; P.ad.adS2 = ctx->d_adS2.as<uint32_t>() + 1; P.ad.rcS2 = ctx->d_rcS2.as<uint32_t>() + 1;
     P.ad.lenF = (int)ctx->adF.size(); P.ad.lenS = (int)ctx->adS.size(); P.ad.read_len = ctx->read_len;

@@ -8,7 +8,7 @@
 namespace ggd {
 
 // stream ids (Philox counter word 3)
-enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4, ST_FRAG2 = 5 };
+enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4, ST_FRAG2 = 5, ST_GCPROBE = 6, ST_FRAG3 = 7 };
 
 // ---------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -52,6 +52,19 @@ __device__ __forceinline__ uint32_t revcomp16(uint32_t x) {
     uint32_t y = __brev(x);
     y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
     return ~y;
+}
+// number of G/C among W bases starting at base index p0 (G = 10b, C = 01b: exactly one of the two bits set)
+__device__ __forceinline__ int gc_count(const uint32_t* __restrict__ seq2, uint64_t p0, int W) {
+    int c = 0; uint64_t p = p0; const uint64_t end = p0 + (uint64_t)W;
+#pragma unroll 1
+    while (p < end) {
+        const uint32_t w = __ldg(seq2 + (p >> 4));
+        const int o = (int)(p & 15), n = (int)min((uint64_t)(16 - o), end - p);
+        uint32_t x = ((w ^ (w >> 1)) & 0x55555555u) >> (2 * o);
+        if (n < 16) x &= (1u << (2 * n)) - 1u;
+        c += __popc(x); p += (uint64_t)n;
+    }
+    return c;
 }
 // mask with the low n 2-bit fields set, n in [0,16]
 // (PTX shl.b32 clamps shift amounts above 31, so n == 16 gives (1<<32)-1 == 0xFFFFFFFF without a compare)

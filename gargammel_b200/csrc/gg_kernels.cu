@@ -14,6 +14,12 @@
 namespace ggk {
 using namespace ggd;
 
+__device__ __forceinline__ unsigned long long warp_sum_u64_early(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // ======================================================================================= pack
 // one thread per 32 bases of the packed base space (2 seq2 words + 1 mask word)
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ fasta, uint64_t n,
@@ -60,6 +66,50 @@ cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t*
     if (n_units == 0) return cudaSuccess;
     const uint64_t blocks = (n_units + 255) / 256;
     k_pack_genome<<<(unsigned)blocks, 256, 0, st>>>(fasta, n, c_off, c_len, c_blen, c_llen, c_gbase, n_contigs, n_units, seq2, nmask);
+    return cudaGetLastError();
+}
+
+// ======================================================================================= GC probes (fragSim -gc)
+// GC content of 1,000,000 random 50-bp windows (fragSim.cpp:1190-1269): thread per probe, integer sums so that the
+// statistics do not depend on the reduction order.
+__global__ void __launch_bounds__(256) k_gc_probe(const GenomeDev G, const uint64_t* __restrict__ cum_end, const uint64_t* __restrict__ gbase,
+                                                  const uint32_t* __restrict__ clen, int d, Key key, unsigned long long* __restrict__ sums) {
+    const uint64_t pidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long s1 = 0, s2 = 0, bad = 0;
+    if (pidx < 1000000ull) {
+        const int length = 50, W = length + 2 * d;
+        const uint64_t* cum = cum_end + G.first_contig;
+        bool done = false;
+        for (uint32_t attempt = 0; attempt < 65536u && !done; attempt++) {
+            const uint4 x = rng_block(key, pidx, attempt, ST_GCPROBE);
+            const uint64_t coord = __umul64hi(((uint64_t)x.w << 32) | x.z, G.G);
+            if (coord == 0) continue;
+            int a = 0, b = G.n_contigs - 1;                            // contig whose span holds coord
+            while (a < b) { int mid = (a + b) >> 1; if (coord <= __ldg(cum + mid)) b = mid; else a = mid + 1; }
+            const int ci = G.first_contig + a;
+            const uint64_t len = __ldg(clen + ci);
+            const uint64_t idx = (coord - 1) - (__ldg(cum + a) - len);
+            if (idx < (uint64_t)d || idx + (uint64_t)length + (uint64_t)d > len) continue;      // start+d <= coord <= end-length-d+1 (fragSim.cpp:1217-1219)
+            const uint64_t s0 = __ldg(gbase + ci) + idx - (uint64_t)d, e = s0 + (uint64_t)W - 1;
+            uint32_t any = 0;
+            for (uint64_t w = s0 >> 5; w <= (e >> 5); w++) {
+                uint32_t m = __ldg(G.nmask + w);
+                if (w == (s0 >> 5)) m &= 0xFFFFFFFFu << (s0 & 31);
+                if (w == (e >> 5)) m &= 0xFFFFFFFFu >> (31 - (e & 31));
+                any |= m;
+            }
+            if (any) continue;                                         // isResolvedDNAstring (fragSim.cpp:1241-1242)
+            const unsigned long long g = (unsigned long long)gc_count(G.seq2, s0, W);
+            s1 = g; s2 = g * g; done = true;
+        }
+        if (!done) bad = 1;
+    }
+    s1 = warp_sum_u64_early(s1); s2 = warp_sum_u64_early(s2); bad = warp_sum_u64_early(bad);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(sums + 0, s1); atomicAdd(sums + 1, s2); if (bad) atomicAdd(sums + 2, bad); }
+}
+cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, Key key,
+                            unsigned long long* sums, cudaStream_t st) {
+    k_gc_probe<<<(1000000 + 255) / 256, 256, 0, st>>>(G, cum_end, gbase, clen, dist, key, sums);
     return cudaGetLastError();
 }
 
@@ -395,6 +445,13 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     if (any) continue;
                 }
                 plus = P.norev ? 1u : (x.y & 1u);                                      // randomBool, fragSim.cpp:1462-1467
+                if (rg->gc >= 0) {                                                     // -gc survival (fragSim.cpp:1509-1534, repeated :1548-1576 without --comp)
+                    const int Wn = L + 2 * d;
+                    const uint32_t thr = __ldg(P.gc[rg->gc].thr + (Wn * (Wn + 1) / 2 + gc_count(G.seq2, gpos - (uint64_t)d, Wn)));
+                    const uint4 y = rng_block(P.key, id, attempt, ST_FRAG3);
+                    if ((y.x >> 1) >= thr) continue;
+                    if (!d && (y.y >> 1) >= thr) continue;
+                }
                 if (d && !comp_accept(P, P.comp[rg->comp], G.seq2, gpos, L, plus, id, attempt)) continue;   // --comp, fragSim.cpp:1609-1759
                 ok = true; break;
             }

@@ -24,6 +24,7 @@ struct ContigTab {           // struct-of-arrays over all contigs of all genomes
 struct RangeDev {            // one `fragSim -tag T -n N file` of the plan
     uint64_t first_id, count;
     int genome, slot, tag_len, comp;
+    int gc, pad0;
     char tag[24];
 };
 struct CompDev {             // fragSim --comp tables of one slot (fp64: the acceptance product must round like the reference)
@@ -33,6 +34,9 @@ struct CompDev {             // fragSim --comp tables of one slot (fp64: the acc
 };
 struct AdptNaming {           // adptSim -name / -tag (adptSim.cpp:375-393)
     int add_in_name, tag_len; char tag[24];
+};
+struct GcDev {               // fragSim -gc: survive iff u31 < thr[W*(W+1)/2 + gcCount], W = window length (fragment + flanks)
+    const uint32_t* thr; int wmax, on;
 };
 struct Adapters {
     const uint32_t* adF2;    // forward adapter, 2-bit packed (+slack)
@@ -72,6 +76,7 @@ struct FusedParams {
     // damage + adapters
     ggd::DamageDev dmg[4];
     CompDev comp[4];
+    GcDev gc[4];
     Adapters ad;
     // output
     uint8_t* out; uint64_t out_cap;
@@ -93,6 +98,8 @@ cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t*
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
                                const uint64_t* unit_start, int n_contigs, uint64_t n_units,
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
+cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, ggd::Key key,
+                            unsigned long long* sums /* [0]=sum gc, [1]=sum gc^2, [2]=give-ups */, cudaStream_t st);
 cudaError_t launch_fused(const FusedParams& P, int grid, int threads, cudaStream_t st);
 cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs);
 

@@ -59,6 +59,9 @@ typedef enum gg_damage_mode {
 #define GG_MAX_DAMAGE_SLOTS 4
 #define GG_MAX_COMP_SLOTS 4
 #define GG_MAX_COMP_DIST 32
+#define GG_MAX_GC_SLOTS 4
+#define GG_GC_PROBES 1000000u   /* fragSim.cpp:1198 */
+#define GG_GC_PROBE_LEN 50       /* fragSim.cpp:1199 */
 
 /* ---- what the last stage writes ---- */
 typedef enum gg_emit_mode {
@@ -89,7 +92,7 @@ typedef struct gg_range {
     int32_t  genome;         /* id returned by gg_genome_upload               */
     int32_t  damage_slot;    /* 0..GG_MAX_DAMAGE_SLOTS-1, or -1 = no damage   */
     int32_t  comp_slot;      /* base-composition table (fragSim --comp), 0..GG_MAX_COMP_SLOTS-1, or -1 = none */
-    int32_t  reserved;
+    int32_t  gc_slot;        /* GC-bias table (fragSim -gc), 0..GG_MAX_GC_SLOTS-1, or -1 = none */
     char     tag[24];        /* NUL-terminated -tag string appended to defline (fragSim.cpp:1505-1507) */
 } gg_range;
 
@@ -141,6 +144,12 @@ int  gg_tables_set_norev(gg_ctx* ctx, int norev);   /* --norev, fragSim.cpp:1463
  * 3' end; rows 0..dist-1 are the positions outside the fragment on the 5' side / inside on the 3' side (reference order). */
 int  gg_tables_set_composition(gg_ctx* ctx, int slot, int dist, const double* s5p, const double* s5m, const double* s3p, const double* s3m);
 int  gg_tables_clear_composition(gg_ctx* ctx, int slot);
+/* fragSim -gc bias (fragSim.cpp:1190-1269,1509-1576): GC content of 1,000,000 random 50-bp windows of `genome_id` gives mean/stdev; every
+ * attempt then survives with probability 1/(1+exp(bias*(gc-mean))) * N(gc; mean, sd)/N(mean; mean, sd) (drawn twice without --comp, as the
+ * reference does).  comp_dist = the --dist of the composition slot used together with it (0 without --comp).  Call after
+ * gg_tables_set_sizes and gg_genome_upload.  mean_out/sd_out may be NULL. */
+int  gg_tables_set_gcbias(gg_ctx* ctx, int slot, int genome_id, int comp_dist, double gc_bias, double* mean_out, double* sd_out);
+int  gg_tables_clear_gcbias(gg_ctx* ctx, int slot);
 /* deamSim -matfile/-profile (deamSim.cpp:956-1241): sub5[r][12], sub3[r][12] with index 0 = terminal base
  * (i.e. AFTER the 3' reversal of deamSim.cpp:1236); clamp_last = !(-last) (deamSim.cpp:1811-1817). */
 int  gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5,

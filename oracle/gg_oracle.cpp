@@ -30,6 +30,7 @@
 #include <vector>
 #include <algorithm>
 #include <map>
+#include <math.h>
 
 #include "../include/gargammel_b200.h"   /* struct layouts + enums only (gg_fai_entry, gg_range, modes) */
 
@@ -52,7 +53,7 @@ static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
 }
 
 /* stream ids (counter word 3) -- DESIGN.md "Draw specification" */
-enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4, ST_FRAG2 = 5 };
+enum { ST_FRAG = 0, ST_DEAM = 1, ST_ADPT_F = 2, ST_DEAM2 = 3, ST_ADPT_R = 4, ST_FRAG2 = 5, ST_GCPROBE = 6, ST_FRAG3 = 7 };
 
 struct Rng {
     uint32_t k0, k1;
@@ -89,8 +90,10 @@ struct Damage {
     Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0) {}
 };
 struct Comp { int dist; std::vector<double> s5p, s5m, s3p, s3m; double maxP, maxM; Comp() : dist(0), maxP(1), maxM(1) {} };
+struct GcBias { bool on; int dist; double bias, mean, sd, maxNorm; GcBias() : on(false), dist(0), bias(0), mean(0.4), sd(0.1), maxNorm(1) {} };
 struct orc_ctx {
     Rng rng;
+    GcBias gc[GG_MAX_GC_SLOTS];
     Comp comp[GG_MAX_COMP_SLOTS];
     std::vector<Genome> genomes;
     int size_mode, fixed_len, minlen, maxlen, norev;
@@ -142,7 +145,16 @@ struct FragResult { const Chr* chr; uint64_t idx; int length; bool plus; std::st
 
 /* One fragment = the first accepted attempt; mirrors the while-loop body fragSim.cpp:1361-1507
  * with distFromEnd == 0 (no --comp: fragSim.cpp:1019-1021), no --circ, no -gc. */
-static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slot, FragResult* out) {
+/* pdfNorm, fragSim.cpp:96-102 */
+static double pdfNorm(double x, double m, double s) { static const double inv_sqrt_2pi = 0.3989422804014327; double a = (x - m) / s; return inv_sqrt_2pi / s * exp(-0.5 * a * a); }
+/* survival probability of a window with gcCount G/C and atCount A/T bases, fragSim.cpp:1524-1526 */
+static double gcSurvival(const GcBias& B, unsigned gcCount, unsigned atCount) {
+    double gcContent = double(gcCount) / double(gcCount + atCount);
+    double pSurv = 1 / (1 + exp(B.bias * (gcContent - B.mean)));
+    pSurv = pSurv * (pdfNorm(gcContent, B.mean, B.sd) / B.maxNorm);
+    return pSurv;
+}
+static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slot, int gc_slot, FragResult* out) {
     const Comp* cp = (comp_slot >= 0 && c->comp[comp_slot].dist > 0) ? &c->comp[comp_slot] : NULL;
     const int d = cp ? cp->dist : 0;                         /* distFromEnd: 0 without --comp (fragSim.cpp:1019-1021) */
     for (uint32_t attempt = 0; attempt < GG_MAX_ATTEMPTS; attempt++) {
@@ -174,6 +186,14 @@ static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slo
         for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
         if (!resolved) continue;
         if (!plus) temp = reverseComplement(temp);           /* :1484 */
+        if (gc_slot >= 0 && c->gc[gc_slot].on) {             /* -gc, fragSim.cpp:1509-1534 (and again :1548-1576 without --comp) */
+            unsigned gcCount = 0, atCount = 0;
+            for (size_t i = 0; i < temp.size(); i++) { if (temp[i] == 'G' || temp[i] == 'C') gcCount++; else atCount++; }
+            const double pSurv = gcSurvival(c->gc[gc_slot], gcCount, atCount);
+            uint32_t y[4]; c->rng.block(id, attempt, ST_FRAG3, y);
+            if (u01(y[0]) > pSurv) continue;                 /* killed = (rP > pSurv) */
+            if (!cp && u01(y[1]) > pSurv) continue;          /* the reference repeats the test when no composition file is given */
+        }
         std::string preFrag = temp.substr(0, d), frag = temp.substr(d, length), posFrag = temp.substr(length + d, d);   /* :1485-1496 */
         if (cp) {                                            /* --comp acceptance, fragSim.cpp:1609-1759 */
             const std::vector<double>& s5 = plus ? cp->s5p : cp->s5m;
@@ -432,6 +452,44 @@ int orc_tables_set_composition(orc_ctx* c, int slot, int dist, const double* s5p
     return 0;
 }
 int orc_tables_clear_composition(orc_ctx* c, int slot) { if (slot < 0 || slot >= GG_MAX_COMP_SLOTS) return GG_ERR_ARG; c->comp[slot] = Comp(); return 0; }
+/* GC statistics of GG_GC_PROBES random 50-bp windows, fragSim.cpp:1190-1269 (probe p draws from stream GCPROBE, id = p) */
+int orc_tables_set_gcbias(orc_ctx* c, int slot, int genome_id, int comp_dist, double gc_bias, double* mean_out, double* sd_out) {
+    if (slot < 0 || slot >= GG_MAX_GC_SLOTS || genome_id < 0 || genome_id >= (int)c->genomes.size() || comp_dist < 0) return GG_ERR_ARG;
+    const Genome& g = c->genomes[genome_id];
+    const int d = comp_dist, length = GG_GC_PROBE_LEN, W = length + 2 * d;
+    uint64_t S1 = 0, S2 = 0;
+    for (uint64_t p = 0; p < GG_GC_PROBES; p++) {
+        bool done = false;
+        for (uint32_t attempt = 0; attempt < GG_MAX_ATTEMPTS && !done; attempt++) {
+            uint32_t x[4]; c->rng.block(p, attempt, ST_GCPROBE, x);
+            uint64_t r64 = ((uint64_t)x[3] << 32) | x[2];
+            uint64_t coord = (uint64_t)(((unsigned __int128)r64 * g.G) >> 64);
+            const Chr* found = NULL;
+            for (size_t i = 0; i < g.chrs.size(); i++)     /* :1217-1219 */
+                if (g.chrs[i].start + (uint64_t)d <= coord && coord + (uint64_t)length + (uint64_t)d <= g.chrs[i].end + 1) { found = &g.chrs[i]; break; }
+            if (!found) continue;
+            std::string temp = fetchSeq(g, *found, (int64_t)(coord - found->start) - d, W);
+            bool resolved = true;
+            for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
+            if (!resolved) continue;                         /* :1241-1242 */
+            uint64_t gcCount = 0;
+            for (size_t i = 0; i < temp.size(); i++) if (temp[i] == 'G' || temp[i] == 'C') gcCount++;
+            S1 += gcCount; S2 += gcCount * gcCount; done = true;
+        }
+        if (!done) { c->err = "GC probe exhausted its attempts"; return GG_ERR_GIVEUP; }
+    }
+    GcBias& B = c->gc[slot];
+    const double n = (double)GG_GC_PROBES, w = (double)W;
+    B.mean = (double)S1 / (n * w);
+    const double var = (double)S2 / (n * w * w) - B.mean * B.mean;
+    B.sd = sqrt(var > 0 ? var : 0);
+    B.maxNorm = pdfNorm(B.mean, B.mean, B.sd);               /* :1266 */
+    B.bias = gc_bias; B.dist = d; B.on = true;
+    if (mean_out) *mean_out = B.mean;
+    if (sd_out) *sd_out = B.sd;
+    return 0;
+}
+int orc_tables_clear_gcbias(orc_ctx* c, int slot) { if (slot < 0 || slot >= GG_MAX_GC_SLOTS) return GG_ERR_ARG; c->gc[slot] = GcBias(); return 0; }
 int orc_tables_set_briggs(orc_ctx* c, int slot, double v, double l, double d, double s) {
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
     Damage& D = c->dmg[slot]; D.mode = GG_DMG_BRIGGS; D.v = v; D.l = l; D.d = d; D.s = s; return 0;
@@ -458,7 +516,7 @@ int orc_run_fused(orc_ctx* c, uint64_t first, uint64_t count, int emit, uint8_t*
         if (!rg) { c->err = "fragment id outside the plan"; return GG_ERR_STATE; }
         if (rg->genome < 0 || rg->genome >= (int)c->genomes.size()) { c->err = "bad genome id"; return GG_ERR_ARG; }
         FragResult f;
-        int rc = sampleFragment(c, c->genomes[rg->genome], id, rg->comp_slot, &f);
+        int rc = sampleFragment(c, c->genomes[rg->genome], id, rg->comp_slot, rg->gc_slot, &f);
         if (rc) { c->err = "fragment exhausted its attempts"; return rc; }
         std::string name = fragDefline(f, rg->tag);
         std::string seq = f.frag;

@@ -234,6 +234,13 @@ def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
         ta = np.array([[s[pos] == c for c in b"ACGT"] for _, s in util.records(oc.stdout)]).sum(0)
         tb = np.array([[s[pos] == c for c in b"ACGT"] for _, s in util.records(rc.stdout)]).sum(0)
         assert stats.chi2_contingency(np.array([ta, tb]))[1] > 0.001, (pos, ta, tb)
+    # -gc: GC-biased survival, ours vs the reference (KS on the per-fragment GC fraction)
+    og = run([os.path.join(BIN, "fragSim"), "--seed", "9", "-n", "60000", "-l", "60", "-gc", "8", str(d / "g.fa")])
+    rg = run([_ref("fragSim"), "--seed", "9", "-n", "20000", "-l", "60", "-gc", "8", str(d / "g.fa")])
+    assert og.returncode == 0 and rg.returncode == 0, og.stderr + rg.stderr
+    assert b"GC content: mean:" in og.stderr
+    fa_ = np.array([(s.count(b"G") + s.count(b"C")) / 60 for _, s in util.records(og.stdout)]); fb_ = np.array([(s.count(b"G") + s.count(b"C")) / 60 for _, s in util.records(rg.stdout)])
+    assert stats.ks_2samp(fa_, fb_).pvalue > 0.001 and abs(fa_.mean() - fb_.mean()) < 0.004
     plain = run([os.path.join(BIN, "fragSim"), "--seed", "8", "-n", "120000", "-l", "40", str(d / "g.fa")])
     t0 = np.array([[s[0] == c for c in b"ACGT"] for _, s in util.records(plain.stdout)]).sum(0)
     t1 = np.array([[s[0] == c for c in b"ACGT"] for _, s in util.records(oc.stdout)]).sum(0)

@@ -296,3 +296,40 @@ def test_deam_name_tags(oracle_mod, damage):
     for c in (g, o):
         c.set_deam_naming(False)
     util.assert_same(g.run_deam(recs, 0, 5)[0], o.run_deam(recs, 0, 5)[0], "naming off")
+
+
+def test_fused_gc_bias(oracle_mod, tmp_path):
+    """fragSim -gc (fragSim.cpp:1190-1269,1509-1576): probe statistics and survival tests, alone and together with --comp."""
+    from oracle import parsers
+    rng = np.random.default_rng(21)
+    contigs = []
+    for i in range(4):                                      # GC content drifts along the contigs so that the bias has something to bite on
+        n = 9000 + 1500 * i
+        pgc = np.clip(0.25 + 0.5 * np.arange(n) / n + 0.1 * np.sin(np.arange(n) / 300.0), 0.05, 0.95)
+        isgc = rng.random(n) < pgc
+        seq = np.where(isgc, np.where(rng.random(n) < 0.5, ord("G"), ord("C")), np.where(rng.random(n) < 0.5, ord("A"), ord("T"))).astype(np.uint8)
+        seq[2000:2040] = ord("N")
+        contigs.append(("gc%d" % i, seq))
+    fa, fai = synth.fasta_bytes(contigs, 61)
+    p = str(tmp_path / "dnacomp.txt"); synth.write_dnacomp(p, seed=2)
+    tabs = [np.array(t) for t in parsers.load_dnacomp(p, 2)]
+    g = api.Context(0, 77); o = oracle_mod.OracleContext(77)
+    stats = []
+    for c in (g, o):
+        gid = c.upload_genome(fa, fai)
+        c.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq())
+        util.set_damage(c, 0, "matrix"); c.set_adapters(read_len=75)
+        c.set_composition(0, 2, *tabs)
+        stats.append((c.set_gcbias(0, gid, 0, 6.0), c.set_gcbias(1, gid, 2, -4.0)))
+        c.set_plan([api.Range(0, 900, gid, 0, "e", -1, 0), api.Range(900, 800, gid, 0, "b1", 0, 1), api.Range(1700, 500, gid, -1, "c1", -1, -1)])
+    assert stats[0] == stats[1]                              # integer probe sums -> identical mean / stdev on both sides
+    assert 0.3 < stats[0][0][0] < 0.7 and 0.03 < stats[0][0][1] < 0.3
+    for emit in (api.EMIT_FRAG, api.EMIT_ARTP):
+        a, ia = g.run_fused(0, 2200, emit); b, ib = o.run_fused(0, 2200, emit)
+        util.assert_same(a, b, "-gc emit=%d" % emit)
+        assert ia.attempts == ib.attempts and ia.attempts > 2 * 2200
+    gcf = lambda recs: np.mean([(s.count(b"G") + s.count(b"C")) / len(s) for _, s in recs])   # noqa: E731
+    recs = util.records(g.run_fused(0, 2200, api.EMIT_FRAG)[0])
+    assert gcf(recs[:900]) < gcf(recs[1700:]) - 0.02        # positive bias factor penalises GC-rich windows
+    g.clear_gcbias(0); o.clear_gcbias(0)
+    util.assert_same(g.run_fused(0, 900, api.EMIT_FRAG)[0], o.run_fused(0, 900, api.EMIT_FRAG)[0], "gc cleared")
