@@ -1,0 +1,80 @@
+"""Drop-in check against the reference's own driver (CPU, this container only): `perl gargammel.pl --mock ...` prints the
+shell commands it would run (gargammel.pl:71-84); every fragSim/deamSim/adptSim command line it composes must be accepted
+by our binaries -- same flags, same arity, input file last.  Without a GPU our binaries get as far as opening the device and
+stop with the loud "no CPU fallback" error; an "unknown option" or a validation error would mean the CLI drifted."""
+import os
+import re
+import shlex
+import shutil
+import subprocess
+
+import pytest
+
+from gargammel_b200 import synth
+from tests.conftest import ROOT
+
+REF = "/root/reference/gargammel.pl"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF) or shutil.which("perl") is None, reason="reference driver or perl not available")
+
+
+@pytest.fixture(scope="module")
+def layout(tmp_path_factory):
+    t = tmp_path_factory.mktemp("dropin")
+    gg = t / "gg"
+    (gg / "src").mkdir(parents=True)
+    (gg / "art_src_MountRainier").mkdir()
+    shutil.copy(REF, gg / "gargammel.pl")                      # a temp copy outside the repo: abs_path($0) must resolve next to src/
+    for b in ("fragSim", "deamSim", "adptSim"):
+        os.symlink(os.path.join(ROOT, "bin", b), gg / "src" / b)
+    art = gg / "art_src_MountRainier" / "art_illumina"
+    art.write_text("#!/bin/sh\nexit 0\n"); art.chmod(0o755)
+    d = t / "in"
+    for sub, names in (("endo", ["endo.1.fa", "endo.2.fa"]), ("cont", ["cont.1.fa"]), ("bact", ["b1.fa", "b2.fa"])):
+        (d / sub).mkdir(parents=True)
+        for k, nm in enumerate(names):
+            fa, fai = synth.make_genome(k + 1, 2, 20000, prefix=sub[0])
+            (d / sub / nm).write_bytes(fa); synth.write_fai(str(d / sub / (nm + ".fai")), fai)
+    (d / "bact" / "list").write_text("b1.fa\t0.4\nb2.fa\t0.6\n")
+    synth.write_sizefreq(str(t / "sf.size"))
+    open(t / "sl.size", "w").write("\n".join(str(x) for x in synth.golden_sizelist()[:500]) + "\n")
+    s5, s3 = synth.golden_matrix("single-")
+    synth.write_matrix_dat(str(t / "m-"), s5, s3)
+    synth.write_dnacomp(str(t / "dnacomp.txt"))
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "mapdamage_sample.txt"), t / "mis.txt")
+    return t
+
+
+def mock_commands(t, extra):
+    r = subprocess.run(["perl", str(t / "gg" / "gargammel.pl"), "--mock", "--comp", "0.3,0.1,0.6", "-n", "2000", "-o", str(t / "out_sim")] + extra + [str(t / "in") + "/"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cmds = [l[len("running cmd "):] for l in r.stderr.splitlines() if l.startswith("running cmd ")]
+    ours = [c for c in cmds if re.search(r"/src/(fragSim|deamSim|adptSim)\b", c)]
+    assert ours, r.stderr[-2000:]
+    return ours
+
+
+@pytest.mark.parametrize("extra", [
+    ["-f", "SF", "-matfile", "M"],
+    ["-l", "45", "-damage", "0.03,0.4,0.01,0.3", "-se"],
+    ["-s", "SL", "-mapdamage", "MIS", "double", "-rl", "100"],
+    ["--loc", "4.1", "--scale", "0.35", "-matfilee", "M", "-damageb", "0.02,0.3,0.01,0.5", "-minsize", "30", "-maxsize", "200"],
+    ["-f", "SF", "--misince", "DNACOMP", "--misincb", "DNACOMP", "--distmis", "2", "-uniq", "-matfile", "M"],
+])
+def test_reference_driver_command_lines_are_accepted(layout, extra):
+    import torch
+    t = layout
+    sub = {"SF": str(t / "sf.size"), "SL": str(t / "sl.size"), "M": str(t / "m-"), "MIS": str(t / "mis.txt"), "DNACOMP": str(t / "dnacomp.txt")}
+    cmds = mock_commands(t, [sub.get(x, x) for x in extra])
+    kinds = set()
+    for c in cmds:
+        head = re.split(r"\s[|>]", c, 1)[0]                    # drop "| gzip > file" / ">> file"
+        argv = shlex.split(head)
+        kinds.add(os.path.basename(argv[0]))
+        r = subprocess.run(argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        err = r.stderr.decode("utf-8", "replace")
+        assert "unknown option" not in err.lower() and "not supported" not in err, (c, err)
+        if not torch.cuda.is_available():
+            # intermediate .fa.gz inputs do not exist in --mock mode; our tools open the device first and fail loudly there
+            assert r.returncode == 1 and "no CPU fallback" in err, (c, err)
+    assert {"fragSim", "deamSim", "adptSim"} <= kinds
