@@ -8,7 +8,7 @@ from collections import namedtuple
 
 EMIT_FRAG, EMIT_DEAM, EMIT_STDOUT4, EMIT_ARTS, EMIT_ARTP, EMIT_FR, EMIT_RR = range(7)
 SIZE_FIXED, SIZE_LIST, SIZE_FREQ = range(3)
-DMG_NONE, DMG_MATRIX, DMG_BRIGGS, DMG_SINGLE, DMG_DOUBLE = range(5)
+DMG_NONE, DMG_MATRIX, DMG_BRIGGS, DMG_SINGLE, DMG_DOUBLE, DMG_BRIGGS_SS = range(6)
 DEFAULT_ADAPTER_F = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"   # adptSim.cpp:28
 DEFAULT_ADAPTER_S = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"         # adptSim.cpp:29
 
@@ -119,8 +119,9 @@ class Context:
     def genome_clear(self):
         self._ck(self._f("genome_clear")(self._h))
 
-    def upload_genome(self, fasta, fai):
-        """fasta: bytes, or any object with data_ptr()/numel() (a pinned torch uint8 tensor), or a numpy uint8 array."""
+    def upload_genome(self, fasta, fai, circ=-1):
+        """fasta: bytes, or any object with data_ptr()/numel() (a pinned torch uint8 tensor), or a numpy uint8 array.
+        circ: index into `fai` of the contig fragSim --circ names (-1 = none)."""
         arr = (_Fai * len(fai))()
         for i, e in enumerate(fai):
             arr[i].name = e.name.encode()
@@ -132,7 +133,7 @@ class Context:
             ptr, n = C.c_void_p(fasta.ctypes.data), int(fasta.size)
         else:
             ptr, n = C.cast(C.c_char_p(fasta), C.c_void_p), len(fasta)
-        self._ck(self._f("genome_upload")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.byref(gid)))
+        self._ck(self._f("genome_upload_circ")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.c_int(circ), C.byref(gid)))
         return gid.value
 
     def genome_fetch(self, genome, chr_index, start, length):
@@ -181,6 +182,9 @@ class Context:
 
     def set_briggs(self, slot, v, l, d, s):
         self._ck(self._f("tables_set_briggs")(self._h, C.c_int(slot), C.c_double(v), C.c_double(l), C.c_double(d), C.c_double(s)))
+
+    def set_briggs_ss(self, slot, d, s5, s3, l5, l3):
+        self._ck(self._f("tables_set_briggs_ss")(self._h, C.c_int(slot), C.c_double(d), C.c_double(s5), C.c_double(s3), C.c_double(l5), C.c_double(l3)))
 
     def clear_damage(self, slot):
         self._ck(self._f("tables_clear_damage")(self._h, C.c_int(slot)))

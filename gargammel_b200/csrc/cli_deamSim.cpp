@@ -6,11 +6,12 @@ using namespace cli;
 int main(int argc, char** argv) {
     std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix;
     bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false, putDeamInName = false;
+    bool useBriggsss = false; double s5p = 0, s3p = 0, l5p = 0, l3p = 0;            // -damagess, deamSim.cpp:310-340
     double v = 0, l = 0, d = 0, s = 0; uint64_t seed = 0;
     const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds deamination according to a certain model (B200 build)\n\n" +
         "\t\t-o\t[fasta out]\t\t\tWrite fasta output as a zipped fasta\n\t\t-last\t\t\t\t\tdo not use the last matrix row beyond the matrix\n\t\t--seed\t[int]\n\n" +
         "\t\t-mapdamage  [mis.txt] [protocol]\n\t\t-profile  [prof file prefix]\n\t\t-matfile  [matrix file prefix]\n\t\t-mat      [single|double]\n\t\t-damage     [v,l,d,s]\n" +
-        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\tNot in this build: -b -u -damagess -matfilemeth -matfilenonmeth\n";
+        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\tNot in this build: -b -u -matfilemeth -matfilenonmeth\n";
     if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // deamSim.cpp:199-207
     for (int i = 1; i < argc - 1; i++) {                                            // deamSim.cpp:213-378
         const std::string a = argv[i];
@@ -39,16 +40,31 @@ int main(int argc, char** argv) {
             if (s < 0 || s > 1) return die("single-strand deamination prob. must be between 0 and 1, entered:" + t[3]);
             continue;
         }
+        if (a == "-damagess") {                                                     // deamSim.cpp:310-340 (hidden in the reference's usage text)
+            const std::string p = argv[++i]; useBriggsss = true;
+            std::vector<std::string> t = ggh::all_tokens(p, ',');
+            if (t.size() != 5) return die("Specify 4 comma-separated values for the Briggs model, you entered:" + p);          // (sic) :314-316
+            d = to_d(t[0].c_str(), "-damagess"); s5p = to_d(t[1].c_str(), "-damagess"); s3p = to_d(t[2].c_str(), "-damagess");
+            l5p = to_d(t[3].c_str(), "-damagess"); l3p = to_d(t[4].c_str(), "-damagess");
+            if (l5p < 0 || l5p > 1) return die("Geometric parameter for overhang must be between 0 and 1, entered:" + t[3]);
+            if (l3p < 0 || l3p > 1) return die("Geometric parameter for overhang must be between 0 and 1, entered:" + t[4]);
+            if (d < 0 || d > 1) return die("double-strand deamination prob. must be between 0 and 1, entered:" + t[0]);
+            if (s5p < 0 || s5p > 1) return die("single-strand deamination prob. must be between 0 and 1, entered:" + t[1]);
+            if (s3p < 0 || s3p > 1) return die("single-strand deamination prob. must be between 0 and 1, entered:" + t[2]);
+            continue;
+        }
         if (a == "-o") { outGz = argv[++i]; continue; }
         if (a == "-last") { lastRowMatrix = false; continue; }
         if (a == "-v") continue;                                                    // per-read log on stderr: not produced
         if (a == "-name") { putDeamInName = true; continue; }                        // deamSim.cpp:342-345
-        if (a == "-b" || a == "-u" || a == "-damagess" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        if (a == "-b" || a == "-u" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
         return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377
     }
     const bool mapd = !mapdamageFile.empty();
     if (useBriggs && (matrixSpecified || mapd)) return die("Error: cannot specify both a file and Briggs parameter model");        // :380-383
-    if (!useBriggs && !matrixSpecified && matrixFile.empty() && !mapd && profFile.empty())
+    if (useBriggsss && (matrixSpecified || mapd)) return die("Error: cannot specify both a file and Briggs parameter model");      // :385-388
+    if (useBriggs && useBriggsss) return die("Error: cannot specify both a file and Briggs parameter model");                      // :390-393
+    if (!useBriggs && !useBriggsss && !matrixSpecified && matrixFile.empty() && !mapd && profFile.empty())
         return die("Please specify the matrix to use or use the Briggs parameter model");                                          // :395-405
     if (!profFile.empty() && !matrixFile.empty()) return die("Please specify damage profile or substitution matrix");              // :407-412
     if (!seedSpecified) seed = time_seed();
@@ -57,7 +73,8 @@ int main(int argc, char** argv) {
     gg_ctx* ctx = NULL;
     if (open_ctx(seed, &ctx)) return 1;
     std::string err; ggh::Rates s5, s3;
-    if (useBriggs) { if (gg_tables_set_briggs(ctx, 0, v, l, d, s) != GG_OK) return gg_fail(ctx, "-damage"); }
+    if (useBriggsss) { if (gg_tables_set_briggs_ss(ctx, 0, d, s5p, s3p, l5p, l3p) != GG_OK) return gg_fail(ctx, "-damagess"); }   // checked first, like :1337
+    else if (useBriggs) { if (gg_tables_set_briggs(ctx, 0, v, l, d, s) != GG_OK) return gg_fail(ctx, "-damage"); }
     else if (mapd) {                                                                // deamSim.cpp:453-668
         if (!ggh::load_mapdamage(mapdamageFile, s5, s3, err)) return die(err);
         if (gg_tables_set_singledouble(ctx, 0, mapdamageProtocol == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mapdamage");

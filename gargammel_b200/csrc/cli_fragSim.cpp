@@ -10,6 +10,7 @@ int main(int argc, char** argv) {
     bool uniqTags = false, tagb = false, gcBiasB = false; double gcBias = 0;
     std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
+    bool circ = false; std::string circName;                                        // fragSim.cpp:388-389
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
         " aDNA fragments according to a certain distribution (B200 build)\n\n " + argv[0] + " [options]  [chromosome fasta] \n\n" +
         "\t\t-n\t[number]\t\t\tGenerate [number] fragments (default: 10)\n\t\t--norev\t\t\t\t\tDo not reverse complement (default: rev. comp half of seqs.)\n" +
@@ -21,7 +22,8 @@ int main(int argc, char** argv) {
         "\t\t--loc\t[float] --scale\t[float]\tlog-normal fragment lengths\n" +
         "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
         "\t\t-uniq\t\t\t\t\tMake the fragment names unique by appending a counter (host-side pass, like the reference)\n" +
-        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\tNot in this build: --circ --case --fq --trim5p -b -u\n";
+        "\t\t--circ\t[REF NAME]\t\t\tAssume [REF NAME] is circular\n" +
+        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\tNot in this build: --case --fq --trim5p -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -42,7 +44,8 @@ int main(int argc, char** argv) {
         if (a == "--comp") { compFile = argv[++i]; continue; }
         if (a == "--dist") { distFromEnd = (int)to_ll(argv[++i], "--dist"); continue; }
         if (a == "-gc") { gcBias = to_d(argv[++i], "-gc"); gcBiasB = true; continue; }      // fragSim.cpp:589-594
-        if (a == "--circ" || a == "--trim5p" || a == "-b")
+        if (a == "--circ") { circ = true; circName = argv[++i]; continue; }             // fragSim.cpp:553-557
+        if (a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
         if (a == "--case" || a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
@@ -73,10 +76,16 @@ int main(int argc, char** argv) {
     if (!ggh::load_genome(inFile, G, err)) return die(err);
     std::cerr << "Mapped " << inFile << " into memory" << std::endl;                // fragSim.cpp:1149
 
+    int circChr = -1;
+    if (circ) {                                                                     // fragSim.cpp:1171-1178
+        for (size_t i = 0; i < G.fai.size() && circChr < 0; i++) if (G.fai[i].name == circName) circChr = (int)i;
+        if (circChr < 0) return die("ERROR: Cannot find chromosome " + circName + " which is specified via --circ");
+    }
+
     gg_ctx* ctx = NULL;
     if (open_ctx(seed, &ctx)) return 1;
     int gid = -1;
-    if (ggh::upload_genome(ctx, G, &gid) != GG_OK) return gg_fail(ctx, "genome upload");
+    if (ggh::upload_genome(ctx, G, &gid, circChr) != GG_OK) return gg_fail(ctx, "genome upload");
     std::vector<uint8_t>().swap(G.bytes);
     const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || specifiedLoc) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
     if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), sizeFragments, minLen, maxLen) != GG_OK) return gg_fail(ctx, "size tables");

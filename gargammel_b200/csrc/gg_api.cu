@@ -41,12 +41,13 @@ struct HostGenome {
     uint64_t G, n_units;
     uint32_t* d_seq2; uint32_t* d_nmask; size_t seq2_bytes, nmask_bytes;
     int first_contig;
+    int circ_sorted; uint32_t wrap_s0; uint64_t wrap_gbase;     // --circ: index of the circular contig in `contigs` (-1 none) + its wrap image
 };
 struct HostDamage {
     int mode, rows5, rows3, clamp_last;
-    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd;
+    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd, K3;
     DBuf d_thr, d_sd5, d_sd3, d_geoL, d_geoV;
-    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0) {}
+    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0), K3(0) {}
 };
 
 const int GEO_TABLE = 4096;          // geometric inverse-CDF table length (overhangs / nick position)
@@ -158,6 +159,7 @@ int sync_contig_tables(gg_ctx* ctx) {
             names.insert(names.end(), c.name.begin(), c.name.end());
         }
         GenomeDev d; d.seq2 = H.d_seq2; d.nmask = H.d_nmask; d.G = H.G; d.first_contig = H.first_contig; d.n_contigs = (int)H.contigs.size();
+        d.circ_contig = H.circ_sorted >= 0 ? H.first_contig + H.circ_sorted : -1; d.wrap_s0 = H.wrap_s0; d.wrap_gbase = H.wrap_gbase;
         gd.push_back(d);
     }
     ctx->n_contigs_total = (int)cum_end.size();
@@ -209,6 +211,8 @@ void fill_damage_dev(const HostDamage& H, ggd::DamageDev* D) {
     D->mode = H.mode; D->rows5 = H.rows5; D->rows3 = H.rows3; D->clamp_last = H.clamp_last;
     D->thr = H.d_thr.as<uint4>(); D->sd5 = H.d_sd5.as<uint32_t>(); D->sd3 = H.d_sd3.as<uint32_t>();
     D->Ks = H.Ks; D->Kd = H.Kd; D->geoL = H.d_geoL.as<uint32_t>(); D->geoV = H.d_geoV.as<uint32_t>(); D->n_geo = GEO_TABLE;
+    // -damagess keeps its 3' overhang table where plain Briggs keeps the nick table
+    D->K3 = H.mode == GG_DMG_BRIGGS_SS ? H.K3 : H.Ks; D->geoL3 = H.mode == GG_DMG_BRIGGS_SS ? D->geoV : D->geoL;
 }
 
 int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
@@ -355,9 +359,12 @@ double gg_last_device_ms(gg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 
 // ------------------------------------------------------------------------------------------------ genome
 int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int* genome_id_out) {
-    if (!ctx || !fasta || !fai || n_chr <= 0) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_upload: bad arguments") : GG_ERR_ARG;
+    return gg_genome_upload_circ(ctx, fasta, n, fai, n_chr, -1, genome_id_out);
+}
+int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int circ_chr, int* genome_id_out) {
+    if (!ctx || !fasta || !fai || n_chr <= 0 || circ_chr >= n_chr) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_upload: bad arguments") : GG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    HostGenome H; H.d_seq2 = H.d_nmask = nullptr; H.first_contig = 0;
+    HostGenome H; H.d_seq2 = H.d_nmask = nullptr; H.first_contig = 0; H.circ_sorted = -1; H.wrap_s0 = 0; H.wrap_gbase = 0;
     std::vector<HostContig> cs;
     for (int i = 0; i < n_chr; i++) {
         HostContig c; c.name = fai[i].name ? fai[i].name : "";
@@ -379,11 +386,26 @@ int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_e
         H.fai2sorted[c.fai_index] = (int)H.contigs.size();
         H.contigs.push_back(c);
     }
+    // --circ (fragSim.cpp:1171-1178): the named contig (a duplicate name resolves to the map's entry, i.e. the first) gets a
+    // wrap image behind the last contig: K bases before its last base, then its first K+1 bases, K = longest window
+    int wrap_desc = -1; uint32_t wrap_keff = 0, wrap_srclen = 0, wrap_len = 0;
+    if (circ_chr >= 0) {
+        for (size_t i = 0; i < H.contigs.size(); i++) if (H.contigs[i].name == (fai[circ_chr].name ? fai[circ_chr].name : "")) H.circ_sorted = (int)i;
+        if (H.circ_sorted < 0) return ctx->fail(GG_ERR_ARG, "gg_genome_upload_circ: circular contig not found");
+        const HostContig& cc = H.contigs[H.circ_sorted];
+        const uint32_t K = (uint32_t)(MAX_FRAG_LEN + 2 * GG_MAX_COMP_DIST + 1);
+        wrap_srclen = (uint32_t)cc.len; wrap_keff = std::min<uint32_t>(K, wrap_srclen - 1); wrap_len = wrap_keff + K + 1;
+        H.wrap_s0 = wrap_srclen - 1 - wrap_keff; H.wrap_gbase = gb; gb += ((uint64_t)wrap_len + 63) / 64 * 64;
+    }
     H.G = G; H.n_units = gb / 32 + 2;
     // device: raw FASTA (temporary), contig descriptors (temporary), packed arrays (resident)
-    const size_t nc = H.contigs.size();
+    const size_t nc = H.contigs.size() + (circ_chr >= 0 ? 1 : 0);
     std::vector<uint64_t> off(nc), gbase(nc); std::vector<uint32_t> len(nc); std::vector<int32_t> blen(nc), llen(nc);
-    for (size_t i = 0; i < nc; i++) { off[i] = H.contigs[i].offset; gbase[i] = H.contigs[i].gbase; len[i] = (uint32_t)H.contigs[i].len; blen[i] = H.contigs[i].blen; llen[i] = H.contigs[i].llen; }
+    for (size_t i = 0; i < H.contigs.size(); i++) { off[i] = H.contigs[i].offset; gbase[i] = H.contigs[i].gbase; len[i] = (uint32_t)H.contigs[i].len; blen[i] = H.contigs[i].blen; llen[i] = H.contigs[i].llen; }
+    if (circ_chr >= 0) {
+        const HostContig& cc = H.contigs[H.circ_sorted];
+        wrap_desc = (int)nc - 1; off[nc - 1] = cc.offset; gbase[nc - 1] = H.wrap_gbase; len[nc - 1] = wrap_len; blen[nc - 1] = cc.blen; llen[nc - 1] = cc.llen;
+    }
     // staging (reused across uploads): raw FASTA bytes + contig descriptors
     const size_t desc_bytes = nc * (8 + 8 + 4 + 4 + 4) + 64;
     CK(ctx->d_tmp_fa.ensure(n + 16));
@@ -403,7 +425,7 @@ int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_e
     TRY(cudaMemcpyAsync(d_bl, blen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_ll, llen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     // every unit (incl. the guard units in front and the slack behind) is written by the pack kernel
-    TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, nullptr, (int)nc, H.n_units, H.d_seq2, H.d_nmask, ctx->st));
+    TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, (int)nc, wrap_desc, wrap_keff, wrap_srclen, H.n_units, H.d_seq2, H.d_nmask, ctx->st));
     TRY(cudaMemsetAsync(H.d_seq2 + H.n_units * 2, 0, 16, ctx->st));
     TRY(cudaMemsetAsync(H.d_nmask + H.n_units, 0xFF, 16, ctx->st));
     TRY(cudaStreamSynchronize(ctx->st));
@@ -570,6 +592,25 @@ int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, do
     if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
     return upload_vec(ctx, H.d_geoV, H.geoV);
 }
+int gg_tables_set_briggs_ss(gg_ctx* ctx, int slot, double d, double s5, double s3, double l5, double l3) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_tables_set_briggs_ss: bad slot");
+    if (!(l5 >= 0 && l5 <= 1) || !(l3 >= 0 && l3 <= 1)) return ctx->fail(GG_ERR_ARG, "Geometric parameter for overhang must be between 0 and 1");   // deamSim.cpp:329-334
+    if (!(d >= 0 && d <= 1)) return ctx->fail(GG_ERR_ARG, "double-strand deamination prob. must be between 0 and 1");
+    if (!(s5 >= 0 && s5 <= 1) || !(s3 >= 0 && s3 <= 1)) return ctx->fail(GG_ERR_ARG, "single-strand deamination prob. must be between 0 and 1");
+    CK(cudaSetDevice(ctx->device));
+    HostDamage& H = ctx->dmg[slot];
+    H.mode = GG_DMG_BRIGGS_SS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
+    H.Ks = thr_lt(s5); H.K3 = thr_lt(s3); H.Kd = thr_lt(d);
+    H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
+    double q = 1.0; uint32_t prev = 0;                       // geometric_distribution<int>(l5) / (l3), deamSim.cpp:325-326,1342-1343
+    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l5); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoL[k] = t; prev = t; }
+    q = 1.0; prev = 0;
+    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l3); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoV[k] = t; prev = t; }
+    int rc;
+    if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
+    return upload_vec(ctx, H.d_geoV, H.geoV);
+}
 int gg_tables_set_composition(gg_ctx* ctx, int slot, int dist, const double* s5p, const double* s5m, const double* s3p, const double* s3m) {
     if (!ctx) return GG_ERR_ARG;
     if (slot < 0 || slot >= GG_MAX_COMP_SLOTS || dist < 1 || dist > GG_MAX_COMP_DIST || !s5p || !s5m || !s3p || !s3m) return ctx->fail(GG_ERR_ARG, "gg_tables_set_composition: bad arguments");
@@ -628,6 +669,7 @@ int gg_tables_set_gcbias(gg_ctx* ctx, int slot, int genome_id, int comp_dist, do
     CK(cudaMemsetAsync(d_sums, 0, 24, ctx->st));
     const HostGenome& HG = ctx->genomes[genome_id];
     GenomeDev G; G.seq2 = HG.d_seq2; G.nmask = HG.d_nmask; G.G = HG.G; G.first_contig = HG.first_contig; G.n_contigs = (int)HG.contigs.size();
+    G.circ_contig = -1; G.wrap_s0 = 0; G.wrap_gbase = 0;       // the probe loop has no --circ branch (fragSim.cpp:1214-1225)
     ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
     CK(launch_gc_probe(G, ctx->d_cum_end.as<uint64_t>(), ctx->d_gbase.as<uint64_t>(), ctx->d_clen.as<uint32_t>(), comp_dist, key, d_sums, ctx->st));
     unsigned long long sums[3];
@@ -786,7 +828,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.size_thr = ctx->d_size_thr.as<uint32_t>(); P.size_len = ctx->d_size_len.as<int32_t>();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) fill_damage_dev(ctx->dmg[s], &P.dmg[s]);
     for (int s = 0; s < GG_MAX_GC_SLOTS; s++) {
-        if (ctx->gc[s].on && ctx->gc[s].wmax < Lmax + 2 * ctx->gc[s].dist) { int rc2 = build_gc_table(ctx, s, Lmax + 2 * ctx->gc[s].dist); if (rc2) return rc2; }
+        if (ctx->gc[s].on && ctx->gc[s].wmax < Lmax + 2 * ctx->gc[s].dist + 1) { int rc2 = build_gc_table(ctx, s, Lmax + 2 * ctx->gc[s].dist + 1); if (rc2) return rc2; }   // +1: the --circ corner window
         P.gc[s].thr = ctx->gc[s].d_thr.as<uint32_t>(); P.gc[s].wmax = ctx->gc[s].wmax; P.gc[s].on = ctx->gc[s].on ? 1 : 0;
     }
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) { P.comp[s].dist = ctx->comp[s].dist; P.comp[s].tab = ctx->comp[s].d_tab.as<double>(); P.comp[s].maxP = ctx->comp[s].maxP; P.comp[s].maxM = ctx->comp[s].maxM; }

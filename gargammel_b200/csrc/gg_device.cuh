@@ -84,6 +84,9 @@ struct DamageDev {
     const uint32_t* sd5; const uint32_t* sd3;
     // BRIGGS: Ks,Kd strict thresholds (u31 < K); geometric tables (u31 < cdf_thr[k] first k) of n_geo entries
     uint32_t Ks, Kd; const uint32_t* geoL; const uint32_t* geoV; int n_geo;
+    // BRIGGS_SS (-damagess d,s5,s3,l5,l3): Ks = 5' overhang rate, K3 = 3' overhang rate, geoL = 5' lengths, geoL3 = 3' lengths
+    // (plain Briggs: K3 == Ks, geoL3 == geoL)
+    uint32_t K3; const uint32_t* geoL3;
 };
 
 // first k with u < thr[k], thr ascending; returns n if none
@@ -130,7 +133,7 @@ struct BriggsHdr { int o5, o3, nick; };
 __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const uint4& h) {
     BriggsHdr B;
     B.o5 = first_below_gallop(D.geoL, D.n_geo, h.x >> 1);
-    B.o3 = first_below_gallop(D.geoL, D.n_geo, h.y >> 1);
+    B.o3 = first_below_gallop(D.geoL3, D.n_geo, h.y >> 1);
     B.nick = first_below_gallop(D.geoV, D.n_geo, h.z >> 1);
     return B;
 }
@@ -138,10 +141,19 @@ __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const ui
 //   C->T at s  if all single-stranded, or inside the 5' overhang            (:1486-1494, :1513-1523, :1557-1567)
 //   G->A at s  inside the 3' overhang                                       (:1527-1537, :1571-1581)
 //   G->A at d  in the double-stranded part at/after the nick, C->T at d before it   (:1542-1548, :1586-1592)
+//   -damagess (mode 5, deamSim.cpp:1337-1468): C->T only; 5' overhang at s5, 3' overhang at s3, double-stranded part at d; a base
+//   inside both overhangs takes the nearer end (i < int(len*0.5) -> 5', :1351-1371).  SS = false compiles that model out.
+template <bool SS>
 __device__ __forceinline__ uint32_t dmg_briggs_base(const DamageDev& D, const BriggsHdr& B, int i, int L, uint32_t b, uint32_t x) {
     const uint32_t u = x >> 1;
-    const bool ss5 = (B.o5 + B.o3 >= L) || (i + 1 <= B.o5);
-    const bool ss3 = !ss5 && (L - i <= B.o3);
+    const bool in5 = i + 1 <= B.o5, in3 = L - i <= B.o3;
+    if (SS && D.mode == 5) {
+        const bool s5 = (in5 && in3) ? (i < (L >> 1)) : in5;
+        const uint32_t K = s5 ? D.Ks : in3 ? D.K3 : D.Kd;
+        return (b == 1u && u < K) ? 3u : b;
+    }
+    const bool ss5 = (B.o5 + B.o3 >= L) || in5;
+    const bool ss3 = !ss5 && in3;
     const bool ct = ss5 || (!ss3 && B.nick > i);
     const uint32_t K = (ss5 || ss3) ? D.Ks : D.Kd;
     const uint32_t from = ct ? 1u : 2u, to = ct ? 3u : 0u;

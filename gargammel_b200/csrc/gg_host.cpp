@@ -445,10 +445,10 @@ bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err)
     for (size_t i = 0; i < g.fai.size(); i++) g.total_len += (uint64_t)g.fai[i].len;
     return true;
 }
-int upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out) {
+int upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out, int circ_chr) {
     std::vector<gg_fai_entry> f(g.fai.size());
     for (size_t i = 0; i < f.size(); i++) { f[i].name = g.fai[i].name.c_str(); f[i].len = g.fai[i].len; f[i].offset = g.fai[i].offset; f[i].line_blen = g.fai[i].line_blen; f[i].line_len = g.fai[i].line_len; }
-    return gg_genome_upload(ctx, g.bytes.data(), g.bytes.size(), f.data(), (int)f.size(), id_out);
+    return gg_genome_upload_circ(ctx, g.bytes.data(), g.bytes.size(), f.data(), (int)f.size(), circ_chr, id_out);
 }
 
 } // namespace ggh

@@ -69,7 +69,7 @@ bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vec
 // ---- one genome file ready for upload ----
 struct GenomeFile { std::string path; std::vector<uint8_t> bytes; std::vector<FaiEntry> fai; uint64_t total_len; };
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err);
-int  upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out);
+int  upload_genome(gg_ctx* ctx, const GenomeFile& g, int* id_out, int circ_chr = -1);   // circ_chr: fai index of the --circ contig
 
 } // namespace ggh
 

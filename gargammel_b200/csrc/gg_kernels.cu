@@ -21,11 +21,13 @@ __device__ __forceinline__ unsigned long long warp_sum_u64_early(unsigned long l
 }
 
 // ======================================================================================= pack
-// one thread per 32 bases of the packed base space (2 seq2 words + 1 mask word)
+// one thread per 32 bases of the packed base space (2 seq2 words + 1 mask word).  Descriptor `wrap_desc` (if >= 0) is the
+// --circ wrap image of a contig of `wrap_srclen` bases: image base j is contig base (srclen-1-keff+j) for j < keff and
+// (j-keff) behind it (fragSim.cpp:1413-1422: temp1 stops one base short of the contig end, temp2 restarts at 0).
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ fasta, uint64_t n,
         const uint64_t* __restrict__ c_off, const uint32_t* __restrict__ c_len,
         const int32_t* __restrict__ c_blen, const int32_t* __restrict__ c_llen,
-        const uint64_t* __restrict__ c_gbase, int n_contigs, uint64_t n_units,
+        const uint64_t* __restrict__ c_gbase, int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
         uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
@@ -39,20 +41,37 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         const uint64_t len = c_len[c];
         if (local < len) {
             const uint64_t blen = (uint64_t)c_blen[c], llen = (uint64_t)c_llen[c];
-            uint64_t line = local / blen, col = local % blen;
-            uint64_t pos = c_off[c] + line * llen + col;     // fetchSeq, fragSim.cpp:312-314
             m = 0;
-            for (int t = 0; t < 32; t++) {
-                uint32_t code = 0, bad = 1;
-                if (local + t < len) {
-                    const uint8_t ch = pos < n ? upper(fasta[pos]) : 0;   // toupper, fragSim.cpp:315
-                    const int cd = ascii2code(ch);
-                    if (cd >= 0) { code = (uint32_t)cd; bad = 0; }
-                    pos++; col++;
-                    if (col == blen) { col = 0; pos += llen - blen; }
+            if (c == wrap_desc) {
+                for (int t = 0; t < 32; t++) {
+                    uint32_t code = 0, bad = 1;
+                    const uint64_t j = local + t;
+                    if (j < len) {
+                        const uint64_t src = j < wrap_keff ? (uint64_t)wrap_srclen - 1 - wrap_keff + j : j - wrap_keff;
+                        if (src < wrap_srclen) {
+                            const uint64_t pos = c_off[c] + src / blen * llen + src % blen;
+                            const int cd = ascii2code(pos < n ? upper(fasta[pos]) : 0);
+                            if (cd >= 0) { code = (uint32_t)cd; bad = 0; }
+                        }
+                    }
+                    if (t < 16) w0 |= code << (2 * t); else w1 |= code << (2 * (t - 16));
+                    m |= bad << t;
                 }
-                if (t < 16) w0 |= code << (2 * t); else w1 |= code << (2 * (t - 16));
-                m |= bad << t;
+            } else {
+                uint64_t line = local / blen, col = local % blen;
+                uint64_t pos = c_off[c] + line * llen + col;     // fetchSeq, fragSim.cpp:312-314
+                for (int t = 0; t < 32; t++) {
+                    uint32_t code = 0, bad = 1;
+                    if (local + t < len) {
+                        const uint8_t ch = pos < n ? upper(fasta[pos]) : 0;   // toupper, fragSim.cpp:315
+                        const int cd = ascii2code(ch);
+                        if (cd >= 0) { code = (uint32_t)cd; bad = 0; }
+                        pos++; col++;
+                        if (col == blen) { col = 0; pos += llen - blen; }
+                    }
+                    if (t < 16) w0 |= code << (2 * t); else w1 |= code << (2 * (t - 16));
+                    m |= bad << t;
+                }
             }
         }
     }
@@ -61,11 +80,11 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
 
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
-                               const uint64_t*, int n_contigs, uint64_t n_units,
+                               int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st) {
     if (n_units == 0) return cudaSuccess;
     const uint64_t blocks = (n_units + 255) / 256;
-    k_pack_genome<<<(unsigned)blocks, 256, 0, st>>>(fasta, n, c_off, c_len, c_blen, c_llen, c_gbase, n_contigs, n_units, seq2, nmask);
+    k_pack_genome<<<(unsigned)blocks, 256, 0, st>>>(fasta, n, c_off, c_len, c_blen, c_llen, c_gbase, n_contigs, wrap_desc, wrap_keff, wrap_srclen, n_units, seq2, nmask);
     return cudaGetLastError();
 }
 
@@ -303,7 +322,7 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
             }
             Wn |= nb << (8 * q);
         }
-    } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i
+    } else if (mode == 2 || (DMODE == 0 && mode == 5)) {  // Briggs / -damagess: header block 0, per-base word 4+i
         BriggsHdr B; B.o5 = (int)(bh & 0xFFFFu); B.o3 = (int)((bh >> 16) & 0xFFFFu); B.nick = (int)((bh >> 32) & 0xFFFFu);   // drawn once per fragment in pass A
 #pragma unroll 1
         for (int q = 0; q < nq; q++) {
@@ -311,7 +330,7 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
             const uint32_t Wq = W >> (8 * q);
             uint32_t nb = 0;
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
+            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base<DMODE == 0>(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
             Wn |= nb << (8 * q);
         }
     } else {                                             // single / double: two passes, two streams
@@ -429,10 +448,18 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 ci = G.first_contig + a;
                 const uint64_t clen = __ldg(P.ctab.len + ci);
                 idx = cp - (__ldg(cum + a) - clen);                                    // coord - startIndexChr, fragSim.cpp:1404
-                if (idx < (uint64_t)d || idx + (uint64_t)L + (uint64_t)d > clen) continue;   // outside [start+d, end-d+1], or run-off past the contig end (always rejected, fragSim.cpp:1472)
+                if (idx < (uint64_t)d) continue;                                       // outside [start+d, end-d+1]
                 gpos = __ldg(P.ctab.gbase + ci) + idx;
+                int xtra = 0;
+                if (idx + (uint64_t)L + (uint64_t)d > clen) {                          // run-off past the contig end: always rejected (fragSim.cpp:1472) ...
+                    const GenomeDev* Gc = P.genomes + rg->genome;                      // (rare branch: fields re-read here, not kept live)
+                    if (ci != __ldg(&Gc->circ_contig) || __ldg(cum + a) + 1 < (uint64_t)(L + d)) continue;   // (u64 wrap of end-length-d+1, fragSim.cpp:1410)
+                    uint64_t s = idx - (uint64_t)d;                                    // ... except on the --circ contig (fragSim.cpp:1412-1426)
+                    if (s >= clen) { s = clen - 1; xtra = 1; }                         // coord == end+1 (d == 0): temp1 = "" and temp2 has length+1 bases
+                    gpos = __ldg(&Gc->wrap_gbase) + (s - (uint64_t)__ldg(&Gc->wrap_s0)) + (uint64_t)d;
+                }
                 if (L + 2 * d > 0) {                                                   // isResolvedDNAstring over the window incl. the flanks, fragSim.cpp:333-339,1472
-                    const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1;
+                    const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1 + (uint64_t)xtra;
                     const uint64_t w0 = s0 >> 5, w1 = e >> 5;
                     uint32_t any = 0;
 #pragma unroll 1
@@ -446,12 +473,13 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 }
                 plus = P.norev ? 1u : (x.y & 1u);                                      // randomBool, fragSim.cpp:1462-1467
                 if (rg->gc >= 0) {                                                     // -gc survival (fragSim.cpp:1509-1534, repeated :1548-1576 without --comp)
-                    const int Wn = L + 2 * d;
+                    const int Wn = L + 2 * d + xtra;
                     const uint32_t thr = __ldg(P.gc[rg->gc].thr + (Wn * (Wn + 1) / 2 + gc_count(G.seq2, gpos - (uint64_t)d, Wn)));
                     const uint4 y = rng_block(P.key, id, attempt, ST_FRAG3);
                     if ((y.x >> 1) >= thr) continue;
                     if (!d && (y.y >> 1) >= thr) continue;
                 }
+                if (xtra && !plus) gpos++;                                             // reverseComplement of the length+1 window, then substr(0,length) (fragSim.cpp:1484-1498)
                 if (d && !comp_accept(P, P.comp[rg->comp], G.seq2, gpos, L, plus, id, attempt)) continue;   // --comp, fragSim.cpp:1609-1759
                 ok = true; break;
             }
@@ -470,7 +498,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             s_meta[lane] = META(L, plus, rg->slot, rg->genome);
             s_hdr[lane] = (uint16_t)hdr;
             s_idx[lane] = idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
-            if (DMODE != 1 && emit != 0 && rg->slot >= 0 && (DMODE == 2 || P.dmg[rg->slot].mode == 2)) {   // Briggs: overhangs + nick, once per fragment (deamSim.cpp:1478-1507)
+            if (DMODE != 1 && emit != 0 && rg->slot >= 0 && (DMODE == 2 || P.dmg[rg->slot].mode == 2 || P.dmg[rg->slot].mode == 5)) {   // Briggs / -damagess: overhangs + nick, once per fragment (deamSim.cpp:1478-1507)
                 const BriggsHdr B = dmg_briggs_hdr(P.dmg[rg->slot], rng_block(P.key, id, 0u, ST_DEAM));
                 s_bh[lane] = (unsigned long long)B.o5 | ((unsigned long long)B.o3 << 16) | ((unsigned long long)B.nick << 32);
             }
@@ -818,14 +846,14 @@ __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t
         for (uint64_t i = p.ids + lane; i < p.ss; i += 32) out[i] = R.in[i];          // ID line + '\n' unchanged (deamSim.cpp:2038)
         const int L = (int)(p.se - p.ss);
         BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (has_damage && D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        if (has_damage && (D.mode == 2 || D.mode == 5)) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         for (int i = lane; i < L; i += 32) {
             uint8_t c = upper(R.in[p.ss + i]);                                         // toupper, deamSim.cpp:1319-1321
             const int code = ascii2code(c);
             if (has_damage && code >= 0) {                                             // unresolved bases are never touched (deamSim.cpp:1795)
                 uint32_t nb = (uint32_t)code;
                 if (D.mode == 1) nb = dmg_matrix_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i));
-                else if (D.mode == 2) nb = dmg_briggs_base(D, B, i, L, nb, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
+                else if (D.mode == 2 || D.mode == 5) nb = dmg_briggs_base<true>(D, B, i, L, nb, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
                 else if (D.mode == 3 || D.mode == 4) nb = dmg_sd_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i), rng_word(key, id, ST_DEAM2, (uint32_t)i));
                 c = code2ascii(nb);
             }
@@ -844,8 +872,8 @@ __device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHd
     if (D.mode == 1) {
         e.nb = dmg_matrix_base(D, i, L, b, rng_word(key, id, ST_DEAM, (uint32_t)i));
         if (e.nb != b) e.v0 = (i < (L >> 1)) ? i + 1 : -(L - i);
-    } else if (D.mode == 2) {
-        e.nb = dmg_briggs_base(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
+    } else if (D.mode == 2 || D.mode == 5) {
+        e.nb = dmg_briggs_base<true>(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
         if (e.nb != b) e.v0 = i + 1;
     } else {
         const uint32_t x1 = rng_word(key, id, ST_DEAM, (uint32_t)i), x2 = rng_word(key, id, ST_DEAM2, (uint32_t)i);
@@ -871,7 +899,7 @@ __global__ void __launch_bounds__(256) k_deam_name_sizes(const RecStream R, cons
         if (lane == 0 && (p.ide <= p.ids || R.in[p.ids] != '>')) atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
         const int L = (int)(p.se - p.ss);
         BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        if (D.mode == 2 || D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         unsigned long long txt = 0;
         for (int i = lane; i < L; i += 32) {
             const int code = ascii2code(upper(R.in[p.ss + i]));
@@ -894,7 +922,7 @@ __global__ void __launch_bounds__(256) k_deam_name_records(const RecStream R, co
         uint8_t* o = out + out_off[r];
         for (uint64_t i = lane; i < idlen; i += 32) o[i] = R.in[p.ids + i];
         BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        if (D.mode == 2 || D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         const uint64_t total = out_off[r + 1] - out_off[r];                       // sizes array has a sentinel entry
         uint8_t* seqo = o + (total - (uint64_t)L - 1);                            // sequence start
         const bool any = total > idlen + 1 + (uint64_t)L + 1;

@@ -12,6 +12,11 @@ struct GenomeDev {           // one uploaded FASTA file, packed (DESIGN.md "Data
     uint64_t G;              // sum of contig lengths = size of the sampling space (fragSim.cpp:1163)
     int first_contig;        // index of this genome's first contig in the (name-sorted) contig table
     int n_contigs;
+    // fragSim --circ (fragSim.cpp:1407-1426): windows that run off the circular contig are gathered from a "wrap image"
+    // = contig[wrap_s0 .. len-1) ++ contig[0 ..) packed behind the last contig (the reference drops the contig's last base there)
+    int circ_contig;         // absolute index in the contig table, -1 = none
+    uint32_t wrap_s0;
+    uint64_t wrap_gbase;
 };
 struct ContigTab {           // struct-of-arrays over all contigs of all genomes
     const uint64_t* cum_end; // inclusive running end within its genome, name-sorted order (fragSim.cpp:1160-1163)
@@ -96,7 +101,7 @@ enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
 // ---- launchers (gg_kernels.cu) ----
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
-                               const uint64_t* unit_start, int n_contigs, uint64_t n_units,
+                               int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
 cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, ggd::Key key,
                             unsigned long long* sums /* [0]=sum gc, [1]=sum gc^2, [2]=give-ups */, cudaStream_t st);

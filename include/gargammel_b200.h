@@ -54,7 +54,8 @@ typedef enum gg_damage_mode {
     GG_DMG_MATRIX = 1,   /* -matfile / -profile    deamSim.cpp:1794-1930 */
     GG_DMG_BRIGGS = 2,   /* -damage v,l,d,s        deamSim.cpp:1477-1613 */
     GG_DMG_SINGLE = 3,   /* -mat single / -mapdamage f single  deamSim.cpp:1941-1971 */
-    GG_DMG_DOUBLE = 4    /* -mat double / -mapdamage f double  deamSim.cpp:1973-2002 */
+    GG_DMG_DOUBLE = 4,   /* -mat double / -mapdamage f double  deamSim.cpp:1973-2002 */
+    GG_DMG_BRIGGS_SS = 5 /* -damagess d,s5,s3,l5,l3 (single-strand libraries)  deamSim.cpp:310-340,1337-1468 */
 } gg_damage_mode;
 #define GG_MAX_DAMAGE_SLOTS 4
 #define GG_MAX_COMP_SLOTS 4
@@ -127,6 +128,11 @@ void* gg_ctx_stream(gg_ctx* ctx);
  * reference's std::map (fragSim.cpp:215,1152-1166). */
 int  gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n,
                       const gg_fai_entry* fai, int n_chr, int* genome_id_out);
+/* fragSim --circ NAME (fragSim.cpp:553-556,1171-1178,1407-1426): contig fai[circ_chr] is circular.  A window that runs off its end
+ * continues at its first base; like the reference, the wrapped window skips the contig's LAST base (temp1 is one base short,
+ * fragSim.cpp:1413-1415) and the defline keeps idx and idx+len un-wrapped.  circ_chr = -1: same as gg_genome_upload. */
+int  gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n,
+                           const gg_fai_entry* fai, int n_chr, int circ_chr, int* genome_id_out);
 int  gg_genome_count(gg_ctx* ctx);
 /* drop every uploaded genome and the plan (tables stay) */
 int  gg_genome_clear(gg_ctx* ctx);
@@ -159,6 +165,9 @@ int  gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const doubl
                                 const double* sub3, int rows3);
 /* deamSim -damage v,l,d,s (deamSim.cpp:285-306,1477-1613) */
 int  gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, double s);
+/* deamSim -damagess d,s5,s3,l5,l3 (deamSim.cpp:310-340,1337-1468): C->T only; 5'/3' overhangs ~ geometric(l5)/(l3) deaminate at s5/s3,
+ * the double-stranded middle at d; a base inside both overhangs takes the nearer end */
+int  gg_tables_set_briggs_ss(gg_ctx* ctx, int slot, double d, double s5, double s3, double l5, double l3);
 int  gg_tables_clear_damage(gg_ctx* ctx, int slot);
 /* deamSim -name (deamSim.cpp:342-345,2029-2037): append "_DEAM:p1,p2,..." to the ID of damaged records; stand-alone deamSim stage only */
 int  gg_tables_set_deam_naming(gg_ctx* ctx, int put_deam_in_name);

@@ -82,12 +82,13 @@ static std::string reverseComplement(const std::string& s) {
 
 /* ------------------------------------------------------------------ state */
 struct Chr { std::string name; int64_t len; uint64_t offset; int32_t line_blen, line_len; uint64_t start, end; /* 1-based concatenated, fragSim.cpp:1160-1162 */ };
-struct Genome { std::vector<uint8_t> fasta; std::vector<Chr> chrs; /* name-sorted like std::map */ uint64_t G; };
+struct Genome { std::vector<uint8_t> fasta; std::vector<Chr> chrs; /* name-sorted like std::map */ uint64_t G; int circ; /* --circ: index in chrs, -1 none */ };
 struct Damage {
     int mode; int clamp_last;
     std::vector<double> sub5, sub3;  /* rows x 12 */
     double v, l, d, s;
-    Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0) {}
+    double s5, s3, l5, l3;           /* -damagess */
+    Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0), s5(0), s3(0), l5(0), l3(0) {}
 };
 struct Comp { int dist; std::vector<double> s5p, s5m, s3p, s3m; double maxP, maxM; Comp() : dist(0), maxP(1), maxM(1) {} };
 struct GcBias { bool on; int dist; double bias, mean, sd, maxNorm; GcBias() : on(false), dist(0), bias(0), mean(0.4), sd(0.1), maxNorm(1) {} };
@@ -114,7 +115,7 @@ struct orc_ctx {
 /* IndexedGenome::fetchSeq, fragSim.cpp:305-329 (uppercase branch).  Positions that run past the
  * file are returned as '\0' (the reference would read past the mmap: undefined). */
 static std::string fetchSeq(const Genome& g, const Chr& c, int64_t index, int n) {
-    std::string s; s.reserve(n);
+    std::string s; if (n > 0) s.reserve(n);              /* n <= 0 gives "" like the reference loop (a --circ corner) */
     int64_t index2 = index;
     for (int j = 0; j < n; j++) {
         uint64_t pos = c.offset + (uint64_t)(index2 / c.line_blen) * c.line_len + (uint64_t)(index2 % c.line_blen);
@@ -175,12 +176,23 @@ static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slo
         }
         if (!found) continue;   /* the reference redraws only the coordinate (:1390); we redraw the attempt */
         uint64_t idx = coord - found->start;                 /* :1404 */
-        if (idx + (uint64_t)length + (uint64_t)d > (uint64_t)found->len) {
-            /* run-off: the reference fetches past the contig and always hits '\n', '>' or EOF, so
-             * isResolvedDNAstring rejects it (:1472).  Same outcome, stated directly. */
-            continue;
+        std::string temp;
+        const bool circular = g.circ >= 0 && found == &g.chrs[(size_t)g.circ];       /* :1407-1408 */
+        /* :1410, in the reference's own uint64_t arithmetic (end-length-d+1 may wrap around for the very first contigs) */
+        if (circular && !(coord <= (found->end - (uint64_t)length - (uint64_t)d + 1))) {
+            /* need to circularize, :1412-1426: temp1 stops one base short of the contig end, temp2 restarts at base 0 */
+            int n1 = (int)(found->end - (coord - (uint64_t)d));
+            int l2 = (int)((uint64_t)length + 2 * (uint64_t)d - (found->end - (coord - (uint64_t)d)));
+            temp = fetchSeq(g, *found, (int64_t)idx - d, n1) + fetchSeq(g, *found, 0, l2);
+        } else {
+            if (idx + (uint64_t)length + (uint64_t)d > (uint64_t)found->len) {
+                /* run-off: the reference fetches past the contig and always hits '\n', '>' or EOF, so
+                 * isResolvedDNAstring rejects it (:1472); with --circ on another contig it redraws the coordinate (:1428-1432).
+                 * Same outcome, stated directly. */
+                continue;
+            }
+            temp = fetchSeq(g, *found, (int64_t)idx - d, length + 2 * d);            /* :1443 */
         }
-        std::string temp = fetchSeq(g, *found, (int64_t)idx - d, length + 2 * d);    /* :1443 */
         bool plus = c->norev ? true : ((x[1] & 1u) != 0);    /* :1462-1467 randomBool */
         bool resolved = true;                                /* :1472 isResolvedDNAstring */
         for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
@@ -306,6 +318,29 @@ static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::stri
     }
 }
 
+/* -damagess d,s5,s3,l5,l3 loop, deamSim.cpp:1337-1468 (single-strand libraries: C->T only).  Draw layout as for -damage:
+ * DEAM words 0,1 = 5' / 3' overhang, per-base word 4+i. */
+static void deamBriggsSS(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
+    int len = (int)seq.size();
+    std::vector<double> cdf5 = geomCdf(D.l5, GEOM_TABLE), cdf3 = geomCdf(D.l3, GEOM_TABLE);
+    uint32_t h[4]; c->rng.block(id, 0, ST_DEAM, h);
+    int overhang5p = geomDraw(cdf5, h[0]);                          /* :1342 */
+    int overhang3p = geomDraw(cdf3, h[1]);                          /* :1343 */
+    for (int i = 0; i < len; i++) {
+        double rate;
+        if ((overhang5p + overhang3p) >= len) {                     /* :1345 all single strand */
+            if (((i + 1) <= overhang5p) && ((len - i) <= overhang3p)) rate = (i < int(double(len) * 0.5)) ? D.s5 : D.s3;   /* :1351-1371 */
+            else if (!((i + 1) <= overhang5p) && ((len - i) <= overhang3p)) rate = D.s3;                                   /* :1372-1380 */
+            else rate = D.s5;                                                                                              /* :1384-1393; "neither" cannot happen */
+        } else {
+            if ((i + 1) <= overhang5p) rate = D.s5;                 /* :1414-1424 */
+            else if ((len - i) <= overhang3p) rate = D.s3;          /* :1428-1438 */
+            else rate = D.d;                                        /* :1439-1449 */
+        }
+        if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i)) < rate) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
+    }
+}
+
 /* -mat single|double / -mapdamage loops, deamSim.cpp:1941-2002.  Row index clamped to the last row
  * (the reference indexes out of bounds for len > rows: DESIGN.md deviation). */
 static void deamSingleDouble(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
@@ -334,6 +369,7 @@ static void deaminate(const orc_ctx* c, int slot, uint64_t id, std::string& seq,
     switch (D.mode) {
         case GG_DMG_MATRIX: deamMatrix(c, D, id, seq, deamPos); break;
         case GG_DMG_BRIGGS: deamBriggs(c, D, id, seq, deamPos); break;
+        case GG_DMG_BRIGGS_SS: deamBriggsSS(c, D, id, seq, deamPos); break;
         case GG_DMG_SINGLE: case GG_DMG_DOUBLE: deamSingleDouble(c, D, id, seq, deamPos); break;
         default: break;
     }
@@ -393,8 +429,12 @@ void orc_philox_raw(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) 
     philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4);
 }
 
+int orc_genome_upload_circ(orc_ctx* c, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int circ_chr, int* id_out);
 int orc_genome_upload(orc_ctx* c, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int* id_out) {
-    Genome g; g.fasta.assign(fasta, fasta + n);
+    return orc_genome_upload_circ(c, fasta, n, fai, n_chr, -1, id_out);
+}
+int orc_genome_upload_circ(orc_ctx* c, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int circ_chr, int* id_out) {
+    Genome g; g.fasta.assign(fasta, fasta + n); g.circ = -1;
     std::map<std::string, Chr> byname;                      /* std::map ordering, fragSim.cpp:215 */
     for (int i = 0; i < n_chr; i++) {
         Chr ch; ch.name = fai[i].name; ch.len = fai[i].len; ch.offset = fai[i].offset;
@@ -408,6 +448,10 @@ int orc_genome_upload(orc_ctx* c, const uint8_t* fasta, size_t n, const gg_fai_e
         g.chrs.push_back(ch);
     }
     g.G = G;
+    if (circ_chr >= 0) {                                    /* name2index[circName], fragSim.cpp:1173-1178 */
+        if (circ_chr >= n_chr) { c->err = "bad circular contig"; return GG_ERR_ARG; }
+        for (size_t i = 0; i < g.chrs.size(); i++) if (g.chrs[i].name == fai[circ_chr].name) g.circ = (int)i;
+    }
     c->genomes.push_back(g);
     if (id_out) *id_out = (int)c->genomes.size() - 1;
     return 0;
@@ -493,6 +537,10 @@ int orc_tables_clear_gcbias(orc_ctx* c, int slot) { if (slot < 0 || slot >= GG_M
 int orc_tables_set_briggs(orc_ctx* c, int slot, double v, double l, double d, double s) {
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
     Damage& D = c->dmg[slot]; D.mode = GG_DMG_BRIGGS; D.v = v; D.l = l; D.d = d; D.s = s; return 0;
+}
+int orc_tables_set_briggs_ss(orc_ctx* c, int slot, double d, double s5, double s3, double l5, double l3) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;
+    Damage& D = c->dmg[slot]; D.mode = GG_DMG_BRIGGS_SS; D.d = d; D.s5 = s5; D.s3 = s3; D.l5 = l5; D.l3 = l3; return 0;
 }
 int orc_tables_clear_damage(orc_ctx* c, int slot) {
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS) return GG_ERR_ARG;

@@ -59,6 +59,12 @@ def test_cli_validation_errors(workdir):
     assert r.returncode == 1 and b"3 comma-delimited fields" in r.stderr
 
 
+def test_cli_circ_unknown_contig(workdir):
+    d, _, _ = workdir
+    r = run([os.path.join(BIN, "fragSim"), "-n", "5", "--circ", "nosuchchr", str(d / "g.fa")])
+    assert r.returncode == 1 and b"Cannot find chromosome nosuchchr which is specified via --circ" in r.stderr   # fragSim.cpp:1175
+
+
 def test_cli_without_gpu_fails_loudly(workdir):
     import torch
     if torch.cuda.is_available():
@@ -115,6 +121,21 @@ def test_cli_pipeline_matches_oracle(workdir, oracle_mod):
     r6 = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-damage", "0.03,0.4,0.01,0.3", "-o", str(d / "b.fa.gz"), str(d / "f.fa")])
     assert r6.returncode == 0, r6.stderr
     util.assert_same(gzip.open(str(d / "b.fa.gz")).read(), o.run_fused(0, n, api.EMIT_DEAM)[0], "bin/deamSim -damage -o")
+
+
+@pytest.mark.gpu
+def test_cli_fragsim_circ_matches_oracle(tmp_path, oracle_mod):
+    """bin/fragSim --circ NAME == the oracle with that contig circular (fragSim.cpp:1171-1178,1407-1426)."""
+    fa, fai = util.circ_genome()
+    (tmp_path / "g.fa").write_bytes(fa)
+    synth.write_fai(str(tmp_path / "g.fa.fai"), fai)
+    o = oracle_mod.OracleContext(17)
+    gid = o.upload_genome(fa, fai, circ=1)
+    o.set_sizes(api.SIZE_FIXED, fixed_len=50)
+    o.set_plan([api.Range(0, 5000, gid, -1, "")])
+    r = run([os.path.join(BIN, "fragSim"), "--seed", "17", "-n", "5000", "-l", "50", "--circ", "m2", str(tmp_path / "g.fa")])
+    assert r.returncode == 0, r.stderr
+    util.assert_same(r.stdout, o.run_fused(0, 5000, api.EMIT_FRAG)[0], "bin/fragSim --circ")
 
 
 @pytest.mark.gpu
@@ -210,6 +231,21 @@ def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
     rct, rga, rnC = rates(_ref("deamSim"), 300_000, 42)
     sd = np.sqrt(want_ct * (1 - want_ct) * (1.0 / nC + 1.0 / rnC))
     assert (np.abs(ct - rct) < 5 * sd + 1e-4).all()
+    # -damagess (single-strand model): ours vs the reference's binary, per-position C->T
+    def rates_ss(exe, n, seed):
+        seqs = synth._BASES[rng.integers(0, 4, size=(n, 30))]
+        p = tmp_path / ("ss_%d.fa" % n)
+        with open(p, "wb") as f:
+            f.write(b"".join(b">r%d\n%s\n" % (i, seqs[i].tobytes()) for i in range(n)))
+        r = run([exe, "--seed", str(seed), "-damagess", "0.02,0.5,0.7,0.25,0.1", str(p)])
+        assert r.returncode == 0, r.stderr
+        got = np.frombuffer(b"".join(r.stdout.split(b"\n")[1::2]), dtype=np.uint8).reshape(n, 30)
+        isC = seqs == ord("C")
+        assert ((got != seqs) <= (isC & (got == ord("T")))).all()
+        return ((got == ord("T")) & isC).sum(0) / isC.sum(0), isC.sum(0)
+    a_ss, na = rates_ss(os.path.join(BIN, "deamSim"), 400_000, 42)
+    b_ss, nb = rates_ss(_ref("deamSim"), 200_000, 42)
+    assert (np.abs(a_ss - b_ss) < 5 * np.sqrt(np.maximum(a_ss * (1 - a_ss), 1e-4) * (1.0 / na + 1.0 / nb))).all(), (a_ss, b_ss)
     # lengths and strands: fragSim -f sizefreq
     ours = run([os.path.join(BIN, "fragSim"), "--seed", "5", "-n", "200000", "-f", str(d / "sf.size"), str(d / "g.fa")])
     ref = run([_ref("fragSim"), "--seed", "5", "-n", "60000", "-f", str(d / "sf.size"), str(d / "g.fa")])

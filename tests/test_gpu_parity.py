@@ -36,7 +36,7 @@ def test_pack_genome_matches_fasta(genomes):
                 assert g.genome_fetch(gid, ci, e.len // 3, min(77, e.len - e.len // 3)) == want[e.len // 3:e.len // 3 + 77]
 
 
-@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double"])
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "briggs_ss", "single", "double"])
 @pytest.mark.parametrize("sizes", ["freq", "list", "fixed", "lognormal"])
 def test_fused_bit_exact(oracle_mod, genomes, damage, sizes):
     g, o, ids = _pair(oracle_mod, genomes, sizes=sizes, damage=damage)
@@ -108,7 +108,7 @@ def test_fused_many_contigs_and_long_names(oracle_mod):
         assert ia.attempts == ib.attempts and ia.attempts > 3000
 
 
-@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double", "none"])
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "briggs_ss", "single", "double", "none"])
 def test_standalone_stages_bit_exact(oracle_mod, genomes, damage):
     """deamSim / adptSim as separate stages over the record stream the previous stage wrote, and fused == composition."""
     g, o, ids = _pair(oracle_mod, genomes, damage=damage)
@@ -277,7 +277,7 @@ def test_adpt_name_and_tag(oracle_mod):
     assert out[0] == b">x_adpt_rand_lib7" and out[2] == b">x_r_adpt_rand_lib7" and out[4] == b">y_adpt_lib7" and out[8] == b">z_lib7"
 
 
-@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double"])
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "briggs_ss", "single", "double"])
 def test_deam_name_tags(oracle_mod, damage):
     """deamSim -name: "_DEAM:" + positions in the reference's push order (deamSim.cpp:1857,1919,1949-1994,2035)."""
     g = api.Context(0, 31); o = oracle_mod.OracleContext(31)
@@ -333,3 +333,53 @@ def test_fused_gc_bias(oracle_mod, tmp_path):
     assert gcf(recs[:900]) < gcf(recs[1700:]) - 0.02        # positive bias factor penalises GC-rich windows
     g.clear_gcbias(0); o.clear_gcbias(0)
     util.assert_same(g.run_fused(0, 900, api.EMIT_FRAG)[0], o.run_fused(0, 900, api.EMIT_FRAG)[0], "gc cleared")
+
+
+@pytest.mark.parametrize("circ", [0, 1, 3])
+@pytest.mark.parametrize("sizes", ["fixed", "freq"])
+def test_fused_circular_contig(oracle_mod, genomes, tmp_path, circ, sizes):
+    """fragSim --circ (fragSim.cpp:1407-1426): run-off windows of the circular contig are gathered from the wrap image, incl.
+    the reference's quirks (last base skipped, coord == end+1, contig shorter than the fragment, u64 wrap of end-length+1),
+    alone and together with --comp (flanks wrap too) and -gc."""
+    from oracle import parsers
+    fa, fai = util.circ_genome()
+    p = str(tmp_path / "dnacomp.txt"); synth.write_dnacomp(p, seed=3)
+    tabs = [np.array(t) for t in parsers.load_dnacomp(p, 2)]
+    g = api.Context(0, 5); o = oracle_mod.OracleContext(5)
+    for c in (g, o):
+        other = c.upload_genome(*genomes[0])
+        gid = c.upload_genome(fa, fai, circ=circ)
+        if sizes == "fixed":
+            c.set_sizes(api.SIZE_FIXED, fixed_len=40)
+        else:
+            c.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq())
+        util.set_damage(c, 0, "matrix"); c.set_adapters(read_len=75)
+        c.set_composition(0, 2, *tabs)
+        c.set_gcbias(0, gid, 0, 3.0)
+        c.set_plan([api.Range(0, 3000, gid, 0, "e1_0"), api.Range(3000, 500, other, 0, "b1"), api.Range(3500, 1500, gid, -1, "c1", 0),
+                    api.Range(5000, 1000, gid, 0, "c2", -1, 0)])
+    for emit in (api.EMIT_FRAG, api.EMIT_ARTP):
+        a, ia = g.run_fused(0, 6000, emit); b, ib = o.run_fused(0, 6000, emit)
+        util.assert_same(a, b, "--circ %d sizes=%s emit=%d" % (circ, sizes, emit))
+        assert (ia.attempts, ia.gather_bytes) == (ib.attempts, ib.gather_bytes)
+    clen = fai[circ].len
+    wrapped = sum(1 for h, _ in util.records(g.run_fused(0, 3000, api.EMIT_FRAG)[0]) if int(h.split(b":")[3]) > clen and h.startswith(b">" + fai[circ].name.encode() + b":"))
+    assert wrapped > (0 if clen < 100 else 20)
+    g.close(); o.close()
+
+
+def test_fused_mixed_damage_slots(oracle_mod, genomes):
+    """All five damage models side by side in one plan (the DMODE = any-mix kernel), incl. -damagess."""
+    g, o, ids = _pair(oracle_mod, genomes, damage="briggs_ss")
+    for c in (g, o):
+        util.set_damage(c, 1, "matrix"); util.set_damage(c, 2, "briggs"); util.set_damage(c, 3, "double")
+    plan = [api.Range(0, 500, ids[0], 0, "e1_0"), api.Range(500, 400, ids[1], 1, "b1"), api.Range(900, 400, ids[2], 2, "b2"),
+            api.Range(1300, 300, ids[0], 3, "b3"), api.Range(1600, 200, ids[1], -1, "c1")]
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in (api.EMIT_DEAM, api.EMIT_ARTP, api.EMIT_FR):
+        util.assert_same(g.run_fused(0, 1800, emit)[0], o.run_fused(0, 1800, emit)[0], "mixed damage emit=%d" % emit)
+    recs, _ = o.run_fused(0, 500, api.EMIT_FRAG)
+    dam, _ = g.run_fused(0, 500, api.EMIT_DEAM)
+    diff = [(a, b) for (_, s), (_, t) in zip(util.records(recs), util.records(dam)) for a, b in zip(s, t) if a != b]
+    assert len(diff) > 200 and set(diff) == {(ord("C"), ord("T"))}       # -damagess: C->T only (deamSim.cpp:1337-1468)
+    g.close(); o.close()

@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself: Philox known answers, golden tables, deterministic transforms,
 structural properties of its output.  (No GPU.)"""
 import collections
+import os
 
 import numpy as np
 import pytest
@@ -107,7 +108,7 @@ def test_oracle_is_pure_function_of_id(oracle_mod):
     assert other != full
 
 
-@pytest.mark.parametrize("damage", ["matrix", "briggs", "single", "double", "none"])
+@pytest.mark.parametrize("damage", ["matrix", "briggs", "briggs_ss", "single", "double", "none"])
 def test_oracle_fused_equals_stage_composition(oracle_mod, damage):
     """fragSim | deamSim | adptSim over files == the fused run (same seed, ids = record index)."""
     ctx, ids = _oracle_ctx(oracle_mod, damage=damage)
@@ -186,3 +187,81 @@ def test_oracle_sizefreq_distribution(oracle_mod):
     chi = ((obs[keep] - pmf[keep] * len(L)) ** 2 / (pmf[keep] * len(L))).sum()
     assert stats.chi2.sf(chi, keep.sum() - 1) > 0.001
     assert abs(L.mean() - 72.45) < 1.0
+
+
+def _check_circ_records(out, seqs, circ_name, d=0):
+    """--circ (fragSim.cpp:1407-1426): a window that runs off the circular contig is contig[idx-d : len-1] ++ contig[0:...]
+    (the LAST base is skipped: temp1 has end-(coord-d) bases), cut to [d, d+length); deflines keep idx un-wrapped."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    wrapped = 0
+    for hdr, seq in util.records(out):
+        name, strand, start, end, ln = hdr[1:].split(b":")
+        start, end, ln = int(start), int(end), int(ln)
+        contig = seqs[name.decode()]
+        assert end - start == ln and len(seq) == ln
+        if end + d > len(contig):
+            assert name.decode() == circ_name, "run-off outside the circular contig"
+            n1 = len(contig) - 1 - (start - d)            # may be -1 (coord == end+1): temp1 = "", temp2 gets length+1 bases
+            temp = (contig[start - d:len(contig) - 1] if n1 > 0 else b"") + contig[0:ln + 2 * d - n1]
+            wrapped += 1
+        else:
+            temp = contig[start - d:end + d]
+        if strand == b"-":
+            temp = temp.translate(comp)[::-1]
+        assert seq == temp[d:d + ln], hdr
+    return wrapped
+
+
+@pytest.mark.parametrize("circ", [1, 0, 3])
+def test_oracle_circular_contig(oracle_mod, circ):
+    fa, fai = util.circ_genome()
+    seqs = util.contig_seqs(fa, fai)
+    o = oracle_mod.OracleContext(3)
+    gid = o.upload_genome(fa, fai, circ=circ)
+    o.set_sizes(api.SIZE_FIXED, fixed_len=40)
+    o.set_plan([api.Range(0, 4000, gid, -1, "")])
+    out, _ = o.run_fused(0, 4000, api.EMIT_FRAG)
+    wrapped = _check_circ_records(out, seqs, fai[circ].name)
+    expect = 4000 * 40.0 / sum(e.len for e in fai)          # P(start within the last ~40 coordinates of the circular contig)
+    assert 0.6 * expect < wrapped < 1.5 * expect
+    o.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(util.ROOT, "oracle", "_ref", "src", "fragSim")), reason="oracle/_ref not built")
+def test_reference_binary_circular_quirk(tmp_path):
+    """Pins the oracle's reading of --circ on the reference's own code: the wrapped window drops the contig's last base."""
+    import subprocess
+    fa, fai = util.circ_genome()
+    (tmp_path / "g.fa").write_bytes(fa)
+    synth.write_fai(str(tmp_path / "g.fa.fai"), fai)
+    ref = os.path.join(util.ROOT, "oracle", "_ref", "src", "fragSim")
+    out = subprocess.run([ref, "--seed", "4", "-n", "3000", "-l", "40", "--circ", "m2", str(tmp_path / "g.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+    assert _check_circ_records(out, util.contig_seqs(fa, fai), "m2") > 30
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(util.ROOT, "oracle", "_ref", "src", "deamSim")), reason="oracle/_ref not built")
+def test_oracle_damagess_vs_reference_binary(oracle_mod, tmp_path):
+    """-damagess d,s5,s3,l5,l3 (deamSim.cpp:310-340,1337-1468): per-position C->T rate of the oracle against the reference's own
+    binary (G->A never happens)."""
+    import subprocess
+    rng = np.random.default_rng(5)
+    n, L = 120_000, 30
+    seqs = synth._BASES[rng.integers(0, 4, size=(n, L))]
+    recs = b"".join(b">r%d\n%s\n" % (i, seqs[i].tobytes()) for i in range(n))
+    (tmp_path / "in.fa").write_bytes(recs)
+    pars = (0.02, 0.5, 0.7, 0.25, 0.1)
+    o = oracle_mod.OracleContext(9)
+    o.set_briggs_ss(0, *pars)
+    ours = o.run_deam(recs, 0)[0]
+    ref = subprocess.run([os.path.join(util.ROOT, "oracle", "_ref", "src", "deamSim"), "--seed", "3", "-damagess", ",".join(map(str, pars)), str(tmp_path / "in.fa")],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+    isC = seqs == ord("C")
+
+    def ct(out):
+        got = np.frombuffer(b"".join(out.split(b"\n")[1::2]), dtype=np.uint8).reshape(n, L)
+        assert ((got != seqs) <= (isC & (got == ord("T")))).all()          # C->T only
+        return ((got == ord("T")) & isC).sum(0) / isC.sum(0)
+    a, b = ct(ours), ct(ref)
+    sd = np.sqrt(np.maximum(a * (1 - a), 1e-4) * 2.0 / isC.sum(0).min())
+    assert (np.abs(a - b) < 5 * sd).all(), (a, b)
+    assert a[0] > 0.1 and a[-1] > 0.05 and a[L // 2] < a[-1]

@@ -1,7 +1,11 @@
 """Shared scaffolding of the parity tests: build the same state in a product Context and an oracle Context."""
+import os
+
 import numpy as np
 
 from gargammel_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def tiny_genomes(seed=7, n_files=3):
@@ -12,6 +16,17 @@ def tiny_genomes(seed=7, n_files=3):
                                     width=[60, 37, 80][g % 3], n_frac=0.03, n_run=(5, 120), lower_frac=0.2)
         out.append((fa, fai))
     return out
+
+
+def circ_genome(seed=11, lens=(45, 310, 900, 130), width=37):
+    """Small N-free contigs (names m1..mK) so that --circ wraps often; returns (fasta, fai)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return synth.fasta_bytes([("m%d" % (i + 1), synth.random_contig(rng, n, 0.0)) for i, n in enumerate(lens)], width)
+
+
+def contig_seqs(fa, fai):
+    return {e.name: fa[e.offset:e.offset + e.len + e.len // e.line_blen + 1].replace(b"\n", b"")[:e.len].upper() for e in fai}
 
 
 def configure(ctx, genomes, sizes="freq", damage="matrix", read_len=75, minlen=0, maxlen=1000, norev=False,
@@ -49,6 +64,8 @@ def set_damage(ctx, slot, damage, clamp_last=True, matrix="single-"):
         ctx.set_matrix(slot, s5, s3, clamp_last=clamp_last)
     elif damage == "briggs":
         ctx.set_briggs(slot, 0.03, 0.4, 0.01, 0.3)
+    elif damage == "briggs_ss":
+        ctx.set_briggs_ss(slot, 0.02, 0.5, 0.7, 0.25, 0.03)      # a small l3 makes "inside both overhangs" and "all single-stranded" common
     elif damage == "single":
         ctx.set_singledouble(slot, api.DMG_SINGLE, s5, s3)
     elif damage == "double":
