@@ -133,7 +133,10 @@ class Context:
             ptr, n = C.c_void_p(fasta.ctypes.data), int(fasta.size)
         else:
             ptr, n = C.cast(C.c_char_p(fasta), C.c_void_p), len(fasta)
-        self._ck(self._f("genome_upload_circ")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.c_int(circ), C.byref(gid)))
+        if circ < 0:
+            self._ck(self._f("genome_upload")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.byref(gid)))
+        else:
+            self._ck(self._f("genome_upload_circ")(self._h, ptr, C.c_size_t(n), arr, C.c_int(len(fai)), C.c_int(circ), C.byref(gid)))
         return gid.value
 
     def genome_fetch(self, genome, chr_index, start, length):

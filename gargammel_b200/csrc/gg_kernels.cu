@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 int xtra = 0;
                 if (idx + (uint64_t)L + (uint64_t)d > clen) {                          // run-off past the contig end: always rejected (fragSim.cpp:1472) ...
                     const GenomeDev* Gc = P.genomes + rg->genome;                      // (rare branch: fields re-read here, not kept live)
-                    if (ci != __ldg(&Gc->circ_contig) || __ldg(cum + a) + 1 < (uint64_t)(L + d)) continue;   // (u64 wrap of end-length-d+1, fragSim.cpp:1410)
+                    if (ci != __ldg(&Gc->circ_contig) || idx + (uint64_t)d > clen || __ldg(cum + a) + 1 < (uint64_t)(L + d)) continue;   // coord <= end-d+1 (:1400); u64 wrap of end-length-d+1 (:1410)
                     uint64_t s = idx - (uint64_t)d;                                    // ... except on the --circ contig (fragSim.cpp:1412-1426)
                     if (s >= clen) { s = clen - 1; xtra = 1; }                         // coord == end+1 (d == 0): temp1 = "" and temp2 has length+1 bases
                     gpos = __ldg(&Gc->wrap_gbase) + (s - (uint64_t)__ldg(&Gc->wrap_s0)) + (uint64_t)d;
