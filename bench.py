@@ -386,6 +386,43 @@ def main():
                                     "compressed_bytes_per_step": int(zn.value), "steps": 1}
         except Exception as ex:
             e2e["with_bgzf"] = {"value": None, "error": repr(ex)}
+        # ... and with the BGZF members produced ON THE DEVICE (gg_bgzf_dev: Huffman-only deflate + CRC-32 kernels), so that only
+        # the compressed members cross PCIe.  One step is inflated on the host afterwards and compared with the plain stream.
+        try:
+            def e2e_step_z():
+                ctx.genome_clear()
+                gids = [ctx.upload_genome(t, fai) for t, fai in pinned_src]
+                p2, _, _ = make_plan(api, n * world, gids)
+                ctx.set_plan(p2)
+                return ctx.run_fused_bgzf(first, count, api.EMIT_ARTP, zhost.data_ptr(), zcap)
+            zhost = torch.empty(zcap, dtype=torch.uint8, pin_memory=True)
+            e2e_step_z()
+            barrier()
+            td0 = time.perf_counter()
+            for _ in range(e_steps):
+                ri, zi = e2e_step_z()
+            barrier()
+            td = torch.tensor([time.perf_counter() - td0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            e2e["with_device_bgzf"] = {"value": count * world * e_steps / float(td.item()), "unit": "fragments/s", "steps": e_steps,
+                                       "d2h_bytes_per_step": int(zi.bytes), "uncompressed_bytes_per_step": int(zi.in_bytes),
+                                       "bgzf_device_ms": zi.device_ms, "bgzf_GBps_in": zi.in_bytes / (zi.device_ms / 1e3) / 1e9,
+                                       "what": "per step: gg_genome_upload x3 + gg_run_fused + gg_bgzf_dev + gg_out_fetch of the BGZF members to pinned host"}
+            if rank == 0:
+                import zlib
+                zb = zhost[:int(zi.bytes)].numpy()
+                plain = host_out[:int(ei.bytes)].numpy()
+                off, pos, okz = 0, 0, True
+                while off < len(zb) and pos < (32 << 20):                   # the first 32 MB of members (zlib verifies CRC-32 and ISIZE of each)
+                    bsize = int(zb[off + 16]) + (int(zb[off + 17]) << 8) + 1
+                    part = zlib.decompress(zb[off:off + bsize].tobytes(), wbits=31)
+                    okz = okz and part == plain[pos:pos + len(part)].tobytes()
+                    off += bsize; pos += len(part)
+                e2e["with_device_bgzf"]["verified_bytes"] = pos
+                assert okz, "device BGZF does not inflate to the plain stream"
+        except Exception as ex:
+            e2e["with_device_bgzf"] = {"value": None, "error": repr(ex)}
         # cheap end-to-end sanity on what reached the host
         head = bytes(host_out[:64].numpy().tobytes())
         assert head.startswith(b">chr"), head

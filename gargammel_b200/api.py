@@ -8,6 +8,7 @@ from collections import namedtuple
 
 EMIT_FRAG, EMIT_DEAM, EMIT_STDOUT4, EMIT_ARTS, EMIT_ARTP, EMIT_FR, EMIT_RR = range(7)
 SIZE_FIXED, SIZE_LIST, SIZE_FREQ = range(3)
+BGZF_EOF = bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
 DMG_NONE, DMG_MATRIX, DMG_BRIGGS, DMG_SINGLE, DMG_DOUBLE, DMG_BRIGGS_SS = range(6)
 DEFAULT_ADAPTER_F = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"   # adptSim.cpp:28
 DEFAULT_ADAPTER_S = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"         # adptSim.cpp:29
@@ -236,6 +237,26 @@ class Context:
         self._ck(self._f("run_fused_to_host")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.c_void_p(host_ptr),
                                               C.c_size_t(cap), C.c_uint64(chunk), C.byref(o)))
         return _info(o)
+
+    def run_fused_bgzf(self, first, count, emit, host_ptr=None, cap=0):
+        """gg_run_fused + gg_bgzf_dev (device BGZF) + D2H of the compressed members.  With host_ptr: copies into caller memory and
+        returns (RunInfo of the run, RunInfo of the compression); without: returns (bgzf bytes, run info, bgzf info).
+        The 28-byte BGZF EOF marker (api.BGZF_EOF) is not included."""
+        o, z = _Out(), _Out()
+        self._ck(self._f("run_fused")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.byref(o)))
+        self._ck(self._f("bgzf_dev")(self._h, C.byref(o), C.byref(z)))
+        if host_ptr is None:
+            return self._fetch(z), _info(o), _info(z)
+        n = C.c_size_t(0)
+        self._ck(self._f("out_fetch")(self._h, C.byref(z), C.c_void_p(host_ptr), C.c_size_t(cap), C.byref(n)))
+        return _info(o), _info(z)
+
+    def bgzf(self, data: bytes):
+        """gg_bgzf_host: BGZF members of a host byte string, compressed on the device (no EOF marker)."""
+        z = _Out()
+        src = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data) if len(data) else (C.c_uint8 * 1)()
+        self._ck(self._f("bgzf_host")(self._h, src, C.c_size_t(len(data)), C.byref(z)))
+        return self._fetch(z), _info(z)
 
     def _fetch(self, o):
         buf = C.create_string_buffer(max(int(o.bytes), 1))

@@ -12,6 +12,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../include/gargammel_b200.h"
+#include "gg_host.h"
 #include "gg_kernels.cuh"
 
 using namespace ggk;
@@ -105,6 +106,8 @@ struct gg_ctx {
     std::vector<std::pair<void*, size_t> > pool;     // device blocks of cleared genomes, reused by the next uploads
     DBuf d_tmp_fa, d_tmp_desc;                       // upload staging (raw FASTA bytes, contig descriptors)
     DBuf d_out, d_out2, d_tile_state, d_ticket_stats, d_in, d_nl, d_scan, d_sizes, d_flush;
+    DBuf d_bgzf, d_bgzf_tab, d_bgzf_state;           // device BGZF: output slab, code/CRC tables, look-back state + histogram
+    std::vector<uint32_t> bgzf_static;               // CRC tables and shift polynomials (built once)
     void* h_pinned; size_t h_pinned_cap;
     double last_ms;
 
@@ -1033,6 +1036,75 @@ int gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, 
     out->dev_ptr = nullptr;
     ctx->last_ms = out->device_ms;
     return GG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device BGZF
+int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
+    if (!ctx || !in || !out) return ctx ? ctx->fail(GG_ERR_ARG, "gg_bgzf_dev: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    out->records = in->records; out->in_bytes = in->bytes;
+    if (in->bytes == 0) return GG_OK;
+    if (!in->dev_ptr || ((uintptr_t)in->dev_ptr & 15)) return ctx->fail(GG_ERR_ARG, "gg_bgzf_dev: input must be a 16-byte aligned device stream");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n = in->bytes;
+    const uint64_t n_blocks = (n + BGZF_BLOCK - 1) / BGZF_BLOCK;
+    if (n_blocks > 0xFFFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_bgzf_dev: stream too long");
+    const uint64_t out_cap = n + n_blocks * (18 + 5 + 8) + 64;            // every member at worst stored
+    CK(ctx->d_bgzf.ensure(out_cap));
+    CK(ctx->d_bgzf_tab.ensure((size_t)BGZF_TAB_WORDS * 4));
+    CK(ctx->d_bgzf_state.ensure((size_t)n_blocks * 8 + 256 * 8 + 64));
+    unsigned long long* d_state = ctx->d_bgzf_state.as<unsigned long long>();
+    unsigned long long* d_hist = d_state + n_blocks;                         // 256 counters
+    unsigned long long* d_total = d_hist + 256;                              // [0] bytes, [1] error flag
+    unsigned int* d_ticket = (unsigned int*)(d_total + 2);
+    CK(cudaEventRecord(ctx->ev0, ctx->st));
+    CK(cudaMemsetAsync(d_state, 0, (size_t)n_blocks * 8 + 256 * 8 + 32, ctx->st));
+    // 1. sampled byte histogram (<= ~32 MB of the stream) -> one dynamic Huffman code for the whole stream
+    const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
+    CK(launch_byte_hist((const uint8_t*)in->dev_ptr, n, stride, d_hist, ctx->st));
+    unsigned long long hist[256];
+    CK(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ggh::DeflateCode code; std::string e;
+    uint64_t h64[256]; for (int i = 0; i < 256; i++) h64[i] = hist[i];
+    if (!ggh::build_deflate_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
+    if (code.header_nbits > BGZF_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
+    if (ctx->bgzf_static.empty()) {
+        ctx->bgzf_static.assign(BGZF_TAB_WORDS, 0u);
+        uint32_t t[4][256]; ggh::crc32_tables(t);
+        memcpy(&ctx->bgzf_static[BGZF_TAB_CRC], t, sizeof t);
+        for (int k = 0; k < BGZF_THREADS; k++) ctx->bgzf_static[BGZF_TAB_SHIFT + k] = ggh::crc32_x8n((uint64_t)BGZF_RUN * (uint64_t)(BGZF_THREADS - 1 - k));
+        for (int k = 0; k < 17; k++) ctx->bgzf_static[BGZF_TAB_X8 + k] = ggh::crc32_x8n(1ull << k);
+    }
+    std::vector<uint32_t> tab(ctx->bgzf_static);
+    memcpy(&tab[BGZF_TAB_SYM], code.sym, sizeof code.sym);
+    for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
+    CK(cudaMemcpyAsync(ctx->d_bgzf_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+    // 2. one CTA per 65280-byte member, persistent over the SMs
+    BgzfParams P;
+    P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = ctx->d_bgzf.as<uint8_t>(); P.out_cap = out_cap;
+    P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = code.header_nbits; P.n_blocks = (uint32_t)n_blocks;
+    P.state = d_state; P.ticket = d_ticket; P.total = d_total;
+    CK(launch_bgzf_deflate(P, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
+    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    unsigned long long tot[2];
+    CK(cudaMemcpyAsync(tot, d_total, sizeof tot, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));                                     // (tab is a local: must outlive the copy)
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (tot[1]) return ctx->fail(GG_ERR_CAPACITY, "gg_bgzf_dev: output overflow");
+    out->dev_ptr = ctx->d_bgzf.p; out->bytes = tot[0]; out->device_ms = ms; out->launches = 2;
+    return GG_OK;
+}
+
+int gg_bgzf_host(gg_ctx* ctx, const void* src, size_t n, gg_out* out) {
+    if (!ctx || !out || (!src && n)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_bgzf_host: bad arguments") : GG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_in.ensure(n + 64));
+    if (n) CK(cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->st));
+    gg_out in; memset(&in, 0, sizeof in);
+    in.dev_ptr = ctx->d_in.p; in.bytes = n;
+    return gg_bgzf_dev(ctx, &in, out);
 }
 
 int gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n) {

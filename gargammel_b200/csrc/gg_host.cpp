@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <map>
 #include <thread>
+#include <queue>
 
 namespace ggh {
 
@@ -432,6 +433,119 @@ bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vec
     return true;
 }
 
+
+// ---------------------------------------------------------------- Huffman-only deflate code (device BGZF encoder)
+namespace {
+// code lengths of an optimal prefix code, at most `limit` bits: plain Huffman, and while the tree is too deep the counts are
+// halved (floor 1) and the tree rebuilt (the classic zlib-style flattening; costs a fraction of a percent in ratio)
+void huff_lengths(const std::vector<uint64_t>& cnt_in, int limit, std::vector<int>& len) {
+    const int n = (int)cnt_in.size();
+    std::vector<uint64_t> cnt(cnt_in);
+    len.assign(n, 0);
+    int used = 0, last = -1;
+    for (int i = 0; i < n; i++) if (cnt[i]) { used++; last = i; }
+    if (used == 0) return;
+    if (used == 1) { len[last] = 1; return; }
+    for (;;) {
+        struct Node { uint64_t w; int l, r; };
+        std::vector<Node> nodes;
+        typedef std::pair<uint64_t, int> QE;              // (weight, node index); ties broken by index: deterministic
+        std::priority_queue<QE, std::vector<QE>, std::greater<QE> > q;
+        for (int i = 0; i < n; i++) if (cnt[i]) { Node nd = {cnt[i], -1 - i, 0}; nodes.push_back(nd); q.push(QE(cnt[i], (int)nodes.size() - 1)); }
+        while (q.size() > 1) {
+            QE a = q.top(); q.pop(); QE b = q.top(); q.pop();
+            Node nd = {a.first + b.first, a.second, b.second}; nodes.push_back(nd);
+            q.push(QE(nd.w, (int)nodes.size() - 1));
+        }
+        int maxd = 0;
+        std::vector<std::pair<int, int> > st; st.push_back(std::make_pair(q.top().second, 0));
+        while (!st.empty()) {
+            const int v = st.back().first, d = st.back().second; st.pop_back();
+            if (nodes[v].l < 0) { len[-1 - nodes[v].l] = d; if (d > maxd) maxd = d; }
+            else { st.push_back(std::make_pair(nodes[v].l, d + 1)); st.push_back(std::make_pair(nodes[v].r, d + 1)); }
+        }
+        if (maxd <= limit) return;
+        for (int i = 0; i < n; i++) if (cnt[i]) cnt[i] = (cnt[i] + 1) / 2;
+    }
+}
+// canonical codes of RFC 1951 3.2.2 from lengths
+void canonical_codes(const std::vector<int>& len, int maxbits, std::vector<uint32_t>& code) {
+    std::vector<int> bl_count(maxbits + 2, 0);
+    for (size_t i = 0; i < len.size(); i++) bl_count[len[i]]++;
+    bl_count[0] = 0;
+    std::vector<uint32_t> next(maxbits + 2, 0);
+    uint32_t c = 0;
+    for (int b = 1; b <= maxbits; b++) { c = (c + (uint32_t)bl_count[b - 1]) << 1; next[b] = c; }
+    code.assign(len.size(), 0);
+    for (size_t i = 0; i < len.size(); i++) if (len[i]) code[i] = next[len[i]]++;
+}
+uint32_t bitrev(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1u); v >>= 1; } return r; }
+struct BitWriter {
+    std::vector<uint8_t> b; int nbits; BitWriter() : nbits(0) {}
+    void put(uint32_t v, int n) { for (int i = 0; i < n; i++) { if ((nbits & 7) == 0) b.push_back(0); if ((v >> i) & 1u) b[nbits >> 3] |= (uint8_t)(1u << (nbits & 7)); nbits++; } }
+};
+const uint32_t CRC_POLY = 0xEDB88320u;
+}
+bool build_deflate_code(const uint64_t hist[256], DeflateCode& out, std::string& err) {
+    std::vector<uint64_t> cnt(257);
+    uint64_t total = 0;
+    for (int i = 0; i < 256; i++) { cnt[i] = hist[i] ? hist[i] : 1; total += cnt[i]; }
+    cnt[256] = std::max<uint64_t>(1, total / 65280);                       // one end-of-block per BGZF block
+    std::vector<int> len; huff_lengths(cnt, 15, len);
+    std::vector<uint32_t> code; canonical_codes(len, 15, code);
+    for (int s = 0; s < 257; s++) {
+        if (len[s] < 1 || len[s] > 15) { err = "build_deflate_code: bad code length"; return false; }
+        out.sym[s] = bitrev(code[s], len[s]) | ((uint32_t)len[s] << 16);
+    }
+    // code-length sequence: 257 literal/length codes + 1 distance code of length 0; runs of equal lengths use symbol 16 (repeat 3-6)
+    std::vector<int> seq(len.begin(), len.end()); seq.push_back(0);
+    std::vector<std::pair<int, int> > cl;                                  // (symbol, extra-bit value)
+    for (size_t i = 0; i < seq.size();) {
+        size_t j = i; while (j < seq.size() && seq[j] == seq[i]) j++;
+        size_t run = j - i;
+        cl.push_back(std::make_pair(seq[i], 0)); run--;
+        while (run >= 3) { const int r = (int)std::min<size_t>(run, 6); cl.push_back(std::make_pair(16, r - 3)); run -= (size_t)r; }
+        while (run--) cl.push_back(std::make_pair(seq[i], 0));
+        i = j;
+    }
+    std::vector<uint64_t> clcnt(19, 0);
+    for (size_t i = 0; i < cl.size(); i++) clcnt[cl[i].first]++;
+    std::vector<int> cllen; huff_lengths(clcnt, 7, cllen);
+    std::vector<uint32_t> clcode; canonical_codes(cllen, 7, clcode);
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int hclen = 19; while (hclen > 4 && cllen[order[hclen - 1]] == 0) hclen--;
+    BitWriter w;
+    w.put(1, 1); w.put(2, 2);                                              // BFINAL = 1 (one deflate block per BGZF member), BTYPE = 10 dynamic
+    w.put(257 - 257, 5); w.put(1 - 1, 5); w.put((uint32_t)(hclen - 4), 4);
+    for (int i = 0; i < hclen; i++) w.put((uint32_t)cllen[order[i]], 3);
+    for (size_t i = 0; i < cl.size(); i++) {
+        w.put(bitrev(clcode[cl[i].first], cllen[cl[i].first]), cllen[cl[i].first]);
+        if (cl[i].first == 16) w.put((uint32_t)cl[i].second, 2);
+    }
+    out.header = w.b; out.header_nbits = w.nbits;
+    return true;
+}
+void crc32_tables(uint32_t t[4][256]) {
+    for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1; t[0][i] = c; }
+    for (uint32_t i = 0; i < 256; i++) for (int s = 1; s < 4; s++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFFu];
+}
+// product of two polynomials mod P, reflected representation (bit 31 = x^0)
+uint32_t crc32_mul(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (int i = 31; i >= 0; i--) {
+        if ((a >> i) & 1u) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+uint32_t crc32_x8n(uint64_t n_bytes) {
+    uint32_t r = 0x80000000u;                   // x^0
+    uint32_t sq = crc32_mul(0x40000000u, 0x40000000u);      // x^2 ...
+    sq = crc32_mul(sq, sq); sq = crc32_mul(sq, sq);         // ... x^8
+    for (uint64_t n = n_bytes; n; n >>= 1) { if (n & 1u) r = crc32_mul(r, sq); sq = crc32_mul(sq, sq); }
+    return r;
+}
+
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err) {
     g.path = fasta_path;
     if (!read_file(fasta_path, g.bytes, err)) return false;            // .gz is inflated in memory (the reference writes a temp file, fragSim.cpp:1108-1147)
@@ -509,6 +623,16 @@ int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int e
     if (o.size() > cap) return -2;
     memcpy(out, o.data(), o.size()); return 0;
 }
+// test hook: the deflate code + header for a histogram, and a reference encoding of `in` with it (one BGZF member per 65280 bytes)
+int ggh_deflate_code(const uint64_t* hist, uint32_t* sym257, uint8_t* hdr, int hdr_cap, int* hdr_nbits) {
+    ggh::DeflateCode c; std::string e;
+    if (!ggh::build_deflate_code(hist, c, e)) return -1;
+    memcpy(sym257, c.sym, sizeof c.sym);
+    if ((int)c.header.size() > hdr_cap) return -2;
+    memcpy(hdr, c.header.data(), c.header.size()); *hdr_nbits = c.header_nbits; return 0;
+}
+uint32_t ggh_crc32_x8n(uint64_t n) { return ggh::crc32_x8n(n); }
+uint32_t ggh_crc32_mul(uint32_t a, uint32_t b) { return ggh::crc32_mul(a, b); }
 int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, double* s3p, double* s3m, char* err, int errcap) {
     ggh::CompTables t; std::string e;
     if (!ggh::load_dnacomp(path, dist, t, e)) return set_err(err, errcap, e);

@@ -66,6 +66,18 @@ uint64_t binomial_draw(uint64_t n, double p, uint64_t seed, uint64_t stream);
 // Splits `in` into 65280-byte blocks, deflates them on `threads` host threads (0 = all), concatenates in order.
 bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vector<uint8_t>& out, bool eof_marker, std::string& err);
 
+// ---- Huffman-only deflate code for the device BGZF encoder (k_bgzf_deflate) ----
+// One dynamic-Huffman code (RFC 1951 3.2.7) for a whole output stream, built from a byte histogram: every literal 0..255 and the
+// end-of-block symbol get a code of at most 15 bits (unseen bytes are floored to a count of 1, so any input is encodable); no
+// distance codes (HDIST = 0 with one zero-length code: "all literals").  sym[s] = bit-reversed code | len << 16 (ready to be OR-ed
+// into an LSB-first bit stream); header = BFINAL=1, BTYPE=10 and the code description, LSB-first, header_nbits bits.
+struct DeflateCode { uint32_t sym[257]; std::vector<uint8_t> header; int header_nbits; };
+bool build_deflate_code(const uint64_t hist[256], DeflateCode& out, std::string& err);
+// CRC-32 (IEEE, reflected) helpers for the device encoder: slicing-by-4 tables and x^(8n) mod P in the reflected domain
+void crc32_tables(uint32_t t[4][256]);
+uint32_t crc32_x8n(uint64_t n_bytes);                       // multiply a CRC by this (crc32_mul) to append n_bytes zero-effect bytes
+uint32_t crc32_mul(uint32_t a, uint32_t b);
+
 // ---- one genome file ready for upload ----
 struct GenomeFile { std::string path; std::vector<uint8_t> bytes; std::vector<FaiEntry> fai; uint64_t total_len; };
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err);

@@ -1076,4 +1076,240 @@ cudaError_t launch_l2_flush(uint4* buf, uint64_t n16, cudaStream_t st) {
     k_l2_flush<<<148 * 8, 256, 0, st>>>(buf, n16); return cudaGetLastError();
 }
 
+
+// ======================================================================================= device BGZF
+// Blocked gzip of a byte stream already resident in HBM (the host gzip hops are the cliff after the kernel).
+// Huffman-only deflate: one dynamic code per stream (built on the host from a sampled histogram), every BGZF member = one
+// final deflate block of literals.  On simulated reads this matches zlib level 1 (random bases give LZ77 nothing to find).
+// One CTA per 65280-byte member: stage the input in shared memory, thread t owns bytes [68t, 68t+68): pass 1 = code-length sum
+// + CRC-32 of the run, block scan -> bit offsets, CRC runs combined by polynomial shifts, decoupled look-back over members ->
+// byte offset in the output, pass 2 = bit packing into a shared-memory image pre-shifted to the output's 16-byte phase,
+// 16-byte stores.  A member that would not shrink is written as a stored block.
+__global__ void __launch_bounds__(256) k_byte_hist(const uint8_t* __restrict__ in, uint64_t n, uint64_t group_stride, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int h[8][256];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t n_groups = n >> 4;
+    for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * group_stride; g < n_groups; g += (uint64_t)gridDim.x * blockDim.x * group_stride) {
+        const uint4 v = __ldg((const uint4*)in + g);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(&h[warp][w[k] & 0xFFu], 1u); atomicAdd(&h[warp][(w[k] >> 8) & 0xFFu], 1u);
+            atomicAdd(&h[warp][(w[k] >> 16) & 0xFFu], 1u); atomicAdd(&h[warp][w[k] >> 24], 1u);
+        }
+    }
+    if (blockIdx.x == 0) for (uint64_t i = (n_groups << 4) + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&h[warp][in[i]], 1u);   // tail bytes
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        unsigned long long c = 0;
+        for (int k = 0; k < 8; k++) c += h[k][i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+cudaError_t launch_byte_hist(const uint8_t* in, uint64_t n, uint64_t group_stride, unsigned long long* hist, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_byte_hist<<<148 * 4, 256, 0, st>>>(in, n, group_stride ? group_stride : 1, hist);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {      // polynomial product mod P, reflected (bit 31 = x^0)
+    uint32_t p = 0;
+#pragma unroll 1
+    for (int i = 31; i >= 0; i--) {
+        if ((a >> i) & 1u) p ^= b;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+    }
+    return p;
+}
+__device__ __forceinline__ void put_bits_atomic(uint32_t* w, uint32_t bitpos, uint32_t v, int nbits) {    // nbits <= 16
+    if (nbits <= 0) return;
+    const uint32_t sh = bitpos & 31u;
+    atomicOr(w + (bitpos >> 5), v << sh);
+    if (sh + (uint32_t)nbits > 32u) atomicOr(w + (bitpos >> 5) + 1, v >> (32u - sh));
+}
+
+__global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_constant__ BgzfParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* const s_in = smem;                                             // 65280
+    uint32_t* const s_out = (uint32_t*)(smem + BGZF_BLOCK);                 // 65536 + 64 bytes
+    uint32_t* const s_tab = s_out + (65536 + 64) / 4;                       // BGZF_TAB_WORDS
+    uint32_t* const s_scan = s_tab + BGZF_TAB_WORDS;                        // 32 + 32 + 8
+    const uint32_t* const s_sym = s_tab + BGZF_TAB_SYM;
+    const uint32_t* const s_crc = s_tab + BGZF_TAB_CRC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < BGZF_TAB_WORDS; i += BGZF_THREADS) s_tab[i] = __ldg(P.tab + i);
+    const uint32_t eob = __ldg(P.tab + 256);
+    __syncthreads();
+
+    while (true) {
+        if (tid == 0) s_scan[64] = atomicAdd(P.ticket, 1u);                 // members are started in order: look-back never waits on an unstarted one
+        __syncthreads();
+        const uint32_t b = s_scan[64];
+        if (b >= P.n_blocks) break;
+        const uint64_t base = (uint64_t)b * BGZF_BLOCK;
+        const int nb = (int)min((uint64_t)BGZF_BLOCK, P.n - base);
+        // ---- stage the input, clear the output image
+        for (int g = tid; g < BGZF_BLOCK / 16; g += BGZF_THREADS) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (16 * g + 16 <= nb) v = __ldg((const uint4*)(P.in + base) + g);
+            else if (16 * g < nb) { uint8_t t[16]; for (int k = 0; k < 16; k++) t[k] = (16 * g + k < nb) ? P.in[base + 16 * g + k] : 0; v = *(const uint4*)t; }
+            ((uint4*)s_in)[g] = v;
+        }
+        for (int g = tid; g < (65536 + 64) / 16; g += BGZF_THREADS) ((uint4*)s_out)[g] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        // ---- pass 1: bits and CRC of my run
+        const int r0 = tid * BGZF_RUN;
+        const int len = max(0, min(BGZF_RUN, nb - r0));
+        const uint32_t* const wp = (const uint32_t*)(s_in + r0);
+        uint32_t bits = 0, crc = 0xFFFFFFFFu;
+#pragma unroll 1
+        for (int w = 0; 4 * w < len; w++) {
+            const uint32_t x = wp[w];
+            if (4 * w + 4 <= len) {
+                bits += (s_sym[x & 0xFFu] >> 16) + (s_sym[(x >> 8) & 0xFFu] >> 16) + (s_sym[(x >> 16) & 0xFFu] >> 16) + (s_sym[x >> 24] >> 16);
+                crc ^= x;
+                crc = s_crc[768 + (crc & 0xFFu)] ^ s_crc[512 + ((crc >> 8) & 0xFFu)] ^ s_crc[256 + ((crc >> 16) & 0xFFu)] ^ s_crc[crc >> 24];
+            } else {
+                for (int k = 0; 4 * w + k < len; k++) {
+                    const uint32_t c = (x >> (8 * k)) & 0xFFu;
+                    bits += s_sym[c] >> 16;
+                    crc = s_crc[(crc ^ c) & 0xFFu] ^ (crc >> 8);
+                }
+            }
+        }
+        crc = len ? ~crc : 0u;
+        // my run's CRC shifted over the bytes that follow it in the member (crc(A||B) = crc(A) * x^(8|B|) + crc(B))
+        if (len) {
+            uint32_t sh;
+            if (nb == BGZF_BLOCK) sh = s_tab[BGZF_TAB_SHIFT + tid];
+            else {
+                sh = 0x80000000u;
+                uint32_t after = (uint32_t)(nb - r0 - len);
+                for (int k = 0; after; k++, after >>= 1) if (after & 1u) sh = crc_mul(sh, s_tab[BGZF_TAB_X8 + k]);
+            }
+            crc = crc_mul(crc, sh);
+        }
+        // ---- block scan of bits, XOR-reduction of the shifted CRCs
+        uint32_t inc = bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+        if (lane == 31) s_scan[warp] = inc;
+        if (lane == 0) s_scan[32 + warp] = crc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = lane < BGZF_THREADS / 32 ? s_scan[lane] : 0u;
+            uint32_t wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            uint32_t c = lane < BGZF_THREADS / 32 ? s_scan[32 + lane] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+            const uint32_t data_bits = __shfl_sync(0xffffffffu, wi, 31);
+            s_scan[lane] = wi - v;                                           // exclusive warp offsets
+            // ---- member size and its place in the output (decoupled look-back over members)
+            const uint32_t total_bits = (uint32_t)P.hdr_nbits + data_bits + (eob >> 16);
+            uint32_t payload = (total_bits + 7u) >> 3;
+            const bool stored = payload >= (uint32_t)nb + 5u;
+            if (stored) payload = (uint32_t)nb + 5u;
+            const unsigned long long S = 18ull + payload + 8ull;
+            if (lane == 0) st_volatile_u64(P.state + b, ((b == 0 ? 2ull : 1ull) << 62) | S);
+            unsigned long long gofs = 0;
+            if (b > 0) {
+                long long look = (long long)b - 1;
+                while (true) {
+                    const long long i = look - lane;
+                    unsigned long long lb = 2ull << 62;
+                    if (i >= 0) { do { lb = ld_volatile_u64(P.state + i); } while ((lb >> 62) == 0); }
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (lb >> 62) == 2ull);
+                    const int first_inc = incl ? (__ffs(incl) - 1) : 32;
+                    gofs += warp_sum_u64(lane <= first_inc ? (lb & 0x3FFFFFFFFFFFFFFFull) : 0ull);
+                    if (incl) break;
+                    look -= 32;
+                }
+                if (lane == 0) st_volatile_u64(P.state + b, (2ull << 62) | (gofs + S));
+            }
+            if (lane == 0) {
+                if (b == P.n_blocks - 1) *P.total = gofs + S;
+                s_scan[65] = (uint32_t)gofs; s_scan[66] = (uint32_t)(gofs >> 32); s_scan[67] = payload; s_scan[68] = stored ? 1u : 0u; s_scan[69] = c; s_scan[70] = data_bits;
+            }
+        }
+        __syncthreads();
+        const unsigned long long gofs = (unsigned long long)s_scan[65] | ((unsigned long long)s_scan[66] << 32);
+        const uint32_t payload = s_scan[67]; const bool stored = s_scan[68] != 0; const uint32_t crc_all = s_scan[69], data_bits = s_scan[70];
+        const bool fits = gofs + 18ull + payload + 8ull <= P.out_cap;
+        uint8_t* const dst = P.out + gofs;
+        const uint32_t pad = (uint32_t)((gofs + 18ull) & 15ull);          // P.out is 16-byte aligned
+        if (fits && !stored) {
+            // ---- pass 2: pack my run's codes at my bit offset
+            uint32_t bitpos = 8u * pad + (uint32_t)P.hdr_nbits + s_scan[warp] + (inc - bits);
+            uint32_t* wout = s_out + (bitpos >> 5);
+            unsigned long long acc = 0; uint32_t fill = bitpos & 31u; bool first = true;
+#pragma unroll 1
+            for (int w = 0; 4 * w < len; w++) {
+                const uint32_t x = wp[w];
+                const int nk = min(4, len - 4 * w);
+                for (int k = 0; k < nk; k++) {
+                    const uint32_t sy = s_sym[(x >> (8 * k)) & 0xFFu];
+                    acc |= (unsigned long long)(sy & 0xFFFFu) << fill; fill += sy >> 16;
+                }
+                if (fill >= 32u) {                                          // at most 4 x 15 bits were added: one flush suffices? no: up to 60 -> flush while
+                    do {
+                        if (first) { atomicOr(wout, (uint32_t)acc); first = false; } else *wout = (uint32_t)acc;
+                        wout++; acc >>= 32; fill -= 32u;
+                    } while (fill >= 32u);
+                }
+            }
+            if (fill > (first ? (bitpos & 31u) : 0u)) atomicOr(wout, (uint32_t)acc);
+            // header bits and the end-of-block code
+            if (tid >= 32 && tid < 32 + BGZF_HDR_WORDS * 2) {
+                const int piece = tid - 32;                                 // 16 bits each
+                const int nbp = min(16, P.hdr_nbits - 16 * piece);
+                if (nbp > 0) put_bits_atomic(s_out, 8u * pad + 16u * (uint32_t)piece, (s_tab[BGZF_TAB_HDR + (piece >> 1)] >> (16 * (piece & 1))) & (0xFFFFu >> (16 - nbp)), nbp);
+            }
+            if (tid == BGZF_THREADS - 1) put_bits_atomic(s_out, 8u * pad + (uint32_t)P.hdr_nbits + data_bits, eob & 0xFFFFu, (int)(eob >> 16));
+        }
+        __syncthreads();
+        if (fits) {
+            // ---- member header (RFC 1952 + the BGZF "BC" extra field), payload, CRC-32 and ISIZE
+            if (tid < 18) {
+                const uint32_t bsize1 = 18u + payload + 8u - 1u;
+                const uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)(bsize1 & 0xFFu), (uint8_t)(bsize1 >> 8)};
+                dst[tid] = h[tid];
+            } else if (tid >= 32 && tid < 40) {
+                const int k = tid - 32;
+                dst[18 + payload + k] = (uint8_t)((k < 4 ? crc_all >> (8 * k) : (uint32_t)nb >> (8 * (k - 4))) & 0xFFu);
+            }
+            uint8_t* const pay = dst + 18;
+            if (!stored) {
+                const uint8_t* img = (const uint8_t*)s_out;                 // image byte pad+k <-> pay[k]; (pay - pad) is 16-byte aligned
+                const uint32_t end = pad + payload;
+                for (uint32_t g = tid; 16u * g < end; g += BGZF_THREADS) {
+                    if (16u * g >= pad && 16u * g + 16u <= end) *(uint4*)(pay - pad + 16u * g) = ((const uint4*)img)[g];
+                    else for (uint32_t k = max(16u * g, pad); k < min(16u * g + 16u, end); k++) pay[k - pad] = img[k];
+                }
+            } else {
+                if (tid < 5) { const uint32_t L = (uint32_t)nb; const uint8_t sh[5] = {1, (uint8_t)(L & 0xFFu), (uint8_t)(L >> 8), (uint8_t)(~L & 0xFFu), (uint8_t)((~L >> 8) & 0xFFu)}; pay[tid] = sh[tid]; }
+                for (int k = tid; k < nb; k += BGZF_THREADS) pay[5 + k] = s_in[k];
+            }
+        } else if (tid == 0) atomicOr(P.total + 1, 1ull);                   // capacity error flag
+        __syncthreads();
+    }
+}
+cudaError_t bgzf_prepare(size_t* smem_bytes) {
+    const size_t sm = (size_t)BGZF_BLOCK + 65536 + 64 + (size_t)BGZF_TAB_WORDS * 4 + 80 * 4;
+    *smem_bytes = sm;
+    return cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+}
+cudaError_t launch_bgzf_deflate(const BgzfParams& P, int grid, cudaStream_t st) {
+    size_t sm = 0;
+    cudaError_t e = bgzf_prepare(&sm);
+    if (e != cudaSuccess) return e;
+    k_bgzf_deflate<<<grid, BGZF_THREADS, sm, st>>>(P);
+    return cudaGetLastError();
+}
+
 } // namespace ggk

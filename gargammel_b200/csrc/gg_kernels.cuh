@@ -99,6 +99,26 @@ enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
 
 
 // ---- launchers (gg_kernels.cu) ----
+// ---- device BGZF (Huffman-only deflate) ----
+constexpr int BGZF_BLOCK = 65280;        // input bytes per BGZF member (the same 0xff00 htslib uses)
+constexpr int BGZF_RUN = 68;             // bytes per thread: 17 words, an odd word stride (conflict-free shared-memory reads)
+constexpr int BGZF_THREADS = 960;        // 960 x 68 = 65280
+constexpr int BGZF_HDR_WORDS = 40;       // room for the dynamic-code description (<= 1280 bits)
+// table layout (uint32): [0,257) symbol codes | [260,1284) CRC slicing-by-4 | [1284,2244) per-thread shift polynomials x^(8*68*(959-t))
+// | [2244,2261) x^(8*2^k) | [2264, 2264+BGZF_HDR_WORDS) header bits
+constexpr int BGZF_TAB_SYM = 0, BGZF_TAB_CRC = 260, BGZF_TAB_SHIFT = 1284, BGZF_TAB_X8 = 2244, BGZF_TAB_HDR = 2264, BGZF_TAB_WORDS = BGZF_TAB_HDR + BGZF_HDR_WORDS;
+struct BgzfParams {
+    const uint8_t* in; uint64_t n;       // plain stream (16-byte aligned)
+    uint8_t* out; uint64_t out_cap;      // BGZF members, back to back (16-byte aligned)
+    const uint32_t* tab; int hdr_nbits;
+    uint32_t n_blocks;
+    unsigned long long* state;           // look-back state per block
+    unsigned int* ticket; unsigned long long* total;
+};
+cudaError_t launch_byte_hist(const uint8_t* in, uint64_t n, uint64_t group_stride, unsigned long long* hist, cudaStream_t st);
+cudaError_t bgzf_prepare(size_t* smem_bytes);
+cudaError_t launch_bgzf_deflate(const BgzfParams& P, int grid, cudaStream_t st);
+
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
                                int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,

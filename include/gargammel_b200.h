@@ -197,6 +197,15 @@ int  gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint
  * host_dst should be pinned memory for the copies to overlap.  out->device_ms = sum of the kernels' event times. */
 int  gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* host_dst, size_t cap,
                           uint64_t chunk, gg_out* out);
+/* ---- device BGZF: replaces the `| gzip >` hops of gargammel.pl:1510,1729,1873-1884 and ogzstream (-o) ----
+ * Compresses a device-resident stream (the gg_out of a gg_run_*) into BGZF members (blocked gzip: zcat/gzstream/htslib read it)
+ * on the GPU: Huffman-only deflate with one dynamic code per stream, one member per 65280 input bytes, CRC-32 computed on the
+ * device.  out->dev_ptr/bytes = the members back to back (fetch with gg_out_fetch); the 28-byte BGZF EOF marker is NOT appended
+ * (the writer of the file appends it once).  out->in_bytes = uncompressed bytes. */
+int  gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out);
+/* the same for a stream in host memory (H2D copy, then gg_bgzf_dev) */
+int  gg_bgzf_host(gg_ctx* ctx, const void* src, size_t n, gg_out* out);
+
 /* copy a run's bytes to the host (pinned staging inside; blocking) */
 int  gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n);
 /* CUDA-event time (ms) of the kernels of the last gg_run_* on this context */

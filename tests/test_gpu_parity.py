@@ -383,3 +383,51 @@ def test_fused_mixed_damage_slots(oracle_mod, genomes):
     diff = [(a, b) for (_, s), (_, t) in zip(util.records(recs), util.records(dam)) for a, b in zip(s, t) if a != b]
     assert len(diff) > 200 and set(diff) == {(ord("C"), ord("T"))}       # -damagess: C->T only (deamSim.cpp:1337-1468)
     g.close(); o.close()
+
+
+def _bgzf_members(z):
+    """walk the BGZF members: (offset, BSIZE, ISIZE) from the BC extra field"""
+    out, p = [], 0
+    while p < len(z):
+        assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 10:p + 16] == b"\x06\x00BC\x02\x00", "not a BGZF member at %d" % p
+        bsize = int.from_bytes(z[p + 16:p + 18], "little") + 1
+        out.append((p, bsize, int.from_bytes(z[p + bsize - 4:p + bsize], "little")))
+        p += bsize
+    assert p == len(z)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 700, 2500])
+def test_device_bgzf_round_trip(oracle_mod, genomes, n):
+    """gg_bgzf_dev: the members inflate (zlib checks every CRC-32 and ISIZE) to exactly the stream the oracle gives; member
+    framing is valid BGZF (BC field, BSIZE, <= 64 KiB, 65280 input bytes per member)."""
+    import gzip
+    import zlib
+    g, o, ids = _pair(oracle_mod, genomes)
+    plan = util.plan3(ids, counts=(1000, 700, 800))
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in (api.EMIT_FRAG, api.EMIT_ARTP):
+        z, info, zi = g.run_fused_bgzf(0, n, emit)
+        want = o.run_fused(0, n, emit)[0]
+        assert gzip.decompress(z + api.BGZF_EOF) == want
+        mem = _bgzf_members(z)
+        assert len(mem) == (len(want) + 65279) // 65280 and all(b <= 65536 for _, b, _ in mem)
+        assert [i for _, _, i in mem] == [min(65280, len(want) - 65280 * k) for k in range(len(mem))]
+        for k, (off, bsize, isize) in enumerate(mem[:3]):               # each member is a self-contained gzip file
+            assert zlib.decompress(z[off:off + bsize], wbits=31) == want[k * 65280:k * 65280 + isize]
+        assert zi.in_bytes == len(want) and zi.bytes == len(z) and zi.launches == 2
+        if len(want) > 50000:
+            assert len(z) < 0.45 * len(want)                            # ~2.6 bits per byte on FASTA of reads
+    g.close(); o.close()
+
+
+def test_device_bgzf_incompressible_and_binary(oracle_mod):
+    """Streams the code was not built for: all 256 byte values, and random bytes (members fall back to stored blocks)."""
+    import gzip
+    rng = np.random.default_rng(3)
+    g = api.Context(0, 1)
+    for data in (bytes(range(256)) * 600, rng.integers(0, 256, size=200_000, dtype=np.uint8).tobytes(), b"A" * 70000, b"ACGT\n" * 13057 + b"x", b"", b"G"):
+        z, zi = g.bgzf(data)
+        assert gzip.decompress(z + api.BGZF_EOF) == data
+        assert all(b <= 65536 for _, b, _ in _bgzf_members(z)) and zi.in_bytes == len(data)
+    g.close()

@@ -250,3 +250,40 @@ def test_dnacomp_parser(tmp_path, golden):
         for a, b in zip(got, synth.golden_dnacomp()):
             assert np.array_equal(a, b)
     assert len(golden["dnacomp_dist2"]) == 4 and len(golden["dnacomp_dist2"][0]) == 4
+
+
+def test_deflate_code_for_device_bgzf():
+    """ggh::build_deflate_code: the dynamic-Huffman description + per-symbol codes the device encoder uses decode under zlib for
+    any byte values (unseen bytes still get a code), also when the histogram forces the 15-bit length limit; CRC shift algebra."""
+    import ctypes as C
+    import zlib
+    lib = api.load_library()
+    lib.ggh_crc32_x8n.restype = C.c_uint32; lib.ggh_crc32_mul.restype = C.c_uint32
+    rng = np.random.default_rng(0)
+    fasta = b"".join(b">chr1:+:%d:%d:75e1_0\n%s\n" % (i * 3, i * 3 + 75, synth._BASES[rng.integers(0, 4, size=150)].tobytes()) for i in range(300))
+
+    def code_for(hist):
+        sym = (C.c_uint32 * 257)(); hdr = C.create_string_buffer(512); nb = C.c_int(0)
+        assert lib.ggh_deflate_code((C.c_uint64 * 256)(*hist), sym, hdr, 512, C.byref(nb)) == 0
+        assert all(1 <= (sym[i] >> 16) <= 15 for i in range(257)) and nb.value <= 1280
+
+        def encode(d):
+            bits, n = 0, 0
+            for i in range(nb.value):
+                bits |= ((hdr.raw[i >> 3] >> (i & 7)) & 1) << n; n += 1
+            for b in list(d) + [256]:
+                bits |= (sym[b] & 0xFFFF) << n; n += sym[b] >> 16
+            return bits.to_bytes((n + 7) // 8, "little"), n
+        return sym, encode
+    sym, enc = code_for(np.bincount(np.frombuffer(fasta, dtype=np.uint8), minlength=256).tolist())
+    raw, nbits = enc(fasta)
+    assert zlib.decompress(raw, wbits=-15) == fasta and nbits / len(fasta) < 3.0
+    assert max(sym[c] >> 16 for c in b"ACGT") <= 3
+    allbytes = bytes(range(256)) * 3
+    assert zlib.decompress(enc(allbytes)[0], wbits=-15) == allbytes
+    sym2, enc2 = code_for([int(1.7 ** i) if i < 60 else 0 for i in range(256)])        # Fibonacci-like: unlimited depth would be ~60
+    assert max(sym2[i] >> 16 for i in range(257)) == 15
+    assert zlib.decompress(enc2(allbytes)[0], wbits=-15) == allbytes
+    a, b = fasta[:1234], fasta[1234:]
+    comb = lib.ggh_crc32_mul(C.c_uint32(zlib.crc32(a)), C.c_uint32(lib.ggh_crc32_x8n(C.c_uint64(len(b))))) ^ zlib.crc32(b)
+    assert comb == zlib.crc32(fasta)
