@@ -55,9 +55,7 @@ int main(int argc, char** argv) {
         for (size_t c = 0; c < chunks.size(); c++) {
             gg_out o;
             if (gg_run_adpt(ctx, recs.data() + chunks[c].off, chunks[c].bytes, passes[k].emit, first, &o) != GG_OK) return gg_fail(ctx, "adptSim kernel");
-            host.resize(o.bytes); size_t n = 0;
-            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
-            if (!passes[k].sink.write(host.data(), n)) return die("Error: write failed");
+            if (!passes[k].sink.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
             first += chunks[c].recs;
         }
         if (!passes[k].sink.close()) return die("Error: write failed");

@@ -77,6 +77,26 @@ struct Sink {
         pend.insert(pend.end(), (const uint8_t*)d, (const uint8_t*)d + n);
         return pend.size() >= (8u << 20) ? flush_blocks(false) : true;
     }
+    // a stream still on the device (the gg_out of a gg_run_*): plain sinks fetch and write it; gz sinks compress it ON THE DEVICE
+    // (gg_bgzf_dev) and fetch only the BGZF members.  GG_HOST_BGZF=1 keeps the host zlib path (for comparison).
+    bool write_out(gg_ctx* ctx, const gg_out& o, std::vector<uint8_t>& host) {
+        size_t n = 0;
+        if (!bgzf || getenv("GG_HOST_BGZF")) {
+            host.resize(o.bytes);
+            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return false;
+            return write(host.data(), n);
+        }
+        if (!pend.empty()) {                                               // members are independent: flush what the host path buffered
+            std::vector<uint8_t> z; std::string e;
+            if (!ggh::bgzf_compress(pend.data(), pend.size(), 0, 1, z, false, e) || fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
+            pend.clear();
+        }
+        gg_out z;
+        if (gg_bgzf_dev(ctx, &o, &z) != GG_OK) return false;
+        host.resize(z.bytes);
+        if (gg_out_fetch(ctx, &z, host.data(), host.size(), &n) != GG_OK) return false;
+        return fwrite(host.data(), 1, n, f) == n;
+    }
     bool close() {
         bool ok = true;
         if (f) { if (bgzf) ok = flush_blocks(true); ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; }

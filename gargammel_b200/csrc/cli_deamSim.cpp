@@ -98,9 +98,7 @@ int main(int argc, char** argv) {
     for (size_t c = 0; c < chunks.size(); c++) {
         gg_out o;
         if (gg_run_deam(ctx, recs.data() + chunks[c].off, chunks[c].bytes, 0, first, &o) != GG_OK) return gg_fail(ctx, "deamSim kernel");
-        host.resize(o.bytes); size_t n = 0;
-        if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
-        if (!out.write(host.data(), n)) return die("Error: write failed");
+        if (!out.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
         first += chunks[c].recs;
     }
     if (!out.close()) return die("Error: write failed");

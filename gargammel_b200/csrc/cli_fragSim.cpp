@@ -115,10 +115,11 @@ int main(int argc, char** argv) {
         const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
         gg_out o;
         if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
-        host.resize(o.bytes); size_t n = 0;
-        if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
-        if (uniqTags) { renamed.clear(); uniq.apply((const char*)host.data(), n, renamed); if (!out.write(renamed.data(), renamed.size())) return die("Error: write failed"); }
-        else if (!out.write(host.data(), n)) return die("Error: write failed");
+        if (uniqTags) {
+            host.resize(o.bytes); size_t n = 0;
+            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+            renamed.clear(); uniq.apply((const char*)host.data(), n, renamed); if (!out.write(renamed.data(), renamed.size())) return die("Error: write failed");
+        } else if (!out.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
     }
     if (!out.close()) return die("Error: write failed");
     gg_ctx_destroy(ctx);

@@ -1116,10 +1116,11 @@ cudaError_t launch_byte_hist(const uint8_t* in, uint64_t n, uint64_t group_strid
 
 __device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {      // polynomial product mod P, reflected (bit 31 = x^0)
     uint32_t p = 0;
-#pragma unroll 1
-    for (int i = 31; i >= 0; i--) {
-        if ((a >> i) & 1u) p ^= b;
-        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+        p ^= b & (uint32_t)((int32_t)a >> 31);                              // coefficient of x^i in a
+        a <<= 1;
+        b = (b >> 1) ^ (0xEDB88320u & (0u - (b & 1u)));
     }
     return p;
 }
@@ -1130,54 +1131,67 @@ __device__ __forceinline__ void put_bits_atomic(uint32_t* w, uint32_t bitpos, ui
     if (sh + (uint32_t)nbits > 32u) atomicOr(w + (bitpos >> 5) + 1, v >> (32u - sh));
 }
 
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void bgzf_prefetch(const BgzfParams& P, uint32_t b, uint8_t* s_dst, int tid) {
+    if (b >= P.n_blocks) return;
+    const uint64_t base = (uint64_t)b * BGZF_BLOCK;
+    const int nb = (int)min((uint64_t)BGZF_BLOCK, P.n - base);
+    for (int g = tid; g < BGZF_BLOCK / 16; g += BGZF_THREADS) {
+        const int valid = max(0, min(16, nb - 16 * g));                      // bytes past the stream are zero-filled
+        cp_async16_zfill(s_dst + 16 * g, P.in + base + (valid ? 16 * g : 0), valid);
+    }
+}
+
 __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_constant__ BgzfParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* const s_in = smem;                                             // 65280
-    uint32_t* const s_out = (uint32_t*)(smem + BGZF_BLOCK);                 // 65536 + 64 bytes
+    uint32_t* const s_out = (uint32_t*)(smem + 2 * BGZF_BLOCK);             // 65536 + 64 bytes: the member's payload image, bit 0 = first payload bit
     uint32_t* const s_tab = s_out + (65536 + 64) / 4;                       // BGZF_TAB_WORDS
-    uint32_t* const s_scan = s_tab + BGZF_TAB_WORDS;                        // 32 + 32 + 8
+    uint32_t* const s_scan = s_tab + BGZF_TAB_WORDS;                        // 32 + 32 + 16
     const uint32_t* const s_sym = s_tab + BGZF_TAB_SYM;
     const uint32_t* const s_crc = s_tab + BGZF_TAB_CRC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < BGZF_TAB_WORDS; i += BGZF_THREADS) s_tab[i] = __ldg(P.tab + i);
     const uint32_t eob = __ldg(P.tab + 256);
+    // members are handed out in order (look-back never waits on an unstarted one); the next member's input is prefetched with
+    // cp.async into the other input buffer while this one is encoded
+    if (tid == 0) s_scan[64] = atomicAdd(P.ticket, 1u);
     __syncthreads();
+    uint32_t b = s_scan[64];
+    int cur = 0;
+    bgzf_prefetch(P, b, smem, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    while (true) {
-        if (tid == 0) s_scan[64] = atomicAdd(P.ticket, 1u);                 // members are started in order: look-back never waits on an unstarted one
-        __syncthreads();
-        const uint32_t b = s_scan[64];
-        if (b >= P.n_blocks) break;
+    while (b < P.n_blocks) {
+        uint8_t* const s_in = smem + cur * BGZF_BLOCK;
         const uint64_t base = (uint64_t)b * BGZF_BLOCK;
         const int nb = (int)min((uint64_t)BGZF_BLOCK, P.n - base);
-        // ---- stage the input, clear the output image
-        for (int g = tid; g < BGZF_BLOCK / 16; g += BGZF_THREADS) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (16 * g + 16 <= nb) v = __ldg((const uint4*)(P.in + base) + g);
-            else if (16 * g < nb) { uint8_t t[16]; for (int k = 0; k < 16; k++) t[k] = (16 * g + k < nb) ? P.in[base + 16 * g + k] : 0; v = *(const uint4*)t; }
-            ((uint4*)s_in)[g] = v;
-        }
+        if (tid == 0) s_scan[71] = atomicAdd(P.ticket, 1u);
         for (int g = tid; g < (65536 + 64) / 16; g += BGZF_THREADS) ((uint4*)s_out)[g] = make_uint4(0, 0, 0, 0);
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
+        const uint32_t b_next = s_scan[71];
+        bgzf_prefetch(P, b_next, smem + (cur ^ 1) * BGZF_BLOCK, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- pass 1: bits and CRC of my run
         const int r0 = tid * BGZF_RUN;
         const int len = max(0, min(BGZF_RUN, nb - r0));
         const uint32_t* const wp = (const uint32_t*)(s_in + r0);
         uint32_t bits = 0, crc = 0xFFFFFFFFu;
-#pragma unroll 1
-        for (int w = 0; 4 * w < len; w++) {
+        const int nw = len >> 2;                                             // whole words; only the stream's last run has a tail
+#pragma unroll 2
+        for (int w = 0; w < nw; w++) {
             const uint32_t x = wp[w];
-            if (4 * w + 4 <= len) {
-                bits += (s_sym[x & 0xFFu] >> 16) + (s_sym[(x >> 8) & 0xFFu] >> 16) + (s_sym[(x >> 16) & 0xFFu] >> 16) + (s_sym[x >> 24] >> 16);
-                crc ^= x;
-                crc = s_crc[768 + (crc & 0xFFu)] ^ s_crc[512 + ((crc >> 8) & 0xFFu)] ^ s_crc[256 + ((crc >> 16) & 0xFFu)] ^ s_crc[crc >> 24];
-            } else {
-                for (int k = 0; 4 * w + k < len; k++) {
-                    const uint32_t c = (x >> (8 * k)) & 0xFFu;
-                    bits += s_sym[c] >> 16;
-                    crc = s_crc[(crc ^ c) & 0xFFu] ^ (crc >> 8);
-                }
-            }
+            bits += (s_sym[x & 0xFFu] >> 16) + (s_sym[(x >> 8) & 0xFFu] >> 16) + (s_sym[(x >> 16) & 0xFFu] >> 16) + (s_sym[x >> 24] >> 16);
+            crc ^= x;
+            crc = s_crc[768 + (crc & 0xFFu)] ^ s_crc[512 + ((crc >> 8) & 0xFFu)] ^ s_crc[256 + ((crc >> 16) & 0xFFu)] ^ s_crc[crc >> 24];
+        }
+        for (int k = 4 * nw; k < len; k++) {
+            const uint32_t c = s_in[r0 + k];
+            bits += s_sym[c] >> 16;
+            crc = s_crc[(crc ^ c) & 0xFFu] ^ (crc >> 8);
         }
         crc = len ? ~crc : 0u;
         // my run's CRC shifted over the bytes that follow it in the member (crc(A||B) = crc(A) * x^(8|B|) + crc(B))
@@ -1210,13 +1224,51 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_c
             for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
             const uint32_t data_bits = __shfl_sync(0xffffffffu, wi, 31);
             s_scan[lane] = wi - v;                                           // exclusive warp offsets
-            // ---- member size and its place in the output (decoupled look-back over members)
+            // member size: published at once so that successors can look back over it
             const uint32_t total_bits = (uint32_t)P.hdr_nbits + data_bits + (eob >> 16);
             uint32_t payload = (total_bits + 7u) >> 3;
             const bool stored = payload >= (uint32_t)nb + 5u;
             if (stored) payload = (uint32_t)nb + 5u;
+            if (lane == 0) {
+                st_volatile_u64(P.state + b, ((b == 0 ? 2ull : 1ull) << 62) | (18ull + payload + 8ull));
+                s_scan[67] = payload; s_scan[68] = stored ? 1u : 0u; s_scan[69] = c; s_scan[70] = data_bits;
+            }
+        }
+        __syncthreads();
+        const uint32_t payload = s_scan[67]; const bool stored = s_scan[68] != 0; const uint32_t crc_all = s_scan[69], data_bits = s_scan[70];
+        if (!stored) {
+            // ---- pass 2: pack my run's codes at my bit offset (first and last word shared with the neighbours: atomicOr)
+            const uint32_t bitpos = (uint32_t)P.hdr_nbits + s_scan[warp] + (inc - bits);
+            uint32_t* wout = s_out + (bitpos >> 5);
+            unsigned long long acc = 0; uint32_t fill = bitpos & 31u; bool first = true;
+            // two codes (<= 30 bits) are merged in 32-bit arithmetic, then shifted into the 64-bit window; one flush per pair at most
+#define BGZF_FLUSH() if (fill >= 32u) { if (first) { atomicOr(wout, (uint32_t)acc); first = false; } else *wout = (uint32_t)acc; wout++; acc >>= 32; fill -= 32u; }
+#pragma unroll 2
+            for (int w = 0; w < nw; w++) {
+                const uint32_t x = wp[w];
+                const uint32_t s0 = s_sym[x & 0xFFu], s1 = s_sym[(x >> 8) & 0xFFu], s2 = s_sym[(x >> 16) & 0xFFu], s3 = s_sym[x >> 24];
+                const uint32_t l0 = s0 >> 16, l2 = s2 >> 16;
+                const uint32_t p01 = (s0 & 0xFFFFu) | ((s1 & 0xFFFFu) << l0), p23 = (s2 & 0xFFFFu) | ((s3 & 0xFFFFu) << l2);
+                acc |= (unsigned long long)p01 << fill; fill += l0 + (s1 >> 16); BGZF_FLUSH();
+                acc |= (unsigned long long)p23 << fill; fill += l2 + (s3 >> 16); BGZF_FLUSH();
+            }
+            for (int k = 4 * nw; k < len; k++) {
+                const uint32_t sy = s_sym[s_in[r0 + k]];
+                acc |= (unsigned long long)(sy & 0xFFFFu) << fill; fill += sy >> 16; BGZF_FLUSH();
+            }
+#undef BGZF_FLUSH
+            if (fill > (first ? (bitpos & 31u) : 0u)) atomicOr(wout, (uint32_t)acc);
+            // the code description in front and the end-of-block code behind
+            if (tid >= 32 && tid < 32 + BGZF_HDR_WORDS * 2) {
+                const int piece = tid - 32;                                 // 16 bits each
+                const int nbp = min(16, P.hdr_nbits - 16 * piece);
+                if (nbp > 0) put_bits_atomic(s_out, 16u * (uint32_t)piece, (s_tab[BGZF_TAB_HDR + (piece >> 1)] >> (16 * (piece & 1))) & (0xFFFFu >> (16 - nbp)), nbp);
+            }
+            if (tid == BGZF_THREADS - 1) put_bits_atomic(s_out, (uint32_t)P.hdr_nbits + data_bits, eob & 0xFFFFu, (int)(eob >> 16));
+        }
+        // ---- the member's place in the output: decoupled look-back over the members before it (by now they have published)
+        if (warp == 0) {
             const unsigned long long S = 18ull + payload + 8ull;
-            if (lane == 0) st_volatile_u64(P.state + b, ((b == 0 ? 2ull : 1ull) << 62) | S);
             unsigned long long gofs = 0;
             if (b > 0) {
                 long long look = (long long)b - 1;
@@ -1234,47 +1286,14 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_c
             }
             if (lane == 0) {
                 if (b == P.n_blocks - 1) *P.total = gofs + S;
-                s_scan[65] = (uint32_t)gofs; s_scan[66] = (uint32_t)(gofs >> 32); s_scan[67] = payload; s_scan[68] = stored ? 1u : 0u; s_scan[69] = c; s_scan[70] = data_bits;
+                s_scan[65] = (uint32_t)gofs; s_scan[66] = (uint32_t)(gofs >> 32);
             }
         }
         __syncthreads();
         const unsigned long long gofs = (unsigned long long)s_scan[65] | ((unsigned long long)s_scan[66] << 32);
-        const uint32_t payload = s_scan[67]; const bool stored = s_scan[68] != 0; const uint32_t crc_all = s_scan[69], data_bits = s_scan[70];
-        const bool fits = gofs + 18ull + payload + 8ull <= P.out_cap;
-        uint8_t* const dst = P.out + gofs;
-        const uint32_t pad = (uint32_t)((gofs + 18ull) & 15ull);          // P.out is 16-byte aligned
-        if (fits && !stored) {
-            // ---- pass 2: pack my run's codes at my bit offset
-            uint32_t bitpos = 8u * pad + (uint32_t)P.hdr_nbits + s_scan[warp] + (inc - bits);
-            uint32_t* wout = s_out + (bitpos >> 5);
-            unsigned long long acc = 0; uint32_t fill = bitpos & 31u; bool first = true;
-#pragma unroll 1
-            for (int w = 0; 4 * w < len; w++) {
-                const uint32_t x = wp[w];
-                const int nk = min(4, len - 4 * w);
-                for (int k = 0; k < nk; k++) {
-                    const uint32_t sy = s_sym[(x >> (8 * k)) & 0xFFu];
-                    acc |= (unsigned long long)(sy & 0xFFFFu) << fill; fill += sy >> 16;
-                }
-                if (fill >= 32u) {                                          // at most 4 x 15 bits were added: one flush suffices? no: up to 60 -> flush while
-                    do {
-                        if (first) { atomicOr(wout, (uint32_t)acc); first = false; } else *wout = (uint32_t)acc;
-                        wout++; acc >>= 32; fill -= 32u;
-                    } while (fill >= 32u);
-                }
-            }
-            if (fill > (first ? (bitpos & 31u) : 0u)) atomicOr(wout, (uint32_t)acc);
-            // header bits and the end-of-block code
-            if (tid >= 32 && tid < 32 + BGZF_HDR_WORDS * 2) {
-                const int piece = tid - 32;                                 // 16 bits each
-                const int nbp = min(16, P.hdr_nbits - 16 * piece);
-                if (nbp > 0) put_bits_atomic(s_out, 8u * pad + 16u * (uint32_t)piece, (s_tab[BGZF_TAB_HDR + (piece >> 1)] >> (16 * (piece & 1))) & (0xFFFFu >> (16 - nbp)), nbp);
-            }
-            if (tid == BGZF_THREADS - 1) put_bits_atomic(s_out, 8u * pad + (uint32_t)P.hdr_nbits + data_bits, eob & 0xFFFFu, (int)(eob >> 16));
-        }
-        __syncthreads();
-        if (fits) {
+        if (gofs + 18ull + payload + 8ull <= P.out_cap) {
             // ---- member header (RFC 1952 + the BGZF "BC" extra field), payload, CRC-32 and ISIZE
+            uint8_t* const dst = P.out + gofs;
             if (tid < 18) {
                 const uint32_t bsize1 = 18u + payload + 8u - 1u;
                 const uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)(bsize1 & 0xFFu), (uint8_t)(bsize1 >> 8)};
@@ -1285,11 +1304,21 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_c
             }
             uint8_t* const pay = dst + 18;
             if (!stored) {
-                const uint8_t* img = (const uint8_t*)s_out;                 // image byte pad+k <-> pay[k]; (pay - pad) is 16-byte aligned
-                const uint32_t end = pad + payload;
+                // 16-byte stores at the output's own alignment: group g holds payload bytes [16g - A, 16g - A + 16), A = pay & 15,
+                // assembled from the image with byte funnel-shifts (the image starts at payload byte 0)
+                const uint32_t A = (uint32_t)((uintptr_t)pay & 15u);
+                const uint32_t end = A + payload;
+                const uint8_t* img = (const uint8_t*)s_out;
                 for (uint32_t g = tid; 16u * g < end; g += BGZF_THREADS) {
-                    if (16u * g >= pad && 16u * g + 16u <= end) *(uint4*)(pay - pad + 16u * g) = ((const uint4*)img)[g];
-                    else for (uint32_t k = max(16u * g, pad); k < min(16u * g + 16u, end); k++) pay[k - pad] = img[k];
+                    if (16u * g >= A && 16u * g + 16u <= end) {
+                        const uint32_t s0 = 16u * g - A;                    // first payload byte of the group
+                        const uint32_t* wsrc = s_out + (s0 >> 2);
+                        const uint32_t sh = 8u * (s0 & 3u);
+                        uint4 v;
+                        v.x = __funnelshift_r(wsrc[0], wsrc[1], sh); v.y = __funnelshift_r(wsrc[1], wsrc[2], sh);
+                        v.z = __funnelshift_r(wsrc[2], wsrc[3], sh); v.w = __funnelshift_r(wsrc[3], wsrc[4], sh);
+                        *(uint4*)(pay - A + 16u * g) = v;
+                    } else for (uint32_t k = max(16u * g, A); k < min(16u * g + 16u, end); k++) pay[k - A] = img[k - A];
                 }
             } else {
                 if (tid < 5) { const uint32_t L = (uint32_t)nb; const uint8_t sh[5] = {1, (uint8_t)(L & 0xFFu), (uint8_t)(L >> 8), (uint8_t)(~L & 0xFFu), (uint8_t)((~L >> 8) & 0xFFu)}; pay[tid] = sh[tid]; }
@@ -1297,10 +1326,12 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_c
             }
         } else if (tid == 0) atomicOr(P.total + 1, 1ull);                   // capacity error flag
         __syncthreads();
+        b = b_next; cur ^= 1;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 cudaError_t bgzf_prepare(size_t* smem_bytes) {
-    const size_t sm = (size_t)BGZF_BLOCK + 65536 + 64 + (size_t)BGZF_TAB_WORDS * 4 + 80 * 4;
+    const size_t sm = 2 * (size_t)BGZF_BLOCK + 65536 + 64 + (size_t)BGZF_TAB_WORDS * 4 + 80 * 4;
     *smem_bytes = sm;
     return cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 }
