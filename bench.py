@@ -275,6 +275,8 @@ def main():
     ap.add_argument("--frags", type=int, default=FRAGS_PER_STEP, help="fragments per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="fragments per chunk of the plain e2e path (0 = one gg_run_fused + one gg_out_fetch)")
+    ap.add_argument("--bgzf-chunk", type=int, default=1 << 19, help="fragments per chunk of the device-BGZF e2e pipeline (0 = one piece)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -353,6 +355,8 @@ def main():
             gids = [ctx.upload_genome(t, fai) for t, fai in pinned_src]
             p2, _, _ = make_plan(api, n * world, gids)
             ctx.set_plan(p2)
+            if args.e2e_chunk > 0:
+                return ctx.run_fused_to_host(first, count, api.EMIT_ARTP, host_out.data_ptr(), cap, args.e2e_chunk)
             return ctx.run_fused_into(first, count, api.EMIT_ARTP, host_out.data_ptr(), cap)
         e2e_step()
         barrier()
@@ -365,7 +369,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": count * world * e_steps / float(te.item()), "unit": "fragments/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(ei.bytes), "steps": e_steps,
-               "what": "per step: gg_genome_upload x3 from pinned host + gg_run_fused + gg_out_fetch to pinned host (PCIe-bound: the D2H of the FASTA stream)"}
+               "chunk_fragments": args.e2e_chunk,
+               "what": "per step: gg_genome_upload x3 from pinned host + gg_run_fused_to_host (fused kernel per chunk, D2H of chunk k overlapping kernel k+1) to pinned host; PCIe-bound: the D2H of the FASTA stream"}
         # the same with host BGZF of the byte stream on all host threads (north_star: with and without gzip/BGZF output)
         try:
             import ctypes as C
@@ -394,8 +399,13 @@ def main():
                 gids = [ctx.upload_genome(t, fai) for t, fai in pinned_src]
                 p2, _, _ = make_plan(api, n * world, gids)
                 ctx.set_plan(p2)
+                if args.bgzf_chunk > 0:
+                    zi_ = ctx.run_fused_bgzf_to_host(first, count, api.EMIT_ARTP, zhost.data_ptr(), zcap, args.bgzf_chunk)
+                    return zi_, zi_
                 return ctx.run_fused_bgzf(first, count, api.EMIT_ARTP, zhost.data_ptr(), zcap)
             zhost = torch.empty(zcap, dtype=torch.uint8, pin_memory=True)
+            ctx.run_fused_bgzf(first, count, api.EMIT_ARTP, zhost.data_ptr(), zcap)             # (first call allocates the slabs)
+            _, z0 = ctx.run_fused_bgzf(first, count, api.EMIT_ARTP, zhost.data_ptr(), zcap)     # untimed: the compression alone, in one piece
             e2e_step_z()
             barrier()
             td0 = time.perf_counter()
@@ -407,8 +417,9 @@ def main():
                 dist.all_reduce(td, op=dist.ReduceOp.MAX)
             e2e["with_device_bgzf"] = {"value": count * world * e_steps / float(td.item()), "unit": "fragments/s", "steps": e_steps,
                                        "d2h_bytes_per_step": int(zi.bytes), "uncompressed_bytes_per_step": int(zi.in_bytes),
-                                       "bgzf_device_ms": zi.device_ms, "bgzf_GBps_in": zi.in_bytes / (zi.device_ms / 1e3) / 1e9,
-                                       "what": "per step: gg_genome_upload x3 + gg_run_fused + gg_bgzf_dev + gg_out_fetch of the BGZF members to pinned host"}
+                                       "bgzf_device_ms": z0.device_ms, "bgzf_GBps_in": z0.in_bytes / (z0.device_ms / 1e3) / 1e9,
+                                       "chunk_fragments": args.bgzf_chunk,
+                                       "what": "per step: gg_genome_upload x3 + gg_run_fused_bgzf_to_host (fused kernel + device BGZF per chunk, D2H of the members overlapped with the next chunk)"}
             if rank == 0:
                 import zlib
                 zb = zhost[:int(zi.bytes)].numpy()

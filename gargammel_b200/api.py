@@ -251,6 +251,13 @@ class Context:
         self._ck(self._f("out_fetch")(self._h, C.byref(z), C.c_void_p(host_ptr), C.c_size_t(cap), C.byref(n)))
         return _info(o), _info(z)
 
+    def run_fused_bgzf_to_host(self, first, count, emit, host_ptr, cap, chunk=0):
+        """gg_run_fused_bgzf_to_host: chunked fused run + device BGZF, D2H of the members overlapped with the next chunk."""
+        o = _Out()
+        self._ck(self._f("run_fused_bgzf_to_host")(self._h, C.c_uint64(first), C.c_uint64(count), C.c_int(emit), C.c_void_p(host_ptr),
+                                                   C.c_size_t(cap), C.c_uint64(chunk), C.byref(o)))
+        return _info(o)
+
     def bgzf(self, data: bytes):
         """gg_bgzf_host: BGZF members of a host byte string, compressed on the device (no EOF marker)."""
         z = _Out()

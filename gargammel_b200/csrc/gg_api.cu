@@ -106,9 +106,11 @@ struct gg_ctx {
     std::vector<std::pair<void*, size_t> > pool;     // device blocks of cleared genomes, reused by the next uploads
     DBuf d_tmp_fa, d_tmp_desc;                       // upload staging (raw FASTA bytes, contig descriptors)
     DBuf d_out, d_out2, d_tile_state, d_ticket_stats, d_in, d_nl, d_scan, d_sizes, d_flush;
-    DBuf d_bgzf, d_bgzf_tab, d_bgzf_state;           // device BGZF: output slab, code/CRC tables, look-back state + histogram
+    DBuf d_bgzf, d_bgzf2, d_bgzf_tab, d_bgzf_state;  // device BGZF: output slabs (ping-pong), code/CRC tables, look-back state + histogram
+    int bgzf_slab, bgzf_reuse_code, bgzf_hdr_nbits;  // pipeline state of gg_run_fused_bgzf_to_host
     std::vector<uint32_t> bgzf_static;               // CRC tables and shift polynomials (built once)
     void* h_pinned; size_t h_pinned_cap;
+    unsigned long long* h_pub; unsigned long long* d_pub;   // 512 u64 of mapped pinned memory: small results published by k_publish
     double last_ms;
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -120,6 +122,19 @@ struct gg_ctx {
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call); } while (0)
 
 namespace {
+
+// n u64 words of device memory -> host, through mapped pinned memory (see k_publish); syncs the compute stream
+int fetch_small(gg_ctx* ctx, const void* dsrc, unsigned long long* host, int n) {
+    if (n > 512) return ctx->fail(GG_ERR_ARG, "fetch_small: too many words");
+    if (!ctx->h_pub) {
+        CK(cudaHostAlloc((void**)&ctx->h_pub, 512 * 8, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&ctx->d_pub, ctx->h_pub, 0));
+    }
+    CK(launch_publish((const unsigned long long*)dsrc, ctx->d_pub, n, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    memcpy(host, ctx->h_pub, (size_t)n * 8);
+    return GG_OK;
+}
 
 template <typename T> int upload_vec(gg_ctx* ctx, DBuf& b, const std::vector<T>& v, size_t slack_elems = 0) {
     const size_t bytes = (v.size() + slack_elems) * sizeof(T);
@@ -319,7 +334,8 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
     ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
-    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0;
+    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0; ctx->h_pub = ctx->d_pub = nullptr;
+    ctx->bgzf_slab = 0; ctx->bgzf_reuse_code = 0; ctx->bgzf_hdr_nbits = 0;
     for (int i = 0; i < GG_MAX_GC_SLOTS; i++) { ctx->gc[i].on = false; ctx->gc[i].wmax = -1; }
     for (int i = 0; i < GG_MAX_COMP_SLOTS; i++) { ctx->comp[i].dist = 0; ctx->comp[i].maxP = ctx->comp[i].maxM = 1.0; }
     cudaDeviceProp prop;
@@ -348,6 +364,7 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     }
     for (size_t i = 0; i < ctx->pool.size(); i++) cudaFree(ctx->pool[i].first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_pub) cudaFreeHost(ctx->h_pub);
     cudaStreamSynchronize(ctx->st_copy);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_k[i]); cudaEventDestroy(ctx->ev_c[i]); }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st_copy);
@@ -856,8 +873,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(launch_fused(P, grid, warps * 32, ctx->st));
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long stats[ST_N];
-    CK(cudaMemcpyAsync(stats, P.stats, sizeof stats, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    { int rcp = fetch_small(ctx, P.stats, stats, ST_N); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     out->dev_ptr = oslab.p; out->bytes = stats[ST_TOTAL]; out->records = count;
@@ -1050,7 +1066,8 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
     const uint64_t n_blocks = (n + BGZF_BLOCK - 1) / BGZF_BLOCK;
     if (n_blocks > 0xFFFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_bgzf_dev: stream too long");
     const uint64_t out_cap = n + n_blocks * (18 + 5 + 8) + 64;            // every member at worst stored
-    CK(ctx->d_bgzf.ensure(out_cap));
+    DBuf& oslab = ctx->bgzf_slab ? ctx->d_bgzf2 : ctx->d_bgzf;
+    CK(oslab.ensure(out_cap));
     CK(ctx->d_bgzf_tab.ensure((size_t)BGZF_TAB_WORDS * 4));
     CK(ctx->d_bgzf_state.ensure((size_t)n_blocks * 8 + 256 * 8 + 64));
     unsigned long long* d_state = ctx->d_bgzf_state.as<unsigned long long>();
@@ -1059,41 +1076,75 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
     unsigned int* d_ticket = (unsigned int*)(d_total + 2);
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(d_state, 0, (size_t)n_blocks * 8 + 256 * 8 + 32, ctx->st));
+    int launches = 1;
+    if (!(ctx->bgzf_reuse_code && ctx->bgzf_hdr_nbits > 0)) {      // (the chunked pipeline keeps the code of its first chunk)
     // 1. sampled byte histogram (<= ~32 MB of the stream) -> one dynamic Huffman code for the whole stream
-    const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
-    CK(launch_byte_hist((const uint8_t*)in->dev_ptr, n, stride, d_hist, ctx->st));
-    unsigned long long hist[256];
-    CK(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    ggh::DeflateCode code; std::string e;
-    uint64_t h64[256]; for (int i = 0; i < 256; i++) h64[i] = hist[i];
-    if (!ggh::build_deflate_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
-    if (code.header_nbits > BGZF_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
-    if (ctx->bgzf_static.empty()) {
-        ctx->bgzf_static.assign(BGZF_TAB_WORDS, 0u);
-        uint32_t t[4][256]; ggh::crc32_tables(t);
-        memcpy(&ctx->bgzf_static[BGZF_TAB_CRC], t, sizeof t);
-        for (int k = 0; k < BGZF_THREADS; k++) ctx->bgzf_static[BGZF_TAB_SHIFT + k] = ggh::crc32_x8n((uint64_t)BGZF_RUN * (uint64_t)(BGZF_THREADS - 1 - k));
-        for (int k = 0; k < 17; k++) ctx->bgzf_static[BGZF_TAB_X8 + k] = ggh::crc32_x8n(1ull << k);
+        const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
+        CK(launch_byte_hist((const uint8_t*)in->dev_ptr, n, stride, d_hist, ctx->st));
+        unsigned long long hist[256];
+        { int rcp = fetch_small(ctx, d_hist, hist, 256); if (rcp) return rcp; }
+        ggh::DeflateCode code; std::string e;
+        uint64_t h64[256]; for (int i = 0; i < 256; i++) h64[i] = hist[i];
+        if (!ggh::build_deflate_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
+        if (code.header_nbits > BGZF_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
+        if (ctx->bgzf_static.empty()) {
+            ctx->bgzf_static.assign(BGZF_TAB_WORDS, 0u);
+            uint32_t t[4][256]; ggh::crc32_tables(t);
+            memcpy(&ctx->bgzf_static[BGZF_TAB_CRC], t, sizeof t);
+            for (int k = 0; k < BGZF_THREADS; k++) ctx->bgzf_static[BGZF_TAB_SHIFT + k] = ggh::crc32_x8n((uint64_t)BGZF_RUN * (uint64_t)(BGZF_THREADS - 1 - k));
+            for (int k = 0; k < 17; k++) ctx->bgzf_static[BGZF_TAB_X8 + k] = ggh::crc32_x8n(1ull << k);
+        }
+        std::vector<uint32_t> tab(ctx->bgzf_static);
+        memcpy(&tab[BGZF_TAB_SYM], code.sym, sizeof code.sym);
+        for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
+        CK(cudaMemcpyAsync(ctx->d_bgzf_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));                                 // tab is a local
+        ctx->bgzf_hdr_nbits = code.header_nbits; launches = 2;
     }
-    std::vector<uint32_t> tab(ctx->bgzf_static);
-    memcpy(&tab[BGZF_TAB_SYM], code.sym, sizeof code.sym);
-    for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
-    CK(cudaMemcpyAsync(ctx->d_bgzf_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->st));
     // 2. one CTA per 65280-byte member, persistent over the SMs
     BgzfParams P;
-    P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = ctx->d_bgzf.as<uint8_t>(); P.out_cap = out_cap;
-    P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = code.header_nbits; P.n_blocks = (uint32_t)n_blocks;
+    P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;
+    P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = ctx->bgzf_hdr_nbits; P.n_blocks = (uint32_t)n_blocks;
     P.state = d_state; P.ticket = d_ticket; P.total = d_total;
     CK(launch_bgzf_deflate(P, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
     CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long tot[2];
-    CK(cudaMemcpyAsync(tot, d_total, sizeof tot, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));                                     // (tab is a local: must outlive the copy)
+    { int rcp = fetch_small(ctx, d_total, tot, 2); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     if (tot[1]) return ctx->fail(GG_ERR_CAPACITY, "gg_bgzf_dev: output overflow");
-    out->dev_ptr = ctx->d_bgzf.p; out->bytes = tot[0]; out->device_ms = ms; out->launches = 2;
+    out->dev_ptr = oslab.p; out->bytes = tot[0]; out->device_ms = ms; out->launches = launches;
+    return GG_OK;
+}
+
+int gg_run_fused_bgzf_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* host_dst, size_t cap, uint64_t chunk, gg_out* out) {
+    if (!ctx || !out || (!host_dst && count)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_fused_bgzf_to_host: bad arguments") : GG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (chunk == 0) chunk = 1u << 20;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* dst = (uint8_t*)host_dst; size_t used = 0; int rc = GG_OK;
+    ctx->bgzf_hdr_nbits = 0;                                                // the first chunk builds the code, the others reuse it
+    for (uint64_t a = 0, i = 0; a < count; a += chunk, i++) {
+        const int slab = (int)(i & 1);
+        if (i >= 2) CK(cudaEventSynchronize(ctx->ev_c[slab]));              // the copy that last read this BGZF slab has finished
+        gg_out o, z;
+        rc = gg_run_fused(ctx, first + a, std::min<uint64_t>(chunk, count - a), emit, &o);
+        if (rc != GG_OK) break;
+        ctx->bgzf_slab = slab; ctx->bgzf_reuse_code = 1;
+        rc = gg_bgzf_dev(ctx, &o, &z);                                      // syncs the compute stream: the members are complete
+        if (rc != GG_OK) break;
+        if (used + z.bytes > cap) { rc = ctx->fail(GG_ERR_CAPACITY, "gg_run_fused_bgzf_to_host: destination too small"); break; }
+        CK(cudaMemcpyAsync(dst + used, z.dev_ptr, z.bytes, cudaMemcpyDeviceToHost, ctx->st_copy));   // overlaps the next chunk's kernels
+        CK(cudaEventRecord(ctx->ev_c[slab], ctx->st_copy));
+        used += z.bytes; out->bytes += z.bytes; out->in_bytes += o.bytes; out->records += o.records; out->attempts += o.attempts;
+        out->gather_bytes += o.gather_bytes; out->device_ms += o.device_ms + z.device_ms; out->launches += o.launches + z.launches;
+    }
+    ctx->bgzf_slab = 0; ctx->bgzf_reuse_code = 0;
+    cudaError_t e = cudaStreamSynchronize(ctx->st_copy);
+    if (rc != GG_OK) return rc;
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "gg_run_fused_bgzf_to_host: copy");
+    out->dev_ptr = nullptr;
+    ctx->last_ms = out->device_ms;
     return GG_OK;
 }
 

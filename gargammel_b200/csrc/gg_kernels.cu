@@ -1068,6 +1068,15 @@ cudaError_t launch_adpt_records(const RecStream& R, const unsigned long long* ou
     return cudaGetLastError();
 }
 
+// small results (byte totals, error flags, histograms) reach the host through SM stores into mapped pinned memory, not through the
+// copy engine: a 16-byte D2H memcpy queues behind whatever bulk D2H the egress stream has in flight and would serialise the pipeline
+__global__ void k_publish(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst_mapped, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+    __threadfence_system();
+}
+cudaError_t launch_publish(const unsigned long long* src, unsigned long long* dst_mapped, int n, cudaStream_t st) {
+    k_publish<<<1, 64, 0, st>>>(src, dst_mapped, n); return cudaGetLastError();
+}
 __global__ void __launch_bounds__(256) k_l2_flush(uint4* __restrict__ buf, uint64_t n16) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
         buf[i] = make_uint4((uint32_t)i, 0u, 1u, 2u);
@@ -1240,24 +1249,26 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const __grid_c
             // ---- pass 2: pack my run's codes at my bit offset (first and last word shared with the neighbours: atomicOr)
             const uint32_t bitpos = (uint32_t)P.hdr_nbits + s_scan[warp] + (inc - bits);
             uint32_t* wout = s_out + (bitpos >> 5);
-            unsigned long long acc = 0; uint32_t fill = bitpos & 31u; bool first = true;
-            // two codes (<= 30 bits) are merged in 32-bit arithmetic, then shifted into the 64-bit window; one flush per pair at most
-#define BGZF_FLUSH() if (fill >= 32u) { if (first) { atomicOr(wout, (uint32_t)acc); first = false; } else *wout = (uint32_t)acc; wout++; acc >>= 32; fill -= 32u; }
+            // pending bits live in lo (bits [0,fill) of the current word, fill < 32 between steps) and hi (the spill of one step);
+            // two codes (<= 30 bits) are merged in 32-bit arithmetic and enter with one shift + one funnel shift
+            uint32_t lo = 0, hi = 0, fill = bitpos & 31u; bool first = true;
+#define BGZF_PUT(p, n) { hi = __funnelshift_l((p), 0u, fill); lo |= (p) << fill; fill += (n); \
+                if (fill >= 32u) { if (first) { atomicOr(wout, lo); first = false; } else *wout = lo; wout++; lo = hi; fill -= 32u; } }
 #pragma unroll 2
             for (int w = 0; w < nw; w++) {
                 const uint32_t x = wp[w];
                 const uint32_t s0 = s_sym[x & 0xFFu], s1 = s_sym[(x >> 8) & 0xFFu], s2 = s_sym[(x >> 16) & 0xFFu], s3 = s_sym[x >> 24];
                 const uint32_t l0 = s0 >> 16, l2 = s2 >> 16;
                 const uint32_t p01 = (s0 & 0xFFFFu) | ((s1 & 0xFFFFu) << l0), p23 = (s2 & 0xFFFFu) | ((s3 & 0xFFFFu) << l2);
-                acc |= (unsigned long long)p01 << fill; fill += l0 + (s1 >> 16); BGZF_FLUSH();
-                acc |= (unsigned long long)p23 << fill; fill += l2 + (s3 >> 16); BGZF_FLUSH();
+                BGZF_PUT(p01, l0 + (s1 >> 16));
+                BGZF_PUT(p23, l2 + (s3 >> 16));
             }
             for (int k = 4 * nw; k < len; k++) {
                 const uint32_t sy = s_sym[s_in[r0 + k]];
-                acc |= (unsigned long long)(sy & 0xFFFFu) << fill; fill += sy >> 16; BGZF_FLUSH();
+                BGZF_PUT(sy & 0xFFFFu, sy >> 16);
             }
-#undef BGZF_FLUSH
-            if (fill > (first ? (bitpos & 31u) : 0u)) atomicOr(wout, (uint32_t)acc);
+#undef BGZF_PUT
+            if (fill > (first ? (bitpos & 31u) : 0u)) atomicOr(wout, lo);
             // the code description in front and the end-of-block code behind
             if (tid >= 32 && tid < 32 + BGZF_HDR_WORDS * 2) {
                 const int piece = tid - 32;                                 // 16 bits each

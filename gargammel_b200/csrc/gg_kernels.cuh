@@ -145,6 +145,7 @@ cudaError_t launch_adpt_sizes(const RecStream& R, int emit, Adapters ad, AdptNam
 cudaError_t launch_adpt_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, int emit, Adapters ad,
                                 const uint8_t* adF, const uint8_t* adS, AdptNaming nm, ggd::Key key, uint64_t first_id, cudaStream_t st);
 cudaError_t launch_l2_flush(uint4* buf, uint64_t n16, cudaStream_t st);
+cudaError_t launch_publish(const unsigned long long* src, unsigned long long* dst_mapped, int n, cudaStream_t st);
 constexpr int NL_BLOCK_BYTES = 1 << 16;
 
 } // namespace ggk

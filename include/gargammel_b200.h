@@ -203,6 +203,11 @@ int  gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit,
  * device.  out->dev_ptr/bytes = the members back to back (fetch with gg_out_fetch); the 28-byte BGZF EOF marker is NOT appended
  * (the writer of the file appends it once).  out->in_bytes = uncompressed bytes. */
 int  gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out);
+/* gg_run_fused + gg_bgzf_dev in chunks of `chunk` fragments (0 = 1 Mi), the D2H copy of chunk k's members overlapping the kernels of
+ * chunk k+1; one Huffman code (from the first chunk) for the whole stream.  host_dst should be pinned.  out->bytes = BGZF bytes
+ * written to host_dst, out->in_bytes = plain bytes they inflate to. */
+int  gg_run_fused_bgzf_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* host_dst, size_t cap,
+                               uint64_t chunk, gg_out* out);
 /* the same for a stream in host memory (H2D copy, then gg_bgzf_dev) */
 int  gg_bgzf_host(gg_ctx* ctx, const void* src, size_t n, gg_out* out);
 

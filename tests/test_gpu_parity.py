@@ -431,3 +431,22 @@ def test_device_bgzf_incompressible_and_binary(oracle_mod):
         assert gzip.decompress(z + api.BGZF_EOF) == data
         assert all(b <= 65536 for _, b, _ in _bgzf_members(z)) and zi.in_bytes == len(data)
     g.close()
+
+
+def test_fused_bgzf_to_host_chunked(oracle_mod, genomes):
+    """gg_run_fused_bgzf_to_host: chunk boundaries and the reused Huffman code leave the inflated stream untouched."""
+    import ctypes as C
+    import gzip
+    g, o, ids = _pair(oracle_mod, genomes)
+    plan = util.plan3(ids, counts=(3000, 2000, 2500))
+    g.set_plan(plan); o.set_plan(plan)
+    want = o.run_fused(0, 7500, api.EMIT_ARTP)[0]
+    buf = (C.c_uint8 * (len(want) + 65536))()
+    for chunk in (1000, 2048, 7500, 0):
+        info = g.run_fused_bgzf_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), len(buf), chunk)
+        z = bytes(buf[:info.bytes])
+        assert gzip.decompress(z + api.BGZF_EOF) == want and info.in_bytes == len(want) and info.records == 7500
+        _bgzf_members(z)
+    with pytest.raises(api.GGError):
+        g.run_fused_bgzf_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), 1000, 1000)
+    g.close(); o.close()
