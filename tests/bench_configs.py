@@ -7,14 +7,15 @@
   C5  fragSim only: -l 40 / -f sizefreq / -s sizedist on a 50 Mb genome (EMIT_FRAG), and the fused -artp variants
 
 Each line: fragments/s from CUDA-event time, algorithmic GB/s and the fraction of the measured HBM copy bandwidth.
-Sampled id windows of every run are checked bit-exact against the CPU oracle (tests may use the oracle; this is a test)."""
+Sampled id windows of every run are checked bit-exact against the CPU oracle: that makes this a test harness, so it lives under tests/
+(run it as `python tests/bench_configs.py`; it is not collected by pytest)."""
 import argparse
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
