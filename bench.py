@@ -465,7 +465,7 @@ def main():
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "fragments_per_step_per_gpu": count, "genome_bp_per_file": GENOME_BP, "read_len": READ_LEN, "seed": SEED,
                    "l2": "flushed between steps (256 MiB write, untimed); output per step (%.2f GB) exceeds L2" % (info.bytes / 1e9),
-                   "timing": "CUDA events on the launching stream around each step (memsets + k_fused), summed over steps, max over ranks",
+                   "timing": "CUDA events on the launching stream around each step (memsets + k_fused + k_publish = the byte count reaching the host through mapped memory), summed over steps, max over ranks",
                    "attempts_per_fragment": info.attempts / max(1, info.records), "bytes_per_fragment": alg_bytes / max(1, info.records)},
         "wall_ms_per_step": 1000.0 * (t1 - t0) / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -124,13 +124,14 @@ struct gg_ctx {
 namespace {
 
 // n u64 words of device memory -> host, through mapped pinned memory (see k_publish); syncs the compute stream
-int fetch_small(gg_ctx* ctx, const void* dsrc, unsigned long long* host, int n) {
+int fetch_small(gg_ctx* ctx, const void* dsrc, unsigned long long* host, int n, cudaEvent_t after = nullptr) {
     if (n > 512) return ctx->fail(GG_ERR_ARG, "fetch_small: too many words");
     if (!ctx->h_pub) {
         CK(cudaHostAlloc((void**)&ctx->h_pub, 512 * 8, cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer((void**)&ctx->d_pub, ctx->h_pub, 0));
     }
     CK(launch_publish((const unsigned long long*)dsrc, ctx->d_pub, n, ctx->st));
+    if (after) CK(cudaEventRecord(after, ctx->st));                         // the publish kernel belongs to the timed run
     CK(cudaStreamSynchronize(ctx->st));
     memcpy(host, ctx->h_pub, (size_t)n * 8);
     return GG_OK;
@@ -871,13 +872,12 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles * 8, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
     CK(launch_fused(P, grid, warps * 32, ctx->st));
-    CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long stats[ST_N];
-    { int rcp = fetch_small(ctx, P.stats, stats, ST_N); if (rcp) return rcp; }
+    { int rcp = fetch_small(ctx, P.stats, stats, ST_N, ctx->ev1); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     out->dev_ptr = oslab.p; out->bytes = stats[ST_TOTAL]; out->records = count;
-    out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = 1;
+    out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = 2;   // k_fused + k_publish
     if (stats[ST_ERR] & ERRF_GIVEUP) return ctx->fail(GG_ERR_GIVEUP, "gg_run_fused: a fragment exhausted its sampling attempts (genome without an admissible window?)");
     if (stats[ST_ERR] & ERRF_OVERFLOW) return ctx->fail(GG_ERR_CAPACITY, "gg_run_fused: internal staging/output overflow");
     return GG_OK;
@@ -1076,7 +1076,7 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
     unsigned int* d_ticket = (unsigned int*)(d_total + 2);
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(d_state, 0, (size_t)n_blocks * 8 + 256 * 8 + 32, ctx->st));
-    int launches = 1;
+    int launches = 2;                                                       // k_bgzf_deflate + k_publish
     if (!(ctx->bgzf_reuse_code && ctx->bgzf_hdr_nbits > 0)) {      // (the chunked pipeline keeps the code of its first chunk)
     // 1. sampled byte histogram (<= ~32 MB of the stream) -> one dynamic Huffman code for the whole stream
         const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
@@ -1099,7 +1099,7 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
         for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
         CK(cudaMemcpyAsync(ctx->d_bgzf_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));                                 // tab is a local
-        ctx->bgzf_hdr_nbits = code.header_nbits; launches = 2;
+        ctx->bgzf_hdr_nbits = code.header_nbits; launches = 4;     // + k_byte_hist + its k_publish
     }
     // 2. one CTA per 65280-byte member, persistent over the SMs
     BgzfParams P;
@@ -1107,9 +1107,8 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
     P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = ctx->bgzf_hdr_nbits; P.n_blocks = (uint32_t)n_blocks;
     P.state = d_state; P.ticket = d_ticket; P.total = d_total;
     CK(launch_bgzf_deflate(P, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
-    CK(cudaEventRecord(ctx->ev1, ctx->st));
     unsigned long long tot[2];
-    { int rcp = fetch_small(ctx, d_total, tot, 2); if (rcp) return rcp; }
+    { int rcp = fetch_small(ctx, d_total, tot, 2, ctx->ev1); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     if (tot[1]) return ctx->fail(GG_ERR_CAPACITY, "gg_bgzf_dev: output overflow");

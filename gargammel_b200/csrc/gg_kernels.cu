@@ -362,7 +362,6 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int emit = P.emit, RL = P.ad.read_len;
     const int nlines = emit_lines(emit);
-    const bool emit_prefetch = true;
 
     // 4 bases (one byte of codes) -> 4 ASCII chars
     for (int v = tid; v < 256; v += blockDim.x) {
@@ -485,13 +484,11 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 ok = true; break;
             }
             if (!ok) { my_err |= ERRF_GIVEUP; L = 0; idx = 0; }
-#ifndef GG_NO_PREFETCH
-            else if (emit_prefetch) {   // the gather of pass C is a dependent random access: start pulling its lines into L2 now
+            else {      // the gather of pass C is a dependent random access: start pulling its lines into L2 now (+6 % on a 6.2 Gb genome)
                 const uint32_t* sp = G.seq2 + (gpos >> 4);
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(sp));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + ((L + 15) >> 4)));
             }
-#endif
             my_gather += (unsigned long long)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
             const int nlen = __ldg(P.ctab.name_len + ci);

@@ -13,4 +13,9 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 3 -c 1 -o gpurun_out/${TAG}_fused $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
-ls -la gpurun_out/
+
+# device BGZF kernel: plain run, then one full capture (second launch: warm)
+python scripts/bgzf_probe.py > gpurun_out/${TAG}_bgzf_probe.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_bgzf_deflate -s 1 -c 1 -o gpurun_out/${TAG}_bgzf python scripts/bgzf_probe.py > gpurun_out/${TAG}_ncu_bgzf.log 2>&1
+python tests/bench_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err
+ls -la gpurun_out/ | tail -30
