@@ -57,7 +57,7 @@ struct Sink {
     bool open_stdout() { f = stdout; own = false; setvbuf(stdout, NULL, _IOFBF, 1 << 22); return true; }
     bool open_plain(const std::string& p) { f = fopen(p.c_str(), "wb"); own = true; if (f) setvbuf(f, NULL, _IOFBF, 1 << 22); return f != NULL; }
     bool open_gz(const std::string& p, bool append = false) { f = fopen(p.c_str(), append ? "ab" : "wb"); own = true; bgzf = true; return f != NULL; }
-    bool flush_blocks(bool final) {
+    bool flush_blocks(bool final, bool eof_marker = true) {
         const size_t B = 0xff00, whole = final ? pend.size() : pend.size() / B * B;
         if (whole) {
             std::vector<uint8_t> z; std::string e;
@@ -65,7 +65,7 @@ struct Sink {
             if (fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
             pend.erase(pend.begin(), pend.begin() + whole);
         }
-        if (final) {
+        if (final && eof_marker) {
             std::vector<uint8_t> z; std::string e;
             if (!ggh::bgzf_compress(NULL, 0, 1, 1, z, true, e)) return false;     // EOF marker block
             if (fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
@@ -97,10 +97,22 @@ struct Sink {
         if (gg_out_fetch(ctx, &z, host.data(), host.size(), &n) != GG_OK) return false;
         return fwrite(host.data(), 1, n, f) == n;
     }
-    bool close() {
+    // eof_marker = false: a part that will be concatenated with others (BGZF members are independent; one marker ends the file)
+    bool close(bool eof_marker = true) {
         bool ok = true;
-        if (f) { if (bgzf) ok = flush_blocks(true); ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; }
+        if (f) { if (bgzf) ok = flush_blocks(true, eof_marker); ok = (fflush(f) == 0) && ok; if (own) fclose(f); f = NULL; }
         return ok;
+    }
+    // device-resident run -> this sink through a pinned buffer, chunk by chunk with the copies overlapped (gg_run_fused[_bgzf]_to_host)
+    bool write_run(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, void* pinned, size_t cap) {
+        gg_out o;
+        if (bgzf && !getenv("GG_HOST_BGZF")) {
+            if (!pend.empty() && !flush_blocks(true, false)) return false;
+            if (gg_run_fused_bgzf_to_host(ctx, first, count, emit, pinned, cap, 1u << 19, &o) != GG_OK) return false;
+            return fwrite(pinned, 1, o.bytes, f) == o.bytes;
+        }
+        if (gg_run_fused_to_host(ctx, first, count, emit, pinned, cap, 1u << 20, &o) != GG_OK) return false;
+        return write(pinned, o.bytes);
     }
 };
 

@@ -175,10 +175,9 @@ int main(int argc, char** argv) {
     // ---- one worker per GPU: rank r takes the r-th contiguous slice of the id space; outputs are concatenated in rank order
     std::vector<std::string> shard(gpus), shard_err(gpus); std::vector<int> rcs(gpus, 0);
     std::vector<std::vector<std::string> > shard_keep(gpus, std::vector<std::string>(4));
-    auto worker = [&](int r) {
-        gg_ctx* ctx = NULL;
-        if (gg_ctx_create(r, seed, &ctx) != GG_OK) { shard_err[r] = "cannot open CUDA device " + std::to_string(r) + " (no CPU fallback)"; rcs[r] = 1; return; }
-        auto fail = [&](const char* what) { shard_err[r] = std::string(what) + ": " + gg_last_error(ctx); rcs[r] = 1; gg_ctx_destroy(ctx); };
+    // tables + plan of one rank's context; returns false (with shard_err[r]) on failure
+    auto setup = [&](int r, gg_ctx* ctx) -> bool {
+        auto fail = [&](const char* what) -> bool { shard_err[r] = std::string(what) + ": " + gg_last_error(ctx); return false; };
         std::vector<gg_range> plan; uint64_t first = 0;
         for (size_t k = 0; k < items.size(); k++) {
             int gid = -1;
@@ -188,18 +187,63 @@ int main(int argc, char** argv) {
         }
         const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
         if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
-        if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) { rcs[r] = 1; gg_ctx_destroy(ctx); return; }
+        if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) return false;
         const std::string* mis[3] = {&misE, &misB, &misC};
         for (int m = 0; m < 3; m++) if (!mis[m]->empty()) {                        // fragSim --comp F --dist D per source (gargammel.pl:1492-1495,1615-1618,1664-1667)
             ggh::CompTables ct; std::string e2;
-            if (!ggh::load_dnacomp(*mis[m], distmis, ct, e2)) { shard_err[r] = e2; rcs[r] = 1; gg_ctx_destroy(ctx); return; }
+            if (!ggh::load_dnacomp(*mis[m], distmis, ct, e2)) { shard_err[r] = e2; return false; }
             if (gg_tables_set_composition(ctx, m, ct.dist, ct.s5p.data(), ct.s5m.data(), ct.s3p.data(), ct.s3m.data()) != GG_OK) return fail("--misinc");
         }
         if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), rl) != GG_OK) return fail("adapters");
         if (!plan.empty() && gg_plan_set(ctx, plan.data(), (int)plan.size()) != GG_OK) return fail("plan");
+        return true;
+    };
+    const int emits[3] = {emit, GG_EMIT_FRAG, GG_EMIT_DEAM};
+    // Streaming path (everything but -uniq): every rank writes its slice straight to disk through a pinned buffer, the D2H copies
+    // overlapped with the kernels and the .gz outputs compressed on the device; nothing is held in host memory.  With several GPUs
+    // the ranks write <file>.part<r>, concatenated in rank order afterwards (BGZF members are independent).
+    const bool streaming = !uniq;
+    const char* gz_names[4] = {"_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz"};
+    auto part_name = [&](const std::string& final_name, int r) { return gpus == 1 ? final_name : final_name + ".part" + std::to_string(r); };
+    auto stream_worker = [&](int r) {
+        gg_ctx* ctx = NULL;
+        if (gg_ctx_create(r, seed, &ctx) != GG_OK) { shard_err[r] = "cannot open CUDA device " + std::to_string(r) + " (no CPU fallback)"; rcs[r] = 1; return; }
+        void* pin = NULL;
+        auto bail = [&](const std::string& m) { if (!m.empty()) shard_err[r] = m; rcs[r] = 1; if (pin) gg_host_free(ctx, pin); gg_ctx_destroy(ctx); };
+        if (!setup(r, ctx)) return bail("");
+        const uint64_t lo = total * (uint64_t)r / (uint64_t)gpus, hi = total * (uint64_t)(r + 1) / (uint64_t)gpus;
+        uint64_t rec_max = 1; for (int p = 0; p < (keep ? 3 : 1); p++) rec_max = std::max<uint64_t>(rec_max, gg_max_record_bytes(ctx, emits[p]));
+        const uint64_t chunk = std::max<uint64_t>(1u << 16, std::min<uint64_t>(4u << 20, (1ull << 30) / rec_max));   // <= 1 GiB of pinned memory
+        const size_t cap = (size_t)(chunk * rec_max + 65536);
+        if (gg_host_alloc(ctx, cap, &pin) != GG_OK) return bail(std::string("pinned buffer: ") + gg_last_error(ctx));
+        Sink a; if (!a.open_plain(part_name(prefix + "_a.fa", r))) return bail("Cannot write to file " + prefix + "_a.fa");
+        for (uint64_t x = lo; x < hi; x += chunk)
+            if (!a.write_run(ctx, x, std::min<uint64_t>(chunk, hi - x), emit, pin, cap)) return bail(std::string("fused kernel / write: ") + gg_last_error(ctx));
+        if (!a.close()) return bail("Error: write failed");
+        if (keep) {
+            // <prefix>_d.fa.gz = deamSim output in e,b,c order; <prefix>.{e,b,c}.fa.gz = the fragSim outputs per source class
+            Sink z[4];
+            for (int k = 0; k < 4; k++) if (!z[k].open_gz(part_name(prefix + gz_names[k], r))) return bail("Cannot write intermediate files for prefix " + prefix);
+            for (uint64_t x = lo; x < hi; x += chunk)
+                if (!z[0].write_run(ctx, x, std::min<uint64_t>(chunk, hi - x), GG_EMIT_DEAM, pin, cap)) return bail(std::string("fused kernel / write: ") + gg_last_error(ctx));
+            const uint64_t edge[4] = {0, ap.nE, ap.nE + ap.nB, total};             // ids are in e, b, c order
+            for (int k = 0; k < 3; k++) {
+                const uint64_t c0 = std::max(lo, edge[k]), c1 = std::min(hi, edge[k + 1]);
+                for (uint64_t x = c0; x < c1; x += chunk)
+                    if (!z[1 + k].write_run(ctx, x, std::min<uint64_t>(chunk, c1 - x), GG_EMIT_FRAG, pin, cap)) return bail(std::string("fused kernel / write: ") + gg_last_error(ctx));
+            }
+            for (int k = 0; k < 4; k++) if (!z[k].close(gpus == 1)) return bail("Error: write failed");
+        }
+        gg_host_free(ctx, pin); gg_ctx_destroy(ctx);
+    };
+    auto worker = [&](int r) {
+        if (streaming) return stream_worker(r);
+        gg_ctx* ctx = NULL;
+        if (gg_ctx_create(r, seed, &ctx) != GG_OK) { shard_err[r] = "cannot open CUDA device " + std::to_string(r) + " (no CPU fallback)"; rcs[r] = 1; return; }
+        auto fail = [&](const char* what) { shard_err[r] = std::string(what) + ": " + gg_last_error(ctx); rcs[r] = 1; gg_ctx_destroy(ctx); };
+        if (!setup(r, ctx)) { rcs[r] = 1; gg_ctx_destroy(ctx); return; }
         const uint64_t lo = total * (uint64_t)r / (uint64_t)gpus, hi = total * (uint64_t)(r + 1) / (uint64_t)gpus;
         const uint64_t chunk = 8u << 20;
-        int emits[3] = {emit, GG_EMIT_FRAG, GG_EMIT_DEAM};
         for (int pass = 0; pass < (keep ? 3 : 1); pass++)
             for (uint64_t a = lo; a < hi; a += chunk) {
                 const uint64_t cnt = std::min<uint64_t>(chunk, hi - a);
@@ -215,6 +259,25 @@ int main(int argc, char** argv) {
     for (int r = 0; r < gpus; r++) th.push_back(std::thread(worker, r));
     for (int r = 0; r < gpus; r++) th[r].join();
     for (int r = 0; r < gpus; r++) if (rcs[r]) return die("Error: " + shard_err[r]);
+    if (streaming) {
+        if (gpus > 1) {                                            // concatenate the parts in rank order
+            std::vector<char> buf(64u << 20);
+            for (int k = -1; k < (keep ? 4 : 0); k++) {
+                const std::string fin = prefix + (k < 0 ? "_a.fa" : gz_names[k]);
+                FILE* out = fopen(fin.c_str(), "wb"); if (!out) return die("Cannot write to file " + fin);
+                for (int r = 0; r < gpus; r++) {
+                    const std::string pn = part_name(fin, r);
+                    FILE* in2 = fopen(pn.c_str(), "rb"); if (!in2) return die("Cannot read " + pn);
+                    size_t got; while ((got = fread(buf.data(), 1, buf.size(), in2)) > 0) if (fwrite(buf.data(), 1, got, out) != got) return die("Error: write failed");
+                    fclose(in2); remove(pn.c_str());
+                }
+                if (k >= 0) { static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0}; fwrite(eof, 1, 28, out); }
+                if (fclose(out) != 0) return die("Error: write failed");
+            }
+        }
+        std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << total << " sequences to " << prefix << "_a.fa" << std::endl;
+        return 0;
+    }
     // -uniq: one defline counter per source file, exactly one fragSim invocation each in the reference
     auto uniq_pass = [&](std::vector<std::string>& parts) {
         std::string all; for (size_t r = 0; r < parts.size(); r++) { all += parts[r]; std::string().swap(parts[r]); }

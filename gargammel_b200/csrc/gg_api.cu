@@ -1168,6 +1168,20 @@ int gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, siz
     return GG_OK;
 }
 
+int gg_host_alloc(gg_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return ctx ? ctx->fail(GG_ERR_ARG, "gg_host_alloc: bad arguments") : GG_ERR_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx->fail(GG_ERR_NOMEM, "gg_host_alloc: cannot pin host memory"); }
+    return GG_OK;
+}
+int gg_host_free(gg_ctx* ctx, void* p) {
+    if (!ctx) return GG_ERR_ARG;
+    if (p) CK(cudaFreeHost(p));
+    return GG_OK;
+}
+
 int gg_flush_l2(gg_ctx* ctx) {
     if (!ctx) return GG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));

@@ -211,6 +211,10 @@ int  gg_run_fused_bgzf_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int 
 /* the same for a stream in host memory (H2D copy, then gg_bgzf_dev) */
 int  gg_bgzf_host(gg_ctx* ctx, const void* src, size_t n, gg_out* out);
 
+/* page-locked host memory for the *_to_host entry points (plain malloc'ed memory works too, at a fraction of the PCIe rate) */
+int  gg_host_alloc(gg_ctx* ctx, size_t bytes, void** out);
+int  gg_host_free(gg_ctx* ctx, void* p);
+
 /* copy a run's bytes to the host (pinned staging inside; blocking) */
 int  gg_out_fetch(gg_ctx* ctx, const gg_out* out, void* host_dst, size_t cap, size_t* n);
 /* CUDA-event time (ms) of the kernels of the last gg_run_* on this context */

@@ -19,8 +19,10 @@ for sub, names in (("endo", ["endo.1.fa"]), ("cont", ["cont.1.fa"]), ("bact", []
 synth.write_sizefreq(os.path.join(d, "sf.size"))
 outs = []
 for g in (1, 2):
-    r = subprocess.run(["bin/gargammel-b200", "--comp", "0,0.1,0.9", "-n", "300000", "-f", os.path.join(d, "sf.size"), "-damage", "0.03,0.4,0.01,0.3", "--seed", "9", "--gpus", str(g), "-o", os.path.join(d, "s%d" % g), os.path.join(d, "in")], stderr=subprocess.PIPE)
+    r = subprocess.run(["bin/gargammel-b200", "--comp", "0,0.1,0.9", "-n", "300000", "-f", os.path.join(d, "sf.size"), "-damage", "0.03,0.4,0.01,0.3", "--seed", "9", "--gpus", str(g), "--keep", "-o", os.path.join(d, "s%d" % g), os.path.join(d, "in")], stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr
-    outs.append(open(os.path.join(d, "s%d_a.fa" % g), "rb").read())
-print("driver 1 GPU vs 2 GPUs identical:", outs[0] == outs[1], len(outs[0]))
+    import gzip
+    outs.append([open(os.path.join(d, "s%d_a.fa" % g), "rb").read()] + [gzip.open(os.path.join(d, "s%d%s" % (g, sfx))).read() for sfx in ("_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz")])
+    assert not [f for f in os.listdir(d) if ".part" in f], "part files left behind"
+print("driver 1 GPU vs 2 GPUs identical (_a.fa, _d, .e, .b, .c):", [a == b for a, b in zip(outs[0], outs[1])], [len(a) for a in outs[0]])
 PY
