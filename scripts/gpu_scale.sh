@@ -7,7 +7,9 @@ for N in 1 2 4 8; do
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err; fi
   python - <<PY
 import json
-d=json.loads(open("gpurun_out/scale_$N.json").read().strip().splitlines()[-1])
-print("N=$N value %.3f G frag/s  ms/step %.3f  e2e %.1f M frag/s  bgzf %s  clocks %s" % (d["value"]/1e9, d["ms_per_step"], d["e2e"]["value"]/1e6, d["e2e"].get("with_bgzf",{}).get("value"), d["clocks"]))
+line=[l for l in open("gpurun_out/scale_$N.json").read().strip().splitlines() if l.startswith("{")][-1]
+open("gpurun_out/r01_scale_n$N.json","w").write(line+"\n")
+d=json.loads(line)
+print("N=$N value %.3f G frag/s  ms/step %.3f  e2e %.1f M frag/s  host-bgzf %s  device-bgzf %s  clocks %s" % (d["value"]/1e9, d["ms_per_step"], d["e2e"]["value"]/1e6, d["e2e"].get("with_bgzf",{}).get("value"), d["e2e"].get("with_device_bgzf",{}).get("value"), d["clocks"]))
 PY
 done
