@@ -817,6 +817,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int regs = 96, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
     int F = 32;
+    { const char* envF = getenv("GG_FUSED_F"); if (envF) F = std::max(1, std::min(32, atoi(envF))); }   // tuning knob, like GG_FUSED_WARPS
     while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) F >>= 1;
     if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
     const int ctas = envC ? std::max(1, atoi(envC)) : 1;
