@@ -109,17 +109,26 @@ int main(int argc, char** argv) {
     Sink out;
     if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); }       // fragSim.cpp:1297-1303
     else out.open_stdout();
-    const uint64_t chunk = 4u << 20;
     std::vector<uint8_t> host; UniqSuffixer uniq; uniq.reset(tag, tagb); std::string renamed;
-    for (uint64_t first = 0; first < nFragments; first += chunk) {
-        const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
-        gg_out o;
-        if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
-        if (uniqTags) {
+    if (uniqTags) {                                                                 // host-side counters over the plain stream
+        const uint64_t chunk = 4u << 20;
+        for (uint64_t first = 0; first < nFragments; first += chunk) {
+            const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
+            gg_out o;
+            if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
             host.resize(o.bytes); size_t n = 0;
             if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
             renamed.clear(); uniq.apply((const char*)host.data(), n, renamed); if (!out.write(renamed.data(), renamed.size())) return die("Error: write failed");
-        } else if (!out.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
+        }
+    } else {                                                                        // pinned staging, copies overlapped with the kernels, .gz made on the device
+        const uint64_t rec_max = std::max<uint64_t>(1, gg_max_record_bytes(ctx, GG_EMIT_FRAG));
+        const uint64_t chunk = std::max<uint64_t>(1u << 16, std::min<uint64_t>(4u << 20, (1ull << 30) / rec_max));
+        const size_t cap = (size_t)(std::min<uint64_t>(chunk, std::max<uint64_t>(nFragments, 1)) * rec_max + 65536);
+        void* pin = NULL;
+        if (gg_host_alloc(ctx, cap, &pin) != GG_OK) return gg_fail(ctx, "pinned buffer");
+        for (uint64_t first = 0; first < nFragments; first += chunk)
+            if (!out.write_run(ctx, first, std::min<uint64_t>(chunk, nFragments - first), GG_EMIT_FRAG, pin, cap)) return die(std::string("Error: fragSim kernel / write failed: ") + gg_last_error(ctx));
+        gg_host_free(ctx, pin);
     }
     if (!out.close()) return die("Error: write failed");
     gg_ctx_destroy(ctx);

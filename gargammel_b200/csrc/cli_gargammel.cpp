@@ -214,7 +214,7 @@ int main(int argc, char** argv) {
         const uint64_t lo = total * (uint64_t)r / (uint64_t)gpus, hi = total * (uint64_t)(r + 1) / (uint64_t)gpus;
         uint64_t rec_max = 1; for (int p = 0; p < (keep ? 3 : 1); p++) rec_max = std::max<uint64_t>(rec_max, gg_max_record_bytes(ctx, emits[p]));
         const uint64_t chunk = std::max<uint64_t>(1u << 16, std::min<uint64_t>(4u << 20, (1ull << 30) / rec_max));   // <= 1 GiB of pinned memory
-        const size_t cap = (size_t)(chunk * rec_max + 65536);
+        const size_t cap = (size_t)(std::min<uint64_t>(chunk, std::max<uint64_t>(hi - lo, 1)) * rec_max + 65536);
         if (gg_host_alloc(ctx, cap, &pin) != GG_OK) return bail(std::string("pinned buffer: ") + gg_last_error(ctx));
         Sink a; if (!a.open_plain(part_name(prefix + "_a.fa", r))) return bail("Cannot write to file " + prefix + "_a.fa");
         for (uint64_t x = lo; x < hi; x += chunk)
