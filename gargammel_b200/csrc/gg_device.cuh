@@ -178,12 +178,17 @@ __device__ __forceinline__ uint8_t complement_ascii(uint8_t c) {
     return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
 }
 
+static __constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 // decimal digits
 // (coordinates are < 2^33: contig lengths are u32 and fragment lengths <= 4095)
 __device__ __forceinline__ int ndigits(uint64_t v) {
-    return 1 + (v >= 10ull) + (v >= 100ull) + (v >= 1000ull) + (v >= 10000ull) + (v >= 100000ull) +
-           (v >= 1000000ull) + (v >= 10000000ull) + (v >= 100000000ull) + (v >= 1000000000ull) +
-           (v >= 10000000000ull);
+    if (v <= 0xFFFFFFFFull) {                      // floor(log10) from the bit length, corrected by one table compare
+        const uint32_t w = (uint32_t)v;
+        const uint32_t t = ((32u - (uint32_t)__clz((int)(w | 1u))) * 1233u) >> 12;      // 0..9
+        const uint32_t p10 = c_pow10[t];
+        return (int)(t + 1u - (w < p10 ? 1u : 0u)) + (w == 0u ? 1 : 0);
+    }
+    return v >= 10000000000ull ? 11 : 10;          // 2^32 .. 2^33: 10 digits below 1e10
 }
 
 } // namespace ggd

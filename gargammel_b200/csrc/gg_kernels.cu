@@ -665,15 +665,11 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             else {
                 uint8_t* const gal = P.out + gofs - pad;                 // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+T)
                 const int end = pad + (int)T;
-                const int nchunks = (end + 15) >> 4;
-                for (int c = lane; c < nchunks; c += 32) {
-                    const int s0 = 16 * c;
-                    if (s0 >= pad && s0 + 16 <= end) st_global_v4(gal + s0, *(const uint4*)(s_stage + s0));
-                    else {
-#pragma unroll 1
-                        for (int t = max(s0, pad); t < min(s0 + 16, end); t++) gal[t] = s_stage[t];
-                    }
-                }
+                const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
+                for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
+                // the partial head [pad, 16 c_lo) and tail [16 max(c_hi, c_lo), end): at most 15 bytes each, one byte per lane
+                const int t = lane < 16 ? pad + lane : 16 * max(c_hi, c_lo) + (lane - 16);
+                if (lane < 16 ? t < min(16 * c_lo, end) : t < end) gal[t] = s_stage[t];
             }
         }
         __syncwarp();
