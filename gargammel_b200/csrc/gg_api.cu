@@ -542,7 +542,7 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_MATRIX; H.rows5 = rows5; H.rows3 = rows3; H.clamp_last = clamp_last ? 1 : 0;
-    // device layout: rows5 real rows + sentinel, rows3 real rows + sentinel.  The sentinel is the last row when clamping
+    // device layout: rows5 real rows + sentinel, then sentinel + rows3 real rows in reverse order (distance rows3-1 .. 0).  The sentinel is the last row when clamping
     // (deamSim.cpp:1811-1813) or an identity row (base unchanged) with -last (deamSim.cpp:1814-1816).
     H.thr.assign((size_t)(rows5 + rows3 + 2) * 4, make_uint4(0, 0, 0, 0));
     for (int e = 0; e < 2; e++) {
@@ -570,7 +570,9 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
                     // the device picks (u>=K1)+(u>=K2)+(u>=K3): exact iff the last cumulative value covers every u31
                     if (k[3] != 2147483648u) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: cumulative probabilities of a row do not reach 1");
                 }
-                H.thr[(base + (size_t)r) * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
+                // 3' rows are stored in REVERSE (sentinel first, terminal base last): the row of position i is then max(i + c, base)
+                const size_t slot_r = e == 0 ? (size_t)r : base + (size_t)(rows - r);
+                H.thr[slot_r * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
             }
         }
     }

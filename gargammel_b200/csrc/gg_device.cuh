@@ -78,7 +78,8 @@ struct DamageDev {
     int rows5, rows3;    // matrix / single-double rows
     int clamp_last;      // matrix: clamp to last row (default) or skip (-last)
     // MATRIX: thr[(r*4+b)] = {K1,K2,K3,K4}: new base = first a with u31 < K[a+1] (K4 == 2^31 always, checked on the host).
-    // Layout: rows5 real 5' rows, one sentinel row (= last row when clamping, identity when -last), rows3 real 3' rows, sentinel.
+    // Layout: rows5 real 5' rows, one sentinel row (= last row when clamping, identity when -last), then the 3' block REVERSED:
+    // its sentinel, then distance rows3-1 .. 0, so that the row of position i on the 3' side is max(i + rows5+rows3+2-L, rows5+1).
     const uint4* thr;
     // SINGLE/DOUBLE: sd5[r] (C->T 5'), sd3[r] (C->T single / G->A double)
     const uint32_t* sd5; const uint32_t* sd3;
@@ -112,14 +113,14 @@ __device__ __forceinline__ int first_below_gallop(const uint32_t* __restrict__ t
 
 // -matfile, one base (deamSim.cpp:1794-1930): i = position, L = fragment length, b = code, x = raw Philox word
 __device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x) {
-    const int r = (i < (L >> 1)) ? min(i, D.rows5) : D.rows5 + 1 + min(L - 1 - i, D.rows3);   // sentinel rows absorb the clamp / -last cases
+    const int r = (i < (L >> 1)) ? min(i, D.rows5) : max(i + (D.rows5 + D.rows3 + 2 - L), D.rows5 + 1);   // sentinel rows absorb the clamp / -last cases
     const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
     const uint32_t u = x >> 1;
     return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z);
 }
 // same, returning the new base already placed in its 2-bit field: (new base) * unit with unit = 1 << 2j
 __device__ __forceinline__ uint32_t dmg_matrix_base_shifted(const DamageDev& D, int i, int L, uint32_t b, uint32_t x, uint32_t unit) {
-    const int r = (i < (L >> 1)) ? min(i, D.rows5) : D.rows5 + 1 + min(L - 1 - i, D.rows3);
+    const int r = (i < (L >> 1)) ? min(i, D.rows5) : max(i + (D.rows5 + D.rows3 + 2 - L), D.rows5 + 1);
     const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
     const uint32_t u = x >> 1;
     uint32_t v = 0;

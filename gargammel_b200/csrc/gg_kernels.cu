@@ -186,13 +186,13 @@ __device__ __forceinline__ uint32_t run_mask(int lo, int hi) {
 
 // ---- line image: the 2-bit packed sequence line(s) of one record, assembled once per fragment by its owner thread
 // (adptSim.cpp:288-322,396-411 restated as a concatenation of runs over 2-bit sources; D = damaged fragment in smem)
-struct BitAppender {
-    uint32_t* out; uint64_t acc; int fill;
+struct BitAppender {                  // pending bits: lo holds bits [0,fill) of the current word (fill < 32 between puts), hi one put's spill
+    uint32_t* out; uint32_t lo, hi; int fill;
     __device__ __forceinline__ void put(uint32_t x, int n) {        // n fields (1..16); fields of x above n are zero
-        acc |= (uint64_t)x << fill; fill += 2 * n;
-        if (fill >= 32) { *out++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        hi = __funnelshift_l(x, 0u, (uint32_t)fill); lo |= x << fill; fill += 2 * n;
+        if (fill >= 32) { *out++ = lo; lo = hi; fill -= 32; }
     }
-    __device__ __forceinline__ void flush() { if (fill > 0) *out++ = (uint32_t)acc; }
+    __device__ __forceinline__ void flush() { if (fill > 0) *out++ = lo; }
 };
 __device__ __forceinline__ void put_run_smem(BitAppender& A, const uint32_t* src, int start, int len) {
 #pragma unroll 1
@@ -251,7 +251,7 @@ __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) 
 // One packed sequence line: kind 0 = forward read, 1 = reverse read, 2 = forward read ++ revcomp(reverse read) (-artp).
 // Deliberately not inlined: it is called from two places and the kernel's code size matters (asynchronous warps).
 __device__ __noinline__ void build_line_image(const FusedParams& P, const uint32_t* D, int L, uint64_t id, int kind, uint32_t* out) {
-    BitAppender A; A.out = out; A.acc = 0; A.fill = 0;
+    BitAppender A; A.out = out; A.lo = 0; A.hi = 0; A.fill = 0;
     if (kind == 1) put_reverse_read(A, P, D, L, id);
     else {
         put_forward_read(A, P, D, L, id);
@@ -301,9 +301,9 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
     const int nq = (n + 3) >> 2;
     uint32_t Wn = 0;
     if (mode == 1) {                                     // -matfile: one uniform per base (deamSim.cpp:1847,1911)
-        const int R5 = D.rows5;
-        const uint32_t R3 = (uint32_t)D.rows3, r3base = (uint32_t)R5 + 1u;
-        const uint4* thr = DMODE == 1 ? thr_sm : D.thr;   // rows5 + sentinel, rows3 + sentinel; shared-memory copy in the matrix-only kernel
+        const int R5 = D.rows5, r3base = R5 + 1;
+        const int c3 = R5 + D.rows3 + 2 - fl;             // 3' rows are stored reversed: row(i) = max(i + c3, r3base)
+        const uint4* thr = DMODE == 1 ? thr_sm : D.thr;   // rows5 + sentinel, sentinel + rows3 reversed; shared-memory copy in the matrix-only kernel
         const int half = fl >> 1;                         // positions i < half are on the 5' side (deamSim.cpp:1805)
 #pragma unroll 1
         for (int q = 0; q < nq; q++) {
@@ -315,7 +315,7 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
             for (int jj = 0; jj < 4; jj++) {
                 const int i = i4 + jj;
                 const uint32_t b = (Wq >> (2 * jj)) & 3u;
-                const uint32_t r = (i < half) ? (uint32_t)min(i, R5) : r3base + min((uint32_t)(fl - 1 - i), R3);
+                const uint32_t r = (uint32_t)((i < half) ? min(i, R5) : max(i + c3, r3base));
                 const uint4 Tq = DMODE == 1 ? thr[r * 4u + b] : __ldg(thr + (r * 4u + b));
                 const uint32_t u = pick(x, jj) >> 1;
                 nb += (u >= Tq.z ? 3u : u >= Tq.y ? 2u : u >= Tq.x ? 1u : 0u) << (2 * jj);      // thresholds ascend: number of them <= u
