@@ -798,7 +798,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
 
     // One warp per tile of F = 32 fragments (fewer only if 32 maximal records do not fit one warp's shared memory);
     // warps per CTA chosen to fill the SM: limited by shared memory, registers and the kernel's launch bound.
-    const size_t sm_budget = std::min<size_t>(227 * 1024, ctx->smem_optin) - 2304;   // static: length guide table
+    const size_t sm_budget = std::min<size_t>(227 * 1024, ctx->smem_optin) - 2560;   // static: length guide table + two-digit table (2256 B)
     // specialised kernels: 1 = every used damage slot is a matrix, 2 = every used slot is Briggs, 0 = any mix
     bool has_matrix = false, has_briggs = false, has_other = false;
     for (size_t i = 0; i < ctx->plan.size(); i++) {

@@ -235,13 +235,15 @@ __device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedP
     put_run_smem(A, D, L - nD, nD);
 }
 
-__device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd) {
+// nd decimal digits of v at p; d100 = shared table of the 100 two-digit strings ("00".."99", low byte = tens)
+__device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd, const uint16_t* d100) {
     int k = nd - 1;
 #pragma unroll 1
     for (; v > 0xFFFFFFFFull; k--) { const uint64_t q = v / 10ull; p[k] = (uint8_t)('0' + (uint32_t)(v - q * 10ull)); v = q; }
     uint32_t w = (uint32_t)v;
 #pragma unroll 1
-    for (; k >= 0; k--) { const uint32_t q = w / 10u; p[k] = (uint8_t)('0' + (w - q * 10u)); w = q; }
+    for (; k >= 1; k -= 2) { const uint32_t q = w / 100u; const uint32_t two = d100[w - q * 100u]; p[k - 1] = (uint8_t)two; p[k] = (uint8_t)(two >> 8); w = q; }
+    if (k == 0) p[0] = (uint8_t)('0' + w);
     return p + nd;
 }
 
@@ -356,13 +358,16 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
 template <bool FASTB, int DMODE>
 __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint16_t s_d100[100];                // "00".."99" for the decimal fields of the deflines
     __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
     uint32_t* const s_lut = (uint32_t*)(smem + P.sm.lut);     // 256 x 4 ASCII bytes (CTA-shared)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int emit = P.emit, RL = P.ad.read_len;
     const int nlines = emit_lines(emit);
+    const int sfx0 = emit_suffix(emit, 0), sfx1 = emit_suffix(emit, 1);     // "_r" on line 0 / line 1
 
+    for (int v = tid; v < 100; v += blockDim.x) s_d100[v] = (uint16_t)(('0' + v / 10) | (('0' + v % 10) << 8));
     // 4 bases (one byte of codes) -> 4 ASCII chars
     for (int v = tid; v < 256; v += blockDim.x) {
         uint32_t w = 0;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             hdr = 1 + nlen + 3 + ndigits(idx) + 1 + ndigits(idx + (uint64_t)L) + 1 + ndigits((uint64_t)L) + tag_len;
             const int S = emit_seqlen(emit, L, RL);
             uint32_t bytes = 0;
-            for (int ln = 0; ln < nlines; ln++) bytes += hdr + emit_suffix(emit, ln) + 1 + S + 1;
+            for (int ln = 0; ln < nlines; ln++) bytes += hdr + (ln ? sfx1 : sfx0) + 1 + S + 1;
             const uint32_t chunks = (L + 15) >> 4;
             const uint32_t groups = nlines * (((S + 15) >> 4) + 1);
             pk = PK(bytes, chunks, groups);
@@ -601,12 +606,12 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
 #pragma unroll 1
                     for (int k = 0; k < nlen; k++) *p++ = (uint8_t)__ldg(nm + k);
                     *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
-                    p = put_decimal(p, idx, ndigits(idx)); *p++ = ':';
-                    p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L)); *p++ = ':';
-                    p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L));
+                    p = put_decimal(p, idx, ndigits(idx), s_d100); *p++ = ':';
+                    p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L), s_d100); *p++ = ':';
+                    p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L), s_d100);
 #pragma unroll 1
                     for (int k = 0; k < tag_len; k++) *p++ = (uint8_t)tag[k];
-                    if (emit_suffix(emit, ln)) { *p++ = '_'; *p++ = 'r'; }
+                    if (ln ? sfx1 : sfx0) { *p++ = '_'; *p++ = 'r'; }
                     *p++ = '\n';
                     p += S;
                     *p++ = '\n';
@@ -627,7 +632,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             g -= line * gpl;
             const int h = s_hdr[f];
             // staging offset of the first sequence byte of this line
-            const int ls = pad + (int)s_recoff[f] + line * (h + 1 + S + 1) + h + emit_suffix(emit, line) + 1;
+            const int ls = pad + (int)s_recoff[f] + line * (h + 1 + S + 1) + h + (line ? sfx1 : sfx0) + 1;
             const int sigma = ls & 15;
             const int j0 = 16 * g - sigma;
             const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
