@@ -83,7 +83,7 @@ struct gg_ctx {
     std::vector<HostGenome> genomes;
     DBuf d_cum_end, d_gbase, d_clen, d_name_off, d_name_len, d_names, d_genomes;
     bool ctab_dirty;
-    int n_contigs_total;
+    int n_contigs_total, names_bytes;
     // sizes
     int size_mode, fixed_len, minlen, maxlen, norev;
     std::vector<int32_t> size_len; std::vector<uint32_t> size_thr;
@@ -181,7 +181,7 @@ int sync_contig_tables(gg_ctx* ctx) {
         d.circ_contig = H.circ_sorted >= 0 ? H.first_contig + H.circ_sorted : -1; d.wrap_s0 = H.wrap_s0; d.wrap_gbase = H.wrap_gbase;
         gd.push_back(d);
     }
-    ctx->n_contigs_total = (int)cum_end.size();
+    ctx->n_contigs_total = (int)cum_end.size(); ctx->names_bytes = (int)names.size();
     int rc;
     if ((rc = upload_vec(ctx, ctx->d_cum_end, cum_end))) return rc;
     if ((rc = upload_vec(ctx, ctx->d_gbase, gbase))) return rc;
@@ -284,7 +284,8 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
 }
 
 // shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared LUT
-SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords) {
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords,
+                       int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false) {
     SmemLayout s; int o = 0;
     o += 16;                                   // readable slack before staging
     s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
@@ -309,6 +310,16 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.gmap = o; o += F * max_groups;
     s.warp_bytes = align_up(o, 16);
     s.lut = 0; s.thr = 1024; s.thr_bytes = thr_bytes; s.warp0 = 1024 + align_up(thr_bytes, 16);
+    s.tab = -1; s.tab_bytes = 0; s.n_contigs = tab_contigs; s.names_bytes = tab_names;
+    s.tab_ranges = s.tab_genomes = s.tab_cum = s.tab_gbase = s.tab_len = s.tab_noff = s.tab_nlen = s.tab_names = 0;
+    if (tab_on) {                              // small plan / genome / contig tables, CTA-shared
+        int t = 0;
+        s.tab_cum = t; t += 8 * tab_contigs; s.tab_gbase = t; t += 8 * tab_contigs;
+        s.tab_ranges = t; t += (int)sizeof(RangeDev) * tab_ranges; s.tab_genomes = t; t += (int)sizeof(GenomeDev) * tab_genomes;
+        s.tab_len = t; t += 4 * tab_contigs; s.tab_noff = t; t += 4 * tab_contigs; s.tab_nlen = t; t += align_up(2 * tab_contigs, 4);
+        s.tab_names = t; t += tab_names;
+        s.tab = s.warp0; s.tab_bytes = align_up(t, 16); s.warp0 += s.tab_bytes;
+    }
     for (int i = 0; i < 4; i++) s.thr_slot[i] = -1;
     s.total = s.warp0 + warps * s.warp_bytes;
     return s;
@@ -830,6 +841,14 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (envW) warps = std::min(warps, std::max(1, atoi(envW)));
     warps = std::max(warps, 1);
     SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4);
+    // small plan / genome / contig tables ride along in shared memory when that costs no resident warp (pass A walks them with
+    // dependent loads; L1 is only a few KB at this carve-out)
+    if (!getenv("GG_FUSED_NOTAB") && ctx->plan.size() <= 16 && ctx->genomes.size() <= 16 && ctx->n_contigs_total <= 96 && ctx->names_bytes <= 1024 &&
+        sizeof(RangeDev) % 4 == 0 && sizeof(GenomeDev) % 4 == 0) {
+        SmemLayout st = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4,
+                                    (int)ctx->plan.size(), (int)ctx->genomes.size(), ctx->n_contigs_total, ctx->names_bytes, true);
+        if ((size_t)st.total <= sm_budget) sm = st;
+    }
     for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) sm.thr_slot[i] = thr_slot[i];
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");

@@ -381,10 +381,34 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             if (P.dmg[slot].mode == 1 && P.sm.thr_slot[slot] >= 0)
                 for (int q = tid; q < 4 * (P.dmg[slot].rows5 + P.dmg[slot].rows3 + 2); q += blockDim.x)
                     ((uint4*)(smem + P.sm.thr))[P.sm.thr_slot[slot] + q] = __ldg(P.dmg[slot].thr + q);
+    if (P.sm.tab >= 0) {                              // small plan / genome / contig tables: global -> shared, once per CTA
+        uint8_t* tb = smem + P.sm.tab;
+        for (int q = tid; q < P.n_ranges * (int)(sizeof(RangeDev) / 4); q += blockDim.x) ((uint32_t*)(tb + P.sm.tab_ranges))[q] = __ldg((const uint32_t*)P.ranges + q);
+        for (int q = tid; q < P.n_genomes * (int)(sizeof(GenomeDev) / 4); q += blockDim.x) ((uint32_t*)(tb + P.sm.tab_genomes))[q] = __ldg((const uint32_t*)P.genomes + q);
+        for (int q = tid; q < P.sm.n_contigs; q += blockDim.x) {
+            ((uint64_t*)(tb + P.sm.tab_cum))[q] = __ldg(P.ctab.cum_end + q); ((uint64_t*)(tb + P.sm.tab_gbase))[q] = __ldg(P.ctab.gbase + q);
+            ((uint32_t*)(tb + P.sm.tab_len))[q] = __ldg(P.ctab.len + q); ((uint32_t*)(tb + P.sm.tab_noff))[q] = __ldg(P.ctab.name_off + q);
+            ((uint16_t*)(tb + P.sm.tab_nlen))[q] = __ldg(P.ctab.name_len + q);
+        }
+        for (int q = tid; q < P.sm.names_bytes; q += blockDim.x) ((char*)(tb + P.sm.tab_names))[q] = __ldg(P.ctab.names + q);
+    }
     if (P.size_mode == 2)
         for (int q = tid; q < 1024; q += blockDim.x) s_guide[q] = (uint16_t)first_below(P.size_thr, P.n_sizes, (uint32_t)q << 21);
     __syncthreads();                                  // the only CTA barrier
 
+    // plan / genome / contig tables: the shared-memory copy when there is one (generic pointers, warp-uniform)
+    const bool tsm = P.sm.tab >= 0;
+    const uint8_t* const tb = smem + (tsm ? P.sm.tab : 0);
+    const RangeDev*  const t_ranges  = tsm ? (const RangeDev*)(tb + P.sm.tab_ranges) : P.ranges;
+    const GenomeDev* const t_genomes = tsm ? (const GenomeDev*)(tb + P.sm.tab_genomes) : P.genomes;
+    const uint64_t*  const t_cum     = tsm ? (const uint64_t*)(tb + P.sm.tab_cum) : P.ctab.cum_end;
+    const uint64_t*  const t_gbase   = tsm ? (const uint64_t*)(tb + P.sm.tab_gbase) : P.ctab.gbase;
+    const uint32_t*  const t_len     = tsm ? (const uint32_t*)(tb + P.sm.tab_len) : P.ctab.len;
+    const uint32_t*  const t_noff    = tsm ? (const uint32_t*)(tb + P.sm.tab_noff) : P.ctab.name_off;
+    const uint16_t*  const t_nlen    = tsm ? (const uint16_t*)(tb + P.sm.tab_nlen) : P.ctab.name_len;
+    const char*      const t_names   = tsm ? (const char*)(tb + P.sm.tab_names) : P.ctab.names;
+
+#define TLD(p) (tsm ? *(p) : __ldg(p))          /* shared copy: plain load; global: read-only path */
     // this warp's private shared memory
     uint8_t*  const wb       = smem + P.sm.warp0 + (size_t)warp * P.sm.warp_bytes;
     uint8_t*  const s_stage  = wb + P.sm.stage;
@@ -422,10 +446,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             uint64_t idx = 0; int L = 0, ci = 0, hdr = 0, tag_len = 0; uint32_t plus = 1;
             const uint64_t id = P.first + tile_first + (uint64_t)lane;
             int lo = 0, hi = P.n_ranges - 1;                    // last range with first_id <= id
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.ranges[mid].first_id <= id) lo = mid; else hi = mid - 1; }
-            const RangeDev* rg = P.ranges + lo;
-            const GenomeDev G = P.genomes[rg->genome];
-            const uint64_t* cum = P.ctab.cum_end + G.first_contig;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (t_ranges[mid].first_id <= id) lo = mid; else hi = mid - 1; }
+            const RangeDev* rg = t_ranges + lo;
+            const GenomeDev G = t_genomes[rg->genome];
+            const uint64_t* cum = t_cum + G.first_contig;
             const int d = rg->comp >= 0 ? P.comp[rg->comp].dist : 0;       // distFromEnd: 0 without --comp (fragSim.cpp:1019-1021)
             uint64_t gpos = 0; bool ok = false;
             for (uint32_t attempt = 0; attempt < 65536u; attempt++) {
@@ -449,19 +473,19 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 // first contig with start+d <= coord <= end-d+1 (fragSim.cpp:1397-1403); for d == 0 that is the first with cp <= cum_end
                 const uint64_t key = d ? coord : cp;
                 int a = 0, b = G.n_contigs - 1;
-                while (a < b) { int mid = (a + b) >> 1; if (key <= __ldg(cum + mid)) b = mid; else a = mid + 1; }
+                while (a < b) { int mid = (a + b) >> 1; if (key <= TLD(cum + mid)) b = mid; else a = mid + 1; }
                 ci = G.first_contig + a;
-                const uint64_t clen = __ldg(P.ctab.len + ci);
-                idx = cp - (__ldg(cum + a) - clen);                                    // coord - startIndexChr, fragSim.cpp:1404
+                const uint64_t clen = TLD(t_len + ci);
+                idx = cp - (TLD(cum + a) - clen);                                    // coord - startIndexChr, fragSim.cpp:1404
                 if (idx < (uint64_t)d) continue;                                       // outside [start+d, end-d+1]
-                gpos = __ldg(P.ctab.gbase + ci) + idx;
+                gpos = TLD(t_gbase + ci) + idx;
                 int xtra = 0;
                 if (idx + (uint64_t)L + (uint64_t)d > clen) {                          // run-off past the contig end: always rejected (fragSim.cpp:1472) ...
-                    const GenomeDev* Gc = P.genomes + rg->genome;                      // (rare branch: fields re-read here, not kept live)
-                    if (ci != __ldg(&Gc->circ_contig) || idx + (uint64_t)d > clen || __ldg(cum + a) + 1 < (uint64_t)(L + d)) continue;   // coord <= end-d+1 (:1400); u64 wrap of end-length-d+1 (:1410)
+                    const GenomeDev* Gc = t_genomes + rg->genome;                      // (rare branch: fields re-read here, not kept live)
+                    if (ci != Gc->circ_contig || idx + (uint64_t)d > clen || cum[a] + 1 < (uint64_t)(L + d)) continue;   // coord <= end-d+1 (:1400); u64 wrap of end-length-d+1 (:1410)
                     uint64_t s = idx - (uint64_t)d;                                    // ... except on the --circ contig (fragSim.cpp:1412-1426)
                     if (s >= clen) { s = clen - 1; xtra = 1; }                         // coord == end+1 (d == 0): temp1 = "" and temp2 has length+1 bases
-                    gpos = __ldg(&Gc->wrap_gbase) + (s - (uint64_t)__ldg(&Gc->wrap_s0)) + (uint64_t)d;
+                    gpos = Gc->wrap_gbase + (s - (uint64_t)Gc->wrap_s0) + (uint64_t)d;
                 }
                 if (L + 2 * d > 0) {                                                   // isResolvedDNAstring over the window incl. the flanks, fragSim.cpp:333-339,1472
                     const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1 + (uint64_t)xtra;
@@ -496,7 +520,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             }
             my_gather += (unsigned long long)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
-            const int nlen = __ldg(P.ctab.name_len + ci);
+            const int nlen = t_nlen[ci];
             hdr = 1 + nlen + 3 + ndigits(idx) + 1 + ndigits(idx + (uint64_t)L) + 1 + ndigits((uint64_t)L) + tag_len;
             const int S = emit_seqlen(emit, L, RL);
             uint32_t bytes = 0;
@@ -547,7 +571,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const uint32_t meta = s_meta[f];
             const int fl = META_L(meta), slot = META_SLOT(meta);
             const uint64_t gp = s_gpos[f];
-            const uint32_t* seq2 = P.genomes[META_GEN(meta)].seq2;
+            const uint32_t* seq2 = t_genomes[META_GEN(meta)].seq2;
             const int n = min(16, fl - 16 * k);
             uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
                                          : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
@@ -594,17 +618,17 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 const uint32_t meta = s_meta[lane];
                 const int L = META_L(meta); const uint32_t plus = META_PLUS(meta);
                 const uint64_t idx = s_idx[lane]; const int ci = (int)s_ci[lane];
-                const RangeDev* rg = P.ranges + s_rg[lane];
+                const RangeDev* rg = t_ranges + s_rg[lane];
                 const char* tag = rg->tag; const int tag_len = rg->tag_len;
                 const int S = emit_seqlen(emit, L, RL);
-                const char* nm = P.ctab.names + __ldg(P.ctab.name_off + ci);
-                const int nlen = __ldg(P.ctab.name_len + ci);
+                const char* nm = t_names + t_noff[ci];
+                const int nlen = t_nlen[ci];
                 uint8_t* p = s_stage + pad + s_recoff[lane];
                 for (int ln = 0; ln < nlines; ln++) {
                     // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
                     *p++ = '>';
 #pragma unroll 1
-                    for (int k = 0; k < nlen; k++) *p++ = (uint8_t)__ldg(nm + k);
+                    for (int k = 0; k < nlen; k++) *p++ = (uint8_t)nm[k];
                     *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
                     p = put_decimal(p, idx, ndigits(idx), s_d100); *p++ = ':';
                     p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L), s_d100); *p++ = ':';

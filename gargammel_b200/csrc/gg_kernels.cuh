@@ -59,6 +59,9 @@ struct SmemLayout {          // byte offsets into dynamic shared memory, compute
     int idx, ci, rg;                               // per-fragment header state parked between passes
     int bh;                                        // per-fragment Briggs header draws (overhangs, nick), u64 each
     int dwords, lwords, cmap, gmap, total;
+    // CTA-shared copy of the plan / genome / contig tables when they are small (tab < 0: read them from global memory)
+    int tab, tab_ranges, tab_genomes, tab_cum, tab_gbase, tab_len, tab_noff, tab_nlen, tab_names, tab_bytes;
+    int n_contigs, names_bytes;
 };
 struct FusedParams {
     // work
