@@ -285,7 +285,8 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
 
 // shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared LUT
 SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords,
-                       int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false) {
+                       int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false,
+                       int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
     SmemLayout s; int o = 0;
     o += 16;                                   // readable slack before staging
     s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
@@ -312,12 +313,16 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.lut = 0; s.thr = 1024; s.thr_bytes = thr_bytes; s.warp0 = 1024 + align_up(thr_bytes, 16);
     s.tab = -1; s.tab_bytes = 0; s.n_contigs = tab_contigs; s.names_bytes = tab_names;
     s.tab_ranges = s.tab_genomes = s.tab_cum = s.tab_gbase = s.tab_len = s.tab_noff = s.tab_nlen = s.tab_names = 0;
+    s.tab_sthr = s.tab_slen = s.n_sizes_sm = 0; for (int k = 0; k < 3; k++) { s.tab_ad[k] = 0; s.ad_words[k] = 0; }
     if (tab_on) {                              // small plan / genome / contig tables, CTA-shared
         int t = 0;
         s.tab_cum = t; t += 8 * tab_contigs; s.tab_gbase = t; t += 8 * tab_contigs;
         s.tab_ranges = t; t += (int)sizeof(RangeDev) * tab_ranges; s.tab_genomes = t; t += (int)sizeof(GenomeDev) * tab_genomes;
         s.tab_len = t; t += 4 * tab_contigs; s.tab_noff = t; t += 4 * tab_contigs; s.tab_nlen = t; t += align_up(2 * tab_contigs, 4);
-        s.tab_names = t; t += tab_names;
+        s.tab_names = t; t += tab_names; t = align_up(t, 4);
+        s.tab_sthr = t; t += 4 * tab_sizes; s.tab_slen = t; t += 4 * tab_sizes; s.n_sizes_sm = tab_sizes;
+        s.ad_words[0] = adF_words; s.ad_words[1] = s.ad_words[2] = adS_words;
+        for (int k = 0; k < 3; k++) { s.tab_ad[k] = t; t += 4 * s.ad_words[k]; }
         s.tab = s.warp0; s.tab_bytes = align_up(t, 16); s.warp0 += s.tab_bytes;
     }
     for (int i = 0; i < 4; i++) s.thr_slot[i] = -1;
@@ -846,7 +851,10 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (!getenv("GG_FUSED_NOTAB") && ctx->plan.size() <= 16 && ctx->genomes.size() <= 16 && ctx->n_contigs_total <= 96 && ctx->names_bytes <= 1024 &&
         sizeof(RangeDev) % 4 == 0 && sizeof(GenomeDev) % 4 == 0) {
         SmemLayout st = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4,
-                                    (int)ctx->plan.size(), (int)ctx->genomes.size(), ctx->n_contigs_total, ctx->names_bytes, true);
+                                    (int)ctx->plan.size(), (int)ctx->genomes.size(), ctx->n_contigs_total, ctx->names_bytes, true,
+                                    (ctx->size_mode == GG_SIZE_FREQ && ctx->size_len.size() <= 512) ? (int)ctx->size_len.size() : 0,
+                                    (ctx->adF.size() <= 512 && ctx->adS.size() <= 512 && emit >= GG_EMIT_STDOUT4) ? (int)(1 + (ctx->adF.size() + 15) / 16 + 3) : 0,
+                                    (ctx->adF.size() <= 512 && ctx->adS.size() <= 512 && emit >= GG_EMIT_STDOUT4) ? (int)(1 + (ctx->adS.size() + 15) / 16 + 3) : 0);
         if ((size_t)st.total <= sm_budget) sm = st;
     }
     for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) sm.thr_slot[i] = thr_slot[i];

@@ -211,27 +211,32 @@ __device__ __forceinline__ uint32_t pad_base(const FusedParams& P, uint64_t id, 
     return (rng_word(P.key, id, stream, (uint32_t)(q >> 4)) >> (2 * (q & 15))) & 3u;
 }
 // forward read S1 = (frag + adapterF)[0:RL] + random tail      adptSim.cpp:298-310
-__device__ __forceinline__ void put_forward_read(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+// adapter k (0 forward, 1 second, 2 revcomp of the second): from the shared-memory copy when there is one
+__device__ __forceinline__ void put_run_ad(BitAppender& A, const FusedParams& P, const uint32_t* adsm, int k, int start, int len) {
+    if (adsm) put_run_smem(A, adsm + (P.sm.tab_ad[k] >> 2) + 1, start, len);
+    else put_run_glob(A, k == 0 ? P.ad.adF2 : k == 1 ? P.ad.adS2 : P.ad.rcS2, start, len);
+}
+__device__ __forceinline__ void put_forward_read(BitAppender& A, const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id) {
     const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenF);
     put_run_smem(A, D, 0, nD);
-    put_run_glob(A, P.ad.adF2, 0, nA);
+    put_run_ad(A, P, adsm, 0, 0, nA);
 #pragma unroll 1
     for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_F, q), 1);
 }
 // reverse read SR = (revcomp(frag) + adapterS)[0:RL] + random tail      adptSim.cpp:289,313-322
-__device__ __forceinline__ void put_reverse_read(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+__device__ __forceinline__ void put_reverse_read(BitAppender& A, const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id) {
     const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenS);
     put_rc_run(A, D, L, nD);
-    put_run_glob(A, P.ad.adS2, 0, nA);
+    put_run_ad(A, P, adsm, 1, 0, nA);
 #pragma unroll 1
     for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_R, q), 1);
 }
 // revcomp(SR): complemented random tail reversed, suffix of revcomp(adapterS), the last min(L,RL) fragment bases   adptSim.cpp:404
-__device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedParams& P, const uint32_t* D, int L, uint64_t id) {
+__device__ __forceinline__ void put_reverse_read_rc(BitAppender& A, const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id) {
     const int RL = P.ad.read_len, nD = min(L, RL), mAd = RL - nD, nS = min(mAd, P.ad.lenS), nP = mAd - nS;
 #pragma unroll 1
     for (int t = 0; t < nP; t++) A.put(3u - pad_base(P, id, ST_ADPT_R, nP - 1 - t), 1);
-    put_run_glob(A, P.ad.rcS2, P.ad.lenS - nS, nS);
+    put_run_ad(A, P, adsm, 2, P.ad.lenS - nS, nS);
     put_run_smem(A, D, L - nD, nD);
 }
 
@@ -252,12 +257,12 @@ __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd, 
 #endif
 // One packed sequence line: kind 0 = forward read, 1 = reverse read, 2 = forward read ++ revcomp(reverse read) (-artp).
 // Deliberately not inlined: it is called from two places and the kernel's code size matters (asynchronous warps).
-__device__ __noinline__ void build_line_image(const FusedParams& P, const uint32_t* D, int L, uint64_t id, int kind, uint32_t* out) {
+__device__ __noinline__ void build_line_image(const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id, int kind, uint32_t* out) {
     BitAppender A; A.out = out; A.lo = 0; A.hi = 0; A.fill = 0;
-    if (kind == 1) put_reverse_read(A, P, D, L, id);
+    if (kind == 1) put_reverse_read(A, P, adsm, D, L, id);
     else {
-        put_forward_read(A, P, D, L, id);
-        if (kind == 2) put_reverse_read_rc(A, P, D, L, id);
+        put_forward_read(A, P, adsm, D, L, id);
+        if (kind == 2) put_reverse_read_rc(A, P, adsm, D, L, id);
     }
     A.flush();
 }
@@ -391,6 +396,13 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             ((uint16_t*)(tb + P.sm.tab_nlen))[q] = __ldg(P.ctab.name_len + q);
         }
         for (int q = tid; q < P.sm.names_bytes; q += blockDim.x) ((char*)(tb + P.sm.tab_names))[q] = __ldg(P.ctab.names + q);
+        for (int q = tid; q < P.sm.n_sizes_sm; q += blockDim.x) {
+            ((uint32_t*)(tb + P.sm.tab_sthr))[q] = __ldg(P.size_thr + q); ((int32_t*)(tb + P.sm.tab_slen))[q] = __ldg(P.size_len + q);
+        }
+        for (int k = 0; k < 3; k++) {
+            const uint32_t* src = (k == 0 ? P.ad.adF2 : k == 1 ? P.ad.adS2 : P.ad.rcS2) - 1;      // guard word first
+            for (int q = tid; q < P.sm.ad_words[k]; q += blockDim.x) ((uint32_t*)(tb + P.sm.tab_ad[k]))[q] = __ldg(src + q);
+        }
     }
     if (P.size_mode == 2)
         for (int q = tid; q < 1024; q += blockDim.x) s_guide[q] = (uint16_t)first_below(P.size_thr, P.n_sizes, (uint32_t)q << 21);
@@ -408,7 +420,11 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     const uint16_t*  const t_nlen    = tsm ? (const uint16_t*)(tb + P.sm.tab_nlen) : P.ctab.name_len;
     const char*      const t_names   = tsm ? (const char*)(tb + P.sm.tab_names) : P.ctab.names;
 
-#define TLD(p) (tsm ? *(p) : __ldg(p))          /* shared copy: plain load; global: read-only path */
+    const bool ssm = tsm && P.sm.n_sizes_sm > 0;
+    const uint32_t* const t_sthr = ssm ? (const uint32_t*)(tb + P.sm.tab_sthr) : P.size_thr;
+    const int32_t*  const t_slen = ssm ? (const int32_t*)(tb + P.sm.tab_slen) : P.size_len;
+    const uint32_t* const adsm = (tsm && P.sm.ad_words[0] > 0) ? (const uint32_t*)tb : nullptr;
+#define TLD(p) (*(p))                           /* generic load: the shared copy or global memory (a per-use select of __ldg costs 0.7 %) */
     // this warp's private shared memory
     uint8_t*  const wb       = smem + P.sm.warp0 + (size_t)warp * P.sm.warp_bytes;
     uint8_t*  const s_stage  = wb + P.sm.stage;
@@ -461,9 +477,9 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 else {
                     const uint32_t u = x.x >> 1;
                     int k = s_guide[u >> 21];                                       // first i with p <= cProb[i] (fragSim.cpp:162-171)
-                    while (k < P.n_sizes && u >= __ldg(P.size_thr + k)) k++;
+                    while (k < P.n_sizes && u >= (ssm ? t_sthr[k] : __ldg(t_sthr + k))) k++;
                     if (k == P.n_sizes) k = (int)(((uint64_t)(x.y >> 1) * (uint64_t)P.n_sizes) >> 31);   // fragSim.cpp:176
-                    L = __ldg(P.size_len + k);
+                    L = ssm ? t_slen[k] : __ldg(t_slen + k);
                 }
                 if (L < d || L < P.minlen || L > P.maxlen) continue;                 // fragSim.cpp:1375-1381
                 const uint64_t r64 = ((uint64_t)x.w << 32) | x.z;
@@ -588,8 +604,8 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const uint32_t* D = s_dwords + s_cstart[lane];
             uint32_t* lw = s_lwords + lane * (nlines * LWL);
             // -rr: reverse read; -artp: forward ++ revcomp(reverse); otherwise the forward read (first line)
-            build_line_image(P, D, L, id, emit == 6 ? 1 : emit == 4 ? 2 : 0, lw + 1);
-            if (emit == 2) build_line_image(P, D, L, id, 1, lw + LWL + 1);     // default 4-line output: second line = reverse read
+            build_line_image(P, adsm, D, L, id, emit == 6 ? 1 : emit == 4 ? 2 : 0, lw + 1);
+            if (emit == 2) build_line_image(P, adsm, D, L, id, 1, lw + LWL + 1);     // default 4-line output: second line = reverse read
         }
 
         // ------------------------------------------------------------ look-back: global byte offset of this tile

@@ -62,6 +62,9 @@ struct SmemLayout {          // byte offsets into dynamic shared memory, compute
     // CTA-shared copy of the plan / genome / contig tables when they are small (tab < 0: read them from global memory)
     int tab, tab_ranges, tab_genomes, tab_cum, tab_gbase, tab_len, tab_noff, tab_nlen, tab_names, tab_bytes;
     int n_contigs, names_bytes;
+    // ... plus the FREQ length tables (n_sizes_sm entries, 0 = not copied) and the three packed adapters (ad_words[k] words each incl.
+    // guard and slack, 0 = not copied), byte offsets relative to tab
+    int tab_sthr, tab_slen, n_sizes_sm, tab_ad[3], ad_words[3];
 };
 struct FusedParams {
     // work
