@@ -477,9 +477,9 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 else {
                     const uint32_t u = x.x >> 1;
                     int k = s_guide[u >> 21];                                       // first i with p <= cProb[i] (fragSim.cpp:162-171)
-                    while (k < P.n_sizes && u >= (ssm ? t_sthr[k] : __ldg(t_sthr + k))) k++;
+                    while (k < P.n_sizes && u >= t_sthr[k]) k++;
                     if (k == P.n_sizes) k = (int)(((uint64_t)(x.y >> 1) * (uint64_t)P.n_sizes) >> 31);   // fragSim.cpp:176
-                    L = ssm ? t_slen[k] : __ldg(t_slen + k);
+                    L = t_slen[k];
                 }
                 if (L < d || L < P.minlen || L > P.maxlen) continue;                 // fragSim.cpp:1375-1381
                 const uint64_t r64 = ((uint64_t)x.w << 32) | x.z;
@@ -508,11 +508,18 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     const uint64_t w0 = s0 >> 5, w1 = e >> 5;
                     uint32_t any = 0;
 #pragma unroll 1
-                    for (uint64_t w = w0; w <= w1; w++) {
-                        uint32_t m = __ldg(G.nmask + w);
-                        if (w == w0) m &= 0xFFFFFFFFu << (s0 & 31);
-                        if (w == w1) m &= 0xFFFFFFFFu >> (31 - (e & 31));
-                        any |= m;
+                    for (uint64_t w = w0; w <= w1; w += 4) {           // four independent loads in flight (a dependent chain of misses costs pass A dearly)
+                        uint32_t m[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) m[t] = __ldg(G.nmask + min(w + (uint64_t)t, w1));
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const uint64_t wt = min(w + (uint64_t)t, w1);
+                            uint32_t v = m[t];
+                            if (wt == w0) v &= 0xFFFFFFFFu << (s0 & 31);
+                            if (wt == w1) v &= 0xFFFFFFFFu >> (31 - (e & 31));
+                            any |= v;
+                        }
                     }
                     if (any) continue;
                 }
