@@ -218,7 +218,12 @@ __device__ __forceinline__ void put_run_ad(BitAppender& A, const FusedParams& P,
 }
 __device__ __forceinline__ void put_forward_read(BitAppender& A, const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id) {
     const int RL = P.ad.read_len, nD = min(L, RL), nA = min(max(RL - L, 0), P.ad.lenF);
-    put_run_smem(A, D, 0, nD);
+    if (A.fill == 0) {                                   // the read opens its line: whole words of D are copied as they are
+        const int full = nD >> 4;
+#pragma unroll 1
+        for (int j = 0; j < full; j++) *A.out++ = D[j];
+        if (nD & 15) A.put(D[full] & lowfields(nD & 15), nD & 15);
+    } else put_run_smem(A, D, 0, nD);
     put_run_ad(A, P, adsm, 0, 0, nA);
 #pragma unroll 1
     for (int q = 0; q < RL - nD - nA; q++) A.put(pad_base(P, id, ST_ADPT_F, q), 1);
