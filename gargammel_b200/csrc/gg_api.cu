@@ -46,9 +46,9 @@ struct HostGenome {
 };
 struct HostDamage {
     int mode, rows5, rows3, clamp_last;
-    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd, K3;
+    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd, K3; double pL, pV;   // pL/pV: parameters of the geoL/geoV tables
     DBuf d_thr, d_sd5, d_sd3, d_geoL, d_geoV;
-    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0), K3(0) {}
+    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0), K3(0), pL(0), pV(0) {}
 };
 
 const int GEO_TABLE = 4096;          // geometric inverse-CDF table length (overhangs / nick position)
@@ -232,6 +232,9 @@ void fill_damage_dev(const HostDamage& H, ggd::DamageDev* D) {
     D->Ks = H.Ks; D->Kd = H.Kd; D->geoL = H.d_geoL.as<uint32_t>(); D->geoV = H.d_geoV.as<uint32_t>(); D->n_geo = GEO_TABLE;
     // -damagess keeps its 3' overhang table where plain Briggs keeps the nick table
     D->K3 = H.mode == GG_DMG_BRIGGS_SS ? H.K3 : H.Ks; D->geoL3 = H.mode == GG_DMG_BRIGGS_SS ? D->geoV : D->geoL;
+    auto inv_log = [](double p) { return p <= 0.0 ? -INFINITY : p >= 1.0 ? -0.0f : (float)(1.0 / log(1.0 - p)); };   // p = 0: never a success (k = n); p = 1: always k = 0
+    D->inv_logL = inv_log(H.pL); D->inv_logV = inv_log(H.pV);
+    D->inv_logL3 = H.mode == GG_DMG_BRIGGS_SS ? D->inv_logV : D->inv_logL;
 }
 
 int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
@@ -620,7 +623,7 @@ int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, do
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_BRIGGS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
-    H.Ks = thr_lt(s); H.Kd = thr_lt(d);
+    H.Ks = thr_lt(s); H.Kd = thr_lt(d); H.pL = l; H.pV = v;
     H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
     // inverse-CDF tables of geometric_distribution<int>(p): CDF(k) = 1-(1-p)^(k+1) as a running product (deamSim.cpp:297,1478-1479,1503-1507)
     double q = 1.0; uint32_t prev = 0;
@@ -640,7 +643,7 @@ int gg_tables_set_briggs_ss(gg_ctx* ctx, int slot, double d, double s5, double s
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_BRIGGS_SS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
-    H.Ks = thr_lt(s5); H.K3 = thr_lt(s3); H.Kd = thr_lt(d);
+    H.Ks = thr_lt(s5); H.K3 = thr_lt(s3); H.Kd = thr_lt(d); H.pL = l5; H.pV = l3;
     H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
     double q = 1.0; uint32_t prev = 0;                       // geometric_distribution<int>(l5) / (l3), deamSim.cpp:325-326,1342-1343
     for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l5); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoL[k] = t; prev = t; }

@@ -88,6 +88,8 @@ struct DamageDev {
     // BRIGGS_SS (-damagess d,s5,s3,l5,l3): Ks = 5' overhang rate, K3 = 3' overhang rate, geoL = 5' lengths, geoL3 = 3' lengths
     // (plain Briggs: K3 == Ks, geoL3 == geoL)
     uint32_t K3; const uint32_t* geoL3;
+    // 1 / ln(1 - p) of the three geometric tables: starting guess of the inverse-CDF search (the table decides)
+    float inv_logL, inv_logL3, inv_logV;
 };
 
 // first k with u < thr[k], thr ascending; returns n if none
@@ -129,13 +131,29 @@ __device__ __forceinline__ uint32_t dmg_matrix_base_shifted(const DamageDev& D, 
     if (u >= T.z) v += unit;
     return v;
 }
+// Inverse CDF of a geometric table thr[k] = thr_le(1 - q^(k+1)): first k with u < thr[k] (n if none).  The closed form
+// k = ceil(ln(1-p) / ln q) - 1 gives a starting point in one step; the integer table then decides, so the result is exactly
+// first_below's (two independent loads instead of a dependent chain of 4-12).
+__device__ __forceinline__ int first_below_geo(const uint32_t* __restrict__ thr, int n, uint32_t u, float inv_logq) {
+    const float omp = (float)(2147483648u - u) * 4.656612873e-10f;      // 1 - p, exact for the small values where it matters
+    float x = ceilf(__logf(omp) * inv_logq) - 1.0f;
+    x = fminf(fmaxf(x, 0.0f), (float)n);                                // NaN (q = 0 or 1) -> 0
+    int k = (int)x;
+    const uint32_t below = k > 0 ? __ldg(thr + k - 1) : 0u, here = k < n ? __ldg(thr + k) : 0xFFFFFFFFu;
+    if (u >= below && u < here) return k;
+#pragma unroll 1
+    while (k > 0 && u < __ldg(thr + k - 1)) k--;
+#pragma unroll 1
+    while (k < n && u >= __ldg(thr + k)) k++;
+    return k;
+}
 // Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
 struct BriggsHdr { int o5, o3, nick; };
 __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const uint4& h) {
     BriggsHdr B;
-    B.o5 = first_below_gallop(D.geoL, D.n_geo, h.x >> 1);
-    B.o3 = first_below_gallop(D.geoL3, D.n_geo, h.y >> 1);
-    B.nick = first_below_gallop(D.geoV, D.n_geo, h.z >> 1);
+    B.o5 = first_below_geo(D.geoL, D.n_geo, h.x >> 1, D.inv_logL);
+    B.o3 = first_below_geo(D.geoL3, D.n_geo, h.y >> 1, D.inv_logL3);
+    B.nick = first_below_geo(D.geoV, D.n_geo, h.z >> 1, D.inv_logV);
     return B;
 }
 // -damage, one base (deamSim.cpp:1483-1594), branch-free:
