@@ -334,15 +334,37 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
             }
             Wn |= nb << (8 * q);
         }
-    } else if (mode == 2 || (DMODE == 0 && mode == 5)) {  // Briggs / -damagess: header block 0, per-base word 4+i
-        BriggsHdr B; B.o5 = (int)(bh & 0xFFFFu); B.o3 = (int)((bh >> 16) & 0xFFFFu); B.nick = (int)((bh >> 32) & 0xFFFFu);   // drawn once per fragment in pass A
+    } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i; the rule of dmg_briggs_base over the
+        // 16 bases of the chunk at once: region masks in the "spread" domain (bit 2j = base j), then C->T and G->A are both "flip the high bit"
+        const int o5 = (int)(bh & 0xFFFFu), o3 = (int)((bh >> 16) & 0xFFFFu), nick = (int)((bh >> 32) & 0xFFFFu);      // drawn once per fragment in pass A
+        const uint32_t M = 0x55555555u;
+        auto low = [](int kk) -> uint32_t { return kk <= 0 ? 0u : kk >= 16 ? 0x55555555u : ((1u << (2 * kk)) - 1u) & 0x55555555u; };   // bases j < kk
+        const uint32_t m5 = (o5 + o3 >= fl) ? M : low(o5 - i0);                // single-stranded 5' side: all of it, or i + 1 <= o5   (deamSim.cpp:1483,1513)
+        const uint32_t m3 = ~m5 & ~low(fl - o3 - i0) & M;                      // 3' overhang: L - i <= o3                              (:1527)
+        const uint32_t mct = m5 | (~m3 & low(nick - i0));                      // C->T: 5' overhang, or double-stranded before the nick (:1542,1586)
+        uint32_t mS = m5 | m3;                                                 // rate s there, d elsewhere
+        const uint32_t lo = W & M, hi = (W >> 1) & M;
+        const uint32_t cand = ((lo & ~hi) & mct) | ((hi & ~lo) & ~mct);        // C where C->T applies, G where G->A applies
+        uint32_t hit = 0;
+#pragma unroll 1
+        for (int q = 0; q < nq; q++) {
+            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
+            uint32_t h4 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) h4 |= ((pick(x, jj) >> 1) < (((mS >> (2 * jj)) & 1u) ? D.Ks : D.Kd) ? 1u : 0u) << (2 * jj);
+            hit |= h4 << (8 * q);
+            mS >>= 8;
+        }
+        Wn = W ^ ((cand & hit) << 1);
+    } else if (DMODE == 0 && mode == 5) {                // -damagess: per-base rule
+        BriggsHdr B; B.o5 = (int)(bh & 0xFFFFu); B.o3 = (int)((bh >> 16) & 0xFFFFu); B.nick = (int)((bh >> 32) & 0xFFFFu);
 #pragma unroll 1
         for (int q = 0; q < nq; q++) {
             const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
             const uint32_t Wq = W >> (8 * q);
             uint32_t nb = 0;
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base<DMODE == 0>(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
+            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base<true>(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
             Wn |= nb << (8 * q);
         }
     } else {                                             // single / double: two passes, two streams
