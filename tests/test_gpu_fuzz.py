@@ -98,3 +98,31 @@ def test_random_configurations_bit_exact(oracle_mod, tmp_path, block):
         finally:
             g.close(); o.close()
     assert done >= 10
+
+
+@pytest.mark.parametrize("block", range(int(__import__("os").environ.get("GG_FUZZ_BLOCKS", "4"))))
+def test_random_record_streams_bit_exact(oracle_mod, block):
+    """The stand-alone deamSim / adptSim kernels over random FASTA record streams: sequence lengths 0..400, lower case, N and other
+    IUPAC letters, odd headers, every damage model with and without -name / -last, every dialect with and without -name / -tag."""
+    rng = np.random.default_rng(7000 + block)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTacgtNnRYKM", dtype=np.uint8)
+    for it in range(8):
+        recs = []
+        for i in range(int(rng.integers(1, 300))):
+            n = int(rng.choice([0, 1, 2, 15, 16, 17, int(rng.integers(0, 400))]))
+            hdr = b">" + bytes(rng.choice(np.frombuffer(b"abcXYZ019:+-_|.", dtype=np.uint8), size=int(rng.integers(1, 40))))
+            recs.append(hdr + b"\n" + alphabet[rng.integers(0, len(alphabet), size=n)].tobytes() + b"\n")
+        data = b"".join(recs)
+        seed = int(rng.integers(0, 2**62)); first_id = int(rng.integers(0, 2**40))
+        g = api.Context(0, seed); o = oracle_mod.OracleContext(seed)
+        dm = str(rng.choice(["matrix", "briggs", "briggs_ss", "single", "double"]))
+        name, clamp = bool(rng.random() < 0.5), bool(rng.random() < 0.7)
+        rl = int(rng.choice([20, 75, 130])); tag = str(rng.choice(["", "x", "lib_42"])); addname = bool(rng.random() < 0.5)
+        for c in (g, o):
+            util.set_damage(c, 0, dm, clamp_last=clamp)
+            c.set_deam_naming(name)
+            c.set_adapters(read_len=rl); c.set_adpt_naming(addname, tag)
+        util.assert_same(g.run_deam(data, 0, first_id)[0], o.run_deam(data, 0, first_id)[0], "deam %s name=%s clamp=%s block %d/%d" % (dm, name, clamp, block, it))
+        for emit in (api.EMIT_STDOUT4, api.EMIT_ARTS, api.EMIT_ARTP, api.EMIT_FR, api.EMIT_RR):
+            util.assert_same(g.run_adpt(data, emit, first_id)[0], o.run_adpt(data, emit, first_id)[0], "adpt emit=%d rl=%d tag=%r name=%s block %d/%d" % (emit, rl, tag, addname, block, it))
+        g.close(); o.close()
