@@ -851,8 +851,8 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4);
     // small plan / genome / contig tables ride along in shared memory when that costs no resident warp (pass A walks them with
     // dependent loads; L1 is only a few KB at this carve-out)
-    if (!getenv("GG_FUSED_NOTAB") && ctx->plan.size() <= 16 && ctx->genomes.size() <= 16 && ctx->n_contigs_total <= 96 && ctx->names_bytes <= 1024 &&
-        sizeof(RangeDev) % 4 == 0 && sizeof(GenomeDev) % 4 == 0) {
+    if (!getenv("GG_FUSED_NOTAB") && ctx->plan.size() <= 16 && ctx->genomes.size() <= 16 && ctx->n_contigs_total <= 96 && ctx->names_bytes <= 1024) {
+        static_assert(sizeof(RangeDev) % 8 == 0 && sizeof(GenomeDev) % 8 == 0, "the shared-memory table copy moves whole words");
         SmemLayout st = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4,
                                     (int)ctx->plan.size(), (int)ctx->genomes.size(), ctx->n_contigs_total, ctx->names_bytes, true,
                                     (ctx->size_mode == GG_SIZE_FREQ && ctx->size_len.size() <= 512) ? (int)ctx->size_len.size() : 0,
