@@ -242,7 +242,7 @@ def run_reference_arm(args, rank, world):
     sources = make_sources()
     w = prepare_reference_dir(sources)
     try:
-        per_core = 50000
+        per_core = 150000          # ~1 s per core per step: 15-25 core-seconds of CPU work per step
         n = per_core * cores
         for _ in range(args.warmup):
             reference_step(w, n, cores)
@@ -481,7 +481,7 @@ def main():
             cores = host_cores()
             w = prepare_reference_dir(sources)
             try:
-                per_core = 50000
+                per_core = 150000
                 reference_step(w, 2000 * cores, cores)
                 f, dt, kind = reference_step(w, per_core * cores, cores)
             finally:
