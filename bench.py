@@ -162,10 +162,11 @@ class Clocks:
 
 
 # --------------------------------------------------------------------------- reference arm (CPU)
-def reference_step(workdir, n_frag, cores):
+def reference_step(workdir, n_frag, cores, gzip_hops=False):
     """One bounded sample: `cores` independent shards, each the reference composition of gargammel.pl:1457-1848 without
     the gzip hops:  fragSim(e1) ; fragSim(e2) >> P.e.fa ; fragSim(c1) > P.c.fa ; deamSim -matfile P.e.fa > P_d.fa ;
-    cat P.c.fa >> P_d.fa ; adptSim -artp P_a.fa P_d.fa.   Returns (fragments, seconds, kind)."""
+    cat P.c.fa >> P_d.fa ; adptSim -artp P_a.fa P_d.fa.   gzip_hops=True inserts the driver's own `| gzip >` / gz-input hops
+    (gargammel.pl:1510,1729,1847).  Returns (fragments, seconds, kind)."""
     from oracle import oracle
     kind = "reference" if oracle.ref_bin("fragSim") else "port"
     per = max(1, n_frag // cores)
@@ -181,6 +182,14 @@ def reference_step(workdir, n_frag, cores):
               "{p} -f {af} -s {as_} -l {rl} -artp P${{S}}_a.fa P${{S}}_d.fa 2>/dev/null; rm -f P$S.e.fa P$S.c.fa P${{S}}_d.fa P${{S}}_a.fa").format(
             w=workdir, f=frag, d=deam, p=adpt, a=nE1, b=nE2, c=nC, rl=READ_LEN,
             af="AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", as_="AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT")
+        if gzip_hops:
+            sh = ("set -e; cd {w}; S=$1; "
+                  "( {f} -tag e1_0 -n {a} -m 0 -M 1000 -f sf.size endo.1.fa 2>/dev/null; {f} -tag e2_0 -n {b} -m 0 -M 1000 -f sf.size endo.2.fa 2>/dev/null ) | gzip > P$S.e.fa.gz; "
+                  "{f} -tag c1 -n {c} -m 0 -M 1000 -f sf.size cont.1.fa 2>/dev/null | gzip > P$S.c.fa.gz; "
+                  "{d} -matfile m- P$S.e.fa.gz 2>/dev/null | gzip > P${{S}}_d.fa.gz; gzip -dc P$S.c.fa.gz | gzip >> P${{S}}_d.fa.gz; "
+                  "{p} -f {af} -s {as_} -l {rl} -artp P${{S}}_a.fa P${{S}}_d.fa.gz 2>/dev/null; rm -f P$S.e.fa.gz P$S.c.fa.gz P${{S}}_d.fa.gz P${{S}}_a.fa").format(
+                w=workdir, f=frag, d=deam, p=adpt, a=nE1, b=nE2, c=nC, rl=READ_LEN,
+                af="AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", as_="AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT")
         t0 = time.perf_counter()
         procs = [subprocess.Popen(["bash", "-c", sh, "shard", str(i)]) for i in range(cores)]
         rcs = [p.wait() for p in procs]
@@ -489,6 +498,13 @@ def main():
             line["cpu_baseline"] = {"value": f / dt, "unit": "fragments/s", "cores": cores, "kind": kind,
                                     "sample": "%d fragments (%d per core x %d cores) of the same workload, %s, no gzip hops, files on tmpfs" % (
                                         f, per_core, cores, "reference sources + our shim (oracle/_ref): fragSim;deamSim;adptSim per shard" if kind == "reference" else "oracle port")}
+            if kind == "reference" and shutil.which("gzip"):               # the same with the driver's gzip hops, as gargammel.pl runs it
+                w = prepare_reference_dir(sources)
+                try:
+                    fz, dtz, _ = reference_step(w, 50000 * cores, cores, gzip_hops=True)
+                    line["cpu_baseline"]["with_gzip_hops"] = {"value": fz / dtz, "unit": "fragments/s", "sample": "%d fragments (50000 per core x %d cores), `| gzip >` after fragSim and deamSim, gz inputs to deamSim/adptSim (gargammel.pl:1510,1729,1847)" % (fz, cores)}
+                finally:
+                    shutil.rmtree(w, ignore_errors=True)
         except Exception as ex:      # the baseline is a reported figure; never let it kill the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "fragments/s", "cores": host_cores(), "kind": "port", "sample": "failed: %r" % (ex,)}
     print(json.dumps(line), flush=True)
