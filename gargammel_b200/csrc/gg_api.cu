@@ -46,10 +46,14 @@ struct HostGenome {
 };
 struct HostDamage {
     int mode, rows5, rows3, clamp_last;
-    std::vector<uint4> thr; std::vector<uint32_t> sd5, sd3, geoL, geoV; uint32_t Ks, Kd, K3; double pL, pV;   // pL/pV: parameters of the geoL/geoV tables
-    DBuf d_thr, d_sd5, d_sd3, d_geoL, d_geoV;
-    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), Ks(0), Kd(0), K3(0), pL(0), pV(0) {}
+    int n5t, n3t;                                  // matrix: terminal rows drawn per base (draw specification v2)
+    std::vector<uint4> term, acc; std::vector<uint32_t> sd5, sd3, geoL, geoV, geoA, geoB; uint32_t Ks, Kd, K3;
+    double pL, pV, pA, pB;                         // parameters of the geometric tables geoL/geoV and geoA (matrix: majorant M; Briggs: s) / geoB (Briggs: d)
+    DBuf d_term, d_acc, d_sd5, d_sd3, d_geoL, d_geoV, d_geoA, d_geoB;
+    HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), n5t(0), n3t(0), Ks(0), Kd(0), K3(0), pL(0), pV(0), pA(0), pB(0) {}
 };
+const int NT_MAX = 8;                // at most this many terminal rows per end are drawn per base
+const double NT_KAPPA = 1.25;        // a row is terminal when its total rate exceeds NT_KAPPA x the largest rate of the rows >= NT_MAX
 
 const int GEO_TABLE = 4096;          // geometric inverse-CDF table length (overhangs / nick position)
 const int MAX_FRAG_LEN = 4095;
@@ -69,6 +73,13 @@ uint32_t thr_lt(double c) {
     if (y <= 0.0) return 0;
     const double k = ceil(y);
     return k >= 2147483648.0 ? 2147483648u : (uint32_t)k;
+}
+
+// inverse-CDF table of geometric_distribution<int>(p): CDF(k) = 1-(1-p)^(k+1) as a running product (deamSim.cpp:297,1478-1479,1503-1507)
+void geo_table(double p, int n, std::vector<uint32_t>& t) {
+    t.resize(n);
+    double q = 1.0; uint32_t prev = 0;
+    for (int k = 0; k < n; k++) { q *= (1.0 - p); uint32_t v = thr_le(1.0 - q); if (v < prev) v = prev; t[k] = v; prev = v; }
 }
 
 } // namespace
@@ -228,13 +239,16 @@ int sync_plan(gg_ctx* ctx) {
 void fill_damage_dev(const HostDamage& H, ggd::DamageDev* D) {
     memset(D, 0, sizeof *D);
     D->mode = H.mode; D->rows5 = H.rows5; D->rows3 = H.rows3; D->clamp_last = H.clamp_last;
-    D->thr = H.d_thr.as<uint4>(); D->sd5 = H.d_sd5.as<uint32_t>(); D->sd3 = H.d_sd3.as<uint32_t>();
+    D->term = H.d_term.as<uint4>(); D->acc = H.d_acc.as<uint4>(); D->n5t = H.n5t; D->n3t = H.n3t;
+    D->sd5 = H.d_sd5.as<uint32_t>(); D->sd3 = H.d_sd3.as<uint32_t>();
     D->Ks = H.Ks; D->Kd = H.Kd; D->geoL = H.d_geoL.as<uint32_t>(); D->geoV = H.d_geoV.as<uint32_t>(); D->n_geo = GEO_TABLE;
+    D->geoM = H.d_geoA.as<uint32_t>(); D->geoS = H.d_geoA.as<uint32_t>(); D->geoD = H.d_geoB.as<uint32_t>();
     // -damagess keeps its 3' overhang table where plain Briggs keeps the nick table
     D->K3 = H.mode == GG_DMG_BRIGGS_SS ? H.K3 : H.Ks; D->geoL3 = H.mode == GG_DMG_BRIGGS_SS ? D->geoV : D->geoL;
     auto inv_log = [](double p) { return p <= 0.0 ? -INFINITY : p >= 1.0 ? -0.0f : (float)(1.0 / log(1.0 - p)); };   // p = 0: never a success (k = n); p = 1: always k = 0
     D->inv_logL = inv_log(H.pL); D->inv_logV = inv_log(H.pV);
     D->inv_logL3 = H.mode == GG_DMG_BRIGGS_SS ? D->inv_logV : D->inv_logL;
+    D->inv_logM = D->inv_logS = inv_log(H.pA); D->inv_logD = inv_log(H.pB);
 }
 
 int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
@@ -286,7 +300,7 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
     return cudaMalloc(p, bytes);
 }
 
-// shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared LUT
+// shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared tables
 SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords,
                        int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false,
                        int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
@@ -297,7 +311,7 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.idx = o; o += 8 * F;
     s.bh = o; o += 8 * F;
     s.meta = o; o += 4 * F;
-    s.recoff = o; o += 4 * F;
+    s.so = o; o += 4 * F;
     s.ci = o; o += 4 * F;
     if (alias_dwords && s.stage_bytes >= 4 * (F * max_chunks + 4)) {
         s.dwords = s.stage;                    // adptSim dialects: the damaged words are dead once the line images exist, before staging is written
@@ -307,13 +321,14 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     }
     s.lwords = o; o += 4 * (F * line_words + 4);
     s.hdr = o; o += 2 * F;
+    s.nd = o; o += 2 * F;
     s.cstart = o; o += 2 * F;
     s.gstart = o; o += 2 * F;
     s.rg = o; o += 2 * F;
     s.cmap = o; o += F * max_chunks;
-    s.gmap = o; o += F * max_groups;
+    s.gmap = o; o += F * max_groups;           // (only the fragSim / deamSim dialects use the group map)
     s.warp_bytes = align_up(o, 16);
-    s.lut = 0; s.thr = 1024; s.thr_bytes = thr_bytes; s.warp0 = 1024 + align_up(thr_bytes, 16);
+    s.thr = 0; s.thr_bytes = thr_bytes; s.warp0 = align_up(thr_bytes, 16);
     s.tab = -1; s.tab_bytes = 0; s.n_contigs = tab_contigs; s.names_bytes = tab_names;
     s.tab_ranges = s.tab_genomes = s.tab_cum = s.tab_gbase = s.tab_len = s.tab_noff = s.tab_nlen = s.tab_names = 0;
     s.tab_sthr = s.tab_slen = s.n_sizes_sm = 0; for (int k = 0; k < 3; k++) { s.tab_ad[k] = 0; s.ad_words[k] = 0; }
@@ -328,7 +343,7 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
         for (int k = 0; k < 3; k++) { s.tab_ad[k] = t; t += 4 * s.ad_words[k]; }
         s.tab = s.warp0; s.tab_bytes = align_up(t, 16); s.warp0 += s.tab_bytes;
     }
-    for (int i = 0; i < 4; i++) s.thr_slot[i] = -1;
+    for (int i = 0; i < 4; i++) s.thr_slot[i] = s.term_slot[i] = -1;
     s.total = s.warp0 + warps * s.warp_bytes;
     return s;
 }
@@ -380,7 +395,7 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
     for (int s = 0; s < GG_MAX_GC_SLOTS; s++) ctx->gc[s].d_thr.release();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
-        ctx->dmg[s].d_thr.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release();
+        ctx->dmg[s].d_term.release(); ctx->dmg[s].d_acc.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release(); ctx->dmg[s].d_geoA.release(); ctx->dmg[s].d_geoB.release();
     }
     for (size_t i = 0; i < ctx->pool.size(); i++) cudaFree(ctx->pool[i].first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -552,6 +567,14 @@ static int check_rates(gg_ctx* ctx, const double* sub, int rows, const char* wha
     return GG_OK;
 }
 
+// total substitution rate of base b in a row of 12, summed in the reference's order (a ascending, deamSim.cpp:1820-1830)
+static double row_rate(const double* row, int b) {
+    double sum = 0.0;
+    for (int a = 0; a < 4; a++) { if (a == b) continue; sum += row[a < b ? b * 3 + a : b * 3 + (a - 1)]; }
+    return sum;
+}
+static double row_max(const double* row) { double m = 0.0; for (int b = 0; b < 4; b++) m = std::max(m, row_rate(row, b)); return m; }
+
 int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, const double* sub3, int rows3, int clamp_last) {
     if (!ctx) return GG_ERR_ARG;
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || !sub5 || !sub3 || rows5 <= 0 || rows3 <= 0) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: bad arguments");
@@ -561,16 +584,35 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_MATRIX; H.rows5 = rows5; H.rows3 = rows3; H.clamp_last = clamp_last ? 1 : 0;
-    // device layout: rows5 real rows + sentinel, then sentinel + rows3 real rows in reverse order (distance rows3-1 .. 0).  The sentinel is the last row when clamping
-    // (deamSim.cpp:1811-1813) or an identity row (base unchanged) with -last (deamSim.cpp:1814-1816).
-    H.thr.assign((size_t)(rows5 + rows3 + 2) * 4, make_uint4(0, 0, 0, 0));
+    // row that applies at distance `dist` from end e (0 = 5', 1 = 3'); nullptr = left untouched (-last, deamSim.cpp:1811-1817)
+    auto eff_row = [&](int e, int dist) -> const double* {
+        const double* sub = e ? sub3 : sub5; const int n = e ? rows3 : rows5;
+        if (dist >= n) { if (!H.clamp_last) return nullptr; dist = n - 1; }
+        return sub + (size_t)dist * 12;
+    };
+    // draw specification v2: the rows of each end whose total rate stands out are drawn per base, every other position by
+    // thinning under the majorant M = the largest total rate among them
+    double tail = 0.0;
     for (int e = 0; e < 2; e++) {
-        const double* sub = e == 0 ? sub5 : sub3; const int rows = e == 0 ? rows5 : rows3; const size_t base = e == 0 ? 0 : (size_t)rows5 + 1;
-        for (int r = 0; r <= rows; r++) {
-            const double* row = sub + (size_t)std::min(r, rows - 1) * 12;
+        const double* sub = e ? sub3 : sub5; const int n = e ? rows3 : rows5;
+        for (int r = NT_MAX; r < n; r++) tail = std::max(tail, row_max(sub + (size_t)r * 12));
+        if (H.clamp_last) tail = std::max(tail, row_max(sub + (size_t)(n - 1) * 12));
+    }
+    double M = tail; int nt[2];
+    for (int e = 0; e < 2; e++) {
+        nt[e] = 0;
+        for (int dist = 0; dist < NT_MAX; dist++) { const double* row = eff_row(e, dist); if (row && row_max(row) > NT_KAPPA * tail) nt[e] = dist + 1; }
+        for (int dist = nt[e]; dist < NT_MAX; dist++) { const double* row = eff_row(e, dist); if (row) M = std::max(M, row_max(row)); }
+    }
+    H.n5t = nt[0]; H.n3t = nt[1]; H.pA = M;
+    // terminal rows: the reference's categorical pick; K[a] = number of u31 with p <= sumProb[a+1]
+    H.term.assign((size_t)(H.n5t + H.n3t) * 4 + 4, make_uint4(0, 0, 0, 0));
+    for (int e = 0; e < 2; e++)
+        for (int t = 0; t < nt[e]; t++) {
+            const double* row = eff_row(e, t);
             for (int b = 0; b < 4; b++) {
                 uint32_t k[4];
-                if (r == rows && !H.clamp_last) {            // identity: u >= K for every a < b, u < K for a >= b
+                if (!row) {                                  // identity: u >= K for every a < b, u < K for a >= b
                     for (int a = 0; a < 4; a++) k[a] = a < b ? 0u : 2147483648u;
                 } else {
                     // cumulative table exactly as deamSim.cpp:1797-1837 builds it (same operation order, fp64)
@@ -582,20 +624,43 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
                         sum += row[idx]; _sumProb[a + 1] = row[idx];
                     }
                     _sumProb[b + 1] = 1.0 - sum;
-                    double s = 0;
-                    for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }
+                    double sacc = 0;
+                    for (int a = 0; a < 5; a++) { sacc += _sumProb[a]; sumProb[a] = sacc; }
                     uint32_t prev = 0;
-                    for (int a = 0; a < 4; a++) { uint32_t t = thr_le(sumProb[a + 1]); if (t < prev) t = prev; k[a] = t; prev = t; }
+                    for (int a = 0; a < 4; a++) { uint32_t v = thr_le(sumProb[a + 1]); if (v < prev) v = prev; k[a] = v; prev = v; }
                     // the device picks (u>=K1)+(u>=K2)+(u>=K3): exact iff the last cumulative value covers every u31
                     if (k[3] != 2147483648u) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: cumulative probabilities of a row do not reach 1");
                 }
-                // 3' rows are stored in REVERSE (sentinel first, terminal base last): the row of position i is then max(i + c, base)
+                H.term[(size_t)((e ? H.n5t : 0) + t) * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
+            }
+        }
+    // acceptance rows of the thinned positions: rows5 real rows + sentinel, then sentinel + rows3 real rows in reverse order (distance
+    // rows3-1 .. 0); the sentinel is the last row when clamping (deamSim.cpp:1811-1813) or "unchanged" with -last (:1814-1816).
+    // K_k = number of u31 with p < (r_1 + .. + r_k) / M over the other bases in ascending order.
+    H.acc.assign((size_t)(rows5 + rows3 + 2) * 4, make_uint4(0, 0, 0, 0));
+    for (int e = 0; e < 2; e++) {
+        const int rows = e == 0 ? rows5 : rows3; const size_t base = e == 0 ? 0 : (size_t)rows5 + 1;
+        for (int r = 0; r <= rows; r++) {
+            const double* row = eff_row(e, r);
+            for (int b = 0; b < 4; b++) {
+                uint32_t k[3] = {0u, 0u, 0u};
+                if (row && M > 0.0) {
+                    double cum = 0.0; int n = 0; uint32_t prev = 0;
+                    for (int a = 0; a < 4; a++) {
+                        if (a == b) continue;
+                        cum += row[a < b ? b * 3 + a : b * 3 + (a - 1)];
+                        uint32_t v = thr_lt(cum / M); if (v < prev) v = prev; k[n++] = v; prev = v;
+                    }
+                }
                 const size_t slot_r = e == 0 ? (size_t)r : base + (size_t)(rows - r);
-                H.thr[slot_r * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
+                H.acc[slot_r * 4 + b] = make_uint4(k[0], k[1], k[2], 0u);
             }
         }
     }
-    return upload_vec(ctx, H.d_thr, H.thr);
+    geo_table(M, GEO_TABLE, H.geoA);
+    if ((rc = upload_vec(ctx, H.d_term, H.term))) return rc;
+    if ((rc = upload_vec(ctx, H.d_acc, H.acc))) return rc;
+    return upload_vec(ctx, H.d_geoA, H.geoA);
 }
 
 int gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const double* sub5, int rows5, const double* sub3, int rows3) {
@@ -623,16 +688,15 @@ int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, do
     CK(cudaSetDevice(ctx->device));
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_BRIGGS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
-    H.Ks = thr_lt(s); H.Kd = thr_lt(d); H.pL = l; H.pV = v;
-    H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
-    // inverse-CDF tables of geometric_distribution<int>(p): CDF(k) = 1-(1-p)^(k+1) as a running product (deamSim.cpp:297,1478-1479,1503-1507)
-    double q = 1.0; uint32_t prev = 0;
-    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoL[k] = t; prev = t; }
-    q = 1.0; prev = 0;
-    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - v); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoV[k] = t; prev = t; }
+    H.Ks = thr_lt(s); H.Kd = thr_lt(d); H.pL = l; H.pV = v; H.pA = s; H.pB = d;
+    // overhang lengths (l), nick position (v), and the geometric skips of the event draws over the single-stranded (s) and
+    // double-stranded (d) positions (draw specification v2)
+    geo_table(l, GEO_TABLE, H.geoL); geo_table(v, GEO_TABLE, H.geoV); geo_table(s, GEO_TABLE, H.geoA); geo_table(d, GEO_TABLE, H.geoB);
     int rc;
     if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
-    return upload_vec(ctx, H.d_geoV, H.geoV);
+    if ((rc = upload_vec(ctx, H.d_geoV, H.geoV))) return rc;
+    if ((rc = upload_vec(ctx, H.d_geoA, H.geoA))) return rc;
+    return upload_vec(ctx, H.d_geoB, H.geoB);
 }
 int gg_tables_set_briggs_ss(gg_ctx* ctx, int slot, double d, double s5, double s3, double l5, double l3) {
     if (!ctx) return GG_ERR_ARG;
@@ -644,11 +708,7 @@ int gg_tables_set_briggs_ss(gg_ctx* ctx, int slot, double d, double s5, double s
     HostDamage& H = ctx->dmg[slot];
     H.mode = GG_DMG_BRIGGS_SS; H.rows5 = H.rows3 = 0; H.clamp_last = 1;
     H.Ks = thr_lt(s5); H.K3 = thr_lt(s3); H.Kd = thr_lt(d); H.pL = l5; H.pV = l3;
-    H.geoL.resize(GEO_TABLE); H.geoV.resize(GEO_TABLE);
-    double q = 1.0; uint32_t prev = 0;                       // geometric_distribution<int>(l5) / (l3), deamSim.cpp:325-326,1342-1343
-    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l5); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoL[k] = t; prev = t; }
-    q = 1.0; prev = 0;
-    for (int k = 0; k < GEO_TABLE; k++) { q *= (1.0 - l3); uint32_t t = thr_le(1.0 - q); if (t < prev) t = prev; H.geoV[k] = t; prev = t; }
+    geo_table(l5, GEO_TABLE, H.geoL); geo_table(l3, GEO_TABLE, H.geoV);      // geometric_distribution<int>(l5) / (l3), deamSim.cpp:325-326,1342-1343
     int rc;
     if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
     return upload_vec(ctx, H.d_geoV, H.geoV);
@@ -827,13 +887,16 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     }
     int dmode = has_other || (has_matrix && has_briggs) ? 0 : has_briggs ? 2 : 1;
     // matrix-only plans keep their threshold tables in shared memory (L1 is only a few KB at this carve-out)
-    int thr_bytes = 0, thr_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
+    int thr_bytes = 0, thr_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1}, term_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
     if (dmode == 1 && emit != GG_EMIT_FRAG) {
         bool used[GG_MAX_DAMAGE_SLOTS] = {false, false, false, false};
         for (size_t i = 0; i < ctx->plan.size(); i++) if (ctx->plan[i].damage_slot >= 0) used[ctx->plan[i].damage_slot] = true;
         for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++)
-            if (used[sl] && ctx->dmg[sl].mode == GG_DMG_MATRIX) { thr_slot[sl] = thr_bytes / 16; thr_bytes += 64 * (ctx->dmg[sl].rows5 + ctx->dmg[sl].rows3 + 2); }
-        if (thr_bytes > 48 * 1024) { dmode = 0; thr_bytes = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) thr_slot[sl] = -1; }   // huge matrices: read them from global
+            if (used[sl] && ctx->dmg[sl].mode == GG_DMG_MATRIX) {
+                thr_slot[sl] = thr_bytes / 16; thr_bytes += 64 * (ctx->dmg[sl].rows5 + ctx->dmg[sl].rows3 + 2);
+                term_slot[sl] = thr_bytes / 16; thr_bytes += 64 * (ctx->dmg[sl].n5t + ctx->dmg[sl].n3t);
+            }
+        if (thr_bytes > 48 * 1024) { dmode = 0; thr_bytes = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) thr_slot[sl] = term_slot[sl] = -1; }   // huge matrices: read them from global
     }
     int regs = 96, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
@@ -843,7 +906,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
     const int ctas = envC ? std::max(1, atoi(envC)) : 1;
     const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).warp_bytes;
-    int warps = (int)((sm_budget / (size_t)ctas - 1024 - (size_t)thr_bytes) / per_warp);
+    int warps = (int)((sm_budget / (size_t)ctas - (size_t)thr_bytes - 16) / per_warp);
     warps = std::min(warps, 65536 / (regs * 32) / ctas);
     warps = std::min(warps, GG_FUSED_MAXT / 32);
     if (envW) warps = std::min(warps, std::max(1, atoi(envW)));
@@ -860,7 +923,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
                                     (ctx->adF.size() <= 512 && ctx->adS.size() <= 512 && emit >= GG_EMIT_STDOUT4) ? (int)(1 + (ctx->adS.size() + 15) / 16 + 3) : 0);
         if ((size_t)st.total <= sm_budget) sm = st;
     }
-    for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) sm.thr_slot[i] = thr_slot[i];
+    for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) { sm.thr_slot[i] = thr_slot[i]; sm.term_slot[i] = term_slot[i]; }
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
     const int n_tiles = (int)n_tiles64;
@@ -873,6 +936,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
 
     FusedParams P; memset(&P, 0, sizeof P);
     P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary; P.dmode = dmode;
+    { const uint64_t gpf = (uint64_t)emit_lines(emit) * (uint64_t)((Smax + 15) / 16 + 1); P.gmagic = (uint32_t)((0x100000000ull + gpf - 1) / gpf); }
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();

@@ -77,20 +77,27 @@ struct DamageDev {
     int mode;            // gg_damage_mode
     int rows5, rows3;    // matrix / single-double rows
     int clamp_last;      // matrix: clamp to last row (default) or skip (-last)
-    // MATRIX: thr[(r*4+b)] = {K1,K2,K3,K4}: new base = first a with u31 < K[a+1] (K4 == 2^31 always, checked on the host).
-    // Layout: rows5 real 5' rows, one sentinel row (= last row when clamping, identity when -last), then the 3' block REVERSED:
-    // its sentinel, then distance rows3-1 .. 0, so that the row of position i on the 3' side is max(i + rows5+rows3+2-L, rows5+1).
-    const uint4* thr;
+    // MATRIX (draw specification v2: events).  Thresholds are uint4 per (row, base):
+    //   term[(t)*4 + b], t < n5t: categorical of the 5' terminal position t; term[(n5t + t)*4 + b], t < n3t: 3' terminal position L-1-t.
+    //     {K1,K2,K3,K4}: new base = number of K <= u31 (K4 == 2^31 always, checked on the host); rows past a -last table are identities.
+    //   acc[(r)*4 + b]: a candidate of the interior takes the k-th other base (ascending) iff K_k <= u31 < K_{k+1} ... i.e. the number
+    //     of K <= u31 indexes {a1,a2,a3,unchanged}.  Row layout: rows5 real 5' rows, one sentinel row (= last row when clamping,
+    //     "unchanged" with -last), then the 3' block REVERSED: its sentinel, then distance rows3-1 .. 0, so that the row of position i
+    //     on the 3' side is max(i + rows5+rows3+2-L, rows5+1).
+    //   geoM: geometric skips under the majorant M (inverse CDF, like geoL/geoV).
+    const uint4* term; const uint4* acc; const uint32_t* geoM; int n5t, n3t; float inv_logM;
     // SINGLE/DOUBLE: sd5[r] (C->T 5'), sd3[r] (C->T single / G->A double)
     const uint32_t* sd5; const uint32_t* sd3;
-    // BRIGGS: Ks,Kd strict thresholds (u31 < K); geometric tables (u31 < cdf_thr[k] first k) of n_geo entries
-    uint32_t Ks, Kd; const uint32_t* geoL; const uint32_t* geoV; int n_geo;
-    // BRIGGS_SS (-damagess d,s5,s3,l5,l3): Ks = 5' overhang rate, K3 = 3' overhang rate, geoL = 5' lengths, geoL3 = 3' lengths
-    // (plain Briggs: K3 == Ks, geoL3 == geoL)
-    uint32_t K3; const uint32_t* geoL3;
-    // 1 / ln(1 - p) of the three geometric tables: starting guess of the inverse-CDF search (the table decides)
-    float inv_logL, inv_logL3, inv_logV;
+    // BRIGGS: geometric tables (u31 < cdf_thr[k] first k) of n_geo entries: overhang lengths, nick position, and the skips of the
+    // event draws over the single-stranded (rate s) and double-stranded (rate d) positions
+    const uint32_t* geoL; const uint32_t* geoV; const uint32_t* geoS; const uint32_t* geoD; int n_geo;
+    // BRIGGS_SS (-damagess d,s5,s3,l5,l3; still drawn per base): Ks = 5' overhang rate, K3 = 3' overhang rate, Kd = middle, geoL = 5' lengths,
+    // geoL3 = 3' lengths (plain Briggs: geoL3 == geoL)
+    uint32_t Ks, Kd, K3; const uint32_t* geoL3;
+    // 1 / ln(1 - p) of the geometric tables: starting guess of the inverse-CDF search (the table decides)
+    float inv_logL, inv_logL3, inv_logV, inv_logS, inv_logD;
 };
+#define GG_GEO_MISS (1 << 29)     // an overhang / nick draw that ran off its table: beyond any record
 
 // first k with u < thr[k], thr ascending; returns n if none
 __device__ __forceinline__ int first_below(const uint32_t* __restrict__ thr, int n, uint32_t u) {
@@ -113,24 +120,6 @@ __device__ __forceinline__ int first_below_gallop(const uint32_t* __restrict__ t
     return lo;
 }
 
-// -matfile, one base (deamSim.cpp:1794-1930): i = position, L = fragment length, b = code, x = raw Philox word
-__device__ __forceinline__ uint32_t dmg_matrix_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x) {
-    const int r = (i < (L >> 1)) ? min(i, D.rows5) : max(i + (D.rows5 + D.rows3 + 2 - L), D.rows5 + 1);   // sentinel rows absorb the clamp / -last cases
-    const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
-    const uint32_t u = x >> 1;
-    return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z);
-}
-// same, returning the new base already placed in its 2-bit field: (new base) * unit with unit = 1 << 2j
-__device__ __forceinline__ uint32_t dmg_matrix_base_shifted(const DamageDev& D, int i, int L, uint32_t b, uint32_t x, uint32_t unit) {
-    const int r = (i < (L >> 1)) ? min(i, D.rows5) : max(i + (D.rows5 + D.rows3 + 2 - L), D.rows5 + 1);
-    const uint4 T = __ldg(D.thr + (r * 4 + (int)b));
-    const uint32_t u = x >> 1;
-    uint32_t v = 0;
-    if (u >= T.x) v += unit;
-    if (u >= T.y) v += unit;
-    if (u >= T.z) v += unit;
-    return v;
-}
 // Inverse CDF of a geometric table thr[k] = thr_le(1 - q^(k+1)): first k with u < thr[k] (n if none).  The closed form
 // k = ceil(ln(1-p) / ln q) - 1 gives a starting point in one step; the integer table then decides, so the result is exactly
 // first_below's (two independent loads instead of a dependent chain of 4-12).
@@ -154,30 +143,138 @@ __device__ __forceinline__ BriggsHdr dmg_briggs_hdr(const DamageDev& D, const ui
     B.o5 = first_below_geo(D.geoL, D.n_geo, h.x >> 1, D.inv_logL);
     B.o3 = first_below_geo(D.geoL3, D.n_geo, h.y >> 1, D.inv_logL3);
     B.nick = first_below_geo(D.geoV, D.n_geo, h.z >> 1, D.inv_logV);
+    if (B.o5 == D.n_geo) B.o5 = GG_GEO_MISS;                            // off the table: longer than any record
+    if (B.o3 == D.n_geo) B.o3 = GG_GEO_MISS;
+    if (B.nick == D.n_geo) B.nick = GG_GEO_MISS;
     return B;
 }
-// -damage, one base (deamSim.cpp:1483-1594), branch-free:
-//   C->T at s  if all single-stranded, or inside the 5' overhang            (:1486-1494, :1513-1523, :1557-1567)
-//   G->A at s  inside the 3' overhang                                       (:1527-1537, :1571-1581)
-//   G->A at d  in the double-stranded part at/after the nick, C->T at d before it   (:1542-1548, :1586-1592)
-//   -damagess (mode 5, deamSim.cpp:1337-1468): C->T only; 5' overhang at s5, 3' overhang at s3, double-stranded part at d; a base
-//   inside both overhangs takes the nearer end (i < int(len*0.5) -> 5', :1351-1371).  SS = false compiles that model out.
-template <bool SS>
-__device__ __forceinline__ uint32_t dmg_briggs_base(const DamageDev& D, const BriggsHdr& B, int i, int L, uint32_t b, uint32_t x) {
+// -damagess, one base (deamSim.cpp:1337-1468; still drawn per base, word 4+i): C->T only; 5' overhang at s5, 3' overhang at s3,
+// double-stranded part at d; a base inside both overhangs takes the nearer end (i < int(len*0.5) -> 5', :1351-1371).
+__device__ __forceinline__ uint32_t dmg_briggs_ss_base(const DamageDev& D, const BriggsHdr& B, int i, int L, uint32_t b, uint32_t x) {
     const uint32_t u = x >> 1;
     const bool in5 = i + 1 <= B.o5, in3 = L - i <= B.o3;
-    if (SS && D.mode == 5) {
-        const bool s5 = (in5 && in3) ? (i < (L >> 1)) : in5;
-        const uint32_t K = s5 ? D.Ks : in3 ? D.K3 : D.Kd;
-        return (b == 1u && u < K) ? 3u : b;
-    }
-    const bool ss5 = (B.o5 + B.o3 >= L) || in5;
-    const bool ss3 = !ss5 && in3;
-    const bool ct = ss5 || (!ss3 && B.nick > i);
-    const uint32_t K = (ss5 || ss3) ? D.Ks : D.Kd;
-    const uint32_t from = ct ? 1u : 2u, to = ct ? 3u : 0u;
-    return (b == from && u < K) ? to : b;
+    const bool s5 = (in5 && in3) ? (i < (L >> 1)) : in5;
+    const uint32_t K = s5 ? D.Ks : in3 ? D.K3 : D.Kd;
+    return (b == 1u && u < K) ? 3u : b;
 }
+// ---------------------------------------------------------------- damage as events (draw specification v2)
+// The reference draws one uniform per base (deamSim.cpp:1847,1488-1587).  Per-base draws are independent, so the same law comes
+// from thinning: geometric skips under a majorant find the few candidate positions of a fragment, and a candidate with base b
+// becomes a with probability rate(b->a)/majorant.  A fragment then costs a handful of Philox words instead of one per base.
+// SeqT gives access to the bases of one fragment / record:  code(i) -> 0..3 or -1 (unresolved), put(i, old, new).
+__device__ __forceinline__ uint32_t count_le(uint32_t u, const uint4& T) { return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z); }
+
+// matrix row (acc layout) of position i of a fragment of length L
+__device__ __forceinline__ int matrix_row(const DamageDev& D, int i, int L) {
+    return (i < (L >> 1)) ? min(i, D.rows5) : max(i + (D.rows5 + D.rows3 + 2 - L), D.rows5 + 1);
+}
+// PH: bit 0 = 5' terminal positions, bit 1 = interior, bit 2 = 3' terminal positions (deamSim -name walks them in this order);
+// TSM: term/acc are shared-memory copies (plain loads) instead of global tables
+template <int PH, bool TSM, class SeqT>
+__device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D, const uint4* term, const uint4* acc, SeqT& S, int L, uint64_t id) {
+    const int half = L >> 1;                                    // positions i < half are on the 5' side (deamSim.cpp:1805)
+    const int n5 = min(D.n5t, half), n3 = min(D.n3t, L - half);
+    const uint32_t b3 = (uint32_t)(D.n5t + 3) >> 2, bg = b3 + ((uint32_t)(D.n3t + 3) >> 2);
+    if (PH & 1) {
+#pragma unroll 1
+        for (int t0 = 0; t0 < n5; t0 += 4) {
+            const uint4 x = rng_block(key, id, (uint32_t)t0 >> 2, ST_DEAM);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int t = t0 + jj;
+                if (t < n5) {
+                    const int b = S.code(t);
+                    if (b >= 0) { const uint4 T = TSM ? term[t * 4 + b] : __ldg(term + t * 4 + b); S.put(t, (uint32_t)b, count_le(pick(x, jj) >> 1, T)); }
+                }
+            }
+        }
+    }
+    if (PH & 2) {
+        int pos = n5; const int end = L - n3;
+#pragma unroll 1
+        for (uint32_t n = 0; pos < end; n += 2) {
+            const uint4 x = rng_block(key, id, bg + (n >> 1), ST_DEAM);
+#pragma unroll
+            for (int sub = 0; sub < 2; sub++) {
+                if (pos < end) {
+                    const int j = first_below_geo(D.geoM, D.n_geo, (sub ? x.z : x.x) >> 1, D.inv_logM);
+                    pos += j;                                   // a table miss is "at least n_geo": no candidate, the next round goes on from there
+                    if (j < D.n_geo && pos < end) {
+                        const int b = S.code(pos);
+                        if (b >= 0) {
+                            const int r = matrix_row(D, pos, L);
+                            const uint4 A = TSM ? acc[r * 4 + b] : __ldg(acc + r * 4 + b);
+                            const uint32_t cnt = count_le((sub ? x.w : x.y) >> 1, A);            // 0,1,2: the cnt-th other base (ascending); 3: unchanged
+                            if (cnt < 3u) S.put(pos, (uint32_t)b, cnt + (cnt >= (uint32_t)b ? 1u : 0u));
+                        }
+                        pos++;
+                    }
+                }
+            }
+        }
+    }
+    if (PH & 4) {
+#pragma unroll 1
+        for (int t0 = ((n3 - 1) >> 2) << 2; t0 >= 0; t0 -= 4) {     // t descending = position ascending
+            const uint4 x = rng_block(key, id, b3 + ((uint32_t)t0 >> 2), ST_DEAM);
+#pragma unroll
+            for (int jj = 3; jj >= 0; jj--) {
+                const int t = t0 + jj;
+                if (t < n3) {
+                    const int i = L - 1 - t;
+                    const int b = S.code(i);
+                    if (b >= 0) { const uint4 T = TSM ? term[(D.n5t + t) * 4 + b] : __ldg(term + (D.n5t + t) * 4 + b); S.put(i, (uint32_t)b, count_le(pick(x, jj) >> 1, T)); }
+                }
+            }
+        }
+    }
+}
+
+// Briggs (deamSim.cpp:1477-1613) as events.  Block 0 = header (overhangs, nick).  Block 1+n: words 0,2 = geometric skips (rate s) over
+// the single-stranded positions (5' overhang then 3' overhang; everything when the overhangs meet), words 1,3 = skips (rate d) over the
+// double-stranded middle.  A candidate changes iff its base is the one its region deaminates: C->T in the 5' overhang / before the
+// nick, G->A in the 3' overhang / from the nick on; both are "flip the high bit of the code".
+// PH: bit 0 = 5' overhang (or everything, when all single-stranded), bit 1 = middle, bit 2 = 3' overhang.
+template <int PH, class SeqT>
+__device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D, const BriggsHdr& B, SeqT& S, int L, uint64_t id) {
+    const bool allss = B.o5 + B.o3 >= L;                            // deamSim.cpp:1483
+    const int nS = allss ? L : B.o5 + B.o3, qend = allss ? L : L - B.o3;
+    int v = (PH & 5) ? 0 : nS, q = (PH & 2) ? (allss ? L : B.o5) : qend;
+#pragma unroll 1
+    for (uint32_t n = 0; v < nS || q < qend; n++) {
+        const uint4 x = rng_block(key, id, 1u + n, ST_DEAM);
+#pragma unroll
+        for (int sub = 0; sub < 2; sub++) {
+            if ((PH & 5) && v < nS) {
+                const int j = first_below_geo(D.geoS, D.n_geo, (sub ? x.z : x.x) >> 1, D.inv_logS);
+                v += j;
+                if (j < D.n_geo && v < nS) {
+                    const bool five = allss || v < B.o5;
+                    const int i = five ? v : L - B.o3 + (v - B.o5);
+                    if (five ? (PH & 1) : (PH & 4)) { if (S.code(i) == (five ? 1 : 2)) S.put(i, five ? 1u : 2u, five ? 3u : 0u); }
+                    v++;
+                }
+            }
+            if ((PH & 2) && q < qend) {
+                const int j = first_below_geo(D.geoD, D.n_geo, (sub ? x.w : x.y) >> 1, D.inv_logD);
+                q += j;
+                if (j < D.n_geo && q < qend) {
+                    const bool ct = B.nick > q;                     // placedNick = nick <= i (deamSim.cpp:1510,1542,1586)
+                    if (S.code(q) == (ct ? 1 : 2)) S.put(q, ct ? 1u : 2u, ct ? 3u : 0u);
+                    q++;
+                }
+            }
+        }
+    }
+}
+
+// 2-bit packed fragment in shared memory (16 bases per word)
+struct SeqPacked {
+    uint32_t* w;
+    __device__ __forceinline__ int code(int i) const { return (int)((w[i >> 4] >> (2 * (i & 15))) & 3u); }
+    __device__ __forceinline__ void put(int i, uint32_t oldb, uint32_t newb) { w[i >> 4] ^= (oldb ^ newb) << (2 * (i & 15)); }
+};
+
 // -mat single|double / -mapdamage, one base, both passes (deamSim.cpp:1941-2002); x1 pass-1 word, x2 pass-2 word
 __device__ __forceinline__ uint32_t dmg_sd_base(const DamageDev& D, int i, int L, uint32_t b, uint32_t x1, uint32_t x2) {
     const int r5 = min(i, D.rows5 - 1), r3 = min(L - 1 - i, D.rows3 - 1);

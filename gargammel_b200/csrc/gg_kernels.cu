@@ -257,9 +257,6 @@ __device__ __forceinline__ uint8_t* put_decimal(uint8_t* p, uint64_t v, int nd, 
     return p + nd;
 }
 
-#ifndef GG_FUSED_MINB
-#define GG_FUSED_MINB 3
-#endif
 // One packed sequence line: kind 0 = forward read, 1 = reverse read, 2 = forward read ++ revcomp(reverse read) (-artp).
 // Deliberately not inlined: it is called from two places and the kernel's code size matters (asynchronous warps).
 __device__ __noinline__ void build_line_image(const FusedParams& P, const uint32_t* adsm, const uint32_t* D, int L, uint64_t id, int kind, uint32_t* out) {
@@ -301,70 +298,22 @@ __device__ __noinline__ bool comp_accept(const FusedParams& P, const CompDev& C,
     return p < acc;
 }
 
-// Damage of one 16-base chunk (fields 0..15 of W = fragment positions 16k..16k+15, n of them inside the fragment).
-// All fields of a 4-base group are processed without per-base branches; fields at or beyond the fragment end hold
-// neighbouring genome bases, index sentinel/clamped rows, and are masked off by the caller.  The group loop is NOT
-// unrolled: the kernel's warps run asynchronously, so code size (instruction cache) matters more than loop overhead.
-// DMODE: 1 = every damage slot of the plan is a -matfile matrix, 2 = every slot is Briggs (only that code is compiled in), 0 = any mix.
-template <int DMODE>
-__device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const DamageDev& D, const uint4* thr_sm, unsigned long long bh, uint64_t id, int k, int fl, int n, uint32_t W) {
-    const int mode = DMODE != 0 ? DMODE : D.mode;
+// Per-base damage of one 16-base chunk for the models that are still drawn per base (-damagess, -mat single|double / -mapdamage;
+// -matfile and -damage are drawn as events, see matrix_events / briggs_events).  Fields 0..15 of W = fragment positions 16k..16k+15, n of
+// them inside the fragment; fields beyond the fragment end are masked off by the caller.
+__device__ __noinline__ uint32_t damage_chunk_perbase(const FusedParams& P, const DamageDev& D, unsigned long long bh, uint64_t id, int k, int fl, int n, uint32_t W) {
     const int i0 = 16 * k;
     const int nq = (n + 3) >> 2;
     uint32_t Wn = 0;
-    if (mode == 1) {                                     // -matfile: one uniform per base (deamSim.cpp:1847,1911)
-        const int R5 = D.rows5, r3base = R5 + 1;
-        const int c3 = R5 + D.rows3 + 2 - fl;             // 3' rows are stored reversed: row(i) = max(i + c3, r3base)
-        const uint4* thr = DMODE == 1 ? thr_sm : D.thr;   // rows5 + sentinel, sentinel + rows3 reversed; shared-memory copy in the matrix-only kernel
-        const int half = fl >> 1;                         // positions i < half are on the 5' side (deamSim.cpp:1805)
-#pragma unroll 1
-        for (int q = 0; q < nq; q++) {
-            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q), ST_DEAM);
-            const uint32_t Wq = W >> (8 * q);
-            const int i4 = i0 + 4 * q;
-            uint32_t nb = 0;
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int i = i4 + jj;
-                const uint32_t b = (Wq >> (2 * jj)) & 3u;
-                const uint32_t r = (uint32_t)((i < half) ? min(i, R5) : max(i + c3, r3base));
-                const uint4 Tq = DMODE == 1 ? thr[r * 4u + b] : __ldg(thr + (r * 4u + b));
-                const uint32_t u = pick(x, jj) >> 1;
-                nb += (u >= Tq.z ? 3u : u >= Tq.y ? 2u : u >= Tq.x ? 1u : 0u) << (2 * jj);      // thresholds ascend: number of them <= u
-            }
-            Wn |= nb << (8 * q);
-        }
-    } else if (mode == 2) {                              // Briggs: header block 0, per-base word 4+i; the rule of dmg_briggs_base over the
-        // 16 bases of the chunk at once: region masks in the "spread" domain (bit 2j = base j), then C->T and G->A are both "flip the high bit"
-        const int o5 = (int)(bh & 0xFFFFu), o3 = (int)((bh >> 16) & 0xFFFFu), nick = (int)((bh >> 32) & 0xFFFFu);      // drawn once per fragment in pass A
-        const uint32_t M = 0x55555555u;
-        auto low = [](int kk) -> uint32_t { return kk <= 0 ? 0u : kk >= 16 ? 0x55555555u : ((1u << (2 * kk)) - 1u) & 0x55555555u; };   // bases j < kk
-        const uint32_t m5 = (o5 + o3 >= fl) ? M : low(o5 - i0);                // single-stranded 5' side: all of it, or i + 1 <= o5   (deamSim.cpp:1483,1513)
-        const uint32_t m3 = ~m5 & ~low(fl - o3 - i0) & M;                      // 3' overhang: L - i <= o3                              (:1527)
-        const uint32_t mct = m5 | (~m3 & low(nick - i0));                      // C->T: 5' overhang, or double-stranded before the nick (:1542,1586)
-        uint32_t mS = m5 | m3;                                                 // rate s there, d elsewhere
-        const uint32_t lo = W & M, hi = (W >> 1) & M;
-        const uint32_t cand = ((lo & ~hi) & mct) | ((hi & ~lo) & ~mct);        // C where C->T applies, G where G->A applies
-        uint32_t hit = 0;
-#pragma unroll 1
-        for (int q = 0; q < nq; q++) {
-            const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
-            uint32_t h4 = 0;
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) h4 |= ((pick(x, jj) >> 1) < (((mS >> (2 * jj)) & 1u) ? D.Ks : D.Kd) ? 1u : 0u) << (2 * jj);
-            hit |= h4 << (8 * q);
-            mS >>= 8;
-        }
-        Wn = W ^ ((cand & hit) << 1);
-    } else if (DMODE == 0 && mode == 5) {                // -damagess: per-base rule
-        BriggsHdr B; B.o5 = (int)(bh & 0xFFFFu); B.o3 = (int)((bh >> 16) & 0xFFFFu); B.nick = (int)((bh >> 32) & 0xFFFFu);
+    if (D.mode == 5) {                                   // -damagess: header block 0 (drawn once per fragment in pass A), per-base word 4+i
+        BriggsHdr B; B.o5 = (int)(uint32_t)(bh & 0xFFFFFFFFu); B.o3 = (int)(uint32_t)(bh >> 32); B.nick = 0;
 #pragma unroll 1
         for (int q = 0; q < nq; q++) {
             const uint4 x = rng_block(P.key, id, (uint32_t)(4 * k + q + 1), ST_DEAM);
             const uint32_t Wq = W >> (8 * q);
             uint32_t nb = 0;
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_base<true>(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
+            for (int jj = 0; jj < 4; jj++) nb |= dmg_briggs_ss_base(D, B, i0 + 4 * q + jj, fl, (Wq >> (2 * jj)) & 3u, pick(x, jj)) << (2 * jj);
             Wn |= nb << (8 * q);
         }
     } else {                                             // single / double: two passes, two streams
@@ -382,17 +331,51 @@ __device__ __forceinline__ uint32_t damage_chunk(const FusedParams& P, const Dam
     return Wn;
 }
 
+// 16 bases (2 bits each) -> 16 ASCII bytes with byte permutes: a nibble of the selector picks one byte of "ACGT" (both operands hold
+// the table, so bit 2 of a nibble is don't-care and only bit 3 has to be cleared); even and odd bases are looked up separately and
+// interleaved.  13 ALU instructions, no shared-memory table.
+__device__ __forceinline__ uint4 codes16_to_ascii(uint32_t x) {
+    const uint32_t lut = 0x54474341u;                                      // 'A','C','G','T'
+    const uint32_t e = x & 0x77777777u, o = (x >> 2) & 0x77777777u;
+    const uint32_t e0 = __byte_perm(lut, lut, e), o0 = __byte_perm(lut, lut, o);               // bases 0,2,4,6 / 1,3,5,7
+    const uint32_t e1 = __byte_perm(lut, lut, e >> 16), o1 = __byte_perm(lut, lut, o >> 16);   // bases 8,10,12,14 / 9,11,13,15
+    uint4 a;
+    a.x = __byte_perm(e0, o0, 0x5140u); a.y = __byte_perm(e0, o0, 0x7362u);
+    a.z = __byte_perm(e1, o1, 0x5140u); a.w = __byte_perm(e1, o1, 0x7362u);
+    return a;
+}
+// nd decimal digits of a 32-bit value, two at a time from the right
+__device__ __forceinline__ void put_dec32(uint8_t* p, uint32_t w, int nd, const uint16_t* d100) {
+    int k = nd - 2;
+#pragma unroll 1
+    for (; k >= 0; k -= 2) { const uint32_t q = w / 100u; const uint32_t two = d100[w - q * 100u]; p[k] = (uint8_t)two; p[k + 1] = (uint8_t)(two >> 8); w = q; }
+    if (k == -1) p[0] = (uint8_t)('0' + w);
+}
+
+// ---- staged tile -> global memory with the bulk-copy engine (one instruction for the 16-byte aligned body of a tile)
+#ifndef GG_BULK_COPY
+#define GG_BULK_COPY 1
+#endif
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // One warp owns one tile of up to 32 fragments from sampling to the global store; warps never wait for each other
 // (no CTA barrier inside the loop).  Byte offsets come from a decoupled look-back over per-warp-tile states.
 //
 // FASTB: every header is >= 13 bytes, so a partial 16-byte group of one sequence line can never reach another line's
 // sequence bytes: groups are stored whole and the headers/newlines are written afterwards (no read-modify-write).
+// DMODE: 1 = every damage slot of the plan is a -matfile matrix (tables in shared memory), 2 = every slot is Briggs, 0 = any mix.
 template <bool FASTB, int DMODE>
 __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint16_t s_d100[100];                // "00".."99" for the decimal fields of the deflines
     __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
-    uint32_t* const s_lut = (uint32_t*)(smem + P.sm.lut);     // 256 x 4 ASCII bytes (CTA-shared)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int emit = P.emit, RL = P.ad.read_len;
@@ -400,19 +383,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     const int sfx0 = emit_suffix(emit, 0), sfx1 = emit_suffix(emit, 1);     // "_r" on line 0 / line 1
 
     for (int v = tid; v < 100; v += blockDim.x) s_d100[v] = (uint16_t)(('0' + v / 10) | (('0' + v % 10) << 8));
-    // 4 bases (one byte of codes) -> 4 ASCII chars
-    for (int v = tid; v < 256; v += blockDim.x) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) w |= (uint32_t)code2ascii((v >> (2 * k)) & 3) << (8 * k);
-        s_lut[v] = w;
-    }
     const uint4* const s_thr = (const uint4*)(smem + P.sm.thr);
-    if (DMODE == 1)                                   // matrix thresholds of the used slots: global -> shared, once per CTA
+    if (DMODE == 1)                                   // matrix tables of the used slots (acceptance rows, then terminal rows): global -> shared, once per CTA
         for (int slot = 0; slot < 4; slot++)
-            if (P.dmg[slot].mode == 1 && P.sm.thr_slot[slot] >= 0)
-                for (int q = tid; q < 4 * (P.dmg[slot].rows5 + P.dmg[slot].rows3 + 2); q += blockDim.x)
-                    ((uint4*)(smem + P.sm.thr))[P.sm.thr_slot[slot] + q] = __ldg(P.dmg[slot].thr + q);
+            if (P.dmg[slot].mode == 1 && P.sm.thr_slot[slot] >= 0) {
+                const int na = 4 * (P.dmg[slot].rows5 + P.dmg[slot].rows3 + 2), nt = 4 * (P.dmg[slot].n5t + P.dmg[slot].n3t);
+                for (int q = tid; q < na; q += blockDim.x) ((uint4*)(smem + P.sm.thr))[P.sm.thr_slot[slot] + q] = __ldg(P.dmg[slot].acc + q);
+                for (int q = tid; q < nt; q += blockDim.x) ((uint4*)(smem + P.sm.thr))[P.sm.term_slot[slot] + q] = __ldg(P.dmg[slot].term + q);
+            }
     if (P.sm.tab >= 0) {                              // small plan / genome / contig tables: global -> shared, once per CTA
         uint8_t* tb = smem + P.sm.tab;
         for (int q = tid; q < P.n_ranges * (int)(sizeof(RangeDev) / 4); q += blockDim.x) ((uint32_t*)(tb + P.sm.tab_ranges))[q] = __ldg((const uint32_t*)P.ranges + q);
@@ -459,9 +437,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint64_t* const s_idx    = (uint64_t*)(wb + P.sm.idx);
     unsigned long long* const s_bh = (unsigned long long*)(wb + P.sm.bh);
     uint32_t* const s_meta   = (uint32_t*)(wb + P.sm.meta);
-    uint32_t* const s_recoff = (uint32_t*)(wb + P.sm.recoff);
+    uint32_t* const s_so     = (uint32_t*)(wb + P.sm.so);       // staging offset (without the tile's pad) of the first sequence byte of line 0
     uint32_t* const s_ci     = (uint32_t*)(wb + P.sm.ci);
     uint16_t* const s_hdr    = (uint16_t*)(wb + P.sm.hdr);
+    uint16_t* const s_nd     = (uint16_t*)(wb + P.sm.nd);       // digit counts of start | end << 4 | length << 8
     uint16_t* const s_cstart = (uint16_t*)(wb + P.sm.cstart);
     uint16_t* const s_gstart = (uint16_t*)(wb + P.sm.gstart);
     uint16_t* const s_rg     = (uint16_t*)(wb + P.sm.rg);
@@ -474,6 +453,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint32_t my_err = 0;
     const int S_ad = emit == 4 ? 2 * RL : RL;                       // sequence-line length of the adptSim dialects
     const int LWL = ((S_ad + 15) >> 4) + 2;                          // words per line image: guard + data + read slack
+    const uint32_t gpl_ad = (uint32_t)((S_ad + 15) >> 4) + 1u, gpf_ad = (uint32_t)nlines * gpl_ad;   // staging groups per line / per fragment (adptSim dialects: the same for every fragment)
 
     while (true) {
         int tile = 0;
@@ -571,7 +551,8 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             my_gather += (unsigned long long)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
             const int nlen = t_nlen[ci];
-            hdr = 1 + nlen + 3 + ndigits(idx) + 1 + ndigits(idx + (uint64_t)L) + 1 + ndigits((uint64_t)L) + tag_len;
+            const int n1 = ndigits(idx), n2 = ndigits(idx + (uint64_t)L), n3 = ndigits((uint64_t)L);
+            hdr = 1 + nlen + 3 + n1 + 1 + n2 + 1 + n3 + tag_len;
             const int S = emit_seqlen(emit, L, RL);
             uint32_t bytes = 0;
             for (int ln = 0; ln < nlines; ln++) bytes += hdr + (ln ? sfx1 : sfx0) + 1 + S + 1;
@@ -581,10 +562,11 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             s_gpos[lane] = gpos;
             s_meta[lane] = META(L, plus, rg->slot, rg->genome);
             s_hdr[lane] = (uint16_t)hdr;
+            s_nd[lane] = (uint16_t)(n1 | (n2 << 4) | (n3 << 8));
             s_idx[lane] = idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
-            if (DMODE != 1 && emit != 0 && rg->slot >= 0 && (DMODE == 2 || P.dmg[rg->slot].mode == 2 || P.dmg[rg->slot].mode == 5)) {   // Briggs / -damagess: overhangs + nick, once per fragment (deamSim.cpp:1478-1507)
+            if (DMODE == 0 && emit != 0 && rg->slot >= 0 && P.dmg[rg->slot].mode == 5) {   // -damagess (drawn per base in pass C): the two overhangs, once per fragment (deamSim.cpp:1342-1343)
                 const BriggsHdr B = dmg_briggs_hdr(P.dmg[rg->slot], rng_block(P.key, id, 0u, ST_DEAM));
-                s_bh[lane] = (unsigned long long)B.o5 | ((unsigned long long)B.o3 << 16) | ((unsigned long long)B.nick << 32);
+                s_bh[lane] = (unsigned long long)(uint32_t)B.o5 | ((unsigned long long)(uint32_t)B.o3 << 32);
             }
         }
         // warp exclusive scan of pk
@@ -596,38 +578,68 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         if (lane == 0) {   // publish this tile's byte count for the look-back
             st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
             if (overflow) my_err |= ERRF_OVERFLOW;
+#if GG_BULK_COPY
+            bulk_wait_read();                                    // the previous tile's bulk copy has read its staging bytes (pass A gave it time)
+#endif
         }
+        __syncwarp();
 
         // ------------------------------------------------------------ pass B1: work maps (owner lane)
         if (lane < nf && !overflow) {
             const uint32_t roff = PK_BYTES(excl), c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
-            s_recoff[lane] = roff; s_cstart[lane] = (uint16_t)c0; s_gstart[lane] = (uint16_t)g0;
-            const uint32_t nch = PK_CHUNKS(pk), ngr = PK_GROUPS(pk);
+            s_so[lane] = roff + (uint32_t)s_hdr[lane] + (uint32_t)sfx0 + 1u; s_cstart[lane] = (uint16_t)c0;
+            const uint32_t nch = PK_CHUNKS(pk);
 #pragma unroll 1
             for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)lane;
+            if (emit <= 1) {                                     // the adptSim dialects have the same number of groups for every fragment: no map
+                const uint32_t ngr = PK_GROUPS(pk);
+                s_gstart[lane] = (uint16_t)g0;
 #pragma unroll 1
-            for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)lane;
+                for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)lane;
+            }
         }
         // first look-back probe, issued now and consumed after the damage pass (its latency overlaps pass C)
         unsigned long long lb = 2ull << 62;
         if (tile > 0 && tile - 1 - lane >= 0) lb = ld_volatile_u64(P.tile_state + (tile - 1 - lane));
         __syncwarp();
 
-        // ------------------------------------------------------------ pass C: gather + damage (lane per 16-base chunk)
+        // ------------------------------------------------------------ pass C: gather (lane per 16-base chunk)
         if (!overflow)
         for (uint32_t e = lane; e < n_chunks; e += 32) {
             const int f = s_cmap[e];
             const int k = (int)e - (int)s_cstart[f];
             const uint32_t meta = s_meta[f];
-            const int fl = META_L(meta), slot = META_SLOT(meta);
+            const int fl = META_L(meta);
             const uint64_t gp = s_gpos[f];
             const uint32_t* seq2 = t_genomes[META_GEN(meta)].seq2;
             const int n = min(16, fl - 16 * k);
             uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
                                          : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
-            if (slot >= 0 && emit != 0)
-                W = damage_chunk<DMODE>(P, P.dmg[slot], s_thr + P.sm.thr_slot[slot], DMODE == 1 ? 0ull : s_bh[f], P.first + tile_first + (uint64_t)f, k, fl, n, W);
+            if (DMODE == 0 && emit != 0) {                           // the models still drawn per base
+                const int slot = META_SLOT(meta);
+                if (slot >= 0 && P.dmg[slot].mode >= 3) W = damage_chunk_perbase(P, P.dmg[slot], s_bh[f], P.first + tile_first + (uint64_t)f, k, fl, n, W);
+            }
             s_dwords[e] = W & lowfields(n);
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------ pass E: damage events (lane per fragment; deamSim.cpp:1477-1613,1794-1930)
+        if (emit != 0 && lane < nf && !overflow) {
+            const uint32_t meta = s_meta[lane];
+            const int slot = META_SLOT(meta);
+            if (slot >= 0) {
+                const int mode = DMODE != 0 ? DMODE : P.dmg[slot].mode;
+                const int L = META_L(meta);
+                const uint64_t id = P.first + tile_first + (uint64_t)lane;
+                SeqPacked Sq; Sq.w = s_dwords + s_cstart[lane];
+                if (mode == 1) {
+                    if (DMODE == 1) matrix_events<7, true>(P.key, P.dmg[slot], s_thr + P.sm.term_slot[slot], s_thr + P.sm.thr_slot[slot], Sq, L, id);
+                    else matrix_events<7, false>(P.key, P.dmg[slot], P.dmg[slot].term, P.dmg[slot].acc, Sq, L, id);
+                } else if (mode == 2) {
+                    const BriggsHdr B = dmg_briggs_hdr(P.dmg[slot], rng_block(P.key, id, 0u, ST_DEAM));
+                    briggs_events<7>(P.key, P.dmg[slot], B, Sq, L, id);
+                }
+            }
         }
         __syncwarp();
 
@@ -673,22 +685,26 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 const int S = emit_seqlen(emit, L, RL);
                 const char* nm = t_names + t_noff[ci];
                 const int nlen = t_nlen[ci];
-                uint8_t* p = s_stage + pad + s_recoff[lane];
+                const uint32_t nd = s_nd[lane];
+                const int n1 = (int)(nd & 15u), n2 = (int)((nd >> 4) & 15u), n3 = (int)(nd >> 8);
+                const uint64_t iend = idx + (uint64_t)L;
+                uint8_t* p = s_stage + pad + (int)s_so[lane] - (int)s_hdr[lane] - sfx0 - 1;      // first byte of the record
                 for (int ln = 0; ln < nlines; ln++) {
                     // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
                     *p++ = '>';
 #pragma unroll 1
-                    for (int k = 0; k < nlen; k++) *p++ = (uint8_t)nm[k];
-                    *p++ = ':'; *p++ = plus ? '+' : '-'; *p++ = ':';
-                    p = put_decimal(p, idx, ndigits(idx), s_d100); *p++ = ':';
-                    p = put_decimal(p, idx + (uint64_t)L, ndigits(idx + (uint64_t)L), s_d100); *p++ = ':';
-                    p = put_decimal(p, (uint64_t)L, ndigits((uint64_t)L), s_d100);
+                    for (int k = 0; k < nlen; k++) p[k] = (uint8_t)nm[k];
+                    p += nlen;
+                    p[0] = ':'; p[1] = plus ? '+' : '-'; p[2] = ':'; p += 3;
+                    if (iend <= 0xFFFFFFFFull) { put_dec32(p, (uint32_t)idx, n1, s_d100); p[n1] = ':'; p += n1 + 1; put_dec32(p, (uint32_t)iend, n2, s_d100); p[n2] = ':'; p += n2 + 1; }
+                    else { p = put_decimal(p, idx, n1, s_d100); *p++ = ':'; p = put_decimal(p, iend, n2, s_d100); *p++ = ':'; }
+                    put_dec32(p, (uint32_t)L, n3, s_d100); p += n3;
 #pragma unroll 1
-                    for (int k = 0; k < tag_len; k++) *p++ = (uint8_t)tag[k];
-                    if (ln ? sfx1 : sfx0) { *p++ = '_'; *p++ = 'r'; }
-                    *p++ = '\n';
-                    p += S;
-                    *p++ = '\n';
+                    for (int k = 0; k < tag_len; k++) p[k] = (uint8_t)tag[k];
+                    p += tag_len;
+                    if (ln ? sfx1 : sfx0) { p[0] = '_'; p[1] = 'r'; p += 2; }
+                    p[0] = '\n'; p[S + 1] = '\n';
+                    p += S + 2;
                 }
             }
         };
@@ -697,25 +713,20 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         // ------------------------------------------------------------ pass D: ASCII (lane per 16-byte staging group)
         if (!overflow)
         for (uint32_t e = lane; e < n_groups; e += 32) {
-            const int f = s_gmap[e];
-            const int fl = META_L(s_meta[f]);
-            const int S = emit_seqlen(emit, fl, RL);
-            const int gpl = ((S + 15) >> 4) + 1;                    // group slots per line
-            int g = (int)e - (int)s_gstart[f];
-            const int line = g >= gpl ? 1 : 0;
-            g -= line * gpl;
-            const int h = s_hdr[f];
-            // staging offset of the first sequence byte of this line
-            const int ls = pad + (int)s_recoff[f] + line * (h + 1 + S + 1) + h + (line ? sfx1 : sfx0) + 1;
+            int f, g;
+            if (emit >= 2) { f = (int)__umulhi(e, P.gmagic); g = (int)(e - (uint32_t)f * gpf_ad); }   // e / groups-per-fragment by a host-made reciprocal
+            else { f = s_gmap[e]; g = (int)e - (int)s_gstart[f]; }
+            int S = S_ad, gpl = (int)gpl_ad;
+            if (emit <= 1) { S = META_L(s_meta[f]); gpl = ((S + 15) >> 4) + 1; }
+            int ls = pad + (int)s_so[f];                           // staging offset of the first sequence byte of this line
+            int line = 0;
+            if (nlines == 2 && g >= gpl) { line = 1; g -= gpl; ls += (int)s_hdr[f] + sfx1 + S + 2; }
             const int sigma = ls & 15;
             const int j0 = 16 * g - sigma;
             const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
             if (jhi <= jlo) continue;
             const uint32_t* src = emit <= 1 ? s_dwords + s_cstart[f] : s_lwords + f * (nlines * LWL) + line * LWL + 1;
-            const uint32_t codes = fetch_run_smem(src, j0);
-            uint4 a;
-            a.x = s_lut[codes & 0xFFu]; a.y = s_lut[(codes >> 8) & 0xFFu];
-            a.z = s_lut[(codes >> 16) & 0xFFu]; a.w = s_lut[codes >> 24];
+            const uint4 a = codes16_to_ascii(fetch_run_smem(src, j0));
             uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
             if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
                 *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
@@ -738,14 +749,20 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
         if (FASTB) { write_headers(); __syncwarp(); }
 
-        // ------------------------------------------------------------ copy-out: staging -> global, aligned 16-byte vector stores
+        // ------------------------------------------------------------ copy-out: staging -> global
         if (!overflow) {
             if (gofs + T > P.out_cap) { my_err |= ERRF_OVERFLOW; }
             else {
                 uint8_t* const gal = P.out + gofs - pad;                 // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+T)
                 const int end = pad + (int)T;
                 const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
+#if GG_BULK_COPY
+                fence_async_smem();                                      // this lane's staging writes -> visible to the bulk-copy engine
+                __syncwarp();
+                if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
+#else
                 for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
+#endif
                 // the partial head [pad, 16 c_lo) and tail [16 max(c_hi, c_lo), end): at most 15 bytes each, one byte per lane
                 const int t = lane < 16 ? pad + lane : 16 * max(c_hi, c_lo) + (lane - 16);
                 if (lane < 16 ? t < min(16 * c_lo, end) : t < end) gal[t] = s_stage[t];
@@ -753,6 +770,9 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         }
         __syncwarp();
     }
+#if GG_BULK_COPY
+    if (lane == 0) bulk_wait_all();
+#endif
 
     // per-warp statistics
     my_attempts = warp_sum_u64(my_attempts); my_gather = warp_sum_u64(my_gather);
@@ -914,46 +934,75 @@ __device__ __forceinline__ RecPos rec_pos(const RecStream& R, uint64_t r) {
     return p;
 }
 
-// stand-alone deamSim main loop (deamSim.cpp:1300-2042): warp per record
+// ASCII record in global memory (already upper-cased) as the sequence the event draws work on
+struct SeqAscii {
+    uint8_t* p;
+    __device__ __forceinline__ int code(int i) const { return ascii2code(p[i]); }
+    __device__ __forceinline__ void put(int i, uint32_t oldb, uint32_t newb) { if (newb != oldb) p[i] = code2ascii(newb); }
+};
+// the event-drawn models (-matfile, -damage) on one record; PH as in matrix_events / briggs_events
+template <int PH, class SeqT>
+__device__ __forceinline__ void deam_events(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int L, SeqT& S) {
+    if (D.mode == 1) matrix_events<PH, false>(key, D, D.term, D.acc, S, L, id);
+    else if (D.mode == 2) briggs_events<PH>(key, D, B, S, L, id);
+}
+
+// stand-alone deamSim main loop (deamSim.cpp:1300-2042): a warp takes 32 records; the lanes copy them (upper-casing the sequence,
+// deamSim.cpp:1319-1321, and applying the models that are drawn per base), then every lane draws the damage events of one record
 __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t* __restrict__ out, const DamageDev D, int has_damage,
                                                       Key key, uint64_t first_id, unsigned long long* stats) {
     const int lane = threadIdx.x & 31;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < R.n_rec; r += nw) {
-        const RecPos p = rec_pos(R, r);
-        const uint64_t id = first_id + r;
-        if (lane == 0 && (p.ide <= p.ids || R.in[p.ids] != '>')) atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
-        for (uint64_t i = p.ids + lane; i < p.ss; i += 32) out[i] = R.in[i];          // ID line + '\n' unchanged (deamSim.cpp:2038)
-        const int L = (int)(p.se - p.ss);
-        BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (has_damage && (D.mode == 2 || D.mode == 5)) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
-        for (int i = lane; i < L; i += 32) {
-            uint8_t c = upper(R.in[p.ss + i]);                                         // toupper, deamSim.cpp:1319-1321
-            const int code = ascii2code(c);
-            if (has_damage && code >= 0) {                                             // unresolved bases are never touched (deamSim.cpp:1795)
-                uint32_t nb = (uint32_t)code;
-                if (D.mode == 1) nb = dmg_matrix_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i));
-                else if (D.mode == 2 || D.mode == 5) nb = dmg_briggs_base<true>(D, B, i, L, nb, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
-                else if (D.mode == 3 || D.mode == 4) nb = dmg_sd_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i), rng_word(key, id, ST_DEAM2, (uint32_t)i));
-                c = code2ascii(nb);
+    const bool perbase = has_damage && D.mode >= 3, events = has_damage && (D.mode == 1 || D.mode == 2);
+    for (uint64_t r0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32ull; r0 < R.n_rec; r0 += nw * 32ull) {
+        const int nr = (int)min((uint64_t)32, R.n_rec - r0);
+        for (int rr = 0; rr < nr; rr++) {
+            const uint64_t r = r0 + (uint64_t)rr;
+            const RecPos p = rec_pos(R, r);
+            const uint64_t id = first_id + r;
+            if (lane == 0 && (p.ide <= p.ids || R.in[p.ids] != '>')) atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
+            for (uint64_t i = p.ids + lane; i < p.ss; i += 32) out[i] = R.in[i];          // ID line + '\n' unchanged (deamSim.cpp:2038)
+            const int L = (int)(p.se - p.ss);
+            BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+            if (perbase && D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+            for (int i = lane; i < L; i += 32) {
+                uint8_t c = upper(R.in[p.ss + i]);                                         // toupper, deamSim.cpp:1319-1321
+                const int code = ascii2code(c);
+                if (perbase && code >= 0) {                                                // unresolved bases are never touched (deamSim.cpp:1795)
+                    uint32_t nb = (uint32_t)code;
+                    if (D.mode == 5) nb = dmg_briggs_ss_base(D, B, i, L, nb, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
+                    else nb = dmg_sd_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i), rng_word(key, id, ST_DEAM2, (uint32_t)i));
+                    c = code2ascii(nb);
+                }
+                out[p.ss + i] = c;
             }
-            out[p.ss + i] = c;
+            if (lane == 0) out[p.se] = '\n';
         }
-        if (lane == 0) out[p.se] = '\n';
+        if (events) {
+            __syncwarp();                                                                  // the copies above are visible to the lane that owns the record
+            if (lane < nr) {
+                const uint64_t r = r0 + (uint64_t)lane;
+                const RecPos p = rec_pos(R, r);
+                const uint64_t id = first_id + r;
+                const int L = (int)(p.se - p.ss);
+                BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+                if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+                SeqAscii S; S.p = out + p.ss;
+                deam_events<7>(D, B, key, id, L, S);
+            }
+        }
     }
 }
 // ---- deamSim -name: "_DEAM:p1,p2,..." appended to the ID of every damaged record (deamSim.cpp:2029-2037).
 // Position lists follow the reference's push order: matrix: i ascending, +(i+1) in the 5' half, -(len-i) in the 3' half
 // (:1857,1919); Briggs: +(i+1) (:1489-1589); single/double: all pass-1 hits +(i+1), then all pass-2 hits -(len-i) (:1949-1994).
 struct DeamEvt { uint32_t nb; int v0, v1; };     // new base; list-0 value (0 = none); list-1 value (0 = none)
+// the models drawn per base (-damagess, -mat single|double)
 __device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int i, int L, int code) {
     DeamEvt e; e.nb = (uint32_t)code; e.v0 = 0; e.v1 = 0;
     const uint32_t b = (uint32_t)code;
-    if (D.mode == 1) {
-        e.nb = dmg_matrix_base(D, i, L, b, rng_word(key, id, ST_DEAM, (uint32_t)i));
-        if (e.nb != b) e.v0 = (i < (L >> 1)) ? i + 1 : -(L - i);
-    } else if (D.mode == 2 || D.mode == 5) {
-        e.nb = dmg_briggs_base<true>(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
+    if (D.mode == 5) {
+        e.nb = dmg_briggs_ss_base(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
         if (e.nb != b) e.v0 = i + 1;
     } else {
         const uint32_t x1 = rng_word(key, id, ST_DEAM, (uint32_t)i), x2 = rng_word(key, id, ST_DEAM2, (uint32_t)i);
@@ -967,19 +1016,52 @@ __device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHd
     return e;
 }
 __device__ __forceinline__ int evt_text_len(int v) { return v == 0 ? 0 : 1 + (v < 0 ? 1 : 0) + ndigits((uint64_t)(v < 0 ? -v : v)); }   // separator + sign + digits
+// the event-drawn models under -name: the phases of matrix_events / briggs_events run in position order, so the list comes out in the
+// reference's order.  Sizing pass: in = the input sequence (upper-cased on the fly), txt = nullptr; writing pass: the output record.
+struct SeqAsciiNamed {
+    const uint8_t* in; uint8_t* outp; uint8_t* txt; uint32_t cur; int L, half_or_neg;     // half_or_neg: matrix = L/2 (3' half listed as -(L-i)), Briggs = -1
+    __device__ __forceinline__ int code(int i) const { return ascii2code(upper(in[i])); }
+    __device__ __forceinline__ void put(int i, uint32_t oldb, uint32_t newb) {
+        if (newb == oldb) return;
+        const int v = (half_or_neg < 0 || i < half_or_neg) ? i + 1 : -(L - i);
+        if (txt) {
+            outp[i] = code2ascii(newb);
+            uint8_t* q = txt + cur;
+            *q++ = cur == 5u ? ':' : ',';                                                  // the first event follows "_DEAM"
+            if (v < 0) *q++ = '-';
+            uint32_t a = (uint32_t)(v < 0 ? -v : v); const int nd = ndigits((uint64_t)a);
+            for (int k = nd - 1; k >= 0; k--) { q[k] = (uint8_t)('0' + a % 10u); a /= 10u; }
+        }
+        cur += (uint32_t)evt_text_len(v);
+    }
+};
 
 // pass 1: output bytes per record
 __global__ void __launch_bounds__(256) k_deam_name_sizes(const RecStream R, const DamageDev D, Key key, uint64_t first_id,
                                                          unsigned long long* __restrict__ sizes, unsigned long long* stats) {
     const int lane = threadIdx.x & 31;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (D.mode == 1 || D.mode == 2) {                                                      // event-drawn models: thread per record
+        for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R.n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
+            const RecPos p = rec_pos(R, r);
+            const uint64_t id = first_id + r;
+            if (p.ide <= p.ids || R.in[p.ids] != '>') atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
+            const int L = (int)(p.se - p.ss);
+            BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+            if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+            SeqAsciiNamed S; S.in = R.in + p.ss; S.outp = nullptr; S.txt = nullptr; S.cur = 5u; S.L = L; S.half_or_neg = D.mode == 1 ? (L >> 1) : -1;
+            deam_events<1>(D, B, key, id, L, S); deam_events<2>(D, B, key, id, L, S); deam_events<4>(D, B, key, id, L, S);
+            sizes[r] = (p.ide - p.ids) + (S.cur > 5u ? (unsigned long long)S.cur : 0ull) + 1ull + (unsigned long long)L + 1ull;
+        }
+        return;
+    }
     for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < R.n_rec; r += nw) {
         const RecPos p = rec_pos(R, r);
         const uint64_t id = first_id + r;
         if (lane == 0 && (p.ide <= p.ids || R.in[p.ids] != '>')) atomicOr(stats + ST_ERR, (unsigned long long)ERRF_PARSE);
         const int L = (int)(p.se - p.ss);
         BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (D.mode == 2 || D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        if (D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         unsigned long long txt = 0;
         for (int i = lane; i < L; i += 32) {
             const int code = ascii2code(upper(R.in[p.ss + i]));
@@ -994,6 +1076,38 @@ __global__ void __launch_bounds__(256) k_deam_name_records(const RecStream R, co
                                                            const DamageDev D, Key key, uint64_t first_id) {
     const int lane = threadIdx.x & 31;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (D.mode == 1 || D.mode == 2) {                                                      // event-drawn models: the warp copies 32 records, then a lane per record
+        for (uint64_t r0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32ull; r0 < R.n_rec; r0 += nw * 32ull) {
+            const int nr = (int)min((uint64_t)32, R.n_rec - r0);
+            for (int rr = 0; rr < nr; rr++) {
+                const uint64_t r = r0 + (uint64_t)rr;
+                const RecPos p = rec_pos(R, r);
+                const int L = (int)(p.se - p.ss);
+                const uint64_t idlen = p.ide - p.ids, total = out_off[r + 1] - out_off[r];
+                uint8_t* o = out + out_off[r];
+                uint8_t* seqo = o + (total - (uint64_t)L - 1);
+                for (uint64_t i = lane; i < idlen; i += 32) o[i] = R.in[p.ids + i];
+                if (total > idlen + 1 + (uint64_t)L + 1 && lane < 5) o[idlen + lane] = (uint8_t)"_DEAM"[lane];
+                for (int i = lane; i < L; i += 32) seqo[i] = upper(R.in[p.ss + i]);
+                if (lane == 0) { seqo[-1] = '\n'; seqo[L] = '\n'; }
+            }
+            __syncwarp();
+            if (lane < nr) {
+                const uint64_t r = r0 + (uint64_t)lane;
+                const RecPos p = rec_pos(R, r);
+                const uint64_t id = first_id + r;
+                const int L = (int)(p.se - p.ss);
+                const uint64_t idlen = p.ide - p.ids, total = out_off[r + 1] - out_off[r];
+                uint8_t* o = out + out_off[r];
+                BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
+                if (D.mode == 2) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+                SeqAsciiNamed S; S.in = R.in + p.ss; S.outp = o + (total - (uint64_t)L - 1); S.txt = o + idlen; S.cur = 5u; S.L = L; S.half_or_neg = D.mode == 1 ? (L >> 1) : -1;
+                deam_events<1>(D, B, key, id, L, S); deam_events<2>(D, B, key, id, L, S); deam_events<4>(D, B, key, id, L, S);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < R.n_rec; r += nw) {
         const RecPos p = rec_pos(R, r);
         const uint64_t id = first_id + r;
@@ -1002,7 +1116,7 @@ __global__ void __launch_bounds__(256) k_deam_name_records(const RecStream R, co
         uint8_t* o = out + out_off[r];
         for (uint64_t i = lane; i < idlen; i += 32) o[i] = R.in[p.ids + i];
         BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
-        if (D.mode == 2 || D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+        if (D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         const uint64_t total = out_off[r + 1] - out_off[r];                       // sizes array has a sentinel entry
         uint8_t* seqo = o + (total - (uint64_t)L - 1);                            // sequence start
         const bool any = total > idlen + 1 + (uint64_t)L + 1;

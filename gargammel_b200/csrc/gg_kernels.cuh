@@ -50,12 +50,12 @@ struct Adapters {
     int lenF, lenS, read_len, pad;
 };
 struct SmemLayout {          // byte offsets into dynamic shared memory, computed by the host
-    int lut;                 // CTA-shared: 4-bases -> 4-ASCII table
-    int thr, thr_bytes;      // CTA-shared copy of the matrix thresholds of the used damage slots (DMODE 1)
-    int thr_slot[4];         // uint4 index of each slot's table inside that copy
+    int thr, thr_bytes;      // CTA-shared copy of the matrix tables of the used damage slots (DMODE 1)
+    int thr_slot[4];         // uint4 index of each slot's acceptance rows inside that copy ...
+    int term_slot[4];        // ... and of its terminal rows
     int warp0, warp_bytes;   // per-warp regions start at warp0 + warp * warp_bytes; the offsets below are relative to a region
     int stage, stage_bytes;  // output staging (readable slack before and after)
-    int gpos, meta, recoff, hdr, cstart, gstart;   // per-fragment descriptors
+    int gpos, meta, so, hdr, nd, cstart, gstart;   // per-fragment descriptors
     int idx, ci, rg;                               // per-fragment header state parked between passes
     int bh;                                        // per-fragment Briggs header draws (overhangs, nick), u64 each
     int dwords, lwords, cmap, gmap, total;
@@ -74,7 +74,8 @@ struct FusedParams {
     int emit;                // gg_emit_mode
     int norev;
     int fast_boundary;       // every header >= 13 bytes: whole-group stores, headers written afterwards
-    int dmode;               // 1: every damage slot used by the plan is a matrix (specialised kernel), 0: any mix
+    int dmode;               // 1: every damage slot used by the plan is a matrix (specialised kernel), 2: every slot is Briggs, 0: any mix
+    uint32_t gmagic;         // ceil(2^32 / staging groups per fragment) of the adptSim dialects: group index -> fragment by one multiply
     ggd::Key key;
     // plan + genomes
     const RangeDev* ranges; int n_ranges;
@@ -98,7 +99,7 @@ struct FusedParams {
 };
 
 #ifndef GG_FUSED_MAXT
-#define GG_FUSED_MAXT 640      // launch bound of k_fused: 20 warps, 96 registers (measured best of 640/672/704)
+#define GG_FUSED_MAXT 640      // launch bound of k_fused: 20 warps, 96 registers
 #endif
 enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
 enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };

@@ -242,6 +242,13 @@ static std::vector<double> geomCdf(double p, int n) {
     for (int k = 0; k < n; k++) { q *= (1.0 - p); cdf[k] = 1.0 - q; }
     return cdf;
 }
+/* the same table, built once per parameter (the oracle is single-threaded) */
+static const std::vector<double>& geomCdfCached(double p) {
+    static std::map<double, std::vector<double> > cache;
+    std::map<double, std::vector<double> >::iterator it = cache.find(p);
+    if (it == cache.end()) it = cache.insert(std::make_pair(p, geomCdf(p, 4096))).first;
+    return it->second;
+}
 static int geomDraw(const std::vector<double>& cdf, uint32_t x) {
     double p = u01(x);
     for (size_t k = 0; k < cdf.size(); k++) if (p <= cdf[k]) return (int)k;
@@ -249,73 +256,163 @@ static int geomDraw(const std::vector<double>& cdf, uint32_t x) {
 }
 #define GEOM_TABLE 4096
 
-/* -matfile loop, deamSim.cpp:1794-1930 */
+/* ---- draw specification v2 (DESIGN.md "Draw specification"): -matfile and -damage are drawn as EVENTS, not per base.
+ * The reference draws one uniform per base and changes the base with the probability its table gives (deamSim.cpp:1847-1863,
+ * 1488-1592).  Per-base draws are independent, so the same law is obtained by thinning: positions become "candidates" with a
+ * probability m >= (the total rate of any base there), found by geometric skips, and a candidate with base b becomes a with
+ * probability rate(b->a)/m.  The few terminal rows whose rates are far above the rest keep a per-base categorical draw. */
+#define NT_MAX 8                     /* at most this many terminal rows per end are drawn per base */
+#define NT_KAPPA 1.25                /* a row is terminal when its total rate exceeds NT_KAPPA x (largest rate of the rows >= NT_MAX) */
+#define GEOM_MISS (1 << 30)          /* "beyond any record": an overhang / nick draw that ran off the 4096-entry table */
+
+/* total substitution rate of base b in a row of 12, summed in the reference's order (a ascending, deamSim.cpp:1820-1830) */
+static double rowRate(const double* row, int b) {
+    double sum = 0.0;
+    for (int a = 0; a < 4; a++) { if (a == b) continue; sum += row[(a < b) ? b * 3 + a : b * 3 + (a - 1)]; }
+    return sum;
+}
+static double rowMax(const double* row) { double m = 0.0; for (int b = 0; b < 4; b++) m = std::max(m, rowRate(row, b)); return m; }
+/* row of `sub` (n rows) that applies at distance `dist` from its end; NULL = position left untouched (-last, deamSim.cpp:1814-1816) */
+static const double* effRow(const std::vector<double>& sub, int clamp_last, int dist) {
+    int n = (int)(sub.size() / 12);
+    if (dist >= n) { if (!clamp_last) return NULL; dist = n - 1; }          /* :1811-1813 */
+    return &sub[(size_t)dist * 12];
+}
+struct MatrixPlan { int n5t, n3t; double M; std::vector<double> cdfM; };
+static MatrixPlan matrixPlan(const Damage& D) {
+    MatrixPlan P; P.n5t = P.n3t = 0;
+    double tail = 0.0;                                                      /* largest total rate at distances >= NT_MAX */
+    for (int e = 0; e < 2; e++) {
+        const std::vector<double>& sub = e ? D.sub3 : D.sub5; const int n = (int)(sub.size() / 12);
+        for (int r = NT_MAX; r < n; r++) tail = std::max(tail, rowMax(&sub[(size_t)r * 12]));
+        if (D.clamp_last) tail = std::max(tail, rowMax(&sub[(size_t)(n - 1) * 12]));
+    }
+    double M = tail;
+    for (int e = 0; e < 2; e++) {
+        const std::vector<double>& sub = e ? D.sub3 : D.sub5;
+        int nt = 0;
+        for (int dist = 0; dist < NT_MAX; dist++) { const double* row = effRow(sub, D.clamp_last, dist); if (row && rowMax(row) > NT_KAPPA * tail) nt = dist + 1; }
+        for (int dist = nt; dist < NT_MAX; dist++) { const double* row = effRow(sub, D.clamp_last, dist); if (row) M = std::max(M, rowMax(row)); }
+        if (e) P.n3t = nt; else P.n5t = nt;
+    }
+    P.M = M;
+    return P;
+}
+/* the reference's categorical pick for one base (deamSim.cpp:1797-1863): cumulative sums in its operation order, inclusive compares */
+static int categorical(const double* row, int b, double p) {
+    double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
+    double sum = 0.0;
+    for (int a = 0; a < 4; a++) {                                           /* :1820-1830 */
+        if (a == b) continue;
+        int idx = (a < b) ? b * 3 + a : b * 3 + (a - 1);
+        sum += row[idx]; _sumProb[a + 1] = row[idx];
+    }
+    _sumProb[b + 1] = 1.0 - sum;                                            /* :1831 */
+    double s = 0;
+    for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }       /* :1833-1837 */
+    for (int a = 0; a < 4; a++) if (sumProb[a] <= p && sumProb[a + 1] >= p) return a;   /* :1849-1863 */
+    return b;
+}
+
+/* -matfile, deamSim.cpp:1794-1930, drawn as events.  Stream DEAM of the fragment:
+ *   block t/4, word t%4 (t < n5t): the categorical draw of the 5' terminal position t           (exists while t < len/2)
+ *   block B3 + t/4, word t%4 (t < n3t), B3 = ceil(n5t/4): the 3' terminal position len-1-t       (exists while len-1-t >= len/2)
+ *   block BG + n/2, BG = B3 + ceil(n3t/4): round n of the interior [min(n5t,len/2), max(len/2,len-n3t)) uses words 2(n%2) (geometric
+ *   skip under the majorant M) and 2(n%2)+1 (which substitution, if any, the candidate takes). */
 static void deamMatrix(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
-    int n5 = (int)(D.sub5.size() / 12), n3 = (int)(D.sub3.size() / 12);
-    int len = (int)seq.size();
-    for (int i = 0; i < len; i++) {
-        if (!isResolvedDNA(seq[i])) continue;                       /* :1795 */
-        double sumProb[5], _sumProb[5];
-        sumProb[0] = 0.0; _sumProb[0] = 0.0;
-        const double* row;
-        if (i < len / 2) {                                          /* :1805  5p */
-            int r = i;
-            if (r >= n5) { if (D.clamp_last) r = n5 - 1; else continue; }   /* :1811-1817 */
-            row = &D.sub5[(size_t)r * 12];
-        } else {                                                    /* :1868  3p */
-            int r = len - i - 1;                                    /* :1873 */
-            if (r >= n3) { if (D.clamp_last) r = n3 - 1; else continue; }   /* :1874-1880 */
-            row = &D.sub3[(size_t)r * 12];
-        }
-        int b = base2int(seq[i]);
-        double sum = 0.0;
-        for (int a = 0; a < 4; a++) {                               /* :1820-1830 */
-            if (a == b) continue;
-            int idx = (a < b) ? b * 3 + a : b * 3 + (a - 1);
-            sum += row[idx];
-            _sumProb[a + 1] = row[idx];
-        }
-        _sumProb[b + 1] = 1.0 - sum;                                /* :1831 */
-        double s = 0;
-        for (int a = 0; a < 5; a++) { s += _sumProb[a]; sumProb[a] = s; }   /* :1833-1837 */
-        double p = u01(c->rng.word(id, ST_DEAM, (uint32_t)i));      /* :1847 one uniform per resolved base */
-        for (int a = 0; a < 4; a++) {                               /* :1849-1863 */
-            if (sumProb[a] <= p && sumProb[a + 1] >= p) {
-                seq[i] = "ACGT"[a];
-                if (a != b && deamPos) deamPos->push_back(i < len / 2 ? i + 1 : -(len - i));          /* :1856-1859, :1918-1921 */
-                break;
+    const int len = (int)seq.size(), half = len / 2;                        /* i < len/2 is the 5' side (:1805) */
+    const MatrixPlan P = matrixPlan(D);
+    const int n5 = std::min(P.n5t, half), n3 = std::min(P.n3t, len - half);
+    const int B3 = (P.n5t + 3) / 4, BG = B3 + (P.n3t + 3) / 4;
+    std::vector<std::pair<int, int> > ev;                                   /* (position, new base) */
+    for (int t = 0; t < n5; t++) {
+        const int i = t;
+        if (!isResolvedDNA(seq[i])) continue;                               /* :1795 */
+        const double* row = effRow(D.sub5, D.clamp_last, t); if (!row) continue;
+        const int b = base2int(seq[i]), a = categorical(row, b, u01(c->rng.word(id, ST_DEAM, (uint32_t)t)));
+        if (a != b) ev.push_back(std::make_pair(i, a));
+    }
+    for (int t = 0; t < n3; t++) {
+        const int i = len - 1 - t;
+        if (!isResolvedDNA(seq[i])) continue;
+        const double* row = effRow(D.sub3, D.clamp_last, t); if (!row) continue;   /* distance from the 3' end, :1873 */
+        const int b = base2int(seq[i]), a = categorical(row, b, u01(c->rng.word(id, ST_DEAM, (uint32_t)(4 * B3 + t))));
+        if (a != b) ev.push_back(std::make_pair(i, a));
+    }
+    if (P.M > 0.0) {
+        const std::vector<double>& cdfM = geomCdfCached(P.M);
+        const int end = len - n3;
+        int pos = n5;
+        for (uint32_t n = 0; pos < end; n++) {
+            const uint32_t w0 = (uint32_t)(4 * BG) + 2 * n;
+            const int j = geomDraw(cdfM, c->rng.word(id, ST_DEAM, w0));
+            pos += j;                                                       /* a table miss is "at least GEOM_TABLE": no candidate, the next round goes on from there */
+            if (j == GEOM_TABLE || pos >= end) continue;
+            const int i = pos++;
+            if (!isResolvedDNA(seq[i])) continue;
+            const double* row = (i < half) ? effRow(D.sub5, D.clamp_last, i) : effRow(D.sub3, D.clamp_last, len - i - 1);
+            if (!row) continue;
+            const int b = base2int(seq[i]);
+            const double p = u01(c->rng.word(id, ST_DEAM, w0 + 1));
+            double cum = 0.0;
+            for (int a = 0; a < 4; a++) {                                   /* rate(b->a)/M, a ascending */
+                if (a == b) continue;
+                cum += row[(a < b) ? b * 3 + a : b * 3 + (a - 1)];
+                if (p < cum / P.M) { ev.push_back(std::make_pair(i, a)); break; }
             }
         }
     }
+    std::sort(ev.begin(), ev.end());                                        /* the reference walks i upwards (:1794) */
+    for (size_t k = 0; k < ev.size(); k++) {
+        const int i = ev[k].first;
+        seq[i] = "ACGT"[ev[k].second];
+        if (deamPos) deamPos->push_back(i < half ? i + 1 : -(len - i));     /* :1856-1859, :1918-1921 */
+    }
 }
 
-/* -damage v,l,d,s loop, deamSim.cpp:1477-1613.  Draw layout: DEAM words 0,1,2 = 5' overhang, 3' overhang,
- * nick position (geometric: first success of the per-base Bernoulli(v) scan :1503-1507); per-base word 4+i. */
+/* -damage v,l,d,s, deamSim.cpp:1477-1613, drawn as events.  Stream DEAM: block 0 words 0,1,2 = 5' overhang, 3' overhang, nick
+ * position (geometric: first success of the per-base Bernoulli(v) scan :1503-1507); block 1+n: words 0 and 2 are geometric skips
+ * (rate s) over the single-stranded positions (5' overhang, then 3' overhang; the whole fragment when the overhangs meet, :1483),
+ * words 1 and 3 geometric skips (rate d) over the double-stranded middle.  A candidate changes iff its base is the one the region
+ * deaminates (C->T before the nick / in the 5' overhang, G->A behind it / in the 3' overhang). */
 static void deamBriggs(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
-    int len = (int)seq.size();
-    std::vector<double> cdfL = geomCdf(D.l, GEOM_TABLE), cdfV = geomCdf(D.v, GEOM_TABLE);
+    const int len = (int)seq.size();
+    const std::vector<double> &cdfL = geomCdfCached(D.l), &cdfV = geomCdfCached(D.v), &cdfS = geomCdfCached(D.s), &cdfD = geomCdfCached(D.d);
     uint32_t h[4]; c->rng.block(id, 0, ST_DEAM, h);
-    int overhang5p = geomDraw(cdfL, h[0]);                          /* :1478 */
-    int overhang3p = geomDraw(cdfL, h[1]);                          /* :1479 */
-    if (overhang5p + overhang3p >= len) {                           /* :1483 all single strand */
-        for (int i = 0; i < len; i++)
-            if (seq[i] == 'C' && u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i)) < D.s) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }   /* :1486-1494 */
-        return;
-    }
-    int indexNick = geomDraw(cdfV, h[2]);                           /* first i with randomProb()<v, :1503-1507 */
-    for (int i = 0; i < len; i++) {
-        bool placedNick = (indexNick <= i);                         /* nick applies from its own position on (:1510) */
-        double p = u01(c->rng.word(id, ST_DEAM, 4 + (uint32_t)i));
-        if ((i + 1) <= overhang5p) {                                /* :1513 / :1557 */
-            if (seq[i] == 'C' && p < D.s) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
-        } else if ((len - i) <= overhang3p) {                       /* :1527 / :1571 */
-            if (seq[i] == 'G' && p < D.s) { seq[i] = 'A'; if (deamPos) deamPos->push_back(i + 1); }
-        } else if (placedNick) {                                    /* :1542 */
-            if (seq[i] == 'G' && p < D.d) { seq[i] = 'A'; if (deamPos) deamPos->push_back(i + 1); }
-        } else {                                                    /* :1586 */
-            if (seq[i] == 'C' && p < D.d) { seq[i] = 'T'; if (deamPos) deamPos->push_back(i + 1); }
+    long o5 = geomDraw(cdfL, h[0]), o3 = geomDraw(cdfL, h[1]), nick = geomDraw(cdfV, h[2]);   /* :1478, :1479, :1503-1507 */
+    if (o5 == GEOM_TABLE) o5 = GEOM_MISS;                               /* off the table: longer than any record */
+    if (o3 == GEOM_TABLE) o3 = GEOM_MISS;
+    if (nick == GEOM_TABLE) nick = GEOM_MISS;
+    const bool allss = o5 + o3 >= len;                                      /* :1483 */
+    const long nS = allss ? len : o5 + o3, qend = allss ? len : len - o3;
+    long v = 0, q = allss ? len : o5;
+    std::vector<int> hits;
+    for (uint32_t n = 0; v < nS || q < qend; n++) {
+        uint32_t x[4]; c->rng.block(id, 1 + n, ST_DEAM, x);
+        for (int sub = 0; sub < 2; sub++) {
+            if (v < nS) {
+                const int j = geomDraw(cdfS, x[2 * sub]);
+                v += j;
+                if (j != GEOM_TABLE && v < nS) {
+                    const bool five = allss || v < o5;                      /* :1486, :1513 / :1527 */
+                    const long i = five ? v : len - o3 + (v - o5);
+                    if (five) { if (seq[i] == 'C') { seq[i] = 'T'; hits.push_back((int)i); } }
+                    else      { if (seq[i] == 'G') { seq[i] = 'A'; hits.push_back((int)i); } }
+                    v++;
+                }
+            }
+            if (q < qend) {
+                const int j = geomDraw(cdfD, x[2 * sub + 1]);
+                q += j;
+                if (j != GEOM_TABLE && q < qend) {
+                    if (nick <= q) { if (seq[q] == 'G') { seq[q] = 'A'; hits.push_back((int)q); } }      /* :1542 */
+                    else           { if (seq[q] == 'C') { seq[q] = 'T'; hits.push_back((int)q); } }      /* :1586 */
+                    q++;
+                }
+            }
         }
     }
+    if (deamPos) { std::sort(hits.begin(), hits.end()); for (size_t k = 0; k < hits.size(); k++) deamPos->push_back(hits[k] + 1); }
 }
 
 /* -damagess d,s5,s3,l5,l3 loop, deamSim.cpp:1337-1468 (single-strand libraries: C->T only).  Draw layout as for -damage:

@@ -171,6 +171,42 @@ def test_oracle_matrix_rates_analytic(oracle_mod):
 _BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
+@pytest.mark.parametrize("L", [50, 7, 171])
+def test_oracle_matrix_event_draws_follow_the_table(oracle_mod, L):
+    """Draw specification v2 draws -matfile damage as events (terminal rows per base, the rest by geometric skips under a majorant
+    and an acceptance draw).  The law must stay the reference's per-base categorical (deamSim.cpp:1794-1930): EVERY one of the 12
+    substitution rates at EVERY position equals its matrix entry (5 sigma), rows beyond the table clamp to the last one, and
+    substitutions at different positions stay independent."""
+    rng = np.random.default_rng(L)
+    n = 240000 if L <= 50 else 60000
+    seqs = _BASES[rng.integers(0, 4, size=(n, L))]
+    recs = b"".join(b">r%d\n%s\n" % (i, seqs[i].tobytes()) for i in range(n))
+    ctx = oracle_mod.OracleContext(1234 + L)
+    s5, s3 = synth.golden_matrix("single-")
+    ctx.set_matrix(0, s5, s3)
+    out, _ = ctx.run_deam(recs, 0)
+    got = np.frombuffer(b"".join(s for _, s in util.records(out)), dtype=np.uint8).reshape(n, L)
+    worst = 0.0
+    for i in range(L):
+        row = s5[min(i, len(s5) - 1)] if i < L // 2 else s3[min(L - 1 - i, len(s3) - 1)]
+        for b in range(4):
+            was = seqs[:, i] == _BASES[b]
+            nb = was.sum()
+            for a in range(4):
+                if a == b:
+                    continue
+                want = row[b * 3 + (a if a < b else a - 1)]
+                obs = ((got[:, i] == _BASES[a]) & was).sum() / nb
+                sd = np.sqrt(max(want * (1 - want), 1e-9) / nb)
+                worst = max(worst, abs(obs - want) / sd)
+                assert abs(obs - want) < 5.2 * sd + 1e-5, (i, b, a, obs, want)
+    # independence: changed-at-i and changed-at-j are uncorrelated (adjacent interior positions and the two ends)
+    ch = got != seqs
+    for i, j in ((L // 2 - 1, L // 2), (0, L - 1), (min(9, L - 2), min(10, L - 1))):
+        pi, pj, pij = ch[:, i].mean(), ch[:, j].mean(), (ch[:, i] & ch[:, j]).mean()
+        assert abs(pij - pi * pj) < 5 * np.sqrt(max(pi * pj, 1e-9) / n) + 1e-6, (i, j, pi, pj, pij)
+
+
 def test_oracle_sizefreq_distribution(oracle_mod):
     """-f sizefreq: the empirical length pmf follows the file (KS p > 0.01 as in north_star)."""
     from scipy import stats
