@@ -306,10 +306,10 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
                        int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
     SmemLayout s; int o = 0;
     o += 16;                                   // readable slack before staging
-    s.stage = o; s.stage_bytes = (int)((uint64_t)F * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // + tile misalignment pad (<16) + read slack
+    s.stage = o; s.stage_bytes = (int)((uint64_t)((F + 1) / 2) * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // half a tile (+ misalignment pad (<16) + read slack)
     s.gpos = o; o += 8 * F;
-    s.idx = o; o += 8 * F;
     s.bh = o; o += 8 * F;
+    s.idx = o; o += 4 * F;
     s.meta = o; o += 4 * F;
     s.so = o; o += 4 * F;
     s.ci = o; o += 4 * F;
@@ -323,7 +323,7 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     s.hdr = o; o += 2 * F;
     s.nd = o; o += 2 * F;
     s.cstart = o; o += 2 * F;
-    s.gstart = o; o += 2 * F;
+    s.gstart = o; o += 2 * F + 4;
     s.rg = o; o += 2 * F;
     s.cmap = o; o += F * max_chunks;
     s.gmap = o; o += F * max_groups;           // (only the fragSim / deamSim dialects use the group map)
@@ -885,7 +885,8 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
         const int m = ctx->dmg[sl].mode;
         if (m == GG_DMG_MATRIX) has_matrix = true; else if (m == GG_DMG_BRIGGS) has_briggs = true; else if (m != GG_DMG_NONE) has_other = true;
     }
-    int dmode = has_other || (has_matrix && has_briggs) ? 0 : has_briggs ? 2 : 1;
+    int dmode = has_other || (has_matrix && has_briggs) || !fast_boundary ? 0 : has_briggs ? 2 : 1;   // (short headers: only the general variant is built)
+    const int emitc = emit <= GG_EMIT_DEAM ? 0 : emit == GG_EMIT_STDOUT4 ? 2 : 1;
     // matrix-only plans keep their threshold tables in shared memory (L1 is only a few KB at this carve-out)
     int thr_bytes = 0, thr_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1}, term_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
     if (dmode == 1 && emit != GG_EMIT_FRAG) {
@@ -898,7 +899,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
             }
         if (thr_bytes > 48 * 1024) { dmode = 0; thr_bytes = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) thr_slot[sl] = term_slot[sl] = -1; }   // huge matrices: read them from global
     }
-    int regs = 96, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, 32, 4096, &bps0, &regs));
+    int regs = 64, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, emitc, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
     int F = 32;
     { const char* envF = getenv("GG_FUSED_F"); if (envF) F = std::max(1, std::min(32, atoi(envF))); }   // tuning knob, like GG_FUSED_WARPS
@@ -936,7 +937,13 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
 
     FusedParams P; memset(&P, 0, sizeof P);
     P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary; P.dmode = dmode;
-    { const uint64_t gpf = (uint64_t)emit_lines(emit) * (uint64_t)((Smax + 15) / 16 + 1); P.gmagic = (uint32_t)((0x100000000ull + gpf - 1) / gpf); }
+    if (emitc) {                                     // adptSim dialects: the sequence-line geometry is the same for every fragment
+        P.S_ad = Smax; P.LWL = (Smax + 15) / 16 + 2; P.lw_stride = emit_lines(emit) * P.LWL;
+        P.gpl_ad = (uint32_t)((Smax + 15) / 16 + 1); P.gpf_ad = (uint32_t)emit_lines(emit) * P.gpl_ad;
+        P.gmagic = (uint32_t)((0x100000000ull + P.gpf_ad - 1) / P.gpf_ad);
+        P.sfx0 = emit == GG_EMIT_RR ? 2 : 0;
+    }
+    P.E = (F + 1) / 2;
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();
@@ -959,16 +966,19 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.sm = sm;
 
     int bps = 0;
-    CK(fused_prepare(fast_boundary, dmode, warps * 32, sm.total, &bps, &regs));
+    CK(fused_prepare(fast_boundary, dmode, emitc, warps * 32, sm.total, &bps, &regs));
     if (bps < 1) return ctx->fail(GG_ERR_CUDA, "gg_run_fused: kernel does not fit on an SM");
     bps = std::min(bps, ctas);
     const uint64_t want_ctas = (n_tiles64 + (uint64_t)warps - 1) / (uint64_t)warps;
     const int grid = (int)std::min<uint64_t>(want_ctas, (uint64_t)bps * (uint64_t)ctx->sm_count);
 
+    if (getenv("GG_FUSED_DEBUG"))
+        fprintf(stderr, "[gg_run_fused] variant fast=%d dmode=%d emitc=%d regs=%d | F=%d E=%d warps=%d ctas/SM=%d grid=%d | smem/warp=%d B (stage %d) tables=%d B total=%d B\n",
+                fast_boundary, dmode, emitc, regs, F, P.E, warps, bps, grid, sm.warp_bytes, sm.stage_bytes, sm.warp0, sm.total);
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles * 8, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
-    CK(launch_fused(P, grid, warps * 32, ctx->st));
+    CK(launch_fused(P, emitc, grid, warps * 32, ctx->st));
     unsigned long long stats[ST_N];
     { int rcp = fetch_small(ctx, P.stats, stats, ST_N, ctx->ev1); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

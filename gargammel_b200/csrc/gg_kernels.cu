@@ -366,21 +366,27 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // One warp owns one tile of up to 32 fragments from sampling to the global store; warps never wait for each other
-// (no CTA barrier inside the loop).  Byte offsets come from a decoupled look-back over per-warp-tile states.
+// (no CTA barrier inside the loop).  Byte offsets come from a decoupled look-back over per-warp-tile states.  Sampling, gather,
+// damage events and line images work on the whole tile (a lane per fragment / per 16-base chunk); the records are then rendered and
+// stored in two halves of up to 16 fragments, so that the staging buffer -- the largest piece of a warp's shared memory -- holds
+// half a tile and 32 warps fit on an SM.
 //
 // FASTB: every header is >= 13 bytes, so a partial 16-byte group of one sequence line can never reach another line's
 // sequence bytes: groups are stored whole and the headers/newlines are written afterwards (no read-modify-write).
 // DMODE: 1 = every damage slot of the plan is a -matfile matrix (tables in shared memory), 2 = every slot is Briggs, 0 = any mix.
-template <bool FASTB, int DMODE>
+// EMITC: 0 = fragSim / deamSim records (sequence line = the fragment), 1 = the one-line adptSim dialects (-arts, -artp, -fr, -rr),
+//        2 = adptSim's default four-line output.
+template <bool FASTB, int DMODE, int EMITC>
 __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constant__ FusedParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint16_t s_d100[100];                // "00".."99" for the decimal fields of the deflines
     __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int emit = P.emit, RL = P.ad.read_len;
-    const int nlines = emit_lines(emit);
-    const int sfx0 = emit_suffix(emit, 0), sfx1 = emit_suffix(emit, 1);     // "_r" on line 0 / line 1
+    const int emit = P.emit;
+    constexpr int NLINES = EMITC == 2 ? 2 : 1;
+    const int sfx0 = EMITC == 1 ? P.sfx0 : 0;                              // "_r" on the only line of -rr ...
+    constexpr int sfx1 = 2;                                                 // ... and on the second line of the default output (adptSim.cpp:286)
 
     for (int v = tid; v < 100; v += blockDim.x) s_d100[v] = (uint16_t)(('0' + v / 10) | (('0' + v % 10) << 8));
     const uint4* const s_thr = (const uint4*)(smem + P.sm.thr);
@@ -434,10 +440,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint8_t*  const wb       = smem + P.sm.warp0 + (size_t)warp * P.sm.warp_bytes;
     uint8_t*  const s_stage  = wb + P.sm.stage;
     uint64_t* const s_gpos   = (uint64_t*)(wb + P.sm.gpos);
-    uint64_t* const s_idx    = (uint64_t*)(wb + P.sm.idx);
+    uint32_t* const s_idx    = (uint32_t*)(wb + P.sm.idx);      // start coordinate within the contig (contigs are shorter than 2^32)
     unsigned long long* const s_bh = (unsigned long long*)(wb + P.sm.bh);
     uint32_t* const s_meta   = (uint32_t*)(wb + P.sm.meta);
-    uint32_t* const s_so     = (uint32_t*)(wb + P.sm.so);       // staging offset (without the tile's pad) of the first sequence byte of line 0
+    uint32_t* const s_so     = (uint32_t*)(wb + P.sm.so);       // offset within the tile's bytes of the first sequence byte of line 0
     uint32_t* const s_ci     = (uint32_t*)(wb + P.sm.ci);
     uint16_t* const s_hdr    = (uint16_t*)(wb + P.sm.hdr);
     uint16_t* const s_nd     = (uint16_t*)(wb + P.sm.nd);       // digit counts of start | end << 4 | length << 8
@@ -449,17 +455,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint8_t*  const s_cmap   = wb + P.sm.cmap;
     uint8_t*  const s_gmap   = wb + P.sm.gmap;
 
-    unsigned long long my_attempts = 0, my_gather = 0;
-    uint32_t my_err = 0;
-    const int S_ad = emit == 4 ? 2 * RL : RL;                       // sequence-line length of the adptSim dialects
-    const int LWL = ((S_ad + 15) >> 4) + 2;                          // words per line image: guard + data + read slack
-    const uint32_t gpl_ad = (uint32_t)((S_ad + 15) >> 4) + 1u, gpf_ad = (uint32_t)nlines * gpl_ad;   // staging groups per line / per fragment (adptSim dialects: the same for every fragment)
+    uint32_t my_attempts = 0, my_gather = 0, my_err = 0;
 
-    while (true) {
-        int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= P.n_tiles) break;
+    int tile = 0;
+    if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < P.n_tiles) {
+        int next_tile = 0;
+        if (lane == 0) next_tile = (int)atomicAdd(P.ticket, 1u);       // the next ticket is taken now and read at the end of this tile
         const uint64_t tile_first = (uint64_t)tile * (uint64_t)P.F;
         const int nf = (int)min((uint64_t)P.F, P.count - tile_first);
 
@@ -548,22 +551,22 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(sp));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + ((L + 15) >> 4)));
             }
-            my_gather += (unsigned long long)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
+            my_gather += (uint32_t)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
             const int nlen = t_nlen[ci];
             const int n1 = ndigits(idx), n2 = ndigits(idx + (uint64_t)L), n3 = ndigits((uint64_t)L);
             hdr = 1 + nlen + 3 + n1 + 1 + n2 + 1 + n3 + tag_len;
-            const int S = emit_seqlen(emit, L, RL);
+            const int S = EMITC ? P.S_ad : L;
             uint32_t bytes = 0;
-            for (int ln = 0; ln < nlines; ln++) bytes += hdr + (ln ? sfx1 : sfx0) + 1 + S + 1;
+            for (int ln = 0; ln < NLINES; ln++) bytes += hdr + (ln ? sfx1 : sfx0) + 1 + S + 1;
             const uint32_t chunks = (L + 15) >> 4;
-            const uint32_t groups = nlines * (((S + 15) >> 4) + 1);
+            const uint32_t groups = EMITC ? P.gpf_ad : (uint32_t)((S + 15) >> 4) + 1u;
             pk = PK(bytes, chunks, groups);
             s_gpos[lane] = gpos;
             s_meta[lane] = META(L, plus, rg->slot, rg->genome);
             s_hdr[lane] = (uint16_t)hdr;
             s_nd[lane] = (uint16_t)(n1 | (n2 << 4) | (n3 << 8));
-            s_idx[lane] = idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
+            s_idx[lane] = (uint32_t)idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
             if (DMODE == 0 && emit != 0 && rg->slot >= 0 && P.dmg[rg->slot].mode == 5) {   // -damagess (drawn per base in pass C): the two overhangs, once per fragment (deamSim.cpp:1342-1343)
                 const BriggsHdr B = dmg_briggs_hdr(P.dmg[rg->slot], rng_block(P.key, id, 0u, ST_DEAM));
                 s_bh[lane] = (unsigned long long)(uint32_t)B.o5 | ((unsigned long long)(uint32_t)B.o3 << 32);
@@ -573,11 +576,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         const unsigned long long incl = warp_scan_u64(pk, lane);
         const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
         const unsigned long long excl = incl - pk;
-        const uint32_t T = PK_BYTES(tot), n_chunks = PK_CHUNKS(tot), n_groups = PK_GROUPS(tot);
-        const bool overflow = T > (uint32_t)P.sm.stage_bytes;    // host sizing bug guard: never write past staging
+        const uint32_t T = PK_BYTES(tot), n_chunks = PK_CHUNKS(tot);
+        const uint32_t roff = PK_BYTES(excl);                    // byte offset of this lane's record within the tile
         if (lane == 0) {   // publish this tile's byte count for the look-back
             st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
-            if (overflow) my_err |= ERRF_OVERFLOW;
 #if GG_BULK_COPY
             bulk_wait_read();                                    // the previous tile's bulk copy has read its staging bytes (pass A gave it time)
 #endif
@@ -585,18 +587,21 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass B1: work maps (owner lane)
-        if (lane < nf && !overflow) {
-            const uint32_t roff = PK_BYTES(excl), c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
+        if (lane < nf) {
+            const uint32_t c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
             s_so[lane] = roff + (uint32_t)s_hdr[lane] + (uint32_t)sfx0 + 1u; s_cstart[lane] = (uint16_t)c0;
             const uint32_t nch = PK_CHUNKS(pk);
 #pragma unroll 1
             for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)lane;
-            if (emit <= 1) {                                     // the adptSim dialects have the same number of groups for every fragment: no map
+            if (EMITC == 0) {                                    // the adptSim dialects have the same number of groups for every fragment: no map
                 const uint32_t ngr = PK_GROUPS(pk);
-                s_gstart[lane] = (uint16_t)g0;
 #pragma unroll 1
                 for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)lane;
             }
+        }
+        if (EMITC == 0) {                                        // group slot of every fragment's first group (lanes past the tile and the sentinel hold the total)
+            s_gstart[lane] = (uint16_t)PK_GROUPS(excl);
+            if (lane == 31) s_gstart[32] = (uint16_t)PK_GROUPS(tot);
         }
         // first look-back probe, issued now and consumed after the damage pass (its latency overlaps pass C)
         unsigned long long lb = 2ull << 62;
@@ -604,7 +609,6 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass C: gather (lane per 16-base chunk)
-        if (!overflow)
         for (uint32_t e = lane; e < n_chunks; e += 32) {
             const int f = s_cmap[e];
             const int k = (int)e - (int)s_cstart[f];
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass E: damage events (lane per fragment; deamSim.cpp:1477-1613,1794-1930)
-        if (emit != 0 && lane < nf && !overflow) {
+        if (emit != 0 && lane < nf) {
             const uint32_t meta = s_meta[lane];
             const int slot = META_SLOT(meta);
             if (slot >= 0) {
@@ -644,14 +648,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass C2: line images (owner lane; adptSim dialects only)
-        if (emit >= 2 && lane < nf && !overflow) {
+        if (EMITC != 0 && lane < nf) {
             const int L = META_L(s_meta[lane]);
             const uint64_t id = P.first + tile_first + (uint64_t)lane;
             const uint32_t* D = s_dwords + s_cstart[lane];
-            uint32_t* lw = s_lwords + lane * (nlines * LWL);
+            uint32_t* lw = s_lwords + lane * P.lw_stride;
             // -rr: reverse read; -artp: forward ++ revcomp(reverse); otherwise the forward read (first line)
             build_line_image(P, adsm, D, L, id, emit == 6 ? 1 : emit == 4 ? 2 : 0, lw + 1);
-            if (emit == 2) build_line_image(P, adsm, D, L, id, 1, lw + LWL + 1);     // default 4-line output: second line = reverse read
+            if (EMITC == 2) build_line_image(P, adsm, D, L, id, 1, lw + P.LWL + 1);     // default 4-line output: second line = reverse read
         }
 
         // ------------------------------------------------------------ look-back: global byte offset of this tile
@@ -671,128 +675,155 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             if (lane == 0) st_volatile_u64(P.tile_state + tile, (2ull << 62) | (gofs + (unsigned long long)T));
         }
         if (lane == 0 && tile == P.n_tiles - 1) P.stats[ST_TOTAL] = gofs + (unsigned long long)T;
-        const int pad = (int)((uintptr_t)(P.out + gofs) & 15);          // the tile is staged with its global misalignment
+        const bool fits = gofs + T <= P.out_cap;                         // host sizing guard: never write past the output
+        if (!fits) my_err |= ERRF_OVERFLOW;
         __syncwarp();
 
-        // ------------------------------------------------------------ pass B2 (before D unless FASTB): headers + newlines (owner lane)
-        auto write_headers = [&]() {
-            if (lane < nf && !overflow) {
-                const uint32_t meta = s_meta[lane];
-                const int L = META_L(meta); const uint32_t plus = META_PLUS(meta);
-                const uint64_t idx = s_idx[lane]; const int ci = (int)s_ci[lane];
-                const RangeDev* rg = t_ranges + s_rg[lane];
-                const char* tag = rg->tag; const int tag_len = rg->tag_len;
-                const int S = emit_seqlen(emit, L, RL);
-                const char* nm = t_names + t_noff[ci];
-                const int nlen = t_nlen[ci];
-                const uint32_t nd = s_nd[lane];
-                const int n1 = (int)(nd & 15u), n2 = (int)((nd >> 4) & 15u), n3 = (int)(nd >> 8);
-                const uint64_t iend = idx + (uint64_t)L;
-                uint8_t* p = s_stage + pad + (int)s_so[lane] - (int)s_hdr[lane] - sfx0 - 1;      // first byte of the record
-                for (int ln = 0; ln < nlines; ln++) {
-                    // ">chr:+:start:end:len" + tag   (fragSim.cpp:1489,1498,1505-1507,1603)
-                    *p++ = '>';
-#pragma unroll 1
-                    for (int k = 0; k < nlen; k++) p[k] = (uint8_t)nm[k];
-                    p += nlen;
-                    p[0] = ':'; p[1] = plus ? '+' : '-'; p[2] = ':'; p += 3;
-                    if (iend <= 0xFFFFFFFFull) { put_dec32(p, (uint32_t)idx, n1, s_d100); p[n1] = ':'; p += n1 + 1; put_dec32(p, (uint32_t)iend, n2, s_d100); p[n2] = ':'; p += n2 + 1; }
-                    else { p = put_decimal(p, idx, n1, s_d100); *p++ = ':'; p = put_decimal(p, iend, n2, s_d100); *p++ = ':'; }
-                    put_dec32(p, (uint32_t)L, n3, s_d100); p += n3;
-#pragma unroll 1
-                    for (int k = 0; k < tag_len; k++) p[k] = (uint8_t)tag[k];
-                    p += tag_len;
-                    if (ln ? sfx1 : sfx0) { p[0] = '_'; p[1] = 'r'; p += 2; }
-                    p[0] = '\n'; p[S + 1] = '\n';
-                    p += S + 2;
-                }
-            }
-        };
-        if (!FASTB) { write_headers(); __syncwarp(); }
+        // ------------------------------------------------------------ emission in halves of up to P.E fragments
+        for (int f0 = 0; f0 < nf; f0 += P.E) {
+            const int f1 = min(nf, f0 + P.E);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, roff, f0);                              // bytes [b0, b1) of the tile
+            const uint32_t b1x = __shfl_sync(0xffffffffu, roff, f1 & 31);
+            const uint32_t b1 = f1 < nf ? b1x : T;
+            const uint32_t TB = b1 - b0;
+            const int pad = (int)((uintptr_t)(P.out + gofs + b0) & 15);                           // the half is staged with its global misalignment
+            const int pofs = pad - (int)b0;                                                     // staging offset = pofs + offset within the tile
+            const bool ok = fits && TB <= (uint32_t)P.sm.stage_bytes;                           // host sizing guard: never write past staging
+            if (!ok) my_err |= ERRF_OVERFLOW;
 
-        // ------------------------------------------------------------ pass D: ASCII (lane per 16-byte staging group)
-        if (!overflow)
-        for (uint32_t e = lane; e < n_groups; e += 32) {
-            int f, g;
-            if (emit >= 2) { f = (int)__umulhi(e, P.gmagic); g = (int)(e - (uint32_t)f * gpf_ad); }   // e / groups-per-fragment by a host-made reciprocal
-            else { f = s_gmap[e]; g = (int)e - (int)s_gstart[f]; }
-            int S = S_ad, gpl = (int)gpl_ad;
-            if (emit <= 1) { S = META_L(s_meta[f]); gpl = ((S + 15) >> 4) + 1; }
-            int ls = pad + (int)s_so[f];                           // staging offset of the first sequence byte of this line
-            int line = 0;
-            if (nlines == 2 && g >= gpl) { line = 1; g -= gpl; ls += (int)s_hdr[f] + sfx1 + S + 2; }
-            const int sigma = ls & 15;
-            const int j0 = 16 * g - sigma;
-            const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
-            if (jhi <= jlo) continue;
-            const uint32_t* src = emit <= 1 ? s_dwords + s_cstart[f] : s_lwords + f * (nlines * LWL) + line * LWL + 1;
-            const uint4 a = codes16_to_ascii(fetch_run_smem(src, j0));
-            uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
-            if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
-                *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
-            } else {
-                // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
-                // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
-                const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
-                const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
-                uint32_t* d4 = (uint32_t*)dst;
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            // ---- headers + newlines: two lanes per fragment (lane 2k: ">name:strand:start:", lane 2k+1: "end:len" tag "\n" ... "\n")
+            auto write_headers = [&]() {
+                const int fh = f0 + (lane >> 1), part = lane & 1;
+                if (fh < f1 && ok) {
+                    const uint32_t meta = s_meta[fh];
+                    const int L = META_L(meta);
+                    const int hdr = (int)s_hdr[fh];
+                    const uint32_t nd = s_nd[fh];
+                    const int n1 = (int)(nd & 15u), n2 = (int)((nd >> 4) & 15u), n3 = (int)(nd >> 8);
+                    const int S = EMITC ? P.S_ad : L;
+                    uint8_t* rec = s_stage + pofs + (int)s_so[fh] - hdr - sfx0 - 1;             // first byte of the record
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const uint32_t nib = (V >> (4 * w)) & 0xFu;
-                    const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
-                    if (nib == 0xFu) d4[w] = aw[w];
-                    else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                    for (int ln = 0; ln < NLINES; ln++) {
+                        const int sfx = ln ? sfx1 : sfx0;
+                        if (part == 0) {                        // ">chr:+:start:"   (fragSim.cpp:1489,1498,1603)
+                            const int ci = (int)s_ci[fh];
+                            const char* nm = t_names + t_noff[ci];
+                            const int nlen = t_nlen[ci];
+                            uint8_t* p = rec;
+                            *p++ = '>';
+#pragma unroll 1
+                            for (int k = 0; k < nlen; k++) p[k] = (uint8_t)nm[k];
+                            p += nlen;
+                            p[0] = ':'; p[1] = META_PLUS(meta) ? '+' : '-'; p[2] = ':';
+                            put_dec32(p + 3, s_idx[fh], n1, s_d100); p[3 + n1] = ':';
+                        } else {                                // "end:len" + tag (no separator, fragSim.cpp:1505-1507) [+ "_r"] + "\n", and the newline behind the sequence
+                            const RangeDev* rg = t_ranges + s_rg[fh];
+                            const char* tag = rg->tag; const int tag_len = rg->tag_len;
+                            const uint64_t iend = (uint64_t)s_idx[fh] + (uint64_t)L;
+                            uint8_t* p = rec + (hdr - tag_len - n3 - 1 - n2);
+                            if (iend <= 0xFFFFFFFFull) put_dec32(p, (uint32_t)iend, n2, s_d100); else put_decimal(p, iend, n2, s_d100);
+                            p[n2] = ':'; p += n2 + 1;
+                            put_dec32(p, (uint32_t)L, n3, s_d100); p += n3;
+#pragma unroll 1
+                            for (int k = 0; k < tag_len; k++) p[k] = (uint8_t)tag[k];
+                            p += tag_len;
+                            if (sfx) { p[0] = '_'; p[1] = 'r'; p += 2; }
+                            p[0] = '\n'; p[S + 1] = '\n';
+                        }
+                        rec += hdr + sfx + 1 + S + 1;
+                    }
+                }
+            };
+            if (!FASTB) { write_headers(); __syncwarp(); }
+
+            // ---- ASCII: lane per 16-byte staging group
+            uint32_t e0, e1;                                     // group slots of fragments [f0, f1)
+            if (EMITC) { e0 = (uint32_t)f0 * P.gpf_ad; e1 = (uint32_t)f1 * P.gpf_ad; }
+            else { e0 = s_gstart[f0]; e1 = s_gstart[f1]; }
+            if (ok)
+            for (uint32_t e = e0 + lane; e < e1; e += 32) {
+                int f, g;
+                if (EMITC) { f = (int)__umulhi(e, P.gmagic); g = (int)(e - (uint32_t)f * P.gpf_ad); }   // e / groups-per-fragment by a host-made reciprocal
+                else { f = s_gmap[e]; g = (int)e - (int)s_gstart[f]; }
+                int S = P.S_ad;
+                if (EMITC == 0) S = META_L(s_meta[f]);
+                int ls = pofs + (int)s_so[f];                       // staging offset of the first sequence byte of this line
+                int line = 0;
+                if (EMITC == 2 && g >= (int)P.gpl_ad) { line = 1; g -= (int)P.gpl_ad; ls += (int)s_hdr[f] + sfx1 + S + 2; }
+                const int sigma = ls & 15;
+                const int j0 = 16 * g - sigma;
+                const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
+                if (jhi <= jlo) continue;
+                const uint32_t* src = EMITC == 0 ? s_dwords + s_cstart[f] : s_lwords + f * P.lw_stride + line * P.LWL + 1;
+                const uint4 a = codes16_to_ascii(fetch_run_smem(src, j0));
+                uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
+                if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
+                    *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
+                } else {
+                    // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
+                    // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
+                    const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
+                    const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
+                    uint32_t* d4 = (uint32_t*)dst;
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const uint32_t nib = (V >> (4 * w)) & 0xFu;
+                        const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
+                        if (nib == 0xFu) d4[w] = aw[w];
+                        else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                    }
                 }
             }
-        }
-        __syncwarp();
-        if (FASTB) { write_headers(); __syncwarp(); }
+            __syncwarp();
+            if (FASTB) { write_headers(); __syncwarp(); }
 
-        // ------------------------------------------------------------ copy-out: staging -> global
-        if (!overflow) {
-            if (gofs + T > P.out_cap) { my_err |= ERRF_OVERFLOW; }
-            else {
-                uint8_t* const gal = P.out + gofs - pad;                 // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+T)
-                const int end = pad + (int)T;
+            // ---- copy-out: staging -> global
+            if (ok) {
+                uint8_t* const gal = P.out + gofs + b0 - pad;            // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+TB)
+                const int end = pad + (int)TB;
                 const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
 #if GG_BULK_COPY
-                fence_async_smem();                                      // this lane's staging writes -> visible to the bulk-copy engine
-                __syncwarp();
-                if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
-#else
-                for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
+                if (f1 == nf) {                                          // the tile's last half goes out through the bulk-copy engine: its staging is not needed before the next tile's emission
+                    fence_async_smem();                                  // this lane's staging writes -> visible to the bulk-copy engine
+                    __syncwarp();
+                    if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
+                } else
 #endif
+                for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
                 // the partial head [pad, 16 c_lo) and tail [16 max(c_hi, c_lo), end): at most 15 bytes each, one byte per lane
                 const int t = lane < 16 ? pad + lane : 16 * max(c_hi, c_lo) + (lane - 16);
                 if (lane < 16 ? t < min(16 * c_lo, end) : t < end) gal[t] = s_stage[t];
             }
+            __syncwarp();
         }
-        __syncwarp();
+        tile = __shfl_sync(0xffffffffu, next_tile, 0);
     }
 #if GG_BULK_COPY
     if (lane == 0) bulk_wait_all();
 #endif
 
     // per-warp statistics
-    my_attempts = warp_sum_u64(my_attempts); my_gather = warp_sum_u64(my_gather);
+    unsigned long long a64 = warp_sum_u64((unsigned long long)my_attempts), g64 = warp_sum_u64((unsigned long long)my_gather);
     uint32_t e = my_err;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e |= __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 0) {
-        if (my_attempts) atomicAdd(P.stats + ST_ATTEMPTS, my_attempts);
-        if (my_gather) atomicAdd(P.stats + ST_GATHER, my_gather);
+        if (a64) atomicAdd(P.stats + ST_ATTEMPTS, a64);
+        if (g64) atomicAdd(P.stats + ST_GATHER, g64);
         if (e) atomicOr(P.stats + ST_ERR, (unsigned long long)e);
     }
 }
 
 typedef void (*fused_fn)(const FusedParams);
-static fused_fn fused_variant(int fast, int dmode) {
-    if (fast) return dmode == 1 ? k_fused<true, 1> : dmode == 2 ? k_fused<true, 2> : k_fused<true, 0>;
-    return dmode == 1 ? k_fused<false, 1> : dmode == 2 ? k_fused<false, 2> : k_fused<false, 0>;
+static fused_fn fused_variant(int fast, int dmode, int emitc) {
+#define GG_V(F, D) (emitc == 0 ? k_fused<F, D, 0> : emitc == 1 ? k_fused<F, D, 1> : k_fused<F, D, 2>)
+    if (fast) return dmode == 1 ? GG_V(true, 1) : dmode == 2 ? GG_V(true, 2) : GG_V(true, 0);
+    return GG_V(false, 0);                           // short headers (rare): only the general damage variant is built
+#undef GG_V
 }
-cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs) {
-    fused_fn f = fused_variant(fast, dmode);
+cudaError_t fused_prepare(int fast, int dmode, int emitc, int threads, int smem_bytes, int* blocks_per_sm, int* regs) {
+    fused_fn f = fused_variant(fast, dmode, emitc);
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes a; e = cudaFuncGetAttributes(&a, f);
@@ -800,8 +831,8 @@ cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int*
     *regs = a.numRegs;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, threads, smem_bytes);
 }
-cudaError_t launch_fused(const FusedParams& P, int grid, int threads, cudaStream_t st) {
-    fused_variant(P.fast_boundary, P.dmode)<<<grid, threads, P.sm.total, st>>>(P);
+cudaError_t launch_fused(const FusedParams& P, int emitc, int grid, int threads, cudaStream_t st) {
+    fused_variant(P.fast_boundary, P.dmode, emitc)<<<grid, threads, P.sm.total, st>>>(P);
     return cudaGetLastError();
 }
 

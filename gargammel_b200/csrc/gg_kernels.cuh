@@ -75,7 +75,13 @@ struct FusedParams {
     int norev;
     int fast_boundary;       // every header >= 13 bytes: whole-group stores, headers written afterwards
     int dmode;               // 1: every damage slot used by the plan is a matrix (specialised kernel), 2: every slot is Briggs, 0: any mix
-    uint32_t gmagic;         // ceil(2^32 / staging groups per fragment) of the adptSim dialects: group index -> fragment by one multiply
+    // constants of the adptSim dialects (every fragment has the same sequence-line length there)
+    int S_ad;                // bases per sequence line: read length, or twice that for -artp
+    int LWL, lw_stride;      // words per packed line image (guard + data + slack), words per fragment (lines x LWL)
+    uint32_t gpl_ad, gpf_ad; // 16-byte staging groups per line / per fragment
+    uint32_t gmagic;         // ceil(2^32 / gpf_ad): group index -> fragment by one multiply
+    int sfx0;                // 2 when the only line carries "_r" (-rr), else 0
+    int E;                   // fragments per emission half (the staging buffer holds E records)
     ggd::Key key;
     // plan + genomes
     const RangeDev* ranges; int n_ranges;
@@ -99,7 +105,7 @@ struct FusedParams {
 };
 
 #ifndef GG_FUSED_MAXT
-#define GG_FUSED_MAXT 640      // launch bound of k_fused: 20 warps, 96 registers
+#define GG_FUSED_MAXT 1024     // launch bound of k_fused: 32 warps, 64 registers
 #endif
 enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
 enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
@@ -132,8 +138,8 @@ cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t*
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
 cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, ggd::Key key,
                             unsigned long long* sums /* [0]=sum gc, [1]=sum gc^2, [2]=give-ups */, cudaStream_t st);
-cudaError_t launch_fused(const FusedParams& P, int grid, int threads, cudaStream_t st);
-cudaError_t fused_prepare(int fast, int dmode, int threads, int smem_bytes, int* blocks_per_sm, int* regs);
+cudaError_t launch_fused(const FusedParams& P, int emitc, int grid, int threads, cudaStream_t st);
+cudaError_t fused_prepare(int fast, int dmode, int emitc, int threads, int smem_bytes, int* blocks_per_sm, int* regs);
 
 // stand-alone record-stream kernels
 struct RecStream {
