@@ -47,9 +47,9 @@ struct HostGenome {
 struct HostDamage {
     int mode, rows5, rows3, clamp_last;
     int n5t, n3t;                                  // matrix: terminal rows drawn per base (draw specification v2)
-    std::vector<uint4> term, acc; std::vector<uint32_t> sd5, sd3, geoL, geoV, geoA, geoB; uint32_t Ks, Kd, K3;
+    std::vector<uint4> term, acc; std::vector<uint32_t> sd5, sd3, geoL, geoV, geoA, geoB; std::vector<uint8_t> guideA, guideB; uint32_t Ks, Kd, K3;
     double pL, pV, pA, pB;                         // parameters of the geometric tables geoL/geoV and geoA (matrix: majorant M; Briggs: s) / geoB (Briggs: d)
-    DBuf d_term, d_acc, d_sd5, d_sd3, d_geoL, d_geoV, d_geoA, d_geoB;
+    DBuf d_term, d_acc, d_sd5, d_sd3, d_geoL, d_geoV, d_geoA, d_geoB, d_guideA, d_guideB;
     HostDamage() : mode(GG_DMG_NONE), rows5(0), rows3(0), clamp_last(1), n5t(0), n3t(0), Ks(0), Kd(0), K3(0), pL(0), pV(0), pA(0), pB(0) {}
 };
 const int NT_MAX = 8;                // at most this many terminal rows per end are drawn per base
@@ -80,6 +80,16 @@ void geo_table(double p, int n, std::vector<uint32_t>& t) {
     t.resize(n);
     double q = 1.0; uint32_t prev = 0;
     for (int k = 0; k < n; k++) { q *= (1.0 - p); uint32_t v = thr_le(1.0 - q); if (v < prev) v = prev; t[k] = v; prev = v; }
+}
+// 512-entry guide of such a table: guide[c] = first k with (c << 22) < t[k], capped at 255 (the device scans upwards from there)
+void geo_guide(const std::vector<uint32_t>& t, std::vector<uint8_t>& g) {
+    g.resize(512);
+    size_t k = 0;
+    for (uint32_t c = 0; c < 512; c++) {
+        const uint32_t lo = c << 22;
+        while (k < t.size() && lo >= t[k]) k++;
+        g[c] = (uint8_t)std::min<size_t>(k, 255);
+    }
 }
 
 } // namespace
@@ -243,12 +253,12 @@ void fill_damage_dev(const HostDamage& H, ggd::DamageDev* D) {
     D->sd5 = H.d_sd5.as<uint32_t>(); D->sd3 = H.d_sd3.as<uint32_t>();
     D->Ks = H.Ks; D->Kd = H.Kd; D->geoL = H.d_geoL.as<uint32_t>(); D->geoV = H.d_geoV.as<uint32_t>(); D->n_geo = GEO_TABLE;
     D->geoM = H.d_geoA.as<uint32_t>(); D->geoS = H.d_geoA.as<uint32_t>(); D->geoD = H.d_geoB.as<uint32_t>();
+    D->guideA = H.d_guideA.as<uint8_t>(); D->guideB = H.d_guideB.as<uint8_t>();
     // -damagess keeps its 3' overhang table where plain Briggs keeps the nick table
     D->K3 = H.mode == GG_DMG_BRIGGS_SS ? H.K3 : H.Ks; D->geoL3 = H.mode == GG_DMG_BRIGGS_SS ? D->geoV : D->geoL;
     auto inv_log = [](double p) { return p <= 0.0 ? -INFINITY : p >= 1.0 ? -0.0f : (float)(1.0 / log(1.0 - p)); };   // p = 0: never a success (k = n); p = 1: always k = 0
     D->inv_logL = inv_log(H.pL); D->inv_logV = inv_log(H.pV);
     D->inv_logL3 = H.mode == GG_DMG_BRIGGS_SS ? D->inv_logV : D->inv_logL;
-    D->inv_logM = D->inv_logS = inv_log(H.pA); D->inv_logD = inv_log(H.pB);
 }
 
 int digits10(uint64_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
@@ -304,15 +314,10 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
 SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords,
                        int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false,
                        int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
-    SmemLayout s; int o = 0;
+    SmemLayout s; int o = align_up(fused_desc_bytes(), 16);   // fixed-layout per-fragment descriptors (WarpDesc, gg_kernels.cu)
     o += 16;                                   // readable slack before staging
     s.stage = o; s.stage_bytes = (int)((uint64_t)((F + 1) / 2) * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // half a tile (+ misalignment pad (<16) + read slack)
-    s.gpos = o; o += 8 * F;
     s.bh = o; o += 8 * F;
-    s.idx = o; o += 4 * F;
-    s.meta = o; o += 4 * F;
-    s.so = o; o += 4 * F;
-    s.ci = o; o += 4 * F;
     if (alias_dwords && s.stage_bytes >= 4 * (F * max_chunks + 4)) {
         s.dwords = s.stage;                    // adptSim dialects: the damaged words are dead once the line images exist, before staging is written
     } else {
@@ -320,21 +325,16 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
         s.dwords = o; o += 4 * (F * max_chunks + 4);
     }
     s.lwords = o; o += 4 * (F * line_words + 4);
-    s.hdr = o; o += 2 * F;
-    s.nd = o; o += 2 * F;
-    s.cstart = o; o += 2 * F;
-    s.gstart = o; o += 2 * F + 4;
-    s.rg = o; o += 2 * F;
     s.cmap = o; o += F * max_chunks;
     s.gmap = o; o += F * max_groups;           // (only the fragSim / deamSim dialects use the group map)
     s.warp_bytes = align_up(o, 16);
     s.thr = 0; s.thr_bytes = thr_bytes; s.warp0 = align_up(thr_bytes, 16);
     s.tab = -1; s.tab_bytes = 0; s.n_contigs = tab_contigs; s.names_bytes = tab_names;
-    s.tab_ranges = s.tab_genomes = s.tab_cum = s.tab_gbase = s.tab_len = s.tab_noff = s.tab_nlen = s.tab_names = 0;
+    s.tab_ranges = s.tab_genomes = s.tab_cum = s.tab_gbase = s.tab_name8 = s.tab_len = s.tab_noff = s.tab_nlen = s.tab_names = 0;
     s.tab_sthr = s.tab_slen = s.n_sizes_sm = 0; for (int k = 0; k < 3; k++) { s.tab_ad[k] = 0; s.ad_words[k] = 0; }
     if (tab_on) {                              // small plan / genome / contig tables, CTA-shared
         int t = 0;
-        s.tab_cum = t; t += 8 * tab_contigs; s.tab_gbase = t; t += 8 * tab_contigs;
+        s.tab_cum = t; t += 8 * tab_contigs; s.tab_gbase = t; t += 8 * tab_contigs; s.tab_name8 = t; t += 8 * tab_contigs;
         s.tab_ranges = t; t += (int)sizeof(RangeDev) * tab_ranges; s.tab_genomes = t; t += (int)sizeof(GenomeDev) * tab_genomes;
         s.tab_len = t; t += 4 * tab_contigs; s.tab_noff = t; t += 4 * tab_contigs; s.tab_nlen = t; t += align_up(2 * tab_contigs, 4);
         s.tab_names = t; t += tab_names; t = align_up(t, 4);
@@ -395,7 +395,7 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
     for (int s = 0; s < GG_MAX_GC_SLOTS; s++) ctx->gc[s].d_thr.release();
     for (int s = 0; s < GG_MAX_DAMAGE_SLOTS; s++) {
-        ctx->dmg[s].d_term.release(); ctx->dmg[s].d_acc.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release(); ctx->dmg[s].d_geoA.release(); ctx->dmg[s].d_geoB.release();
+        ctx->dmg[s].d_term.release(); ctx->dmg[s].d_acc.release(); ctx->dmg[s].d_sd5.release(); ctx->dmg[s].d_sd3.release(); ctx->dmg[s].d_geoL.release(); ctx->dmg[s].d_geoV.release(); ctx->dmg[s].d_geoA.release(); ctx->dmg[s].d_geoB.release(); ctx->dmg[s].d_guideA.release(); ctx->dmg[s].d_guideB.release();
     }
     for (size_t i = 0; i < ctx->pool.size(); i++) cudaFree(ctx->pool[i].first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -657,9 +657,10 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
             }
         }
     }
-    geo_table(M, GEO_TABLE, H.geoA);
+    geo_table(M, GEO_TABLE, H.geoA); geo_guide(H.geoA, H.guideA);
     if ((rc = upload_vec(ctx, H.d_term, H.term))) return rc;
     if ((rc = upload_vec(ctx, H.d_acc, H.acc))) return rc;
+    if ((rc = upload_vec(ctx, H.d_guideA, H.guideA))) return rc;
     return upload_vec(ctx, H.d_geoA, H.geoA);
 }
 
@@ -692,7 +693,10 @@ int gg_tables_set_briggs(gg_ctx* ctx, int slot, double v, double l, double d, do
     // overhang lengths (l), nick position (v), and the geometric skips of the event draws over the single-stranded (s) and
     // double-stranded (d) positions (draw specification v2)
     geo_table(l, GEO_TABLE, H.geoL); geo_table(v, GEO_TABLE, H.geoV); geo_table(s, GEO_TABLE, H.geoA); geo_table(d, GEO_TABLE, H.geoB);
+    geo_guide(H.geoA, H.guideA); geo_guide(H.geoB, H.guideB);
     int rc;
+    if ((rc = upload_vec(ctx, H.d_guideA, H.guideA))) return rc;
+    if ((rc = upload_vec(ctx, H.d_guideB, H.guideB))) return rc;
     if ((rc = upload_vec(ctx, H.d_geoL, H.geoL))) return rc;
     if ((rc = upload_vec(ctx, H.d_geoV, H.geoV))) return rc;
     if ((rc = upload_vec(ctx, H.d_geoA, H.geoA))) return rc;
@@ -943,7 +947,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
         P.gmagic = (uint32_t)((0x100000000ull + P.gpf_ad - 1) / P.gpf_ad);
         P.sfx0 = emit == GG_EMIT_RR ? 2 : 0;
     }
-    P.E = (F + 1) / 2;
+    P.E = (F + 1) / 2; P.lut = 0x54474341u;
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();

@@ -85,17 +85,18 @@ struct DamageDev {
     //     "unchanged" with -last), then the 3' block REVERSED: its sentinel, then distance rows3-1 .. 0, so that the row of position i
     //     on the 3' side is max(i + rows5+rows3+2-L, rows5+1).
     //   geoM: geometric skips under the majorant M (inverse CDF, like geoL/geoV).
-    const uint4* term; const uint4* acc; const uint32_t* geoM; int n5t, n3t; float inv_logM;
+    const uint4* term; const uint4* acc; const uint32_t* geoM; int n5t, n3t;
     // SINGLE/DOUBLE: sd5[r] (C->T 5'), sd3[r] (C->T single / G->A double)
     const uint32_t* sd5; const uint32_t* sd3;
     // BRIGGS: geometric tables (u31 < cdf_thr[k] first k) of n_geo entries: overhang lengths, nick position, and the skips of the
     // event draws over the single-stranded (rate s) and double-stranded (rate d) positions
     const uint32_t* geoL; const uint32_t* geoV; const uint32_t* geoS; const uint32_t* geoD; int n_geo;
+    const uint8_t* guideA; const uint8_t* guideB;      // 512-entry guides of geoM / geoS (A) and geoD (B)
     // BRIGGS_SS (-damagess d,s5,s3,l5,l3; still drawn per base): Ks = 5' overhang rate, K3 = 3' overhang rate, Kd = middle, geoL = 5' lengths,
     // geoL3 = 3' lengths (plain Briggs: geoL3 == geoL)
     uint32_t Ks, Kd, K3; const uint32_t* geoL3;
     // 1 / ln(1 - p) of the geometric tables: starting guess of the inverse-CDF search (the table decides)
-    float inv_logL, inv_logL3, inv_logV, inv_logS, inv_logD;
+    float inv_logL, inv_logL3, inv_logV;
 };
 #define GG_GEO_MISS (1 << 29)     // an overhang / nick draw that ran off its table: beyond any record
 
@@ -135,6 +136,15 @@ __device__ __forceinline__ int first_below_geo(const uint32_t* __restrict__ thr,
 #pragma unroll 1
     while (k < n && u >= __ldg(thr + k)) k++;
     return k;
+}
+// The same inverse CDF for the hot draws (the skips of the event draws): guide[u31 >> 22] = first k whose threshold lies above the cell's
+// lower edge, then a short upward scan; one byte load + (usually) one threshold load.  Entries of 255 mean "255 or later".  The scan
+// stops at lim <= n (the positions that are left): a result of lim means "lim or more".
+__device__ __forceinline__ int first_below_guided(const uint32_t* __restrict__ thr, const uint8_t* __restrict__ guide, int lim, uint32_t u) {
+    int k = (int)__ldg(guide + (u >> 22));
+#pragma unroll 1
+    while (k < lim && u >= __ldg(thr + k)) k++;
+    return min(k, lim);
 }
 // Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
 struct BriggsHdr { int o5, o3, nick; };
@@ -197,9 +207,10 @@ __device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D
 #pragma unroll
             for (int sub = 0; sub < 2; sub++) {
                 if (pos < end) {
-                    const int j = first_below_geo(D.geoM, D.n_geo, (sub ? x.z : x.x) >> 1, D.inv_logM);
-                    pos += j;                                   // a table miss is "at least n_geo": no candidate, the next round goes on from there
-                    if (j < D.n_geo && pos < end) {
+                    const int lim = min(D.n_geo, end - pos);    // a skip of lim or more ends the walk (or, off a table shorter than the record, goes on from there)
+                    const int j = first_below_guided(D.geoM, D.guideA, lim, (sub ? x.z : x.x) >> 1);
+                    pos += j;
+                    if (j < lim) {
                         const int b = S.code(pos);
                         if (b >= 0) {
                             const int r = matrix_row(D, pos, L);
@@ -246,9 +257,10 @@ __device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D
 #pragma unroll
         for (int sub = 0; sub < 2; sub++) {
             if ((PH & 5) && v < nS) {
-                const int j = first_below_geo(D.geoS, D.n_geo, (sub ? x.z : x.x) >> 1, D.inv_logS);
+                const int lim = min(D.n_geo, nS - v);
+                const int j = first_below_guided(D.geoS, D.guideA, lim, (sub ? x.z : x.x) >> 1);
                 v += j;
-                if (j < D.n_geo && v < nS) {
+                if (j < lim) {
                     const bool five = allss || v < B.o5;
                     const int i = five ? v : L - B.o3 + (v - B.o5);
                     if (five ? (PH & 1) : (PH & 4)) { if (S.code(i) == (five ? 1 : 2)) S.put(i, five ? 1u : 2u, five ? 3u : 0u); }
@@ -256,9 +268,10 @@ __device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D
                 }
             }
             if ((PH & 2) && q < qend) {
-                const int j = first_below_geo(D.geoD, D.n_geo, (sub ? x.w : x.y) >> 1, D.inv_logD);
+                const int lim = min(D.n_geo, qend - q);
+                const int j = first_below_guided(D.geoD, D.guideB, lim, (sub ? x.w : x.y) >> 1);
                 q += j;
-                if (j < D.n_geo && q < qend) {
+                if (j < lim) {
                     const bool ct = B.nick > q;                     // placedNick = nick <= i (deamSim.cpp:1510,1542,1586)
                     if (S.code(q) == (ct ? 1 : 2)) S.put(q, ct ? 1u : 2u, ct ? 3u : 0u);
                     q++;

@@ -334,8 +334,7 @@ __device__ __noinline__ uint32_t damage_chunk_perbase(const FusedParams& P, cons
 // 16 bases (2 bits each) -> 16 ASCII bytes with byte permutes: a nibble of the selector picks one byte of "ACGT" (both operands hold
 // the table, so bit 2 of a nibble is don't-care and only bit 3 has to be cleared); even and odd bases are looked up separately and
 // interleaved.  13 ALU instructions, no shared-memory table.
-__device__ __forceinline__ uint4 codes16_to_ascii(uint32_t x) {
-    const uint32_t lut = 0x54474341u;                                      // 'A','C','G','T'
+__device__ __forceinline__ uint4 codes16_to_ascii(uint32_t x, uint32_t lut /* 0x54474341 = 'A','C','G','T', in a register */) {
     const uint32_t e = x & 0x77777777u, o = (x >> 2) & 0x77777777u;
     const uint32_t e0 = __byte_perm(lut, lut, e), o0 = __byte_perm(lut, lut, o);               // bases 0,2,4,6 / 1,3,5,7
     const uint32_t e1 = __byte_perm(lut, lut, e >> 16), o1 = __byte_perm(lut, lut, o >> 16);   // bases 8,10,12,14 / 9,11,13,15
@@ -354,7 +353,7 @@ __device__ __forceinline__ void put_dec32(uint8_t* p, uint32_t w, int nd, const 
 
 // ---- staged tile -> global memory with the bulk-copy engine (one instruction for the 16-byte aligned body of a tile)
 #ifndef GG_BULK_COPY
-#define GG_BULK_COPY 1
+#define GG_BULK_COPY 0      /* measured: plain 16-byte stores 1.633 ms, bulk copy of the last half 1.660 ms, of both halves 1.645 ms per 10 M fragments */
 #endif
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
@@ -364,6 +363,14 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-warp tile descriptors (a tile has at most 32 fragments); gg_api.cu reserves sizeof(WarpDesc) at the head of a warp's region
+struct WarpDesc {
+    uint64_t gpos[32];
+    uint32_t idx[32], meta[32], so[32], ci[32];
+    uint16_t hdr[32], nd[32], cstart[32], rg[32], gstart[36];
+};
+int fused_desc_bytes() { return (int)sizeof(WarpDesc); }
 
 // One warp owns one tile of up to 32 fragments from sampling to the global store; warps never wait for each other
 // (no CTA barrier inside the loop).  Byte offsets come from a decoupled look-back over per-warp-tile states.  Sampling, gather,
@@ -382,7 +389,9 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     __shared__ uint16_t s_d100[100];                // "00".."99" for the decimal fields of the deflines
     __shared__ uint16_t s_guide[1024];              // FREQ lengths: first candidate row for the top 10 bits of the uniform
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
+    asm volatile("" : "+r"(lane));                  // opaque: kept in a register instead of being re-derived from %tid at every use
     const int emit = P.emit;
     constexpr int NLINES = EMITC == 2 ? 2 : 1;
     const int sfx0 = EMITC == 1 ? P.sfx0 : 0;                              // "_r" on the only line of -rr ...
@@ -407,6 +416,11 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             ((uint16_t*)(tb + P.sm.tab_nlen))[q] = __ldg(P.ctab.name_len + q);
         }
         for (int q = tid; q < P.sm.names_bytes; q += blockDim.x) ((char*)(tb + P.sm.tab_names))[q] = __ldg(P.ctab.names + q);
+        for (int q = tid; q < P.sm.n_contigs; q += blockDim.x) {          // the first 8 bytes of every contig name as one word (header pass)
+            uint64_t w8 = 0; const int nl = min((int)__ldg(P.ctab.name_len + q), 8); const char* nm = P.ctab.names + __ldg(P.ctab.name_off + q);
+            for (int k = 0; k < nl; k++) w8 |= (uint64_t)(uint8_t)__ldg(nm + k) << (8 * k);
+            ((uint64_t*)(tb + P.sm.tab_name8))[q] = w8;
+        }
         for (int q = tid; q < P.sm.n_sizes_sm; q += blockDim.x) {
             ((uint32_t*)(tb + P.sm.tab_sthr))[q] = __ldg(P.size_thr + q); ((int32_t*)(tb + P.sm.tab_slen))[q] = __ldg(P.size_len + q);
         }
@@ -430,39 +444,46 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     const uint32_t*  const t_noff    = tsm ? (const uint32_t*)(tb + P.sm.tab_noff) : P.ctab.name_off;
     const uint16_t*  const t_nlen    = tsm ? (const uint16_t*)(tb + P.sm.tab_nlen) : P.ctab.name_len;
     const char*      const t_names   = tsm ? (const char*)(tb + P.sm.tab_names) : P.ctab.names;
+    const uint64_t*  const t_name8   = tsm ? (const uint64_t*)(tb + P.sm.tab_name8) : nullptr;
 
     const bool ssm = tsm && P.sm.n_sizes_sm > 0;
     const uint32_t* const t_sthr = ssm ? (const uint32_t*)(tb + P.sm.tab_sthr) : P.size_thr;
     const int32_t*  const t_slen = ssm ? (const int32_t*)(tb + P.sm.tab_slen) : P.size_len;
     const uint32_t* const adsm = (tsm && P.sm.ad_words[0] > 0) ? (const uint32_t*)tb : nullptr;
 #define TLD(p) (*(p))                           /* generic load: the shared copy or global memory (a per-use select of __ldg costs 0.7 %) */
-    // this warp's private shared memory
-    uint8_t*  const wb       = smem + P.sm.warp0 + (size_t)warp * P.sm.warp_bytes;
+    // this warp's private shared memory: the fixed-layout descriptors first (one base register + immediate offsets), then the
+    // regions whose size depends on the run
+    uint32_t wofs = (uint32_t)P.sm.warp0 + (uint32_t)warp * (uint32_t)P.sm.warp_bytes;
+    asm volatile("" : "+r"(wofs));                  // opaque, like lane: one register, every region is an immediate or constant-bank offset from it
+    uint8_t*  const wb       = smem + wofs;
+    WarpDesc* const wd       = (WarpDesc*)wb;
+    uint64_t* const s_gpos   = wd->gpos;
+    uint32_t* const s_idx    = wd->idx;        // start coordinate within the contig (contigs are shorter than 2^32)
+    uint32_t* const s_meta   = wd->meta;
+    uint32_t* const s_so     = wd->so;         // offset within the tile's bytes of the first sequence byte of line 0
+    uint32_t* const s_ci     = wd->ci;
+    uint16_t* const s_hdr    = wd->hdr;
+    uint16_t* const s_nd     = wd->nd;         // digit counts of start | end << 4 | length << 8
+    uint16_t* const s_cstart = wd->cstart;
+    uint16_t* const s_gstart = wd->gstart;
+    uint16_t* const s_rg     = wd->rg;
     uint8_t*  const s_stage  = wb + P.sm.stage;
-    uint64_t* const s_gpos   = (uint64_t*)(wb + P.sm.gpos);
-    uint32_t* const s_idx    = (uint32_t*)(wb + P.sm.idx);      // start coordinate within the contig (contigs are shorter than 2^32)
     unsigned long long* const s_bh = (unsigned long long*)(wb + P.sm.bh);
-    uint32_t* const s_meta   = (uint32_t*)(wb + P.sm.meta);
-    uint32_t* const s_so     = (uint32_t*)(wb + P.sm.so);       // offset within the tile's bytes of the first sequence byte of line 0
-    uint32_t* const s_ci     = (uint32_t*)(wb + P.sm.ci);
-    uint16_t* const s_hdr    = (uint16_t*)(wb + P.sm.hdr);
-    uint16_t* const s_nd     = (uint16_t*)(wb + P.sm.nd);       // digit counts of start | end << 4 | length << 8
-    uint16_t* const s_cstart = (uint16_t*)(wb + P.sm.cstart);
-    uint16_t* const s_gstart = (uint16_t*)(wb + P.sm.gstart);
-    uint16_t* const s_rg     = (uint16_t*)(wb + P.sm.rg);
     uint32_t* const s_dwords = (uint32_t*)(wb + P.sm.dwords);
     uint32_t* const s_lwords = (uint32_t*)(wb + P.sm.lwords);   // line images (adptSim dialects only)
     uint8_t*  const s_cmap   = wb + P.sm.cmap;
     uint8_t*  const s_gmap   = wb + P.sm.gmap;
 
     uint32_t my_attempts = 0, my_gather = 0, my_err = 0;
+    const uint32_t lut = P.lut;                     // 'A','C','G','T' for the byte permutes of the ASCII pass (a kernel parameter: as an immediate it was re-materialised four times per group)
 
-    int tile = 0;
-    if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    while (tile < P.n_tiles) {
-        int next_tile = 0;
-        if (lane == 0) next_tile = (int)atomicAdd(P.ticket, 1u);       // the next ticket is taken now and read at the end of this tile
+    while (true) {
+        // tiles are handed out in ticket order when a warp is ready for one: a tile's predecessors have then started earlier, which
+        // keeps the look-back short (taking the ticket ahead of time made the tiles behind it spin)
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= P.n_tiles) break;
         const uint64_t tile_first = (uint64_t)tile * (uint64_t)P.F;
         const int nf = (int)min((uint64_t)P.F, P.count - tile_first);
 
@@ -515,22 +536,18 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 }
                 if (L + 2 * d > 0) {                                                   // isResolvedDNAstring over the window incl. the flanks, fragSim.cpp:333-339,1472
                     const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1 + (uint64_t)xtra;
-                    const uint64_t w0 = s0 >> 5, w1 = e >> 5;
-                    uint32_t any = 0;
+                    const uint32_t* mw = G.nmask + (s0 >> 5);                          // first mask word of the window
+                    const int nw = (int)((e >> 5) - (s0 >> 5));                        // index of its last word
+                    const uint32_t first = 0xFFFFFFFFu << (s0 & 31), last = 0xFFFFFFFFu >> (31 - (e & 31));
+                    // the loads are independent (a dependent chain of misses costs pass A dearly): the edge words and up to three interior words at once
+                    const uint32_t m0 = __ldg(mw), mn = __ldg(mw + nw);
+                    const uint32_t m1 = __ldg(mw + min(1, nw)), m2 = __ldg(mw + min(2, nw)), m3 = __ldg(mw + min(3, nw));
+                    uint32_t any = nw == 0 ? (m0 & first & last) : ((m0 & first) | (mn & last));
+                    if (nw > 1) any |= m1;
+                    if (nw > 2) any |= m2;
+                    if (nw > 3) any |= m3;
 #pragma unroll 1
-                    for (uint64_t w = w0; w <= w1; w += 4) {           // four independent loads in flight (a dependent chain of misses costs pass A dearly)
-                        uint32_t m[4];
-#pragma unroll
-                        for (int t = 0; t < 4; t++) m[t] = __ldg(G.nmask + min(w + (uint64_t)t, w1));
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint64_t wt = min(w + (uint64_t)t, w1);
-                            uint32_t v = m[t];
-                            if (wt == w0) v &= 0xFFFFFFFFu << (s0 & 31);
-                            if (wt == w1) v &= 0xFFFFFFFFu >> (31 - (e & 31));
-                            any |= v;
-                        }
-                    }
+                    for (int w = 4; w < nw; w++) any |= __ldg(mw + w);                 // windows beyond 128 bases
                     if (any) continue;
                 }
                 plus = P.norev ? 1u : (x.y & 1u);                                      // randomBool, fragSim.cpp:1462-1467
@@ -609,21 +626,42 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass C: gather (lane per 16-base chunk)
-        for (uint32_t e = lane; e < n_chunks; e += 32) {
-            const int f = s_cmap[e];
-            const int k = (int)e - (int)s_cstart[f];
-            const uint32_t meta = s_meta[f];
-            const int fl = META_L(meta);
-            const uint64_t gp = s_gpos[f];
-            const uint32_t* seq2 = t_genomes[META_GEN(meta)].seq2;
-            const int n = min(16, fl - 16 * k);
-            uint32_t W = META_PLUS(meta) ? fetch16(seq2, (int64_t)(gp + 16ull * k))
-                                         : revcomp16(fetch16(seq2, (int64_t)(gp + (uint64_t)fl) - 16ll * k - 16ll));   // reverseComplement, fragSim.cpp:1484
-            if (DMODE == 0 && emit != 0) {                           // the models still drawn per base
-                const int slot = META_SLOT(meta);
-                if (slot >= 0 && P.dmg[slot].mode >= 3) W = damage_chunk_perbase(P, P.dmg[slot], s_bh[f], P.first + tile_first + (uint64_t)f, k, fl, n, W);
+        // two chunks per lane and trip: the four loads are issued before any of them is used (the gather is a dependent L2 access)
+        for (uint32_t e0 = lane; e0 < n_chunks; e0 += 64) {
+            uint32_t wlo[2], whi[2], wsh[2], wn[2]; bool rcmp[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t e = e0 + 32u * (uint32_t)u;
+                wlo[u] = whi[u] = wsh[u] = wn[u] = 0u; rcmp[u] = false;
+                if (e < n_chunks) {
+                    const int f = s_cmap[e];
+                    const int k = (int)e - (int)s_cstart[f];
+                    const uint32_t meta = s_meta[f];
+                    const int fl = META_L(meta);
+                    const uint32_t* seq2 = t_genomes[META_GEN(meta)].seq2;
+                    // forward strand: bases gp+16k ..; reverse strand: the 16 bases that end at gp+fl-16k, reverse-complemented (fragSim.cpp:1484)
+                    const int64_t pos = META_PLUS(meta) ? (int64_t)(s_gpos[f] + 16ull * (uint64_t)k) : (int64_t)(s_gpos[f] + (uint64_t)fl) - 16ll * k - 16ll;
+                    const uint32_t* wp = seq2 + (pos >> 4);
+                    wlo[u] = __ldg(wp); whi[u] = __ldg(wp + 1);
+                    wsh[u] = ((uint32_t)pos & 15u) * 2u; wn[u] = (uint32_t)min(16, fl - 16 * k); rcmp[u] = !META_PLUS(meta);
+                }
             }
-            s_dwords[e] = W & lowfields(n);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t e = e0 + 32u * (uint32_t)u;
+                if (e < n_chunks) {
+                    uint32_t W = __funnelshift_r(wlo[u], whi[u], wsh[u]);
+                    if (rcmp[u]) W = revcomp16(W);
+                    if (DMODE == 0 && emit != 0) {                   // the models still drawn per base
+                        const int f = s_cmap[e];
+                        const uint32_t meta = s_meta[f];
+                        const int slot = META_SLOT(meta);
+                        if (slot >= 0 && P.dmg[slot].mode >= 3)
+                            W = damage_chunk_perbase(P, P.dmg[slot], s_bh[f], P.first + tile_first + (uint64_t)f, (int)e - (int)s_cstart[f], META_L(meta), (int)wn[u], W);
+                    }
+                    s_dwords[e] = W & lowfields((int)wn[u]);
+                }
+            }
         }
         __syncwarp();
 
@@ -690,8 +728,12 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const int pofs = pad - (int)b0;                                                     // staging offset = pofs + offset within the tile
             const bool ok = fits && TB <= (uint32_t)P.sm.stage_bytes;                           // host sizing guard: never write past staging
             if (!ok) my_err |= ERRF_OVERFLOW;
+#if GG_BULK_COPY == 2
+            if (f0 > 0) { if (lane == 0) bulk_wait_read(); __syncwarp(); }                      // the first half's bulk copy has read the staging buffer
+#endif
 
-            // ---- headers + newlines: two lanes per fragment (lane 2k: ">name:strand:start:", lane 2k+1: "end:len" tag "\n" ... "\n")
+            // ---- headers + newlines: two lanes per fragment running the same code on different fields.  Lane 2k: '>' name ":s:" start ':';
+            // lane 2k+1: end ':' length tag ["_r"] '\n' and the newline behind the sequence   (fragSim.cpp:1489,1498,1505-1507,1603)
             auto write_headers = [&]() {
                 const int fh = f0 + (lane >> 1), part = lane & 1;
                 if (fh < f1 && ok) {
@@ -699,36 +741,43 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     const int L = META_L(meta);
                     const int hdr = (int)s_hdr[fh];
                     const uint32_t nd = s_nd[fh];
-                    const int n1 = (int)(nd & 15u), n2 = (int)((nd >> 4) & 15u), n3 = (int)(nd >> 8);
+                    const int n3 = (int)(nd >> 8);
                     const int S = EMITC ? P.S_ad : L;
                     uint8_t* rec = s_stage + pofs + (int)s_so[fh] - hdr - sfx0 - 1;             // first byte of the record
+                    const char* csrc; int cn, nv, coff, voff; uint64_t v;                       // bytes to copy (name / tag) and the coordinate to print, with their offsets in the header
+                    uint64_t cw = 0; bool wordcopy;                                             // names / tags of up to 8 bytes travel in a register pair
+                    if (part == 0) {
+                        const int ci = (int)s_ci[fh];
+                        csrc = t_names + t_noff[ci]; cn = t_nlen[ci]; coff = 1;
+                        v = s_idx[fh]; nv = (int)(nd & 15u); voff = 1 + cn + 3;
+                        wordcopy = t_name8 != nullptr && cn <= 8;
+                        if (wordcopy) cw = t_name8[ci];
+                    } else {
+                        const RangeDev* rg = t_ranges + s_rg[fh];
+                        csrc = rg->tag; cn = rg->tag_len; coff = hdr - cn;
+                        v = (uint64_t)s_idx[fh] + (uint64_t)L; nv = (int)((nd >> 4) & 15u); voff = hdr - cn - n3 - 1 - nv;
+                        wordcopy = cn <= 8;
+                        if (wordcopy) cw = *(const uint64_t*)rg->tag;
+                    }
 #pragma unroll
                     for (int ln = 0; ln < NLINES; ln++) {
                         const int sfx = ln ? sfx1 : sfx0;
-                        if (part == 0) {                        // ">chr:+:start:"   (fragSim.cpp:1489,1498,1603)
-                            const int ci = (int)s_ci[fh];
-                            const char* nm = t_names + t_noff[ci];
-                            const int nlen = t_nlen[ci];
-                            uint8_t* p = rec;
-                            *p++ = '>';
+                        if (wordcopy) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) if (k < cn) rec[coff + k] = (uint8_t)(cw >> (8 * k));
+                        } else {
 #pragma unroll 1
-                            for (int k = 0; k < nlen; k++) p[k] = (uint8_t)nm[k];
-                            p += nlen;
-                            p[0] = ':'; p[1] = META_PLUS(meta) ? '+' : '-'; p[2] = ':';
-                            put_dec32(p + 3, s_idx[fh], n1, s_d100); p[3 + n1] = ':';
-                        } else {                                // "end:len" + tag (no separator, fragSim.cpp:1505-1507) [+ "_r"] + "\n", and the newline behind the sequence
-                            const RangeDev* rg = t_ranges + s_rg[fh];
-                            const char* tag = rg->tag; const int tag_len = rg->tag_len;
-                            const uint64_t iend = (uint64_t)s_idx[fh] + (uint64_t)L;
-                            uint8_t* p = rec + (hdr - tag_len - n3 - 1 - n2);
-                            if (iend <= 0xFFFFFFFFull) put_dec32(p, (uint32_t)iend, n2, s_d100); else put_decimal(p, iend, n2, s_d100);
-                            p[n2] = ':'; p += n2 + 1;
-                            put_dec32(p, (uint32_t)L, n3, s_d100); p += n3;
-#pragma unroll 1
-                            for (int k = 0; k < tag_len; k++) p[k] = (uint8_t)tag[k];
-                            p += tag_len;
-                            if (sfx) { p[0] = '_'; p[1] = 'r'; p += 2; }
-                            p[0] = '\n'; p[S + 1] = '\n';
+                            for (int k = 0; k < cn; k++) rec[coff + k] = (uint8_t)csrc[k];
+                        }
+                        uint8_t* p = rec + voff;
+                        if (v <= 0xFFFFFFFFull) put_dec32(p, (uint32_t)v, nv, s_d100); else put_decimal(p, v, nv, s_d100);
+                        p[nv] = ':';
+                        if (part == 0) { rec[0] = '>'; p[-3] = ':'; p[-2] = META_PLUS(meta) ? '+' : '-'; p[-1] = ':'; }
+                        else {
+                            put_dec32(p + nv + 1, (uint32_t)L, n3, s_d100);
+                            uint8_t* q = rec + hdr;
+                            if (sfx) { q[0] = '_'; q[1] = 'r'; q += 2; }
+                            q[0] = '\n'; q[S + 1] = '\n';
                         }
                         rec += hdr + sfx + 1 + S + 1;
                     }
@@ -736,42 +785,51 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             };
             if (!FASTB) { write_headers(); __syncwarp(); }
 
-            // ---- ASCII: lane per 16-byte staging group
-            uint32_t e0, e1;                                     // group slots of fragments [f0, f1)
-            if (EMITC) { e0 = (uint32_t)f0 * P.gpf_ad; e1 = (uint32_t)f1 * P.gpf_ad; }
-            else { e0 = s_gstart[f0]; e1 = s_gstart[f1]; }
-            if (ok)
-            for (uint32_t e = e0 + lane; e < e1; e += 32) {
-                int f, g;
-                if (EMITC) { f = (int)__umulhi(e, P.gmagic); g = (int)(e - (uint32_t)f * P.gpf_ad); }   // e / groups-per-fragment by a host-made reciprocal
-                else { f = s_gmap[e]; g = (int)e - (int)s_gstart[f]; }
-                int S = P.S_ad;
-                if (EMITC == 0) S = META_L(s_meta[f]);
-                int ls = pofs + (int)s_so[f];                       // staging offset of the first sequence byte of this line
-                int line = 0;
-                if (EMITC == 2 && g >= (int)P.gpl_ad) { line = 1; g -= (int)P.gpl_ad; ls += (int)s_hdr[f] + sfx1 + S + 2; }
-                const int sigma = ls & 15;
-                const int j0 = 16 * g - sigma;
-                const int jlo = max(j0, 0), jhi = min(j0 + 16, S);
-                if (jhi <= jlo) continue;
-                const uint32_t* src = EMITC == 0 ? s_dwords + s_cstart[f] : s_lwords + f * P.lw_stride + line * P.LWL + 1;
-                const uint4 a = codes16_to_ascii(fetch_run_smem(src, j0));
-                uint8_t* dst = s_stage + (ls - sigma) + 16 * g;         // 16-byte aligned
-                if (FASTB || (jlo == j0 && jhi == j0 + 16)) {
-                    *(uint4*)dst = a;                                   // FASTB: bytes outside the line are rewritten by the header pass
-                } else {
-                    // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
-                    // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
-                    const int t0 = jlo - j0, t1 = jhi - j0;                  // valid bytes [t0,t1) of the group
-                    const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
-                    uint32_t* d4 = (uint32_t*)dst;
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            // ---- ASCII: two lanes per fragment; a lane walks half of the staging groups of a sequence line (or one of the two lines of the
+            // four-line dialect) with one running source word: one shared-memory load, one funnel shift, the expansion and one 16-byte
+            // store per group
+            {
+                const int fd = f0 + (lane >> 1), h = lane & 1;
+                if (fd < f1 && ok) {
+                    int S = P.S_ad;
+                    if (EMITC == 0) S = META_L(s_meta[fd]);
+                    int ls = pofs + (int)s_so[fd];                                              // staging offset of the first sequence byte of the line
+                    const uint32_t* src = EMITC == 0 ? s_dwords + s_cstart[fd] : s_lwords + fd * P.lw_stride + 1;
+                    if (EMITC == 2 && h) { ls += (int)s_hdr[fd] + sfx1 + S + 2; src += P.LWL; }   // the reverse read's line
+                    const int sigma = ls & 15;
+                    const int ngr = (sigma + S + 15) >> 4;                                      // staging groups that hold bases of the line
+                    const int half = (ngr + 1) >> 1;
+                    const int g_lo = (EMITC == 2 || !h) ? 0 : half, g_hi = (EMITC == 2 || h) ? ngr : half;
+                    uint8_t* dst = s_stage + (ls - sigma) + 16 * g_lo;                          // 16-byte aligned
+                    // group g holds bases [16 g - sigma, 16 g - sigma + 16): source words (16 (g+1) - sigma) >> 4 - 1 and the next one (a guard
+                    // word sits in front of every source)
+                    const uint32_t* sp = src + (((16 * (g_lo + 1) - sigma) >> 4) - 1);
+                    const uint32_t sh = ((uint32_t)(16 - sigma) & 15u) * 2u;
+                    uint32_t prev = *sp;
+#pragma unroll 1
+                    for (int g = g_lo; g < g_hi; g++) {
+                        const uint32_t next = *++sp;
+                        const uint4 a = codes16_to_ascii(__funnelshift_r(prev, next, sh), lut);
+                        prev = next;
+                        const int j0 = 16 * g - sigma;
+                        if (FASTB || (j0 >= 0 && j0 + 16 <= S)) {
+                            *(uint4*)dst = a;                           // FASTB: bytes outside the line are rewritten by the header pass
+                        } else {
+                            // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
+                            // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
+                            const int t0 = max(j0, 0) - j0, t1 = min(j0 + 16, S) - j0;          // valid bytes [t0,t1) of the group
+                            const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
+                            uint32_t* d4 = (uint32_t*)dst;
+                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        const uint32_t nib = (V >> (4 * w)) & 0xFu;
-                        const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
-                        if (nib == 0xFu) d4[w] = aw[w];
-                        else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                            for (int w = 0; w < 4; w++) {
+                                const uint32_t nib = (V >> (4 * w)) & 0xFu;
+                                const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
+                                if (nib == 0xFu) d4[w] = aw[w];
+                                else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                            }
+                        }
+                        dst += 16;
                     }
                 }
             }
@@ -784,7 +842,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 const int end = pad + (int)TB;
                 const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
 #if GG_BULK_COPY
-                if (f1 == nf) {                                          // the tile's last half goes out through the bulk-copy engine: its staging is not needed before the next tile's emission
+                if (GG_BULK_COPY == 2 || f1 == nf) {                     // the tile's last half goes out through the bulk-copy engine: its staging is not needed before the next tile's emission
                     fence_async_smem();                                  // this lane's staging writes -> visible to the bulk-copy engine
                     __syncwarp();
                     if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
@@ -797,7 +855,6 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             }
             __syncwarp();
         }
-        tile = __shfl_sync(0xffffffffu, next_tile, 0);
     }
 #if GG_BULK_COPY
     if (lane == 0) bulk_wait_all();

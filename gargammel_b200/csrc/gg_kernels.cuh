@@ -55,12 +55,10 @@ struct SmemLayout {          // byte offsets into dynamic shared memory, compute
     int term_slot[4];        // ... and of its terminal rows
     int warp0, warp_bytes;   // per-warp regions start at warp0 + warp * warp_bytes; the offsets below are relative to a region
     int stage, stage_bytes;  // output staging (readable slack before and after)
-    int gpos, meta, so, hdr, nd, cstart, gstart;   // per-fragment descriptors
-    int idx, ci, rg;                               // per-fragment header state parked between passes
     int bh;                                        // per-fragment Briggs header draws (overhangs, nick), u64 each
     int dwords, lwords, cmap, gmap, total;
     // CTA-shared copy of the plan / genome / contig tables when they are small (tab < 0: read them from global memory)
-    int tab, tab_ranges, tab_genomes, tab_cum, tab_gbase, tab_len, tab_noff, tab_nlen, tab_names, tab_bytes;
+    int tab, tab_ranges, tab_genomes, tab_cum, tab_gbase, tab_name8, tab_len, tab_noff, tab_nlen, tab_names, tab_bytes;
     int n_contigs, names_bytes;
     // ... plus the FREQ length tables (n_sizes_sm entries, 0 = not copied) and the three packed adapters (ad_words[k] words each incl.
     // guard and slack, 0 = not copied), byte offsets relative to tab
@@ -82,6 +80,7 @@ struct FusedParams {
     uint32_t gmagic;         // ceil(2^32 / gpf_ad): group index -> fragment by one multiply
     int sfx0;                // 2 when the only line carries "_r" (-rr), else 0
     int E;                   // fragments per emission half (the staging buffer holds E records)
+    uint32_t lut;            // 0x54474341: the bytes 'A','C','G','T'
     ggd::Key key;
     // plan + genomes
     const RangeDev* ranges; int n_ranges;
@@ -138,6 +137,7 @@ cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t*
                                uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
 cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, ggd::Key key,
                             unsigned long long* sums /* [0]=sum gc, [1]=sum gc^2, [2]=give-ups */, cudaStream_t st);
+int fused_desc_bytes();      // bytes of the fixed-layout descriptors at the head of a warp's shared-memory region
 cudaError_t launch_fused(const FusedParams& P, int emitc, int grid, int threads, cudaStream_t st);
 cudaError_t fused_prepare(int fast, int dmode, int emitc, int threads, int smem_bytes, int* blocks_per_sm, int* regs);
 
