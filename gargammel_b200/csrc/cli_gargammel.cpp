@@ -2,10 +2,14 @@
 // apportions the fragments across the sources (gargammel.pl:1256-1283,1320-1349,1421-1431), and runs
 // fragSim -> deamSim -> adptSim as ONE kernel per GPU instead of ~N process launches, 3 gzip and 2 gunzip hops.
 // Writes <prefix>_a.fa (what adptSim -artp/-arts writes for ART, gargammel.pl:1838-1848); with --keep also the
-// intermediate <prefix>.{e,b,c}.fa.gz and <prefix>_d.fa.gz of the reference.  ART stays on the host (north_star).
+// intermediate <prefix>.{e,b,c}.fa.gz and <prefix>_d.fa.gz of the reference.  ART stays on the host (north_star): when an
+// art_illumina is found (--art PATH, next to this binary like gargammel.pl:232-239, or on PATH) it is run exactly as gargammel.pl:1856-1869
+// does and the outputs get the reference's final names <prefix>_a.fa.gz, <prefix>_s.fq.gz / _s1.fq.gz + _s2.fq.gz (:1871-1889).
 #include "cli_common.h"
 #include <dirent.h>
 #include <sys/stat.h>
+#include <unistd.h>
+#include <limits.h>
 #include <algorithm>
 #include <thread>
 #include <math.h>
@@ -25,6 +29,29 @@ static std::vector<std::string> list_fa(const std::string& dir) {
     closedir(d); std::sort(out.begin(), out.end());
     return out;
 }
+// runcmd, gargammel.pl:71-84: echo the command, run it through bash unless --mock, die on a non-zero status
+static bool run_cmd(const std::string& cmd, bool mock) {
+    std::cerr << "running cmd " << cmd << std::endl;
+    if (mock) return true;
+    const std::string full = "bash -c '" + cmd + "'";
+    const int rc = system(full.c_str());
+    if (rc != 0) { std::cerr << "system  cmd " << cmd << " failed: " << rc << std::endl; return false; }
+    return true;
+}
+static bool is_exe(const std::string& p) { struct stat st; return !p.empty() && stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode) && access(p.c_str(), X_OK) == 0; }
+// art_illumina: --art PATH, else <dir of this binary>/../art_src_MountRainier/art_illumina (the reference's layout, gargammel.pl:239), else $PATH
+static std::string find_art(const std::string& given, const char* argv0) {
+    if (!given.empty()) return is_exe(given) ? given : std::string();
+    char self[PATH_MAX]; const ssize_t n = readlink("/proc/self/exe", self, sizeof self - 1);
+    std::string dir = n > 0 ? std::string(self, (size_t)n) : std::string(argv0);
+    const size_t sl = dir.rfind('/'); dir = sl == std::string::npos ? "." : dir.substr(0, sl);
+    const std::string cand[2] = {dir + "/../art_src_MountRainier/art_illumina", dir + "/art_src_MountRainier/art_illumina"};
+    for (int k = 0; k < 2; k++) if (is_exe(cand[k])) return cand[k];
+    const char* path = getenv("PATH");
+    for (const std::string& d : ggh::all_tokens(path ? path : "", ':')) if (is_exe(d + "/art_illumina")) return d + "/art_illumina";
+    return std::string();
+}
+
 struct DamageSpec { std::string matfile, briggs, mapd_file, mapd_proto; bool any() const { return !matfile.empty() || !briggs.empty() || !mapd_file.empty(); } };
 
 static int set_damage(gg_ctx* ctx, int slot, const DamageSpec& d) {
@@ -48,13 +75,16 @@ int main(int argc, char** argv) {
     double compB = 0, compC = 0, compE = 1; std::string comp = "0,0,1";
     uint64_t n = 1000; double coverage = -1; int fraglength = 35, minsize = 0, maxsize = 1000, rl = 75, gpus = 1;
     std::string sizeList, sizeFreq, prefix, adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG", adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";   // gargammel.pl:255-257
-    bool uniq = false;
+    bool uniq = false, mock = false, no_art = false;
+    std::string ss = "HS25", art_given; int qs = 0, qs2 = 0;                           // ART options of gargammel.pl:460-462 (defaults :268-270)
     bool se = false, keep = false, n_given = false, seedSpecified = false, lognorm = false; uint64_t seed = 0; double loc = 0, scale = 0;
     DamageSpec dAll, dE, dB, dC;
     std::string misE, misB, misC; int distmis = 1;                                  // --misince/--misincb/--misincc/--distmis (gargammel.pl:300-303)
     const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
         "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
-        "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t--seed [int]\t--gpus [N]\t--keep\n";
+        "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t-ss [system] -qs [int] -qs2 [int]\tART sequencing system and quality shifts\n" +
+        "\t--art [path]\tart_illumina to run on <prefix>_a.fa (default: ../art_src_MountRainier/art_illumina next to this binary, then $PATH)\n\t--noart\t\tstop after <prefix>_a.fa\n" +
+        "\t--mock\t\tprint what would be run, run nothing\n\t--seed [int]\t--gpus [N]\t--keep\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }
     for (int i = 1; i < argc - 1; i++) {
         std::string a = argv[i]; if (a.size() > 2 && a[0] == '-' && a[1] == '-') a = a.substr(1);      // Getopt::Long takes -x and --x
@@ -88,8 +118,13 @@ int main(int argc, char** argv) {
         if (a == "-gpus") { gpus = (int)to_ll(next(), "--gpus"); continue; }
         if (a == "-keep") { keep = true; continue; }
         if (a == "-uniq") { uniq = true; continue; }                                // fragSim -uniq for every source (gargammel.pl:1506-1507,1544,1628,1675)
-        if (a == "-mock" || a == "-methyl" || a == "-ss" ||
-            a == "-matfilenonmeth" || a == "-matfilemeth" || a == "-qs" || a == "-qs2") return unsupported(a, "SURVEY.md 8f");
+        if (a == "-mock") { mock = true; continue; }                               // gargammel.pl:71-84
+        if (a == "-ss") { ss = next(); continue; }
+        if (a == "-qs") { qs = (int)to_ll(next(), "-qs"); continue; }
+        if (a == "-qs2") { qs2 = (int)to_ll(next(), "-qs2"); continue; }
+        if (a == "-art") { art_given = next(); continue; }
+        if (a == "-noart") { no_art = true; continue; }
+        if (a == "-methyl" || a == "-matfilenonmeth" || a == "-matfilemeth") return unsupported(a, "SURVEY.md 8f-4");
         return die("Unknown option: " + a);
     }
     if (coverage >= 0 && n_given) return die("Must use the -c or -n but not both");                    // gargammel.pl:753-756
@@ -153,6 +188,7 @@ int main(int argc, char** argv) {
         const double sumEeff = fE.size() == 2 ? sumE / 2.0 : (double)sumE;
         const uint64_t nE = (uint64_t)(coverage * (sumEeff / use));
         n = (uint64_t)((double)nE / compE);
+        in.has_nE = true; in.nE = nE;                                              // the endogenous count stays what the coverage asks for (gargammel.pl:1255)
     }
     in.n_fragments = n;
     ggh::ApportionOut ap;
@@ -165,13 +201,42 @@ int main(int argc, char** argv) {
     std::vector<PlanItem> items;
     for (size_t i = 0; i < srcs.size(); i++) {
         const Src& s = srcs[i]; PlanItem it; it.src = i; it.count = 0; it.slot = -1; it.comp = -1;
-        if (s.kind == 'e') { it.count = ap.endo[s.idx]; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0; }
-        if (s.kind == 'b') { it.count = ap.bact[s.idx]; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; it.comp = misB.empty() ? -1 : 1; }
-        if (s.kind == 'c') { it.count = ap.cont[s.idx]; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; it.comp = misC.empty() ? -1 : 2; }
+        if (s.kind == 'e') { it.count = (size_t)s.idx < ap.endo.size() ? ap.endo[s.idx] : 0; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0; }
+        if (s.kind == 'b') { it.count = (size_t)s.idx < ap.bact.size() ? ap.bact[s.idx] : 0; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; it.comp = misB.empty() ? -1 : 1; }
+        if (s.kind == 'c') { it.count = (size_t)s.idx < ap.cont.size() ? ap.cont[s.idx] : 0; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; it.comp = misC.empty() ? -1 : 2; }
         if (it.count) items.push_back(it);
     }
     if (gpus < 1) gpus = 1;
     const int emit = se ? GG_EMIT_ARTS : GG_EMIT_ARTP;
+    // ---- what follows the kernel: art_illumina and the final names, exactly as gargammel.pl:1856-1889 composes them
+    if (!art_given.empty() && !is_exe(art_given)) return die("Cannot find file " + art_given);                     // fileExists, gargammel.pl:212-218
+    const std::string art = no_art ? std::string() : find_art(art_given, argv[0]);
+    const std::string cmd_art = art + " -ss " + ss + " -amp -na " + (se ? "    " : " -p ") + " -i " + prefix + "_a.fa  -l " + std::to_string(rl) + "  -c 1  -qs  " + std::to_string(qs) +
+                                "  -qs2 " + std::to_string(qs2) + "  -o " + prefix + "_s";
+    auto post = [&]() -> int {
+        if (art.empty()) {
+            std::cerr << (no_art ? "--noart: " : "art_illumina not found (--art PATH): ") << "stopping after " << prefix << "_a.fa" << std::endl;
+            return 0;
+        }
+        if (!run_cmd(cmd_art, mock) || !run_cmd("gzip -f " + prefix + "_a.fa", mock)) return 1;
+        if (se) { if (!run_cmd("gzip -f " + prefix + "_s.fq", mock)) return 1; std::cerr << "Single-end reads available here: " << prefix << "_s.fq.gz" << std::endl; }
+        else {
+            if (!run_cmd("gzip -f " + prefix + "_s1.fq", mock) || !run_cmd("gzip -f " + prefix + "_s2.fq", mock)) return 1;
+            std::cerr << "Paired-end forward reads available here: " << prefix << "_s1.fq.gz" << std::endl << "Paired-end reverse reads available here: " << prefix << "_s2.fq.gz" << std::endl;
+        }
+        std::cerr << "Program finished successfully" << std::endl;
+        return 0;
+    };
+    if (mock) {                                                    // print the plan instead of the reference's ~N fragSim/deamSim/adptSim command lines
+        uint64_t first = 0;
+        for (size_t k = 0; k < items.size(); k++) {
+            std::cerr << "fused range ids [" << first << "," << first + items[k].count << ") tag " << items[k].tag << " file " << srcs[items[k].src].path
+                      << " damage slot " << items[k].slot << " comp slot " << items[k].comp << std::endl;
+            first += items[k].count;
+        }
+        std::cerr << "running fused kernel fragSim->deamSim->adptSim " << (se ? "-arts " : "-artp ") << prefix << "_a.fa on " << gpus << " GPU(s)" << std::endl;
+        return post();
+    }
     // ---- one worker per GPU: rank r takes the r-th contiguous slice of the id space; outputs are concatenated in rank order
     std::vector<std::string> shard(gpus), shard_err(gpus); std::vector<int> rcs(gpus, 0);
     std::vector<std::vector<std::string> > shard_keep(gpus, std::vector<std::string>(4));
@@ -276,7 +341,7 @@ int main(int argc, char** argv) {
             }
         }
         std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << total << " sequences to " << prefix << "_a.fa" << std::endl;
-        return 0;
+        return post();
     }
     // -uniq: one defline counter per source file, exactly one fragSim invocation each in the reference
     auto uniq_pass = [&](std::vector<std::string>& parts) {
@@ -317,5 +382,5 @@ int main(int argc, char** argv) {
         se_.close(); sb_.close(); sc_.close();
     }
     std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << total << " sequences to " << prefix << "_a.fa" << std::endl;
-    return 0;
+    return post();
 }

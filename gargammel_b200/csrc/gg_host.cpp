@@ -362,9 +362,16 @@ bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err) {
         err = std::string("The --comp option must have 3 comma-delimited numbers that sum up to 1, current sum ") + t; return false;
     }
     if (in.n_endo != 1 && in.n_endo != 2 && in.compE > 0) { err = "The endogenous directory must have 1 (haploid) or 2 (diploid) files"; return false; }
-    out.nC = (uint64_t)((double)in.n_fragments * in.compC);             // gargammel.pl:1261-1263  int()
-    out.nB = (uint64_t)((double)in.n_fragments * in.compB);
-    out.nE = (uint64_t)((double)in.n_fragments * in.compE);
+    if (in.has_nE) {                                                    // -c: gargammel.pl:1255-1258
+        const double sum = in.compE + in.compC + in.compB;
+        out.nE = in.nE;
+        out.nC = (uint64_t)((double)in.n_fragments * in.compC / sum);
+        out.nB = (uint64_t)((double)in.n_fragments * in.compB / sum);
+    } else {
+        out.nC = (uint64_t)((double)in.n_fragments * in.compC);         // gargammel.pl:1261-1263  int()
+        out.nB = (uint64_t)((double)in.n_fragments * in.compB);
+        out.nE = (uint64_t)((double)in.n_fragments * in.compE);
+    }
     if (out.nC && in.cont_len.empty()) { err = "If you want contamination, please have at least one file in the cont/ directory"; return false; }
     if (out.nB && in.bact_w.empty()) { err = "If you want bacterial contamination, please have at least one file in the bact/ directory"; return false; }
     UStream U(in.seed, 1);

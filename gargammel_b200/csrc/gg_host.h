@@ -53,6 +53,10 @@ struct ApportionIn {
     std::vector<uint64_t> cont_len;        // contaminant file lengths (bp)
     std::vector<double> bact_w;            // bacterial weights (sum ~ 1)
     uint64_t seed;
+    // -c coverage path (gargammel.pl:1255-1258): the endogenous count is fixed by the coverage and kept as it is; only the contaminant and
+    // bacterial counts derive from n_fragments = int(nE / compE), as int(n * comp / (compE + compC + compB))
+    bool has_nE; uint64_t nE;
+    ApportionIn() : n_fragments(0), compB(0), compC(0), compE(1), n_endo(1), seed(0), has_nE(false), nE(0) {}
 };
 struct ApportionOut {
     uint64_t nE, nC, nB;                   // int(n*comp)  (gargammel.pl:1261-1263)

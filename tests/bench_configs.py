@@ -76,7 +76,9 @@ def main():
         rng = np.random.default_rng(1)
         n, L = 1_000_000, 50
         seqs = synth._BASES[rng.integers(0, 4, size=(n, L))]
-        recs = b"".join(b">chrS:+:%d:%d:50\n%s\n" % (i * 50, i * 50 + 50, seqs[i].tobytes()) for i in range(n))
+        rec_list = [b">chrS:+:%d:%d:50\n%s\n" % (i * 50, i * 50 + 50, seqs[i].tobytes()) for i in range(n)]
+        recs = b"".join(rec_list)
+        head = b"".join(rec_list[:30000])                   # whole records: a record's damage depends on its length
         ctx = api.Context(0, 42)
         ctx.set_matrix(0, s5, s3)
         ctx.run_deam(recs, 0)
@@ -86,7 +88,7 @@ def main():
             out, info = ctx.run_deam(recs, 0)
             t.append(info.device_ms)
         o = oracle.OracleContext(42); o.set_matrix(0, s5, s3)
-        assert out[:2_000_000] == o.run_deam(recs[:2_000_000], 0)[0][:2_000_000]
+        assert out[:len(head)] == o.run_deam(head, 0)[0]
         report("C1 deamSim -matfile single-, 1M x 50bp (record index + damage kernels; the H2D of the record stream is enqueued before the first event)", n, min(t), 2.0 * len(recs),
                "bytes = record stream read + written; %d kernels" % info.launches)
         ctx.close()

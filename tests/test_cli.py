@@ -285,3 +285,100 @@ def test_statistical_equivalence_with_reference_binaries(workdir, tmp_path):
     def starts(out):
         return np.array([int(h.split(b":")[2]) for h, _ in util.records(out) if h.startswith(b">chr1:")])
     assert stats.ks_2samp(starts(ours.stdout), starts(ref.stdout)).pvalue > 0.001
+
+
+def _three_dirs(t, n_bact=2):
+    d = t / "in"
+    for sub, names in (("endo", ["endo.1.fa", "endo.2.fa"]), ("cont", ["cont.1.fa"]), ("bact", ["b%d.fa" % (k + 1) for k in range(n_bact)])):
+        (d / sub).mkdir(parents=True)
+        for k, nm in enumerate(names):
+            fa, fai = synth.make_genome(3 * len(sub) + k, 2, 30000, prefix=sub[0] if sub == "endo" else sub[0] + str(k))
+            (d / sub / nm).write_bytes(fa); synth.write_fai(str(d / sub / (nm + ".fai")), fai)
+    (d / "bact" / "list").write_text("".join("b%d.fa\t%g\n" % (k + 1, 1.0 / n_bact) for k in range(n_bact)))
+    return d
+
+
+def test_fused_driver_mock_prints_plan_and_art_hand_off(tmp_path):
+    """--mock (gargammel.pl:71-84): nothing runs, the plan and the commands after the kernel are printed; the ART command line and the
+    final gzips are the reference's (gargammel.pl:1856-1889), -ss/-qs/-qs2 are passed through (:460-462).  Runs without a GPU."""
+    d = _three_dirs(tmp_path)
+    art = tmp_path / "art_illumina"; art.write_text("#!/bin/sh\nexit 0\n"); art.chmod(0o755)
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "--comp", "0.3,0.1,0.6", "-n", "1000", "-l", "40", "-damage", "0.03,0.4,0.01,0.3", "-ss", "MSv3", "-qs", "-3", "-qs2", "2",
+             "--art", str(art), "-o", str(tmp_path / "sim"), str(d)])
+    err = r.stderr.decode()
+    assert r.returncode == 0, err
+    assert "600\tendogenous fragments" in err and "100\tcontaminant fragments" in err and "300\tbacterial fragments" in err
+    assert err.count("fused range ids") == 5 and "tag e1_0" in err and "tag c1" in err
+    art_cmd = [l for l in err.splitlines() if l.startswith("running cmd " + str(art))]
+    assert len(art_cmd) == 1
+    toks = art_cmd[0].split()
+    assert toks[3:] == ["-ss", "MSv3", "-amp", "-na", "-p", "-i", str(tmp_path / "sim") + "_a.fa", "-l", "75", "-c", "1", "-qs", "-3", "-qs2", "2", "-o", str(tmp_path / "sim") + "_s"]
+    for f in ("_a.fa", "_s1.fq", "_s2.fq"):
+        assert "running cmd gzip -f " + str(tmp_path / "sim") + f in err
+    assert not os.path.exists(str(tmp_path / "sim") + "_a.fa")
+    # single-end: no -p, one fastq
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "-se", "-n", "10", "--art", str(art), "-o", str(tmp_path / "s2"), str(d)])
+    err = r.stderr.decode()
+    assert r.returncode == 0 and " -p " not in err and "gzip -f " + str(tmp_path / "s2") + "_s.fq" in err
+    # a missing --art is an error like the reference's fileExists (gargammel.pl:212-218,245-248); without one the run stops after _a.fa
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "-n", "10", "--art", str(tmp_path / "nope"), str(d)])
+    assert r.returncode == 1 and b"Cannot find file" in r.stderr
+
+
+def test_fused_driver_coverage_counts_follow_gargammel_pl(tmp_path):
+    """-c: the endogenous count is int(coverage * sumE/2 / size) and stays that; contaminant and bacterial counts come from
+    n = int(nE / compE) as int(n * comp / sum) (gargammel.pl:1236-1258)."""
+    d = _three_dirs(tmp_path)
+    cov, compB, compC, compE, L = 0.37, 0.3, 0.1, 0.6, 41
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "--noart", "--comp", "%g,%g,%g" % (compB, compC, compE), "-c", str(cov), "-l", str(L), str(d)])
+    err = r.stderr.decode()
+    assert r.returncode == 0, err
+    sumE = 0
+    for nm in ("endo.1.fa", "endo.2.fa"):
+        sumE += sum(int(l.split("\t")[1]) for l in open(str(d / "endo" / (nm + ".fai"))))
+    nE = int(cov * ((sumE / 2) / L)); n = int(nE / compE)
+    nC = int(n * compC / (compE + compC + compB)); nB = int(n * compB / (compE + compC + compB))
+    assert "%d\tendogenous fragments" % nE in err and "%d\tcontaminant fragments" % nC in err and "%d\tbacterial fragments" % nB in err
+
+
+def _run_fused_driver(tmp_path, d, name, extra):
+    synth.write_sizefreq(str(tmp_path / "sf.size"))
+    s5, s3 = synth.golden_matrix("single-")
+    synth.write_matrix_dat(str(tmp_path / "m-"), s5, s3)
+    r = run([os.path.join(BIN, "gargammel-b200"), "--comp", "0.3,0.1,0.6", "-n", "20000", "-f", str(tmp_path / "sf.size"), "-matfile", str(tmp_path / "m-"),
+             "-rl", "75", "--seed", "4242", "-o", str(tmp_path / name)] + extra + [str(d)])
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return r.stderr.decode()
+
+
+@pytest.mark.gpu
+def test_fused_driver_art_hand_off_final_names(tmp_path):
+    """With an art_illumina at hand the fused driver finishes like gargammel.pl:1856-1889: ART on <prefix>_a.fa, then <prefix>_a.fa.gz,
+    <prefix>_s1.fq.gz and <prefix>_s2.fq.gz (tests/art_stub.py stands in for ART, which this image does not have)."""
+    import gzip
+    d = _three_dirs(tmp_path)
+    art = tmp_path / "art_illumina"
+    art.write_text("#!/bin/sh\nexec python3 %s \"$@\"\n" % os.path.join(ROOT, "tests", "art_stub.py")); art.chmod(0o755)
+    _run_fused_driver(tmp_path, d, "plain", ["--noart"])
+    err = _run_fused_driver(tmp_path, d, "sim", ["--art", str(art)])
+    assert "Program finished successfully" in err
+    assert not os.path.exists(str(tmp_path / "sim_a.fa"))
+    amplicons = gzip.open(str(tmp_path / "sim_a.fa.gz")).read()
+    assert amplicons == (tmp_path / "plain_a.fa").read_bytes() and amplicons.count(b"\n") == 2 * 20000
+    for f in ("sim_s1.fq.gz", "sim_s2.fq.gz"):
+        assert gzip.open(str(tmp_path / f)).read().count(b"\n") == 4 * 20000
+
+
+@pytest.mark.gpu
+def test_fused_driver_two_gpus_byte_identical(tmp_path):
+    """--gpus 2: every rank takes a contiguous slice of the fragment ids; the concatenated outputs are the single-GPU bytes."""
+    import gzip
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d = _three_dirs(tmp_path)
+    _run_fused_driver(tmp_path, d, "one", ["--noart", "--keep", "--gpus", "1"])
+    _run_fused_driver(tmp_path, d, "two", ["--noart", "--keep", "--gpus", "2"])
+    assert (tmp_path / "one_a.fa").read_bytes() == (tmp_path / "two_a.fa").read_bytes()
+    for suffix in ("_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz"):
+        assert gzip.open(str(tmp_path / ("one" + suffix))).read() == gzip.open(str(tmp_path / ("two" + suffix))).read(), suffix
