@@ -44,7 +44,7 @@ def log(*a):
 # --------------------------------------------------------------------------- synthetic C2 directory
 def make_sources(genome_bp=GENOME_BP):
     """endo.1, endo.2 (= endo.1 with 0.1% SNPs), cont.1; iid bases, 0.5% of positions in N runs, 60-col lines."""
-    from gargammel_b200 import synth
+    from tests import synth
     rng = np.random.default_rng(20251019)
     n_contigs = 5
     edges = np.linspace(0, genome_bp, n_contigs + 1).astype(np.int64)
@@ -84,7 +84,7 @@ def make_plan(api, n_total, ids, seed=SEED):
 
 
 def setup_tables(api, ctx):
-    from gargammel_b200 import synth
+    from tests import synth
     lens, cum = synth.golden_sizefreq()
     ctx.set_sizes(api.SIZE_FREQ, lens, cum, minlen=0, maxlen=1000)       # gargammel.pl passes -m 0 -M 1000
     s5, s3 = synth.golden_matrix("single-")
@@ -209,7 +209,8 @@ def reference_step(workdir, n_frag, cores, gzip_hops=False):
 
 
 def oracle_shard(workdir, shard, nE1, nE2, nC):
-    from gargammel_b200 import api, synth
+    from gargammel_b200 import api
+    from tests import synth
     from oracle import oracle
     ctx = oracle.OracleContext(SEED + shard)
     ids = []
@@ -224,7 +225,7 @@ def oracle_shard(workdir, shard, nE1, nE2, nC):
 
 
 def prepare_reference_dir(sources):
-    from gargammel_b200 import synth
+    from tests import synth
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     w = tempfile.mkdtemp(prefix="gg_ref_", dir=base)
     for (fa, fai), name in zip(sources, ("endo.1.fa", "endo.2.fa", "cont.1.fa")):

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
         }
         if (a == "-o") { outGz = argv[++i]; continue; }
         if (a == "-last") { lastRowMatrix = false; continue; }
-        if (a == "-v") continue;                                                    // per-read log on stderr: not produced
+        if (a == "-v") return unsupported(a, "the per-read log of deamSim.cpp:1458-1465,1602-1611 is not produced by this build");
         if (a == "-name") { putDeamInName = true; continue; }                        // deamSim.cpp:342-345
         if (a == "-b" || a == "-u" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
         return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377

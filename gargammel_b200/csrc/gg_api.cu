@@ -119,7 +119,7 @@ struct gg_ctx {
     // adapters
     std::string adF, adS; int read_len;
     DBuf d_adF2, d_adS2, d_rcS2, d_adF, d_adS;
-    bool ad_dirty;
+    bool ad_dirty, ad_acgt;                            // ad_acgt: both adapters are upper-case ACGT (what the 2-bit fused path can carry)
     AdptNaming naming; int deam_name;
     // plan
     std::vector<gg_range> plan; DBuf d_ranges; bool plan_dirty;
@@ -276,17 +276,21 @@ int emit_seqlen(int emit, int L, int RL) { return emit <= GG_EMIT_DEAM ? L : (em
 
 // upper bounds over the current plan: header bytes, record bytes
 void plan_bounds(const gg_ctx* ctx, int emit, int Lmax, int* hdr_max, uint64_t* rec_max) {
-    size_t name = 1, tag = 0; uint64_t clen = 1;
+    size_t name = 1, tag = 0; uint64_t clen = 1, cend = 1;
     for (size_t i = 0; i < ctx->plan.size(); i++) {
         const gg_range& r = ctx->plan[i];
         tag = std::max(tag, strnlen(r.tag, sizeof(r.tag) - 1));
-        if (r.genome >= 0 && r.genome < (int)ctx->genomes.size())
-            for (size_t c = 0; c < ctx->genomes[r.genome].contigs.size(); c++) {
-                name = std::max(name, ctx->genomes[r.genome].contigs[c].name.size());
-                clen = std::max(clen, ctx->genomes[r.genome].contigs[c].len);
+        if (r.genome >= 0 && r.genome < (int)ctx->genomes.size()) {
+            const HostGenome& HG = ctx->genomes[r.genome];
+            for (size_t c = 0; c < HG.contigs.size(); c++) {
+                name = std::max(name, HG.contigs[c].name.size());
+                clen = std::max(clen, HG.contigs[c].len);
+                // the defline's end is start+length, un-wrapped on a --circ contig (fragSim.cpp:1489): it can pass the contig length by a fragment
+                cend = std::max(cend, HG.contigs[c].len + ((int)c == HG.circ_sorted ? (uint64_t)std::max(Lmax, 1) + 2 * GG_MAX_COMP_DIST + 1 : 0));
             }
+        }
     }
-    const int h = 1 + (int)name + 3 + digits10(clen) + 1 + digits10(clen) + 1 + digits10((uint64_t)std::max(Lmax, 1)) + (int)tag;
+    const int h = 1 + (int)name + 3 + digits10(clen) + 1 + digits10(cend) + 1 + digits10((uint64_t)std::max(Lmax, 1)) + (int)tag;
     *hdr_max = h;
     const int S = emit_seqlen(emit, Lmax, ctx->read_len);
     uint64_t b = 0;
@@ -368,7 +372,7 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false;
     ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
-    ctx->read_len = 100; ctx->ad_dirty = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
+    ctx->read_len = 100; ctx->ad_dirty = true; ctx->ad_acgt = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
     ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; ctx->last_ms = 0.0; ctx->h_pub = ctx->d_pub = nullptr;
     ctx->bgzf_slab = 0; ctx->bgzf_reuse_code = 0; ctx->bgzf_hdr_nbits = 0;
     for (int i = 0; i < GG_MAX_GC_SLOTS; i++) { ctx->gc[i].on = false; ctx->gc[i].wmax = -1; }
@@ -754,7 +758,7 @@ static int build_gc_table(gg_ctx* ctx, int slot, int wmax) {
                 double pSurv = 1 / (1 + exp(H.bias * (gcContent - H.mean)));
                 const double a = (gcContent - H.mean) / H.sd;
                 pSurv = pSurv * ((inv_sqrt_2pi / H.sd * exp(-0.5 * a * a)) / maxNorm);
-                t = thr_le(pSurv);
+                t = pSurv == pSurv ? thr_le(pSurv) : 2147483648u;                        // NaN (a genome whose probes all have the same GC content: sd = 0): "rP > NaN" is false, never killed
             }
             thr[(size_t)W * (W + 1) / 2 + g] = t;
         }
@@ -805,9 +809,12 @@ int gg_tables_set_adapters(gg_ctx* ctx, const char* fwd, const char* rev, int re
     if (!ctx || !fwd || !rev) return ctx ? ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: bad arguments") : GG_ERR_ARG;
     if (read_len < 1 || read_len > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: read length must be in [1,4095]");
     std::string f(fwd), s(rev);
-    for (size_t i = 0; i < f.size(); i++) if (!strchr("ACGT", f[i])) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be upper-case ACGT");
-    for (size_t i = 0; i < s.size(); i++) if (!strchr("ACGT", s[i])) return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be upper-case ACGT");
-    ctx->adF = f; ctx->adS = s; ctx->read_len = read_len; ctx->ad_dirty = true;
+    // the reference appends the adapter strings as they are (adptSim.cpp:298-315): lower case or index placeholders (N) pass through the
+    // stand-alone adptSim stage, which works on ASCII; the fused kernel carries sequences in 2 bits and needs upper-case ACGT
+    bool acgt = true;
+    for (size_t i = 0; i < f.size(); i++) { if ((unsigned char)f[i] < 0x21 || f[i] == '>') return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be printable"); if (!strchr("ACGT", f[i])) acgt = false; }
+    for (size_t i = 0; i < s.size(); i++) { if ((unsigned char)s[i] < 0x21 || s[i] == '>') return ctx->fail(GG_ERR_ARG, "gg_tables_set_adapters: adapters must be printable"); if (!strchr("ACGT", s[i])) acgt = false; }
+    ctx->adF = f; ctx->adS = s; ctx->read_len = read_len; ctx->ad_dirty = true; ctx->ad_acgt = acgt;
     return GG_OK;
 }
 
@@ -850,6 +857,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (!ctx || !out) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_fused: bad arguments") : GG_ERR_ARG;
     memset(out, 0, sizeof *out);
     if (emit < GG_EMIT_FRAG || emit > GG_EMIT_RR) return ctx->fail(GG_ERR_ARG, "gg_run_fused: unknown emit mode");
+    if (emit >= GG_EMIT_STDOUT4 && !ctx->ad_acgt) return ctx->fail(GG_ERR_ARG, "gg_run_fused: adapters with characters other than upper-case ACGT are only supported by the stand-alone adptSim stage (gg_run_adpt)");
     if (ctx->plan.empty() || ctx->genomes.empty()) return ctx->fail(GG_ERR_STATE, "gg_run_fused: no plan / genome");
     const uint64_t p0 = ctx->plan.front().first_id, p1 = ctx->plan.back().first_id + ctx->plan.back().count;
     if (first < p0 || first + count > p1) return ctx->fail(GG_ERR_ARG, "gg_run_fused: fragment ids outside the plan");
@@ -992,6 +1000,16 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (stats[ST_ERR] & ERRF_GIVEUP) return ctx->fail(GG_ERR_GIVEUP, "gg_run_fused: a fragment exhausted its sampling attempts (genome without an admissible window?)");
     if (stats[ST_ERR] & ERRF_OVERFLOW) return ctx->fail(GG_ERR_CAPACITY, "gg_run_fused: internal staging/output overflow");
     return GG_OK;
+}
+
+namespace {
+// the chunked egress pipelines steer gg_run_fused / gg_bgzf_dev through these context fields; whatever way the pipeline leaves
+// (CUDA error, capacity error, success) they go back to their defaults
+struct PipelineReset {
+    gg_ctx* c;
+    explicit PipelineReset(gg_ctx* ctx) : c(ctx) {}
+    ~PipelineReset() { c->out_slab = 0; c->bgzf_slab = 0; c->bgzf_reuse_code = 0; }
+};
 }
 
 // ------------------------------------------------------------------------------------------------ stand-alone stages
@@ -1142,6 +1160,7 @@ int gg_run_fused_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, 
     memset(out, 0, sizeof *out);
     if (chunk == 0) chunk = 1u << 20;
     CK(cudaSetDevice(ctx->device));
+    PipelineReset reset(ctx);
     uint8_t* dst = (uint8_t*)host_dst; size_t used = 0; int rc = GG_OK;
     for (uint64_t a = 0, i = 0; a < count; a += chunk, i++) {
         const int slab = (int)(i & 1);
@@ -1232,6 +1251,7 @@ int gg_run_fused_bgzf_to_host(gg_ctx* ctx, uint64_t first, uint64_t count, int e
     memset(out, 0, sizeof *out);
     if (chunk == 0) chunk = 1u << 20;
     CK(cudaSetDevice(ctx->device));
+    PipelineReset reset(ctx);
     uint8_t* dst = (uint8_t*)host_dst; size_t used = 0; int rc = GG_OK;
     ctx->bgzf_hdr_nbits = 0;                                                // the first chunk builds the code, the others reuse it
     for (uint64_t a = 0, i = 0; a < count; a += chunk, i++) {

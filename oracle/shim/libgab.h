@@ -66,6 +66,8 @@ inline char complement(char c) {
 }
 inline string reverseComplement(const string& s) { string r(s.size(), 'N'); for (size_t i = 0; i < s.size(); i++) r[i] = complement(s[s.size() - 1 - i]); return r; }
 
+/* mapDamage2prof.cpp:337 (-h format only): the row number right-aligned in a field of `width` characters (inferred from the name) */
+inline string printIntAsWhitePaddedString(int i, int width) { string t = stringify(i); while ((int)t.size() < width) t = " " + t; return t; }
 template <typename T> inline string thousandSeparator(const T v) {
     string d = stringify(v), out; int n = 0;
     for (int i = int(d.size()) - 1; i >= 0; i--) { out += d[i]; if (++n % 3 == 0 && i > 0 && isdigit(d[i - 1])) out += ','; }

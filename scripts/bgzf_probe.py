@@ -4,7 +4,8 @@ import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
-from gargammel_b200 import api, synth  # noqa: E402
+from gargammel_b200 import api
+from tests import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 rng = np.random.default_rng(7)

@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-from gargammel_b200 import api, synth  # noqa: E402
+from gargammel_b200 import api
+from tests import synth  # noqa: E402
 
 
 def peak():

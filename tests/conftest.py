@@ -21,5 +21,5 @@ def oracle_mod():
 
 @pytest.fixture(scope="session")
 def golden():
-    from gargammel_b200 import synth
+    from tests import synth
     return synth.golden()

@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from gargammel_b200 import synth  # noqa: E402
+from tests import synth  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "src")
 

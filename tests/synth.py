@@ -1,13 +1,14 @@
 """Synthetic inputs of the shapes BASELINE.json names (random genomes with N-runs, .fai, reference-format
-tables rebuilt from tests/golden/ref_tables.json).  Pure numpy; used by tests/ and bench.py."""
+tables rebuilt from tests/golden/ref_tables.json).  Pure numpy; test and benchmark infrastructure (tests/, bench.py,
+__graft_entry__.smoke()), not part of the product package."""
 import json
 import os
 
 import numpy as np
 
-from .api import FaiEntry
+from gargammel_b200.api import FaiEntry
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ref_tables.json")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tables.json")
 _BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 

@@ -7,7 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 from tests import util
 from tests.conftest import ROOT
 
@@ -382,3 +383,46 @@ def test_fused_driver_two_gpus_byte_identical(tmp_path):
     assert (tmp_path / "one_a.fa").read_bytes() == (tmp_path / "two_a.fa").read_bytes()
     for suffix in ("_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz"):
         assert gzip.open(str(tmp_path / ("one" + suffix))).read() == gzip.open(str(tmp_path / ("two" + suffix))).read(), suffix
+
+
+@pytest.mark.gpu
+def test_cli_deamsim_table_modes_match_oracle(workdir, tmp_path, oracle_mod):
+    """bin/deamSim -profile / -mat single|double / -mapdamage f single|double / -last / -name through the CLI == the oracle with the tables
+    the reference's loaders give (deamSim.cpp:453-668,956-1094,1098-1241,1941-2002); -v (the per-read log) is rejected, not swallowed."""
+    from oracle import parsers
+    d, fa, fai = workdir
+    seed, n = 99, 6000
+    o = oracle_mod.OracleContext(seed)
+    gid = o.upload_genome(fa, fai)
+    o.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=0, maxlen=1000)
+    o.set_plan([api.Range(0, n, gid, -1, "t")])
+    frags = o.run_fused(0, n, api.EMIT_FRAG)[0]
+    (tmp_path / "f.fa").write_bytes(frags)
+    # the reference resolves -mat through <dir of the executable>/matrices/ (deamSim.cpp:1105-1106): a src/ directory like gargammel's
+    src = tmp_path / "src"; (src / "matrices").mkdir(parents=True)
+    os.symlink(os.path.join(BIN, "deamSim"), src / "deamSim")
+    s5, s3 = synth.golden_matrix("single-"); d5, d3 = synth.golden_matrix("double-")
+    synth.write_matrix_dat(str(src / "matrices" / "single-"), s5, s3)
+    synth.write_matrix_dat(str(src / "matrices" / "double-"), d5, d3)
+    prof = os.path.join(ROOT, "tests", "golden", "sample_")
+    md = os.path.join(ROOT, "tests", "golden", "mapdamage_sample.txt")
+    p5, p3 = parsers.load_profile(prof)
+    m5, m3 = parsers.load_mapdamage(md)
+    cases = [
+        (["-profile", prof], lambda: o.set_matrix(0, np.array(p5), np.array(p3))),
+        (["-profile", prof, "-last", "-name"], lambda: (o.set_matrix(0, np.array(p5), np.array(p3), clamp_last=False), o.set_deam_naming(True))),
+        (["-mat", "single"], lambda: o.set_singledouble(0, api.DMG_SINGLE, s5, s3)),
+        (["-mat", "double", "-name"], lambda: (o.set_singledouble(0, api.DMG_DOUBLE, d5, d3), o.set_deam_naming(True))),
+        (["-mapdamage", md, "double"], lambda: o.set_singledouble(0, api.DMG_DOUBLE, np.array(m5), np.array(m3))),
+        (["-mapdamage", md, "single"], lambda: o.set_singledouble(0, api.DMG_SINGLE, np.array(m5), np.array(m3))),
+    ]
+    for args, setup in cases:
+        o.set_deam_naming(False)
+        setup()
+        r = run([str(src / "deamSim"), "--seed", str(seed)] + args + [str(tmp_path / "f.fa")])
+        assert r.returncode == 0, (args, r.stderr)
+        want = o.run_deam(frags, 0)[0]
+        util.assert_same(r.stdout, want, "bin/deamSim " + " ".join(args))
+        assert r.stdout != frags
+    r = run([str(src / "deamSim"), "-v", "-mat", "single", str(tmp_path / "f.fa")])
+    assert r.returncode == 1 and b"not supported" in r.stderr

@@ -10,7 +10,7 @@ import subprocess
 
 import pytest
 
-from gargammel_b200 import synth
+from tests import synth
 from tests.conftest import ROOT
 
 REF = "/root/reference/gargammel.pl"

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from gargammel_b200 import synth
+from tests import synth
 from tests import util
 from tests.conftest import ROOT
 

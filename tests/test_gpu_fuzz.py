@@ -3,7 +3,8 @@ strands, --comp, -gc, --circ and id windows; the CUDA path must stay bit-exact a
 import numpy as np
 import pytest
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 from tests import util
 
 pytestmark = pytest.mark.gpu

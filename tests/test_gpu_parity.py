@@ -3,7 +3,8 @@ same seeded inputs -- integer/byte work, so no tolerance anywhere."""
 import numpy as np
 import pytest
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -275,6 +276,45 @@ def test_adpt_name_and_tag(oracle_mod):
             util.assert_same(a, b, "adpt naming %r %r emit=%d" % (name, tag, emit))
     out = g.run_adpt(b">x\nACGT\n>y\n" + b"A" * 30 + b"\n>z\n" + b"C" * 50 + b"\n", api.EMIT_STDOUT4)[0].split(b"\n")
     assert out[0] == b">x_adpt_rand_lib7" and out[2] == b">x_r_adpt_rand_lib7" and out[4] == b">y_adpt_lib7" and out[8] == b">z_lib7"
+
+
+def test_standalone_deam_long_records(oracle_mod):
+    """Stand-alone deamSim has no bound on the record length, the geometric tables have 4096 entries: an overhang / nick draw that runs off
+    its table means "longer than any record", a skip that runs off the table carries on from there (DESIGN.md draw specification)."""
+    g = api.Context(0, 77); o = oracle_mod.OracleContext(77)
+    rng = np.random.default_rng(5)
+    recs = b"".join(b">long%d\n%s\n" % (i, synth._BASES[rng.integers(0, 4, int(n))].tobytes()) for i, n in enumerate([9000, 5000, 12000, 4096, 4097, 40, 8191] * 6))
+    flat = np.full((3, 12), 1e-4); flat[:, 5] = 2e-4
+    for name, setup in (("briggs tiny l", lambda c: c.set_briggs(0, 0.0001, 0.00005, 0.0002, 0.3)),
+                        ("briggs no overhang", lambda c: c.set_briggs(0, 0.00002, 0.9, 0.0001, 0.5)),
+                        ("matrix small rates", lambda c: c.set_matrix(0, flat, flat)),
+                        ("matrix small rates -last", lambda c: c.set_matrix(0, flat, flat, clamp_last=False))):
+        for c in (g, o):
+            setup(c)
+        for naming in (False, True):
+            g.set_deam_naming(naming); o.set_deam_naming(naming)
+            a = g.run_deam(recs, 0, 3)[0]; b = o.run_deam(recs, 0, 3)[0]
+            util.assert_same(a, b, "long records: %s, -name %r" % (name, naming))
+        if "last" not in name:
+            assert a != recs
+
+
+def test_adpt_adapters_pass_through_as_given(oracle_mod, genomes):
+    """The reference appends -f/-s as they are (adptSim.cpp:298-315): lower case and index placeholders (N) go through the stand-alone
+    adptSim stage untouched; the fused kernel (2-bit sequences) refuses them loudly."""
+    g = api.Context(0, 3); o = oracle_mod.OracleContext(3)
+    rng = np.random.default_rng(18)
+    recs = b"".join(b">f%d\n%s\n" % (i, synth._BASES[rng.integers(0, 4, int(rng.integers(1, 60)))].tobytes()) for i in range(300))
+    for c in (g, o):
+        c.set_adapters("AGATCGGAAGAGCacacgtNNNNNNNNatctcg", "agatcGGAAGNNNNgtgt", 50)
+    for emit in ALL_EMITS[2:]:
+        util.assert_same(g.run_adpt(recs, emit)[0], o.run_adpt(recs, emit)[0], "raw adapters emit=%d" % emit)
+    assert b"acacgtNNNNNNNNatctcg" in g.run_adpt(recs, api.EMIT_FR)[0]
+    ids = [g.upload_genome(fa, fai) for fa, fai in genomes]
+    g.set_sizes(api.SIZE_FIXED, fixed_len=30); g.set_plan([api.Range(0, 10, ids[0], -1, "x")])
+    with pytest.raises(api.GGError, match="upper-case ACGT"):
+        g.run_fused(0, 10, api.EMIT_ARTP)
+    g.run_fused(0, 10, api.EMIT_FRAG)                          # the fragSim / deamSim dialects do not use the adapters
 
 
 @pytest.mark.parametrize("damage", ["matrix", "briggs", "briggs_ss", "single", "double"])

@@ -7,7 +7,8 @@ import re
 import numpy as np
 import pytest
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 from oracle import parsers
 from tests.conftest import ROOT
 
@@ -75,6 +76,22 @@ def test_parsers_on_reference_files(golden):
     ol, oc = synth.golden_sizefreq()
     assert lens == ol and cum == oc
     assert _size_list("/root/reference/src/sizedist.size.gz")[:32] == golden["sizedist_first32"]
+
+
+def test_profile_parser():
+    """-profile (deamSim.cpp:956-1094): <prefix>5p.prof / <prefix>3p.prof, 12 columns, header skipped, the 3' file NOT reversed.  The fixture
+    was written by the reference's own mapDamage2prof (tests/golden/make_prof_fixture.py) from tests/golden/mapdamage_sample.txt."""
+    prefix = os.path.join(ROOT, "tests", "golden", "sample_")
+    g5, g3 = _load_rates(prefix, 1)
+    o5, o3 = parsers.load_profile(prefix)
+    assert g5.shape == (70, 12) and g3.shape == (70, 12)
+    assert np.array_equal(g5, np.array(o5)) and np.array_equal(g3, np.array(o3))
+    # the rates are the mapDamage counts turned into frequencies (mapDamage2prof.cpp:334-367): the same numbers -mapdamage computes itself
+    m5, m3 = parsers.load_mapdamage(os.path.join(ROOT, "tests", "golden", "mapdamage_sample.txt"))
+    assert np.allclose(g5[:, 5], np.array(m5)[:, 5], rtol=1e-5) and np.allclose(g3[:, 6], np.array(m3)[:, 6], rtol=1e-5)
+    assert g5[0, 5] > 0.1 > g5[20, 5]                                   # C->T decays from the 5' end
+    with pytest.raises(ValueError, match="Unable to open"):
+        _load_rates(prefix + "missing_", 1)
 
 
 def test_mapdamage_parser(golden):

@@ -9,7 +9,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 from tests import util
 
 

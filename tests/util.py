@@ -3,7 +3,8 @@ import os
 
 import numpy as np
 
-from gargammel_b200 import api, synth
+from gargammel_b200 import api
+from tests import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
