@@ -42,9 +42,13 @@ inline uint64_t time_seed() {       // the reference seeds from the clock when -
     return (uint64_t)t.tv_sec * 1000000ull + (uint64_t)t.tv_usec;
 }
 inline std::string exe_dir(const char* argv0) {     // getCWD(argv[0]) of libgab: directory of the executable, trailing '/'
-    char buf[PATH_MAX]; std::string p;
-    ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
-    if (n > 0) { buf[n] = 0; p = buf; } else p = argv0;
+    // the path the program was called by wins (a src/deamSim symlink in a gargammel tree finds src/matrices/ next to it); a bare name
+    // found through $PATH resolves through /proc/self/exe
+    char buf[PATH_MAX]; std::string p = argv0 ? argv0 : "";
+    if (p.find('/') == std::string::npos) {
+        ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+        if (n > 0) { buf[n] = 0; p = buf; }
+    }
     size_t k = p.find_last_of('/');
     return k == std::string::npos ? std::string("./") : p.substr(0, k + 1);
 }

@@ -166,7 +166,7 @@ def test_errors_are_loud(genomes):
     with pytest.raises(api.GGError):
         g.set_sizes(api.SIZE_FIXED, fixed_len=5000, maxlen=10000)
     with pytest.raises(api.GGError):
-        g.set_adapters("ACGU", "ACGT", 75)
+        g.set_adapters("AC GT", "ACGT", 75)                     # adapters are printable strings (any letters: the reference appends them as given)
     with pytest.raises(api.GGError):
         g.set_briggs(0, 1.5, 0.4, 0.01, 0.3)
 
