@@ -295,9 +295,10 @@ def reference_step(workdir, J, counts, n_frag, cores, gzip_hops=False):
                 parts.append(("gzip -dc P$S.c.fa.gz | gzip >> P${S}_d.fa.gz" if gzip_hops else "cat P$S.c.fa >> P${S}_d.fa"))
             parts.append("%s -f %s -s %s -l %d -artp P${S}_a.fa P${S}_d.fa%s 2>/dev/null" % (adpt, AD_F, AD_S, J["read_len"], x))
         parts.append("rm -f P$S.d.fa%s P$S.c.fa%s P${S}_d.fa%s P${S}_a.fa" % (x, x, x))
-        sh = "; ".join(parts)
+        with open(os.path.join(workdir, "shard.sh"), "w") as fh:           # (a file: a thousand fragSim lines do not fit an argument)
+            fh.write("\n".join(parts) + "\n")
         t0 = time.perf_counter()
-        procs = [subprocess.Popen(["bash", "-c", sh, "shard", str(i)]) for i in range(cores)]
+        procs = [subprocess.Popen(["bash", os.path.join(workdir, "shard.sh"), str(i)]) for i in range(cores)]
         rcs = [p.wait() for p in procs]
         dt = time.perf_counter() - t0
         if any(rcs):

@@ -1053,15 +1053,39 @@ int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint6
     unsigned long long* d_stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
-    RecStream R; int launches = 0;
-    int rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches);
-    if (rc) return rc;
-    uint64_t out_bytes = n ? (R.n_nl == 2 * R.n_rec ? n : n + 1) : 0;
     DBuf& ob = pick_out(ctx, recs_dev);
     ggd::DamageDev D; memset(&D, 0, sizeof D);
     const int has = (slot >= 0 && ctx->dmg[slot].mode != GG_DMG_NONE) ? 1 : 0;
     if (has) fill_damage_dev(ctx->dmg[slot], &D);
     ggd::Key key; key.k0 = (uint32_t)ctx->seed; key.k1 = (uint32_t)(ctx->seed >> 32);
+    // ---- single pass (k_deam_stream): no record index, no host round trip.  It covers the event-drawn models without -name (record
+    // sizes unchanged) on a 16-byte aligned stream; ERRF_FALLBACK (very short lines, records longer than its look-ahead) -> general path
+    if (n && !getenv("GG_DEAM_GENERAL") && ((uintptr_t)recs_dev & 15) == 0 && (!has || ((D.mode == GG_DMG_MATRIX || D.mode == GG_DMG_BRIGGS) && !ctx->deam_name))) {
+        const uint64_t n_tiles64 = (n + (uint64_t)deam_stream_tile_bytes() - 1) / (uint64_t)deam_stream_tile_bytes();
+        if (n_tiles64 < 0xFFFFFFF0ull) {
+            CK(ob.ensure(n + 1 + 64));
+            CK(ctx->d_tile_state.ensure((size_t)n_tiles64 * 8));
+            CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles64 * 8, ctx->st));
+            CK(launch_deam_stream((const uint8_t*)recs_dev, n, ob.as<uint8_t>(), D, has, key, first_id, ctx->d_tile_state.as<unsigned long long>(),
+                                  ctx->d_ticket_stats.as<unsigned int>(), d_stats, (uint32_t)n_tiles64, ctx->sm_count, ctx->st));
+            unsigned long long stats[ST_N];
+            { int rcp = fetch_small(ctx, d_stats, stats, ST_N, ctx->ev1); if (rcp) return rcp; }
+            if (!(stats[ST_ERR] & ERRF_FALLBACK)) {
+                float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+                ctx->last_ms = ms;
+                const uint64_t lines = stats[ST_TOTAL];
+                out->dev_ptr = ob.p; out->bytes = n + stats[ST_ATTEMPTS]; out->records = lines / 2; out->in_bytes = n; out->device_ms = ms; out->launches = 2;   // k_deam_stream + k_publish
+                if (lines & 1) return ctx->fail(GG_ERR_PARSE, "record stream has an odd number of lines (expected ID line + sequence line per record)");
+                if (stats[ST_ERR] & ERRF_PARSE) return ctx->fail(GG_ERR_PARSE, "gg_run_deam: a record does not start with '>'");
+                return GG_OK;
+            }
+            CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));         // general path below (the event times then cover both attempts)
+        }
+    }
+    RecStream R; int launches = 0;
+    int rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches);
+    if (rc) return rc;
+    uint64_t out_bytes = n ? (R.n_nl == 2 * R.n_rec ? n : n + 1) : 0;
     if (ctx->deam_name && has && R.n_rec) {
         // -name: record sizes depend on the damage -> sizes, scan, write (the draws are counter-based, so both passes agree)
         const uint64_t nbk = (R.n_rec + 1 + 2047) / 2048;

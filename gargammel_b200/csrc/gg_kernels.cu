@@ -1081,6 +1081,222 @@ __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t
         }
     }
 }
+// ======================================================================================= stand-alone deamSim, single pass
+// deamSim's main loop (deamSim.cpp:1300-2042) over a 2-line FASTA record stream in ONE kernel: persistent, autonomous warps take
+// 4 KB tiles of the input by ticket.  A warp copies its tile (plus 1.5 KB of the next one: the record that starts in a tile may end
+// behind it) into shared memory with 16-byte loads, finds the newlines, learns the number of lines in front of the tile from a
+// decoupled look-back over per-tile line counts (that gives the line parity and the record index = the Philox fragment id), then
+// every lane takes one record that STARTS in the tile: upper-cases the sequence (deamSim.cpp:1319-1321), draws its damage events
+// and the warp stores the bytes of its records with 16-byte stores at the input's own offsets (the stage does not change the record
+// sizes without -name).  No record index in global memory, no host round trip.  Anything unusual (more than DS_NLMAX lines in a
+// tile, a record that does not end inside the buffer) raises ERRF_FALLBACK and the host takes the general multi-kernel path.
+constexpr int DS_TILE = 4096, DS_TAIL = 1536, DS_BUF = DS_TILE + DS_TAIL, DS_NLMAX = 320;      // at most 255 lines per tile on this path, plus the tail's
+constexpr int DS_WARP_BYTES = DS_BUF + 16 + 2 * DS_NLMAX + 32;
+constexpr int DS_WARPS = 32;
+
+// exact per-byte "== '\n'" flags of a word: 0x80 in every matching byte
+__device__ __forceinline__ uint32_t nl_flags(uint32_t x) {
+    const uint32_t t = x ^ 0x0A0A0A0Au;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);
+}
+// upper-case the ASCII letters of a word (toupper of deamSim.cpp:1319-1321 on four bytes)
+__device__ __forceinline__ uint32_t upper4(uint32_t x) {
+    const uint32_t y = x & 0x7F7F7F7Fu;
+    const uint32_t m = (y + 0x1F1F1F1Fu) & ~(y + 0x05050505u) & ~x & 0x80808080u;      // 'a' <= byte <= 'z'
+    return x ^ (m >> 2);
+}
+struct SeqAsciiSmem {                    // an upper-cased record in shared memory
+    uint8_t* p;
+    __device__ __forceinline__ int code(int i) const {
+        const uint32_t c = p[i];
+        const uint32_t v = (c >> 1) & 3u, k = v ^ (v >> 1);                 // A 0x41 -> 0, C 0x43 -> 1, G 0x47 -> 2, T 0x54 -> 3
+        return ((0x54474341u >> (8 * k)) & 0xFFu) == c ? (int)k : -1;
+    }
+    __device__ __forceinline__ void put(int i, uint32_t oldb, uint32_t newb) { if (newb != oldb) p[i] = code2ascii(newb); }
+};
+
+__global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, const DamageDev D, int has_damage,
+                                                                 Key key, uint64_t first_id, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
+                                                                 unsigned long long* __restrict__ stats, uint32_t n_tiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* const buf = smem + (size_t)warp * DS_WARP_BYTES;               // tile bytes at their global alignment (tiles start at multiples of 4096)
+    uint16_t* const nlpos = (uint16_t*)(buf + DS_BUF + 16);
+    uint32_t my_err = 0;
+    while (true) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const uint64_t b0 = (uint64_t)tile * DS_TILE;
+        const int tlen = (int)min((uint64_t)DS_TILE, n - b0);              // bytes of the tile proper
+        const int blen = (int)min((uint64_t)DS_BUF, n - b0);               // bytes in the buffer (tile + tail)
+        // ---- load: 16-byte chunks, chunk c = lane + 32 k; newline flags of the chunks are kept for the counting below
+        uint32_t cnt_lo = 0, cnt_hi = 0;                                    // newline counts of my chunks k = 0..3 / 4..7 (tile proper), 8 bits each
+        uint32_t msk[11];                                                   // 16-bit newline masks of my chunks (bit j = byte j)
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const int c = lane + 32 * k;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (16 * c < blen) v = __ldg((const uint4*)(in + b0) + c);      // (the input buffer has 16 bytes of slack behind n)
+            *(uint4*)(buf + 16 * c) = v;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t m16 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t f = nl_flags(w[q]);                          // 0x80 per newline byte -> 4 mask bits
+                m16 |= (((f >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * q);  // gather bits 0,8,16,24 into a nibble
+            }
+            const int valid = min(16, max(0, blen - 16 * c));               // bytes of the chunk inside the stream
+            m16 &= (1u << valid) - 1u;
+            msk[k] = m16;
+            if (k < 8) { const uint32_t pc = (uint32_t)__popc(16 * c < tlen ? (m16 & ((1u << min(16, tlen - 16 * c)) - 1u)) : 0u); if (k < 4) cnt_lo |= pc << (8 * k); else cnt_hi |= pc << (8 * (k - 4)); }
+        }
+        // ---- ranks: newlines are ordered by position = by (k, lane); exclusive prefix of the counts in that order.  The 8-bit fields of
+        // the packed scans cannot overflow when the tile has at most 255 newlines; a tile with more falls back.
+        uint32_t my_nl = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) my_nl += ((cnt_lo >> (8 * k)) & 0xFFu) + ((cnt_hi >> (8 * k)) & 0xFFu);
+        const uint32_t tot_nl = __reduce_add_sync(0xffffffffu, my_nl);
+        uint32_t inc_lo = cnt_lo, inc_hi = cnt_hi;                          // per-field inclusive scans over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc_lo, o), b = __shfl_up_sync(0xffffffffu, inc_hi, o);
+            if (lane >= o) { inc_lo += a; inc_hi += b; }
+        }
+        const uint32_t tot_lo = __shfl_sync(0xffffffffu, inc_lo, 31), tot_hi = __shfl_sync(0xffffffffu, inc_hi, 31);
+        uint32_t kbase[9]; kbase[0] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) kbase[k + 1] = kbase[k] + (((k < 4 ? tot_lo : tot_hi) >> (8 * (k & 3))) & 0xFFu);
+        const uint32_t nl_tile = kbase[8];                                  // newlines in the tile proper
+        bool fallback = tot_nl > 255u;
+        if (lane == 0) st_volatile_u64(tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)tot_nl);
+        // first look-back probe (consumed below)
+        unsigned long long lb = 2ull << 62;
+        if (tile > 0 && (long long)tile - 1 - lane >= 0) lb = ld_volatile_u64(tile_state + (tile - 1 - lane));
+        // ---- newline positions of the tile proper, in order, then those of the tail
+        if (!fallback) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = lane + 32 * k;
+                uint32_t m16 = 16 * c < tlen ? (msk[k] & ((1u << min(16, tlen - 16 * c)) - 1u)) : 0u;
+                uint32_t r = kbase[k] + (((k < 4 ? inc_lo : inc_hi) >> (8 * (k & 3))) & 0xFFu) - (uint32_t)__popc(m16);
+                while (m16) { const int b = __ffs(m16) - 1; nlpos[r++] = (uint16_t)(16 * c + b); m16 &= m16 - 1u; }
+            }
+        }
+        // tail (chunks 256..351): at most 48 positions are kept (two are needed per record that crosses the tile's end)
+        uint32_t nl_all = nl_tile;
+        {
+            uint32_t tc = 0;
+#pragma unroll
+            for (int k = 8; k < 11; k++) tc |= (uint32_t)__popc(msk[k]) << (8 * (k - 8));
+            uint32_t ti = tc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += a; }
+            const uint32_t tt = __shfl_sync(0xffffffffu, ti, 31);
+            uint32_t tb = 0;
+            if (!fallback) {
+#pragma unroll
+                for (int k = 8; k < 11; k++) {
+                    uint32_t m16 = msk[k];
+                    uint32_t r = nl_tile + tb + ((ti >> (8 * (k - 8))) & 0xFFu) - (uint32_t)__popc(m16);
+                    while (m16) { const int b = __ffs(m16) - 1; if (r < (uint32_t)DS_NLMAX) nlpos[r] = (uint16_t)(16 * (lane + 32 * k) + b); r++; m16 &= m16 - 1u; }
+                    tb += (tt >> (8 * (k - 8))) & 0xFFu;
+                }
+            }
+            nl_all += (tt & 0xFFu) + ((tt >> 8) & 0xFFu) + ((tt >> 16) & 0xFFu);
+        }
+        nl_all = min(nl_all, (uint32_t)DS_NLMAX);
+        // ---- look-back: lines in front of this tile
+        unsigned long long base = 0;
+        if (tile > 0) {
+            long long look = (long long)tile - 1;
+            while (true) {
+                const long long i = look - lane;
+                while (__any_sync(0xffffffffu, (lb >> 62) == 0)) { if ((lb >> 62) == 0) lb = ld_volatile_u64(tile_state + i); }
+                const uint32_t inc = __ballot_sync(0xffffffffu, (lb >> 62) == 2ull);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+                base += warp_sum_u64(lane <= first_inc ? (lb & 0x3FFFFFFFFFFFFFFFull) : 0ull);
+                if (inc) break;
+                look -= 32;
+                lb = (look - lane >= 0) ? ld_volatile_u64(tile_state + (look - lane)) : (2ull << 62);
+            }
+            if (lane == 0) st_volatile_u64(tile_state + tile, (2ull << 62) | (base + (unsigned long long)tot_nl));
+        }
+        if (tile == n_tiles - 1 && lane == 0) {                             // lines of the whole stream: a last line without '\n' counts (deamSim reads it)
+            const bool open_end = buf[tlen - 1] != '\n';
+            stats[ST_TOTAL] = base + nl_tile + (open_end ? 1ull : 0ull);
+            stats[ST_ATTEMPTS] = open_end ? 1ull : 0ull;                    // (the record gets its newline: one more output byte)
+        }
+        __syncwarp();
+        // ---- the records that start in this tile.  The line that starts behind newline i of the tile has global index base + i + 1 (the
+        // line at the tile's first byte, when one starts there, has index base); ID lines are the even ones.
+        const bool starts_here = tile == 0 || __ldg(in + b0 - 1) == '\n';   // does a line start at the tile's first byte?
+        int i0 = (base & 1ull) ? 0 : -1;                                    // first newline index i with (base + i + 1) even
+        if (i0 == -1 && !starts_here) i0 = 1;
+        // records q = 0,1,..: newline index i = i0 + 2q, start s = nlpos[i] + 1 (or 0), ID line ends at newline i+1, sequence at newline i+2
+        int n_own = 0;
+        if ((int)nl_tile - 1 >= i0) n_own = ((int)nl_tile - 1 - i0) / 2 + 1;                     // records with i <= nl_tile - 1 ...
+        if (n_own > 0 && i0 + 2 * (n_own - 1) >= 0 && (int)nlpos[i0 + 2 * (n_own - 1)] + 1 >= tlen) n_own--;   // ... whose first byte is still inside the tile proper
+        int own_lo = DS_BUF, own_hi = 0;                                    // byte range of my records in the buffer
+        if (!fallback)
+        for (int q = lane; q < n_own; q += 32) {
+            const int i = i0 + 2 * q;
+            const int s = i < 0 ? 0 : (int)nlpos[i] + 1;
+            int e1, e2; bool closed = true;
+            if ((uint32_t)(i + 1) < nl_all) e1 = nlpos[i + 1]; else { e1 = blen; closed = false; }
+            if ((uint32_t)(i + 2) < nl_all) e2 = nlpos[i + 2];
+            else if (closed && b0 + (uint64_t)blen == n) e2 = blen;                              // the stream's last line has no newline
+            else { e2 = blen; closed = false; }
+            if (!closed) { fallback = true; break; }
+            if (e2 >= DS_BUF && !(b0 + (uint64_t)blen == n)) { fallback = true; break; }
+            if (buf[s] != '>' || e1 <= s) my_err |= ERRF_PARSE;                                  // FastQParser: a record starts with '>' (deamSim.cpp:1288)
+            const int ss = e1 + 1, L = e2 - ss;
+            // upper-case the sequence: head bytes up to a word boundary, whole words, tail bytes
+            int p = ss;
+            for (; p < e2 && (p & 3); p++) buf[p] = upper(buf[p]);
+            for (; p + 4 <= e2; p += 4) *(uint32_t*)(buf + p) = upper4(*(const uint32_t*)(buf + p));
+            for (; p < e2; p++) buf[p] = upper(buf[p]);
+            if (e2 < DS_BUF + 16) buf[e2] = '\n';
+            if (has_damage && L > 0) {
+                const uint64_t id = first_id + ((base + (unsigned long long)(i + 1)) >> 1);
+                SeqAsciiSmem S; S.p = buf + ss;
+                if (D.mode == 1) matrix_events<7, false>(key, D, D.term, D.acc, S, L, id);
+                else { const BriggsHdr B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM)); briggs_events<7>(key, D, B, S, L, id); }
+            }
+            own_lo = min(own_lo, s); own_hi = max(own_hi, e2 + 1);
+        }
+        fallback = __any_sync(0xffffffffu, fallback);
+        if (fallback) { my_err |= ERRF_FALLBACK; continue; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { own_lo = min(own_lo, __shfl_xor_sync(0xffffffffu, own_lo, o)); own_hi = max(own_hi, __shfl_xor_sync(0xffffffffu, own_hi, o)); }
+        __syncwarp();
+        // ---- store [own_lo, own_hi) at the input's own offsets (16-byte stores for the aligned body)
+        if (own_hi > own_lo) {
+            uint8_t* const gal = out + b0;
+            const int c_lo = (own_lo + 15) >> 4, c_hi = own_hi >> 4;
+            for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(buf + 16 * c));
+            const int t = lane < 16 ? own_lo + lane : 16 * max(c_hi, c_lo) + (lane - 16);
+            if (lane < 16 ? t < min(16 * c_lo, own_hi) : t < own_hi) gal[t] = buf[t];
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_err |= __shfl_xor_sync(0xffffffffu, my_err, o);
+    if (lane == 0 && my_err) atomicOr(stats + ST_ERR, (unsigned long long)my_err);
+}
+cudaError_t launch_deam_stream(const uint8_t* in, uint64_t n, uint8_t* out, const DamageDev& D, int has_damage, Key key, uint64_t first_id,
+                               unsigned long long* tile_state, unsigned int* ticket, unsigned long long* stats, uint32_t n_tiles, int sm_count, cudaStream_t st) {
+    if (n_tiles == 0) return cudaSuccess;
+    const int smem_bytes = DS_WARPS * DS_WARP_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(k_deam_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)min((uint64_t)sm_count, ((uint64_t)n_tiles + DS_WARPS - 1) / DS_WARPS);
+    k_deam_stream<<<grid, DS_WARPS * 32, smem_bytes, st>>>(in, n, out, D, has_damage, key, first_id, tile_state, ticket, stats, n_tiles);
+    return cudaGetLastError();
+}
+int deam_stream_tile_bytes() { return DS_TILE; }
+
 // ---- deamSim -name: "_DEAM:p1,p2,..." appended to the ID of every damaged record (deamSim.cpp:2029-2037).
 // Position lists follow the reference's push order: matrix: i ascending, +(i+1) in the 5' half, -(len-i) in the 3' half
 // (:1857,1919); Briggs: +(i+1) (:1489-1589); single/double: all pass-1 hits +(i+1), then all pass-2 hits -(len-i) (:1949-1994).

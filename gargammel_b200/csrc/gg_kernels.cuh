@@ -107,7 +107,7 @@ struct FusedParams {
 #define GG_FUSED_MAXT 1024     // launch bound of k_fused: 32 warps, 64 registers
 #endif
 enum { ST_TOTAL = 0, ST_ATTEMPTS = 1, ST_GATHER = 2, ST_ERR = 3, ST_N = 8 };
-enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4 };
+enum { ERRF_GIVEUP = 1, ERRF_OVERFLOW = 2, ERRF_PARSE = 4, ERRF_FALLBACK = 8 };
 
 
 // ---- launchers (gg_kernels.cu) ----
@@ -152,6 +152,10 @@ cudaError_t launch_fill_newlines(const uint8_t* in, uint64_t n, const unsigned l
 cudaError_t launch_exclusive_scan(unsigned long long* data, uint64_t n, unsigned long long* scratch, unsigned long long* total, cudaStream_t st);
 cudaError_t launch_deam_records(const RecStream& R, uint8_t* out, const ggd::DamageDev& D, int has_damage, ggd::Key key,
                                 uint64_t first_id, unsigned long long* stats, cudaStream_t st);
+// single-pass stand-alone deamSim (no record index, no host round trip); ERRF_FALLBACK in stats[ST_ERR] = take the general path instead
+cudaError_t launch_deam_stream(const uint8_t* in, uint64_t n, uint8_t* out, const ggd::DamageDev& D, int has_damage, ggd::Key key, uint64_t first_id,
+                               unsigned long long* tile_state, unsigned int* ticket, unsigned long long* stats /* [ST_TOTAL] = lines */, uint32_t n_tiles, int sm_count, cudaStream_t st);
+int deam_stream_tile_bytes();
 cudaError_t launch_deam_name_sizes(const RecStream& R, const ggd::DamageDev& D, ggd::Key key, uint64_t first_id, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
 cudaError_t launch_deam_name_records(const RecStream& R, const unsigned long long* out_off, uint8_t* out, const ggd::DamageDev& D, ggd::Key key, uint64_t first_id, cudaStream_t st);
 cudaError_t launch_adpt_sizes(const RecStream& R, int emit, Adapters ad, AdptNaming nm, unsigned long long* sizes, unsigned long long* stats, cudaStream_t st);
