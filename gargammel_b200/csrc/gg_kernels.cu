@@ -1093,6 +1093,7 @@ __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t
 constexpr int DS_TILE = 4096, DS_TAIL = 1536, DS_BUF = DS_TILE + DS_TAIL, DS_NLMAX = 320;      // at most 255 lines per tile on this path, plus the tail's
 constexpr int DS_WARP_BYTES = DS_BUF + 16 + 2 * DS_NLMAX + 32;
 constexpr int DS_WARPS = 32;
+constexpr int DS_TAB_BYTES = 16384;      // CTA-shared copy of the matrix tables (acceptance rows, then terminal rows) when they fit
 
 // exact per-byte "== '\n'" flags of a word: 0x80 in every matching byte
 __device__ __forceinline__ uint32_t nl_flags(uint32_t x) {
@@ -1123,6 +1124,15 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
     uint8_t* const buf = smem + (size_t)warp * DS_WARP_BYTES;               // tile bytes at their global alignment (tiles start at multiples of 4096)
     uint16_t* const nlpos = (uint16_t*)(buf + DS_BUF + 16);
     uint32_t my_err = 0;
+    // matrix tables: global -> shared, once per CTA (L1 is small at this carve-out and the record bytes stream through it)
+    const int n_acc = 4 * (D.rows5 + D.rows3 + 2), n_term = 4 * (D.n5t + D.n3t);
+    const bool tab_sm = has_damage && D.mode == 1 && (n_acc + n_term) * 16 <= DS_TAB_BYTES;
+    uint4* const s_tab = (uint4*)(smem + (size_t)DS_WARPS * DS_WARP_BYTES);
+    if (tab_sm) {
+        for (int q = threadIdx.x; q < n_acc; q += blockDim.x) s_tab[q] = __ldg(D.acc + q);
+        for (int q = threadIdx.x; q < n_term; q += blockDim.x) s_tab[n_acc + q] = __ldg(D.term + q);
+    }
+    __syncthreads();
     while (true) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(ticket, 1u);
@@ -1131,26 +1141,29 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
         const uint64_t b0 = (uint64_t)tile * DS_TILE;
         const int tlen = (int)min((uint64_t)DS_TILE, n - b0);              // bytes of the tile proper
         const int blen = (int)min((uint64_t)DS_BUF, n - b0);               // bytes in the buffer (tile + tail)
+        // the tile this warp will most likely take next (tickets sweep the stream in order): pull it into L2 now, one line per lane
+        { const uint64_t pf = b0 + (uint64_t)gridDim.x * DS_WARPS * DS_TILE + 128ull * lane; if (pf < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(in + pf)); }
+        const uint8_t prev_byte = tile == 0 ? (uint8_t)'\n' : __ldg(in + b0 - 1);               // does a line start at the tile's first byte?  (loaded with the tile)
         // ---- load: 16-byte chunks, chunk c = lane + 32 k; newline flags of the chunks are kept for the counting below
         uint32_t cnt_lo = 0, cnt_hi = 0;                                    // newline counts of my chunks k = 0..3 / 4..7 (tile proper), 8 bits each
-        uint32_t msk[11];                                                   // 16-bit newline masks of my chunks (bit j = byte j)
+        uint32_t msk[11];                                                   // newline masks of my chunks: bit 8 j + q = byte j of word q, i.e. position 4 q + j of the chunk
 #pragma unroll
         for (int k = 0; k < 11; k++) {
             const int c = lane + 32 * k;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (16 * c < blen) v = __ldg((const uint4*)(in + b0) + c);      // (the input buffer has 16 bytes of slack behind n)
             *(uint4*)(buf + 16 * c) = v;
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t m16 = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t f = nl_flags(w[q]);                          // 0x80 per newline byte -> 4 mask bits
-                m16 |= (((f >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * q);  // gather bits 0,8,16,24 into a nibble
+            uint32_t f0 = nl_flags(v.x), f1 = nl_flags(v.y), f2 = nl_flags(v.z), f3 = nl_flags(v.w);   // 0x80 per newline byte
+            if (16 * c + 16 > blen) {                                       // the stream's last chunk: bytes behind the end are not data
+                const int valid = max(0, blen - 16 * c);
+                f0 &= valid >= 4 ? 0xFFFFFFFFu : (1u << (8 * max(valid, 0))) - 1u;
+                f1 &= valid >= 8 ? 0xFFFFFFFFu : valid <= 4 ? 0u : (1u << (8 * (valid - 4))) - 1u;
+                f2 &= valid >= 12 ? 0xFFFFFFFFu : valid <= 8 ? 0u : (1u << (8 * (valid - 8))) - 1u;
+                f3 &= valid >= 16 ? 0xFFFFFFFFu : valid <= 12 ? 0u : (1u << (8 * (valid - 12))) - 1u;
             }
-            const int valid = min(16, max(0, blen - 16 * c));               // bytes of the chunk inside the stream
-            m16 &= (1u << valid) - 1u;
-            msk[k] = m16;
-            if (k < 8) { const uint32_t pc = (uint32_t)__popc(16 * c < tlen ? (m16 & ((1u << min(16, tlen - 16 * c)) - 1u)) : 0u); if (k < 4) cnt_lo |= pc << (8 * k); else cnt_hi |= pc << (8 * (k - 4)); }
+            const uint32_t m = (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
+            msk[k] = m;
+            if (k < 8) { const uint32_t pc = (uint32_t)__popc(m); if (k < 4) cnt_lo |= pc << (8 * k); else cnt_hi |= pc << (8 * (k - 4)); }   // (behind the last tile's end the chunks are empty: tile proper == valid bytes)
         }
         // ---- ranks: newlines are ordered by position = by (k, lane); exclusive prefix of the counts in that order.  The 8-bit fields of
         // the packed scans cannot overflow when the tile has at most 255 newlines; a tile with more falls back.
@@ -1179,9 +1192,14 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int c = lane + 32 * k;
-                uint32_t m16 = 16 * c < tlen ? (msk[k] & ((1u << min(16, tlen - 16 * c)) - 1u)) : 0u;
-                uint32_t r = kbase[k] + (((k < 4 ? inc_lo : inc_hi) >> (8 * (k & 3))) & 0xFFu) - (uint32_t)__popc(m16);
-                while (m16) { const int b = __ffs(m16) - 1; nlpos[r++] = (uint16_t)(16 * c + b); m16 &= m16 - 1u; }
+                uint32_t m = msk[k];
+                uint32_t r = kbase[k] + (((k < 4 ? inc_lo : inc_hi) >> (8 * (k & 3))) & 0xFFu) - (uint32_t)__popc(m);
+                // positions in ascending order: byte j of word q sits at bit 8 j + q, so walk q = 0..3 and, inside, j upwards
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t mq = (m >> q) & 0x01010101u;
+                    while (mq) { const int b = __ffs(mq) - 1; nlpos[r++] = (uint16_t)(16 * c + 4 * q + (b >> 3)); mq &= mq - 1u; }
+                }
             }
         }
         // tail (chunks 256..351): at most 48 positions are kept (two are needed per record that crosses the tile's end)
@@ -1198,9 +1216,13 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
             if (!fallback) {
 #pragma unroll
                 for (int k = 8; k < 11; k++) {
-                    uint32_t m16 = msk[k];
-                    uint32_t r = nl_tile + tb + ((ti >> (8 * (k - 8))) & 0xFFu) - (uint32_t)__popc(m16);
-                    while (m16) { const int b = __ffs(m16) - 1; if (r < (uint32_t)DS_NLMAX) nlpos[r] = (uint16_t)(16 * (lane + 32 * k) + b); r++; m16 &= m16 - 1u; }
+                    const uint32_t m = msk[k];
+                    uint32_t r = nl_tile + tb + ((ti >> (8 * (k - 8))) & 0xFFu) - (uint32_t)__popc(m);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t mq = (m >> q) & 0x01010101u;
+                        while (mq) { const int b = __ffs(mq) - 1; if (r < (uint32_t)DS_NLMAX) nlpos[r] = (uint16_t)(16 * (lane + 32 * k) + 4 * q + (b >> 3)); r++; mq &= mq - 1u; }
+                    }
                     tb += (tt >> (8 * (k - 8))) & 0xFFu;
                 }
             }
@@ -1231,7 +1253,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
         __syncwarp();
         // ---- the records that start in this tile.  The line that starts behind newline i of the tile has global index base + i + 1 (the
         // line at the tile's first byte, when one starts there, has index base); ID lines are the even ones.
-        const bool starts_here = tile == 0 || __ldg(in + b0 - 1) == '\n';   // does a line start at the tile's first byte?
+        const bool starts_here = prev_byte == '\n';
         int i0 = (base & 1ull) ? 0 : -1;                                    // first newline index i with (base + i + 1) even
         if (i0 == -1 && !starts_here) i0 = 1;
         // records q = 0,1,..: newline index i = i0 + 2q, start s = nlpos[i] + 1 (or 0), ID line ends at newline i+1, sequence at newline i+2
@@ -1252,17 +1274,34 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
             if (e2 >= DS_BUF && !(b0 + (uint64_t)blen == n)) { fallback = true; break; }
             if (buf[s] != '>' || e1 <= s) my_err |= ERRF_PARSE;                                  // FastQParser: a record starts with '>' (deamSim.cpp:1288)
             const int ss = e1 + 1, L = e2 - ss;
-            // upper-case the sequence: head bytes up to a word boundary, whole words, tail bytes
-            int p = ss;
-            for (; p < e2 && (p & 3); p++) buf[p] = upper(buf[p]);
-            for (; p + 4 <= e2; p += 4) *(uint32_t*)(buf + p) = upper4(*(const uint32_t*)(buf + p));
-            for (; p < e2; p++) buf[p] = upper(buf[p]);
+            // upper-case the sequence (deamSim.cpp:1319-1321).  A, C, G, T, N have bit 5 clear: records without any byte that has it set
+            // (everything fragSim writes) are left alone after one OR over their words
+            uint32_t any;
+            {
+                const int pa = ss & ~3, pe = e2 & ~3;                                            // the words that hold the first base / the byte behind the last
+                const uint32_t head = 0xFFFFFFFFu << (8 * (ss & 3)), tail = (1u << (8 * (e2 & 3))) - 1u;   // bytes of those words that belong to the sequence
+                if (pa == pe) any = *(const uint32_t*)(buf + pa) & head & tail;
+                else {
+                    any = *(const uint32_t*)(buf + pa) & head;
+#pragma unroll 2
+                    for (int p = pa + 4; p < pe; p += 4) any |= *(const uint32_t*)(buf + p);
+                    any |= *(const uint32_t*)(buf + pe) & tail;
+                }
+            }
+            if (any & 0x20202020u) {
+                int p = ss;
+                for (; p < e2 && (p & 3); p++) buf[p] = upper(buf[p]);
+                for (; p + 4 <= e2; p += 4) *(uint32_t*)(buf + p) = upper4(*(const uint32_t*)(buf + p));
+                for (; p < e2; p++) buf[p] = upper(buf[p]);
+            }
             if (e2 < DS_BUF + 16) buf[e2] = '\n';
             if (has_damage && L > 0) {
                 const uint64_t id = first_id + ((base + (unsigned long long)(i + 1)) >> 1);
                 SeqAsciiSmem S; S.p = buf + ss;
-                if (D.mode == 1) matrix_events<7, false>(key, D, D.term, D.acc, S, L, id);
-                else { const BriggsHdr B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM)); briggs_events<7>(key, D, B, S, L, id); }
+                if (D.mode == 1) {
+                    if (tab_sm) matrix_events<7, true>(key, D, s_tab + n_acc, s_tab, S, L, id);
+                    else matrix_events<7, false>(key, D, D.term, D.acc, S, L, id);
+                } else { const BriggsHdr B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM)); briggs_events<7>(key, D, B, S, L, id); }
             }
             own_lo = min(own_lo, s); own_hi = max(own_hi, e2 + 1);
         }
@@ -1288,7 +1327,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
 cudaError_t launch_deam_stream(const uint8_t* in, uint64_t n, uint8_t* out, const DamageDev& D, int has_damage, Key key, uint64_t first_id,
                                unsigned long long* tile_state, unsigned int* ticket, unsigned long long* stats, uint32_t n_tiles, int sm_count, cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
-    const int smem_bytes = DS_WARPS * DS_WARP_BYTES;
+    const int smem_bytes = DS_WARPS * DS_WARP_BYTES + DS_TAB_BYTES;
     cudaError_t e = cudaFuncSetAttribute(k_deam_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)min((uint64_t)sm_count, ((uint64_t)n_tiles + DS_WARPS - 1) / DS_WARPS);
