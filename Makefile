@@ -15,7 +15,7 @@ $(LIB): $(CSRC)/gg_api.cu $(CSRC)/gg_kernels.cu $(CSRC)/gg_host.cpp $(CSRC)/gg_k
 
 bin/%: $(CSRC)/cli_%.cpp $(CSRC)/cli_common.h $(CSRC)/gg_host.h include/gargammel_b200.h $(LIB)
 	@mkdir -p bin
-	$(CXX) -std=c++11 -O2 -Wall -o $@ $< -Lgargammel_b200 -lgargammel_b200 -Wl,-rpath,'$$ORIGIN/../gargammel_b200' -lz
+	$(CXX) -std=c++11 -O2 -Wall -o $@ $< -Lgargammel_b200 -lgargammel_b200 -Wl,-rpath,'$$ORIGIN/../gargammel_b200' -lz -lpthread
 
 bin/gargammel-b200: $(CSRC)/cli_gargammel.cpp $(CSRC)/cli_common.h $(CSRC)/gg_host.h include/gargammel_b200.h $(LIB)
 	@mkdir -p bin

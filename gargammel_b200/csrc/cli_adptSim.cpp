@@ -37,11 +37,7 @@ int main(int argc, char** argv) {
     if (open_ctx(seed, &ctx)) return 1;
     if (gg_tables_set_adapters(ctx, adF.c_str(), adS.c_str(), desiredLength) != GG_OK) return gg_fail(ctx, "adapters");
     if (gg_tables_set_adpt_naming(ctx, addInName ? 1 : 0, tag.c_str()) != GG_OK) return gg_fail(ctx, "-tag");
-    std::string err; std::vector<uint8_t> recs; uint64_t nrec = 0;
-    if (!read_records(infileName, recs, &nrec, err)) return die(err);
-    std::vector<Chunk> chunks = chunk_records(recs, 256u << 20);
-    std::vector<uint8_t> host;
-    // one pass per output file: -fr and -rr are two streams (adptSim.cpp:397-398)
+    // one sink per output file: -fr and -rr are two streams of the same input (adptSim.cpp:397-398)
     struct Pass { int emit; Sink sink; };
     std::vector<Pass> passes;
     if (fa) {
@@ -50,16 +46,27 @@ int main(int argc, char** argv) {
     } else if (arts || artp) {
         Pass p; p.emit = artp ? GG_EMIT_ARTP : GG_EMIT_ARTS; if (!p.sink.open_plain(outArt)) return die("Cannot write to file " + outArt); passes.push_back(p);
     } else { Pass p; p.emit = GG_EMIT_STDOUT4; p.sink.open_stdout(); passes.push_back(p); }
-    for (size_t k = 0; k < passes.size(); k++) {
-        uint64_t first = 0;
-        for (size_t c = 0; c < chunks.size(); c++) {
-            gg_out o;
-            if (gg_run_adpt(ctx, recs.data() + chunks[c].off, chunks[c].bytes, passes[k].emit, first, &o) != GG_OK) return gg_fail(ctx, "adptSim kernel");
-            if (!passes[k].sink.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
-            first += chunks[c].recs;
+    // reader thread -> GPU (this thread) -> writer thread: bounded memory whatever the input size, file I/O overlapped with the device work
+    uint64_t nrec = 0; std::string rerr; bool wfailed = false;
+    BoundedQueue<InChunk> qin(2); BoundedQueue<OutChunk> qout(2);
+    std::vector<Sink*> sinks; for (size_t k = 0; k < passes.size(); k++) sinks.push_back(&passes[k].sink);
+    std::thread rd(record_chunk_reader, infileName, STREAM_CHUNK_BYTES, &qin, &rerr, &nrec);
+    std::thread wr(chunk_writer, &qout, sinks, &wfailed);
+    uint64_t first = 0; InChunk c; std::string gerr;
+    while (qin.pop(c) && gerr.empty()) {
+        for (size_t k = 0; k < passes.size(); k++) {
+            gg_out o; OutChunk oc;
+            if (gg_run_adpt(ctx, c.bytes.data(), c.bytes.size(), passes[k].emit, first, &o) != GG_OK || !fetch_out(ctx, o, passes[k].sink, (int)k, &oc)) { gerr = std::string("adptSim kernel: ") + gg_last_error(ctx); qin.abort(); break; }
+            qout.push(std::move(oc));
         }
-        if (!passes[k].sink.close()) return die("Error: write failed");
+        first += c.recs;
+        if (wfailed) { qin.abort(); break; }
     }
+    qout.close(); rd.join(); wr.join();
+    if (!rerr.empty()) return die(rerr);
+    if (!gerr.empty()) return die("Error: " + gerr);
+    if (wfailed) return die("Error: write failed");
+    for (size_t k = 0; k < passes.size(); k++) if (!passes[k].sink.close()) return die("Error: write failed");
     gg_ctx_destroy(ctx);
     std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nrec << " sequences" << std::endl;   // adptSim.cpp:437
     return 0;

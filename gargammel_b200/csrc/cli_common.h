@@ -14,6 +14,10 @@
 #include <vector>
 #include <iostream>
 #include <unordered_map>
+#include <deque>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include "gg_host.h"
 
 namespace cli {
@@ -175,6 +179,86 @@ inline std::vector<Chunk> chunk_records(const std::vector<uint8_t>& s, size_t ma
     if (p > start) { Chunk c = {start, p - start, recs}; out.push_back(c); }
     return out;
 }
+
+// ---- streaming: deamSim / adptSim read their input chunk by chunk (bounded memory, whatever the file size) while the GPU works on the
+// previous chunk and a writer thread drains the one before: reader thread -> [chunks] -> main thread (H2D, kernel, D2H) -> [outputs] -> writer
+template <class T> struct BoundedQueue {
+    std::mutex m; std::condition_variable cv; std::deque<T> q; size_t cap; bool closed;
+    explicit BoundedQueue(size_t c) : cap(c), closed(false) {}
+    void push(T&& v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return q.size() < cap || closed; }); if (!closed) q.push_back(std::move(v)); cv.notify_all(); }
+    bool pop(T& v) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; v = std::move(q.front()); q.pop_front(); cv.notify_all(); return true; }
+    void close() { std::unique_lock<std::mutex> l(m); closed = true; cv.notify_all(); }
+    // close and drop what is queued (consumer gave up)
+    void abort() { std::unique_lock<std::mutex> l(m); closed = true; q.clear(); cv.notify_all(); }
+};
+struct InChunk { std::vector<uint8_t> bytes; uint64_t recs; InChunk() : recs(0) {} };
+struct OutChunk { std::vector<uint8_t> bytes; int sink; bool raw; OutChunk() : sink(0), raw(false) {} };   // raw: BGZF members made on the device, written as they are
+
+// Reads a FASTA record stream as the reference's FastQParser(file, true) does (gz or plain), normalises it to 2-line records
+// "ID\nSEQ\n" (multi-line sequences are joined, '\r' dropped) and hands it on in chunks of about `target` bytes cut on record boundaries.
+inline void record_chunk_reader(const std::string path, size_t target, BoundedQueue<InChunk>* q, std::string* err, uint64_t* n_rec) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) { *err = "Unable to open file " + path; q->close(); return; }
+    gzbuffer(f, 1 << 20);
+    std::vector<uint8_t> raw(8u << 20); std::vector<uint8_t> carry;            // carry: the unfinished last line of the previous block
+    InChunk cur; cur.bytes.reserve(target + (1u << 20));
+    bool have = false; *n_rec = 0;
+    auto line = [&](const uint8_t* p, size_t len) -> bool {
+        if (len && p[len - 1] == '\r') len--;
+        if (len && p[0] == '>') {
+            if (have) cur.bytes.push_back('\n');                                 // ends the previous record's (joined) sequence line
+            if (have && cur.bytes.size() >= target) { q->push(std::move(cur)); cur = InChunk(); cur.bytes.reserve(target + (1u << 20)); }
+            cur.bytes.insert(cur.bytes.end(), p, p + len); cur.bytes.push_back('\n');
+            have = true; cur.recs++; (*n_rec)++;
+        } else if (len) {
+            if (!have) { *err = "input does not start with a '>' record: " + path; return false; }
+            cur.bytes.insert(cur.bytes.end(), p, p + len);
+        }
+        return true;
+    };
+    bool ok = true;
+    while (ok) {
+        const int n = gzread(f, raw.data(), (unsigned)raw.size());
+        if (n < 0) { *err = "Read error in " + path; ok = false; break; }
+        if (n == 0) break;
+        size_t p = 0;
+        while (p < (size_t)n) {
+            const uint8_t* e = (const uint8_t*)memchr(raw.data() + p, '\n', (size_t)n - p);
+            if (!e) { carry.insert(carry.end(), raw.begin() + p, raw.begin() + n); break; }
+            const size_t le = (size_t)(e - raw.data());
+            if (!carry.empty()) { carry.insert(carry.end(), raw.begin() + p, raw.begin() + le); ok = line(carry.data(), carry.size()); carry.clear(); }
+            else ok = line(raw.data() + p, le - p);
+            if (!ok) break;
+            p = le + 1;
+        }
+    }
+    if (ok && !carry.empty()) ok = line(carry.data(), carry.size());
+    gzclose(f);
+    if (ok) { if (have) cur.bytes.push_back('\n'); if (!cur.bytes.empty()) q->push(std::move(cur)); }
+    q->close();
+}
+// the writer thread: drains the outputs in order into their sinks
+inline void chunk_writer(BoundedQueue<OutChunk>* q, std::vector<Sink*> sinks, bool* failed) {
+    OutChunk c;
+    while (q->pop(c)) {
+        Sink* s = sinks[c.sink];
+        const bool ok = c.raw ? fwrite(c.bytes.data(), 1, c.bytes.size(), s->f) == c.bytes.size() : s->write(c.bytes.data(), c.bytes.size());
+        if (!ok) { *failed = true; q->abort(); return; }
+    }
+}
+// a device-resident result -> an OutChunk: plain sinks get the bytes, gz sinks BGZF members compressed on the device
+inline bool fetch_out(gg_ctx* ctx, const gg_out& o, const Sink& sink, int sink_index, OutChunk* oc) {
+    size_t n = 0; oc->sink = sink_index;
+    if (!sink.bgzf || getenv("GG_HOST_BGZF")) {
+        oc->raw = false; oc->bytes.resize(o.bytes);
+        return gg_out_fetch(ctx, &o, oc->bytes.data(), oc->bytes.size(), &n) == GG_OK;
+    }
+    gg_out z;
+    if (gg_bgzf_dev(ctx, &o, &z) != GG_OK) return false;
+    oc->raw = true; oc->bytes.resize(z.bytes);
+    return gg_out_fetch(ctx, &z, oc->bytes.data(), oc->bytes.size(), &n) == GG_OK;
+}
+constexpr size_t STREAM_CHUNK_BYTES = 64u << 20;
 
 // fragSim -uniq (fragSim.cpp:119-135,1579-1584): every defline gets "_<k>" where k counts how often that exact defline has
 // been produced so far, then "_<tag>" if a tag was given.  Like the reference this is a host-side map over all deflines

@@ -89,19 +89,25 @@ int main(int argc, char** argv) {
         if (gg_tables_set_singledouble(ctx, 0, matrix == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mat");
     }
     gg_tables_set_deam_naming(ctx, putDeamInName ? 1 : 0);
-    std::vector<uint8_t> recs; uint64_t nrec = 0;
-    if (!read_records(inputFile, recs, &nrec, err)) return die(err);
     Sink out;
     if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); } else out.open_stdout();
-    std::vector<Chunk> chunks = chunk_records(recs, 512u << 20);
-    std::vector<uint8_t> host; uint64_t first = 0;
-    for (size_t c = 0; c < chunks.size(); c++) {
-        gg_out o;
-        if (gg_run_deam(ctx, recs.data() + chunks[c].off, chunks[c].bytes, 0, first, &o) != GG_OK) return gg_fail(ctx, "deamSim kernel");
-        if (!out.write_out(ctx, o, host)) return die(std::string("Error: write failed ") + gg_last_error(ctx));
-        first += chunks[c].recs;
+    // reader thread -> GPU (this thread) -> writer thread: bounded memory whatever the input size, file I/O overlapped with the device work
+    uint64_t nrec = 0; std::string rerr; bool wfailed = false;
+    BoundedQueue<InChunk> qin(2); BoundedQueue<OutChunk> qout(2);
+    std::thread rd(record_chunk_reader, inputFile, STREAM_CHUNK_BYTES, &qin, &rerr, &nrec);
+    std::thread wr(chunk_writer, &qout, std::vector<Sink*>(1, &out), &wfailed);
+    uint64_t first = 0; InChunk c; std::string gerr;
+    while (qin.pop(c)) {
+        gg_out o; OutChunk oc;
+        if (gg_run_deam(ctx, c.bytes.data(), c.bytes.size(), 0, first, &o) != GG_OK || !fetch_out(ctx, o, out, 0, &oc)) { gerr = std::string("deamSim kernel: ") + gg_last_error(ctx); qin.abort(); break; }
+        qout.push(std::move(oc));
+        first += c.recs;
+        if (wfailed) { qin.abort(); break; }
     }
-    if (!out.close()) return die("Error: write failed");
+    qout.close(); rd.join(); wr.join();
+    if (!rerr.empty()) return die(rerr);
+    if (!gerr.empty()) return die("Error: " + gerr);
+    if (wfailed || !out.close()) return die("Error: write failed");
     gg_ctx_destroy(ctx);
     std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nrec << " sequences" << std::endl;   // deamSim.cpp:2053
     return 0;

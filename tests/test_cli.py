@@ -426,3 +426,56 @@ def test_cli_deamsim_table_modes_match_oracle(workdir, tmp_path, oracle_mod):
         assert r.stdout != frags
     r = run([str(src / "deamSim"), "-v", "-mat", "single", str(tmp_path / "f.fa")])
     assert r.returncode == 1 and b"not supported" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_streams_large_and_untidy_inputs(tmp_path, oracle_mod):
+    """bin/deamSim and bin/adptSim read their input in chunks through a reader thread (bounded memory whatever the file size), normalise
+    what FastQParser accepts (multi-line sequences, CRLF, concatenated gzip members: gargammel.pl appends with >>) and keep the fragment ids
+    running across chunks."""
+    import gzip
+    import resource
+    seed = 12
+    s5, s3 = synth.golden_matrix("single-")
+    synth.write_matrix_dat(str(tmp_path / "m-"), s5, s3)
+    o = oracle_mod.OracleContext(seed); o.set_matrix(0, s5, s3); o.set_adapters(read_len=60)
+    # ---- untidy: wrapped sequence lines, CRLF, an empty sequence, two gzip members
+    rng = np.random.default_rng(3)
+    seqs = [synth._BASES[rng.integers(0, 4, int(n))].tobytes() for n in rng.integers(0, 300, 400)]
+    tidy = b"".join(b">u%d\n%s\n" % (i, s) for i, s in enumerate(seqs))
+    wrapped = b"".join(b">u%d\r\n" % i + b"".join(s[k:k + 37] + b"\r\n" for k in range(0, len(s), 37)) for i, s in enumerate(seqs))
+    half = wrapped.index(b">u200\r\n")
+    with open(str(tmp_path / "u.fa.gz"), "wb") as f:
+        f.write(gzip.compress(wrapped[:half]) + gzip.compress(wrapped[half:]))
+    r = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-matfile", str(tmp_path / "m-"), str(tmp_path / "u.fa.gz")])
+    assert r.returncode == 0, r.stderr
+    util.assert_same(r.stdout, o.run_deam(tidy, 0)[0], "bin/deamSim on wrapped CRLF gz members")
+    r = run([os.path.join(BIN, "adptSim"), "-l", "60", "-fr", str(tmp_path / "f.gz"), "-rr", str(tmp_path / "r.gz"), str(tmp_path / "u.fa.gz")])
+    assert r.returncode == 0, r.stderr
+    util.assert_same(gzip.open(str(tmp_path / "f.gz")).read(), o.run_adpt(tidy, api.EMIT_FR)[0], "bin/adptSim -fr")
+    util.assert_same(gzip.open(str(tmp_path / "r.gz")).read(), o.run_adpt(tidy, api.EMIT_RR)[0], "bin/adptSim -rr")
+    # ---- large: 2.1 GB of records through bin/deamSim with a resident set far below the input size
+    n, L = 30_000_000, 60
+    rec = np.empty((n, 1 + 8 + 1 + L + 1), dtype=np.uint8)
+    rec[:, 0] = ord(">"); rec[:, 9] = 10; rec[:, -1] = 10
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        rec[:, 8 - d] = 48 + (idx // 10 ** d) % 10
+    rec[:, 10:10 + L] = synth._BASES[np.random.default_rng(4).integers(0, 4, size=(n, L), dtype=np.uint8)]
+    big = str(tmp_path / "big.fa")
+    rec.tofile(big)
+    head = rec[:150_000].tobytes()
+    del rec, idx
+    before = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+    with open(str(tmp_path / "big.out"), "wb") as fo:
+        p = subprocess.run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-matfile", str(tmp_path / "m-"), big], stdout=fo, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr
+    assert b"wrote %d sequences" % n in p.stderr
+    peak_kb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+    assert os.path.getsize(str(tmp_path / "big.out")) == os.path.getsize(big)
+    assert peak_kb > before and peak_kb < 1_500_000, "resident set %d kB for a %.1f GB input" % (peak_kb, os.path.getsize(big) / 1e9)
+    with open(str(tmp_path / "big.out"), "rb") as f:
+        util.assert_same(f.read(len(head)), o.run_deam(head, 0)[0], "first records of the large run")
+        f.seek(-71 * 1000, 2); tail = f.read()
+    want_tail = open(big, "rb").read()[-71 * 1000:]
+    assert [l for l in tail.split(b"\n")[0::2]] == [l for l in want_tail.split(b"\n")[0::2]]           # same deflines at the end: nothing lost or reordered
