@@ -286,6 +286,14 @@ struct UniqSuffixer {
     }
 };
 
+// GG_PRINT_RSS=1: peak / current resident set of this process on stderr (the streaming CLIs promise a bounded one)
+inline void print_rss(const char* where) {
+    if (!getenv("GG_PRINT_RSS")) return;
+    FILE* f = fopen("/proc/self/status", "r"); if (!f) return;
+    char line[256];
+    while (fgets(line, sizeof line, f)) if (!strncmp(line, "VmHWM", 5) || !strncmp(line, "VmRSS", 5) || !strncmp(line, "RssAnon", 7) || !strncmp(line, "RssFile", 7) || !strncmp(line, "RssShmem", 8)) std::cerr << "[" << where << "] " << line;
+    fclose(f);
+}
 inline int gg_fail(gg_ctx* ctx, const char* what) {
     std::cerr << "Error: " << what << ": " << gg_last_error(ctx) << std::endl; return 1;
 }

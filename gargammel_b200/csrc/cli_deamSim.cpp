@@ -72,6 +72,7 @@ int main(int argc, char** argv) {
 
     gg_ctx* ctx = NULL;
     if (open_ctx(seed, &ctx)) return 1;
+    print_rss("context open");
     std::string err; ggh::Rates s5, s3;
     if (useBriggsss) { if (gg_tables_set_briggs_ss(ctx, 0, d, s5p, s3p, l5p, l3p) != GG_OK) return gg_fail(ctx, "-damagess"); }   // checked first, like :1337
     else if (useBriggs) { if (gg_tables_set_briggs(ctx, 0, v, l, d, s) != GG_OK) return gg_fail(ctx, "-damage"); }
@@ -105,6 +106,7 @@ int main(int argc, char** argv) {
         if (wfailed) { qin.abort(); break; }
     }
     qout.close(); rd.join(); wr.join();
+    print_rss("stream done");
     if (!rerr.empty()) return die(rerr);
     if (!gerr.empty()) return die("Error: " + gerr);
     if (wfailed || !out.close()) return die("Error: write failed");
