@@ -238,12 +238,12 @@ def bind_to_gpu_numa_node(local):
     does not cross the socket interconnect.  Returns a description for the bench line; harmless no-op when sysfs does not tell."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE, text=True).stdout.strip()
-            busid = out.lower()[4:] if out.lower().startswith("0000") and len(out) > 12 else out.lower()
+        pr = torch.cuda.get_device_properties(local)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            busid = "%04x:%02x:%02x.0" % (int(getattr(pr, "pci_domain_id", 0)), int(pr.pci_bus_id), int(pr.pci_device_id))
         else:
-            busid = str(bus)
+            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE, text=True).stdout.strip().lower()
+            busid = out[4:] if len(out) > 12 else out                    # 00000000:1b:00.0 -> 0000:1b:00.0
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % busid).read())
         if node < 0:
             return {"numa_node": None, "note": "single NUMA domain / not reported"}

@@ -18,6 +18,7 @@ done
 python - <<PY
 import json
 for l in open("gpurun_out/${TAG}_configs.jsonl"):
+    if not l.startswith("{"): continue
     d = json.loads(l); e = d.get("e2e", {})
     print("%-110s %8.3f G frag/s  frac %.3f  e2e %7.1f M  (dev bgzf %7.1f M)  cpu %s" % (d["config"]["workload"][:110], d["value"] / 1e9, d["roofline"]["frac"], e.get("value", 0) / 1e6,
           (e.get("with_device_bgzf", {}).get("value") or 0) / 1e6, (d.get("cpu_baseline") or {}).get("value")))
