@@ -408,6 +408,40 @@ def test_fused_circular_contig(oracle_mod, genomes, tmp_path, circ, sizes):
     g.close(); o.close()
 
 
+def test_fused_circ_end_coordinate_one_digit_longer(oracle_mod):
+    """A circular contig just short of a power of ten: the un-wrapped end coordinate start+length (fragSim.cpp:1489) takes one digit more
+    than the contig length, in the dialects that have no slack in their record bound (worst-case -l, fragSim / deamSim records)."""
+    rng = np.random.default_rng(77)
+    fa, fai = synth.fasta_bytes([("m1", synth.random_contig(rng, 9990, 0.0)), ("m2", synth.random_contig(rng, 300, 0.0))], 60)
+    g = api.Context(0, 5); o = oracle_mod.OracleContext(5)
+    for c in (g, o):
+        gid = c.upload_genome(fa, fai, circ=0)
+        c.set_sizes(api.SIZE_FIXED, fixed_len=60)
+        util.set_damage(c, 0, "briggs")
+        c.set_plan([api.Range(0, 40000, gid, 0, "")])
+    for emit in (api.EMIT_FRAG, api.EMIT_DEAM):
+        a, _ = g.run_fused(0, 40000, emit); b, _ = o.run_fused(0, 40000, emit)
+        util.assert_same(a, b, "--circ end digits emit=%d" % emit)
+    assert sum(1 for h, _ in util.records(a) if int(h.split(b":")[3]) >= 10000 and int(h.split(b":")[2]) < 10000) > 50
+
+
+def test_gc_bias_on_a_genome_without_gc_variation(oracle_mod):
+    """-gc on a genome whose probe windows all have the same GC content: stdev 0, the survival probability is NaN and "rP > NaN" is false in
+    the reference (fragSim.cpp:1524-1529): no fragment is ever killed (instead of every attempt being rejected)."""
+    unit = np.frombuffer(b"AC" * 5000, dtype=np.uint8).copy()          # every window of any even length is half C
+    fa, fai = synth.fasta_bytes([("flat", unit)], 60)
+    g = api.Context(0, 9); o = oracle_mod.OracleContext(9)
+    for c in (g, o):
+        gid = c.upload_genome(fa, fai)
+        c.set_sizes(api.SIZE_FIXED, fixed_len=40)
+        mean, sd = c.set_gcbias(0, gid, 0, 2.0)
+        assert sd == 0.0 and abs(mean - 0.5) < 1e-12
+        c.set_plan([api.Range(0, 2000, gid, -1, "x", -1, 0)])
+    a, ia = g.run_fused(0, 2000, api.EMIT_FRAG); b, ib = o.run_fused(0, 2000, api.EMIT_FRAG)
+    util.assert_same(a, b, "-gc with sd = 0")
+    assert ia.attempts == ib.attempts
+
+
 def test_fused_mixed_damage_slots(oracle_mod, genomes):
     """All five damage models side by side in one plan (the DMODE = any-mix kernel), incl. -damagess."""
     g, o, ids = _pair(oracle_mod, genomes, damage="briggs_ss")
