@@ -9,7 +9,7 @@ from collections import namedtuple
 EMIT_FRAG, EMIT_DEAM, EMIT_STDOUT4, EMIT_ARTS, EMIT_ARTP, EMIT_FR, EMIT_RR = range(7)
 SIZE_FIXED, SIZE_LIST, SIZE_FREQ = range(3)
 BGZF_EOF = bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
-DMG_NONE, DMG_MATRIX, DMG_BRIGGS, DMG_SINGLE, DMG_DOUBLE, DMG_BRIGGS_SS = range(6)
+DMG_NONE, DMG_MATRIX, DMG_BRIGGS, DMG_SINGLE, DMG_DOUBLE, DMG_BRIGGS_SS, DMG_METH = range(7)
 DEFAULT_ADAPTER_F = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"   # adptSim.cpp:28
 DEFAULT_ADAPTER_S = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"         # adptSim.cpp:29
 
@@ -162,6 +162,16 @@ class Context:
         a3, p3 = _darr(sub3)
         self._ck(self._f("tables_set_matrix")(self._h, C.c_int(slot), p5, C.c_int(a5.size // 12), p3, C.c_int(a3.size // 12),
                                               C.c_int(1 if clamp_last else 0)))
+
+    def set_case(self, keep_case=True):
+        """fragSim --case; call before upload_genome"""
+        self._ck(self._f("tables_set_case")(self._h, C.c_int(1 if keep_case else 0)))
+
+    def set_matrix_meth(self, slot, no5, no3, wi5, wi3, clamp_last=True):
+        """deamSim -matfilenonmeth (no5, no3) -matfilemeth (wi5, wi3)"""
+        a = [_darr(x) for x in (no5, no3, wi5, wi3)]
+        self._ck(self._f("tables_set_matrix_meth")(self._h, C.c_int(slot), a[0][1], C.c_int(a[0][0].size // 12), a[1][1], C.c_int(a[1][0].size // 12),
+                                                   a[2][1], C.c_int(a[2][0].size // 12), a[3][1], C.c_int(a[3][0].size // 12), C.c_int(1 if clamp_last else 0)))
 
     def set_singledouble(self, slot, protocol, sub5, sub3):
         a5, p5 = _darr(sub5)

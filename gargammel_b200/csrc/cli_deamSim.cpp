@@ -4,14 +4,14 @@
 using namespace cli;
 
 int main(int argc, char** argv) {
-    std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix;
+    std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix, matrixFileNoMeth, matrixFileWiMeth;
     bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false, putDeamInName = false;
     bool useBriggsss = false; double s5p = 0, s3p = 0, l5p = 0, l3p = 0;            // -damagess, deamSim.cpp:310-340
     double v = 0, l = 0, d = 0, s = 0; uint64_t seed = 0;
     const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds deamination according to a certain model (B200 build)\n\n" +
         "\t\t-o\t[fasta out]\t\t\tWrite fasta output as a zipped fasta\n\t\t-last\t\t\t\t\tdo not use the last matrix row beyond the matrix\n\t\t--seed\t[int]\n\n" +
         "\t\t-mapdamage  [mis.txt] [protocol]\n\t\t-profile  [prof file prefix]\n\t\t-matfile  [matrix file prefix]\n\t\t-mat      [single|double]\n\t\t-damage     [v,l,d,s]\n" +
-        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\tNot in this build: -b -u -matfilemeth -matfilenonmeth\n";
+        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\t\t-matfilenonmeth  [matrix file prefix]\tRead the matrix file of substitutions for non-methylated Cs\n\t\t-matfilemeth  [matrix file prefix]\tRead the matrix file of substitutions for methylated Cs\n\tNot in this build: -b -u\n";
     if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // deamSim.cpp:199-207
     for (int i = 1; i < argc - 1; i++) {                                            // deamSim.cpp:213-378
         const std::string a = argv[i];
@@ -57,16 +57,21 @@ int main(int argc, char** argv) {
         if (a == "-last") { lastRowMatrix = false; continue; }
         if (a == "-v") return unsupported(a, "the per-read log of deamSim.cpp:1458-1465,1602-1611 is not produced by this build");
         if (a == "-name") { putDeamInName = true; continue; }                        // deamSim.cpp:342-345
-        if (a == "-b" || a == "-u" || a == "-matfilemeth" || a == "-matfilenonmeth") return unsupported(a, "SURVEY.md 8f-3/8f-4");
+        if (a == "-matfilenonmeth") { matrixFileNoMeth = argv[++i]; continue; }      // deamSim.cpp:256-261
+        if (a == "-matfilemeth") { matrixFileWiMeth = argv[++i]; continue; }         // deamSim.cpp:263-268
+        if (a == "-b" || a == "-u") return unsupported(a, "SURVEY.md 8f-4");
         return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377
     }
     const bool mapd = !mapdamageFile.empty();
     if (useBriggs && (matrixSpecified || mapd)) return die("Error: cannot specify both a file and Briggs parameter model");        // :380-383
     if (useBriggsss && (matrixSpecified || mapd)) return die("Error: cannot specify both a file and Briggs parameter model");      // :385-388
     if (useBriggs && useBriggsss) return die("Error: cannot specify both a file and Briggs parameter model");                      // :390-393
-    if (!useBriggs && !useBriggsss && !matrixSpecified && matrixFile.empty() && !mapd && profFile.empty())
-        return die("Please specify the matrix to use or use the Briggs parameter model");                                          // :395-405
-    if (!profFile.empty() && !matrixFile.empty()) return die("Please specify damage profile or substitution matrix");              // :407-412
+    const bool noMeth = !matrixFileNoMeth.empty(), wiMeth = !matrixFileWiMeth.empty();
+    if (!useBriggs && !useBriggsss && !matrixSpecified && matrixFile.empty() && !mapd && profFile.empty() && !noMeth && !wiMeth)
+        return die("Please specify the matrix to use or use the Briggs parameter model");                                          // :394-405
+    if (!profFile.empty() && (!matrixFile.empty() || noMeth || wiMeth)) return die("Please specify damage profile or substitution matrix");   // :407-412
+    if (!matrixFile.empty() && noMeth && wiMeth) return die("Please specify matrix with/without methylation but not the overall matrix");     // :414-419
+    if (noMeth != wiMeth) return die("Please specify both the matrix with/without methylation, not just one");                     // :421-430
     if (!seedSpecified) seed = time_seed();
     const std::string inputFile = argv[argc - 1];                                   // deamSim.cpp:436
 
@@ -76,7 +81,15 @@ int main(int argc, char** argv) {
     std::string err; ggh::Rates s5, s3;
     if (useBriggsss) { if (gg_tables_set_briggs_ss(ctx, 0, d, s5p, s3p, l5p, l3p) != GG_OK) return gg_fail(ctx, "-damagess"); }   // checked first, like :1337
     else if (useBriggs) { if (gg_tables_set_briggs(ctx, 0, v, l, d, s) != GG_OK) return gg_fail(ctx, "-damage"); }
-    else if (mapd) {                                                                // deamSim.cpp:453-668
+    else if (noMeth) {                                                              // deamSim.cpp:673-954: <prefix>5.dat / <prefix>3.dat of each table
+        ggh::Rates m5, m3;
+        std::cerr << "Files deamination with methylation" << std::endl << matrixFileWiMeth << "5.dat" << std::endl << matrixFileWiMeth << "3.dat" << std::endl;      // :683-685
+        if (!ggh::load_matrix_dat(matrixFileWiMeth, m5, m3, err)) return die(err);
+        std::cerr << "Files deamination without methylation" << std::endl << matrixFileNoMeth << "5.dat" << std::endl << matrixFileNoMeth << "3.dat" << std::endl;   // :824-826
+        if (!ggh::load_matrix_dat(matrixFileNoMeth, s5, s3, err)) return die(err);
+        if (gg_tables_set_matrix_meth(ctx, 0, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12), m5.data(), (int)(m5.size() / 12), m3.data(), (int)(m3.size() / 12), lastRowMatrix) != GG_OK)
+            return gg_fail(ctx, "-matfilemeth/-matfilenonmeth");
+    } else if (mapd) {                                                              // deamSim.cpp:453-668
         if (!ggh::load_mapdamage(mapdamageFile, s5, s3, err)) return die(err);
         if (gg_tables_set_singledouble(ctx, 0, mapdamageProtocol == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mapdamage");
     } else if (!profFile.empty()) {                                                 // :956-1094

@@ -10,6 +10,7 @@ int main(int argc, char** argv) {
     bool uniqTags = false, tagb = false, gcBiasB = false; double gcBias = 0;
     std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
+    bool keepCase = false;                                                          // fragSim.cpp:387 (uppercase = true)
     bool circ = false; std::string circName;                                        // fragSim.cpp:388-389
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
         " aDNA fragments according to a certain distribution (B200 build)\n\n " + argv[0] + " [options]  [chromosome fasta] \n\n" +
@@ -23,7 +24,7 @@ int main(int argc, char** argv) {
         "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
         "\t\t-uniq\t\t\t\t\tMake the fragment names unique by appending a counter (host-side pass, like the reference)\n" +
         "\t\t--circ\t[REF NAME]\t\t\tAssume [REF NAME] is circular\n" +
-        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\tNot in this build: --case --fq --trim5p -b -u\n";
+        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\t\t--case\t\t\t\t\tDo not set the sequence to upper-case (default: uppercase the seqs.)\n\tNot in this build: --fq --trim5p -b -u\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -47,7 +48,8 @@ int main(int argc, char** argv) {
         if (a == "--circ") { circ = true; circName = argv[++i]; continue; }             // fragSim.cpp:553-557
         if (a == "--trim5p" || a == "-b")
             return unsupported(a, "SURVEY.md 8f-3");
-        if (a == "--case" || a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-3");
+        if (a == "--case") { keepCase = true; continue; }                              // fragSim.cpp:548-551
+        if (a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-4");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
     }
     if (specifiedLength && sizeFragments > maxLen)                                   // fragSim.cpp:638-643
@@ -85,6 +87,7 @@ int main(int argc, char** argv) {
     gg_ctx* ctx = NULL;
     if (open_ctx(seed, &ctx)) return 1;
     int gid = -1;
+    if (keepCase) gg_tables_set_case(ctx, 1);                                       // the upload then keeps a case bit per base
     if (ggh::upload_genome(ctx, G, &gid, circChr) != GG_OK) return gg_fail(ctx, "genome upload");
     std::vector<uint8_t>().swap(G.bytes);
     const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || specifiedLoc) ? GG_SIZE_FREQ : GG_SIZE_FIXED;

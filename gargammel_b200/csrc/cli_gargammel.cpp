@@ -79,10 +79,11 @@ int main(int argc, char** argv) {
     std::string ss = "HS25", art_given; int qs = 0, qs2 = 0;                           // ART options of gargammel.pl:460-462 (defaults :268-270)
     bool se = false, keep = false, n_given = false, seedSpecified = false, lognorm = false; uint64_t seed = 0; double loc = 0, scale = 0;
     DamageSpec dAll, dE, dB, dC;
+    bool methyl = false; std::string matNoMeth, matWiMeth;                          // --methyl -matfilenonmeth -matfilemeth (gargammel.pl:431-432,457)
     std::string misE, misB, misC; int distmis = 1;                                  // --misince/--misincb/--misincc/--distmis (gargammel.pl:300-303)
     const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
         "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
-        "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t-ss [system] -qs [int] -qs2 [int]\tART sequencing system and quality shifts\n" +
+        "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t--methyl -matfilenonmeth [prefix] -matfilemeth [prefix]\tlower-case c/g in the genomes are methylated cytosines\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t-ss [system] -qs [int] -qs2 [int]\tART sequencing system and quality shifts\n" +
         "\t--art [path]\tart_illumina to run on <prefix>_a.fa (default: ../art_src_MountRainier/art_illumina next to this binary, then $PATH)\n\t--noart\t\tstop after <prefix>_a.fa\n" +
         "\t--mock\t\tprint what would be run, run nothing\n\t--seed [int]\t--gpus [N]\t--keep\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }
@@ -124,7 +125,9 @@ int main(int argc, char** argv) {
         if (a == "-qs2") { qs2 = (int)to_ll(next(), "-qs2"); continue; }
         if (a == "-art") { art_given = next(); continue; }
         if (a == "-noart") { no_art = true; continue; }
-        if (a == "-methyl" || a == "-matfilenonmeth" || a == "-matfilemeth") return unsupported(a, "SURVEY.md 8f-4");
+        if (a == "-methyl") { methyl = true; continue; }                           // gargammel.pl:320-322,461
+        if (a == "-matfilenonmeth") { matNoMeth = next(); continue; }
+        if (a == "-matfilemeth") { matWiMeth = next(); continue; }
         return die("Unknown option: " + a);
     }
     if (coverage >= 0 && n_given) return die("Must use the -c or -n but not both");                    // gargammel.pl:753-756
@@ -132,6 +135,12 @@ int main(int argc, char** argv) {
     if (c3.size() != 3) return die("the --comp option must have 3 comma-delimited fields, found " + std::to_string(c3.size()));   // :748-751
     compB = to_d(c3[0].c_str(), "--comp"); compC = to_d(c3[1].c_str(), "--comp"); compE = to_d(c3[2].c_str(), "--comp");
     if (coverage >= 0 && compE == 0) return die("Cannot use the endogenous coverage -c and not specify some level of endogenous content.");   // :778-780
+    if ((!matNoMeth.empty() || !matWiMeth.empty()) && !methyl) return die("Must define --methyl for the fragment selection");            // gargammel.pl:650-660
+    if (matNoMeth.empty() != matWiMeth.empty()) return die("Must defined matrix file for both methylated and non-methylated");           // :662-668 (sic)
+    if (!matNoMeth.empty() && (dE.any() || dB.any() || dC.any() || dAll.any()))
+        return die("Cannot specify as of yet, different deamination profiles for the endogenous, bacterial, contaminant and methylation deamination");   // :670-678
+    if (methyl && matNoMeth.empty()) return die("Must define --matfilenonmeth if methylation is used");                                  // :691-695
+    if (methyl && matWiMeth.empty()) return die("Must define --matfilemeth if methylation is used");                                     // :697-701
     if (dAll.any()) {                                                              // -matfile/-damage/-mapdamage => endogenous + bacterial only (gargammel.pl:619-648)
         if (dE.any() || dB.any() || dC.any()) return die("Specify either patterns for endogenous and bacterial using either -matfile or -damage but do not specify other parameters");
         dE = dAll; dB = dAll;
@@ -204,6 +213,7 @@ int main(int argc, char** argv) {
         if (s.kind == 'e') { it.count = (size_t)s.idx < ap.endo.size() ? ap.endo[s.idx] : 0; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0; }
         if (s.kind == 'b') { it.count = (size_t)s.idx < ap.bact.size() ? ap.bact[s.idx] : 0; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; it.comp = misB.empty() ? -1 : 1; }
         if (s.kind == 'c') { it.count = (size_t)s.idx < ap.cont.size() ? ap.cont[s.idx] : 0; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; it.comp = misC.empty() ? -1 : 2; }
+        if (methyl) it.slot = 0;                                                    // every source goes through deamSim with the two tables (gargammel.pl:1698-1811)
         if (it.count) items.push_back(it);
     }
     if (gpus < 1) gpus = 1;
@@ -244,6 +254,7 @@ int main(int argc, char** argv) {
     auto setup = [&](int r, gg_ctx* ctx) -> bool {
         auto fail = [&](const char* what) -> bool { shard_err[r] = std::string(what) + ": " + gg_last_error(ctx); return false; };
         std::vector<gg_range> plan; uint64_t first = 0;
+        if (methyl) gg_tables_set_case(ctx, 1);                                     // fragSim --case for every source (gargammel.pl:1486,1526,1561,1605,1653)
         for (size_t k = 0; k < items.size(); k++) {
             int gid = -1;
             if (ggh::upload_genome(ctx, srcs[items[k].src].g, &gid) != GG_OK) return fail("genome upload");
@@ -253,6 +264,12 @@ int main(int argc, char** argv) {
         const int mode = !sizeList.empty() ? GG_SIZE_LIST : (!sizeFreq.empty() || lognorm) ? GG_SIZE_FREQ : GG_SIZE_FIXED;
         if (gg_tables_set_sizes(ctx, mode, lens.data(), cum.data(), (int)lens.size(), fraglength, minsize, maxsize) != GG_OK) return fail("size tables");
         if ((dE.any() && set_damage(ctx, 0, dE)) || (dB.any() && set_damage(ctx, 1, dB)) || (dC.any() && set_damage(ctx, 2, dC))) return false;
+        if (methyl) {
+            ggh::Rates n5, n3, w5, w3; std::string e2;
+            if (!ggh::load_matrix_dat(matNoMeth, n5, n3, e2) || !ggh::load_matrix_dat(matWiMeth, w5, w3, e2)) { shard_err[r] = e2; return false; }
+            if (gg_tables_set_matrix_meth(ctx, 0, n5.data(), (int)(n5.size() / 12), n3.data(), (int)(n3.size() / 12), w5.data(), (int)(w5.size() / 12), w3.data(), (int)(w3.size() / 12), 1) != GG_OK)
+                return fail("-matfilemeth/-matfilenonmeth");
+        }
         const std::string* mis[3] = {&misE, &misB, &misC};
         for (int m = 0; m < 3; m++) if (!mis[m]->empty()) {                        // fragSim --comp F --dist D per source (gargammel.pl:1492-1495,1615-1618,1664-1667)
             ggh::CompTables ct; std::string e2;

@@ -41,6 +41,7 @@ struct HostGenome {
     std::vector<int> fai2sorted;
     uint64_t G, n_units;
     uint32_t* d_seq2; uint32_t* d_nmask; size_t seq2_bytes, nmask_bytes;
+    uint32_t* d_cmask; size_t cmask_bytes;                       // fragSim --case: 1 bit per base, 1 = lower-case (null without --case)
     int first_contig;
     int circ_sorted; uint32_t wrap_s0; uint64_t wrap_gbase;     // --circ: index of the circular contig in `contigs` (-1 none) + its wrap image
 };
@@ -107,6 +108,7 @@ struct gg_ctx {
     int n_contigs_total, names_bytes;
     // sizes
     int size_mode, fixed_len, minlen, maxlen, norev;
+    int keep_case;                                         // fragSim --case
     std::vector<int32_t> size_len; std::vector<uint32_t> size_thr;
     DBuf d_size_len, d_size_thr;
     bool sizes_set;
@@ -127,6 +129,8 @@ struct gg_ctx {
     std::vector<std::pair<void*, size_t> > pool;     // device blocks of cleared genomes, reused by the next uploads
     DBuf d_tmp_fa, d_tmp_desc;                       // upload staging (raw FASTA bytes, contig descriptors)
     DBuf d_out, d_out2, d_tile_state, d_ticket_stats, d_in, d_nl, d_scan, d_sizes, d_flush;
+    DBuf d_case, d_cmask_ptrs;                       // fragSim --case: per-fragment descriptors of a run, case-mask pointer per genome
+    DBuf d_chain_a, d_chain_b; DBuf* fused_dst;      // methylation plans run as chained stage kernels: intermediate streams; where gg_run_fused writes (null = the slabs)
     DBuf d_bgzf, d_bgzf2, d_bgzf_tab, d_bgzf_state;  // device BGZF: output slabs (ping-pong), code/CRC tables, look-back state + histogram
     int bgzf_slab, bgzf_reuse_code, bgzf_hdr_nbits;  // pipeline state of gg_run_fused_bgzf_to_host
     std::vector<uint32_t> bgzf_static;               // CRC tables and shift polynomials (built once)
@@ -369,7 +373,7 @@ int gg_ctx_create(int device, uint64_t seed, gg_ctx** out) {
     ctx->device = device; ctx->seed = seed; ctx->st = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->st_copy = nullptr; ctx->out_slab = 0;
     for (int i = 0; i < 2; i++) ctx->ev_k[i] = ctx->ev_c[i] = nullptr;
     ctx->ctab_dirty = true; ctx->n_contigs_total = 0;
-    ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false;
+    ctx->size_mode = GG_SIZE_FIXED; ctx->fixed_len = 20; ctx->minlen = 0; ctx->maxlen = 1000; ctx->norev = 0; ctx->sizes_set = false; ctx->keep_case = 0; ctx->fused_dst = nullptr;
     ctx->adF = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG";   // adptSim.cpp:28
     ctx->adS = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT";         // adptSim.cpp:29
     ctx->read_len = 100; ctx->ad_dirty = true; ctx->ad_acgt = true; ctx->plan_dirty = true; memset(&ctx->naming, 0, sizeof ctx->naming); ctx->deam_name = 0;                  // adptSim.cpp:31
@@ -391,10 +395,11 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     if (!ctx) return GG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); }
+    for (size_t g = 0; g < ctx->genomes.size(); g++) { cudaFree(ctx->genomes[g].d_seq2); cudaFree(ctx->genomes[g].d_nmask); if (ctx->genomes[g].d_cmask) cudaFree(ctx->genomes[g].d_cmask); }
     DBuf* bufs[] = {&ctx->d_cum_end, &ctx->d_gbase, &ctx->d_clen, &ctx->d_name_off, &ctx->d_name_len, &ctx->d_names, &ctx->d_genomes,
                     &ctx->d_size_len, &ctx->d_size_thr, &ctx->d_adF2, &ctx->d_adS2, &ctx->d_rcS2, &ctx->d_adF, &ctx->d_adS, &ctx->d_ranges,
-                    &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush};
+                    &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush,
+                    &ctx->d_case, &ctx->d_cmask_ptrs, &ctx->d_chain_a, &ctx->d_chain_b};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
     for (int s = 0; s < GG_MAX_GC_SLOTS; s++) ctx->gc[s].d_thr.release();
@@ -423,7 +428,7 @@ int gg_genome_upload(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_e
 int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_fai_entry* fai, int n_chr, int circ_chr, int* genome_id_out) {
     if (!ctx || !fasta || !fai || n_chr <= 0 || circ_chr >= n_chr) return ctx ? ctx->fail(GG_ERR_ARG, "gg_genome_upload: bad arguments") : GG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    HostGenome H; H.d_seq2 = H.d_nmask = nullptr; H.first_contig = 0; H.circ_sorted = -1; H.wrap_s0 = 0; H.wrap_gbase = 0;
+    HostGenome H; H.d_seq2 = H.d_nmask = nullptr; H.d_cmask = nullptr; H.cmask_bytes = 0; H.first_contig = 0; H.circ_sorted = -1; H.wrap_s0 = 0; H.wrap_gbase = 0;
     std::vector<HostContig> cs;
     for (int i = 0; i < n_chr; i++) {
         HostContig c; c.name = fai[i].name ? fai[i].name : "";
@@ -472,10 +477,11 @@ int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_
     uint8_t* d_fa = ctx->d_tmp_fa.as<uint8_t>();
     uint64_t* d_off = ctx->d_tmp_desc.as<uint64_t>(); uint64_t* d_gb = d_off + nc;
     uint32_t* d_len = (uint32_t*)(d_gb + nc); int32_t* d_bl = (int32_t*)(d_len + nc); int32_t* d_ll = d_bl + nc;
-    void* p1 = nullptr; void* p2 = nullptr;
+    void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
     cudaError_t e = pool_alloc(ctx, (H.n_units * 2 + 4) * 4, &p1, &H.seq2_bytes);
     if (e == cudaSuccess) e = pool_alloc(ctx, (H.n_units + 4) * 4, &p2, &H.nmask_bytes);
-    H.d_seq2 = (uint32_t*)p1; H.d_nmask = (uint32_t*)p2;
+    if (e == cudaSuccess && ctx->keep_case) e = pool_alloc(ctx, (H.n_units + 4) * 4, &p3, &H.cmask_bytes);   // --case: one more bit per base
+    H.d_seq2 = (uint32_t*)p1; H.d_nmask = (uint32_t*)p2; H.d_cmask = (uint32_t*)p3;
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(cudaMemcpyAsync(d_fa, fasta, n, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_off, off.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
@@ -484,12 +490,13 @@ int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_
     TRY(cudaMemcpyAsync(d_bl, blen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     TRY(cudaMemcpyAsync(d_ll, llen.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
     // every unit (incl. the guard units in front and the slack behind) is written by the pack kernel
-    TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, (int)nc, wrap_desc, wrap_keff, wrap_srclen, H.n_units, H.d_seq2, H.d_nmask, ctx->st));
+    TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, (int)nc, wrap_desc, wrap_keff, wrap_srclen, H.n_units, H.d_seq2, H.d_nmask, H.d_cmask, ctx->st));
     TRY(cudaMemsetAsync(H.d_seq2 + H.n_units * 2, 0, 16, ctx->st));
     TRY(cudaMemsetAsync(H.d_nmask + H.n_units, 0xFF, 16, ctx->st));
+    if (H.d_cmask) TRY(cudaMemsetAsync(H.d_cmask + H.n_units, 0, 16, ctx->st));
     TRY(cudaStreamSynchronize(ctx->st));
 #undef TRY
-    if (e != cudaSuccess) { if (p1) cudaFree(p1); if (p2) cudaFree(p2); return ctx->cuda_fail(e, "gg_genome_upload"); }
+    if (e != cudaSuccess) { if (p1) cudaFree(p1); if (p2) cudaFree(p2); if (p3) cudaFree(p3); return ctx->cuda_fail(e, "gg_genome_upload"); }
     ctx->genomes.push_back(H);
     ctx->ctab_dirty = true;
     if (genome_id_out) *genome_id_out = (int)ctx->genomes.size() - 1;
@@ -503,6 +510,7 @@ int gg_genome_clear(gg_ctx* ctx) {
     for (size_t g = 0; g < ctx->genomes.size(); g++) {
         ctx->pool.push_back(std::make_pair((void*)ctx->genomes[g].d_seq2, ctx->genomes[g].seq2_bytes));
         ctx->pool.push_back(std::make_pair((void*)ctx->genomes[g].d_nmask, ctx->genomes[g].nmask_bytes));
+        if (ctx->genomes[g].d_cmask) ctx->pool.push_back(std::make_pair((void*)ctx->genomes[g].d_cmask, ctx->genomes[g].cmask_bytes));
     }
     ctx->genomes.clear(); ctx->plan.clear(); ctx->ctab_dirty = true; ctx->plan_dirty = true;
     return GG_OK;
@@ -556,6 +564,7 @@ int gg_tables_set_sizes(gg_ctx* ctx, int mode, const int32_t* len, const double*
     return GG_OK;
 }
 int gg_tables_set_norev(gg_ctx* ctx, int norev) { if (!ctx) return GG_ERR_ARG; ctx->norev = norev ? 1 : 0; return GG_OK; }
+int gg_tables_set_case(gg_ctx* ctx, int keep_case) { if (!ctx) return GG_ERR_ARG; ctx->keep_case = keep_case ? 1 : 0; return GG_OK; }
 
 static int check_rates(gg_ctx* ctx, const double* sub, int rows, const char* what) {
     for (int r = 0; r < rows; r++)
@@ -578,6 +587,23 @@ static double row_rate(const double* row, int b) {
     return sum;
 }
 static double row_max(const double* row) { double m = 0.0; for (int b = 0; b < 4; b++) m = std::max(m, row_rate(row, b)); return m; }
+
+// thresholds of the reference's categorical pick for base b of a row (deamSim.cpp:1797-1863): K[a] = number of u31 with p <= sumProb[a+1]
+static bool categorical_thresholds(const double* row, int b, uint32_t k[4]) {
+    double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
+    double sum = 0.0;
+    for (int a = 0; a < 4; a++) {
+        if (a == b) continue;
+        const int idx = a < b ? b * 3 + a : b * 3 + (a - 1);
+        sum += row[idx]; _sumProb[a + 1] = row[idx];
+    }
+    _sumProb[b + 1] = 1.0 - sum;
+    double sacc = 0;
+    for (int a = 0; a < 5; a++) { sacc += _sumProb[a]; sumProb[a] = sacc; }
+    uint32_t prev = 0;
+    for (int a = 0; a < 4; a++) { uint32_t v = thr_le(sumProb[a + 1]); if (v < prev) v = prev; k[a] = v; prev = v; }
+    return k[3] == 2147483648u;          // the device picks (u>=K1)+(u>=K2)+(u>=K3): exact iff the last cumulative value covers every u31
+}
 
 int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, const double* sub3, int rows3, int clamp_last) {
     if (!ctx) return GG_ERR_ARG;
@@ -620,20 +646,7 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
                     for (int a = 0; a < 4; a++) k[a] = a < b ? 0u : 2147483648u;
                 } else {
                     // cumulative table exactly as deamSim.cpp:1797-1837 builds it (same operation order, fp64)
-                    double sumProb[5], _sumProb[5]; sumProb[0] = 0.0; _sumProb[0] = 0.0;
-                    double sum = 0.0;
-                    for (int a = 0; a < 4; a++) {
-                        if (a == b) continue;
-                        const int idx = a < b ? b * 3 + a : b * 3 + (a - 1);
-                        sum += row[idx]; _sumProb[a + 1] = row[idx];
-                    }
-                    _sumProb[b + 1] = 1.0 - sum;
-                    double sacc = 0;
-                    for (int a = 0; a < 5; a++) { sacc += _sumProb[a]; sumProb[a] = sacc; }
-                    uint32_t prev = 0;
-                    for (int a = 0; a < 4; a++) { uint32_t v = thr_le(sumProb[a + 1]); if (v < prev) v = prev; k[a] = v; prev = v; }
-                    // the device picks (u>=K1)+(u>=K2)+(u>=K3): exact iff the last cumulative value covers every u31
-                    if (k[3] != 2147483648u) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: cumulative probabilities of a row do not reach 1");
+                    if (!categorical_thresholds(row, b, k)) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix: cumulative probabilities of a row do not reach 1");
                 }
                 H.term[(size_t)((e ? H.n5t : 0) + t) * 4 + b] = make_uint4(k[0], k[1], k[2], k[3]);
             }
@@ -666,6 +679,39 @@ int gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5, c
     if ((rc = upload_vec(ctx, H.d_acc, H.acc))) return rc;
     if ((rc = upload_vec(ctx, H.d_guideA, H.guideA))) return rc;
     return upload_vec(ctx, H.d_geoA, H.geoA);
+}
+
+int gg_tables_set_matrix_meth(gg_ctx* ctx, int slot, const double* no5, int rows_no5, const double* no3, int rows_no3,
+                              const double* wi5, int rows_wi5, const double* wi3, int rows_wi3, int clamp_last) {
+    if (!ctx) return GG_ERR_ARG;
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || !no5 || !no3 || !wi5 || !wi3 || rows_no5 <= 0 || rows_no3 <= 0 || rows_wi5 <= 0 || rows_wi3 <= 0)
+        return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix_meth: bad arguments");
+    int rc;
+    if ((rc = check_rates(ctx, no5, rows_no5, "gg_tables_set_matrix_meth"))) return rc;
+    if ((rc = check_rates(ctx, no3, rows_no3, "gg_tables_set_matrix_meth"))) return rc;
+    if ((rc = check_rates(ctx, wi5, rows_wi5, "gg_tables_set_matrix_meth"))) return rc;
+    if ((rc = check_rates(ctx, wi3, rows_wi3, "gg_tables_set_matrix_meth"))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    HostDamage& H = ctx->dmg[slot];
+    H.mode = GG_DMG_METH; H.clamp_last = clamp_last ? 1 : 0; H.n5t = H.n3t = 0;
+    H.rows5 = std::max(rows_no5, rows_wi5); H.rows3 = std::max(rows_no3, rows_wi3);
+    // term[(row)*8 + m*4 + b]: rows5 5' rows, then rows3 3' rows; m = 1 methylated.  A table with fewer rows than the other of its end
+    // repeats its last row (deamSim.cpp:1665-1668) or, with -last, leaves the position alone (w = 0; :1669-1671)
+    H.term.assign((size_t)(H.rows5 + H.rows3) * 8, make_uint4(0, 0, 0, 0));
+    for (int e = 0; e < 2; e++)
+        for (int m = 0; m < 2; m++) {
+            const double* sub = e ? (m ? wi3 : no3) : (m ? wi5 : no5);
+            const int n = e ? (m ? rows_wi3 : rows_no3) : (m ? rows_wi5 : rows_no5), R = e ? H.rows3 : H.rows5;
+            for (int r = 0; r < R; r++)
+                for (int b = 0; b < 4; b++) {
+                    uint4& T = H.term[(size_t)((e ? H.rows5 : 0) + r) * 8 + (size_t)m * 4 + b];
+                    if (r >= n && !H.clamp_last) { T = make_uint4(0, 0, 0, 0); continue; }
+                    uint32_t k[4];
+                    if (!categorical_thresholds(sub + (size_t)std::min(r, n - 1) * 12, b, k)) return ctx->fail(GG_ERR_ARG, "gg_tables_set_matrix_meth: cumulative probabilities of a row do not reach 1");
+                    T = make_uint4(k[0], k[1], k[2], k[3]);
+                }
+        }
+    return upload_vec(ctx, H.d_term, H.term);
 }
 
 int gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const double* sub5, int rows5, const double* sub3, int rows3) {
@@ -853,9 +899,25 @@ uint64_t gg_max_record_bytes(gg_ctx* ctx, int emit) {
 }
 
 // ------------------------------------------------------------------------------------------------ fused run
+static int run_meth_chain(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, int slot, gg_out* out);
+
 int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* out) {
     if (!ctx || !out) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_fused: bad arguments") : GG_ERR_ARG;
     memset(out, 0, sizeof *out);
+    if (emit > GG_EMIT_FRAG && emit <= GG_EMIT_RR && !ctx->plan.empty()) {
+        // methylation (-matfilemeth/-matfilenonmeth) needs the case of every base: such a plan runs as the three stage kernels chained on
+        // the device (fragSim --case -> deamSim -> adptSim), like gargammel.pl --methyl, which hands every source the same two tables (:1698-1811)
+        int meth = -1; bool uniform = true;
+        for (size_t i = 0; i < ctx->plan.size(); i++) {
+            const int sl = ctx->plan[i].damage_slot;
+            if (sl >= 0 && sl < GG_MAX_DAMAGE_SLOTS && ctx->dmg[sl].mode == GG_DMG_METH) meth = sl;
+        }
+        if (meth >= 0) {
+            for (size_t i = 0; i < ctx->plan.size(); i++) if (ctx->plan[i].damage_slot != meth) uniform = false;
+            if (!uniform) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a plan that uses a methylation slot must use it for every range (gargammel.pl:670-677)");
+            return run_meth_chain(ctx, first, count, emit, meth, out);
+        }
+    }
     if (emit < GG_EMIT_FRAG || emit > GG_EMIT_RR) return ctx->fail(GG_ERR_ARG, "gg_run_fused: unknown emit mode");
     if (emit >= GG_EMIT_STDOUT4 && !ctx->ad_acgt) return ctx->fail(GG_ERR_ARG, "gg_run_fused: adapters with characters other than upper-case ACGT are only supported by the stand-alone adptSim stage (gg_run_adpt)");
     if (ctx->plan.empty() || ctx->genomes.empty()) return ctx->fail(GG_ERR_STATE, "gg_run_fused: no plan / genome");
@@ -870,6 +932,10 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int rc;
     if ((rc = sync_contig_tables(ctx)) || (rc = sync_adapters(ctx)) || (rc = sync_plan(ctx))) return rc;
     if (count == 0) { out->dev_ptr = ctx->d_out.p; ctx->last_ms = 0; return GG_OK; }
+    const bool with_case = ctx->keep_case && emit == GG_EMIT_FRAG;      // later stages upper-case what they read (deamSim.cpp:1319, adptSim.cpp:288)
+    if (with_case)
+        for (size_t i = 0; i < ctx->plan.size(); i++)
+            if (!ctx->genomes[ctx->plan[i].genome].d_cmask) return ctx->fail(GG_ERR_STATE, "gg_run_fused: --case was set after a genome upload (call gg_tables_set_case first)");
 
     const int Lmax = max_frag_len(ctx);
     if (Lmax < 0 || Lmax > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_run_fused: no admissible fragment length (check -l/-s/-f against -m/-M)");
@@ -942,8 +1008,14 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     const int n_tiles = (int)n_tiles64;
 
     const uint64_t out_cap = count * rec_max + 64;
-    DBuf& oslab = ctx->out_slab ? ctx->d_out2 : ctx->d_out;
+    DBuf& oslab = ctx->fused_dst ? *ctx->fused_dst : ctx->out_slab ? ctx->d_out2 : ctx->d_out;
     CK(oslab.ensure(out_cap));
+    if (with_case) {
+        CK(ctx->d_case.ensure((size_t)count * 20 + 64));
+        std::vector<const uint32_t*> cm(ctx->genomes.size());
+        for (size_t g = 0; g < cm.size(); g++) cm[g] = ctx->genomes[g].d_cmask;
+        int rcc = upload_vec(ctx, ctx->d_cmask_ptrs, cm); if (rcc) return rcc;
+    }
     CK(ctx->d_tile_state.ensure((size_t)n_tiles * 8));
     CK(ctx->d_ticket_stats.ensure(256));
 
@@ -976,6 +1048,9 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     P.ticket = ctx->d_ticket_stats.as<unsigned int>();
     P.stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
     P.sm = sm;
+    if (with_case) {
+        P.case_off = ctx->d_case.as<unsigned long long>(); P.case_gpos = P.case_off + count; P.case_meta = (uint32_t*)(P.case_gpos + count);
+    }
 
     int bps = 0;
     CK(fused_prepare(fast_boundary, dmode, emitc, warps * 32, sm.total, &bps, &regs));
@@ -991,12 +1066,13 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     CK(cudaMemsetAsync(ctx->d_tile_state.p, 0, (size_t)n_tiles * 8, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
     CK(launch_fused(P, emitc, grid, warps * 32, ctx->st));
+    if (with_case) CK(launch_case_apply(count, P.case_off, P.case_gpos, P.case_meta, ctx->d_cmask_ptrs.as<const uint32_t*>(), P.out, ctx->st));
     unsigned long long stats[ST_N];
     { int rcp = fetch_small(ctx, P.stats, stats, ST_N, ctx->ev1); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     out->dev_ptr = oslab.p; out->bytes = stats[ST_TOTAL]; out->records = count;
-    out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = 2;   // k_fused + k_publish
+    out->attempts = stats[ST_ATTEMPTS]; out->gather_bytes = stats[ST_GATHER]; out->device_ms = ms; out->launches = with_case ? 3 : 2;   // k_fused (+ k_case_apply) + k_publish
     if (stats[ST_ERR] & ERRF_GIVEUP) return ctx->fail(GG_ERR_GIVEUP, "gg_run_fused: a fragment exhausted its sampling attempts (genome without an admissible window?)");
     if (stats[ST_ERR] & ERRF_OVERFLOW) return ctx->fail(GG_ERR_CAPACITY, "gg_run_fused: internal staging/output overflow");
     return GG_OK;
@@ -1044,8 +1120,14 @@ int index_records(gg_ctx* ctx, const uint8_t* d_in, size_t n, RecStream* R, int*
 }
 }
 
+static int run_deam_into(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, DBuf& ob, gg_out* out);
+static int run_adpt_into(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, DBuf& ob, gg_out* out);
+
 int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, gg_out* out) {
     if (!ctx || !out || (n && !recs_dev)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_deam: bad arguments") : GG_ERR_ARG;
+    return run_deam_into(ctx, recs_dev, n, slot, first_id, pick_out(ctx, recs_dev), out);
+}
+static int run_deam_into(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint64_t first_id, DBuf& ob, gg_out* out) {
     memset(out, 0, sizeof *out);
     if (slot < -1 || slot >= GG_MAX_DAMAGE_SLOTS) return ctx->fail(GG_ERR_ARG, "gg_run_deam: bad damage slot");
     CK(cudaSetDevice(ctx->device));
@@ -1053,7 +1135,6 @@ int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint6
     unsigned long long* d_stats = (unsigned long long*)(ctx->d_ticket_stats.as<uint8_t>() + 64);
     CK(cudaEventRecord(ctx->ev0, ctx->st));
     CK(cudaMemsetAsync(ctx->d_ticket_stats.p, 0, 256, ctx->st));
-    DBuf& ob = pick_out(ctx, recs_dev);
     ggd::DamageDev D; memset(&D, 0, sizeof D);
     const int has = (slot >= 0 && ctx->dmg[slot].mode != GG_DMG_NONE) ? 1 : 0;
     if (has) fill_damage_dev(ctx->dmg[slot], &D);
@@ -1121,6 +1202,9 @@ int gg_run_deam_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int slot, uint6
 
 int gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, gg_out* out) {
     if (!ctx || !out || (n && !recs_dev)) return ctx ? ctx->fail(GG_ERR_ARG, "gg_run_adpt: bad arguments") : GG_ERR_ARG;
+    return run_adpt_into(ctx, recs_dev, n, emit, first_id, pick_out(ctx, recs_dev), out);
+}
+static int run_adpt_into(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint64_t first_id, DBuf& ob, gg_out* out) {
     memset(out, 0, sizeof *out);
     if (emit < GG_EMIT_STDOUT4 || emit > GG_EMIT_RR) return ctx->fail(GG_ERR_ARG, "gg_run_adpt: emit mode must be an adptSim dialect");
     CK(cudaSetDevice(ctx->device));
@@ -1133,7 +1217,6 @@ int gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint6
     RecStream R; int launches = 0;
     if ((rc = index_records(ctx, (const uint8_t*)recs_dev, n, &R, &launches))) return rc;
     unsigned long long h_total = 0;
-    DBuf& ob = pick_out(ctx, recs_dev);
     if (R.n_rec) {
         const uint64_t nb = (R.n_rec + 2047) / 2048;
         CK(ctx->d_sizes.ensure((size_t)(R.n_rec + nb + 16) * 8));
@@ -1159,6 +1242,31 @@ int gg_run_adpt_dev(gg_ctx* ctx, const void* recs_dev, size_t n, int emit, uint6
     ctx->last_ms = ms;
     out->dev_ptr = ob.p; out->bytes = h_total; out->records = R.n_rec; out->in_bytes = n; out->device_ms = ms; out->launches = launches;
     if (stats[ST_ERR] & ERRF_PARSE) return ctx->fail(GG_ERR_PARSE, "gg_run_adpt: a record does not start with '>'");
+    return GG_OK;
+}
+
+// a methylation plan: fragSim (--case) -> deamSim -> [adptSim] as stage kernels over device-resident streams; the last stage writes
+// where gg_run_fused would have written (so the egress pipelines work unchanged), the intermediate streams live in their own buffers
+static int run_meth_chain(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, int slot, gg_out* out) {
+    if (!ctx->keep_case) return ctx->fail(GG_ERR_STATE, "gg_run_fused: methylation tables need the case of the genome (gg_tables_set_case before gg_genome_upload)");
+    struct DstReset { gg_ctx* c; ~DstReset() { c->fused_dst = nullptr; } } reset = {ctx};
+    DBuf& final_dst = ctx->out_slab ? ctx->d_out2 : ctx->d_out;
+    gg_out o1, o2, o3;
+    ctx->fused_dst = &ctx->d_chain_a;
+    int rc = gg_run_fused(ctx, first, count, GG_EMIT_FRAG, &o1);
+    ctx->fused_dst = nullptr;
+    if (rc) return rc;
+    rc = run_deam_into(ctx, o1.dev_ptr, (size_t)o1.bytes, slot, first, emit == GG_EMIT_DEAM ? final_dst : ctx->d_chain_b, &o2);
+    if (rc) return rc;
+    *out = o2;
+    if (emit != GG_EMIT_DEAM) {
+        rc = run_adpt_into(ctx, o2.dev_ptr, (size_t)o2.bytes, emit, first, final_dst, &o3);
+        if (rc) return rc;
+        *out = o3; out->device_ms += o2.device_ms; out->launches += o2.launches;
+    }
+    out->records = count; out->attempts = o1.attempts; out->gather_bytes = o1.gather_bytes; out->in_bytes = 0;
+    out->device_ms += o1.device_ms; out->launches += o1.launches;
+    ctx->last_ms = out->device_ms;
     return GG_OK;
 }
 

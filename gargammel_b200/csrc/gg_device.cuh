@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t lowfields(int n) {
 // ---------------------------------------------------------------- damage model tables (device view)
 struct DamageDev {
     int mode;            // gg_damage_mode
-    int rows5, rows3;    // matrix / single-double rows
+    int rows5, rows3;    // matrix / single-double rows (METH: the larger row count of the two tables of an end)
     int clamp_last;      // matrix: clamp to last row (default) or skip (-last)
     // MATRIX (draw specification v2: events).  Thresholds are uint4 per (row, base):
     //   term[(t)*4 + b], t < n5t: categorical of the 5' terminal position t; term[(n5t + t)*4 + b], t < n3t: 3' terminal position L-1-t.
@@ -295,6 +295,19 @@ __device__ __forceinline__ uint32_t dmg_sd_base(const DamageDev& D, int i, int L
     if (D.mode == 3 /*SINGLE*/) { if (b == 1u && (x2 >> 1) < __ldg(D.sd3 + r3)) b = 3u; }
     else                        { if (b == 2u && (x2 >> 1) < __ldg(D.sd3 + r3)) b = 0u; }
     return b;
+}
+
+// -matfilemeth / -matfilenonmeth, one base (deamSim.cpp:1630-1787; drawn per base, word i): bm = base code | 4 for a methylated
+// (lower-case) base.  term[(row)*8 + bm], rows = rows5 5' rows then rows3 3' rows (by distance from the 3' end), holds the reference's
+// categorical thresholds; w == 0 marks a position without a row in that table (-last): the byte stays as it is (returns -1).
+__device__ __forceinline__ int dmg_meth_base(const DamageDev& D, int i, int L, int bm, uint32_t x) {
+    const bool five = i < (L >> 1);                                        // deamSim.cpp:1661
+    int dist = five ? i : L - 1 - i;
+    const int R = five ? D.rows5 : D.rows3;
+    if (dist >= R) { if (!D.clamp_last) return -1; dist = R - 1; }
+    const uint4 T = __ldg(D.term + ((five ? 0 : D.rows5) + dist) * 8 + bm);
+    if (T.w == 0u) return -1;
+    return (int)count_le(x >> 1, T);
 }
 
 // ASCII <-> code

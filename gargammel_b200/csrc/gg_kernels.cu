@@ -28,9 +28,10 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         const uint64_t* __restrict__ c_off, const uint32_t* __restrict__ c_len,
         const int32_t* __restrict__ c_blen, const int32_t* __restrict__ c_llen,
         const uint64_t* __restrict__ c_gbase, int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
-        uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask) {
+        uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask, uint32_t* __restrict__ cmask /* fragSim --case: 1 = lower-case; may be null */) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
+    uint32_t lc = 0;
     const uint64_t base0 = u * 32ull;
     int lo = 0, hi = n_contigs;                       // last contig with gbase <= base0
     while (lo < hi) { int mid = (lo + hi) >> 1; if (c_gbase[mid] <= base0) lo = mid + 1; else hi = mid; }
@@ -50,8 +51,9 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
                         const uint64_t src = j < wrap_keff ? (uint64_t)wrap_srclen - 1 - wrap_keff + j : j - wrap_keff;
                         if (src < wrap_srclen) {
                             const uint64_t pos = c_off[c] + src / blen * llen + src % blen;
-                            const int cd = ascii2code(pos < n ? upper(fasta[pos]) : 0);
-                            if (cd >= 0) { code = (uint32_t)cd; bad = 0; }
+                            const uint8_t raw = pos < n ? fasta[pos] : 0;
+                            const int cd = ascii2code(upper(raw));
+                            if (cd >= 0) { code = (uint32_t)cd; bad = 0; lc |= (raw >= 'a' ? 1u : 0u) << t; }
                         }
                     }
                     if (t < 16) w0 |= code << (2 * t); else w1 |= code << (2 * (t - 16));
@@ -63,9 +65,9 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
                 for (int t = 0; t < 32; t++) {
                     uint32_t code = 0, bad = 1;
                     if (local + t < len) {
-                        const uint8_t ch = pos < n ? upper(fasta[pos]) : 0;   // toupper, fragSim.cpp:315
-                        const int cd = ascii2code(ch);
-                        if (cd >= 0) { code = (uint32_t)cd; bad = 0; }
+                        const uint8_t raw = pos < n ? fasta[pos] : 0;
+                        const int cd = ascii2code(upper(raw));                // toupper, fragSim.cpp:315
+                        if (cd >= 0) { code = (uint32_t)cd; bad = 0; lc |= (raw >= 'a' ? 1u : 0u) << t; }
                         pos++; col++;
                         if (col == blen) { col = 0; pos += llen - blen; }
                     }
@@ -76,15 +78,16 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         }
     }
     seq2[2 * u] = w0; seq2[2 * u + 1] = w1; nmask[u] = m;
+    if (cmask) cmask[u] = lc;
 }
 
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
                                int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
-                               uint32_t* seq2, uint32_t* nmask, cudaStream_t st) {
+                               uint32_t* seq2, uint32_t* nmask, uint32_t* cmask, cudaStream_t st) {
     if (n_units == 0) return cudaSuccess;
     const uint64_t blocks = (n_units + 255) / 256;
-    k_pack_genome<<<(unsigned)blocks, 256, 0, st>>>(fasta, n, c_off, c_len, c_blen, c_llen, c_gbase, n_contigs, wrap_desc, wrap_keff, wrap_srclen, n_units, seq2, nmask);
+    k_pack_genome<<<(unsigned)blocks, 256, 0, st>>>(fasta, n, c_off, c_len, c_blen, c_llen, c_gbase, n_contigs, wrap_desc, wrap_keff, wrap_srclen, n_units, seq2, nmask, cmask);
     return cudaGetLastError();
 }
 
@@ -715,6 +718,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         if (lane == 0 && tile == P.n_tiles - 1) P.stats[ST_TOTAL] = gofs + (unsigned long long)T;
         const bool fits = gofs + T <= P.out_cap;                         // host sizing guard: never write past the output
         if (!fits) my_err |= ERRF_OVERFLOW;
+        if (EMITC == 0 && P.case_off != nullptr && lane < nf) {          // fragSim --case: where the record's bases are and where they came from (k_case_apply)
+            const uint64_t f = tile_first + (uint64_t)lane;
+            P.case_off[f] = gofs + (unsigned long long)s_so[lane]; P.case_gpos[f] = s_gpos[lane]; P.case_meta[f] = s_meta[lane];
+        }
         __syncwarp();
 
         // ------------------------------------------------------------ emission in halves of up to P.E fragments
@@ -893,6 +900,32 @@ cudaError_t launch_fused(const FusedParams& P, int emitc, int grid, int threads,
     return cudaGetLastError();
 }
 
+// fragSim --case (fragSim.cpp:318-326,548-551): the fused kernel writes upper-case bases; this pass lower-cases the bases whose genome
+// position carries the case bit (reverse-strand fragments read the mask backwards: complementing keeps the case).  Warp per record.
+__global__ void __launch_bounds__(256) k_case_apply(uint64_t n_rec, const unsigned long long* __restrict__ off, const unsigned long long* __restrict__ gpos,
+                                                    const uint32_t* __restrict__ meta, const uint32_t* const* __restrict__ cmasks, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += nw) {
+        const uint32_t m = meta[r];
+        const int L = META_L(m);
+        const uint32_t* cm = cmasks[META_GEN(m)];
+        if (cm == nullptr) continue;
+        const uint64_t g = gpos[r], o = off[r];
+        for (int i = lane; i < L; i += 32) {
+            const uint64_t p = META_PLUS(m) ? g + (uint64_t)i : g + (uint64_t)(L - 1 - i);
+            if ((__ldg(cm + (p >> 5)) >> (p & 31)) & 1u) out[o + (uint64_t)i] |= 0x20;
+        }
+    }
+}
+cudaError_t launch_case_apply(uint64_t n_rec, const unsigned long long* off, const unsigned long long* gpos, const uint32_t* meta,
+                              const uint32_t* const* cmasks, uint8_t* out, cudaStream_t st) {
+    if (n_rec == 0) return cudaSuccess;
+    const uint64_t want = (n_rec + 7) / 8;
+    k_case_apply<<<(unsigned)(want < 148ull * 16 ? want : 148ull * 16), 256, 0, st>>>(n_rec, off, gpos, meta, cmasks, out);
+    return cudaGetLastError();
+}
+
 // ======================================================================================= record-stream helpers
 __device__ __forceinline__ int count_nl16(uint4 v) {
     const uint32_t nl = 0x0A0A0A0Au;
@@ -1054,9 +1087,13 @@ __global__ void __launch_bounds__(256) k_deam_records(const RecStream R, uint8_t
             BriggsHdr B; B.o5 = B.o3 = B.nick = 0;
             if (perbase && D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
             for (int i = lane; i < L; i += 32) {
-                uint8_t c = upper(R.in[p.ss + i]);                                         // toupper, deamSim.cpp:1319-1321
+                const uint8_t raw = R.in[p.ss + i];
+                uint8_t c = upper(raw);                                                    // toupper, deamSim.cpp:1319-1321
                 const int code = ascii2code(c);
-                if (perbase && code >= 0) {                                                // unresolved bases are never touched (deamSim.cpp:1795)
+                if (perbase && D.mode == 6) {                                              // methylation: no toupper; a resolved base with a row comes out upper-case (deamSim.cpp:1630-1787)
+                    c = raw;
+                    if (code >= 0) { const int nb = dmg_meth_base(D, i, L, code | (raw != upper(raw) ? 4 : 0), rng_word(key, id, ST_DEAM, (uint32_t)i)); if (nb >= 0) c = code2ascii((uint32_t)nb); }
+                } else if (perbase && code >= 0) {                                         // unresolved bases are never touched (deamSim.cpp:1795)
                     uint32_t nb = (uint32_t)code;
                     if (D.mode == 5) nb = dmg_briggs_ss_base(D, B, i, L, nb, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
                     else nb = dmg_sd_base(D, i, L, nb, rng_word(key, id, ST_DEAM, (uint32_t)i), rng_word(key, id, ST_DEAM2, (uint32_t)i));
@@ -1339,12 +1376,16 @@ int deam_stream_tile_bytes() { return DS_TILE; }
 // ---- deamSim -name: "_DEAM:p1,p2,..." appended to the ID of every damaged record (deamSim.cpp:2029-2037).
 // Position lists follow the reference's push order: matrix: i ascending, +(i+1) in the 5' half, -(len-i) in the 3' half
 // (:1857,1919); Briggs: +(i+1) (:1489-1589); single/double: all pass-1 hits +(i+1), then all pass-2 hits -(len-i) (:1949-1994).
-struct DeamEvt { uint32_t nb; int v0, v1; };     // new base; list-0 value (0 = none); list-1 value (0 = none)
-// the models drawn per base (-damagess, -mat single|double)
-__device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int i, int L, int code) {
-    DeamEvt e; e.nb = (uint32_t)code; e.v0 = 0; e.v1 = 0;
+struct DeamEvt { uint32_t nb; int v0, v1; bool keep; };     // new base; list-0 value (0 = none); list-1 value (0 = none); keep = the input byte stays as it is
+// the models drawn per base (-damagess, -mat single|double, -matfilemeth/-matfilenonmeth); lower = the input byte was a lower-case letter
+__device__ __forceinline__ DeamEvt deam_event(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int i, int L, int code, bool lower) {
+    DeamEvt e; e.nb = (uint32_t)code; e.v0 = 0; e.v1 = 0; e.keep = false;
     const uint32_t b = (uint32_t)code;
-    if (D.mode == 5) {
+    if (D.mode == 6) {                                                                     // deamSim.cpp:1709-1711,1770-1773: one list, in position order
+        const int nb = dmg_meth_base(D, i, L, code | (lower ? 4 : 0), rng_word(key, id, ST_DEAM, (uint32_t)i));
+        if (nb < 0) e.keep = true;
+        else { e.nb = (uint32_t)nb; if (e.nb != b) e.v0 = i < (L >> 1) ? i + 1 : -(L - i); }
+    } else if (D.mode == 5) {
         e.nb = dmg_briggs_ss_base(D, B, i, L, b, rng_word(key, id, ST_DEAM, 4u + (uint32_t)i));
         if (e.nb != b) e.v0 = i + 1;
     } else {
@@ -1407,8 +1448,9 @@ __global__ void __launch_bounds__(256) k_deam_name_sizes(const RecStream R, cons
         if (D.mode == 5) B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
         unsigned long long txt = 0;
         for (int i = lane; i < L; i += 32) {
-            const int code = ascii2code(upper(R.in[p.ss + i]));
-            if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code); txt += (unsigned long long)(evt_text_len(e.v0) + evt_text_len(e.v1)); }
+            const uint8_t raw = R.in[p.ss + i];
+            const int code = ascii2code(upper(raw));
+            if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code, raw != upper(raw)); txt += (unsigned long long)(evt_text_len(e.v0) + evt_text_len(e.v1)); }
         }
         txt = warp_sum_u64(txt);
         if (lane == 0) sizes[r] = (p.ide - p.ids) + (txt ? 5ull + txt : 0ull) + 1ull + (unsigned long long)L + 1ull;
@@ -1471,9 +1513,11 @@ __global__ void __launch_bounds__(256) k_deam_name_records(const RecStream R, co
                 const int i = i0 + lane;
                 int v = 0; uint32_t nb = 0; int code = -1; uint8_t ch = 0;
                 if (i < L) {
-                    ch = upper(R.in[p.ss + i]); code = ascii2code(ch);
-                    if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code); v = list == 0 ? e.v0 : e.v1; nb = e.nb; }
-                    if (list == 0) seqo[i] = code >= 0 ? code2ascii(nb) : ch;   // sequence bytes written once
+                    const uint8_t raw = R.in[p.ss + i];
+                    ch = upper(raw); code = ascii2code(ch);
+                    bool keep = code < 0;
+                    if (code >= 0) { const DeamEvt e = deam_event(D, B, key, id, i, L, code, raw != ch); v = list == 0 ? e.v0 : e.v1; nb = e.nb; keep = e.keep; }
+                    if (list == 0) seqo[i] = !keep ? code2ascii(nb) : (D.mode == 6 ? raw : ch);   // sequence bytes written once (methylation mode does not upper-case what it leaves alone)
                 }
                 const int len = evt_text_len(v);
                 int inc = len;

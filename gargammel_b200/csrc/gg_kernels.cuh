@@ -100,6 +100,8 @@ struct FusedParams {
     unsigned long long* tile_state;   // decoupled look-back: [63:62] status, [61:0] bytes
     unsigned int* ticket;
     unsigned long long* stats;        // [0] total bytes [1] attempts [2] gather bytes [3] error flags
+    // fragSim --case (null otherwise): per fragment, the output offset of its first base, its genome position and its META word
+    unsigned long long* case_off; unsigned long long* case_gpos; uint32_t* case_meta;
     SmemLayout sm;
 };
 
@@ -134,7 +136,9 @@ cudaError_t launch_bgzf_deflate(const BgzfParams& P, int grid, cudaStream_t st);
 cudaError_t launch_pack_genome(const uint8_t* fasta, uint64_t n, const uint64_t* c_off, const uint32_t* c_len,
                                const int32_t* c_blen, const int32_t* c_llen, const uint64_t* c_gbase,
                                int n_contigs, int wrap_desc, uint32_t wrap_keff, uint32_t wrap_srclen, uint64_t n_units,
-                               uint32_t* seq2, uint32_t* nmask, cudaStream_t st);
+                               uint32_t* seq2, uint32_t* nmask, uint32_t* cmask, cudaStream_t st);
+cudaError_t launch_case_apply(uint64_t n_rec, const unsigned long long* off, const unsigned long long* gpos, const uint32_t* meta,
+                              const uint32_t* const* cmasks, uint8_t* out, cudaStream_t st);
 cudaError_t launch_gc_probe(const GenomeDev& G, const uint64_t* cum_end, const uint64_t* gbase, const uint32_t* clen, int dist, ggd::Key key,
                             unsigned long long* sums /* [0]=sum gc, [1]=sum gc^2, [2]=give-ups */, cudaStream_t st);
 int fused_desc_bytes();      // bytes of the fixed-layout descriptors at the head of a warp's shared-memory region

@@ -55,7 +55,8 @@ typedef enum gg_damage_mode {
     GG_DMG_BRIGGS = 2,   /* -damage v,l,d,s        deamSim.cpp:1477-1613 */
     GG_DMG_SINGLE = 3,   /* -mat single / -mapdamage f single  deamSim.cpp:1941-1971 */
     GG_DMG_DOUBLE = 4,   /* -mat double / -mapdamage f double  deamSim.cpp:1973-2002 */
-    GG_DMG_BRIGGS_SS = 5 /* -damagess d,s5,s3,l5,l3 (single-strand libraries)  deamSim.cpp:310-340,1337-1468 */
+    GG_DMG_BRIGGS_SS = 5,/* -damagess d,s5,s3,l5,l3 (single-strand libraries)  deamSim.cpp:310-340,1337-1468 */
+    GG_DMG_METH   = 6    /* -matfilemeth + -matfilenonmeth (lower-case = methylated)  deamSim.cpp:673-954,1630-1787 */
 } gg_damage_mode;
 #define GG_MAX_DAMAGE_SLOTS 4
 #define GG_MAX_COMP_SLOTS 4
@@ -145,6 +146,10 @@ int  gg_genome_fetch(gg_ctx* ctx, int genome_id, int chr, int64_t start, int len
 int  gg_tables_set_sizes(gg_ctx* ctx, int mode, const int32_t* len, const double* cum, int n,
                          int fixed_len, int minlen, int maxlen);
 int  gg_tables_set_norev(gg_ctx* ctx, int norev);   /* --norev, fragSim.cpp:1463-1467 */
+/* fragSim --case (fragSim.cpp:548-551,318-326; gargammel.pl --methyl :1486,1526,1561,1605,1653): fragments keep the case of the genome
+ * file (lower-case c / g = methylated cytosine on the + / - strand, README "methylated and unmethylated").  Set it BEFORE
+ * gg_genome_upload: the upload then also keeps a 1-bit case mask per base; reverse-strand fragments complement within the case. */
+int  gg_tables_set_case(gg_ctx* ctx, int keep_case);
 /* fragSim --comp/--dist (fragSim.cpp:798-1047,1609-1759): base-composition acceptance.  Each table is [2*dist][4] (A,C,G,T) and
  * already holds "frequency - background + 0.25" (fragSim.cpp:948-1012): s5p = 5' end on the + strand, s5m on the - strand, s3p/s3m the
  * 3' end; rows 0..dist-1 are the positions outside the fragment on the 5' side / inside on the 3' side (reference order). */
@@ -160,6 +165,13 @@ int  gg_tables_clear_gcbias(gg_ctx* ctx, int slot);
  * (i.e. AFTER the 3' reversal of deamSim.cpp:1236); clamp_last = !(-last) (deamSim.cpp:1811-1817). */
 int  gg_tables_set_matrix(gg_ctx* ctx, int slot, const double* sub5, int rows5,
                           const double* sub3, int rows3, int clamp_last);
+/* deamSim -matfilenonmeth P -matfilemeth Q (deamSim.cpp:673-954,1630-1787): a lower-case base of the record is methylated and takes the
+ * "wi" tables, an upper-case base the "no" tables (same layout as gg_tables_set_matrix; the four tables may have different row counts).
+ * The record is not upper-cased first (deamSim.cpp:1319); every resolved base that has a row comes out in upper case, unresolved bases
+ * and positions beyond a -last table keep their bytes.  Drawn per base.  The fused entry points run a plan whose every range uses such
+ * a slot as fragSim (--case) -> deamSim -> adptSim stage kernels chained on the device. */
+int  gg_tables_set_matrix_meth(gg_ctx* ctx, int slot, const double* no5, int rows_no5, const double* no3, int rows_no3,
+                               const double* wi5, int rows_wi5, const double* wi3, int rows_wi3, int clamp_last);
 /* deamSim -mat single|double / -mapdamage (deamSim.cpp:1941-2002); protocol = GG_DMG_SINGLE or GG_DMG_DOUBLE */
 int  gg_tables_set_singledouble(gg_ctx* ctx, int slot, int protocol, const double* sub5, int rows5,
                                 const double* sub3, int rows3);

@@ -71,8 +71,11 @@ static inline double u01(uint32_t x) { return ((double)(x >> 1) + 0.5) * (1.0 / 
 /* ------------------------------------------------------------------ helpers (libgab semantics inferred from call sites) */
 static inline bool isResolvedDNA(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 static inline int  base2int(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+/* lower-case letters complement to lower-case letters: "methylated cytosines on the - strand can be specified using 'g'" (README.md:245)
+ * only works if reverseComplement keeps the case that fragSim --case preserved */
 static inline char complementBase(char c) {
-    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+                 case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a'; default: return 'N'; }
 }
 static std::string reverseComplement(const std::string& s) {
     std::string r(s.size(), 'N');
@@ -88,6 +91,7 @@ struct Damage {
     std::vector<double> sub5, sub3;  /* rows x 12 */
     double v, l, d, s;
     double s5, s3, l5, l3;           /* -damagess */
+    std::vector<double> sub5m, sub3m; /* -matfilemeth (methylated = lower-case bases); sub5/sub3 then hold -matfilenonmeth */
     Damage() : mode(GG_DMG_NONE), clamp_last(1), v(0), l(0), d(0), s(0), s5(0), s3(0), l5(0), l3(0) {}
 };
 struct Comp { int dist; std::vector<double> s5p, s5m, s3p, s3m; double maxP, maxM; Comp() : dist(0), maxP(1), maxM(1) {} };
@@ -98,6 +102,7 @@ struct orc_ctx {
     Comp comp[GG_MAX_COMP_SLOTS];
     std::vector<Genome> genomes;
     int size_mode, fixed_len, minlen, maxlen, norev;
+    int keep_case;                   /* fragSim --case (fragSim.cpp:548-551) */
     std::vector<int32_t> size_len; std::vector<double> size_cum;
     Damage dmg[GG_MAX_DAMAGE_SLOTS];
     std::string adF, adS; int read_len;
@@ -105,21 +110,21 @@ struct orc_ctx {
     std::vector<gg_range> plan;
     std::string err;
     uint64_t attempts, gather_bytes;
-    orc_ctx() : size_mode(GG_SIZE_FIXED), fixed_len(20), minlen(0), maxlen(1000), norev(0),
+    orc_ctx() : size_mode(GG_SIZE_FIXED), fixed_len(20), minlen(0), maxlen(1000), norev(0), keep_case(0),
         adF("AGATCGGAAGAGCACACGTCTGAACTCCAGTCACCGATTCGATCTCGTATGCCGTCTTCTGCTTG"),   /* adptSim.cpp:28 */
         adS("AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATTT"),         /* adptSim.cpp:29 */
         read_len(100), add_in_name(0), deam_name(0), attempts(0), gather_bytes(0) {}
 };
 
 /* ------------------------------------------------------------------ fragSim */
-/* IndexedGenome::fetchSeq, fragSim.cpp:305-329 (uppercase branch).  Positions that run past the
- * file are returned as '\0' (the reference would read past the mmap: undefined). */
-static std::string fetchSeq(const Genome& g, const Chr& c, int64_t index, int n) {
+/* IndexedGenome::fetchSeq, fragSim.cpp:305-329 (uppercase branch; with --case the bytes as they are, :318-326).  Positions that run
+ * past the file are returned as '\0' (the reference would read past the mmap: undefined). */
+static std::string fetchSeq(const Genome& g, const Chr& c, int64_t index, int n, bool keep_case = false) {
     std::string s; if (n > 0) s.reserve(n);              /* n <= 0 gives "" like the reference loop (a --circ corner) */
     int64_t index2 = index;
     for (int j = 0; j < n; j++) {
         uint64_t pos = c.offset + (uint64_t)(index2 / c.line_blen) * c.line_len + (uint64_t)(index2 % c.line_blen);
-        char ch = pos < g.fasta.size() ? (char)toupper(g.fasta[pos]) : '\0';
+        char ch = pos < g.fasta.size() ? (keep_case ? (char)g.fasta[pos] : (char)toupper(g.fasta[pos])) : '\0';
         s += ch;
         index2++;
     }
@@ -183,7 +188,7 @@ static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slo
             /* need to circularize, :1412-1426: temp1 stops one base short of the contig end, temp2 restarts at base 0 */
             int n1 = (int)(found->end - (coord - (uint64_t)d));
             int l2 = (int)((uint64_t)length + 2 * (uint64_t)d - (found->end - (coord - (uint64_t)d)));
-            temp = fetchSeq(g, *found, (int64_t)idx - d, n1) + fetchSeq(g, *found, 0, l2);
+            temp = fetchSeq(g, *found, (int64_t)idx - d, n1, c->keep_case) + fetchSeq(g, *found, 0, l2, c->keep_case);
         } else {
             if (idx + (uint64_t)length + (uint64_t)d > (uint64_t)found->len) {
                 /* run-off: the reference fetches past the contig and always hits '\n', '>' or EOF, so
@@ -191,16 +196,16 @@ static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slo
                  * Same outcome, stated directly. */
                 continue;
             }
-            temp = fetchSeq(g, *found, (int64_t)idx - d, length + 2 * d);            /* :1443 */
+            temp = fetchSeq(g, *found, (int64_t)idx - d, length + 2 * d, c->keep_case);   /* :1443 */
         }
         bool plus = c->norev ? true : ((x[1] & 1u) != 0);    /* :1462-1467 randomBool */
-        bool resolved = true;                                /* :1472 isResolvedDNAstring */
-        for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA(temp[i])) { resolved = false; break; }
+        bool resolved = true;                                /* :1472 isResolvedDNAstring; with --case a lower-case acgt is a (methylated) resolved base */
+        for (size_t i = 0; i < temp.size(); i++) if (!isResolvedDNA((char)toupper(temp[i]))) { resolved = false; break; }
         if (!resolved) continue;
         if (!plus) temp = reverseComplement(temp);           /* :1484 */
         if (gc_slot >= 0 && c->gc[gc_slot].on) {             /* -gc, fragSim.cpp:1509-1534 (and again :1548-1576 without --comp) */
             unsigned gcCount = 0, atCount = 0;
-            for (size_t i = 0; i < temp.size(); i++) { if (temp[i] == 'G' || temp[i] == 'C') gcCount++; else atCount++; }
+            for (size_t i = 0; i < temp.size(); i++) { const char u = (char)toupper(temp[i]); if (u == 'G' || u == 'C') gcCount++; else atCount++; }
             const double pSurv = gcSurvival(c->gc[gc_slot], gcCount, atCount);
             uint32_t y[4]; c->rng.block(id, attempt, ST_FRAG3, y);
             if (u01(y[0]) > pSurv) continue;                 /* killed = (rP > pSurv) */
@@ -211,10 +216,10 @@ static int sampleFragment(orc_ctx* c, const Genome& g, uint64_t id, int comp_slo
             const std::vector<double>& s5 = plus ? cp->s5p : cp->s5m;
             const std::vector<double>& s3 = plus ? cp->s3p : cp->s3m;
             double probAcc = 1.0;
-            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)i * 4 + base2int(preFrag[i])];                 /* :1614-1616 */
-            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)(i + d) * 4 + base2int(frag[i])];              /* :1619-1621 */
-            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)i * 4 + base2int(frag[length - d + i])];       /* :1624-1626 */
-            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)(i + d) * 4 + base2int(posFrag[i])];           /* :1629-1631 */
+            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)i * 4 + base2int((char)toupper(preFrag[i]))];                 /* :1614-1616 */
+            for (int i = 0; i < d; i++) probAcc *= s5[(size_t)(i + d) * 4 + base2int((char)toupper(frag[i]))];              /* :1619-1621 */
+            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)i * 4 + base2int((char)toupper(frag[length - d + i]))];       /* :1624-1626 */
+            for (int i = 0; i < d; i++) probAcc *= s3[(size_t)(i + d) * 4 + base2int((char)toupper(posFrag[i]))];           /* :1629-1631 */
             probAcc = probAcc / (plus ? cp->maxP : cp->maxM);                                                 /* :1633 */
             uint32_t y[4]; c->rng.block(id, attempt, ST_FRAG2, y);
             if (!(u01(y[0]) < probAcc)) continue;                                                             /* :1639 */
@@ -459,7 +464,27 @@ static void deamSingleDouble(const orc_ctx* c, const Damage& D, uint64_t id, std
     }
 }
 
+/* -matfilemeth / -matfilenonmeth, deamSim.cpp:1630-1787: a lower-case base is methylated and takes the "with methylation" matrix.
+ * The sequence is NOT upper-cased first (:1319-1321); every resolved base that has a row is rewritten in upper case (:1707, :1769),
+ * unresolved bases and positions beyond the rows of a -last table keep their bytes.  Drawn per base: word i of stream DEAM. */
+static void deamMeth(const orc_ctx* c, const Damage& D, uint64_t id, std::string& seq, std::vector<int>* deamPos) {
+    const int len = (int)seq.size();
+    for (int i = 0; i < len; i++) {
+        const char originalBase = (char)toupper(seq[i]);
+        const bool isMethylated = originalBase != seq[i];                   /* :1638-1639 */
+        if (!isResolvedDNA(originalBase)) continue;                         /* :1651-1652 */
+        const bool five = i < len / 2;                                      /* :1661 */
+        const std::vector<double>& sub = five ? (isMethylated ? D.sub5m : D.sub5) : (isMethylated ? D.sub3m : D.sub3);
+        const double* row = effRow(sub, D.clamp_last, five ? i : len - i - 1);   /* :1665-1672, :1724-1731 */
+        if (!row) continue;
+        const int b = base2int(originalBase), a = categorical(row, b, u01(c->rng.word(id, ST_DEAM, (uint32_t)i)));
+        seq[i] = "ACGT"[a];
+        if (a != b && deamPos) deamPos->push_back(five ? i + 1 : -(len - i));   /* :1709-1711, :1770-1773 */
+    }
+}
+
 static void deaminate(const orc_ctx* c, int slot, uint64_t id, std::string& seq, std::vector<int>* deamPos = NULL) {
+    if (slot >= 0 && c->dmg[slot].mode == GG_DMG_METH) { deamMeth(c, c->dmg[slot], id, seq, deamPos); return; }   /* no toupper: deamSim.cpp:1319 */
     for (size_t i = 0; i < seq.size(); i++) seq[i] = (char)toupper(seq[i]);   /* deamSim.cpp:1319-1321 */
     if (slot < 0) return;
     const Damage& D = c->dmg[slot];
@@ -569,6 +594,15 @@ int orc_tables_set_matrix(orc_ctx* c, int slot, const double* sub5, int rows5, c
     if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || rows5 <= 0 || rows3 <= 0) return GG_ERR_ARG;
     Damage& D = c->dmg[slot]; D.mode = GG_DMG_MATRIX; D.clamp_last = clamp_last;
     D.sub5.assign(sub5, sub5 + (size_t)rows5 * 12); D.sub3.assign(sub3, sub3 + (size_t)rows3 * 12);
+    return 0;
+}
+int orc_tables_set_case(orc_ctx* c, int keep_case) { c->keep_case = keep_case ? 1 : 0; return 0; }
+int orc_tables_set_matrix_meth(orc_ctx* c, int slot, const double* no5, int rows_no5, const double* no3, int rows_no3,
+                               const double* wi5, int rows_wi5, const double* wi3, int rows_wi3, int clamp_last) {
+    if (slot < 0 || slot >= GG_MAX_DAMAGE_SLOTS || rows_no5 <= 0 || rows_no3 <= 0 || rows_wi5 <= 0 || rows_wi3 <= 0) return GG_ERR_ARG;
+    Damage& D = c->dmg[slot]; D = Damage(); D.mode = GG_DMG_METH; D.clamp_last = clamp_last;
+    D.sub5.assign(no5, no5 + (size_t)rows_no5 * 12); D.sub3.assign(no3, no3 + (size_t)rows_no3 * 12);
+    D.sub5m.assign(wi5, wi5 + (size_t)rows_wi5 * 12); D.sub3m.assign(wi3, wi3 + (size_t)rows_wi3 * 12);
     return 0;
 }
 int orc_tables_set_singledouble(orc_ctx* c, int slot, int protocol, const double* sub5, int rows5, const double* sub3, int rows3) {

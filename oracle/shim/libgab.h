@@ -52,7 +52,9 @@ inline int randomInt(int lo, int hi, bool fromTime = true) { shim_seed_once(from
 inline bool randomBool(bool fromTime = true) { shim_seed_once(fromTime); return (rand() & 0x10000) != 0; }
 inline string randomDNASeq(int n) { string s(n, 'A'); for (int i = 0; i < n; i++) s[i] = "ACGT"[(rand() >> 8) & 3]; return s; }
 
-inline bool isResolvedDNA(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+/* lower-case acgt count as resolved: fragSim --case (the documented --methyl mode, README "methylated and unmethylated") passes
+ * lower-case bases through isResolvedDNAstring (fragSim.cpp:333-339,1472) and could not emit a single methylated base otherwise */
+inline bool isResolvedDNA(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't'; }
 inline int baseResolved2int(char c) {
     if (c == 'A') return 0; if (c == 'C') return 1; if (c == 'G') return 2; if (c == 'T') return 3;
     cerr << "baseResolved2int: invalid base " << c << endl; exit(1);

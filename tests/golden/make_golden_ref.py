@@ -60,6 +60,40 @@ def main():
                                 "last_name": run([REF + "/deamSim", "-last", "-name", "-matfile", d + "/m-", src]).decode()}
         out["deam"]["briggs_all_ss"] = {"pars": [0, 1e-9, 0, 1], "name": run([REF + "/deamSim", "-name", "-damage", "0,0.000000001,0,1", src]).decode()}
         out["deam"]["briggs_all_ds"] = {"pars": [0, 1, 1, 0], "name": run([REF + "/deamSim", "-name", "-damage", "0,1,1,0", src]).decode()}
+        # ---- methylation mode (deamSim -matfilenonmeth / -matfilemeth, deamSim.cpp:1630-1787): records with per-base case (lower-case =
+        # methylated), some unresolved letters in both cases; tables of 0/1 rates with DIFFERENT row counts make the output deterministic
+        mrecs = []
+        for i in range(48):
+            n = int(rng.integers(8, 120))
+            b = synth._BASES[rng.integers(0, 4, size=n)].copy()
+            low = rng.random(n) < (0.5 if i % 3 else 0.15)
+            b[low] += 32
+            if i % 7 == 0:
+                b[int(rng.integers(0, n))] = ord("N"); b[int(rng.integers(0, n))] = ord("n")
+            mrecs.append(b">m%d:+:%d:%d:%d\n%s\n" % (i % 4, i * 7, i * 7 + n, n, b.tobytes()))
+        mdata = b"".join(mrecs)
+        msrc = os.path.join(d, "m.fa")
+        open(msrc, "wb").write(mdata)
+        out["meth_input"] = mdata.decode(); out["meth"] = {}
+        for key, no, wi in (("wi_ctga", (0.0, 0.0, 30, 25), (1.0, 1.0, 20, 15)), ("no_ct", (1.0, 0.0, 12, 40), (0.0, 0.0, 33, 9))):
+            for tag, (ct, ga, r5, r3) in (("no", no), ("wi", wi)):
+                s5 = np.zeros((r5, 12)); s3 = np.zeros((r3, 12))
+                s5[:, 5] = s3[:, 5] = ct; s5[:, 6] = s3[:, 6] = ga
+                synth.write_matrix_dat(d + "/%s-" % tag, s5, s3)
+            base = [REF + "/deamSim", "-matfilenonmeth", d + "/no-", "-matfilemeth", d + "/wi-"]
+            out["meth"][key] = {"no": list(no), "wi": list(wi),
+                                "plain": run(base + [msrc]).decode(), "name": run(base + ["-name", msrc]).decode(),
+                                "last_name": run(base + ["-last", "-name", msrc]).decode()}
+        # ---- fragSim --case (fragSim.cpp:318-326,548-551) on a contig exactly as long as the fragment (one admissible window): the
+        # record keeps the case of the file on the + strand and complements within the case on the - strand
+        seq = synth._BASES[rng.integers(0, 4, size=61)].copy(); seq[rng.random(61) < 0.4] += 32
+        fa, fai = synth.fasta_bytes([("cs", seq)], 23)
+        open(d + "/c.fa", "wb").write(fa); synth.write_fai(d + "/c.fa.fai", fai)
+        got = set()
+        for sd in range(1, 9):
+            got |= set(run([REF + "/fragSim", "--seed", str(sd), "--case", "-n", "8", "-l", "61", "-tag", "e", d + "/c.fa"]).decode().split("\n>"))
+        out["frag_case"] = {"fasta": fa.decode(), "fai": [[e.name, e.len, e.offset, e.line_blen, e.line_len] for e in fai],
+                            "records": sorted(">" + r.lstrip(">").rstrip("\n") + "\n" for r in got)}
     json.dump(out, open(os.path.join(HERE, "ref_exact.json"), "w"), indent=0)
     print("wrote ref_exact.json", os.path.getsize(os.path.join(HERE, "ref_exact.json")), "bytes")
 

@@ -478,3 +478,59 @@ def test_cli_streams_large_and_untidy_inputs(tmp_path, oracle_mod):
         f.seek(-71 * 1000, 2); tail = f.read()
     want_tail = open(big, "rb").read()[-71 * 1000:]
     assert [l for l in tail.split(b"\n")[0::2]] == [l for l in want_tail.split(b"\n")[0::2]]           # same deflines at the end: nothing lost or reordered
+
+
+@pytest.mark.gpu
+def test_methylation_through_the_clis_and_the_fused_driver(tmp_path, oracle_mod):
+    """--methyl: `bin/fragSim --case`, `bin/deamSim -matfilenonmeth -matfilemeth` and `bin/gargammel-b200 --methyl` against the
+    oracle's composition of the three loops on genomes with lower-case (methylated) bases."""
+    import gzip
+    from tests.test_driver_real import lower_some
+    d = tmp_path / "in"
+    files = {}
+    for sub, nm, seed in (("endo", "endo.1.fa", 31), ("cont", "cont.1.fa", 32), ("bact", "b1.fa", 33)):
+        (d / sub).mkdir(parents=True)
+        fa, fai = synth.make_genome(seed, 2, 40000, prefix=sub[0] + "_", n_frac=0.01, n_run=(10, 200))
+        fa = lower_some(fa, fai, seed)
+        (d / sub / nm).write_bytes(fa); synth.write_fai(str(d / sub / (nm + ".fai")), fai)
+        files[sub] = (fa, fai)
+    (d / "bact" / "list").write_text("b1.fa\t1.0\n")
+    no5, no3, wi5, wi3 = util.meth_tables()
+    synth.write_matrix_dat(str(tmp_path / "no-"), no5, no3); synth.write_matrix_dat(str(tmp_path / "wi-"), wi5, wi3)
+    synth.write_sizefreq(str(tmp_path / "sf.size"))
+    seed, n = 99, 20000
+    # ---- the three filters chained like gargammel.pl does it
+    r = run([os.path.join(BIN, "fragSim"), "--seed", str(seed), "--case", "-n", "5000", "-f", str(tmp_path / "sf.size"), "-tag", "e", "-o", str(tmp_path / "f.fa.gz"), str(d / "endo" / "endo.1.fa")])
+    assert r.returncode == 0, r.stderr
+    r = run([os.path.join(BIN, "deamSim"), "--seed", str(seed), "-matfilenonmeth", str(tmp_path / "no-"), "-matfilemeth", str(tmp_path / "wi-"), "-name", str(tmp_path / "f.fa.gz")])
+    assert r.returncode == 0, r.stderr
+    o = oracle_mod.OracleContext(seed)
+    o.set_case(True)
+    o.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=0, maxlen=1000)
+    o.set_matrix_meth(0, no5, no3, wi5, wi3)
+    gid = o.upload_genome(*files["endo"])
+    o.set_plan([api.Range(0, 5000, gid, 0, "e")])
+    frag = o.run_fused(0, 5000, api.EMIT_FRAG)[0]
+    util.assert_same(gzip.open(str(tmp_path / "f.fa.gz")).read(), frag, "bin/fragSim --case")
+    o.set_deam_naming(True)
+    util.assert_same(r.stdout, o.run_deam(frag, 0)[0], "bin/deamSim -matfilenonmeth -matfilemeth -name")
+    o.set_deam_naming(False)
+    for bad in (["-matfilemeth", str(tmp_path / "wi-")], ["-matfile", str(tmp_path / "no-"), "-matfilenonmeth", str(tmp_path / "no-"), "-matfilemeth", str(tmp_path / "wi-")]):
+        assert run([os.path.join(BIN, "deamSim")] + bad + [str(tmp_path / "f.fa.gz")]).returncode == 1       # deamSim.cpp:414-430
+    # ---- the fused driver
+    r = run([os.path.join(BIN, "gargammel-b200"), "--comp", "0.2,0.2,0.6", "-n", str(n), "-f", str(tmp_path / "sf.size"), "--methyl", "-matfilenonmeth", str(tmp_path / "no-"),
+             "-matfilemeth", str(tmp_path / "wi-"), "-rl", "75", "--seed", str(seed), "--keep", "--noart", "-o", str(tmp_path / "sim"), str(d)])
+    assert r.returncode == 0, r.stderr
+    o.set_adapters(read_len=75)
+    plan, first = [], 0
+    for sub, cnt, tag in (("endo", int(n * 0.6), "e"), ("bact", int(n * 0.2), "b1"), ("cont", int(n * 0.2), "c1")):
+        plan.append(api.Range(first, cnt, o.upload_genome(*files[sub]), 0, tag)); first += cnt
+    o.set_plan(plan)
+    util.assert_same((tmp_path / "sim_a.fa").read_bytes(), o.run_fused(0, first, api.EMIT_ARTP)[0], "gargammel-b200 --methyl _a.fa")
+    util.assert_same(gzip.open(str(tmp_path / "sim_d.fa.gz")).read(), o.run_fused(0, first, api.EMIT_DEAM)[0], "--methyl _d.fa.gz")
+    got = b"".join(gzip.open(str(tmp_path / ("sim.%s.fa.gz" % k))).read() for k in "ebc")
+    util.assert_same(got, o.run_fused(0, first, api.EMIT_FRAG)[0], "--methyl .e/.b/.c.fa.gz keep the case")
+    assert any(ch in got for ch in b"acgt")
+    r = run([os.path.join(BIN, "gargammel-b200"), "--methyl", "-matfilemeth", str(tmp_path / "wi-"), "-o", str(tmp_path / "x"), str(d)])
+    assert r.returncode == 1 and b"both" in r.stderr
+    o.close()

@@ -60,6 +60,7 @@ def mock_commands(t, extra):
     ["-s", "SL", "-mapdamage", "MIS", "double", "-rl", "100"],
     ["--loc", "4.1", "--scale", "0.35", "-matfilee", "M", "-damageb", "0.02,0.3,0.01,0.5", "-minsize", "30", "-maxsize", "200"],
     ["-f", "SF", "--misince", "DNACOMP", "--misincb", "DNACOMP", "--distmis", "2", "-uniq", "-matfile", "M"],
+    ["-l", "45", "--methyl", "-matfilenonmeth", "M", "-matfilemeth", "M"],
 ])
 def test_reference_driver_command_lines_are_accepted(layout, extra):
     import torch

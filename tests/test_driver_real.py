@@ -119,3 +119,70 @@ def run_and_check(t, bins):
         assert amp[:k] == frag[:k] and amp[150 - k:] == frag[len(frag) - k:]
     # ---- the ART stand-in saw every amplicon
     assert gzip.open(prefix + "_s1.fq.gz", "rb").read().count(b"\n") == 4 * len(a)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# gargammel.pl --methyl: fragSim --case for every source, deamSim -matfilenonmeth/-matfilemeth for every source
+def lower_some(fa, fai, seed, frac=0.35):
+    b = np.frombuffer(fa, dtype=np.uint8).copy()
+    rng = np.random.default_rng(seed)
+    seqb = np.zeros(len(b), dtype=bool)
+    for e in fai:
+        seqb[e.offset:e.offset + e.len + e.len // e.line_blen + 1] = True
+    low = (rng.random(len(b)) < frac) & seqb & (b >= 65) & (b <= 90)
+    return np.where(low, b | 0x20, b).astype(np.uint8).tobytes()
+
+
+def raw_contigs(fa, fai):
+    return {e.name: fa[e.offset:e.offset + e.len + e.len // e.line_blen + 1].replace(b"\n", b"")[:e.len] for e in fai}
+
+
+@pytest.mark.gpu
+def test_reference_driver_methyl_over_the_dropin_binaries(tmp_path):
+    run_methyl(tmp_path, os.path.join(ROOT, "bin"))
+
+
+def test_reference_driver_methyl_over_its_own_binaries(tmp_path):
+    run_methyl(tmp_path, os.path.join(ROOT, "oracle", "_ref", "src"))
+
+
+def run_methyl(t, bins):
+    gg = make_layout(t, bins)
+    d = t / "in"
+    raw = {}
+    for sub, nm, seed in (("endo", "endo.1.fa", 5), ("cont", "cont.1.fa", 6)):
+        (d / sub).mkdir(parents=True)
+        fa, fai = synth.make_genome(seed, 2, 50000, prefix=sub[0], n_frac=0.01, n_run=(20, 200))
+        fa = lower_some(fa, fai, seed)
+        (d / sub / nm).write_bytes(fa); synth.write_fai(str(d / sub / (nm + ".fai")), fai)
+        raw[sub[0]] = raw_contigs(fa, fai)
+    (d / "bact").mkdir()
+    no5, no3, wi5, wi3 = util.meth_tables()
+    synth.write_matrix_dat(str(t / "no-"), no5, no3); synth.write_matrix_dat(str(t / "wi-"), wi5, wi3)
+    (t / "out").mkdir()
+    prefix = str(t / "out" / "sim")
+    n = 8000
+    r = subprocess.run(["perl", str(gg / "gargammel.pl"), "--comp", "0,0.25,0.75", "-n", str(n), "-l", "48", "--methyl", "-matfilenonmeth", str(t / "no-"),
+                        "-matfilemeth", str(t / "wi-"), "-rl", "75", "-se", "-o", prefix, str(d) + "/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "Program finished successfully" in r.stderr
+    e, c, dd = (fasta_records(prefix + s) for s in (".e.fa.gz", ".c.fa.gz", "_d.fa.gz"))
+    assert (len(e), len(c)) == (int(n * 0.75), int(n * 0.25)) and len(dd) == n
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    for recs, kind in ((e, "e"), (c, "c")):
+        for hdr, seq in recs:
+            m = re.match(rb"^>([A-Za-z0-9_.]+):([+-]):(\d+):(\d+):(\d+)", hdr)
+            ref = raw[kind][m.group(1).decode()][int(m.group(3)):int(m.group(4))]
+            assert seq == (ref if m.group(2) == b"+" else ref.translate(comp)[::-1]), hdr     # fragSim --case: the bytes of the file, case included
+    assert any(ch in b"".join(s for _, s in e) for ch in b"acgt")
+    # every source went through deamSim with the two tables (gargammel.pl:1698-1811): all bases upper-case afterwards, and a methylated
+    # cytosine at the first base becomes T far more often than an unmethylated one
+    src = e + c
+    assert [h for h, _ in dd] == [h for h, _ in src]
+    assert not any(ch in b"".join(s for _, s in dd) for ch in b"acgtn")
+    for base, rate in ((b"c", wi5[0][5]), (b"C", no5[0][5])):
+        k = [(s0[:1], s1[:1]) for (_, s0), (_, s1) in zip(src, dd) if s0[:1] == base]
+        nT = sum(1 for _, z in k if z == b"T")
+        assert len(k) > 150 and abs(nT / len(k) - rate) < 5 * np.sqrt(rate * (1 - rate) / len(k)) + 1e-3, (base, nT, len(k), rate)
+    a = fasta_records(prefix + "_a.fa.gz")
+    assert [h for h, _ in a] == [h for h, _ in dd] and all(len(s) == 75 for _, s in a)

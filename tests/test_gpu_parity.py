@@ -524,3 +524,124 @@ def test_fused_bgzf_to_host_chunked(oracle_mod, genomes):
     with pytest.raises(api.GGError):
         g.run_fused_bgzf_to_host(0, 7500, api.EMIT_ARTP, C.addressof(buf), 1000, 1000)
     g.close(); o.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# methylation mode: fragSim --case keeps the case of the genome, deamSim -matfilenonmeth/-matfilemeth reads it
+def _case_genomes():
+    """genomes whose bases are lower-case one by one (methylation calls), not in stretches"""
+    out = []
+    for g, (fa, fai) in enumerate(util.tiny_genomes(seed=19)):
+        b = np.frombuffer(fa, dtype=np.uint8).copy()
+        rng = np.random.default_rng(100 + g)
+        letters = ((b >= 65) & (b <= 90)) | ((b >= 97) & (b <= 122))
+        hdr = np.zeros(len(b), dtype=bool)
+        for e in fai:                                                    # only the sequence lines change case
+            hdr[e.offset:e.offset + e.len + e.len // e.line_blen + 1] = True
+        up = np.where(letters & hdr, b & 0xDF, b)
+        low = (rng.random(len(b)) < 0.3) & letters & hdr
+        out.append((np.where(low, up | 0x20, up).astype(np.uint8).tobytes(), fai))
+    return out
+
+
+@pytest.mark.parametrize("sizes", ["freq", "fixed"])
+def test_fused_case_bit_exact(oracle_mod, sizes):
+    """fragSim --case (fragSim.cpp:318-326,548-551): records keep the case of the file; reverse-strand records complement within the case.
+    The later stages upper-case what they read, so only the fragSim records differ from a run without --case."""
+    genomes = _case_genomes()
+    g, o, ids = _pair(oracle_mod, genomes, sizes=sizes, damage="matrix", case=True)
+    plan = util.plan3(ids)
+    g.set_plan(plan); o.set_plan(plan)
+    a, ia = g.run_fused(0, 1200, api.EMIT_FRAG)
+    b, ib = o.run_fused(0, 1200, api.EMIT_FRAG)
+    util.assert_same(a, b, "--case fragSim records")
+    assert (ia.bytes, ia.attempts, ia.gather_bytes) == (ib.bytes, ib.attempts, ib.gather_bytes)
+    seqs = b"".join(s for _, s in util.records(a))
+    assert any(c in seqs for c in b"acgt") and any(c in seqs for c in b"ACGT")
+    for emit in ALL_EMITS[1:]:
+        util.assert_same(g.run_fused(0, 1200, emit)[0], o.run_fused(0, 1200, emit)[0], "--case emit=%d" % emit)
+    g2, o2, ids2 = _pair(oracle_mod, genomes, sizes=sizes, damage="matrix", case=False)
+    g2.set_plan(util.plan3(ids2))
+    plain = util.records(g2.run_fused(0, 1200, api.EMIT_FRAG)[0])      # same fragments, upper-cased
+    assert [(d, s_.upper()) for d, s_ in util.records(a)] == plain
+    for c in (g, o, g2, o2): c.close()
+
+
+def test_fused_case_on_the_circular_contig(oracle_mod):
+    """--case with --circ: the wrap image carries the case bits too"""
+    fa, fai = util.circ_genome()
+    b = np.frombuffer(fa, dtype=np.uint8).copy()
+    rng = np.random.default_rng(3)
+    seqb = np.zeros(len(b), dtype=bool)
+    for e in fai: seqb[e.offset:e.offset + e.len + e.len // e.line_blen + 1] = True
+    low = (rng.random(len(b)) < 0.4) & seqb & (b >= 65) & (b <= 90)
+    fa = np.where(low, b | 0x20, b).astype(np.uint8).tobytes()
+    with api.Context(0, 5) as g:
+        o = oracle_mod.OracleContext(5)
+        for c in (g, o):
+            c.set_case(True)
+            gid = c.upload_genome(fa, fai, circ=1)
+            c.set_sizes(api.SIZE_FIXED, fixed_len=70, maxlen=1000)
+            c.set_plan([api.Range(0, 3000, gid, -1, "mt")])
+        util.assert_same(g.run_fused(0, 3000, api.EMIT_FRAG)[0], o.run_fused(0, 3000, api.EMIT_FRAG)[0], "--case --circ")
+        o.close()
+
+
+@pytest.mark.parametrize("clamp", [True, False])
+@pytest.mark.parametrize("name", [False, True])
+def test_deam_methylation_standalone_bit_exact(oracle_mod, clamp, name):
+    """deamSim -matfilenonmeth/-matfilemeth (deamSim.cpp:1630-1787) over fragSim --case records plus hand-made ones (unresolved letters in
+    both cases, records shorter than the tables, empty sequence): bit-exact vs the oracle, with -name and -last"""
+    genomes = _case_genomes()
+    g, o, ids = _pair(oracle_mod, genomes, sizes="freq", damage="meth", case=True, clamp_last=clamp)
+    plan = util.plan3(ids)
+    g.set_plan(plan); o.set_plan(plan)
+    recs = g.run_fused(0, 1200, api.EMIT_FRAG)[0]
+    recs += b">odd:+:0:9:9\nacgNnTgca\n>one:+:0:1:1\nc\n>none:+:0:0:0\n\n>x:-:5:25:20\nRYacgtACGTnnNNacgtAC\n"
+    for c in (g, o): c.set_deam_naming(name)
+    a, ia = g.run_deam(recs, 0)
+    b, ib = o.run_deam(recs, 0)
+    util.assert_same(a, b, "methylation deamSim clamp=%s name=%s" % (clamp, name))
+    assert ia.records == ib.records == 1204
+    if clamp:                                                            # every resolved base came out upper-case; unresolved ones kept their case
+        body = b"".join(s for _, s in util.records(a))
+        assert not any(c in body for c in b"acgt") and b"n" in body
+    g.close(); o.close()
+
+
+def test_fused_methylation_plan_runs_as_stage_chain(oracle_mod):
+    """a plan whose every range uses a methylation slot: gg_run_fused chains fragSim(--case) -> deamSim -> adptSim stage kernels on the
+    device; every dialect, id sub-ranges and the host egress paths must equal the oracle's composition of the three loops"""
+    genomes = _case_genomes()
+    g, o, ids = _pair(oracle_mod, genomes, sizes="freq", damage="meth", case=True)
+    plan = util.plan3(ids, slots=(0, 0, 0))
+    g.set_plan(plan); o.set_plan(plan)
+    for emit in ALL_EMITS:
+        a, ia = g.run_fused(0, 1200, emit)
+        b, ib = o.run_fused(0, 1200, emit)
+        util.assert_same(a, b, "methylation chain emit=%d" % emit)
+        assert (ia.bytes, ia.records, ia.attempts, ia.gather_bytes) == (ib.bytes, ib.records, ib.attempts, ib.gather_bytes)
+    full = g.run_fused(0, 1200, api.EMIT_ARTP)[0]
+    assert b"".join(g.run_fused(a0, b0 - a0, api.EMIT_ARTP)[0] for a0, b0 in ((0, 1), (1, 399), (399, 400), (400, 1200))) == full
+    # methylated and unmethylated cytosines really deaminate at different rates: C->T at the first base of + strand records
+    fr = util.records(g.run_fused(0, 1200, api.EMIT_FRAG)[0]); dm = util.records(g.run_fused(0, 1200, api.EMIT_DEAM)[0])
+    lo = [d[1][:1] for f, d in zip(fr, dm) if f[1][:1] == b"c"]; up = [d[1][:1] for f, d in zip(fr, dm) if f[1][:1] == b"C"]
+    assert len(lo) > 30 and len(up) > 60 and lo.count(b"T") / len(lo) > 0.17 > 0.1 > up.count(b"T") / len(up)   # tables: 0.29 vs 0.026
+    # host egress: chunked copies and device BGZF
+    import ctypes as C
+    import zlib
+    cap = int(g.max_record_bytes(api.EMIT_ARTP)) * 1200 + 65536
+    buf = (C.c_uint8 * cap)()
+    n = g.run_fused_to_host(0, 1200, api.EMIT_ARTP, C.addressof(buf), cap, chunk=500).bytes
+    assert bytes(buf[:n]) == full
+    n = g.run_fused_bgzf_to_host(0, 1200, api.EMIT_ARTP, C.addressof(buf), cap, chunk=500).bytes
+    z = bytes(buf[:n]) + api.BGZF_EOF; out = b""
+    while z:
+        d = zlib.decompressobj(31); out += d.decompress(z); z = d.unused_data
+    assert out == full
+    # mixing a methylation slot with another model in one plan is refused (gargammel.pl:670-677)
+    util.set_damage(g, 1, "briggs")
+    g.set_plan(util.plan3(ids, slots=(0, 1, 0)))
+    with pytest.raises(api.GGError):
+        g.run_fused(0, 100, api.EMIT_ARTP)
+    g.close(); o.close()

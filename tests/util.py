@@ -31,7 +31,9 @@ def contig_seqs(fa, fai):
 
 
 def configure(ctx, genomes, sizes="freq", damage="matrix", read_len=75, minlen=0, maxlen=1000, norev=False,
-              adapters=(api.DEFAULT_ADAPTER_F, api.DEFAULT_ADAPTER_S), fixed_len=40, clamp_last=True, matrix="single-"):
+              adapters=(api.DEFAULT_ADAPTER_F, api.DEFAULT_ADAPTER_S), fixed_len=40, clamp_last=True, matrix="single-", case=False):
+    if case:
+        ctx.set_case(True)                                   # fragSim --case: before the uploads
     ids = [ctx.upload_genome(fa, fai) for fa, fai in genomes]
     if sizes == "freq":
         lens, cum = synth.golden_sizefreq()
@@ -71,10 +73,23 @@ def set_damage(ctx, slot, damage, clamp_last=True, matrix="single-"):
         ctx.set_singledouble(slot, api.DMG_SINGLE, s5, s3)
     elif damage == "double":
         ctx.set_singledouble(slot, api.DMG_DOUBLE, s5, s3)
+    elif damage == "meth":
+        no5, no3, wi5, wi3 = meth_tables()
+        ctx.set_matrix_meth(slot, no5, no3, wi5, wi3, clamp_last=clamp_last)
     elif damage == "none":
         ctx.clear_damage(slot)
     else:
         raise ValueError(damage)
+
+
+def meth_tables():
+    """-matfilenonmeth / -matfilemeth test tables with different row counts: unmethylated = the double-stranded profile cut to 9/7 rows,
+    methylated = the single-stranded profile with its C->T rates raised (methylated cytosines deaminate to T and are not repaired)."""
+    d5, d3 = synth.golden_matrix("double-")
+    s5, s3 = synth.golden_matrix("single-")
+    wi5, wi3 = s5.copy(), s3.copy()
+    wi5[:, 5] = np.minimum(0.9, 0.05 + 3.0 * wi5[:, 5]); wi3[:, 5] = np.minimum(0.9, 0.05 + 3.0 * wi3[:, 5])
+    return d5[:9].copy(), d3[:7].copy(), wi5, wi3
 
 
 def plan3(ids, counts=(400, 300, 500), tags=("e1_0", "b1", "c1"), slots=(0, 0, -1)):
