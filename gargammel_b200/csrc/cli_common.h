@@ -286,6 +286,52 @@ struct UniqSuffixer {
     }
 };
 
+// Unaligned BAM out (fragSim -b, deamSim -b, adptSim -bs/-bp; -u = members stored instead of deflated): records are serialised on
+// the host, the BGZF members are made by the device encoder (gg_bgzf_host; GG_HOST_BGZF=1: zlib on host threads)
+struct BamSink {
+    FILE* f; bool stored; std::vector<uint8_t> pend, host; uint64_t n_rec;
+    BamSink() : f(NULL), stored(false), n_rec(0) {}
+    bool open(const std::string& path, const ggh::BamHeader& h, bool uncompressed) {
+        f = fopen(path.c_str(), "wb"); stored = uncompressed;
+        if (f) ggh::bam_header_bytes(h, pend);
+        return f != NULL;
+    }
+    bool flush(gg_ctx* ctx, bool final) {
+        const size_t B = 0xff00, whole = final ? pend.size() : pend.size() / B * B;
+        if (whole) {
+            if (stored || getenv("GG_HOST_BGZF")) {
+                std::vector<uint8_t> z; std::string e;
+                if (!ggh::bgzf_compress(pend.data(), whole, 0, stored ? 0 : 1, z, false, e) || fwrite(z.data(), 1, z.size(), f) != z.size()) return false;
+            } else {
+                gg_out o; size_t n = 0;
+                if (gg_bgzf_host(ctx, pend.data(), whole, &o) != GG_OK) return false;
+                host.resize(o.bytes);
+                if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK || fwrite(host.data(), 1, n, f) != n) return false;
+            }
+            pend.erase(pend.begin(), pend.begin() + whole);
+        }
+        if (final) {
+            std::vector<uint8_t> z; std::string e;
+            if (!ggh::bgzf_compress(NULL, 0, 1, 1, z, true, e) || fwrite(z.data(), 1, z.size(), f) != z.size()) return false;     // EOF marker block
+        }
+        return true;
+    }
+    bool add(gg_ctx* ctx, const ggh::BamRecord& r) { ggh::bam_append_record(r, pend); n_rec++; return pend.size() >= (64u << 20) ? flush(ctx, false) : true; }
+    bool close(gg_ctx* ctx) { bool ok = f && flush(ctx, true); if (f) { ok = (fclose(f) == 0) && ok; f = NULL; } return ok; }
+};
+// the records of a 2-line stream, one callback per record: (id line without its first byte, sequence)
+template <class F> inline void for_each_record(const uint8_t* d, size_t n, F fn) {
+    size_t p = 0;
+    while (p < n) {
+        const uint8_t* e = (const uint8_t*)memchr(d + p, '\n', n - p); const size_t ie = e ? (size_t)(e - d) : n;
+        const size_t ss = std::min(ie + 1, n);
+        const uint8_t* e2 = (const uint8_t*)memchr(d + ss, '\n', n - ss); const size_t se = e2 ? (size_t)(e2 - d) : n;
+        fn(std::string((const char*)d + p + 1, ie - p - 1), std::string((const char*)d + ss, se - ss));
+        p = se + 1;
+    }
+}
+inline std::string command_line(int argc, char** argv) { std::string c; for (int i = 0; i < argc; i++) { c += argv[i]; c += " "; } return c; }
+
 // GG_PRINT_RSS=1: peak / current resident set of this process on stderr (the streaming CLIs promise a bounded one)
 inline void print_rss(const char* where) {
     if (!getenv("GG_PRINT_RSS")) return;

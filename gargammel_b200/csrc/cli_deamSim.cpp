@@ -4,6 +4,7 @@
 using namespace cli;
 
 int main(int argc, char** argv) {
+    std::string outBAM; bool uncompressedBAM = false;
     std::string outGz, matrixFile, profFile, mapdamageFile, mapdamageProtocol, matrix, matrixFileNoMeth, matrixFileWiMeth;
     bool useBriggs = false, seedSpecified = false, lastRowMatrix = true, matrixSpecified = false, putDeamInName = false;
     bool useBriggsss = false; double s5p = 0, s3p = 0, l5p = 0, l3p = 0;            // -damagess, deamSim.cpp:310-340
@@ -11,7 +12,7 @@ int main(int argc, char** argv) {
     const std::string usage = std::string("\t") + argv[0] + " [options]  [fasta file]\n\n This program reads a fasta file containing aDNA fragments and\n adds deamination according to a certain model (B200 build)\n\n" +
         "\t\t-o\t[fasta out]\t\t\tWrite fasta output as a zipped fasta\n\t\t-last\t\t\t\t\tdo not use the last matrix row beyond the matrix\n\t\t--seed\t[int]\n\n" +
         "\t\t-mapdamage  [mis.txt] [protocol]\n\t\t-profile  [prof file prefix]\n\t\t-matfile  [matrix file prefix]\n\t\t-mat      [single|double]\n\t\t-damage     [v,l,d,s]\n" +
-        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\t\t-matfilenonmeth  [matrix file prefix]\tRead the matrix file of substitutions for non-methylated Cs\n\t\t-matfilemeth  [matrix file prefix]\tRead the matrix file of substitutions for methylated Cs\n\tNot in this build: -b -u\n";
+        "\t\t-name\t\t\t\t\tPut a tag in the read name with deam bases\n\t\t-matfilenonmeth  [matrix file prefix]\tRead the matrix file of substitutions for non-methylated Cs\n\t\t-matfilemeth  [matrix file prefix]\tRead the matrix file of substitutions for methylated Cs\n\t\t-b\t[bam out]\t\t\tRead a BAM file, write a BAM file\n\t\t-u\t\t\t\t\tProduce uncompressed BAM\n";
     if (is_help(argc, argv)) { std::cout << "Usage:" << std::endl << std::endl << usage << std::endl; return 1; }   // deamSim.cpp:199-207
     for (int i = 1; i < argc - 1; i++) {                                            // deamSim.cpp:213-378
         const std::string a = argv[i];
@@ -59,7 +60,8 @@ int main(int argc, char** argv) {
         if (a == "-name") { putDeamInName = true; continue; }                        // deamSim.cpp:342-345
         if (a == "-matfilenonmeth") { matrixFileNoMeth = argv[++i]; continue; }      // deamSim.cpp:256-261
         if (a == "-matfilemeth") { matrixFileWiMeth = argv[++i]; continue; }         // deamSim.cpp:263-268
-        if (a == "-b" || a == "-u") return unsupported(a, "SURVEY.md 8f-4");
+        if (a == "-b") { outBAM = argv[++i]; continue; }                              // deamSim.cpp:347-352: BAM in, BAM out
+        if (a == "-u") { uncompressedBAM = true; continue; }                         // deamSim.cpp:354-357
         return die("Error: unknown option " + a);                                   // deamSim.cpp:376-377
     }
     const bool mapd = !mapdamageFile.empty();
@@ -72,6 +74,7 @@ int main(int argc, char** argv) {
     if (!profFile.empty() && (!matrixFile.empty() || noMeth || wiMeth)) return die("Please specify damage profile or substitution matrix");   // :407-412
     if (!matrixFile.empty() && noMeth && wiMeth) return die("Please specify matrix with/without methylation but not the overall matrix");     // :414-419
     if (noMeth != wiMeth) return die("Please specify both the matrix with/without methylation, not just one");                     // :421-430
+    if (!outGz.empty() && !outBAM.empty()) return die("Error: cannot specify both -o and -b");           // deamSim.cpp:432-435
     if (!seedSpecified) seed = time_seed();
     const std::string inputFile = argv[argc - 1];                                   // deamSim.cpp:436
 
@@ -103,6 +106,38 @@ int main(int argc, char** argv) {
         if (gg_tables_set_singledouble(ctx, 0, matrix == "single" ? GG_DMG_SINGLE : GG_DMG_DOUBLE, s5.data(), (int)(s5.size() / 12), s3.data(), (int)(s3.size() / 12)) != GG_OK) return gg_fail(ctx, "-mat");
     }
     gg_tables_set_deam_naming(ctx, putDeamInName ? 1 : 0);
+    if (!outBAM.empty()) {
+        // BAM in, BAM out (deamSim.cpp:1260-1286,1305-1310,2016-2024): every alignment keeps its fields, QueryBases are replaced and, with
+        // -name, the positions go into an XD:Z tag instead of the read name
+        ggh::BamHeader bh; std::vector<ggh::BamRecord> recs;
+        if (!ggh::bam_read(inputFile, bh, recs, err)) return die("Could not open input BAM file  " + inputFile);
+        ggh::bam_add_program(bh, "deamSim", command_line(argc, argv));
+        BamSink bam;
+        if (!bam.open(outBAM, bh, uncompressedBAM)) return die("Could not open output BAM file  " + outBAM);
+        std::vector<uint8_t> in, host; bool ok = true;
+        for (size_t r0 = 0; r0 < recs.size() && ok; ) {
+            in.clear(); size_t r1 = r0;
+            while (r1 < recs.size() && in.size() < STREAM_CHUNK_BYTES) { in.push_back('>'); in.insert(in.end(), recs[r1].name.begin(), recs[r1].name.end()); in.push_back('\n'); in.insert(in.end(), recs[r1].seq.begin(), recs[r1].seq.end()); in.push_back('\n'); r1++; }
+            gg_out o; size_t n = 0;
+            if (gg_run_deam(ctx, in.data(), in.size(), 0, (uint64_t)r0, &o) != GG_OK) return gg_fail(ctx, "deamSim kernel");
+            host.resize(o.bytes);
+            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+            size_t k = r0;
+            for_each_record(host.data(), n, [&](const std::string& name, const std::string& seq) {
+                if (k >= r1) { ok = false; return; }
+                ggh::BamRecord& R = recs[k++];
+                R.seq = seq;
+                if (name.size() > R.name.size()) R.add_tag_z("XD", name.substr(R.name.size() + 6));      // "_DEAM:" + list (deamSim.cpp:2018-2022)
+                ok = ok && bam.add(ctx, R);
+            });
+            ok = ok && k == r1;
+            r0 = r1;
+        }
+        if (!ok || !bam.close(ctx)) return die("Error: write failed");
+        gg_ctx_destroy(ctx);
+        std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << recs.size() << " sequences" << std::endl;
+        return 0;
+    }
     Sink out;
     if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); } else out.open_stdout();
     // reader thread -> GPU (this thread) -> writer thread: bounded memory whatever the input size, file I/O overlapped with the device work

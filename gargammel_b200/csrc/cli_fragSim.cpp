@@ -10,6 +10,7 @@ int main(int argc, char** argv) {
     bool uniqTags = false, tagb = false, gcBiasB = false; double gcBias = 0;
     std::string compFile; int distFromEnd = 1;                                      // fragSim.cpp:356-359
     std::string sizeList, sizeFreq, outGz, tag;
+    std::string outBAM; bool uncompressedBAM = false;                                // -b / -u, fragSim.cpp:384-385,398
     bool keepCase = false;                                                          // fragSim.cpp:387 (uppercase = true)
     bool circ = false; std::string circName;                                        // fragSim.cpp:388-389
     const std::string usage = std::string("\n This program takes a fasta file representing a chromosome and generates\n") +
@@ -24,7 +25,7 @@ int main(int argc, char** argv) {
         "\t\t--comp\t[file] --dist\t[n]\t\tbase composition at the fragment ends (mapDamage dnacomp.txt)\n" +
         "\t\t-uniq\t\t\t\t\tMake the fragment names unique by appending a counter (host-side pass, like the reference)\n" +
         "\t\t--circ\t[REF NAME]\t\t\tAssume [REF NAME] is circular\n" +
-        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\t\t--case\t\t\t\t\tDo not set the sequence to upper-case (default: uppercase the seqs.)\n\tNot in this build: --fq --trim5p -b -u\n";
+        "\t\t-gc\t[gc bias]\t\t\tUse GC bias factor\n\t\t--case\t\t\t\t\tDo not set the sequence to upper-case (default: uppercase the seqs.)\n\t\t-b\t[bam out]\t\t\tWrite output as an unaligned BAM file\n\t\t-u\t\t\t\t\tProduce uncompressed BAM (good for UNIX pipe)\n\tNot in this build: --fq --trim5p\n";
     if (is_help(argc, argv)) { std::cout << usage << std::endl; return 1; }        // fragSim.cpp:463-469
     for (int i = 1; i < argc - 1; i++) {                                            // fragSim.cpp:471-625
         const std::string a = argv[i];
@@ -46,10 +47,12 @@ int main(int argc, char** argv) {
         if (a == "--dist") { distFromEnd = (int)to_ll(argv[++i], "--dist"); continue; }
         if (a == "-gc") { gcBias = to_d(argv[++i], "-gc"); gcBiasB = true; continue; }      // fragSim.cpp:589-594
         if (a == "--circ") { circ = true; circName = argv[++i]; continue; }             // fragSim.cpp:553-557
-        if (a == "--trim5p" || a == "-b")
+        if (a == "-b") { outBAM = argv[++i]; continue; }                               // fragSim.cpp:531-536
+        if (a == "-u") { uncompressedBAM = true; continue; }                          // fragSim.cpp:538-541
+        if (a == "--trim5p")
             return unsupported(a, "SURVEY.md 8f-3");
         if (a == "--case") { keepCase = true; continue; }                              // fragSim.cpp:548-551
-        if (a == "--fq" || a == "-u") return unsupported(a, "SURVEY.md 8f-4");
+        if (a == "--fq") return unsupported(a, "SURVEY.md 8f-3");
         return die("Error: unknown option " + a);                                   // fragSim.cpp:622-623
     }
     if (specifiedLength && sizeFragments > maxLen)                                   // fragSim.cpp:638-643
@@ -65,6 +68,7 @@ int main(int argc, char** argv) {
     if (!sizeList.empty() && !sizeFreq.empty()) return die("Error: cannot specify -s with -f");          // :682-685
     if (specifiedLength && !sizeList.empty()) return die("Error: cannot specify -l and -s");             // :688-691
     if (specifiedLength && !sizeFreq.empty()) return die("Error: cannot specify -l and -f");             // :693-696
+    if (!outGz.empty() && !outBAM.empty()) return die("Error: cannot specify both -o and -b");           // fragSim.cpp:675-678
     if (tag.size() > 23) return die("Error: -tag longer than 23 characters");
     if (!seedSpecified) seed = time_seed();
     const std::string inFile = argv[argc - 1];                                      // fragSim.cpp:1026
@@ -108,6 +112,30 @@ int main(int argc, char** argv) {
         gg_range r; memset(&r, 0, sizeof r); r.first_id = 0; r.count = nFragments; r.genome = gid; r.damage_slot = -1; r.comp_slot = compFile.empty() ? -1 : 0; r.gc_slot = gcBiasB ? 0 : -1;
         snprintf(r.tag, sizeof r.tag, "%s", uniqTags ? "" : tag.c_str());        // with -uniq the tag goes after the count (fragSim.cpp:1505,131-133)
         if (gg_plan_set(ctx, &r, 1) != GG_OK) return gg_fail(ctx, "plan");
+    }
+    if (!outBAM.empty()) {                                                         // unaligned BAM: name = defline, flag 4, phred 0 (fragSim.cpp:1589-1601)
+        ggh::BamHeader bh; ggh::bam_add_program(bh, "fragSim", command_line(argc, argv));     // :1306-1315
+        BamSink bam;
+        if (!bam.open(outBAM, bh, uncompressedBAM)) return die("Cannot open write to BAM output file " + outBAM);
+        std::vector<uint8_t> host; UniqSuffixer uniq; uniq.reset(tag, tagb); std::string renamed; bool ok = true;
+        const uint64_t chunk = 4u << 20;
+        for (uint64_t first = 0; first < nFragments && ok; first += chunk) {
+            const uint64_t cnt = std::min<uint64_t>(chunk, nFragments - first);
+            gg_out o;
+            if (gg_run_fused(ctx, first, cnt, GG_EMIT_FRAG, &o) != GG_OK) return gg_fail(ctx, "fragSim kernel");
+            host.resize(o.bytes); size_t n = 0;
+            if (gg_out_fetch(ctx, &o, host.data(), host.size(), &n) != GG_OK) return gg_fail(ctx, "fetch");
+            const uint8_t* d = host.data();
+            if (uniqTags) { renamed.clear(); uniq.apply((const char*)host.data(), n, renamed); d = (const uint8_t*)renamed.data(); n = renamed.size(); }
+            for_each_record(d, n, [&](const std::string& name, const std::string& seq) {
+                ggh::BamRecord r; r.name = name; r.seq = seq; r.flag = 4; r.qual.assign(seq.size(), 0);
+                ok = ok && bam.add(ctx, r);
+            });
+        }
+        if (!ok || !bam.close(ctx)) return die("Error: write failed");
+        gg_ctx_destroy(ctx);
+        std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << nFragments << " sequences" << std::endl;
+        return 0;
     }
     Sink out;
     if (!outGz.empty()) { if (!out.open_gz(outGz)) return die("Cannot write to file " + outGz); }       // fragSim.cpp:1297-1303

@@ -441,6 +441,90 @@ bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vec
 }
 
 
+// ---------------------------------------------------------------- unaligned BAM (SAM/BAM specification section 4.2)
+namespace {
+void put_u32(std::vector<uint8_t>& o, uint32_t v) { for (int k = 0; k < 4; k++) o.push_back((uint8_t)(v >> (8 * k))); }
+void put_u16(std::vector<uint8_t>& o, uint16_t v) { o.push_back((uint8_t)v); o.push_back((uint8_t)(v >> 8)); }
+uint32_t get_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint8_t base4(char c) {
+    static const char* T = "=ACMGRSVTWYHKDBN";
+    if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    for (int k = 0; k < 16; k++) if (T[k] == c) return (uint8_t)k;
+    return 15;
+}
+}
+void bam_header_bytes(const BamHeader& h, std::vector<uint8_t>& out) {
+    out.push_back('B'); out.push_back('A'); out.push_back('M'); out.push_back(1);
+    put_u32(out, (uint32_t)h.text.size()); out.insert(out.end(), h.text.begin(), h.text.end());
+    put_u32(out, (uint32_t)h.refs.size());
+    for (size_t i = 0; i < h.refs.size(); i++) {
+        put_u32(out, (uint32_t)h.refs[i].first.size() + 1); out.insert(out.end(), h.refs[i].first.begin(), h.refs[i].first.end()); out.push_back(0);
+        put_u32(out, h.refs[i].second);
+    }
+}
+void bam_append_record(const BamRecord& r, std::vector<uint8_t>& out) {
+    const uint32_t l_seq = (uint32_t)r.seq.size(), l_name = (uint32_t)r.name.size() + 1;
+    const uint32_t block = 32 + l_name + 4 * (uint32_t)r.cigar.size() + (l_seq + 1) / 2 + l_seq + (uint32_t)r.aux.size();
+    put_u32(out, block); put_u32(out, (uint32_t)r.refid); put_u32(out, (uint32_t)r.pos);
+    out.push_back((uint8_t)l_name); out.push_back(r.mapq); put_u16(out, r.bin); put_u16(out, (uint16_t)r.cigar.size()); put_u16(out, r.flag);
+    put_u32(out, l_seq); put_u32(out, (uint32_t)r.next_refid); put_u32(out, (uint32_t)r.next_pos); put_u32(out, (uint32_t)r.tlen);
+    out.insert(out.end(), r.name.begin(), r.name.end()); out.push_back(0);
+    for (size_t k = 0; k < r.cigar.size(); k++) put_u32(out, r.cigar[k]);
+    for (uint32_t i = 0; i < l_seq; i += 2) out.push_back((uint8_t)((base4(r.seq[i]) << 4) | (i + 1 < l_seq ? base4(r.seq[i + 1]) : 0)));
+    if (r.qual.size() == l_seq) out.insert(out.end(), r.qual.begin(), r.qual.end()); else out.insert(out.end(), l_seq, (uint8_t)0xFF);
+    out.insert(out.end(), r.aux.begin(), r.aux.end());
+}
+bool bam_read(const std::string& path, BamHeader& h, std::vector<BamRecord>& recs, std::string& err) {
+    std::vector<uint8_t> raw;
+    if (!read_file(path, raw, err)) return false;                      // gzread inflates the BGZF members one after the other
+    const uint8_t* p = raw.data(); const size_t n = raw.size();
+    if (n < 12 || memcmp(p, "BAM\1", 4) != 0) { err = "Could not open input BAM file  " + path; return false; }
+    size_t q = 4;
+    const uint32_t l_text = get_u32(p + q); q += 4;
+    if (q + l_text + 4 > n) { err = "truncated BAM header in " + path; return false; }
+    h.text.assign((const char*)p + q, l_text); q += l_text;
+    while (!h.text.empty() && h.text[h.text.size() - 1] == '\0') h.text.erase(h.text.size() - 1);
+    const uint32_t n_ref = get_u32(p + q); q += 4;
+    h.refs.clear();
+    for (uint32_t i = 0; i < n_ref; i++) {
+        if (q + 4 > n) { err = "truncated BAM header in " + path; return false; }
+        const uint32_t l = get_u32(p + q); q += 4;
+        if (l == 0 || q + l + 4 > n) { err = "truncated BAM header in " + path; return false; }
+        h.refs.push_back(std::make_pair(std::string((const char*)p + q, l - 1), get_u32(p + q + l))); q += l + 4;
+    }
+    static const char* T = "=ACMGRSVTWYHKDBN";
+    while (q + 4 <= n) {
+        const uint32_t block = get_u32(p + q); q += 4;
+        if (block < 32 || q + block > n) { err = "truncated BAM record in " + path; return false; }
+        const uint8_t* b = p + q; q += block;
+        BamRecord r;
+        r.refid = (int32_t)get_u32(b); r.pos = (int32_t)get_u32(b + 4);
+        const uint32_t l_name = b[8]; r.mapq = b[9]; r.bin = (uint16_t)(b[10] | (b[11] << 8));
+        const uint32_t n_cig = (uint32_t)(b[12] | (b[13] << 8)); r.flag = (uint16_t)(b[14] | (b[15] << 8));
+        const uint32_t l_seq = get_u32(b + 16);
+        r.next_refid = (int32_t)get_u32(b + 20); r.next_pos = (int32_t)get_u32(b + 24); r.tlen = (int32_t)get_u32(b + 28);
+        const size_t need = 32 + (size_t)l_name + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + l_seq;
+        if (l_name == 0 || need > block) { err = "malformed BAM record in " + path; return false; }
+        const uint8_t* c = b + 32;
+        r.name.assign((const char*)c, l_name - 1); c += l_name;
+        for (uint32_t k = 0; k < n_cig; k++) { r.cigar.push_back(get_u32(c)); c += 4; }
+        r.seq.resize(l_seq);
+        for (uint32_t i = 0; i < l_seq; i++) r.seq[i] = T[(c[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
+        c += (l_seq + 1) / 2;
+        r.qual.assign(c, c + l_seq); c += l_seq;
+        r.aux.assign(c, b + block);
+        recs.push_back(r);
+    }
+    return true;
+}
+void bam_add_program(BamHeader& h, const std::string& id, const std::string& cmdline) {
+    if (h.text.empty()) h.text = "@HD\tVN:1.4\tSO:unsorted\n";
+    else if (h.text[h.text.size() - 1] != '\n') h.text += "\n";
+    std::string use = id;
+    for (int k = 1; h.text.find("\tID:" + use + "\t") != std::string::npos || h.text.find("\tID:" + use + "\n") != std::string::npos; k++) use = id + "." + std::to_string(k);
+    h.text += "@PG\tID:" + use + "\tPN:" + id + "\tCL:" + cmdline + "\tVN:b200\n";
+}
+
 // ---------------------------------------------------------------- Huffman-only deflate code (device BGZF encoder)
 namespace {
 // code lengths of an optimal prefix code, at most `limit` bits: plain Huffman, and while the tree is too deep the counts are
@@ -645,6 +729,36 @@ int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, doubl
     if (!ggh::load_dnacomp(path, dist, t, e)) return set_err(err, errcap, e);
     const size_t n = (size_t)2 * dist * 4 * 8;
     memcpy(s5p, t.s5p.data(), n); memcpy(s5m, t.s5m.data(), n); memcpy(s3p, t.s3p.data(), n); memcpy(s3m, t.s3m.data(), n); return 0;
+}
+int ggh_bam_from_fasta(const uint8_t* recs, size_t n, const char* path, char* err, int errcap) {
+    std::vector<uint8_t> bam; ggh::BamHeader h; ggh::bam_add_program(h, "test", "ggh_bam_from_fasta");
+    ggh::bam_header_bytes(h, bam);
+    size_t p = 0;
+    while (p < n) {
+        const uint8_t* e = (const uint8_t*)memchr(recs + p, '\n', n - p); const size_t ie = e ? (size_t)(e - recs) : n;
+        const size_t ss = std::min(ie + 1, n);
+        const uint8_t* e2 = (const uint8_t*)memchr(recs + ss, '\n', n - ss); const size_t se = e2 ? (size_t)(e2 - recs) : n;
+        ggh::BamRecord r; r.name.assign((const char*)recs + p + (recs[p] == '>' ? 1 : 0), ie - p - (recs[p] == '>' ? 1 : 0)); r.seq.assign((const char*)recs + ss, se - ss);
+        r.qual.assign(r.seq.size(), 0);
+        ggh::bam_append_record(r, bam);
+        p = se + 1;
+    }
+    std::vector<uint8_t> z; std::string e;
+    if (!ggh::bgzf_compress(bam.data(), bam.size(), 1, 0, z, true, e)) { snprintf(err, errcap, "%s", e.c_str()); return 1; }
+    FILE* f = fopen(path, "wb");
+    if (!f || fwrite(z.data(), 1, z.size(), f) != z.size()) { if (f) fclose(f); snprintf(err, errcap, "cannot write %s", path); return 1; }
+    fclose(f);
+    return 0;
+}
+int ggh_bam_to_fasta(const char* path, uint8_t* out, size_t cap, size_t* out_n, char* err, int errcap) {
+    ggh::BamHeader h; std::vector<ggh::BamRecord> recs; std::string e;
+    if (!ggh::bam_read(path, h, recs, e)) { snprintf(err, errcap, "%s", e.c_str()); return 1; }
+    std::string s;
+    for (size_t i = 0; i < recs.size(); i++) s += ">" + recs[i].name + "\n" + recs[i].seq + "\n";
+    *out_n = s.size();
+    if (s.size() > cap) { snprintf(err, errcap, "buffer too small"); return 1; }
+    memcpy(out, s.data(), s.size());
+    return 0;
 }
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum) {
     std::vector<int32_t> l; std::vector<double> c; ggh::lognormal_table(loc, scale, cap, l, c);

@@ -82,6 +82,28 @@ void crc32_tables(uint32_t t[4][256]);
 uint32_t crc32_x8n(uint64_t n_bytes);                       // multiply a CRC by this (crc32_mul) to append n_bytes zero-effect bytes
 uint32_t crc32_mul(uint32_t a, uint32_t b);
 
+// ---- unaligned BAM in/out (the reference goes through bamtools: fragSim.cpp:1305-1325,1589-1601, deamSim.cpp:1260-1286,
+// 2016-2024, adptSim.cpp:217-243,328-373).  Records are serialised as the SAM/BAM specification lays them out (little-endian; 4-bit
+// bases "=ACMGRSVTWYHKDBN"; qualities as raw phred, 0xFF = absent); the container is BGZF: members of <= 65280 bytes made by the device
+// encoder (gg_bgzf_host), by zlib on host threads, or stored (-u).
+struct BamRecord {
+    std::string name, seq;                  // seq in ASCII (upper-case IUPAC; "" = '*')
+    std::vector<uint8_t> qual;              // raw phred, one per base; empty = 0xFF for every base
+    std::vector<uint8_t> aux;               // tag bytes as they sit in the file
+    std::vector<uint32_t> cigar;
+    int32_t refid, pos, next_refid, next_pos, tlen; uint16_t flag, bin; uint8_t mapq;
+    BamRecord() : refid(-1), pos(-1), next_refid(-1), next_pos(-1), tlen(0), flag(4), bin(4680), mapq(0) {}     // bamtools' fresh BamAlignment; bin = reg2bin(-1, 0)
+    void add_tag_z(const char tag[2], const std::string& v) { aux.push_back((uint8_t)tag[0]); aux.push_back((uint8_t)tag[1]); aux.push_back('Z'); aux.insert(aux.end(), v.begin(), v.end()); aux.push_back(0); }
+};
+struct BamHeader { std::string text; std::vector<std::pair<std::string, uint32_t> > refs; };
+// "BAM\1" + text + references
+void bam_header_bytes(const BamHeader& h, std::vector<uint8_t>& out);
+void bam_append_record(const BamRecord& r, std::vector<uint8_t>& out);
+// the whole file: BGZF members inflated, header and records parsed
+bool bam_read(const std::string& path, BamHeader& h, std::vector<BamRecord>& recs, std::string& err);
+// "@PG\tID:..\tPN:..\tCL:..\tVN:.." appended to a header text (putProgramInHeader; an ID already present gets ".1", ".2", ...)
+void bam_add_program(BamHeader& h, const std::string& id, const std::string& cmdline);
+
 // ---- one genome file ready for upload ----
 struct GenomeFile { std::string path; std::vector<uint8_t> bytes; std::vector<FaiEntry> fai; uint64_t total_len; };
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err);
@@ -106,4 +128,7 @@ uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
 int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int eof_marker, uint8_t* out, size_t cap, size_t* out_n);
 int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, double* s3p, double* s3m, char* err, int errcap);   /* each [2*dist][4] */
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum);   /* cap+2 rows */
+/* BAM round trip for the tests: a 2-line FASTA record stream -> unaligned BAM file (flag 4, phred 0, stored BGZF members), and back */
+int ggh_bam_from_fasta(const uint8_t* recs, size_t n, const char* path, char* err, int errcap);
+int ggh_bam_to_fasta(const char* path, uint8_t* out, size_t cap, size_t* out_n, char* err, int errcap);
 }

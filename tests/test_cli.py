@@ -534,3 +534,59 @@ def test_methylation_through_the_clis_and_the_fused_driver(tmp_path, oracle_mod)
     r = run([os.path.join(BIN, "gargammel-b200"), "--methyl", "-matfilemeth", str(tmp_path / "wi-"), "-o", str(tmp_path / "x"), str(d)])
     assert r.returncode == 1 and b"both" in r.stderr
     o.close()
+
+
+@pytest.mark.gpu
+def test_cli_bam_modes(workdir, tmp_path):
+    """Unaligned BAM in/out: fragSim -b [-u], deamSim -b (BAM in, XD:Z tag with -name), adptSim -bs / -bp (flags 4 / 77+141,
+    XA:Z tag).  Every BAM run must hold exactly the names and sequences of the FASTA run with the same seed, in the fields the
+    reference fills (fragSim.cpp:1589-1601, deamSim.cpp:2016-2024, adptSim.cpp:328-373)."""
+    t = workdir[0]
+    seed = "31"
+    frag_args = ["--seed", seed, "-n", "3000", "-f", str(t / "sf.size"), "-tag", "e1_0"]
+    fa = run([os.path.join(BIN, "fragSim")] + frag_args + [str(t / "g.fa")])
+    assert fa.returncode == 0, fa.stderr
+    want = util.records(fa.stdout)
+    for extra, name in ((["-b"], "f.bam"), (["-u", "-b"], "fu.bam")):
+        r = run([os.path.join(BIN, "fragSim")] + frag_args + extra + [str(tmp_path / name), str(t / "g.fa")])
+        assert r.returncode == 0, r.stderr
+        text, recs = util.read_bam(str(tmp_path / name))
+        assert "@PG\tID:fragSim\tPN:fragSim\tCL:" in text
+        assert [(b">" + n, s) for n, _, s, _, _ in recs] == want
+        assert all(f == 4 and q == bytes(len(s)) and tg == {} for _, f, s, q, tg in recs)
+    assert os.path.getsize(tmp_path / "fu.bam") > 2 * os.path.getsize(tmp_path / "f.bam")       # -u stores, -b deflates (on the device)
+    assert run([os.path.join(BIN, "fragSim")] + frag_args + ["-o", str(tmp_path / "x.gz"), "-b", str(tmp_path / "x.bam"), str(t / "g.fa")]).returncode == 1
+    # ---- deamSim: BAM in, BAM out
+    (tmp_path / "f.fa").write_bytes(fa.stdout)
+    dm_args = ["--seed", seed, "-matfile", str(t / "m-"), "-name"]
+    dfa = run([os.path.join(BIN, "deamSim")] + dm_args + [str(tmp_path / "f.fa")])
+    assert dfa.returncode == 0, dfa.stderr
+    r = run([os.path.join(BIN, "deamSim")] + dm_args + ["-b", str(tmp_path / "d.bam"), str(tmp_path / "f.bam")])
+    assert r.returncode == 0, r.stderr
+    text, recs = util.read_bam(str(tmp_path / "d.bam"))
+    assert "ID:fragSim" in text and "ID:deamSim" in text
+    n_tagged = 0
+    for (hdr, seq), (name, flag, bseq, qual, tags), (h0, _) in zip(util.records(dfa.stdout), recs, want):
+        assert bseq == seq and flag == 4 and name == h0[1:]                      # the read name stays, the list goes into XD:Z
+        assert hdr == (h0 + b"_DEAM:" + tags["XD"].encode() if tags else h0)
+        n_tagged += bool(tags)
+    assert len(recs) == len(want) and n_tagged > 500
+    assert run([os.path.join(BIN, "deamSim")] + dm_args + ["-b", str(tmp_path / "e.bam"), str(tmp_path / "f.fa")]).returncode == 1       # not a BAM file
+    # ---- adptSim: BAM in, single-end / paired-end BAM out
+    ad_args = ["--seed", seed, "-l", "60"]
+    r = run([os.path.join(BIN, "adptSim")] + ad_args + ["-name", "-tag", "lib7", "-bp", str(tmp_path / "p.bam"), str(tmp_path / "d.bam")])
+    assert r.returncode == 0, r.stderr
+    (tmp_path / "d.fa").write_bytes(b"".join(b">" + n + b"\n" + s + b"\n" for n, _, s, _, _ in recs))
+    four = util.records(run([os.path.join(BIN, "adptSim")] + ad_args + [str(tmp_path / "d.fa")]).stdout)
+    text, prec = util.read_bam(str(tmp_path / "p.bam"))
+    assert "ID:adptSim" in text and len(prec) == 2 * len(recs) == len(four)
+    for k, ((hdr, seq), (name, flag, bseq, qual, tags)) in enumerate(zip(four, prec)):
+        src = recs[k // 2]
+        assert bseq == seq and len(seq) == 60 and qual == bytes(60) and name == src[0]        # both mates carry the input's name (adptSim.cpp:273-279)
+        assert flag == (141 if k & 1 else 77)
+        L0 = len(src[2])
+        assert tags["XA"] == ("AD" if L0 < 60 else "") + "lib7"
+    r = run([os.path.join(BIN, "adptSim")] + ad_args + ["-u", "-bs", str(tmp_path / "s.bam"), str(tmp_path / "d.bam")])
+    assert r.returncode == 0, r.stderr
+    _, srec = util.read_bam(str(tmp_path / "s.bam"))
+    assert [(n, f, s) for n, f, s, _, _ in srec] == [(n, 4, s) for (n, _, s, _, _) in prec[0::2]] and all(tg == {} for *_, tg in srec)

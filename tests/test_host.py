@@ -304,3 +304,25 @@ def test_deflate_code_for_device_bgzf():
     a, b = fasta[:1234], fasta[1234:]
     comb = lib.ggh_crc32_mul(C.c_uint32(zlib.crc32(a)), C.c_uint32(lib.ggh_crc32_x8n(C.c_uint64(len(b))))) ^ zlib.crc32(b)
     assert comb == zlib.crc32(fasta)
+
+
+def test_bam_writer_and_reader_round_trip(tmp_path):
+    """ggh::bam_append_record / bam_read (SAM/BAM specification 4.2) through the C exports: a record stream -> stored-BGZF BAM -> back;
+    the file is also parsed by the independent reader in tests/util.py (flag 4, no coordinates, phred 0, 4-bit bases, odd lengths)."""
+    import ctypes as C
+    from tests import util
+    lib = api.load_library()
+    recs = [(b"chr1:+:10:15:5e1_0", b"ACGTN"), (b"x", b""), (b"y:-:0:1:1", b"T"), (b"long" * 40, b"ACGTRYKMSWBDHVN" * 9000)]
+    data = b"".join(b">" + n + b"\n" + s + b"\n" for n, s in recs)
+    err = C.create_string_buffer(256)
+    path = str(tmp_path / "t.bam").encode()
+    assert lib.ggh_bam_from_fasta(data, C.c_size_t(len(data)), path, err, 256) == 0, err.value
+    text, got = util.read_bam(path.decode())
+    assert "@PG\tID:test" in text and text.startswith("@HD")
+    assert [(n, s) for n, _, s, _, _ in got] == recs
+    assert all(f == 4 and q == bytes(len(s)) and t == {} for _, f, s, q, t in got)
+    out = C.create_string_buffer(len(data) + 16); n = C.c_size_t()
+    assert lib.ggh_bam_to_fasta(path, out, C.c_size_t(len(out)), C.byref(n), err, 256) == 0, err.value
+    assert out.raw[:n.value] == data
+    open(str(tmp_path / "bad.bam"), "wb").write(b"not a bam")
+    assert lib.ggh_bam_to_fasta(str(tmp_path / "bad.bam").encode(), out, C.c_size_t(len(out)), C.byref(n), err, 256) != 0

@@ -123,3 +123,44 @@ def assert_same(a: bytes, b: bytes, what=""):
     if i is not None:
         lo = max(0, i - 60)
         raise AssertionError("%s: outputs differ at byte %d (lens %d vs %d)\n cuda  : %r\n oracle: %r" % (what, i, len(a), len(b), a[lo:i + 60], b[lo:i + 60]))
+
+
+def read_bam(path):
+    """Minimal reader of an unaligned BAM (SAM/BAM specification 4.2): returns (header text, [(name, flag, seq, qual bytes, {tag: value})]).
+    Every BGZF member is checked for the 'BC' extra field and inflated on its own."""
+    import struct
+    import zlib
+    z = open(path, "rb").read()
+    assert z[-28:] == api.BGZF_EOF, "BGZF EOF marker missing"
+    raw = b""
+    while z:
+        assert z[:4] == b"\x1f\x8b\x08\x04" and z[12:14] == b"BC", "not a BGZF member"
+        bsize = struct.unpack("<H", z[16:18])[0] + 1
+        d = zlib.decompressobj(31)
+        raw += d.decompress(z[:bsize])
+        assert d.eof and d.unused_data == b""
+        z = z[bsize:]
+    assert raw[:4] == b"BAM\x01"
+    l_text = struct.unpack("<i", raw[4:8])[0]
+    text = raw[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack("<i", raw[p:p + 4])[0]; p += 4
+    assert n_ref == 0
+    recs = []
+    while p < len(raw):
+        block = struct.unpack("<i", raw[p:p + 4])[0]; p += 4
+        b = raw[p:p + block]; p += block
+        refid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nref, npos, tlen = struct.unpack("<iiBBHHHiiii", b[:32])
+        assert (refid, pos, nref, npos, tlen, n_cig, mapq) == (-1, -1, -1, -1, 0, 0, 0)
+        q = 32
+        name = b[q:q + l_name - 1]; assert b[q + l_name - 1] == 0; q += l_name
+        packed = b[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
+        seq = bytes(b"=ACMGRSVTWYHKDBN"[(packed[i >> 1] >> (0 if i & 1 else 4)) & 15] for i in range(l_seq))
+        qual = b[q:q + l_seq]; q += l_seq
+        tags = {}
+        while q < len(b):
+            tag, typ = b[q:q + 2].decode(), chr(b[q + 2]); q += 3
+            assert typ == "Z"
+            e = b.index(b"\0", q); tags[tag] = b[q:e].decode(); q = e + 1
+        recs.append((name, flag, seq, qual, tags))
+    return text, recs
