@@ -463,12 +463,13 @@ void bam_header_bytes(const BamHeader& h, std::vector<uint8_t>& out) {
     }
 }
 void bam_append_record(const BamRecord& r, std::vector<uint8_t>& out) {
-    const uint32_t l_seq = (uint32_t)r.seq.size(), l_name = (uint32_t)r.name.size() + 1;
+    const size_t name_n = std::min<size_t>(r.name.size(), 254);            // l_read_name is one byte (incl. the NUL)
+    const uint32_t l_seq = (uint32_t)r.seq.size(), l_name = (uint32_t)name_n + 1;
     const uint32_t block = 32 + l_name + 4 * (uint32_t)r.cigar.size() + (l_seq + 1) / 2 + l_seq + (uint32_t)r.aux.size();
     put_u32(out, block); put_u32(out, (uint32_t)r.refid); put_u32(out, (uint32_t)r.pos);
     out.push_back((uint8_t)l_name); out.push_back(r.mapq); put_u16(out, r.bin); put_u16(out, (uint16_t)r.cigar.size()); put_u16(out, r.flag);
     put_u32(out, l_seq); put_u32(out, (uint32_t)r.next_refid); put_u32(out, (uint32_t)r.next_pos); put_u32(out, (uint32_t)r.tlen);
-    out.insert(out.end(), r.name.begin(), r.name.end()); out.push_back(0);
+    out.insert(out.end(), r.name.begin(), r.name.begin() + name_n); out.push_back(0);
     for (size_t k = 0; k < r.cigar.size(); k++) put_u32(out, r.cigar[k]);
     for (uint32_t i = 0; i < l_seq; i += 2) out.push_back((uint8_t)((base4(r.seq[i]) << 4) | (i + 1 < l_seq ? base4(r.seq[i + 1]) : 0)));
     if (r.qual.size() == l_seq) out.insert(out.end(), r.qual.begin(), r.qual.end()); else out.insert(out.end(), l_seq, (uint8_t)0xFF);

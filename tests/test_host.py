@@ -312,7 +312,7 @@ def test_bam_writer_and_reader_round_trip(tmp_path):
     import ctypes as C
     from tests import util
     lib = api.load_library()
-    recs = [(b"chr1:+:10:15:5e1_0", b"ACGTN"), (b"x", b""), (b"y:-:0:1:1", b"T"), (b"long" * 40, b"ACGTRYKMSWBDHVN" * 9000)]
+    recs = [(b"chr1:+:10:15:5e1_0", b"ACGTN"), (b"x", b""), (b"y:-:0:1:1", b"T"), (b"long" * 40, b"ACGTRYKMSWBDHVN" * 9000), (b"n" * 254, b"GG")]
     data = b"".join(b">" + n + b"\n" + s + b"\n" for n, s in recs)
     err = C.create_string_buffer(256)
     path = str(tmp_path / "t.bam").encode()
