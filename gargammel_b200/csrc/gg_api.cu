@@ -323,15 +323,17 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
                        int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false,
                        int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
     SmemLayout s; int o = align_up(fused_desc_bytes(), 16);   // fixed-layout per-fragment descriptors (WarpDesc, gg_kernels.cu)
-    o += 16;                                   // readable slack before staging
-    s.stage = o; s.stage_bytes = (int)((uint64_t)((F + 1) / 2) * rec_max); o += align_up(s.stage_bytes, 16) + 48;   // half a tile (+ misalignment pad (<16) + read slack)
+    o += 16;                                   // readable slack before staging / guard word in front of the damaged-fragment words
+    // the damaged-fragment words sit at a FIXED offset behind the descriptors (an immediate in the kernel's addressing).  adptSim
+    // dialects: staging aliases them (the words are dead once the line images exist, before staging is written) and is made large
+    // enough to hold them; fragSim / deamSim records: staging follows them
+    s.dwords = o;
+    s.stage_bytes = (int)((uint64_t)((F + 1) / 2) * rec_max);      // half a tile
+    const int dw_bytes = 4 * (F * max_chunks + 4);
+    if (alias_dwords) { s.stage = o; s.stage_bytes = std::max(s.stage_bytes, dw_bytes); }
+    else { o += align_up(dw_bytes, 16) + 16; s.stage = o; }
+    o += align_up(s.stage_bytes, 16) + 48;     // (+ misalignment pad (<16) + read slack)
     s.bh = o; o += 8 * F;
-    if (alias_dwords && s.stage_bytes >= 4 * (F * max_chunks + 4)) {
-        s.dwords = s.stage;                    // adptSim dialects: the damaged words are dead once the line images exist, before staging is written
-    } else {
-        o += 4;                                // guard word in front of the damaged-fragment words
-        s.dwords = o; o += 4 * (F * max_chunks + 4);
-    }
     s.lwords = o; o += 4 * (F * line_words + 4);
     s.cmap = o; o += F * max_chunks;
     s.gmap = o; o += F * max_groups;           // (only the fragSim / deamSim dialects use the group map)

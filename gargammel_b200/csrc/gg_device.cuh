@@ -316,8 +316,10 @@ __device__ __forceinline__ int ascii2code(uint8_t c) {   // upper-case input; -1
 }
 __device__ __forceinline__ uint8_t code2ascii(uint32_t b) { return (uint8_t)(0x54474341u >> (8 * b)); }
 __device__ __forceinline__ uint8_t upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
-__device__ __forceinline__ uint8_t complement_ascii(uint8_t c) {
-    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+__device__ __forceinline__ uint8_t complement_ascii(uint8_t c) {    // lower-case letters complement within their case (raw adapters given in lower case)
+    const uint8_t u = c & 0xDF, lc = c & 0x20;
+    const uint8_t r = u == 'A' ? 'T' : u == 'C' ? 'G' : u == 'G' ? 'C' : u == 'T' ? 'A' : 0;
+    return (r && ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) ? (uint8_t)(r | lc) : 'N';
 }
 
 static __constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
