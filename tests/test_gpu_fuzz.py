@@ -32,12 +32,15 @@ def _random_case(rng, tmp_path):
     case["damage"] = [str(rng.choice(DAMAGES)) for _ in range(3)]
     case["comp_dist"] = int(rng.choice([0, 0, 1, 3]))
     case["gc"] = bool(rng.random() < 0.2)
+    case["case"] = bool(rng.random() < 0.25)                      # fragSim --case; half of those runs use the methylation tables for every range
+    case["meth"] = case["case"] and bool(rng.random() < 0.5)
     case["seed"] = int(rng.integers(0, 2**62))
     case["counts"] = [int(rng.integers(1, 400)) for _ in range(n_genomes + 1)]
     return case
 
 
 def _setup(ctx, case, tabs):
+    ctx.set_case(case["case"])
     ids = [ctx.upload_genome(fa, fai, circ=c) for (fa, fai), c in zip(case["genomes"], case["circ"])]
     if case["sizes"] == "freq":
         ctx.set_sizes(api.SIZE_FREQ, *synth.golden_sizefreq(), minlen=case["minlen"], maxlen=case["maxlen"])
@@ -49,7 +52,7 @@ def _setup(ctx, case, tabs):
         ctx.set_sizes(api.SIZE_FIXED, fixed_len=case["fixed_len"], minlen=0, maxlen=1000)
     ctx.set_norev(case["norev"])
     for slot, dm in enumerate(case["damage"]):
-        util.set_damage(ctx, slot, dm, clamp_last=(slot != 1))
+        util.set_damage(ctx, slot, "meth" if (case["meth"] and slot == 0) else dm, clamp_last=(slot != 1))
     ctx.set_adapters(case["adapters"][0], case["adapters"][1], case["read_len"])
     if tabs is not None:
         ctx.set_composition(0, case["comp_dist"], *tabs)
@@ -59,6 +62,8 @@ def _setup(ctx, case, tabs):
     for k, cnt in enumerate(case["counts"]):
         g = ids[k % len(ids)]
         slot = [0, 1, 2, -1][k % 4] if case["damage"][k % 3] != "none" else -1
+        if case["meth"]:
+            slot = 0
         plan.append(api.Range(first, cnt, g, slot, ["e1_0", "b12", "c1", ""][k % 4], 0 if (tabs is not None and k % 2 == 0) else -1,
                               0 if (case["gc"] and g == ids[0] and k % 2 == 0) else -1))
         first += cnt
@@ -116,7 +121,7 @@ def test_random_record_streams_bit_exact(oracle_mod, block):
         data = b"".join(recs)
         seed = int(rng.integers(0, 2**62)); first_id = int(rng.integers(0, 2**40))
         g = api.Context(0, seed); o = oracle_mod.OracleContext(seed)
-        dm = str(rng.choice(["matrix", "briggs", "briggs_ss", "single", "double"]))
+        dm = str(rng.choice(["matrix", "briggs", "briggs_ss", "single", "double", "meth"]))
         name, clamp = bool(rng.random() < 0.5), bool(rng.random() < 0.7)
         rl = int(rng.choice([20, 75, 130])); tag = str(rng.choice(["", "x", "lib_42"])); addname = bool(rng.random() < 0.5)
         for c in (g, o):
