@@ -5,6 +5,8 @@ G=gpurun_out; P=profiles
 cp $G/${TAG}_bench.json $G/${TAG}_bench_ref.json $G/${TAG}_launches.csv $G/${TAG}_gpu.csv $P/
 [ -f $G/${TAG}_c1_16m.json ] && cp $G/${TAG}_c1_16m.json $G/${TAG}_c1_launches.csv $P/
 [ -f $G/${TAG}_pytest.log ] && tail -5 $G/${TAG}_pytest.log > $P/${TAG}_pytest_tail.txt
+[ -f $G/${TAG}_smoke.log ] && tail -1 $G/${TAG}_smoke.log >> $P/${TAG}_pytest_tail.txt
+[ -f $G/${TAG}_configs.jsonl ] && grep "^{" $G/${TAG}_configs.jsonl > $P/${TAG}_configs.jsonl
 python scripts/ncu_lines.py $G/${TAG}_fused.ncu-rep 60 > $P/${TAG}_fused_ncu_summary.txt
 python scripts/ncu_passes.py $G/${TAG}_fused.ncu-rep > $P/${TAG}_fused_ncu_passes.txt
 ncu -i $G/${TAG}_fused.ncu-rep --page details > $P/${TAG}_fused_ncu_details.txt
