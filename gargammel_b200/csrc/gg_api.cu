@@ -481,7 +481,7 @@ int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_
     uint32_t* d_len = (uint32_t*)(d_gb + nc); int32_t* d_bl = (int32_t*)(d_len + nc); int32_t* d_ll = d_bl + nc;
     void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
     cudaError_t e = pool_alloc(ctx, (H.n_units * 2 + 4) * 4, &p1, &H.seq2_bytes);
-    if (e == cudaSuccess) e = pool_alloc(ctx, (H.n_units + 4) * 4, &p2, &H.nmask_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (H.n_units + 8) * 4, &p2, &H.nmask_bytes);   // slack: pass A reads the mask in aligned 16-byte pieces
     if (e == cudaSuccess && ctx->keep_case) e = pool_alloc(ctx, (H.n_units + 4) * 4, &p3, &H.cmask_bytes);   // --case: one more bit per base
     H.d_seq2 = (uint32_t*)p1; H.d_nmask = (uint32_t*)p2; H.d_cmask = (uint32_t*)p3;
 #define TRY(x) if (e == cudaSuccess) e = (x)
@@ -494,7 +494,7 @@ int gg_genome_upload_circ(gg_ctx* ctx, const uint8_t* fasta, size_t n, const gg_
     // every unit (incl. the guard units in front and the slack behind) is written by the pack kernel
     TRY(launch_pack_genome(d_fa, n, d_off, d_len, d_bl, d_ll, d_gb, (int)nc, wrap_desc, wrap_keff, wrap_srclen, H.n_units, H.d_seq2, H.d_nmask, H.d_cmask, ctx->st));
     TRY(cudaMemsetAsync(H.d_seq2 + H.n_units * 2, 0, 16, ctx->st));
-    TRY(cudaMemsetAsync(H.d_nmask + H.n_units, 0xFF, 16, ctx->st));
+    TRY(cudaMemsetAsync(H.d_nmask + H.n_units, 0xFF, 32, ctx->st));
     if (H.d_cmask) TRY(cudaMemsetAsync(H.d_cmask + H.n_units, 0, 16, ctx->st));
     TRY(cudaStreamSynchronize(ctx->st));
 #undef TRY
@@ -944,7 +944,8 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int hdr_max; uint64_t rec_max; plan_bounds(ctx, emit, Lmax, &hdr_max, &rec_max);
     const int Smax = emit_seqlen(emit, Lmax, ctx->read_len);
     const int max_chunks = (Lmax + 15) / 16, max_groups = emit_lines(emit) * ((Smax + 15) / 16 + 1);
-    const int line_words = emit >= GG_EMIT_STDOUT4 ? emit_lines(emit) * ((Smax + 15) / 16 + 2) : 0;   // packed line images (adptSim dialects)
+    // packed line images (adptSim dialects); an odd word stride per fragment: the owner lanes' accesses then fall into 32 different banks
+    const int line_words = emit >= GG_EMIT_STDOUT4 ? ((emit_lines(emit) * ((Smax + 15) / 16 + 2)) | 1) : 0;
     // whole-group stores need >= 13 header bytes between two sequence lines: name + tag + 9 >= 13
     size_t min_name_tag = 1000;
     for (size_t i = 0; i < ctx->plan.size(); i++) {
@@ -979,6 +980,20 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
             }
         if (thr_bytes > 48 * 1024) { dmode = 0; thr_bytes = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) thr_slot[sl] = term_slot[sl] = -1; }   // huge matrices: read them from global
     }
+    // ... and so do the skip tables of the event draws (matrix- or Briggs-only plans): the first Lmax+1 thresholds (a skip never exceeds
+    // the record) and the 512-byte guide, once per slot (matrix) or twice (Briggs: rate s, rate d)
+    int geo_n = 0, geo_slot[GG_MAX_DAMAGE_SLOTS] = {-1, -1, -1, -1};
+    if ((dmode == 1 || dmode == 2) && emit != GG_EMIT_FRAG) {
+        geo_n = (std::min(GEO_TABLE, Lmax + 1) + 3) & ~3;
+        int tb = thr_bytes;
+        for (size_t i = 0; i < ctx->plan.size(); i++) {
+            const int sl = ctx->plan[i].damage_slot;
+            if (sl < 0 || geo_slot[sl] >= 0 || ctx->dmg[sl].mode != (dmode == 1 ? GG_DMG_MATRIX : GG_DMG_BRIGGS)) continue;
+            geo_slot[sl] = tb; tb += (dmode == 1 ? 1 : 2) * (4 * geo_n + 512);
+        }
+        if (tb <= 56 * 1024) thr_bytes = tb;
+        else { dmode = 0; thr_bytes = 0; geo_n = 0; for (int sl = 0; sl < GG_MAX_DAMAGE_SLOTS; sl++) geo_slot[sl] = thr_slot[sl] = term_slot[sl] = -1; }   // (records of thousands of bases: the general variant reads its tables from global memory)
+    }
     int regs = 64, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, emitc, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
     int F = 32;
@@ -1004,7 +1019,8 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
                                     (ctx->adF.size() <= 512 && ctx->adS.size() <= 512 && emit >= GG_EMIT_STDOUT4) ? (int)(1 + (ctx->adS.size() + 15) / 16 + 3) : 0);
         if ((size_t)st.total <= sm_budget) sm = st;
     }
-    for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) { sm.thr_slot[i] = thr_slot[i]; sm.term_slot[i] = term_slot[i]; }
+    for (int i = 0; i < GG_MAX_DAMAGE_SLOTS; i++) { sm.thr_slot[i] = thr_slot[i]; sm.term_slot[i] = term_slot[i]; sm.geo_slot[i] = geo_slot[i]; }
+    sm.geo_n = geo_n;
     const uint64_t n_tiles64 = (count + (uint64_t)F - 1) / (uint64_t)F;
     if (n_tiles64 > 0x7FFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_run_fused: too many fragments for one run; split the id range");
     const int n_tiles = (int)n_tiles64;
@@ -1024,13 +1040,13 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     FusedParams P; memset(&P, 0, sizeof P);
     P.first = first; P.count = count; P.F = F; P.n_tiles = n_tiles; P.emit = emit; P.norev = ctx->norev; P.fast_boundary = fast_boundary; P.dmode = dmode;
     if (emitc) {                                     // adptSim dialects: the sequence-line geometry is the same for every fragment
-        P.S_ad = Smax; P.LWL = (Smax + 15) / 16 + 2; P.lw_stride = emit_lines(emit) * P.LWL;
+        P.S_ad = Smax; P.LWL = (Smax + 15) / 16 + 2; P.lw_stride = line_words;
         P.gpl_ad = (uint32_t)((Smax + 15) / 16 + 1); P.gpf_ad = (uint32_t)emit_lines(emit) * P.gpl_ad;
         P.gmagic = (uint32_t)((0x100000000ull + P.gpf_ad - 1) / P.gpf_ad);
         P.sfx0 = emit == GG_EMIT_RR ? 2 : 0;
     }
     P.E = (F + 1) / 2; P.lut = 0x54474341u;
-    P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32);
+    P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32); P.ks = ggd::make_key_sched(P.key.k0, P.key.k1);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();
     P.ctab.cum_end = ctx->d_cum_end.as<uint64_t>(); P.ctab.gbase = ctx->d_gbase.as<uint64_t>(); P.ctab.len = ctx->d_clen.as<uint32_t>();

@@ -28,10 +28,31 @@ struct Key { uint32_t k0, k1; };
 __device__ __forceinline__ uint4 rng_block(const Key& k, uint64_t id, uint32_t blk, uint32_t stream) {
     return philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), blk, stream, k.k0, k.k1);
 }
+// The same generator with its ten round keys precomputed on the host.  As a field of a __grid_constant__ kernel parameter the keys are
+// constant-bank operands of the XORs: the two key additions per round (20 of ~60 instructions per block) disappear.
+struct KeySched { uint32_t a[10], b[10]; };
+__host__ __device__ inline KeySched make_key_sched(uint32_t k0, uint32_t k1) {
+    KeySched K;
+    for (int r = 0; r < 10; r++) { K.a[r] = k0 + (uint32_t)r * 0x9E3779B9u; K.b[r] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    return K;
+}
+__device__ __forceinline__ uint4 rng_block(const KeySched& K, uint64_t id, uint32_t blk, uint32_t stream) {
+    uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = blk, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.a[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.b[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 __device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
     return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
-__device__ __forceinline__ uint32_t rng_word(const Key& k, uint64_t id, uint32_t stream, uint32_t w) {
+template <class KeyT>
+__device__ __forceinline__ uint32_t rng_word(const KeyT& k, uint64_t id, uint32_t stream, uint32_t w) {
     return pick(rng_block(k, id, w >> 2, stream), (int)(w & 3));
 }
 
@@ -140,10 +161,13 @@ __device__ __forceinline__ int first_below_geo(const uint32_t* __restrict__ thr,
 // The same inverse CDF for the hot draws (the skips of the event draws): guide[u31 >> 22] = first k whose threshold lies above the cell's
 // lower edge, then a short upward scan; one byte load + (usually) one threshold load.  Entries of 255 mean "255 or later".  The scan
 // stops at lim <= n (the positions that are left): a result of lim means "lim or more".
+// SM: thr / guide are shared-memory copies (plain loads; a skip is two DEPENDENT loads and a fragment draws several skips in a row, so with
+// the tables in global memory -- L1 is a few KB next to a full shared-memory carve-out -- the event pass waits on L2 most of the time)
+template <bool SM = false>
 __device__ __forceinline__ int first_below_guided(const uint32_t* __restrict__ thr, const uint8_t* __restrict__ guide, int lim, uint32_t u) {
-    int k = (int)__ldg(guide + (u >> 22));
+    int k = SM ? (int)guide[u >> 22] : (int)__ldg(guide + (u >> 22));
 #pragma unroll 1
-    while (k < lim && u >= __ldg(thr + k)) k++;
+    while (k < lim && u >= (SM ? thr[k] : __ldg(thr + k))) k++;
     return min(k, lim);
 }
 // Briggs per-fragment header draws (deamSim.cpp:1478-1483,1503-1507)
@@ -180,12 +204,30 @@ __device__ __forceinline__ int matrix_row(const DamageDev& D, int i, int L) {
 }
 // PH: bit 0 = 5' terminal positions, bit 1 = interior, bit 2 = 3' terminal positions (deamSim -name walks them in this order);
 // TSM: term/acc are shared-memory copies (plain loads) instead of global tables
-template <int PH, bool TSM, class SeqT>
-__device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D, const uint4* term, const uint4* acc, SeqT& S, int L, uint64_t id) {
+// GSM: geoM / guideA point at shared-memory copies of the skip table (its first entries: a skip never exceeds the record) and its guide
+template <int PH, bool TSM, bool GSM, class SeqT, class KeyT>
+__device__ __forceinline__ void matrix_events(const KeyT& key, const DamageDev& D, const uint4* term, const uint4* acc, const uint32_t* geoM, const uint8_t* guideA,
+                                              SeqT& S, int L, uint64_t id) {
     const int half = L >> 1;                                    // positions i < half are on the 5' side (deamSim.cpp:1805)
     const int n5 = min(D.n5t, half), n3 = min(D.n3t, L - half);
     const uint32_t b3 = (uint32_t)(D.n5t + 3) >> 2, bg = b3 + ((uint32_t)(D.n3t + 3) >> 2);
-    if (PH & 1) {
+    if (PH == 7) {
+        // both ends in one loop (the order of the positions does not matter when nobody lists the events): step s < n5 is the 5' terminal
+        // position s, step n5 + t the 3' terminal position L-1-t; a block is drawn when the step enters it.  One copy of the generator and
+        // of the categorical draw instead of eight: the kernel's hot code has to fit the 32 KB instruction cache.
+        uint4 x = make_uint4(0, 0, 0, 0); uint32_t have = 0xFFFFFFFFu;
+#pragma unroll 1
+        for (int s = 0; s < n5 + n3; s++) {
+            const bool five = s < n5;
+            const int t = five ? s : s - n5;
+            const uint32_t blk = (five ? 0u : b3) + ((uint32_t)t >> 2);
+            if (blk != have) { x = rng_block(key, id, blk, ST_DEAM); have = blk; }
+            const int i = five ? t : L - 1 - t;
+            const int b = S.code(i);
+            if (b >= 0) { const int ti = ((five ? 0 : D.n5t) + t) * 4 + b; const uint4 T = TSM ? term[ti] : __ldg(term + ti); S.put(i, (uint32_t)b, count_le(pick(x, t & 3) >> 1, T)); }
+        }
+    }
+    if (PH != 7 && (PH & 1)) {
 #pragma unroll 1
         for (int t0 = 0; t0 < n5; t0 += 4) {
             const uint4 x = rng_block(key, id, (uint32_t)t0 >> 2, ST_DEAM);
@@ -208,7 +250,7 @@ __device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D
             for (int sub = 0; sub < 2; sub++) {
                 if (pos < end) {
                     const int lim = min(D.n_geo, end - pos);    // a skip of lim or more ends the walk (or, off a table shorter than the record, goes on from there)
-                    const int j = first_below_guided(D.geoM, D.guideA, lim, (sub ? x.z : x.x) >> 1);
+                    const int j = first_below_guided<GSM>(geoM, guideA, lim, (sub ? x.z : x.x) >> 1);
                     pos += j;
                     if (j < lim) {
                         const int b = S.code(pos);
@@ -224,7 +266,7 @@ __device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D
             }
         }
     }
-    if (PH & 4) {
+    if (PH != 7 && (PH & 4)) {
 #pragma unroll 1
         for (int t0 = ((n3 - 1) >> 2) << 2; t0 >= 0; t0 -= 4) {     // t descending = position ascending
             const uint4 x = rng_block(key, id, b3 + ((uint32_t)t0 >> 2), ST_DEAM);
@@ -246,8 +288,10 @@ __device__ __forceinline__ void matrix_events(const Key& key, const DamageDev& D
 // double-stranded middle.  A candidate changes iff its base is the one its region deaminates: C->T in the 5' overhang / before the
 // nick, G->A in the 3' overhang / from the nick on; both are "flip the high bit of the code".
 // PH: bit 0 = 5' overhang (or everything, when all single-stranded), bit 1 = middle, bit 2 = 3' overhang.
-template <int PH, class SeqT>
-__device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D, const BriggsHdr& B, SeqT& S, int L, uint64_t id) {
+// GSM: geoS / guideA / geoD / guideB point at shared-memory copies (see matrix_events)
+template <int PH, bool GSM, class SeqT, class KeyT>
+__device__ __forceinline__ void briggs_events(const KeyT& key, const DamageDev& D, const BriggsHdr& B, const uint32_t* geoS, const uint8_t* guideA,
+                                              const uint32_t* geoD, const uint8_t* guideB, SeqT& S, int L, uint64_t id) {
     const bool allss = B.o5 + B.o3 >= L;                            // deamSim.cpp:1483
     const int nS = allss ? L : B.o5 + B.o3, qend = allss ? L : L - B.o3;
     int v = (PH & 5) ? 0 : nS, q = (PH & 2) ? (allss ? L : B.o5) : qend;
@@ -258,7 +302,7 @@ __device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D
         for (int sub = 0; sub < 2; sub++) {
             if ((PH & 5) && v < nS) {
                 const int lim = min(D.n_geo, nS - v);
-                const int j = first_below_guided(D.geoS, D.guideA, lim, (sub ? x.z : x.x) >> 1);
+                const int j = first_below_guided<GSM>(geoS, guideA, lim, (sub ? x.z : x.x) >> 1);
                 v += j;
                 if (j < lim) {
                     const bool five = allss || v < B.o5;
@@ -269,7 +313,7 @@ __device__ __forceinline__ void briggs_events(const Key& key, const DamageDev& D
             }
             if ((PH & 2) && q < qend) {
                 const int lim = min(D.n_geo, qend - q);
-                const int j = first_below_guided(D.geoD, D.guideB, lim, (sub ? x.w : x.y) >> 1);
+                const int j = first_below_guided<GSM>(geoD, guideB, lim, (sub ? x.w : x.y) >> 1);
                 q += j;
                 if (j < lim) {
                     const bool ct = B.nick > q;                     // placedNick = nick <= i (deamSim.cpp:1510,1542,1586)

@@ -10,8 +10,11 @@
 //
 // HBM-bound integer/byte work: no tensor cores.  Layout and byte accounting: DESIGN.md.
 #include "gg_kernels.cuh"
-#ifndef GG_EARLY_TICKET
-#define GG_EARLY_TICKET 1      // the next tile's ticket is taken when the current tile has its byte offset (measured: -0.9 %)
+#ifndef GG_SPIN_SLEEP
+#define GG_SPIN_SLEEP 0
+#endif
+#ifndef GG_GATHER_U
+#define GG_GATHER_U 2          // 16-base chunks gathered per lane and trip (4 loads in flight; measured: 4 and 6 per trip lose 4 % / 3 % -- the unrolled code pushes the hot path past the 32 KB instruction cache)
 #endif
 #ifndef GG_COPY_UNROLL
 #define GG_COPY_UNROLL 1       // copy-out with two 16-byte copies per trip (measured: -2.3 %; four per trip: -1.4 %)
@@ -203,9 +206,22 @@ struct BitAppender {                  // pending bits: lo holds bits [0,fill) of
     }
     __device__ __forceinline__ void flush() { if (fill > 0) *out++ = lo; }
 };
+// bases [start, start+len) of a shared-memory source appended as one unaligned bit copy: bit b of the image's current word is source bit
+// s + b, s = 2 start - fill (>= -31: the guard word), so every output word is ONE funnel shift of two consecutive source words with the
+// same shift amount -- one load, one shift and one store per 16 bases.  Reads at most two words past the last source word it needs.
 __device__ __forceinline__ void put_run_smem(BitAppender& A, const uint32_t* src, int start, int len) {
+    if (len <= 0) return;
+    const int s = 2 * start - A.fill;
+    const uint32_t* sp = src + (s >> 5);
+    const uint32_t sh = (uint32_t)s & 31u;
+    const int bits = A.fill + 2 * len;              // bits [fill, bits) of the word stream that starts at the current word are new
+    uint32_t prev = sp[0], next = sp[1];
+    uint32_t x = A.lo | (__funnelshift_r(prev, next, sh) & ~((1u << A.fill) - 1u));
+    const int nw = bits >> 5;
 #pragma unroll 1
-    for (int o = 0; o < len; o += 16) { const int n = min(16, len - o); A.put(fetch_run_smem(src, start + o) & lowfields(n), n); }
+    for (int k = 0; k < nw; k++) { *A.out++ = x; prev = next; next = sp[k + 2]; x = __funnelshift_r(prev, next, sh); }
+    A.fill = bits & 31;
+    A.lo = x & ((1u << A.fill) - 1u);
 }
 __device__ __forceinline__ void put_run_glob(BitAppender& A, const uint32_t* __restrict__ src, int start, int len) {
 #pragma unroll 1
@@ -352,6 +368,14 @@ __device__ __forceinline__ uint4 codes16_to_ascii(uint32_t x, uint32_t lut /* 0x
     a.z = __byte_perm(e1, o1, 0x5140u); a.w = __byte_perm(e1, o1, 0x7362u);
     return a;
 }
+// four ASCII digits of h < 10000, thousands in byte 0 (print order in little-endian memory): h/100 and h%100 side by side in 16-bit
+// lanes, then each lane's /10 and %10 side by side in bytes
+__device__ __forceinline__ uint32_t dec4_ascii(uint32_t h) {
+    const uint32_t q = (h * 5243u) >> 19;                        // h / 100, exact below 43699
+    const uint32_t x = q | ((h - q * 100u) << 16);
+    const uint32_t t = ((x * 103u) >> 10) & 0x000F000Fu;         // lane / 10, exact below 179; no carry between the lanes
+    return (t | ((x - t * 10u) << 8)) + 0x30303030u;
+}
 // nd decimal digits of a 32-bit value, two at a time from the right
 __device__ __forceinline__ void put_dec32(uint8_t* p, uint32_t w, int nd, const uint16_t* d100) {
     int k = nd - 2;
@@ -414,6 +438,18 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 const int na = 4 * (P.dmg[slot].rows5 + P.dmg[slot].rows3 + 2), nt = 4 * (P.dmg[slot].n5t + P.dmg[slot].n3t);
                 for (int q = tid; q < na; q += blockDim.x) ((uint4*)(smem + P.sm.thr))[P.sm.thr_slot[slot] + q] = __ldg(P.dmg[slot].acc + q);
                 for (int q = tid; q < nt; q += blockDim.x) ((uint4*)(smem + P.sm.thr))[P.sm.term_slot[slot] + q] = __ldg(P.dmg[slot].term + q);
+            }
+    if (DMODE != 0)                                   // skip tables of the event draws (their first geo_n entries) and their guides
+        for (int slot = 0; slot < 4; slot++)
+            if (P.sm.geo_slot[slot] >= 0) {
+                uint32_t* g = (uint32_t*)(smem + P.sm.geo_slot[slot]);
+                const int n = P.sm.geo_n;
+                for (int q = tid; q < n; q += blockDim.x) g[q] = __ldg(P.dmg[slot].geoM + q);                       // (geoM and geoS are the same table)
+                for (int q = tid; q < 128; q += blockDim.x) g[n + q] = __ldg((const uint32_t*)P.dmg[slot].guideA + q);
+                if (DMODE == 2) {
+                    for (int q = tid; q < n; q += blockDim.x) g[n + 128 + q] = __ldg(P.dmg[slot].geoD + q);
+                    for (int q = tid; q < 128; q += blockDim.x) g[2 * n + 128 + q] = __ldg((const uint32_t*)P.dmg[slot].guideB + q);
+                }
             }
     if (P.sm.tab >= 0) {                              // small plan / genome / contig tables: global -> shared, once per CTA
         uint8_t* tb = smem + P.sm.tab;
@@ -487,23 +523,23 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint32_t my_attempts = 0, my_gather = 0, my_err = 0;
     const uint32_t lut = P.lut;                     // 'A','C','G','T' for the byte permutes of the ASCII pass (a kernel parameter: as an immediate it was re-materialised four times per group)
 
-#if GG_EARLY_TICKET
-    int next_tile = 0;
-    if (lane == 0) next_tile = (int)atomicAdd(P.ticket, 1u);
-#endif
+    // Two tiles are in flight per warp: a tile is SAMPLED (pass A) and its byte count published as soon as its ticket is taken, then the
+    // previous tile is rendered and stored, then the new tile is gathered, damaged and given its byte offset.  A ticket is therefore
+    // never held by a warp that is busy with something else (the tiles behind it would spin in their look-back), and a tile's
+    // look-back comes a whole emission after its predecessors published: it practically never waits.  Pass A leaves its results in
+    // registers (the previous tile's descriptors are still needed by the emission).
+    int tile = 0;
+    if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    bool have_prev = false;
+    int p_nf = 0; uint32_t p_T = 0, p_roff = 0; unsigned long long p_gofs = 0; bool p_fits = false;   // the tile waiting for its emission
     while (true) {
-        // tiles are handed out in ticket order when a warp is ready for one: a tile's predecessors have then started earlier, which
-        // keeps the look-back short (taking the ticket ahead of time made the tiles behind it spin)
-        int tile = 0;
-#if GG_EARLY_TICKET
-        tile = next_tile;                                        // taken when the previous tile had its byte offset: the atomic's latency hides behind the emission
-#else
-        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
-#endif
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= P.n_tiles) break;
+        const bool have_tile = tile < P.n_tiles;
+        // (measured: warps that start their tiles together in groups of 2 / 4 / 8 / 32 to share instruction-cache lines lose 2.5 / 3 / 5 / 23 %)
+        if (!have_tile && !have_prev) break;
         const uint64_t tile_first = (uint64_t)tile * (uint64_t)P.F;
-        const int nf = (int)min((uint64_t)P.F, P.count - tile_first);
+        const int nf = have_tile ? (int)min((uint64_t)P.F, P.count - tile_first) : 0;
+        uint32_t nx_meta = 0, nx_idx = 0, nx_ci = 0, nx_rghdr = 0, nx_nd = 0;
 
         // ------------------------------------------------------------ pass A: sample (lane per fragment)
         unsigned long long pk = 0;
@@ -518,7 +554,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const int d = rg->comp >= 0 ? P.comp[rg->comp].dist : 0;       // distFromEnd: 0 without --comp (fragSim.cpp:1019-1021)
             uint64_t gpos = 0; bool ok = false;
             for (uint32_t attempt = 0; attempt < 65536u; attempt++) {
-                const uint4 x = rng_block(P.key, id, attempt, ST_FRAG);
+                const uint4 x = rng_block(P.ks, id, attempt, ST_FRAG);
                 my_attempts++;
                 // selectFragmentLength, fragSim.cpp:137-187
                 if (P.size_mode == 0) L = P.fixed_len;
@@ -554,18 +590,26 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 }
                 if (L + 2 * d > 0) {                                                   // isResolvedDNAstring over the window incl. the flanks, fragSim.cpp:333-339,1472
                     const uint64_t s0 = gpos - (uint64_t)d, e = gpos + (uint64_t)L + (uint64_t)d - 1 + (uint64_t)xtra;
-                    const uint32_t* mw = G.nmask + (s0 >> 5);                          // first mask word of the window
-                    const int nw = (int)((e >> 5) - (s0 >> 5));                        // index of its last word
+                    const uint64_t w0 = s0 >> 5;                                       // first mask word of the window
+                    const int nw = (int)((e >> 5) - w0);                               // index of its last word
                     const uint32_t first = 0xFFFFFFFFu << (s0 & 31), last = 0xFFFFFFFFu >> (31 - (e & 31));
-                    // the loads are independent (a dependent chain of misses costs pass A dearly): the edge words and up to three interior words at once
-                    const uint32_t m0 = __ldg(mw), mn = __ldg(mw + nw);
-                    const uint32_t m1 = __ldg(mw + min(1, nw)), m2 = __ldg(mw + min(2, nw)), m3 = __ldg(mw + min(3, nw));
+                    // two aligned 16-byte loads cover the first five words of any window (a 32-bit load per word costs one L1 wavefront per
+                    // lane and word: the lanes look at unrelated places); words w0 .. w0+4 are elements k .. k+4 of the eight
+                    const uint4* q4 = (const uint4*)G.nmask + (w0 >> 2);
+                    const uint4 Q0 = __ldg(q4), Q1 = __ldg(q4 + 1);
+                    const bool k1 = (w0 & 1u) != 0, k2 = (w0 & 2u) != 0;
+                    const uint32_t t0 = k1 ? Q0.y : Q0.x, t1 = k1 ? Q0.z : Q0.y, t2 = k1 ? Q0.w : Q0.z, t3 = k1 ? Q1.x : Q0.w,
+                                   t4 = k1 ? Q1.y : Q1.x, t5 = k1 ? Q1.z : Q1.y, t6 = k1 ? Q1.w : Q1.z;
+                    const uint32_t m0 = k2 ? t2 : t0, m1 = k2 ? t3 : t1, m2 = k2 ? t4 : t2, m3 = k2 ? t5 : t3, m4 = k2 ? t6 : t4;
+                    const uint32_t* mw = G.nmask + w0;
+                    const uint32_t mn = nw == 0 ? m0 : nw == 1 ? m1 : nw == 2 ? m2 : nw == 3 ? m3 : nw == 4 ? m4 : __ldg(mw + nw);
                     uint32_t any = nw == 0 ? (m0 & first & last) : ((m0 & first) | (mn & last));
                     if (nw > 1) any |= m1;
                     if (nw > 2) any |= m2;
                     if (nw > 3) any |= m3;
+                    if (nw > 4) any |= m4;
 #pragma unroll 1
-                    for (int w = 4; w < nw; w++) any |= __ldg(mw + w);                 // windows beyond 128 bases
+                    for (int w = 5; w < nw; w++) any |= __ldg(mw + w);                 // windows beyond 160 bases
                     if (any) continue;
                 }
                 plus = P.norev ? 1u : (x.y & 1u);                                      // randomBool, fragSim.cpp:1462-1467
@@ -589,7 +633,12 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             my_gather += (uint32_t)((L + 2 * d + 3) / 4 + (L + 2 * d + 7) / 8);
             tag_len = rg->tag_len;
             const int nlen = t_nlen[ci];
-            const int n1 = ndigits(idx), n2 = ndigits(idx + (uint64_t)L), n3 = ndigits((uint64_t)L);
+            // digit counts: the end coordinate has as many digits as the start unless it crosses a power of ten (a few, for starts below L); L <= 4095
+            const int n1 = ndigits(idx);
+            int n2 = n1;
+#pragma unroll 1
+            while (n2 < 10 && idx + (uint64_t)L >= (uint64_t)c_pow10[n2]) n2++;
+            const int n3 = 1 + (L >= 10 ? 1 : 0) + (L >= 100 ? 1 : 0) + (L >= 1000 ? 1 : 0);
             hdr = 1 + nlen + 3 + n1 + 1 + n2 + 1 + n3 + tag_len;
             const int S = EMITC ? P.S_ad : L;
             uint32_t bytes = 0;
@@ -597,11 +646,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const uint32_t chunks = (L + 15) >> 4;
             const uint32_t groups = EMITC ? P.gpf_ad : (uint32_t)((S + 15) >> 4) + 1u;
             pk = PK(bytes, chunks, groups);
-            s_gpos[lane] = gpos;
-            s_meta[lane] = META(L, plus, rg->slot, rg->genome);
-            s_hdr[lane] = (uint16_t)hdr;
-            s_nd[lane] = (uint16_t)(n1 | (n2 << 4) | (n3 << 8));
-            s_idx[lane] = (uint32_t)idx; s_ci[lane] = (uint32_t)ci; s_rg[lane] = (uint16_t)lo;   // parked for the header pass
+            s_gpos[lane] = gpos;                                 // (dead since the previous tile's gather: written in place)
+            nx_meta = META(L, plus, rg->slot, rg->genome);
+            nx_nd = (uint32_t)(n1 | (n2 << 4) | (n3 << 8));
+            nx_idx = (uint32_t)idx; nx_ci = (uint32_t)ci; nx_rghdr = (uint32_t)lo | ((uint32_t)hdr << 16);   // parked for the header pass
             if (DMODE == 0 && emit != 0 && rg->slot >= 0 && P.dmg[rg->slot].mode == 5) {   // -damagess (drawn per base in pass C): the two overhangs, once per fragment (deamSim.cpp:1342-1343)
                 const BriggsHdr B = dmg_briggs_hdr(P.dmg[rg->slot], rng_block(P.key, id, 0u, ST_DEAM));
                 s_bh[lane] = (unsigned long long)(uint32_t)B.o5 | ((unsigned long long)(uint32_t)B.o3 << 32);
@@ -613,30 +661,239 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         const unsigned long long excl = incl - pk;
         const uint32_t T = PK_BYTES(tot), n_chunks = PK_CHUNKS(tot);
         const uint32_t roff = PK_BYTES(excl);                    // byte offset of this lane's record within the tile
-        if (lane == 0) {   // publish this tile's byte count for the look-back
+        if (have_tile && lane == 0)                              // publish this tile's byte count for the look-back
             st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
-#if GG_BULK_COPY
-            bulk_wait_read();                                    // the previous tile's bulk copy has read its staging bytes (pass A gave it time)
-#endif
+
+        // ------------------------------------------------------------ the previous tile: rendered and stored while this tile's byte count is already visible
+        if (have_prev) {
+            // ------------------------------------------------------------ emission in halves of up to P.E fragments
+            for (int f0 = 0; f0 < p_nf; f0 += P.E) {
+                const int f1 = min(p_nf, f0 + P.E);
+                const uint32_t b0 = __shfl_sync(0xffffffffu, p_roff, f0);                              // bytes [b0, b1) of the tile
+                const uint32_t b1x = __shfl_sync(0xffffffffu, p_roff, f1 & 31);
+                const uint32_t b1 = f1 < p_nf ? b1x : p_T;
+                const uint32_t TB = b1 - b0;
+                const int pad = (int)((uintptr_t)(P.out + p_gofs + b0) & 15);                           // the half is staged with its global misalignment
+                const int pofs = pad - (int)b0;                                                     // staging offset = pofs + offset within the tile
+                const bool ok = p_fits && TB <= (uint32_t)P.sm.stage_bytes;                           // host sizing guard: never write past staging
+                if (!ok) my_err |= ERRF_OVERFLOW;
+    #if GG_BULK_COPY == 2
+                if (f0 > 0) { if (lane == 0) bulk_wait_read(); __syncwarp(); }                      // the first half's bulk copy has read the staging buffer
+    #endif
+
+                // ---- headers + newlines: two lanes per fragment running the same code on different fields.  Lane 2k: '>' name ":s:" start ':';
+                // lane 2k+1: end ':' length tag ["_r"] '\n' and the newline behind the sequence   (fragSim.cpp:1489,1498,1505-1507,1603)
+                auto write_headers = [&]() {
+                    const int fh = f0 + (lane >> 1), part = lane & 1;
+                    if (fh < f1 && ok) {
+                        const uint32_t meta = s_meta[fh];
+                        const int L = META_L(meta);
+                        const int hdr = (int)s_hdr[fh];
+                        const uint32_t nd = s_nd[fh];
+                        const int n3 = (int)(nd >> 8);
+                        const int S = EMITC ? P.S_ad : L;
+                        uint8_t* rec = s_stage + pofs + (int)s_so[fh] - hdr - sfx0 - 1;             // first byte of the record
+                        const char* csrc; int cn, nv, coff, voff; uint64_t v;                       // bytes to copy (name / tag) and the coordinate to print, with their offsets in the header
+                        uint64_t cw = 0; bool wordcopy;                                             // names / tags of up to 8 bytes travel in a register pair
+                        if (part == 0) {
+                            const int ci = (int)s_ci[fh];
+                            csrc = t_names + t_noff[ci]; cn = t_nlen[ci]; coff = 1;
+                            v = s_idx[fh]; nv = (int)(nd & 15u); voff = 1 + cn + 3;
+                            wordcopy = t_name8 != nullptr && cn <= 8;
+                            if (wordcopy) cw = t_name8[ci];
+                        } else {
+                            const RangeDev* rg = t_ranges + s_rg[fh];
+                            csrc = rg->tag; cn = rg->tag_len; coff = hdr - cn;
+                            v = (uint64_t)s_idx[fh] + (uint64_t)L; nv = (int)((nd >> 4) & 15u); voff = hdr - cn - n3 - 1 - nv;
+                            wordcopy = cn <= 8;
+                            if (wordcopy) cw = *(const uint64_t*)rg->tag;
+                        }
+                        // Fast path: the coordinate is converted in registers (eight ASCII digits with leading zeros) and stored as eight
+                        // unconditional bytes -- right-aligned by lane 2k (the surplus lands on ":s:" / the name / '>', which this lane writes
+                        // afterwards), left-aligned by lane 2k+1 (the surplus lands on ':' length tag ["_r"] '\n', which that lane writes
+                        // afterwards).  The surplus must stay inside the lane's own bytes; otherwise the lane takes the exact byte loops.
+                        // Everything below is the same instruction stream for both lanes (selects on an opaque copy of `part`: specialised
+                        // per part by the compiler it would run twice).
+                        int pb = part; asm volatile("" : "+r"(pb));
+                        const int pmask = -pb;
+                        const bool fastp = wordcopy && v <= 0xFFFFFFFFull && nv + cn + (pmask & (n3 + sfx0 - 2)) >= 4;
+                        if (fastp) {
+                            const uint32_t v32 = (uint32_t)v;
+                            const uint32_t top = v32 / 100000000u, r8 = v32 - top * 100000000u;
+                            const uint32_t h4 = r8 / 10000u, l4 = r8 - h4 * 10000u;
+                            const int lead = max(0, 8 - nv) & pmask;                                // lane 2k+1 drops the leading zeros
+                            const uint64_t X = (((uint64_t)dec4_ascii(l4) << 32) | (uint64_t)dec4_ascii(h4)) >> (8 * lead);
+                            const uint32_t X0 = (uint32_t)X, X1 = (uint32_t)(X >> 32);
+                            const int qoff = voff + nv - 8 + lead;
+                            // a field of up to four bytes that ends where the next one starts: ":s:" in front of the start coordinate / the length in front of the tag
+                            const uint32_t F4 = pb ? dec4_ascii((uint32_t)L) : (0x3A003A00u | ((META_PLUS(meta) ? (uint32_t)'+' : (uint32_t)'-') << 16));
+                            const int eoff = pb ? coff : voff, nfld = pb ? n3 : 3;
+                            const uint8_t ch = pb ? (uint8_t)'\n' : (uint8_t)'>';                   // '>' in front / the newlines behind the header and behind the sequence
+    #pragma unroll
+                            for (int ln = 0; ln < NLINES; ln++) {
+                                const int sfx = ln ? sfx1 : sfx0;
+                                uint8_t* q = rec + qoff;
+                                q[0] = (uint8_t)X0; q[1] = (uint8_t)(X0 >> 8); q[2] = (uint8_t)(X0 >> 16); q[3] = (uint8_t)(X0 >> 24);
+                                q[4] = (uint8_t)X1; q[5] = (uint8_t)(X1 >> 8); q[6] = (uint8_t)(X1 >> 16); q[7] = (uint8_t)(X1 >> 24);
+                                uint8_t* p = rec + voff;
+                                if (nv > 8) {                                                       // coordinates of 1e8 and more: one or two digits in front
+                                    const uint32_t two = s_d100[top];
+                                    p[nv - 9] = (uint8_t)(two >> 8);
+                                    if (nv > 9) p[0] = (uint8_t)two;
+                                }
+                                p[nv] = ':';
+                                uint8_t* tp = rec + coff;
+    #pragma unroll
+                                for (int k = 0; k < 8; k++) if (k < cn) tp[k] = (uint8_t)(cw >> (8 * k));
+                                uint8_t* e = rec + eoff;
+                                e[-1] = (uint8_t)(F4 >> 24);
+                                if (nfld > 1) e[-2] = (uint8_t)(F4 >> 16);
+                                if (nfld > 2) e[-3] = (uint8_t)(F4 >> 8);
+                                if (nfld > 3) e[-4] = (uint8_t)F4;
+                                if (sfx && pb) { rec[hdr] = '_'; rec[hdr + 1] = 'r'; }
+                                rec[pmask & (hdr + sfx)] = ch; rec[pmask & (hdr + sfx + S + 1)] = ch;
+                                rec += hdr + sfx + 1 + S + 1;
+                            }
+                        } else {
+    #pragma unroll
+                        for (int ln = 0; ln < NLINES; ln++) {
+                            const int sfx = ln ? sfx1 : sfx0;
+                            if (wordcopy) {
+    #pragma unroll
+                                for (int k = 0; k < 8; k++) if (k < cn) rec[coff + k] = (uint8_t)(cw >> (8 * k));
+                            } else {
+    #pragma unroll 1
+                                for (int k = 0; k < cn; k++) rec[coff + k] = (uint8_t)csrc[k];
+                            }
+                            uint8_t* p = rec + voff;
+                            if (v <= 0xFFFFFFFFull) put_dec32(p, (uint32_t)v, nv, s_d100); else put_decimal(p, v, nv, s_d100);
+                            p[nv] = ':';
+                            if (part == 0) { rec[0] = '>'; p[-3] = ':'; p[-2] = META_PLUS(meta) ? '+' : '-'; p[-1] = ':'; }
+                            else {
+                                put_dec32(p + nv + 1, (uint32_t)L, n3, s_d100);
+                                uint8_t* q = rec + hdr;
+                                if (sfx) { q[0] = '_'; q[1] = 'r'; q += 2; }
+                                q[0] = '\n'; q[S + 1] = '\n';
+                            }
+                            rec += hdr + sfx + 1 + S + 1;
+                        }
+                        }
+                    }
+                };
+                if (!FASTB) { write_headers(); __syncwarp(); }
+
+                // ---- ASCII: two lanes per fragment; a lane walks half of the staging groups of a sequence line (or one of the two lines of the
+                // four-line dialect) with one running source word: one shared-memory load, one funnel shift, the expansion and one 16-byte
+                // store per group
+                {
+                    const int fd = f0 + (lane >> 1), h = lane & 1;
+                    if (fd < f1 && ok) {
+                        int S = P.S_ad;
+                        if (EMITC == 0) S = META_L(s_meta[fd]);
+                        int ls = pofs + (int)s_so[fd];                                              // staging offset of the first sequence byte of the line
+                        const uint32_t* src = EMITC == 0 ? s_dwords + s_cstart[fd] : s_lwords + fd * P.lw_stride + 1;
+                        if (EMITC == 2 && h) { ls += (int)s_hdr[fd] + sfx1 + S + 2; src += P.LWL; }   // the reverse read's line
+                        const int sigma = ls & 15;
+                        const int ngr = (sigma + S + 15) >> 4;                                      // staging groups that hold bases of the line
+                        const int half = (ngr + 1) >> 1;
+                        const int g_lo = (EMITC == 2 || !h) ? 0 : half, g_hi = (EMITC == 2 || h) ? ngr : half;
+                        uint8_t* dst = s_stage + (ls - sigma) + 16 * g_lo;                          // 16-byte aligned
+                        // group g holds bases [16 g - sigma, 16 g - sigma + 16): source words (16 (g+1) - sigma) >> 4 - 1 and the next one (a guard
+                        // word sits in front of every source)
+                        const uint32_t* sp = src + (((16 * (g_lo + 1) - sigma) >> 4) - 1);
+                        const uint32_t sh = ((uint32_t)(16 - sigma) & 15u) * 2u;
+                        uint32_t prev = *sp;
+    #pragma unroll 1
+                        for (int g = g_lo; g < g_hi; g++) {
+                            const uint32_t next = *++sp;
+                            const uint4 a = codes16_to_ascii(__funnelshift_r(prev, next, sh), lut);
+                            prev = next;
+                            const int j0 = 16 * g - sigma;
+                            if (FASTB || (j0 >= 0 && j0 + 16 <= S)) {
+                                *(uint4*)dst = a;                           // FASTB: bytes outside the line are rewritten by the header pass
+                            } else {
+                                // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
+                                // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
+                                const int t0 = max(j0, 0) - j0, t1 = min(j0 + 16, S) - j0;          // valid bytes [t0,t1) of the group
+                                const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
+                                uint32_t* d4 = (uint32_t*)dst;
+                                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    #pragma unroll
+                                for (int w = 0; w < 4; w++) {
+                                    const uint32_t nib = (V >> (4 * w)) & 0xFu;
+                                    const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
+                                    if (nib == 0xFu) d4[w] = aw[w];
+                                    else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
+                                }
+                            }
+                            dst += 16;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (FASTB) { write_headers(); __syncwarp(); }
+
+                // ---- copy-out: staging -> global
+                if (ok) {
+                    uint8_t* const gal = P.out + p_gofs + b0 - pad;            // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+TB)
+                    const int end = pad + (int)TB;
+                    const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
+    #if GG_BULK_COPY
+                    if (GG_BULK_COPY == 2 || f1 == p_nf) {                     // the tile's last half goes out through the bulk-copy engine: its staging is not needed before the next tile's emission
+                        fence_async_smem();                                  // this lane's staging writes -> visible to the bulk-copy engine
+                        __syncwarp();
+                        if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
+                    } else
+    #endif
+    #if GG_COPY_UNROLL == 4
+    #pragma unroll 1
+                    for (int c = c_lo + lane; c < c_hi; c += 128) {  // four independent 16-byte copies per trip (a half tile is one or two trips)
+                        const bool p1 = c + 32 < c_hi, p2 = c + 64 < c_hi, p3 = c + 96 < c_hi;
+                        const uint8_t* sp = s_stage + 16 * c; uint8_t* gp = gal + 16 * c;
+                        uint4 v0 = *(const uint4*)sp, v1 = v0, v2 = v0, v3 = v0;
+                        if (p1) v1 = *(const uint4*)(sp + 512);
+                        if (p2) v2 = *(const uint4*)(sp + 1024);
+                        if (p3) v3 = *(const uint4*)(sp + 1536);
+                        st_global_v4(gp, v0);
+                        if (p1) st_global_v4(gp + 512, v1);
+                        if (p2) st_global_v4(gp + 1024, v2);
+                        if (p3) st_global_v4(gp + 1536, v3);
+                    }
+    #elif GG_COPY_UNROLL
+                    {
+                        int c = c_lo + lane;
+    #pragma unroll 1
+                        for (; c + 32 < c_hi; c += 64) {             // two independent 16-byte copies per trip
+                            const uint4 v0 = *(const uint4*)(s_stage + 16 * c), v1 = *(const uint4*)(s_stage + 16 * c + 512);
+                            st_global_v4(gal + 16 * c, v0); st_global_v4(gal + 16 * c + 512, v1);
+                        }
+                        if (c < c_hi) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
+                    }
+    #else
+                    for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
+    #endif
+                    // the partial head [pad, 16 c_lo) and tail [16 max(c_hi, c_lo), end): at most 15 bytes each, one byte per lane
+                    const int t = lane < 16 ? pad + lane : 16 * max(c_hi, c_lo) + (lane - 16);
+                    if (lane < 16 ? t < min(16 * c_lo, end) : t < end) gal[t] = s_stage[t];
+                }
+                __syncwarp();
+            }
         }
+        have_prev = false;
+        if (!have_tile) break;
         __syncwarp();
+        if (lane < nf) {                                         // the new tile's descriptors (the previous tile's are dead now)
+            s_meta[lane] = nx_meta; s_hdr[lane] = (uint16_t)(nx_rghdr >> 16); s_nd[lane] = (uint16_t)nx_nd;
+            s_idx[lane] = nx_idx; s_ci[lane] = nx_ci; s_rg[lane] = (uint16_t)nx_rghdr;
+        }
 
         // ------------------------------------------------------------ pass B1: work maps (owner lane)
         if (lane < nf) {
-            const uint32_t c0 = PK_CHUNKS(excl), g0 = PK_GROUPS(excl);
-            s_so[lane] = roff + (uint32_t)s_hdr[lane] + (uint32_t)sfx0 + 1u; s_cstart[lane] = (uint16_t)c0;
+            const uint32_t c0 = PK_CHUNKS(excl);
+            s_so[lane] = roff + (nx_rghdr >> 16) + (uint32_t)sfx0 + 1u; s_cstart[lane] = (uint16_t)c0;
             const uint32_t nch = PK_CHUNKS(pk);
 #pragma unroll 1
             for (uint32_t k = 0; k < nch; k++) s_cmap[c0 + k] = (uint8_t)lane;
-            if (EMITC == 0) {                                    // the adptSim dialects have the same number of groups for every fragment: no map
-                const uint32_t ngr = PK_GROUPS(pk);
-#pragma unroll 1
-                for (uint32_t k = 0; k < ngr; k++) s_gmap[g0 + k] = (uint8_t)lane;
-            }
-        }
-        if (EMITC == 0) {                                        // group slot of every fragment's first group (lanes past the tile and the sentinel hold the total)
-            s_gstart[lane] = (uint16_t)PK_GROUPS(excl);
-            if (lane == 31) s_gstart[32] = (uint16_t)PK_GROUPS(tot);
         }
         // first look-back probe, issued now and consumed after the damage pass (its latency overlaps pass C)
         unsigned long long lb = 2ull << 62;
@@ -644,13 +901,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         __syncwarp();
 
         // ------------------------------------------------------------ pass C: gather (lane per 16-base chunk)
-        // two chunks per lane and trip: the four loads are issued before any of them is used (the gather is a dependent L2 access)
-        for (uint32_t e0 = lane; e0 < n_chunks; e0 += 64) {
-            uint32_t wlo[2], whi[2], wsh[2], wn[2]; bool rcmp[2];
+        // GG_GATHER_U chunks per lane and trip: all loads of a trip are issued before any of them is used (the gather is a dependent L2
+        // access: a trip costs one exposed L2 latency, so a tile should need as few trips as the registers allow)
+        for (uint32_t e0 = lane; e0 < n_chunks; e0 += 32u * GG_GATHER_U) {
+            uint32_t wlo[GG_GATHER_U], whi[GG_GATHER_U], wmt[GG_GATHER_U];     // wmt: shift [4:0] | fields [10:5] | reverse strand [11]
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < GG_GATHER_U; u++) {
                 const uint32_t e = e0 + 32u * (uint32_t)u;
-                wlo[u] = whi[u] = wsh[u] = wn[u] = 0u; rcmp[u] = false;
+                wlo[u] = whi[u] = wmt[u] = 0u;
                 if (e < n_chunks) {
                     const int f = s_cmap[e];
                     const int k = (int)e - (int)s_cstart[f];
@@ -661,23 +919,24 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     const int64_t pos = META_PLUS(meta) ? (int64_t)(s_gpos[f] + 16ull * (uint64_t)k) : (int64_t)(s_gpos[f] + (uint64_t)fl) - 16ll * k - 16ll;
                     const uint32_t* wp = seq2 + (pos >> 4);
                     wlo[u] = __ldg(wp); whi[u] = __ldg(wp + 1);
-                    wsh[u] = ((uint32_t)pos & 15u) * 2u; wn[u] = (uint32_t)min(16, fl - 16 * k); rcmp[u] = !META_PLUS(meta);
+                    wmt[u] = (((uint32_t)pos & 15u) * 2u) | ((uint32_t)min(16, fl - 16 * k) << 5) | (META_PLUS(meta) ? 0u : 0x800u);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < GG_GATHER_U; u++) {
                 const uint32_t e = e0 + 32u * (uint32_t)u;
                 if (e < n_chunks) {
-                    uint32_t W = __funnelshift_r(wlo[u], whi[u], wsh[u]);
-                    if (rcmp[u]) W = revcomp16(W);
+                    uint32_t W = __funnelshift_r(wlo[u], whi[u], wmt[u] & 31u);
+                    if (wmt[u] & 0x800u) W = revcomp16(W);
+                    const int wn = (int)((wmt[u] >> 5) & 63u);
                     if (DMODE == 0 && emit != 0) {                   // the models still drawn per base
                         const int f = s_cmap[e];
                         const uint32_t meta = s_meta[f];
                         const int slot = META_SLOT(meta);
                         if (slot >= 0 && P.dmg[slot].mode >= 3)
-                            W = damage_chunk_perbase(P, P.dmg[slot], s_bh[f], P.first + tile_first + (uint64_t)f, (int)e - (int)s_cstart[f], META_L(meta), (int)wn[u], W);
+                            W = damage_chunk_perbase(P, P.dmg[slot], s_bh[f], P.first + tile_first + (uint64_t)f, (int)e - (int)s_cstart[f], META_L(meta), wn, W);
                     }
-                    s_dwords[e] = W & lowfields((int)wn[u]);
+                    s_dwords[e] = W & lowfields(wn);
                 }
             }
         }
@@ -692,12 +951,17 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                 const int L = META_L(meta);
                 const uint64_t id = P.first + tile_first + (uint64_t)lane;
                 SeqPacked Sq; Sq.w = s_dwords + s_cstart[lane];
+                // DMODE 1 / 2: the slot's skip tables sit in shared memory (the host falls back to DMODE 0 when they do not fit)
+                const uint32_t* const gA = (const uint32_t*)(smem + (DMODE != 0 ? P.sm.geo_slot[slot] : 0)); const uint8_t* const uA = (const uint8_t*)(gA + P.sm.geo_n);
                 if (mode == 1) {
-                    if (DMODE == 1) matrix_events<7, true>(P.key, P.dmg[slot], s_thr + P.sm.term_slot[slot], s_thr + P.sm.thr_slot[slot], Sq, L, id);
-                    else matrix_events<7, false>(P.key, P.dmg[slot], P.dmg[slot].term, P.dmg[slot].acc, Sq, L, id);
+                    if (DMODE == 1) matrix_events<7, true, true>(P.ks, P.dmg[slot], s_thr + P.sm.term_slot[slot], s_thr + P.sm.thr_slot[slot], gA, uA, Sq, L, id);
+                    else matrix_events<7, false, false>(P.ks, P.dmg[slot], P.dmg[slot].term, P.dmg[slot].acc, P.dmg[slot].geoM, P.dmg[slot].guideA, Sq, L, id);
                 } else if (mode == 2) {
-                    const BriggsHdr B = dmg_briggs_hdr(P.dmg[slot], rng_block(P.key, id, 0u, ST_DEAM));
-                    briggs_events<7>(P.key, P.dmg[slot], B, Sq, L, id);
+                    const BriggsHdr B = dmg_briggs_hdr(P.dmg[slot], rng_block(P.ks, id, 0u, ST_DEAM));
+                    if (DMODE == 2) {
+                        const uint32_t* const gB = (const uint32_t*)(uA + 512); const uint8_t* const uB = (const uint8_t*)(gB + P.sm.geo_n);
+                        briggs_events<7, true>(P.ks, P.dmg[slot], B, gA, uA, gB, uB, Sq, L, id);
+                    } else briggs_events<7, false>(P.ks, P.dmg[slot], B, P.dmg[slot].geoS, P.dmg[slot].guideA, P.dmg[slot].geoD, P.dmg[slot].guideB, Sq, L, id);
                 }
             }
         }
@@ -720,7 +984,12 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             int look = tile - 1;
             while (true) {
                 const int i = look - lane;
-                while (__any_sync(0xffffffffu, (lb >> 62) == 0)) { if ((lb >> 62) == 0) lb = ld_volatile_u64(P.tile_state + i); }
+                while (__any_sync(0xffffffffu, (lb >> 62) == 0)) {
+#if GG_SPIN_SLEEP
+                    __nanosleep(GG_SPIN_SLEEP);                  // a predecessor has not published yet: leave the issue slots to the warps that work
+#endif
+                    if ((lb >> 62) == 0) lb = ld_volatile_u64(P.tile_state + i);
+                }
                 const uint32_t inc = __ballot_sync(0xffffffffu, (lb >> 62) == 2ull);
                 const int first_inc = inc ? (__ffs(inc) - 1) : 32;
                 gofs += warp_sum_u64(lane <= first_inc ? (lb & 0x3FFFFFFFFFFFFFFFull) : 0ull);
@@ -730,9 +999,6 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             }
             if (lane == 0) st_volatile_u64(P.tile_state + tile, (2ull << 62) | (gofs + (unsigned long long)T));
         }
-#if GG_EARLY_TICKET
-        if (lane == 0) next_tile = (int)atomicAdd(P.ticket, 1u);
-#endif
         if (lane == 0 && tile == P.n_tiles - 1) P.stats[ST_TOTAL] = gofs + (unsigned long long)T;
         const bool fits = gofs + T <= P.out_cap;                         // host sizing guard: never write past the output
         if (!fits) my_err |= ERRF_OVERFLOW;
@@ -740,172 +1006,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             const uint64_t f = tile_first + (uint64_t)lane;
             P.case_off[f] = gofs + (unsigned long long)s_so[lane]; P.case_gpos[f] = s_gpos[lane]; P.case_meta[f] = s_meta[lane];
         }
-        __syncwarp();
-
-        // ------------------------------------------------------------ emission in halves of up to P.E fragments
-        for (int f0 = 0; f0 < nf; f0 += P.E) {
-            const int f1 = min(nf, f0 + P.E);
-            const uint32_t b0 = __shfl_sync(0xffffffffu, roff, f0);                              // bytes [b0, b1) of the tile
-            const uint32_t b1x = __shfl_sync(0xffffffffu, roff, f1 & 31);
-            const uint32_t b1 = f1 < nf ? b1x : T;
-            const uint32_t TB = b1 - b0;
-            const int pad = (int)((uintptr_t)(P.out + gofs + b0) & 15);                           // the half is staged with its global misalignment
-            const int pofs = pad - (int)b0;                                                     // staging offset = pofs + offset within the tile
-            const bool ok = fits && TB <= (uint32_t)P.sm.stage_bytes;                           // host sizing guard: never write past staging
-            if (!ok) my_err |= ERRF_OVERFLOW;
-#if GG_BULK_COPY == 2
-            if (f0 > 0) { if (lane == 0) bulk_wait_read(); __syncwarp(); }                      // the first half's bulk copy has read the staging buffer
-#endif
-
-            // ---- headers + newlines: two lanes per fragment running the same code on different fields.  Lane 2k: '>' name ":s:" start ':';
-            // lane 2k+1: end ':' length tag ["_r"] '\n' and the newline behind the sequence   (fragSim.cpp:1489,1498,1505-1507,1603)
-            auto write_headers = [&]() {
-                const int fh = f0 + (lane >> 1), part = lane & 1;
-                if (fh < f1 && ok) {
-                    const uint32_t meta = s_meta[fh];
-                    const int L = META_L(meta);
-                    const int hdr = (int)s_hdr[fh];
-                    const uint32_t nd = s_nd[fh];
-                    const int n3 = (int)(nd >> 8);
-                    const int S = EMITC ? P.S_ad : L;
-                    uint8_t* rec = s_stage + pofs + (int)s_so[fh] - hdr - sfx0 - 1;             // first byte of the record
-                    const char* csrc; int cn, nv, coff, voff; uint64_t v;                       // bytes to copy (name / tag) and the coordinate to print, with their offsets in the header
-                    uint64_t cw = 0; bool wordcopy;                                             // names / tags of up to 8 bytes travel in a register pair
-                    if (part == 0) {
-                        const int ci = (int)s_ci[fh];
-                        csrc = t_names + t_noff[ci]; cn = t_nlen[ci]; coff = 1;
-                        v = s_idx[fh]; nv = (int)(nd & 15u); voff = 1 + cn + 3;
-                        wordcopy = t_name8 != nullptr && cn <= 8;
-                        if (wordcopy) cw = t_name8[ci];
-                    } else {
-                        const RangeDev* rg = t_ranges + s_rg[fh];
-                        csrc = rg->tag; cn = rg->tag_len; coff = hdr - cn;
-                        v = (uint64_t)s_idx[fh] + (uint64_t)L; nv = (int)((nd >> 4) & 15u); voff = hdr - cn - n3 - 1 - nv;
-                        wordcopy = cn <= 8;
-                        if (wordcopy) cw = *(const uint64_t*)rg->tag;
-                    }
-#pragma unroll
-                    for (int ln = 0; ln < NLINES; ln++) {
-                        const int sfx = ln ? sfx1 : sfx0;
-                        if (wordcopy) {
-#pragma unroll
-                            for (int k = 0; k < 8; k++) if (k < cn) rec[coff + k] = (uint8_t)(cw >> (8 * k));
-                        } else {
-#pragma unroll 1
-                            for (int k = 0; k < cn; k++) rec[coff + k] = (uint8_t)csrc[k];
-                        }
-                        uint8_t* p = rec + voff;
-                        if (v <= 0xFFFFFFFFull) put_dec32(p, (uint32_t)v, nv, s_d100); else put_decimal(p, v, nv, s_d100);
-                        p[nv] = ':';
-                        if (part == 0) { rec[0] = '>'; p[-3] = ':'; p[-2] = META_PLUS(meta) ? '+' : '-'; p[-1] = ':'; }
-                        else {
-                            put_dec32(p + nv + 1, (uint32_t)L, n3, s_d100);
-                            uint8_t* q = rec + hdr;
-                            if (sfx) { q[0] = '_'; q[1] = 'r'; q += 2; }
-                            q[0] = '\n'; q[S + 1] = '\n';
-                        }
-                        rec += hdr + sfx + 1 + S + 1;
-                    }
-                }
-            };
-            if (!FASTB) { write_headers(); __syncwarp(); }
-
-            // ---- ASCII: two lanes per fragment; a lane walks half of the staging groups of a sequence line (or one of the two lines of the
-            // four-line dialect) with one running source word: one shared-memory load, one funnel shift, the expansion and one 16-byte
-            // store per group
-            {
-                const int fd = f0 + (lane >> 1), h = lane & 1;
-                if (fd < f1 && ok) {
-                    int S = P.S_ad;
-                    if (EMITC == 0) S = META_L(s_meta[fd]);
-                    int ls = pofs + (int)s_so[fd];                                              // staging offset of the first sequence byte of the line
-                    const uint32_t* src = EMITC == 0 ? s_dwords + s_cstart[fd] : s_lwords + fd * P.lw_stride + 1;
-                    if (EMITC == 2 && h) { ls += (int)s_hdr[fd] + sfx1 + S + 2; src += P.LWL; }   // the reverse read's line
-                    const int sigma = ls & 15;
-                    const int ngr = (sigma + S + 15) >> 4;                                      // staging groups that hold bases of the line
-                    const int half = (ngr + 1) >> 1;
-                    const int g_lo = (EMITC == 2 || !h) ? 0 : half, g_hi = (EMITC == 2 || h) ? ngr : half;
-                    uint8_t* dst = s_stage + (ls - sigma) + 16 * g_lo;                          // 16-byte aligned
-                    // group g holds bases [16 g - sigma, 16 g - sigma + 16): source words (16 (g+1) - sigma) >> 4 - 1 and the next one (a guard
-                    // word sits in front of every source)
-                    const uint32_t* sp = src + (((16 * (g_lo + 1) - sigma) >> 4) - 1);
-                    const uint32_t sh = ((uint32_t)(16 - sigma) & 15u) * 2u;
-                    uint32_t prev = *sp;
-#pragma unroll 1
-                    for (int g = g_lo; g < g_hi; g++) {
-                        const uint32_t next = *++sp;
-                        const uint4 a = codes16_to_ascii(__funnelshift_r(prev, next, sh), lut);
-                        prev = next;
-                        const int j0 = 16 * g - sigma;
-                        if (FASTB || (j0 >= 0 && j0 + 16 <= S)) {
-                            *(uint4*)dst = a;                           // FASTB: bytes outside the line are rewritten by the header pass
-                        } else {
-                            // boundary group: merge under a byte mask.  Headers were written before; two sequence lines are always
-                            // >= 12 bytes apart (newline + a header), so no other lane touches these 4-byte words in this pass.
-                            const int t0 = max(j0, 0) - j0, t1 = min(j0 + 16, S) - j0;          // valid bytes [t0,t1) of the group
-                            const uint32_t V = ((1u << t1) - 1u) & ~((1u << t0) - 1u);
-                            uint32_t* d4 = (uint32_t*)dst;
-                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int w = 0; w < 4; w++) {
-                                const uint32_t nib = (V >> (4 * w)) & 0xFu;
-                                const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;     // 4 bits -> 4 byte masks
-                                if (nib == 0xFu) d4[w] = aw[w];
-                                else if (nib) d4[w] = (d4[w] & ~m) | (aw[w] & m);
-                            }
-                        }
-                        dst += 16;
-                    }
-                }
-            }
-            __syncwarp();
-            if (FASTB) { write_headers(); __syncwarp(); }
-
-            // ---- copy-out: staging -> global
-            if (ok) {
-                uint8_t* const gal = P.out + gofs + b0 - pad;            // 16-byte aligned; staging byte s <-> gal[s], valid s in [pad, pad+TB)
-                const int end = pad + (int)TB;
-                const int c_lo = (pad + 15) >> 4, c_hi = end >> 4;       // chunks [c_lo, c_hi) are complete
-#if GG_BULK_COPY
-                if (GG_BULK_COPY == 2 || f1 == nf) {                     // the tile's last half goes out through the bulk-copy engine: its staging is not needed before the next tile's emission
-                    fence_async_smem();                                  // this lane's staging writes -> visible to the bulk-copy engine
-                    __syncwarp();
-                    if (lane == 0 && c_hi > c_lo) bulk_store(gal + 16 * c_lo, s_stage + 16 * c_lo, (uint32_t)(16 * (c_hi - c_lo)));
-                } else
-#endif
-#if GG_COPY_UNROLL == 4
-#pragma unroll 1
-                for (int c = c_lo + lane; c < c_hi; c += 128) {  // four independent 16-byte copies per trip (a half tile is one or two trips)
-                    const bool p1 = c + 32 < c_hi, p2 = c + 64 < c_hi, p3 = c + 96 < c_hi;
-                    const uint8_t* sp = s_stage + 16 * c; uint8_t* gp = gal + 16 * c;
-                    uint4 v0 = *(const uint4*)sp, v1 = v0, v2 = v0, v3 = v0;
-                    if (p1) v1 = *(const uint4*)(sp + 512);
-                    if (p2) v2 = *(const uint4*)(sp + 1024);
-                    if (p3) v3 = *(const uint4*)(sp + 1536);
-                    st_global_v4(gp, v0);
-                    if (p1) st_global_v4(gp + 512, v1);
-                    if (p2) st_global_v4(gp + 1024, v2);
-                    if (p3) st_global_v4(gp + 1536, v3);
-                }
-#elif GG_COPY_UNROLL
-                {
-                    int c = c_lo + lane;
-#pragma unroll 1
-                    for (; c + 32 < c_hi; c += 64) {             // two independent 16-byte copies per trip
-                        const uint4 v0 = *(const uint4*)(s_stage + 16 * c), v1 = *(const uint4*)(s_stage + 16 * c + 512);
-                        st_global_v4(gal + 16 * c, v0); st_global_v4(gal + 16 * c + 512, v1);
-                    }
-                    if (c < c_hi) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
-                }
-#else
-                for (int c = c_lo + lane; c < c_hi; c += 32) st_global_v4(gal + 16 * c, *(const uint4*)(s_stage + 16 * c));
-#endif
-                // the partial head [pad, 16 c_lo) and tail [16 max(c_hi, c_lo), end): at most 15 bytes each, one byte per lane
-                const int t = lane < 16 ? pad + lane : 16 * max(c_hi, c_lo) + (lane - 16);
-                if (lane < 16 ? t < min(16 * c_lo, end) : t < end) gal[t] = s_stage[t];
-            }
-            __syncwarp();
-        }
+        // this tile now waits for its emission; the next ticket (its sampling starts at once, at the top of the loop)
+        have_prev = true; p_nf = nf; p_T = T; p_roff = roff; p_gofs = gofs; p_fits = fits;
+        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
     }
 #if GG_BULK_COPY
     if (lane == 0) bulk_wait_all();
@@ -1108,8 +1212,8 @@ struct SeqAscii {
 // the event-drawn models (-matfile, -damage) on one record; PH as in matrix_events / briggs_events
 template <int PH, class SeqT>
 __device__ __forceinline__ void deam_events(const DamageDev& D, const BriggsHdr& B, const Key& key, uint64_t id, int L, SeqT& S) {
-    if (D.mode == 1) matrix_events<PH, false>(key, D, D.term, D.acc, S, L, id);
-    else if (D.mode == 2) briggs_events<PH>(key, D, B, S, L, id);
+    if (D.mode == 1) matrix_events<PH, false, false>(key, D, D.term, D.acc, D.geoM, D.guideA, S, L, id);
+    else if (D.mode == 2) briggs_events<PH, false>(key, D, B, D.geoS, D.guideA, D.geoD, D.guideB, S, L, id);
 }
 
 // stand-alone deamSim main loop (deamSim.cpp:1300-2042): a warp takes 32 records; the lanes copy them (upper-casing the sequence,
@@ -1175,6 +1279,8 @@ constexpr int DS_TILE = 4096, DS_TAIL = 1536, DS_BUF = DS_TILE + DS_TAIL, DS_NLM
 constexpr int DS_WARP_BYTES = DS_BUF + 16 + 2 * DS_NLMAX + 32;
 constexpr int DS_WARPS = 32;
 constexpr int DS_TAB_BYTES = 16384;      // CTA-shared copy of the matrix tables (acceptance rows, then terminal rows) when they fit
+constexpr int DS_GEO_N = 1024;           // ... and of the first entries of the skip tables of the event draws with their guides (records up to that length draw their skips from shared memory)
+constexpr int DS_GEO_BYTES = 2 * (4 * DS_GEO_N + 512);
 
 // exact per-byte "== '\n'" flags of a word: 0x80 in every matching byte
 __device__ __forceinline__ uint32_t nl_flags(uint32_t x) {
@@ -1198,7 +1304,7 @@ struct SeqAsciiSmem {                    // an upper-cased record in shared memo
 };
 
 __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, const DamageDev D, int has_damage,
-                                                                 Key key, uint64_t first_id, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
+                                                                 const __grid_constant__ KeySched key, uint64_t first_id, unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
                                                                  unsigned long long* __restrict__ stats, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1212,6 +1318,13 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
     if (tab_sm) {
         for (int q = threadIdx.x; q < n_acc; q += blockDim.x) s_tab[q] = __ldg(D.acc + q);
         for (int q = threadIdx.x; q < n_term; q += blockDim.x) s_tab[n_acc + q] = __ldg(D.term + q);
+    }
+    // skip tables of the event draws (matrix: geoM; Briggs: geoS, geoD): a skip is two dependent loads and a record draws several in a row
+    uint32_t* const s_geo = (uint32_t*)(smem + (size_t)DS_WARPS * DS_WARP_BYTES + DS_TAB_BYTES);   // [geoA | guideA | geoB | guideB]
+    if (has_damage && (D.mode == 1 || D.mode == 2)) {
+        const int ng = min(DS_GEO_N, D.n_geo);
+        for (int q = threadIdx.x; q < ng; q += blockDim.x) { s_geo[q] = __ldg(D.geoM + q); if (D.mode == 2) s_geo[DS_GEO_N + 128 + q] = __ldg(D.geoD + q); }
+        for (int q = threadIdx.x; q < 128; q += blockDim.x) { s_geo[DS_GEO_N + q] = __ldg((const uint32_t*)D.guideA + q); if (D.mode == 2) s_geo[2 * DS_GEO_N + 128 + q] = __ldg((const uint32_t*)D.guideB + q); }
     }
     __syncthreads();
     while (true) {
@@ -1390,10 +1503,17 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
             if (has_damage && L > 0) {
                 const uint64_t id = first_id + ((base + (unsigned long long)(i + 1)) >> 1);
                 SeqAsciiSmem S; S.p = buf + ss;
+                // skips: thresholds from the shared copy when the record is short enough for it (generic pointers, plain loads), guides always
+                const bool gsm = L <= DS_GEO_N;
+                const uint32_t* const gA = gsm ? s_geo : D.geoM; const uint8_t* const uA = (const uint8_t*)(s_geo + DS_GEO_N);
                 if (D.mode == 1) {
-                    if (tab_sm) matrix_events<7, true>(key, D, s_tab + n_acc, s_tab, S, L, id);
-                    else matrix_events<7, false>(key, D, D.term, D.acc, S, L, id);
-                } else { const BriggsHdr B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM)); briggs_events<7>(key, D, B, S, L, id); }
+                    if (tab_sm) matrix_events<7, true, true>(key, D, s_tab + n_acc, s_tab, gA, uA, S, L, id);
+                    else matrix_events<7, false, true>(key, D, D.term, D.acc, gA, uA, S, L, id);
+                } else {
+                    const BriggsHdr B = dmg_briggs_hdr(D, rng_block(key, id, 0u, ST_DEAM));
+                    const uint32_t* const gB = gsm ? s_geo + DS_GEO_N + 128 : D.geoD; const uint8_t* const uB = (const uint8_t*)(s_geo + 2 * DS_GEO_N + 128);
+                    briggs_events<7, true>(key, D, B, gA, uA, gB, uB, S, L, id);
+                }
             }
             own_lo = min(own_lo, s); own_hi = max(own_hi, e2 + 1);
         }
@@ -1425,11 +1545,11 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_deam_stream(const uint8_t*
 cudaError_t launch_deam_stream(const uint8_t* in, uint64_t n, uint8_t* out, const DamageDev& D, int has_damage, Key key, uint64_t first_id,
                                unsigned long long* tile_state, unsigned int* ticket, unsigned long long* stats, uint32_t n_tiles, int sm_count, cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
-    const int smem_bytes = DS_WARPS * DS_WARP_BYTES + DS_TAB_BYTES;
+    const int smem_bytes = DS_WARPS * DS_WARP_BYTES + DS_TAB_BYTES + DS_GEO_BYTES;
     cudaError_t e = cudaFuncSetAttribute(k_deam_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)min((uint64_t)sm_count, ((uint64_t)n_tiles + DS_WARPS - 1) / DS_WARPS);
-    k_deam_stream<<<grid, DS_WARPS * 32, smem_bytes, st>>>(in, n, out, D, has_damage, key, first_id, tile_state, ticket, stats, n_tiles);
+    k_deam_stream<<<grid, DS_WARPS * 32, smem_bytes, st>>>(in, n, out, D, has_damage, make_key_sched(key.k0, key.k1), first_id, tile_state, ticket, stats, n_tiles);
     return cudaGetLastError();
 }
 int deam_stream_tile_bytes() { return DS_TILE; }

@@ -53,6 +53,7 @@ struct SmemLayout {          // byte offsets into dynamic shared memory, compute
     int thr, thr_bytes;      // CTA-shared copy of the matrix tables of the used damage slots (DMODE 1)
     int thr_slot[4];         // uint4 index of each slot's acceptance rows inside that copy ...
     int term_slot[4];        // ... and of its terminal rows
+    int geo_slot[4], geo_n;  // byte offset (in that copy) of each slot's skip tables: geo_n thresholds + 512 guide bytes, once (matrix) or twice (Briggs: s, then d); -1 = none
     int warp0, warp_bytes;   // per-warp regions start at warp0 + warp * warp_bytes; the offsets below are relative to a region
     int stage, stage_bytes;  // output staging (readable slack before and after)
     int bh;                                        // per-fragment Briggs header draws (overhangs, nick), u64 each
@@ -82,6 +83,7 @@ struct FusedParams {
     int E;                   // fragments per emission half (the staging buffer holds E records)
     uint32_t lut;            // 0x54474341: the bytes 'A','C','G','T'
     ggd::Key key;
+    ggd::KeySched ks;        // the ten Philox round keys of `key`
     // plan + genomes
     const RangeDev* ranges; int n_ranges;
     const GenomeDev* genomes; int n_genomes;
