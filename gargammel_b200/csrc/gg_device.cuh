@@ -196,7 +196,8 @@ __device__ __forceinline__ uint32_t dmg_briggs_ss_base(const DamageDev& D, const
 // from thinning: geometric skips under a majorant find the few candidate positions of a fragment, and a candidate with base b
 // becomes a with probability rate(b->a)/majorant.  A fragment then costs a handful of Philox words instead of one per base.
 // SeqT gives access to the bases of one fragment / record:  code(i) -> 0..3 or -1 (unresolved), put(i, old, new).
-__device__ __forceinline__ uint32_t count_le(uint32_t u, const uint4& T) { return (uint32_t)(u >= T.x) + (uint32_t)(u >= T.y) + (uint32_t)(u >= T.z); }
+// number of thresholds <= u among T.x <= T.y <= T.z (ascending by construction: cumulative sums): a two-level select instead of three compare-and-adds
+__device__ __forceinline__ uint32_t count_le(uint32_t u, const uint4& T) { return u >= T.y ? (u >= T.z ? 3u : 2u) : (u >= T.x ? 1u : 0u); }
 
 // matrix row (acc layout) of position i of a fragment of length L
 __device__ __forceinline__ int matrix_row(const DamageDev& D, int i, int L) {

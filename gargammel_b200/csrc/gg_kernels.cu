@@ -665,7 +665,10 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             st_volatile_u64(P.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)T);
 
         // ------------------------------------------------------------ the previous tile: rendered and stored while this tile's byte count is already visible
-        if (have_prev) {
+#ifndef GG_STAGE_TEST
+#define GG_STAGE_TEST 0          /* timing experiments only: 1 = no emission, no look-back (the front half of the kernel alone) */
+#endif
+        if (have_prev && GG_STAGE_TEST != 1) {
             // ------------------------------------------------------------ emission in halves of up to P.E fragments
             for (int f0 = 0; f0 < p_nf; f0 += P.E) {
                 const int f1 = min(p_nf, f0 + P.E);
@@ -915,11 +918,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
                     const uint32_t meta = s_meta[f];
                     const int fl = META_L(meta);
                     const uint32_t* seq2 = t_genomes[META_GEN(meta)].seq2;
-                    // forward strand: bases gp+16k ..; reverse strand: the 16 bases that end at gp+fl-16k, reverse-complemented (fragSim.cpp:1484)
-                    const int64_t pos = META_PLUS(meta) ? (int64_t)(s_gpos[f] + 16ull * (uint64_t)k) : (int64_t)(s_gpos[f] + (uint64_t)fl) - 16ll * k - 16ll;
-                    const uint32_t* wp = seq2 + (pos >> 4);
+                    // forward strand: bases gp+16k ..; reverse strand: the 16 bases that end at gp+fl-16k, reverse-complemented (fragSim.cpp:1484).
+                    // Chunks are 16 bases = one word apart: the word index is that of the fragment's first / last window plus or minus k and
+                    // the shift is the same for all of them (32-bit arithmetic: a packed genome has fewer than 2^32 words)
+                    const uint64_t base = META_PLUS(meta) ? s_gpos[f] : s_gpos[f] + (uint64_t)fl;
+                    const uint32_t w0 = (uint32_t)(base >> 4);
+                    const uint32_t* wp = seq2 + (META_PLUS(meta) ? w0 + (uint32_t)k : w0 - (uint32_t)k - 1u);
                     wlo[u] = __ldg(wp); whi[u] = __ldg(wp + 1);
-                    wmt[u] = (((uint32_t)pos & 15u) * 2u) | ((uint32_t)min(16, fl - 16 * k) << 5) | (META_PLUS(meta) ? 0u : 0x800u);
+                    wmt[u] = (((uint32_t)base & 15u) * 2u) | ((uint32_t)min(16, fl - 16 * k) << 5) | (META_PLUS(meta) ? 0u : 0x800u);
                 }
             }
 #pragma unroll
@@ -978,9 +984,14 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
             if (EMITC == 2) build_line_image(P, adsm, D, L, id, 1, lw + P.LWL + 1);     // default 4-line output: second line = reverse read
         }
 
+        // the next ticket: asked for now, used at the end of the iteration (the atomic's latency hides behind the look-back; sampling starts
+        // as soon as the look-back is done, so the ticket is still not held for long)
+        int next_tile = 0;
+        if (lane == 0) next_tile = (int)atomicAdd(P.ticket, 1u);
+
         // ------------------------------------------------------------ look-back: global byte offset of this tile
         unsigned long long gofs = 0;
-        if (tile > 0) {
+        if (tile > 0 && GG_STAGE_TEST != 1) {
             int look = tile - 1;
             while (true) {
                 const int i = look - lane;
@@ -1008,8 +1019,7 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
         }
         // this tile now waits for its emission; the next ticket (its sampling starts at once, at the top of the loop)
         have_prev = true; p_nf = nf; p_T = T; p_roff = roff; p_gofs = gofs; p_fits = fits;
-        if (lane == 0) tile = (int)atomicAdd(P.ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        tile = __shfl_sync(0xffffffffu, next_tile, 0);
     }
 #if GG_BULK_COPY
     if (lane == 0) bulk_wait_all();
