@@ -319,7 +319,7 @@ cudaError_t pool_alloc(gg_ctx* ctx, size_t bytes, void** p, size_t* got) {
 }
 
 // shared-memory carve-up: one region per warp holding a tile of F (<= 32) fragments, plus the CTA-shared tables
-SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, int line_words, int warps, int thr_bytes, bool alias_dwords,
+SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int e_frags, int line_words, int warps, int thr_bytes, int flags /* 1: staging aliases the fragment words, 2: per-fragment Briggs header words (-damagess) */,
                        int tab_ranges = 0, int tab_genomes = 0, int tab_contigs = 0, int tab_names = 0, bool tab_on = false,
                        int tab_sizes = 0, int adF_words = 0, int adS_words = 0) {
     SmemLayout s; int o = align_up(fused_desc_bytes(), 16);   // fixed-layout per-fragment descriptors (WarpDesc, gg_kernels.cu)
@@ -328,15 +328,16 @@ SmemLayout make_layout(int F, uint64_t rec_max, int max_chunks, int max_groups, 
     // dialects: staging aliases them (the words are dead once the line images exist, before staging is written) and is made large
     // enough to hold them; fragSim / deamSim records: staging follows them
     s.dwords = o;
-    s.stage_bytes = (int)((uint64_t)((F + 1) / 2) * rec_max);      // half a tile
+    const bool alias_dwords = (flags & 1) != 0;
+    s.stage_bytes = (int)((uint64_t)std::min(F, e_frags) * rec_max);      // one emission part (half a tile by default)
     const int dw_bytes = 4 * (F * max_chunks + 4);
     if (alias_dwords) { s.stage = o; s.stage_bytes = std::max(s.stage_bytes, dw_bytes); }
     else { o += align_up(dw_bytes, 16) + 16; s.stage = o; }
     o += align_up(s.stage_bytes, 16) + 48;     // (+ misalignment pad (<16) + read slack)
-    s.bh = o; o += 8 * F;
+    s.bh = o; if (flags & 2) o += 8 * F;
     s.lwords = o; o += 4 * (F * line_words + 4);
     s.cmap = o; o += F * max_chunks;
-    s.gmap = o; o += F * max_groups;           // (only the fragSim / deamSim dialects use the group map)
+    s.gmap = o;
     s.warp_bytes = align_up(o, 16);
     s.thr = 0; s.thr_bytes = thr_bytes; s.warp0 = align_up(thr_bytes, 16);
     s.tab = -1; s.tab_bytes = 0; s.n_contigs = tab_contigs; s.names_bytes = tab_names;
@@ -943,7 +944,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     if (Lmax < 0 || Lmax > MAX_FRAG_LEN) return ctx->fail(GG_ERR_ARG, "gg_run_fused: no admissible fragment length (check -l/-s/-f against -m/-M)");
     int hdr_max; uint64_t rec_max; plan_bounds(ctx, emit, Lmax, &hdr_max, &rec_max);
     const int Smax = emit_seqlen(emit, Lmax, ctx->read_len);
-    const int max_chunks = (Lmax + 15) / 16, max_groups = emit_lines(emit) * ((Smax + 15) / 16 + 1);
+    const int max_chunks = (Lmax + 15) / 16;
     // packed line images (adptSim dialects); an odd word stride per fragment: the owner lanes' accesses then fall into 32 different banks
     const int line_words = emit >= GG_EMIT_STDOUT4 ? ((emit_lines(emit) * ((Smax + 15) / 16 + 2)) | 1) : 0;
     // whole-group stores need >= 13 header bytes between two sequence lines: name + tag + 9 >= 13
@@ -997,22 +998,26 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
     int regs = 64, bps0 = 0; CK(fused_prepare(fast_boundary, dmode, emitc, 32, 4096, &bps0, &regs));
     const char* envW = getenv("GG_FUSED_WARPS"); const char* envC = getenv("GG_FUSED_CTAS");
     int F = 32;
+    // fragments per emission part (the staging buffer holds that many records): half a tile unless GG_FUSED_E says otherwise (tuning knob)
+    const char* envE = getenv("GG_FUSED_E");
+    auto e_frags = [&](int f) { const int e = envE ? std::max(1, atoi(envE)) : (f + 1) / 2; return std::min(f, e); };
+    const int lflags = (emit >= GG_EMIT_STDOUT4 ? 1 : 0) | (dmode == 0 ? 2 : 0);
     { const char* envF = getenv("GG_FUSED_F"); if (envF) F = std::max(1, std::min(32, atoi(envF))); }   // tuning knob, like GG_FUSED_WARPS
-    while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) F >>= 1;
-    if ((size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
+    while (F > 1 && (size_t)make_layout(F, rec_max, max_chunks, e_frags(F), line_words, 1, thr_bytes, lflags).total > sm_budget) F >>= 1;
+    if ((size_t)make_layout(F, rec_max, max_chunks, e_frags(F), line_words, 1, thr_bytes, lflags).total > sm_budget) return ctx->fail(GG_ERR_ARG, "gg_run_fused: a single record does not fit shared memory");
     const int ctas = envC ? std::max(1, atoi(envC)) : 1;
-    const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, max_groups, line_words, 1, thr_bytes, emit >= GG_EMIT_STDOUT4).warp_bytes;
+    const size_t per_warp = (size_t)make_layout(F, rec_max, max_chunks, e_frags(F), line_words, 1, thr_bytes, lflags).warp_bytes;
     int warps = (int)((sm_budget / (size_t)ctas - (size_t)thr_bytes - 16) / per_warp);
     warps = std::min(warps, 65536 / (regs * 32) / ctas);
     warps = std::min(warps, GG_FUSED_MAXT / 32);
     if (envW) warps = std::min(warps, std::max(1, atoi(envW)));
     warps = std::max(warps, 1);
-    SmemLayout sm = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4);
+    SmemLayout sm = make_layout(F, rec_max, max_chunks, e_frags(F), line_words, warps, thr_bytes, lflags);
     // small plan / genome / contig tables ride along in shared memory when that costs no resident warp (pass A walks them with
     // dependent loads; L1 is only a few KB at this carve-out)
     if (!getenv("GG_FUSED_NOTAB") && ctx->plan.size() <= 16 && ctx->genomes.size() <= 16 && ctx->n_contigs_total <= 96 && ctx->names_bytes <= 1024) {
         static_assert(sizeof(RangeDev) % 8 == 0 && sizeof(GenomeDev) % 8 == 0, "the shared-memory table copy moves whole words");
-        SmemLayout st = make_layout(F, rec_max, max_chunks, max_groups, line_words, warps, thr_bytes, emit >= GG_EMIT_STDOUT4,
+        SmemLayout st = make_layout(F, rec_max, max_chunks, e_frags(F), line_words, warps, thr_bytes, lflags,
                                     (int)ctx->plan.size(), (int)ctx->genomes.size(), ctx->n_contigs_total, ctx->names_bytes, true,
                                     (ctx->size_mode == GG_SIZE_FREQ && ctx->size_len.size() <= 512) ? (int)ctx->size_len.size() : 0,
                                     (ctx->adF.size() <= 512 && ctx->adS.size() <= 512 && emit >= GG_EMIT_STDOUT4) ? (int)(1 + (ctx->adF.size() + 15) / 16 + 3) : 0,
@@ -1045,7 +1050,7 @@ int gg_run_fused(gg_ctx* ctx, uint64_t first, uint64_t count, int emit, gg_out* 
         P.gmagic = (uint32_t)((0x100000000ull + P.gpf_ad - 1) / P.gpf_ad);
         P.sfx0 = emit == GG_EMIT_RR ? 2 : 0;
     }
-    P.E = (F + 1) / 2; P.lut = 0x54474341u;
+    P.E = e_frags(F); P.lut = 0x54474341u;
     P.key.k0 = (uint32_t)ctx->seed; P.key.k1 = (uint32_t)(ctx->seed >> 32); P.ks = ggd::make_key_sched(P.key.k0, P.key.k1);
     P.ranges = ctx->d_ranges.as<RangeDev>(); P.n_ranges = (int)ctx->plan.size();
     P.genomes = ctx->d_genomes.as<GenomeDev>(); P.n_genomes = (int)ctx->genomes.size();

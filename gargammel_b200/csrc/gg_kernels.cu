@@ -518,7 +518,6 @@ __global__ void __launch_bounds__(GG_FUSED_MAXT, 1) k_fused(const __grid_constan
     uint32_t* const s_dwords = (uint32_t*)(wb + W0);
     uint32_t* const s_lwords = (uint32_t*)(wb + P.sm.lwords);   // line images (adptSim dialects only)
     uint8_t*  const s_cmap   = wb + P.sm.cmap;
-    uint8_t*  const s_gmap   = wb + P.sm.gmap;
 
     uint32_t my_attempts = 0, my_gather = 0, my_err = 0;
     const uint32_t lut = P.lut;                     // 'A','C','G','T' for the byte permutes of the ASCII pass (a kernel parameter: as an immediate it was re-materialised four times per group)
