@@ -9,7 +9,7 @@ BINS     := bin/fragSim bin/deamSim bin/adptSim bin/gargammel-b200
 
 all: $(LIB) $(BINS) oracle
 
-$(LIB): $(CSRC)/gg_api.cu $(CSRC)/gg_kernels.cu $(CSRC)/gg_host.cpp $(CSRC)/gg_kernels.cuh $(CSRC)/gg_device.cuh $(CSRC)/gg_host.h include/gargammel_b200.h
+$(LIB): $(CSRC)/gg_api.cu $(CSRC)/gg_kernels.cu $(CSRC)/gg_host.cpp $(CSRC)/gg_kernels.cuh $(CSRC)/gg_device.cuh $(CSRC)/gg_host.h $(CSRC)/gg_lz.h include/gargammel_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gg_api.cu $(CSRC)/gg_kernels.cu $(CSRC)/gg_host.cpp -lz 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 	@grep -E "registers|spill" build_ptxas.log | sort | uniq -c | sort -rn | head -20
 

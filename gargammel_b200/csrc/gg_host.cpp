@@ -638,6 +638,150 @@ uint32_t crc32_x8n(uint64_t n_bytes) {
     return r;
 }
 
+// ---------------------------------------------------------------- LZ77 + Huffman deflate of the device BGZF encoder: code builder and host model
+// (parse specification: gg_lz.h)
+bool build_lz_code(const uint64_t hist[gglz::N_SYM], LzCode& out, std::string& err) {
+    using namespace gglz;
+    std::vector<uint64_t> cl_(N_LITLEN), cd_(N_DIST);
+    for (int i = 0; i < N_LITLEN; i++) cl_[i] = hist[i] ? hist[i] : 1;             // every symbol encodable
+    for (int i = 0; i < N_DIST; i++) cd_[i] = hist[N_LITLEN + i] ? hist[N_LITLEN + i] : 1;
+    std::vector<int> ll, dl; huff_lengths(cl_, 15, ll); huff_lengths(cd_, 15, dl);
+    std::vector<uint32_t> lc, dc; canonical_codes(ll, 15, lc); canonical_codes(dl, 15, dc);
+    for (int s = 0; s < N_LITLEN; s++) {
+        if (ll[s] < 1 || ll[s] > 15) { err = "build_lz_code: bad literal/length code length"; return false; }
+        out.sym[s] = bitrev(lc[s], ll[s]) | ((uint32_t)ll[s] << 16);
+    }
+    for (int s = 0; s < N_DIST; s++) {
+        if (dl[s] < 1 || dl[s] > 15) { err = "build_lz_code: bad distance code length"; return false; }
+        out.sym[N_LITLEN + s] = bitrev(dc[s], dl[s]) | ((uint32_t)dl[s] << 16);
+    }
+    std::vector<int> seq(ll.begin(), ll.end()); seq.insert(seq.end(), dl.begin(), dl.end());   // 286 + 30 lengths, one sequence (RFC 1951 3.2.7)
+    std::vector<std::pair<int, int> > cl;
+    for (size_t i = 0; i < seq.size();) {
+        size_t j = i; while (j < seq.size() && seq[j] == seq[i]) j++;
+        size_t run = j - i;
+        cl.push_back(std::make_pair(seq[i], 0)); run--;
+        while (run >= 3) { const int r = (int)std::min<size_t>(run, 6); cl.push_back(std::make_pair(16, r - 3)); run -= (size_t)r; }
+        while (run--) cl.push_back(std::make_pair(seq[i], 0));
+        i = j;
+    }
+    std::vector<uint64_t> clcnt(19, 0);
+    for (size_t i = 0; i < cl.size(); i++) clcnt[cl[i].first]++;
+    std::vector<int> cllen; huff_lengths(clcnt, 7, cllen);
+    std::vector<uint32_t> clcode; canonical_codes(cllen, 7, clcode);
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int hclen = 19; while (hclen > 4 && cllen[order[hclen - 1]] == 0) hclen--;
+    BitWriter w;
+    w.put(1, 1); w.put(2, 2);                                              // BFINAL = 1, BTYPE = 10
+    w.put((uint32_t)(N_LITLEN - 257), 5); w.put((uint32_t)(N_DIST - 1), 5); w.put((uint32_t)(hclen - 4), 4);
+    for (int i = 0; i < hclen; i++) w.put((uint32_t)cllen[order[i]], 3);
+    for (size_t i = 0; i < cl.size(); i++) {
+        w.put(bitrev(clcode[cl[i].first], cllen[cl[i].first]), cllen[cl[i].first]);
+        if (cl[i].first == 16) w.put((uint32_t)cl[i].second, 2);
+    }
+    out.header = w.b; out.header_nbits = w.nbits;
+    return true;
+}
+namespace {
+inline uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+inline uint32_t ld32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+struct LzTok { uint16_t len, dist; uint8_t lit; };       // len == 0: literal
+// tokens of run w of a member (gg_lz.h)
+void lz_run_tokens(const uint8_t* in, int nb, int w, std::vector<LzTok>& toks) {
+    using namespace gglz;
+    const int start = w * RUN, end = std::min(nb, start + RUN);
+    if (start >= end) return;
+    uint16_t T[TABLE]; for (int i = 0; i < TABLE; i++) T[i] = 0xFFFFu;
+    if (w > 0) for (int p = start - WARM; p < start; p++) if (p + MIN_MATCH <= nb) T[lz_hash(ld32(in + p), ld16(in + p + 4))] = (uint16_t)p;
+    int cover = start;
+    for (int base = start; base < end; base += 32) {
+        int dist[32]; bool m[32];
+        for (int l = 0; l < 32; l++) {
+            const int p = base + l; m[l] = false; dist[l] = 0;
+            if (p + MIN_MATCH > end) continue;
+            const uint16_t c = T[lz_hash(ld32(in + p), ld16(in + p + 4))];
+            if (c != 0xFFFFu && p - (int)c <= 32768 && memcmp(in + c, in + p, MIN_MATCH) == 0) { m[l] = true; dist[l] = p - (int)c; }
+        }
+        for (int l = 0; l < 32; l++) { const int p = base + l; if (p + MIN_MATCH <= end) T[lz_hash(ld32(in + p), ld16(in + p + 4))] = (uint16_t)p; }
+        for (int l = 0; l < 32; l++) {
+            const int p = base + l;
+            if (p >= end) break;
+            if (p < cover) continue;
+            LzTok t; t.len = 0; t.dist = 0; t.lit = in[p];
+            if (m[l]) {
+                int len = MIN_MATCH; const int maxlen = std::min(MAX_MATCH, end - p);
+                while (len < maxlen && in[p + len] == in[p + len - dist[l]]) len++;
+                t.len = (uint16_t)len; t.dist = (uint16_t)dist[l]; cover = p + len;
+            }
+            toks.push_back(t);
+        }
+    }
+}
+void lz_count(const std::vector<LzTok>& toks, uint64_t* hist) {
+    using namespace gglz;
+    for (size_t i = 0; i < toks.size(); i++) {
+        if (!toks[i].len) { hist[toks[i].lit]++; continue; }
+        int s, nx; uint32_t xv;
+        len_symbol(toks[i].len, ilog2((uint32_t)toks[i].len - 3u), &s, &nx, &xv); hist[s]++;
+        dist_symbol(toks[i].dist, ilog2((uint32_t)toks[i].dist - 1u), &s, &nx, &xv); hist[N_LITLEN + s]++;
+    }
+}
+}
+bool bgzf_lz_model(const uint8_t* in, size_t n, std::vector<uint8_t>& out, bool eof_marker, std::string& err, uint64_t* hist_out) {
+    using namespace gglz;
+    const size_t B = 65280, n_blocks = (n + B - 1) / B;
+    const size_t stride = std::max<size_t>(1, (n_blocks + SAMPLE_MEMBERS - 1) / SAMPLE_MEMBERS);
+    uint64_t hist[N_SYM]; memset(hist, 0, sizeof hist);
+    std::vector<LzTok> toks;
+    for (size_t b = 0; b < n_blocks; b += stride) {
+        const int nb = (int)std::min(B, n - b * B);
+        for (int w = 0; w < 30; w++) { toks.clear(); lz_run_tokens(in + b * B, nb, w, toks); lz_count(toks, hist); }
+        hist[256]++;
+    }
+    if (hist_out) memcpy(hist_out, hist, sizeof hist);
+    LzCode code;
+    if (!build_lz_code(hist, code, err)) return false;
+    out.clear();
+    for (size_t b = 0; b < n_blocks; b++) {
+        const uint8_t* src = in + b * B; const int nb = (int)std::min(B, n - b * B);
+        BitWriter w; bool overflow = false;
+        for (size_t i = 0; i < code.header.size(); i++) w.b.push_back(code.header[i]);
+        w.nbits = code.header_nbits;
+        for (int r = 0; r < 30; r++) {
+            toks.clear(); lz_run_tokens(src, nb, r, toks);
+            const int bits0 = w.nbits;
+            for (size_t i = 0; i < toks.size(); i++) {
+                if (!toks[i].len) { const uint32_t s = code.sym[toks[i].lit]; w.put(s & 0xFFFFu, (int)(s >> 16)); continue; }
+                int s, nx; uint32_t xv;
+                len_symbol(toks[i].len, ilog2((uint32_t)toks[i].len - 3u), &s, &nx, &xv);
+                w.put(code.sym[s] & 0xFFFFu, (int)(code.sym[s] >> 16)); w.put(xv, nx);
+                dist_symbol(toks[i].dist, ilog2((uint32_t)toks[i].dist - 1u), &s, &nx, &xv);
+                w.put(code.sym[N_LITLEN + s] & 0xFFFFu, (int)(code.sym[N_LITLEN + s] >> 16)); w.put(xv, nx);
+            }
+            if (w.nbits - bits0 > REGION * 8) overflow = true;       // the kernel stages a run's bits in REGION bytes
+        }
+        w.put(code.sym[256] & 0xFFFFu, (int)(code.sym[256] >> 16));
+        size_t payload = ((size_t)w.nbits + 7) / 8;
+        const bool stored = overflow || payload >= (size_t)nb + 5;
+        if (stored) payload = (size_t)nb + 5;
+        const size_t total = 18 + payload + 8;
+        const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1) & 0xFF), (uint8_t)((total - 1) >> 8)};
+        out.insert(out.end(), hdr, hdr + 18);
+        if (stored) {
+            const uint8_t sh[5] = {1, (uint8_t)(nb & 0xFF), (uint8_t)(nb >> 8), (uint8_t)(~nb & 0xFF), (uint8_t)((~nb >> 8) & 0xFF)};
+            out.insert(out.end(), sh, sh + 5); out.insert(out.end(), src, src + nb);
+        } else { w.b.resize(payload, 0); out.insert(out.end(), w.b.begin(), w.b.end()); }
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)nb);
+        for (int k = 0; k < 4; k++) out.push_back((uint8_t)(crc >> (8 * k)));
+        for (int k = 0; k < 4; k++) out.push_back((uint8_t)((uint32_t)nb >> (8 * k)));
+    }
+    if (eof_marker) {
+        static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        out.insert(out.end(), eof, eof + 28);
+    }
+    return true;
+}
+
 bool load_genome(const std::string& fasta_path, GenomeFile& g, std::string& err) {
     g.path = fasta_path;
     if (!read_file(fasta_path, g.bytes, err)) return false;            // .gz is inflated in memory (the reference writes a temp file, fragSim.cpp:1108-1147)
@@ -722,6 +866,14 @@ int ggh_deflate_code(const uint64_t* hist, uint32_t* sym257, uint8_t* hdr, int h
     memcpy(sym257, c.sym, sizeof c.sym);
     if ((int)c.header.size() > hdr_cap) return -2;
     memcpy(hdr, c.header.data(), c.header.size()); *hdr_nbits = c.header_nbits; return 0;
+}
+// test hook: the host model of the device LZ encoder (gg_lz.h): BGZF members of `in`, and the sampled symbol counts (316) if hist != NULL
+int ggh_bgzf_lz_model(const uint8_t* in, size_t n, int eof_marker, uint8_t* out, size_t cap, size_t* out_n, uint64_t* hist) {
+    std::vector<uint8_t> o; std::string e;
+    if (!ggh::bgzf_lz_model(in, n, o, eof_marker != 0, e, hist)) return -1;
+    *out_n = o.size();
+    if (o.size() > cap) return -2;
+    memcpy(out, o.data(), o.size()); return 0;
 }
 uint32_t ggh_crc32_x8n(uint64_t n) { return ggh::crc32_x8n(n); }
 uint32_t ggh_crc32_mul(uint32_t a, uint32_t b) { return ggh::crc32_mul(a, b); }

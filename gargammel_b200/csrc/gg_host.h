@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include "../../include/gargammel_b200.h"
+#include "gg_lz.h"
 
 namespace ggh {
 
@@ -77,6 +78,13 @@ bool bgzf_compress(const uint8_t* in, size_t n, int threads, int level, std::vec
 // into an LSB-first bit stream); header = BFINAL=1, BTYPE=10 and the code description, LSB-first, header_nbits bits.
 struct DeflateCode { uint32_t sym[257]; std::vector<uint8_t> header; int header_nbits; };
 bool build_deflate_code(const uint64_t hist[256], DeflateCode& out, std::string& err);
+// ---- LZ77 + Huffman deflate code for the device BGZF encoder with matches (k_bgzf_lz; parse specification in gg_lz.h) ----
+// sym[0..286): literal/length codes, sym[286..316): distance codes (bit-reversed code | len << 16), every symbol encodable; header =
+// BFINAL=1, BTYPE=10, HLIT=29, HDIST=29 and the code description.  hist = symbol counts of the sampled members (316).
+struct LzCode { uint32_t sym[gglz::N_SYM]; std::vector<uint8_t> header; int header_nbits; };
+bool build_lz_code(const uint64_t hist[gglz::N_SYM], LzCode& out, std::string& err);
+// host model of the device encoder: the same parse, the same code, the same members byte for byte (tests pin the kernel to it)
+bool bgzf_lz_model(const uint8_t* in, size_t n, std::vector<uint8_t>& out, bool eof_marker, std::string& err, uint64_t* hist_out = nullptr);
 // CRC-32 (IEEE, reflected) helpers for the device encoder: slicing-by-4 tables and x^(8n) mod P in the reflected domain
 void crc32_tables(uint32_t t[4][256]);
 uint32_t crc32_x8n(uint64_t n_bytes);                       // multiply a CRC by this (crc32_mul) to append n_bytes zero-effect bytes
@@ -126,6 +134,7 @@ int ggh_apportion(uint64_t n, double compB, double compC, double compE, int n_en
 uint64_t ggh_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream);
 /* returns 0 and the compressed size in *out_n; out needs n + n/255 + 64 KiB */
 int ggh_bgzf_compress(const uint8_t* in, size_t n, int threads, int level, int eof_marker, uint8_t* out, size_t cap, size_t* out_n);
+int ggh_bgzf_lz_model(const uint8_t* in, size_t n, int eof_marker, uint8_t* out, size_t cap, size_t* out_n, uint64_t* hist);
 int ggh_load_dnacomp(const char* path, int dist, double* s5p, double* s5m, double* s3p, double* s3m, char* err, int errcap);   /* each [2*dist][4] */
 int ggh_lognormal_table(double loc, double scale, int cap, int32_t* len, double* cum);   /* cap+2 rows */
 /* BAM round trip for the tests: a 2-line FASTA record stream -> unaligned BAM file (flag 4, phred 0, stored BGZF members), and back */
