@@ -1351,47 +1351,82 @@ int gg_bgzf_dev(gg_ctx* ctx, const gg_out* in, gg_out* out) {
     const uint64_t n_blocks = (n + BGZF_BLOCK - 1) / BGZF_BLOCK;
     if (n_blocks > 0xFFFFFFF0ull) return ctx->fail(GG_ERR_ARG, "gg_bgzf_dev: stream too long");
     const uint64_t out_cap = n + n_blocks * (18 + 5 + 8) + 64;            // every member at worst stored
+    // the encoder with LZ77 matches (k_bgzf_lz) unless GG_BGZF_MODE=huff asks for the Huffman-only one (k_bgzf_deflate)
+    const char* mode_env = getenv("GG_BGZF_MODE");
+    const bool use_lz = !(mode_env && strcmp(mode_env, "huff") == 0);
+    const int HN = use_lz ? 320 : 256;                                      // histogram counters
     DBuf& oslab = ctx->bgzf_slab ? ctx->d_bgzf2 : ctx->d_bgzf;
     CK(oslab.ensure(out_cap));
-    CK(ctx->d_bgzf_tab.ensure((size_t)BGZF_TAB_WORDS * 4));
-    CK(ctx->d_bgzf_state.ensure((size_t)n_blocks * 8 + 256 * 8 + 64));
+    CK(ctx->d_bgzf_tab.ensure((size_t)std::max(BGZF_TAB_WORDS, BGZL_TAB_WORDS) * 4));
+    CK(ctx->d_bgzf_state.ensure((size_t)n_blocks * 8 + (size_t)HN * 8 + 64));
     unsigned long long* d_state = ctx->d_bgzf_state.as<unsigned long long>();
-    unsigned long long* d_hist = d_state + n_blocks;                         // 256 counters
-    unsigned long long* d_total = d_hist + 256;                              // [0] bytes, [1] error flag
-    unsigned int* d_ticket = (unsigned int*)(d_total + 2);
+    unsigned long long* d_hist = d_state + n_blocks;                         // HN counters
+    unsigned long long* d_total = d_hist + HN;                               // [0] bytes, [1] error flag
+    unsigned int* d_ticket = (unsigned int*)(d_total + 2);                   // [0] encoder, [1] counting pass
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    CK(cudaMemsetAsync(d_state, 0, (size_t)n_blocks * 8 + 256 * 8 + 32, ctx->st));
-    int launches = 2;                                                       // k_bgzf_deflate + k_publish
+    CK(cudaMemsetAsync(d_state, 0, (size_t)n_blocks * 8 + (size_t)HN * 8 + 32, ctx->st));
+    int launches = 2;                                                       // the encoder + k_publish
     if (!(ctx->bgzf_reuse_code && ctx->bgzf_hdr_nbits > 0)) {      // (the chunked pipeline keeps the code of its first chunk)
-    // 1. sampled byte histogram (<= ~32 MB of the stream) -> one dynamic Huffman code for the whole stream
-        const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
-        CK(launch_byte_hist((const uint8_t*)in->dev_ptr, n, stride, d_hist, ctx->st));
-        unsigned long long hist[256];
-        { int rcp = fetch_small(ctx, d_hist, hist, 256); if (rcp) return rcp; }
-        ggh::DeflateCode code; std::string e;
-        uint64_t h64[256]; for (int i = 0; i < 256; i++) h64[i] = hist[i];
-        if (!ggh::build_deflate_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
-        if (code.header_nbits > BGZF_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
-        if (ctx->bgzf_static.empty()) {
+        if (ctx->bgzf_static.empty()) {                                     // CRC tables and shift polynomials, in the Huffman-only layout
             ctx->bgzf_static.assign(BGZF_TAB_WORDS, 0u);
             uint32_t t[4][256]; ggh::crc32_tables(t);
             memcpy(&ctx->bgzf_static[BGZF_TAB_CRC], t, sizeof t);
             for (int k = 0; k < BGZF_THREADS; k++) ctx->bgzf_static[BGZF_TAB_SHIFT + k] = ggh::crc32_x8n((uint64_t)BGZF_RUN * (uint64_t)(BGZF_THREADS - 1 - k));
             for (int k = 0; k < 17; k++) ctx->bgzf_static[BGZF_TAB_X8 + k] = ggh::crc32_x8n(1ull << k);
         }
-        std::vector<uint32_t> tab(ctx->bgzf_static);
-        memcpy(&tab[BGZF_TAB_SYM], code.sym, sizeof code.sym);
-        for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
+        std::vector<uint32_t> tab;
+        if (use_lz) {
+            // 1. symbol counts of every stride-th member under the encoder's own parse -> one literal/length + distance code for the stream
+            BgzfLzParams C; memset(&C, 0, sizeof C);
+            C.in = (const uint8_t*)in->dev_ptr; C.n = n; C.stride = (uint32_t)std::max<uint64_t>(1, (n_blocks + gglz::SAMPLE_MEMBERS - 1) / gglz::SAMPLE_MEMBERS);
+            C.n_blocks = (uint32_t)((n_blocks + C.stride - 1) / C.stride); C.ticket = d_ticket + 1; C.hist = d_hist;
+            CK(launch_bgzf_lz(C, true, (int)std::min<uint64_t>(C.n_blocks, (uint64_t)ctx->sm_count), ctx->st));
+            unsigned long long hist[gglz::N_SYM];
+            { int rcp = fetch_small(ctx, d_hist, hist, gglz::N_SYM); if (rcp) return rcp; }
+            ggh::LzCode code; std::string e;
+            uint64_t h64[gglz::N_SYM]; for (int i = 0; i < gglz::N_SYM; i++) h64[i] = hist[i];
+            if (!ggh::build_lz_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
+            if (code.header_nbits > BGZL_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
+            tab.assign(BGZL_TAB_WORDS, 0u);
+            memcpy(&tab[BGZL_TAB_CRC], &ctx->bgzf_static[BGZF_TAB_CRC], 1024 * 4);
+            memcpy(&tab[BGZL_TAB_SHIFT], &ctx->bgzf_static[BGZF_TAB_SHIFT], BGZF_THREADS * 4);
+            memcpy(&tab[BGZL_TAB_X8], &ctx->bgzf_static[BGZF_TAB_X8], 17 * 4);
+            memcpy(&tab[BGZL_TAB_SYM], code.sym, sizeof code.sym);
+            for (size_t i = 0; i < code.header.size(); i++) tab[BGZL_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
+            ctx->bgzf_hdr_nbits = code.header_nbits;
+        } else {
+            // 1. sampled byte histogram (<= ~32 MB of the stream) -> one dynamic Huffman code for the whole stream
+            const uint64_t stride = std::max<uint64_t>(1, (n >> 4) / (2u << 20));
+            CK(launch_byte_hist((const uint8_t*)in->dev_ptr, n, stride, d_hist, ctx->st));
+            unsigned long long hist[256];
+            { int rcp = fetch_small(ctx, d_hist, hist, 256); if (rcp) return rcp; }
+            ggh::DeflateCode code; std::string e;
+            uint64_t h64[256]; for (int i = 0; i < 256; i++) h64[i] = hist[i];
+            if (!ggh::build_deflate_code(h64, code, e)) return ctx->fail(GG_ERR_STATE, e);
+            if (code.header_nbits > BGZF_HDR_WORDS * 32) return ctx->fail(GG_ERR_STATE, "gg_bgzf_dev: code description too long");
+            tab = ctx->bgzf_static;
+            memcpy(&tab[BGZF_TAB_SYM], code.sym, sizeof code.sym);
+            for (size_t i = 0; i < code.header.size(); i++) tab[BGZF_TAB_HDR + (i >> 2)] |= (uint32_t)code.header[i] << (8 * (i & 3));
+            ctx->bgzf_hdr_nbits = code.header_nbits;
+        }
         CK(cudaMemcpyAsync(ctx->d_bgzf_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));                                 // tab is a local
-        ctx->bgzf_hdr_nbits = code.header_nbits; launches = 4;     // + k_byte_hist + its k_publish
+        launches = 4;                                                       // + the counting / histogram pass + its k_publish
     }
     // 2. one CTA per 65280-byte member, persistent over the SMs
-    BgzfParams P;
-    P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;
-    P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = ctx->bgzf_hdr_nbits; P.n_blocks = (uint32_t)n_blocks;
-    P.state = d_state; P.ticket = d_ticket; P.total = d_total;
-    CK(launch_bgzf_deflate(P, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
+    if (use_lz) {
+        BgzfLzParams P; memset(&P, 0, sizeof P);
+        P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;
+        P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = ctx->bgzf_hdr_nbits; P.n_blocks = (uint32_t)n_blocks; P.stride = 1;
+        P.state = d_state; P.ticket = d_ticket; P.total = d_total; P.hist = d_hist;
+        CK(launch_bgzf_lz(P, false, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
+    } else {
+        BgzfParams P;
+        P.in = (const uint8_t*)in->dev_ptr; P.n = n; P.out = oslab.as<uint8_t>(); P.out_cap = out_cap;
+        P.tab = ctx->d_bgzf_tab.as<uint32_t>(); P.hdr_nbits = ctx->bgzf_hdr_nbits; P.n_blocks = (uint32_t)n_blocks;
+        P.state = d_state; P.ticket = d_ticket; P.total = d_total;
+        CK(launch_bgzf_deflate(P, (int)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count), ctx->st));
+    }
     unsigned long long tot[2];
     { int rcp = fetch_small(ctx, d_total, tot, 2, ctx->ev1); if (rcp) return rcp; }
     float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

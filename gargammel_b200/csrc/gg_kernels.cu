@@ -2125,4 +2125,353 @@ cudaError_t launch_bgzf_deflate(const BgzfParams& P, int grid, cudaStream_t st) 
     return cudaGetLastError();
 }
 
+// ======================================================================================= device BGZF with LZ77 matches
+// The same member framing as k_bgzf_deflate, but a member's deflate block carries matches: one warp parses one 2176-byte run of the member
+// in steps of 32 positions (hash of the next 6 bytes -> 512-entry table of the most recent earlier positions, greedy selection, byte-wise
+// extension; gg_lz.h is the specification and ggh::bgzf_lz_model its host model: the output is the model's byte for byte).  A warp
+// appends its codes to a private region of shared memory; once the bit counts of the 30 runs are scanned, the member's payload is
+// gathered from the header bits, the regions and the end-of-block code with funnel shifts, straight into 16-byte global stores.
+// COUNT: the sampling pass in front (every stride-th member): the same parse, symbol counts instead of codes.
+constexpr int BGZL_REGION_WORDS = gglz::REGION / 4;
+constexpr int BGZL_PROV_BYTES = 30 * gglz::REGION + 16;
+constexpr int BGZL_SCAN_WORDS = 160;
+// 6 bytes at byte offset p of a word-aligned shared-memory buffer: low four, then the next two
+__device__ __forceinline__ void lz_load6(const uint8_t* buf, int p, uint32_t& lo, uint32_t& hi16) {
+    const uint32_t* wp = (const uint32_t*)(buf + (p & ~3));
+    const uint32_t sh = 8u * ((uint32_t)p & 3u);
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    lo = __funnelshift_r(w0, w1, sh); hi16 = __funnelshift_r(w1, w2, sh) & 0xFFFFu;
+}
+// segment k of a member's payload: 0 = code description, 1..30 = the runs' regions, 31 = end-of-block code
+__device__ __forceinline__ const uint32_t* lz_seg_src(int k, const uint32_t* s_tab, const uint32_t* s_prov, const uint32_t* s_scan) {
+    return k == 0 ? s_tab + BGZL_TAB_HDR : k == 31 ? s_scan + 120 : s_prov + (k - 1) * BGZL_REGION_WORDS;
+}
+// 32 bits of the payload from bit t on (zeros behind its end); S[k] = first bit of segment k, S[32] = total; k: the caller's running segment index
+__device__ __forceinline__ uint32_t lz_gather32(uint32_t t, int& k, const uint32_t* S, const uint32_t* s_tab, const uint32_t* s_prov, const uint32_t* s_scan) {
+    while (k < 32 && S[k + 1] <= t) k++;
+    uint32_t out = 0, got = 0, tt = t; int kk = k;
+    while (got < 32u && kk < 32) {
+        const uint32_t o = tt - S[kk], avail = S[kk + 1] - tt;
+        const uint32_t* src = lz_seg_src(kk, s_tab, s_prov, s_scan) + (o >> 5);
+        uint32_t v = __funnelshift_r(src[0], src[1], o & 31u);
+        const uint32_t take = min(avail, 32u - got);
+        if (take < 32u) v &= (1u << take) - 1u;
+        out |= v << got; got += take; tt += take;
+        kk++; while (kk < 32 && S[kk + 1] <= tt) kk++;
+    }
+    return out;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_lz(const __grid_constant__ BgzfLzParams P) {
+    using namespace gglz;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* const s_prov = (uint32_t*)(smem + 2 * BGZF_BLOCK);            // 30 regions of REGION bytes: the runs' codes, bit 0 = first bit of the run
+    uint32_t* const s_tab = s_prov + BGZL_PROV_BYTES / 4;
+    uint16_t* const s_hash = (uint16_t*)(s_tab + BGZL_TAB_WORDS);           // 30 tables of TABLE positions
+    uint32_t* const s_scan = (uint32_t*)(s_hash + 30 * TABLE);              // BGZL_SCAN_WORDS: [0,30) run bits, [32,62) run CRCs, [64,97) segment starts S, misc from 100, [120,122) end-of-block code
+    uint32_t* const s_len = s_scan + BGZL_SCAN_WORDS;                       // 256: match length - 3 -> length code with its extra bits | total bits << 24
+    uint32_t* const s_hist = s_prov;                                        // COUNT: 316 symbol counters
+    const uint32_t* const s_sym = s_tab + BGZL_TAB_SYM;
+    const uint32_t* const s_crc = s_tab + BGZL_TAB_CRC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!COUNT) {
+        for (int i = tid; i < BGZL_TAB_WORDS; i += BGZF_THREADS) s_tab[i] = __ldg(P.tab + i);
+    } else {
+        for (int i = tid; i < N_SYM; i += BGZF_THREADS) s_hist[i] = 0u;
+    }
+    if (tid == 0) s_scan[100] = atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const uint32_t eob = COUNT ? 0u : s_sym[256];
+    if (tid == 0) { s_scan[120] = eob & 0xFFFFu; s_scan[121] = 0u; }
+    if (!COUNT && tid < 256) {
+        int ls, lnx; uint32_t lxv;
+        len_symbol(tid + 3, 31 - __clz(tid | 1), &ls, &lnx, &lxv);
+        const uint32_t sy = s_sym[ls], n1 = sy >> 16;
+        s_len[tid] = (sy & 0xFFFFu) | (lxv << n1) | ((n1 + (uint32_t)lnx) << 24);
+    }
+    __syncthreads();
+    uint32_t v = s_scan[100];                                                // visit number; member index = visit * stride
+    int cur = 0;
+    auto prefetch = [&](uint32_t visit, uint8_t* s_dst) {
+        if (visit >= P.n_blocks) return;
+        const uint64_t base = (uint64_t)visit * P.stride * BGZF_BLOCK;
+        const int nbp = (int)min((uint64_t)BGZF_BLOCK, P.n - base);
+        for (int g = tid; g < BGZF_BLOCK / 16; g += BGZF_THREADS) {
+            const int valid = max(0, min(16, nbp - 16 * g));
+            cp_async16_zfill(s_dst + 16 * g, P.in + base + (valid ? 16 * g : 0), valid);
+        }
+    };
+    prefetch(v, smem);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    while (v < P.n_blocks) {
+        uint8_t* const s_in = smem + cur * BGZF_BLOCK;
+        const uint64_t b = (uint64_t)v * P.stride;
+        const uint64_t base = b * BGZF_BLOCK;
+        const int nb = (int)min((uint64_t)BGZF_BLOCK, P.n - base);
+        if (tid == 0) s_scan[101] = atomicAdd(P.ticket, 1u);
+        if (!COUNT) for (int g = tid; g < BGZL_PROV_BYTES / 16; g += BGZF_THREADS) ((uint4*)s_prov)[g] = make_uint4(0, 0, 0, 0);
+        {   // this warp's table: empty
+            uint4* T4 = (uint4*)(s_hash + warp * TABLE);
+            for (int g = lane; g < TABLE * 2 / 16; g += 32) T4[g] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        const uint32_t v_next = s_scan[101];
+        prefetch(v_next, smem + (cur ^ 1) * BGZF_BLOCK);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        // ---- CRC-32 of my 68-byte run, shifted over the bytes behind it (as in k_bgzf_deflate)
+        uint32_t crc = 0;
+        if (!COUNT) {
+            const int r0 = tid * BGZF_RUN;
+            const int len = max(0, min(BGZF_RUN, nb - r0));
+            const uint32_t* const wp = (const uint32_t*)(s_in + r0);
+            crc = 0xFFFFFFFFu;
+            const int nw = len >> 2;
+#pragma unroll 2
+            for (int w = 0; w < nw; w++) {
+                crc ^= wp[w];
+                crc = s_crc[768 + (crc & 0xFFu)] ^ s_crc[512 + ((crc >> 8) & 0xFFu)] ^ s_crc[256 + ((crc >> 16) & 0xFFu)] ^ s_crc[crc >> 24];
+            }
+            for (int k = 4 * nw; k < len; k++) crc = s_crc[(crc ^ s_in[r0 + k]) & 0xFFu] ^ (crc >> 8);
+            crc = len ? ~crc : 0u;
+            if (len) {
+                uint32_t sh;
+                if (nb == BGZF_BLOCK) sh = s_tab[BGZL_TAB_SHIFT + tid];
+                else {
+                    sh = 0x80000000u;
+                    uint32_t after = (uint32_t)(nb - r0 - len);
+                    for (int k = 0; after; k++, after >>= 1) if (after & 1u) sh = crc_mul(sh, s_tab[BGZL_TAB_X8 + k]);
+                }
+                crc = crc_mul(crc, sh);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+        }
+
+        // ---- parse of my warp's run (gg_lz.h), codes appended to the warp's region
+        uint32_t cursor = 0; bool overflow = false;
+        {
+            const int start = warp * RUN, end = min(nb, start + RUN);
+            uint16_t* const T = s_hash + warp * TABLE;
+            uint32_t* const reg = s_prov + warp * BGZL_REGION_WORDS;
+            __syncwarp();
+            if (start < end) {
+                if (warp > 0) {                                              // the 160 positions in front of the run: inserted, not looked up
+#pragma unroll 1
+                    for (int bs = start - WARM; bs < start; bs += 32) {
+                        const int p = bs + lane;
+                        const bool ins = p + MIN_MATCH <= nb;
+                        uint32_t lo, hi; lz_load6(s_in, p, lo, hi);
+                        const uint32_t h = lz_hash(lo, hi);
+                        if (ins) T[h] = (uint16_t)p;
+                        __syncwarp();
+                        bool again = ins && (int)T[h] < p;                   // of equal hashes the highest position stays
+                        while (__any_sync(0xffffffffu, again)) { if (again) T[h] = (uint16_t)p; __syncwarp(); again = ins && (int)T[h] < p; }
+                        __syncwarp();
+                    }
+                }
+                int cover = start;
+                // a step's look-ups are issued one step ahead: behind the previous step's inserts (the table state the specification asks for),
+                // in front of its selection and code assembly, whose shared-memory round trips they overlap
+                int p = start + lane;
+                bool active = p < end, hv = p + MIN_MATCH <= end;
+                uint32_t lo = 0, hi = 0;
+                if (active) lz_load6(s_in, p, lo, hi);
+                uint32_t h = lz_hash(lo, hi);
+                uint32_t c = hv ? (uint32_t)T[h] : 0xFFFFu;
+#pragma unroll 1
+                for (int bs = start; bs < end; bs += 32) {
+                    // inserts of this step: of equal hashes the highest position stays (store, read back, the larger ones store again)
+                    __syncwarp();
+                    if (hv) T[h] = (uint16_t)p;
+                    __syncwarp();
+                    {
+                        bool again = hv && (int)T[h] < p;
+                        while (__any_sync(0xffffffffu, again)) { if (again) T[h] = (uint16_t)p; __syncwarp(); again = hv && (int)T[h] < p; }
+                    }
+                    const int np = p + 32;
+                    const bool n_active = np < end, n_hv = np + MIN_MATCH <= end;
+                    uint32_t n_lo = 0, n_hi = 0;
+                    if (n_active) lz_load6(s_in, np, n_lo, n_hi);
+                    const uint32_t n_h = lz_hash(n_lo, n_hi);
+                    const uint32_t n_c = n_hv ? (uint32_t)T[n_h] : 0xFFFFu;
+                    if (cover < min(bs + 32, end)) {                         // (a step inside an earlier match emits nothing)
+                    bool m = false; int dist = 0;
+                    if (c != 0xFFFFu && p >= cover && p - (int)c <= 32768) {
+                        uint32_t clo, chi; lz_load6(s_in, (int)c, clo, chi);
+                        m = clo == lo && chi == hi; dist = p - (int)c;
+                    }
+                    bool is_lit = false, is_match = false; int mylen = 0;
+                    while (true) {
+                        const uint32_t mm = __ballot_sync(0xffffffffu, m && p >= cover);
+                        if (!mm) break;
+                        const int L = __ffs((int)mm) - 1, q = bs + L;
+                        const int d = __shfl_sync(0xffffffffu, dist, L);
+                        const int maxlen = min(MAX_MATCH, end - q);
+                        int len = maxlen;
+#pragma unroll 1
+                        for (int k0 = MIN_MATCH; k0 < maxlen; k0 += 32) {
+                            const int k = k0 + lane;
+                            const bool eq = k < maxlen && s_in[q + k] == s_in[q + k - d];
+                            const uint32_t ne = __ballot_sync(0xffffffffu, !eq);
+                            if (ne) { len = k0 + __ffs((int)ne) - 1; break; }
+                        }
+                        is_lit |= p >= cover && p < q;
+                        if (lane == L) { is_match = true; mylen = len; }
+                        cover = q + len;
+                    }
+                    is_lit |= active && p >= cover;
+                    // codes of this step
+                    unsigned long long tb = 0; uint32_t tn = 0;
+                    if (is_lit) {
+                        if (COUNT) atomicAdd(&s_hist[lo & 0xFFu], 1u);
+                        else { const uint32_t sy = s_sym[lo & 0xFFu]; tb = sy & 0xFFFFu; tn = sy >> 16; }
+                    } else if (is_match) {
+                        int ds, dnx; uint32_t dxv;
+                        dist_symbol(dist, 31 - __clz((dist - 1) | 1), &ds, &dnx, &dxv);
+                        if (COUNT) {
+                            int ls, lnx; uint32_t lxv;
+                            len_symbol(mylen, 31 - __clz(mylen - 3), &ls, &lnx, &lxv);
+                            atomicAdd(&s_hist[ls], 1u); atomicAdd(&s_hist[N_LITLEN + ds], 1u);
+                        } else {
+                            const uint32_t s1 = s_len[mylen - 3], s2 = s_sym[N_LITLEN + ds];      // length code with its extra bits | bits << 24
+                            const uint32_t n2 = s2 >> 16;
+                            tn = s1 >> 24;
+                            const uint32_t dbits = (s2 & 0xFFFFu) | (dxv << n2);                  // <= 28 bits
+                            tb = (unsigned long long)(s1 & 0xFFFFFFu) | ((unsigned long long)dbits << tn);
+                            tn += n2 + (uint32_t)dnx;
+                        }
+                    }
+                    if (!COUNT) {
+                        uint32_t inc = tn;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                        if (cursor + tot > (uint32_t)(REGION * 8)) { overflow = true; break; }       // (warp-uniform)
+                        if (tn) {
+                            const uint32_t pos = cursor + inc - tn, sh = pos & 31u;
+                            uint32_t* w = reg + (pos >> 5);
+                            const unsigned long long lo64 = tb << sh;
+                            atomicOr(w, (uint32_t)lo64);
+                            if (sh + tn > 32u) atomicOr(w + 1, (uint32_t)(lo64 >> 32));
+                            if (sh + tn > 64u) atomicOr(w + 2, (uint32_t)(tb >> (64u - sh)));
+                        }
+                        cursor += tot;
+                    }
+                    }
+                    p = np; active = n_active; hv = n_hv; lo = n_lo; hi = n_hi; h = n_h; c = n_c;
+                }
+            }
+        }
+        if (COUNT) {
+            if (tid == 0) atomicAdd(&s_hist[256], 1u);
+            __syncthreads();
+            v = v_next; cur ^= 1;
+            continue;
+        }
+        if (lane == 0) { s_scan[warp] = overflow ? 0x80000000u : cursor; s_scan[32 + warp] = crc; }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t raw = lane < 30 ? s_scan[lane] : 0u;
+            const uint32_t ovf = __ballot_sync(0xffffffffu, (raw & 0x80000000u) != 0u);
+            const uint32_t bits = raw & 0x7FFFFFFFu;
+            uint32_t wi = bits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            uint32_t c = lane < 30 ? s_scan[32 + lane] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+            const uint32_t data_bits = __shfl_sync(0xffffffffu, wi, 31);
+            // segment starts: S[0] = 0 (description), S[1 + w] = first bit of run w, S[31] = end-of-block code, S[32] = total
+            if (lane < 30) s_scan[64 + 1 + lane] = (uint32_t)P.hdr_nbits + wi - bits;
+            const uint32_t total_bits = (uint32_t)P.hdr_nbits + data_bits + (eob >> 16);
+            uint32_t payload = (total_bits + 7u) >> 3;
+            const bool stored = ovf != 0u || payload >= (uint32_t)nb + 5u;
+            if (stored) payload = (uint32_t)nb + 5u;
+            if (lane == 0) {
+                s_scan[64] = 0u; s_scan[64 + 31] = (uint32_t)P.hdr_nbits + data_bits; s_scan[64 + 32] = total_bits;
+                st_volatile_u64(P.state + b, ((b == 0 ? 2ull : 1ull) << 62) | (18ull + payload + 8ull));
+                s_scan[102] = payload; s_scan[103] = stored ? 1u : 0u; s_scan[104] = c;
+            }
+            // ---- the member's place in the output: decoupled look-back over the members before it
+            const unsigned long long Sz = 18ull + payload + 8ull;
+            unsigned long long gofs = 0;
+            if (b > 0) {
+                long long look = (long long)b - 1;
+                while (true) {
+                    const long long i = look - lane;
+                    unsigned long long lb = 2ull << 62;
+                    if (i >= 0) { do { lb = ld_volatile_u64(P.state + i); } while ((lb >> 62) == 0); }
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (lb >> 62) == 2ull);
+                    const int first_inc = incl ? (__ffs(incl) - 1) : 32;
+                    gofs += warp_sum_u64(lane <= first_inc ? (lb & 0x3FFFFFFFFFFFFFFFull) : 0ull);
+                    if (incl) break;
+                    look -= 32;
+                }
+                if (lane == 0) st_volatile_u64(P.state + b, (2ull << 62) | (gofs + Sz));
+            }
+            if (lane == 0) {
+                if (b == (uint64_t)P.n_blocks - 1) *P.total = gofs + Sz;
+                s_scan[105] = (uint32_t)gofs; s_scan[106] = (uint32_t)(gofs >> 32);
+            }
+        }
+        __syncthreads();
+        const uint32_t payload = s_scan[102]; const bool stored = s_scan[103] != 0; const uint32_t crc_all = s_scan[104];
+        const unsigned long long gofs = (unsigned long long)s_scan[105] | ((unsigned long long)s_scan[106] << 32);
+        if (gofs + 18ull + payload + 8ull <= P.out_cap) {
+            uint8_t* const dst = P.out + gofs;
+            if (tid < 18) {
+                const uint32_t bsize1 = 18u + payload + 8u - 1u;
+                const uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)(bsize1 & 0xFFu), (uint8_t)(bsize1 >> 8)};
+                dst[tid] = h[tid];
+            } else if (tid >= 32 && tid < 40) {
+                const int k = tid - 32;
+                dst[18 + payload + k] = (uint8_t)((k < 4 ? crc_all >> (8 * k) : (uint32_t)nb >> (8 * (k - 4))) & 0xFFu);
+            }
+            uint8_t* const pay = dst + 18;
+            if (!stored) {
+                // 16-byte stores at the output's own alignment: group g holds payload bytes [16g - A, 16g - A + 16), A = pay & 15
+                const uint32_t* const S = s_scan + 64;
+                const uint32_t A = (uint32_t)((uintptr_t)pay & 15u);
+                const uint32_t endb = A + payload;
+                int k = 0;
+                for (uint32_t g = tid; 16u * g < endb; g += BGZF_THREADS) {
+                    if (16u * g >= A && 16u * g + 16u <= endb) {
+                        const uint32_t t0 = 8u * (16u * g - A);
+                        uint4 o;
+                        o.x = lz_gather32(t0, k, S, s_tab, s_prov, s_scan); o.y = lz_gather32(t0 + 32u, k, S, s_tab, s_prov, s_scan);
+                        o.z = lz_gather32(t0 + 64u, k, S, s_tab, s_prov, s_scan); o.w = lz_gather32(t0 + 96u, k, S, s_tab, s_prov, s_scan);
+                        *(uint4*)(pay - A + 16u * g) = o;
+                    } else {
+                        for (uint32_t i = max(16u * g, A); i < min(16u * g + 16u, endb); i++) {
+                            int k2 = 0;
+                            pay[i - A] = (uint8_t)lz_gather32(8u * (i - A), k2, S, s_tab, s_prov, s_scan);
+                        }
+                    }
+                }
+            } else {
+                if (tid < 5) { const uint32_t L = (uint32_t)nb; const uint8_t sh[5] = {1, (uint8_t)(L & 0xFFu), (uint8_t)(L >> 8), (uint8_t)(~L & 0xFFu), (uint8_t)((~L >> 8) & 0xFFu)}; pay[tid] = sh[tid]; }
+                for (int k = tid; k < nb; k += BGZF_THREADS) pay[5 + k] = s_in[k];
+            }
+        } else if (tid == 0) atomicOr(P.total + 1, 1ull);
+        __syncthreads();
+        v = v_next; cur ^= 1;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (COUNT) {
+        __syncthreads();
+        for (int i = tid; i < N_SYM; i += BGZF_THREADS) if (s_hist[i]) atomicAdd(P.hist + i, (unsigned long long)s_hist[i]);
+    }
+}
+cudaError_t launch_bgzf_lz(const BgzfLzParams& P, bool count_only, int grid, cudaStream_t st) {
+    const size_t sm = 2 * (size_t)BGZF_BLOCK + BGZL_PROV_BYTES + (size_t)BGZL_TAB_WORDS * 4 + 30 * gglz::TABLE * 2 + BGZL_SCAN_WORDS * 4 + 256 * 4;
+    cudaError_t e = cudaFuncSetAttribute(count_only ? k_bgzf_lz<true> : k_bgzf_lz<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    if (count_only) k_bgzf_lz<true><<<grid, BGZF_THREADS, sm, st>>>(P); else k_bgzf_lz<false><<<grid, BGZF_THREADS, sm, st>>>(P);
+    return cudaGetLastError();
+}
+
 } // namespace ggk

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "gg_device.cuh"
+#include "gg_lz.h"
 
 namespace ggk {
 
@@ -131,6 +132,22 @@ struct BgzfParams {
     unsigned long long* state;           // look-back state per block
     unsigned int* ticket; unsigned long long* total;
 };
+// ---- device BGZF with LZ77 matches (k_bgzf_lz; parse specification in gg_lz.h): the default encoder ----
+// table layout (uint32): [0,316) literal/length + distance codes | [320,1344) CRC slicing-by-4 | [1344,2304) per-thread shift polynomials
+// | [2304,2321) x^(8*2^k) | [2324, 2324+BGZL_HDR_WORDS) header bits
+constexpr int BGZL_HDR_WORDS = 64;       // room for the description of both codes (<= 2048 bits)
+constexpr int BGZL_TAB_SYM = 0, BGZL_TAB_CRC = 320, BGZL_TAB_SHIFT = 1344, BGZL_TAB_X8 = 2304, BGZL_TAB_HDR = 2324, BGZL_TAB_WORDS = BGZL_TAB_HDR + BGZL_HDR_WORDS;
+struct BgzfLzParams {
+    const uint8_t* in; uint64_t n;       // plain stream (16-byte aligned)
+    uint8_t* out; uint64_t out_cap;      // BGZF members, back to back (16-byte aligned)
+    const uint32_t* tab; int hdr_nbits;
+    uint32_t n_blocks;                   // members to visit (counting pass: the sampled ones, member index = visit * stride)
+    uint32_t stride;
+    unsigned long long* state;           // look-back state per block
+    unsigned int* ticket; unsigned long long* total;
+    unsigned long long* hist;            // counting pass: 316 symbol counts
+};
+cudaError_t launch_bgzf_lz(const BgzfLzParams& P, bool count_only, int grid, cudaStream_t st);
 cudaError_t launch_byte_hist(const uint8_t* in, uint64_t n, uint64_t group_stride, unsigned long long* hist, cudaStream_t st);
 cudaError_t bgzf_prepare(size_t* smem_bytes);
 cudaError_t launch_bgzf_deflate(const BgzfParams& P, int grid, cudaStream_t st);

@@ -507,6 +507,48 @@ def test_device_bgzf_incompressible_and_binary(oracle_mod):
     g.close()
 
 
+def test_device_bgzf_equals_host_model(oracle_mod, genomes):
+    """k_bgzf_lz against ggh::bgzf_lz_model (gg_lz.h): the same parse, the same code, the same members byte for byte -- simulator
+    dialects, multi-member streams with a partial last member, runs shorter than a match, streams that fall back to stored blocks."""
+    import gzip
+    rng = np.random.default_rng(11)
+    g, o, ids = _pair(oracle_mod, genomes)
+    plan = util.plan3(ids, counts=(1500, 1000, 1200))
+    g.set_plan(plan); o.set_plan(plan)
+    streams = [o.run_fused(0, 3700, emit)[0] for emit in (api.EMIT_FRAG, api.EMIT_ARTP, api.EMIT_STDOUT4)]
+    artp = util.read_like_stream(rng, 9000, "artp")                          # ~1.7 MB: 26 members, every 1st sampled
+    streams += [artp, util.read_like_stream(rng, 2500, "frag"), artp[:65280], artp[:65281], artp[:2176 * 3 + 5], artp[:7], artp[:2181],
+                bytes(range(256)) * 600, rng.integers(0, 256, size=200_000, dtype=np.uint8).tobytes(), b"A" * 70000, b"ACGT\n" * 13057 + b"x",
+                b"G", b"ACGTAC" * 2, bytes(70000), artp[:40000] + rng.integers(0, 256, size=70_000, dtype=np.uint8).tobytes() + artp[:50000]]
+    for k, data in enumerate(streams):
+        z, zi = g.bgzf(data)
+        want, _ = util.bgzf_lz_model(data, eof=False)
+        assert gzip.decompress(z + api.BGZF_EOF) == data, "stream %d does not inflate" % k
+        util.assert_same(z, want, "stream %d: device members vs host model" % k)
+        assert zi.in_bytes == len(data) and zi.bytes == len(z)
+    big = util.read_like_stream(rng, 60_000, "artp")                          # ~11 MB: 170 members, every 2nd sampled, more members than SMs
+    z, _ = g.bgzf(big)
+    util.assert_same(z, util.bgzf_lz_model(big, eof=False)[0], "170 members")
+    g.close(); o.close()
+
+
+def test_device_bgzf_huffman_only_mode(oracle_mod, genomes, monkeypatch):
+    """GG_BGZF_MODE=huff keeps the Huffman-only encoder (k_bgzf_deflate) reachable: same framing, larger members."""
+    import gzip
+    g, o, ids = _pair(oracle_mod, genomes)
+    plan = util.plan3(ids, counts=(1000, 700, 800))
+    g.set_plan(plan); o.set_plan(plan)
+    want = o.run_fused(0, 2500, api.EMIT_ARTP)[0]
+    z_lz = g.run_fused_bgzf(0, 2500, api.EMIT_ARTP)[0]
+    monkeypatch.setenv("GG_BGZF_MODE", "huff")
+    z_h = g.run_fused_bgzf(0, 2500, api.EMIT_ARTP)[0]
+    monkeypatch.delenv("GG_BGZF_MODE")
+    assert gzip.decompress(z_h + api.BGZF_EOF) == want and gzip.decompress(z_lz + api.BGZF_EOF) == want
+    assert len(z_lz) < 0.85 * len(z_h)
+    _bgzf_members(z_h); _bgzf_members(z_lz)
+    g.close(); o.close()
+
+
 def test_fused_bgzf_to_host_chunked(oracle_mod, genomes):
     """gg_run_fused_bgzf_to_host: chunk boundaries and the reused Huffman code leave the inflated stream untouched."""
     import ctypes as C

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from gargammel_b200 import api
-from tests import synth
+from tests import synth, util
 from oracle import parsers
 from tests.conftest import ROOT
 
@@ -326,3 +326,37 @@ def test_bam_writer_and_reader_round_trip(tmp_path):
     assert out.raw[:n.value] == data
     open(str(tmp_path / "bad.bam"), "wb").write(b"not a bam")
     assert lib.ggh_bam_to_fasta(str(tmp_path / "bad.bam").encode(), out, C.c_size_t(len(out)), C.byref(n), err, 256) != 0
+
+
+def test_bgzf_lz_host_model():
+    """ggh::bgzf_lz_model, the host model that pins the device BGZF encoder with LZ77 matches (gg_lz.h): the members inflate under zlib
+    (CRC-32 and ISIZE checked) for read-like streams and for streams the code was not built for; the files are about the size of zlib -1's
+    (fragSim records within 2 %, -artp smaller); member framing is BGZF; incompressible members are stored."""
+    import gzip
+    lib = api.load_library()
+    rng = np.random.default_rng(5)
+
+    def zlib_bgzf(data, level):
+        out = C.create_string_buffer(len(data) + len(data) // 100 + 70000); m = C.c_size_t()
+        assert lib.ggh_bgzf_compress(data, C.c_size_t(len(data)), 2, level, 1, out, C.c_size_t(len(out)), C.byref(m)) == 0
+        return m.value
+    for dialect in ("frag", "artp"):
+        data = util.read_like_stream(rng, 6000, dialect)
+        z, hist = util.bgzf_lz_model(data)
+        assert gzip.decompress(z) == data
+        assert len(z) <= (1.02 if dialect == "frag" else 1.0) * zlib_bgzf(data, 1), (dialect, len(z), zlib_bgzf(data, 1))    # frag: within 2 %; -artp: smaller
+        assert sum(hist[257:286]) == sum(hist[286:]) > 0 and hist[256] == min(96, (len(data) + 65279) // 65280)      # one distance per length; sampled members
+        p, sizes = 0, []
+        while p < len(z):
+            assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 12:p + 14] == b"BC"
+            sizes.append((z[p + 16] | (z[p + 17] << 8)) + 1); p += sizes[-1]
+        assert p == len(z) and len(sizes) == (len(data) + 65279) // 65280 + 1 and max(sizes) <= 65536
+    artp = util.read_like_stream(rng, 3000, "artp")
+    assert len(util.bgzf_lz_model(artp)[0]) < 0.33 * len(artp)                       # the forward / reverse overlap is found: ~2.5 bits per byte (Huffman alone: 3.1)
+    for data in (bytes(range(256)) * 600, rng.integers(0, 256, size=200_000, dtype=np.uint8).tobytes(), b"A" * 70000, b"ACGT\n" * 13057 + b"x",
+                 b"", b"G", b"ACGTACGTA", b"ACGTAC" * 2, bytes(70000), artp[:65280], artp[:65281], artp[:2176 * 3 + 5]):
+        z, _ = util.bgzf_lz_model(data)
+        assert gzip.decompress(z) == data
+    z, _ = util.bgzf_lz_model(rng.integers(0, 256, size=65280 * 2, dtype=np.uint8).tobytes())
+    assert len(z) == 2 * (18 + 5 + 65280 + 8) + 28                                    # random bytes: stored blocks
+    assert len(util.bgzf_lz_model(b"A" * 65280)[0]) < 600                             # a run of one letter: distance-1 matches of 258

@@ -164,3 +164,34 @@ def read_bam(path):
             e = b.index(b"\0", q); tags[tag] = b[q:e].decode(); q = e + 1
         recs.append((name, flag, seq, qual, tags))
     return text, recs
+
+
+def bgzf_lz_model(data: bytes, eof=True):
+    """Host model of the device BGZF encoder with LZ77 matches (ggh::bgzf_lz_model, parse specification gg_lz.h):
+    (members [+ EOF marker], the 316 sampled symbol counts)."""
+    import ctypes as C
+    lib = api.load_library()
+    out = C.create_string_buffer(len(data) + len(data) // 100 + 70000)
+    m = C.c_size_t(); hist = (C.c_uint64 * 316)()
+    rc = lib.ggh_bgzf_lz_model(data, C.c_size_t(len(data)), 1 if eof else 0, out, C.c_size_t(len(out)), C.byref(m), hist)
+    assert rc == 0, rc
+    return out.raw[:m.value], list(hist)
+
+
+def read_like_stream(rng, n_rec, dialect="artp", read_len=75):
+    """FASTA records shaped like the simulator's output (random bases: nothing repeats but what the record structure repeats)."""
+    from tests import synth
+    ad_f, ad_s = api.DEFAULT_ADAPTER_F.encode(), api.DEFAULT_ADAPTER_S.encode()
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    out = []
+    for i in range(n_rec):
+        L = int(rng.integers(30, 140)); st = int(rng.integers(1, 50_000_000))
+        frag = synth._BASES[rng.integers(0, 4, L)].tobytes()
+        hdr = b">chr%d:%s:%d:%d:%de1_0" % (rng.integers(1, 23), b"+-"[i & 1:(i & 1) + 1], st, st + L, L)
+        if dialect == "frag":
+            out.append(hdr + b"\n" + frag + b"\n"); continue
+        pad = synth._BASES[rng.integers(0, 4, 2 * read_len)].tobytes()
+        fwd = (frag + ad_f + pad)[:read_len]
+        rev = (frag.translate(comp)[::-1] + ad_s + pad[::-1])[:read_len]
+        out.append(hdr + b"\n" + fwd + rev.translate(comp)[::-1] + b"\n")
+    return b"".join(out)
