@@ -633,43 +633,53 @@ def main():
             except Exception as ex:
                 e2e["with_bgzf"] = {"value": None, "error": repr(ex)}
         # ---- ... and with the BGZF members produced ON THE DEVICE (gg_bgzf_dev), so that only the compressed members cross PCIe.
-        # One piece of one step is inflated on the host afterwards and compared with the plain stream.
-        try:
-            zcap = cap
-            zhost = torch.empty(zcap, dtype=torch.uint8, pin_memory=True)
+        # One piece of one step is inflated on the host afterwards and compared with the plain stream.  Both device encoders are measured:
+        # the default one with LZ77 matches (k_bgzf_lz: files of zlib -1's size) and the Huffman-only one (GG_BGZF_MODE=huff: k_bgzf_deflate,
+        # a fifth of the kernel time, files 30-40 % larger).
+        zhost = None
+        for key, mode in (("with_device_bgzf", None), ("with_device_bgzf_huffman", "huff")):
+            try:
+                if mode:
+                    os.environ["GG_BGZF_MODE"] = mode
+                zcap = cap
+                if zhost is None:
+                    zhost = torch.empty(zcap, dtype=torch.uint8, pin_memory=True)
 
-            def e2e_step_z():
-                upload_inputs()
-                zb = ib = 0; zi = None
-                for a in range(first, last, sup):
-                    zi = ctx.run_fused_bgzf_to_host(a, min(sup, last - a), emit, zhost.data_ptr(), zcap, args.bgzf_chunk)
-                    zb += zi.bytes; ib += zi.in_bytes
-                return zb, ib, zi
-            e2e_step_z()
-            barrier()
-            td0 = time.perf_counter()
-            for _ in range(e_steps):
-                zb, ib, zi = e2e_step_z()
-            barrier()
-            td = shard.max_over_ranks(time.perf_counter() - td0, device="cuda")
-            e2e["with_device_bgzf"] = {"value": count * world * e_steps / td, "unit": "fragments/s", "steps": e_steps, "d2h_bytes_per_step": int(zb),
-                                       "uncompressed_bytes_per_step": int(ib), "chunk_fragments": args.bgzf_chunk,
-                                       "what": "per step: genome uploads + gg_run_fused_bgzf_to_host (fused kernel + device BGZF per chunk, D2H of the members overlapped with the next chunk)"}
-            if rank == 0:
-                import zlib
-                a_last = first + ((count - 1) // sup) * sup                 # the piece both buffers hold at this point
-                ctx.run_fused_to_host(a_last, min(sup, last - a_last), emit, host_out.data_ptr(), cap, args.e2e_chunk)
-                zbv = zhost[:int(zi.bytes)].numpy(); plain = host_out.numpy()
-                off, pos, okz = 0, 0, True
-                while off < len(zbv) and pos < (32 << 20):                  # the first 32 MB of members (zlib verifies CRC-32 and ISIZE of each)
-                    bsize = int(zbv[off + 16]) + (int(zbv[off + 17]) << 8) + 1
-                    part = zlib.decompress(zbv[off:off + bsize].tobytes(), wbits=31)
-                    okz = okz and part == plain[pos:pos + len(part)].tobytes()
-                    off += bsize; pos += len(part)
-                e2e["with_device_bgzf"]["verified_bytes"] = pos
-                assert okz, "device BGZF does not inflate to the plain stream"
-        except Exception as ex:
-            e2e["with_device_bgzf"] = {"value": None, "error": repr(ex)}
+                def e2e_step_z():
+                    upload_inputs()
+                    zb = ib = 0; zi = None
+                    for a in range(first, last, sup):
+                        zi = ctx.run_fused_bgzf_to_host(a, min(sup, last - a), emit, zhost.data_ptr(), zcap, args.bgzf_chunk)
+                        zb += zi.bytes; ib += zi.in_bytes
+                    return zb, ib, zi
+                e2e_step_z()
+                barrier()
+                td0 = time.perf_counter()
+                for _ in range(e_steps):
+                    zb, ib, zi = e2e_step_z()
+                barrier()
+                td = shard.max_over_ranks(time.perf_counter() - td0, device="cuda")
+                e2e[key] = {"value": count * world * e_steps / td, "unit": "fragments/s", "steps": e_steps, "d2h_bytes_per_step": int(zb),
+                            "uncompressed_bytes_per_step": int(ib), "bits_per_byte": 8.0 * zb / max(ib, 1), "chunk_fragments": args.bgzf_chunk,
+                            "encoder": "k_bgzf_deflate (Huffman only, GG_BGZF_MODE=huff)" if mode else "k_bgzf_lz (LZ77 matches + Huffman; the default)",
+                            "what": "per step: genome uploads + gg_run_fused_bgzf_to_host (fused kernel + device BGZF per chunk, D2H of the members overlapped with the next chunk)"}
+                if rank == 0:
+                    import zlib
+                    a_last = first + ((count - 1) // sup) * sup                 # the piece both buffers hold at this point
+                    ctx.run_fused_to_host(a_last, min(sup, last - a_last), emit, host_out.data_ptr(), cap, args.e2e_chunk)
+                    zbv = zhost[:int(zi.bytes)].numpy(); plain = host_out.numpy()
+                    off, pos, okz = 0, 0, True
+                    while off < len(zbv) and pos < (32 << 20):                  # the first 32 MB of members (zlib verifies CRC-32 and ISIZE of each)
+                        bsize = int(zbv[off + 16]) + (int(zbv[off + 17]) << 8) + 1
+                        part = zlib.decompress(zbv[off:off + bsize].tobytes(), wbits=31)
+                        okz = okz and part == plain[pos:pos + len(part)].tobytes()
+                        off += bsize; pos += len(part)
+                    e2e[key]["verified_bytes"] = pos
+                    assert okz, "device BGZF does not inflate to the plain stream"
+            except Exception as ex:
+                e2e[key] = {"value": None, "error": repr(ex)}
+            finally:
+                os.environ.pop("GG_BGZF_MODE", None)
         head = bytes(host_out[:64].numpy().tobytes())
         assert head.startswith(b">"), head
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run on the GPU box (via gpurun): tests, bench (+ the reference arm), then the ncu launch list and one full capture each of
-# k_fused (C2), k_deam_stream (C1 at 16 M records) and k_bgzf_deflate.  usage: bash scripts/gpu_bench_profile.sh <tag> [notests]
+# k_fused (C2), k_deam_stream (C1 at 16 M records) and k_bgzf_lz.  usage: bash scripts/gpu_bench_profile.sh <tag> [notests]
 TAG=${1:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${TAG}_gpu.csv
@@ -24,7 +24,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
 $C1 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_deam_stream -s 3 -c 1 -o gpurun_out/${TAG}_deam $C1 > gpurun_out/${TAG}_ncu_deam.log 2>&1
 
-# device BGZF kernel: plain run, then one full capture (second launch: warm)
+# device BGZF encoder (k_bgzf_lz<false>; launches alternate counting pass / encoder): plain run of both encoders, then one full capture (fourth launch: the encoder, warm)
+GG_BGZF_MODE=huff python scripts/bgzf_probe.py > gpurun_out/${TAG}_bgzf_probe_huff.log 2>&1
 python scripts/bgzf_probe.py > gpurun_out/${TAG}_bgzf_probe.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_bgzf_deflate -s 1 -c 1 -o gpurun_out/${TAG}_bgzf python scripts/bgzf_probe.py > gpurun_out/${TAG}_ncu_bgzf.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_bgzf_lz -s 3 -c 1 -o gpurun_out/${TAG}_bgzf python scripts/bgzf_probe.py > gpurun_out/${TAG}_ncu_bgzf.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}_

@@ -6,6 +6,7 @@ cp $G/${TAG}_bench.json $G/${TAG}_bench_ref.json $G/${TAG}_launches.csv $G/${TAG
 [ -f $G/${TAG}_c1_16m.json ] && cp $G/${TAG}_c1_16m.json $G/${TAG}_c1_launches.csv $P/
 [ -f $G/${TAG}_pytest.log ] && tail -5 $G/${TAG}_pytest.log > $P/${TAG}_pytest_tail.txt
 [ -f $G/${TAG}_smoke.log ] && tail -1 $G/${TAG}_smoke.log >> $P/${TAG}_pytest_tail.txt
+[ -f $G/${TAG}_bgzf_probe.log ] && cat $G/${TAG}_bgzf_probe.log > $P/${TAG}_bgzf_probe.txt && [ -f $G/${TAG}_bgzf_probe_huff.log ] && (echo '-- GG_BGZF_MODE=huff (k_bgzf_deflate)'; cat $G/${TAG}_bgzf_probe_huff.log) >> $P/${TAG}_bgzf_probe.txt
 [ -f $G/${TAG}_configs.jsonl ] && grep "^{" $G/${TAG}_configs.jsonl > $P/${TAG}_configs.jsonl
 python scripts/ncu_lines.py $G/${TAG}_fused.ncu-rep 60 > $P/${TAG}_fused_ncu_summary.txt
 python scripts/ncu_passes.py $G/${TAG}_fused.ncu-rep > $P/${TAG}_fused_ncu_passes.txt
@@ -32,7 +33,7 @@ f["fragments_per_launch"] = 10000000
 f["source"] = "ncu --set full --clock-control none, profiles/${TAG}_fused_ncu_summary.txt"
 f["command"] = "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 json.dump(f, open("$P/fused_traffic.json", "w"), indent=1)
-b = traffic("$G/${TAG}_bgzf.ncu-rep"); b["kernel"] = "k_bgzf_deflate"; b["dram_bytes_per_launch"] = b["dram_bytes_read"] + b["dram_bytes_write"]; b["input_bytes_per_launch"] = 1819477288
+b = traffic("$G/${TAG}_bgzf.ncu-rep"); b["kernel"] = "k_bgzf_lz"; b["dram_bytes_per_launch"] = b["dram_bytes_read"] + b["dram_bytes_write"]; b["input_bytes_per_launch"] = 1819477288
 b["command"] = "python scripts/bgzf_probe.py"
 json.dump(b, open("$P/bgzf_traffic.json", "w"), indent=1)
 print(f); print(b)
