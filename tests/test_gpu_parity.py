@@ -526,6 +526,14 @@ def test_device_bgzf_equals_host_model(oracle_mod, genomes):
         assert gzip.decompress(z + api.BGZF_EOF) == data, "stream %d does not inflate" % k
         util.assert_same(z, want, "stream %d: device members vs host model" % k)
         assert zi.in_bytes == len(data) and zi.bytes == len(z)
+    for k in range(24):                                                       # random phrase soups: alphabets of 2..256 letters, phrases of 1..300 bytes, odd lengths
+        alpha = rng.integers(0, 256, size=int(rng.integers(2, 257)), dtype=np.uint8)
+        phrases = [alpha[rng.integers(0, len(alpha), size=int(rng.integers(1, 301)))].tobytes() for _ in range(int(rng.integers(1, 40)))]
+        n = int(rng.integers(1, 400_000))
+        data = b"".join(phrases[int(i)] for i in rng.integers(0, len(phrases), size=n // 20 + 1))[:n]
+        z, _ = g.bgzf(data)
+        assert gzip.decompress(z + api.BGZF_EOF) == data, "soup %d does not inflate" % k
+        util.assert_same(z, util.bgzf_lz_model(data, eof=False)[0], "soup %d: device members vs host model" % k)
     big = util.read_like_stream(rng, 60_000, "artp")                          # ~11 MB: 170 members, every 2nd sampled, more members than SMs
     z, _ = g.bgzf(big)
     util.assert_same(z, util.bgzf_lz_model(big, eof=False)[0], "170 members")
