@@ -650,12 +650,14 @@ def main():
                 if zhost is None:
                     zhost = torch.empty(zcap, dtype=torch.uint8, pin_memory=True)
 
+                zms = [0.0]
+
                 def e2e_step_z():
                     upload_inputs()
-                    zb = ib = 0; zi = None
+                    zb = ib = 0; zi = None; zms[0] = 0.0
                     for a in range(first, last, sup):
                         zi = ctx.run_fused_bgzf_to_host(a, min(sup, last - a), emit, zhost.data_ptr(), zcap, args.bgzf_chunk)
-                        zb += zi.bytes; ib += zi.in_bytes
+                        zb += zi.bytes; ib += zi.in_bytes; zms[0] += zi.device_ms
                     return zb, ib, zi
                 e2e_step_z()
                 barrier()
@@ -666,6 +668,7 @@ def main():
                 td = shard.max_over_ranks(time.perf_counter() - td0, device="cuda")
                 e2e[key] = {"value": count * world * e_steps / td, "unit": "fragments/s", "steps": e_steps, "d2h_bytes_per_step": int(zb),
                             "uncompressed_bytes_per_step": int(ib), "bits_per_byte": 8.0 * zb / max(ib, 1), "chunk_fragments": args.bgzf_chunk,
+                            "kernel_ms_per_step": zms[0], "wall_ms_per_step": 1000.0 * td / e_steps,
                             "encoder": "k_bgzf_deflate (Huffman only, GG_BGZF_MODE=huff)" if mode else "k_bgzf_lz (LZ77 matches + Huffman; the default)",
                             "what": "per step: genome uploads + gg_run_fused_bgzf_to_host (fused kernel + device BGZF per chunk, D2H of the members overlapped with the next chunk)"}
                 if rank == 0:
