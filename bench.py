@@ -425,21 +425,27 @@ def run_reference_arm(args, rank, world):
 
 
 # --------------------------------------------------------------------------- the reference's driver, for real (C2, N=1)
-def via_gargammel_pl(J, n, bins, label):
+def via_gargammel_pl(J, n, bins, label, fused=False):
     """perl gargammel.pl (the unmodified script, oracle/_ref) over `bins` = {fragSim,deamSim,adptSim} on the job's directory, n fragments:
     what a user of the reference actually runs (process launches, gzip hops and, for our binaries, one CUDA context per process included).
-    art_illumina is replaced by a no-op stub writing empty FASTQ files."""
+    art_illumina is replaced by a no-op stub writing empty FASTQ files.
+    fused=True: the same job, same directory, same options and the same art stub through bin/gargammel-b200 (one process, the
+    intermediates compressed on the device) -- what a user who switches drivers runs instead of the script."""
     pl = os.path.join(ROOT, "oracle", "_ref", "gargammel.pl")
-    if not os.path.exists(pl) or shutil.which("perl") is None or not all(os.path.exists(os.path.join(bins, b)) for b in ("fragSim", "deamSim", "adptSim")):
+    if fused:
+        if not os.path.exists(os.path.join(bins, "gargammel-b200")):
+            return None
+    elif not os.path.exists(pl) or shutil.which("perl") is None or not all(os.path.exists(os.path.join(bins, b)) for b in ("fragSim", "deamSim", "adptSim")):
         return None
     from tests import synth
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     t = tempfile.mkdtemp(prefix="gg_pl_", dir=base)
     try:
         gg = os.path.join(t, "gg"); os.makedirs(os.path.join(gg, "src")); os.makedirs(os.path.join(gg, "art_src_MountRainier"))
-        shutil.copy(pl, os.path.join(gg, "gargammel.pl"))
-        for b in ("fragSim", "deamSim", "adptSim"):
-            os.symlink(os.path.join(bins, b), os.path.join(gg, "src", b))
+        if not fused:
+            shutil.copy(pl, os.path.join(gg, "gargammel.pl"))
+            for b in ("fragSim", "deamSim", "adptSim"):
+                os.symlink(os.path.join(bins, b), os.path.join(gg, "src", b))
         art = os.path.join(gg, "art_src_MountRainier", "art_illumina")
         with open(art, "w") as fh:
             fh.write("#!/bin/sh\nwhile [ $# -gt 0 ]; do if [ \"$1\" = \"-o\" ]; then O=$2; fi; shift; done\n: > ${O}1.fq; : > ${O}2.fq\n")
@@ -456,15 +462,19 @@ def via_gargammel_pl(J, n, bins, label):
         s5, s3 = synth.golden_matrix("single-")
         synth.write_matrix_dat(os.path.join(t, "m-"), s5, s3)
         os.makedirs(os.path.join(t, "out"))
-        cmd = ["perl", os.path.join(gg, "gargammel.pl"), "--comp", "%g,%g,%g" % J["comp"], "-n", str(n), "-f", os.path.join(t, "sf.size"), "-matfile", os.path.join(t, "m-"),
-               "-rl", str(J["read_len"]), "-o", os.path.join(t, "out", "sim"), d + "/"]
+        opts = ["--comp", "%g,%g,%g" % J["comp"], "-n", str(n), "-f", os.path.join(t, "sf.size"), "-matfile", os.path.join(t, "m-"),
+                "-rl", str(J["read_len"]), "-o", os.path.join(t, "out", "sim")]
+        cmd = ([os.path.join(bins, "gargammel-b200"), "--keep", "--art", art] if fused else ["perl", os.path.join(gg, "gargammel.pl")]) + opts + [d + "/"]
         t0 = time.perf_counter()
         r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
         dt = time.perf_counter() - t0
         if r.returncode != 0:
             return {"value": None, "error": r.stderr[-300:]}
+        out_files = sorted(os.path.basename(f) for f in os.listdir(os.path.join(t, "out")))
+        if fused:
+            return {"value": n / dt, "unit": "fragments/s", "seconds": dt, "fragments": n, "processes": 1, "files": out_files, "binaries": label}
         nproc = sum(1 for l in r.stderr.splitlines() if l.startswith("running cmd ") and "/src/" in l)
-        return {"value": n / dt, "unit": "fragments/s", "seconds": dt, "fragments": n, "filter_processes": nproc, "binaries": label}
+        return {"value": n / dt, "unit": "fragments/s", "seconds": dt, "fragments": n, "filter_processes": nproc, "files": out_files, "binaries": label}
     finally:
         shutil.rmtree(t, ignore_errors=True)
 
@@ -485,6 +495,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-perl", action="store_true", help="skip cpu_baseline.via_gargammel_pl")
+    ap.add_argument("--perl-10x", action="store_true", help="also time gargammel.pl over bin/ at ten times the fragments (about a minute and a half)")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="fragments per chunk of the plain e2e path")
     ap.add_argument("--bgzf-chunk", type=int, default=1 << 19, help="fragments per chunk of the device-BGZF e2e pipeline")
     args = ap.parse_args()
@@ -751,9 +762,15 @@ def main():
                 line["cpu_baseline"]["via_gargammel_pl"] = {
                     "reference_binaries": via_gargammel_pl(J, 200000, os.path.join(ROOT, "oracle", "_ref", "src"), "oracle/_ref/src (reference sources + our shim), single-threaded filters"),
                     "dropin_binaries": via_gargammel_pl(J, 200000, os.path.join(ROOT, "bin"), "bin/ (this repository): one CUDA context (about a second) per filter process"),
-                    "dropin_binaries_10x": via_gargammel_pl(J, 2000000, os.path.join(ROOT, "bin"), "bin/ (this repository), ten times the fragments: the per-process cost is fixed"),
+                    "fused_driver": via_gargammel_pl(J, 200000, os.path.join(ROOT, "bin"), "bin/gargammel-b200 (this repository): one process, one CUDA context, .gz intermediates made on the device", fused=True),
+                    "fused_driver_10x": via_gargammel_pl(J, 2000000, os.path.join(ROOT, "bin"), "bin/gargammel-b200, ten times the fragments", fused=True),
+                    "fused_driver_50x": via_gargammel_pl(J, 10000000, os.path.join(ROOT, "bin"), "bin/gargammel-b200, fifty times the fragments", fused=True),
                     "what": "perl gargammel.pl --comp 0,0.08,0.92 -n 200000 -f sizefreq -matfile single- -rl 75 (unmodified script, art_illumina stubbed, the script's own gzip hops included); "
-                            "the fused driver bin/gargammel-b200 replaces the script's middle with one process"}
+                            "fused_driver*: the same directory, options and art stub through bin/gargammel-b200 --keep, which replaces the script's middle with one process "
+                            "(the script's file set: intermediates .{e,b,c}.fa.gz and _d.fa.gz, _a.fa.gz, _s1/_s2.fq.gz; wall clock from exec to exit, genome loading "
+                            "and all output files on tmpfs included)"}
+                if args.perl_10x:       # 94 s on the round-2 box (21 k fragments/s: the script's gzip -6 hops and Perl loops, not the filters, set the pace)
+                    line["cpu_baseline"]["via_gargammel_pl"]["dropin_binaries_10x"] = via_gargammel_pl(J, 2000000, os.path.join(ROOT, "bin"), "bin/ (this repository), ten times the fragments: the per-process cost is fixed")
         except Exception as ex:      # the baseline is a reported figure; never let it kill the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "fragments/s", "cores": host_cores(), "kind": "port", "sample": "failed: %r" % (ex,)}
     print(json.dumps(line), flush=True)

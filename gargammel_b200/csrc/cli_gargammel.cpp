@@ -38,6 +38,28 @@ static bool run_cmd(const std::string& cmd, bool mock) {
     if (rc != 0) { std::cerr << "system  cmd " << cmd << " failed: " << rc << std::endl; return false; }
     return true;
 }
+// The `gzip -f FILE` steps that end gargammel.pl (:1871-1889), in this process: FILE is deflated block-wise on every host thread
+// (BGZF members at gzip's default level 6: zcat / gzstream / htslib read it like any .gz) into FILE.gz and removed.  A single gzip
+// process takes minutes on the FASTQ files of a large run; the command is echoed like the others so that --mock shows the step.
+static bool gzip_file(const std::string& path, bool mock) {
+    std::cerr << "running cmd gzip -f " << path << "   (in this process: parallel BGZF members)" << std::endl;
+    if (mock) return true;
+    FILE* in = fopen(path.c_str(), "rb");
+    if (!in) { std::cerr << "gzip: cannot read " << path << std::endl; return false; }
+    const std::string gz = path + ".gz";
+    FILE* out = fopen(gz.c_str(), "wb");
+    if (!out) { fclose(in); std::cerr << "gzip: cannot write " << gz << std::endl; return false; }
+    const size_t B = 0xff00, piece = B * 1024;                                       // whole BGZF blocks per piece (about 64 MB)
+    std::vector<uint8_t> buf(piece), z; std::string e; bool ok = true; size_t got;
+    while (ok && (got = fread(buf.data(), 1, piece, in)) > 0)
+        ok = ggh::bgzf_compress(buf.data(), got, 0, 6, z, false, e) && fwrite(z.data(), 1, z.size(), out) == z.size();
+    ok = ok && !ferror(in) && ggh::bgzf_compress(NULL, 0, 1, 6, z, true, e) && fwrite(z.data(), 1, z.size(), out) == z.size();   // the EOF marker block
+    fclose(in);
+    ok = (fclose(out) == 0) && ok;
+    if (!ok) { std::cerr << "gzip: failed on " << path << (e.empty() ? "" : ": " + e) << std::endl; remove(gz.c_str()); return false; }
+    remove(path.c_str());
+    return true;
+}
 static bool is_exe(const std::string& p) { struct stat st; return !p.empty() && stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode) && access(p.c_str(), X_OK) == 0; }
 // art_illumina: --art PATH, else <dir of this binary>/../art_src_MountRainier/art_illumina (the reference's layout, gargammel.pl:239), else $PATH
 static std::string find_art(const std::string& given, const char* argv0) {
@@ -223,15 +245,20 @@ int main(int argc, char** argv) {
     const std::string art = no_art ? std::string() : find_art(art_given, argv[0]);
     const std::string cmd_art = art + " -ss " + ss + " -amp -na " + (se ? "    " : " -p ") + " -i " + prefix + "_a.fa  -l " + std::to_string(rl) + "  -c 1  -qs  " + std::to_string(qs) +
                                 "  -qs2 " + std::to_string(qs2) + "  -o " + prefix + "_s";
+    bool a_gz_on_device = false;                                    // set by the streaming path once <prefix>_a.fa.gz is complete
     auto post = [&]() -> int {
         if (art.empty()) {
             std::cerr << (no_art ? "--noart: " : "art_illumina not found (--art PATH): ") << "stopping after " << prefix << "_a.fa" << std::endl;
             return 0;
         }
-        if (!run_cmd(cmd_art, mock) || !run_cmd("gzip -f " + prefix + "_a.fa", mock)) return 1;
-        if (se) { if (!run_cmd("gzip -f " + prefix + "_s.fq", mock)) return 1; std::cerr << "Single-end reads available here: " << prefix << "_s.fq.gz" << std::endl; }
+        if (!run_cmd(cmd_art, mock)) return 1;
+        if (a_gz_on_device) {                                      // <prefix>_a.fa.gz is already there (members made on the GPU next to <prefix>_a.fa)
+            std::cerr << "running cmd gzip -f " << prefix << "_a.fa   (done on the device: removing the plain file)" << std::endl;
+            remove((prefix + "_a.fa").c_str());
+        } else if (!gzip_file(prefix + "_a.fa", mock)) return 1;
+        if (se) { if (!gzip_file(prefix + "_s.fq", mock)) return 1; std::cerr << "Single-end reads available here: " << prefix << "_s.fq.gz" << std::endl; }
         else {
-            if (!run_cmd("gzip -f " + prefix + "_s1.fq", mock) || !run_cmd("gzip -f " + prefix + "_s2.fq", mock)) return 1;
+            if (!gzip_file(prefix + "_s1.fq", mock) || !gzip_file(prefix + "_s2.fq", mock)) return 1;
             std::cerr << "Paired-end forward reads available here: " << prefix << "_s1.fq.gz" << std::endl << "Paired-end reverse reads available here: " << prefix << "_s2.fq.gz" << std::endl;
         }
         std::cerr << "Program finished successfully" << std::endl;
@@ -285,7 +312,8 @@ int main(int argc, char** argv) {
     // overlapped with the kernels and the .gz outputs compressed on the device; nothing is held in host memory.  With several GPUs
     // the ranks write <file>.part<r>, concatenated in rank order afterwards (BGZF members are independent).
     const bool streaming = !uniq;
-    const char* gz_names[4] = {"_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz"};
+    const bool a_gz = streaming && !art.empty() && !getenv("GG_HOST_GZIP_A");      // ART will run: <prefix>_a.fa.gz comes from the device too
+    const char* gz_names[5] = {"_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz", "_a.fa.gz"};
     auto part_name = [&](const std::string& final_name, int r) { return gpus == 1 ? final_name : final_name + ".part" + std::to_string(r); };
     auto stream_worker = [&](int r) {
         gg_ctx* ctx = NULL;
@@ -302,6 +330,12 @@ int main(int argc, char** argv) {
         for (uint64_t x = lo; x < hi; x += chunk)
             if (!a.write_run(ctx, x, std::min<uint64_t>(chunk, hi - x), emit, pin, cap)) return bail(std::string("fused kernel / write: ") + gg_last_error(ctx));
         if (!a.close()) return bail("Error: write failed");
+        if (a_gz) {                                                // what `gzip -f <prefix>_a.fa` leaves behind after ART (gargammel.pl:1871): made here, on the device
+            Sink z; if (!z.open_gz(part_name(prefix + "_a.fa.gz", r))) return bail("Cannot write to file " + prefix + "_a.fa.gz");
+            for (uint64_t x = lo; x < hi; x += chunk)
+                if (!z.write_run(ctx, x, std::min<uint64_t>(chunk, hi - x), emit, pin, cap)) return bail(std::string("fused kernel / write: ") + gg_last_error(ctx));
+            if (!z.close(gpus == 1)) return bail("Error: write failed");
+        }
         if (keep) {
             // <prefix>_d.fa.gz = deamSim output in e,b,c order; <prefix>.{e,b,c}.fa.gz = the fragSim outputs per source class
             Sink z[4];
@@ -344,7 +378,8 @@ int main(int argc, char** argv) {
     if (streaming) {
         if (gpus > 1) {                                            // concatenate the parts in rank order
             std::vector<char> buf(64u << 20);
-            for (int k = -1; k < (keep ? 4 : 0); k++) {
+            for (int k = -1; k < 5; k++) {
+                if (k >= 0 && (k == 4 ? !a_gz : !keep)) continue;
                 const std::string fin = prefix + (k < 0 ? "_a.fa" : gz_names[k]);
                 FILE* out = fopen(fin.c_str(), "wb"); if (!out) return die("Cannot write to file " + fin);
                 for (int r = 0; r < gpus; r++) {
@@ -358,6 +393,7 @@ int main(int argc, char** argv) {
             }
         }
         std::cerr << "Program " << argv[0] << " terminated succesfully, wrote " << total << " sequences to " << prefix << "_a.fa" << std::endl;
+        a_gz_on_device = a_gz;
         return post();
     }
     // -uniq: one defline counter per source file, exactly one fragSim invocation each in the reference
