@@ -402,7 +402,8 @@ int gg_ctx_destroy(gg_ctx* ctx) {
     DBuf* bufs[] = {&ctx->d_cum_end, &ctx->d_gbase, &ctx->d_clen, &ctx->d_name_off, &ctx->d_name_len, &ctx->d_names, &ctx->d_genomes,
                     &ctx->d_size_len, &ctx->d_size_thr, &ctx->d_adF2, &ctx->d_adS2, &ctx->d_rcS2, &ctx->d_adF, &ctx->d_adS, &ctx->d_ranges,
                     &ctx->d_tmp_fa, &ctx->d_tmp_desc, &ctx->d_out, &ctx->d_out2, &ctx->d_tile_state, &ctx->d_ticket_stats, &ctx->d_in, &ctx->d_nl, &ctx->d_scan, &ctx->d_sizes, &ctx->d_flush,
-                    &ctx->d_case, &ctx->d_cmask_ptrs, &ctx->d_chain_a, &ctx->d_chain_b};
+                    &ctx->d_case, &ctx->d_cmask_ptrs, &ctx->d_chain_a, &ctx->d_chain_b,
+                    &ctx->d_bgzf, &ctx->d_bgzf2, &ctx->d_bgzf_tab, &ctx->d_bgzf_state};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) bufs[i]->release();
     for (int s = 0; s < GG_MAX_COMP_SLOTS; s++) ctx->comp[s].d_tab.release();
     for (int s = 0; s < GG_MAX_GC_SLOTS; s++) ctx->gc[s].d_thr.release();
