@@ -383,6 +383,12 @@ def test_fused_driver_two_gpus_byte_identical(tmp_path):
     assert (tmp_path / "one_a.fa").read_bytes() == (tmp_path / "two_a.fa").read_bytes()
     for suffix in ("_d.fa.gz", ".e.fa.gz", ".b.fa.gz", ".c.fa.gz"):
         assert gzip.open(str(tmp_path / ("one" + suffix))).read() == gzip.open(str(tmp_path / ("two" + suffix))).read(), suffix
+    # with ART at hand every rank also makes its slice of <prefix>_a.fa.gz on the device; the parts are concatenated in rank order
+    art = tmp_path / "art_illumina"
+    art.write_text("#!/bin/sh\nexec python3 %s \"$@\"\n" % os.path.join(ROOT, "tests", "art_stub.py")); art.chmod(0o755)
+    _run_fused_driver(tmp_path, d, "art2", ["--art", str(art), "--gpus", "2"])
+    assert gzip.open(str(tmp_path / "art2_a.fa.gz")).read() == (tmp_path / "one_a.fa").read_bytes()
+    assert not os.path.exists(str(tmp_path / "art2_a.fa")) and not [f for f in os.listdir(str(tmp_path)) if ".part" in f]
 
 
 @pytest.mark.gpu
