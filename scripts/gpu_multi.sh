@@ -9,7 +9,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.
 python - <<'PY'
 import os, subprocess, sys, tempfile
 sys.path.insert(0, os.getcwd())
-from gargammel_b200 import synth
+from tests import synth
 d = tempfile.mkdtemp()
 for sub, names in (("endo", ["endo.1.fa"]), ("cont", ["cont.1.fa"]), ("bact", [])):
     os.makedirs(os.path.join(d, "in", sub))
