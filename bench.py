@@ -426,6 +426,14 @@ def run_reference_arm(args, rank, world):
 
 # --------------------------------------------------------------------------- the reference's driver, for real (C2, N=1)
 def via_gargammel_pl(J, n, bins, label, fused=False):
+    """_via_gargammel_pl, never raising: a leg that cannot run (no space on tmpfs, ...) reports its error instead of a number."""
+    try:
+        return _via_gargammel_pl(J, n, bins, label, fused)
+    except Exception as ex:
+        return {"value": None, "error": repr(ex)[-300:]}
+
+
+def _via_gargammel_pl(J, n, bins, label, fused=False):
     """perl gargammel.pl (the unmodified script, oracle/_ref) over `bins` = {fragSim,deamSim,adptSim} on the job's directory, n fragments:
     what a user of the reference actually runs (process launches, gzip hops and, for our binaries, one CUDA context per process included).
     art_illumina is replaced by a no-op stub writing empty FASTQ files.
