@@ -5,6 +5,7 @@
 // intermediate <prefix>.{e,b,c}.fa.gz and <prefix>_d.fa.gz of the reference.  ART stays on the host (north_star): when an
 // art_illumina is found (--art PATH, next to this binary like gargammel.pl:232-239, or on PATH) it is run exactly as gargammel.pl:1856-1869
 // does and the outputs get the reference's final names <prefix>_a.fa.gz, <prefix>_s.fq.gz / _s1.fq.gz + _s2.fq.gz (:1871-1889).
+// The closing `gzip -f` steps are done in this process: <prefix>_a.fa.gz is made on the device during the run, the FASTQ files by all host threads.
 #include "cli_common.h"
 #include <dirent.h>
 #include <sys/stat.h>
