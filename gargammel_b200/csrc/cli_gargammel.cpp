@@ -30,6 +30,18 @@ static std::vector<std::string> list_fa(const std::string& dir) {
     closedir(d); std::sort(out.begin(), out.end());
     return out;
 }
+// listdirCdir, gargammel.pl:186-210: every subdirectory (sorted here)
+static std::vector<std::string> list_dirs(const std::string& dir) {
+    std::vector<std::string> out; DIR* d = opendir(dir.c_str());
+    if (!d) return out;
+    while (dirent* e = readdir(d)) {
+        std::string n = e->d_name;
+        if (n == "." || n == "..") continue;
+        struct stat st; if (stat((dir + n).c_str(), &st) == 0 && S_ISDIR(st.st_mode)) out.push_back(dir + n);
+    }
+    closedir(d); std::sort(out.begin(), out.end());
+    return out;
+}
 // runcmd, gargammel.pl:71-84: echo the command, run it through bash unless --mock, die on a non-zero status
 static bool run_cmd(const std::string& cmd, bool mock) {
     std::cerr << "running cmd " << cmd << std::endl;
@@ -177,6 +189,31 @@ int main(int argc, char** argv) {
 
     // ---- scan the three directories (gargammel.pl:817-1181)
     std::vector<std::string> fE = list_fa(dir + "endo/"), fC = list_fa(dir + "cont/"), fB = list_fa(dir + "bact/");
+    // multi-cell mode (gargammel.pl:1017-1087): endo/ holds directories C0 .. CN (one cell each, all haploid or all diploid) and no fasta file
+    std::vector<std::vector<std::string> > cells;
+    if (compE > 0) {
+        const std::vector<std::string> cd = list_dirs(dir + "endo/");
+        if (!cd.empty()) {
+            if (!fE.empty()) return die("The endogenous directory " + dir + "endo/ must directories called CX where X is 0...N without any other fasta files, found: " + std::to_string(fE.size()) + " fasta files");
+            long maxc = 0; bool c0 = false;
+            for (size_t k = 0; k < cd.size(); k++) {
+                const size_t sl = cd[k].rfind('/'); const std::string nm = cd[k].substr(sl + 1);
+                bool okn = nm.size() >= 2 && nm[0] == 'C'; for (size_t q = 1; q < nm.size() && okn; q++) okn = nm[q] >= '0' && nm[q] <= '9';
+                if (!okn) return die("Directories " + dir + "endo/ does not correspond to the pattern CX where X is 0...N, found: " + cd[k]);
+                const long v = strtol(nm.c_str() + 1, NULL, 10); if (v > maxc) maxc = v; if (nm == "C0") c0 = true;
+            }
+            if (!c0) return die("Directories " + dir + "endo/ does not correspond to the pattern CX where X is 0...N, must start with C0");
+            for (long i = 0; i <= maxc; i++) {
+                const std::string cdir = dir + "endo/C" + std::to_string(i);
+                if (std::find(cd.begin(), cd.end(), cdir) == cd.end()) return die("Missing directory " + cdir);
+                cells.push_back(list_fa(cdir + "/"));
+                if (i == 0) { if (cells[0].size() != 1 && cells[0].size() != 2) return die("The endogenous directory must have 1 (haploid) or 2 (diploid) files, directory in question: " + cdir + ", found " + std::to_string(cells[0].size())); }
+                else if (cells[(size_t)i].size() != cells[0].size()) return die("The endogenous directory must have all have 1 (haploid) or 2 (diploid) files, directory in question: " + cdir + ", found: " + std::to_string(cells[(size_t)i].size()));
+            }
+            fE = cells[0];                                                          // ploidy and the genome size come from cell 0 (gargammel.pl:1058-1061,1107-1126)
+            std::cerr << "Found " << cd.size() << " directories: C[0..C" << maxc << "]" << std::endl;
+        }
+    }
     if (compE > 0 && fE.size() != 1 && fE.size() != 2) return die("The endogenous directory must have 1 (haploid) or 2 (diploid) files, found: " + std::to_string(fE.size()));
     if (compC > 0 && fC.empty()) return die("If you want contamination, please have at least one file in the cont/ directory");
     std::vector<double> bw;
@@ -193,20 +230,24 @@ int main(int argc, char** argv) {
         }
     }
     // ---- load genomes (only the sources that get fragments)
-    struct Src { std::string path; ggh::GenomeFile g; char kind; int idx; };
+    struct Src { std::string path; ggh::GenomeFile g; char kind; int idx; int cell; };
     std::vector<Src> srcs;
+    int cell_now = 0;
     auto add = [&](const std::vector<std::string>& files, char kind, bool wanted) -> bool {
         for (size_t i = 0; i < files.size(); i++) {
-            Src s; s.path = files[i]; s.kind = kind; s.idx = (int)i;
+            Src s; s.path = files[i]; s.kind = kind; s.idx = (int)i; s.cell = cell_now;
             if (wanted) { if (!ggh::load_genome(files[i], s.g, err)) return false; std::cerr << "Found " << (kind == 'e' ? "endogenous" : kind == 'c' ? "contaminant" : "bacterial") << " file " << files[i] << " (" << s.g.total_len << " bp)" << std::endl; }
             else s.g.total_len = 0;
             srcs.push_back(s);
         }
         return true;
     };
-    if (!add(fE, 'e', compE > 0) || !add(fB, 'b', compB > 0) || !add(fC, 'c', compC > 0)) return die(err);
+    if (cells.empty()) { if (!add(fE, 'e', compE > 0)) return die(err); }
+    else for (size_t i = 0; i < cells.size(); i++) { cell_now = (int)i; if (!add(cells[i], 'e', compE > 0)) return die(err); }   // cells in order, each e1 then e2 (gargammel.pl:1464-1470)
+    cell_now = 0;
+    if (!add(fB, 'b', compB > 0) || !add(fC, 'c', compC > 0)) return die(err);
     uint64_t sumE = 0; std::vector<uint64_t> contLen;
-    for (size_t i = 0; i < srcs.size(); i++) { if (srcs[i].kind == 'e') sumE += srcs[i].g.total_len; if (srcs[i].kind == 'c') contLen.push_back(srcs[i].g.total_len); }
+    for (size_t i = 0; i < srcs.size(); i++) { if (srcs[i].kind == 'e' && srcs[i].cell == 0) sumE += srcs[i].g.total_len; if (srcs[i].kind == 'c') contLen.push_back(srcs[i].g.total_len); }
 
     // ---- size model + average size (gargammel.pl:1185-1229)
     std::vector<int32_t> lens; std::vector<double> cum; double avg = fraglength;
@@ -214,7 +255,7 @@ int main(int argc, char** argv) {
     else if (!sizeFreq.empty()) { if (!ggh::load_size_freq(sizeFreq, lens, cum, err)) return die(err); double t = 0, prev = 0; for (size_t i = 0; i < lens.size(); i++) { t += lens[i] * (cum[i] - prev); prev = cum[i]; } avg = t / cum.back(); }
     else if (lognorm) { if (!(scale > 0)) return die("-scale must be positive"); if (maxsize > 4095) maxsize = 4095; ggh::lognormal_table(loc, scale, 4095, lens, cum); avg = exp(loc + scale * scale / 2); }   // gargammel.pl:1221-1222
     // ---- number of fragments (gargammel.pl:1236-1266)
-    ggh::ApportionIn in; in.compB = compB; in.compC = compC; in.compE = compE; in.n_endo = (int)std::max<size_t>(fE.size(), 1); in.cont_len = contLen; in.bact_w = bw; in.seed = seed;
+    ggh::ApportionIn in; in.compB = compB; in.compC = compC; in.compE = compE; in.n_endo = (int)std::max<size_t>(fE.size(), 1); in.cont_len = contLen; in.bact_w = bw; in.seed = seed; in.n_cells = (int)cells.size();
     if (coverage >= 0) {
         double use = avg; if (se) { if (rl < avg) use = rl; } else if (2 * rl < avg) use = 2 * rl;
         const double sumEeff = fE.size() == 2 ? sumE / 2.0 : (double)sumE;
@@ -225,14 +266,23 @@ int main(int argc, char** argv) {
     in.n_fragments = n;
     ggh::ApportionOut ap;
     if (!ggh::apportion(in, ap, err)) return die(err);
+    std::cerr << "We will generate: \n\n" << ap.nE + ap.nB + ap.nC << "\ttotal fragments\n" << ap.nE << "\tendogenous fragments\n" << ap.nC << "\tcontaminant fragments\n" << ap.nB << "\tbacterial fragments\n";
+    if (!cells.empty()) {                                                           // gargammel.pl:1402; cell 0 carries the script's forced extra fragment(s)
+        uint64_t sum = 0;
+        for (size_t i = 0; i < cells.size(); i++) { std::cerr << "Will extract " << ap.cell_e1[i] + ap.cell_e2[i] << " from cell: " << dir << "endo/C" << i << "/\tendogenous fragments\n"; sum += ap.cell_e1[i] + ap.cell_e2[i]; }
+        ap.nE = sum;                                                                // what the script's fragSim calls add up to: nE+1 (haploid) / nE+2 (diploid)
+    }
     const uint64_t total = ap.nE + ap.nB + ap.nC;
-    std::cerr << "We will generate: \n\n" << total << "\ttotal fragments\n" << ap.nE << "\tendogenous fragments\n" << ap.nC << "\tcontaminant fragments\n" << ap.nB << "\tbacterial fragments\n";
 
     // ---- plan in the reference's output order e, b, c with its tag grammar (gargammel.pl:1476,1521,1554,1600,1648; 1698-1830)
     struct PlanItem { size_t src; uint64_t count; std::string tag; int slot; int comp; };
     std::vector<PlanItem> items;
     for (size_t i = 0; i < srcs.size(); i++) {
         const Src& s = srcs[i]; PlanItem it; it.src = i; it.count = 0; it.slot = -1; it.comp = -1;
+        if (s.kind == 'e' && !cells.empty()) {                                      // tags e1_<cell> / e2_<cell>, or e for every haploid cell (gargammel.pl:1476,1521,1554)
+            it.count = s.idx == 0 ? ap.cell_e1[(size_t)s.cell] : ap.cell_e2[(size_t)s.cell];
+            it.tag = fE.size() == 2 ? std::string(s.idx == 0 ? "e1_" : "e2_") + std::to_string(s.cell) : std::string("e"); it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0;
+        } else
         if (s.kind == 'e') { it.count = (size_t)s.idx < ap.endo.size() ? ap.endo[s.idx] : 0; it.tag = fE.size() == 2 ? (s.idx == 0 ? "e1_0" : "e2_0") : "e"; it.slot = dE.any() ? 0 : -1; it.comp = misE.empty() ? -1 : 0; }
         if (s.kind == 'b') { it.count = (size_t)s.idx < ap.bact.size() ? ap.bact[s.idx] : 0; it.tag = "b" + std::to_string(s.idx + 1); it.slot = dB.any() ? 1 : -1; it.comp = misB.empty() ? -1 : 1; }
         if (s.kind == 'c') { it.count = (size_t)s.idx < ap.cont.size() ? ap.cont[s.idx] : 0; it.tag = "c" + std::to_string(s.idx + 1); it.slot = dC.any() ? 2 : -1; it.comp = misC.empty() ? -1 : 2; }

@@ -379,6 +379,21 @@ bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err) {
     if (in.n_endo == 2) {                                               // gargammel.pl:1272-1279: nE coin flips
         out.endo[0] = binomial_stream(out.nE, 0.5, U); out.endo[1] = out.nE - out.endo[0];
     } else out.endo[0] = out.nE;
+    out.cell.clear(); out.cell_e1.clear(); out.cell_e2.clear();
+    if (in.n_cells > 0) {
+        // multi-cell mode, gargammel.pl:1363-1403: every endogenous fragment picks a cell uniformly; with any endogenous fragments at
+        // all cell 0 is given one fragment MORE before the draws ("force the first file to have at least a fragment", :1372-1374), and
+        // its first file one more on top before the per-cell coin flips (:1383-1385; overwritten in haploid mode, :1397-1398) -- so the
+        // script extracts nE+1 (haploid) or nE+2 (diploid) endogenous fragments.  Mirrored as it is.
+        std::vector<double> w((size_t)in.n_cells, 1.0 / (double)in.n_cells);
+        multinomial(out.nE, w, U, out.cell);
+        out.cell_e1.assign((size_t)in.n_cells, 0); out.cell_e2.assign((size_t)in.n_cells, 0);
+        if (out.nE > 0) out.cell[0]++;
+        for (int i = 0; i < in.n_cells; i++) {
+            if (in.n_endo == 2) { const uint64_t h = binomial_stream(out.cell[i], 0.5, U); out.cell_e1[i] = h + ((i == 0 && out.nE > 0) ? 1 : 0); out.cell_e2[i] = out.cell[i] - h; }
+            else out.cell_e1[i] = out.cell[i];
+        }
+    }
     multinomial(out.nB, in.bact_w, U, out.bact);                        // gargammel.pl:1322-1348 (a miss redraws: weights are renormalised)
     // contaminant: randC = int(rand(sumC)); first j with randC <= cumulative length (gargammel.pl:1421-1431)
     std::vector<double> cw(in.cont_len.size());

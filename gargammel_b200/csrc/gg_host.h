@@ -57,11 +57,14 @@ struct ApportionIn {
     // -c coverage path (gargammel.pl:1255-1258): the endogenous count is fixed by the coverage and kept as it is; only the contaminant and
     // bacterial counts derive from n_fragments = int(nE / compE), as int(n * comp / (compE + compC + compB))
     bool has_nE; uint64_t nE;
-    ApportionIn() : n_fragments(0), compB(0), compC(0), compE(1), n_endo(1), seed(0), has_nE(false), nE(0) {}
+    // multi-cell mode (endo/C0 .. endo/CN, gargammel.pl:1017-1087,1363-1403): number of cell directories, 0 = the plain layout
+    int n_cells;
+    ApportionIn() : n_fragments(0), compB(0), compC(0), compE(1), n_endo(1), seed(0), has_nE(false), nE(0), n_cells(0) {}
 };
 struct ApportionOut {
     uint64_t nE, nC, nB;                   // int(n*comp)  (gargammel.pl:1261-1263)
     std::vector<uint64_t> endo, cont, bact;
+    std::vector<uint64_t> cell, cell_e1, cell_e2;   // multi-cell mode: fragments per cell and from each cell's first / second file
 };
 bool apportion(const ApportionIn& in, ApportionOut& out, std::string& err);
 // exact Binomial(n,p) draw from a Philox-fed uniform stream (inversion for small n*p, BTRS otherwise)

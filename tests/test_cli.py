@@ -596,3 +596,56 @@ def test_cli_bam_modes(workdir, tmp_path):
     assert r.returncode == 0, r.stderr
     _, srec = util.read_bam(str(tmp_path / "s.bam"))
     assert [(n, f, s) for n, f, s, _, _ in srec] == [(n, 4, s) for (n, _, s, _, _) in prec[0::2]] and all(tg == {} for *_, tg in srec)
+
+
+def _cell_dirs(tmp_path, n_cells, ploidy):
+    d = tmp_path / "cells_in"
+    for sub in ("cont", "bact"):
+        (d / sub).mkdir(parents=True)
+    fa, fai = synth.make_genome(99, 2, 30000, prefix="c")
+    (d / "cont" / "cont.1.fa").write_bytes(fa); synth.write_fai(str(d / "cont" / "cont.1.fa.fai"), fai)
+    for i in range(n_cells):
+        (d / "endo" / ("C%d" % i)).mkdir(parents=True)
+        for k in range(ploidy):
+            fa, fai = synth.make_genome(10 * i + k + 1, 2, 30000, prefix="e")
+            nm = "endo.%d.fa" % (k + 1)
+            (d / "endo" / ("C%d" % i) / nm).write_bytes(fa); synth.write_fai(str(d / "endo" / ("C%d" % i) / (nm + ".fai")), fai)
+    return d
+
+
+@pytest.mark.parametrize("ploidy", [1, 2])
+def test_fused_driver_multi_cell_plan_follows_gargammel_pl(tmp_path, ploidy):
+    """endo/C0 .. CN (gargammel.pl:1017-1087,1363-1403,1464-1470): every endogenous fragment picks a cell uniformly, cell 0 gets the
+    script's forced extra fragment (one in haploid mode, one more for its first file in diploid mode), cells run in order with the tags
+    e1_<cell> / e2_<cell> (haploid: e for every cell), then the contaminant.  --mock: runs without a GPU."""
+    import re
+    n_cells = 3
+    d = _cell_dirs(tmp_path, n_cells, ploidy)
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "--noart", "--comp", "0,0.1,0.9", "-n", "30000", "-l", "40", "--seed", "5", "-o", str(tmp_path / "mc"), str(d)])
+    err = r.stderr.decode()
+    assert r.returncode == 0, err
+    assert "Found 3 directories: C[0..C2]" in err and "27000\tendogenous fragments" in err and "3000\tcontaminant fragments" in err
+    per_cell = [int(x) for x in re.findall(r"Will extract (\d+) from cell: ", err)]
+    assert len(per_cell) == n_cells and sum(per_cell) == 27000 + ploidy            # nE+1 (haploid) / nE+2 (diploid), as the script
+    assert all(abs(c - 9000) < 5 * (27000 * (1 / 3) * (2 / 3)) ** 0.5 + 3 for c in per_cell)
+    rng = [(int(a), int(b), tag, path) for a, b, tag, path in re.findall(r"fused range ids \[(\d+),(\d+)\) tag (\S+) file (\S+)", err)]
+    assert [t[2] for t in rng] == (["e1_0", "e2_0", "e1_1", "e2_1", "e1_2", "e2_2", "c1"] if ploidy == 2 else ["e", "e", "e", "c1"])
+    assert [os.path.basename(os.path.dirname(t[3])) for t in rng[:-1]] == [("C%d" % (i // ploidy)) for i in range(n_cells * ploidy)]
+    assert rng[0][0] == 0 and all(rng[k][1] == rng[k + 1][0] for k in range(len(rng) - 1)) and rng[-1][1] == 30000 + ploidy
+    for i in range(n_cells):
+        assert sum(b - a for a, b, _, p in rng[:-1] if os.path.basename(os.path.dirname(p)) == "C%d" % i) == per_cell[i]
+    if ploidy == 2:                                                               # the coin flips of a cell split it about evenly
+        for i in range(n_cells):
+            e1 = rng[2 * i][1] - rng[2 * i][0]
+            assert abs(e1 - per_cell[i] / 2) < 5 * (per_cell[i] / 4) ** 0.5 + 2
+    # the reference's layout errors
+    (d / "endo" / "stray.fa").write_bytes(b">x\nACGT\n")
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "-n", "10", str(d)])
+    assert r.returncode == 1 and b"without any other fasta files" in r.stderr
+    os.remove(str(d / "endo" / "stray.fa"))
+    os.rename(str(d / "endo" / "C1"), str(d / "endo" / "C7"))
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "-n", "10", str(d)])
+    assert r.returncode == 1 and b"Missing directory" in r.stderr and b"endo/C1" in r.stderr
+    os.rename(str(d / "endo" / "C7"), str(d / "endo" / "cellB"))
+    r = run([os.path.join(BIN, "gargammel-b200"), "--mock", "-n", "10", str(d)])
+    assert r.returncode == 1 and b"does not correspond to the pattern CX" in r.stderr
