@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
     DamageSpec dAll, dE, dB, dC;
     bool methyl = false; std::string matNoMeth, matWiMeth;                          // --methyl -matfilenonmeth -matfilemeth (gargammel.pl:431-432,457)
     std::string misE, misB, misC; int distmis = 1;                                  // --misince/--misincb/--misincc/--distmis (gargammel.pl:300-303)
-    const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0)\n\n" +
+    const std::string usage = std::string("\n usage:\t") + argv[0] + " <options> [directory with fasta directories]\n\n This directory should contain endo/ cont/ bact/ (bact/ needs a `list` file when --comp B > 0);\n endo/ holds 1 (haploid) or 2 (diploid) fasta files, or one directory per cell C0 .. CN with 1 or 2 files each\n\n" +
         "\t--comp [B,C,E]\tcomposition (default 0,0,1)\n\t-o\t\toutput prefix (default: [input dir]/simadna)\n\t-n [number] | -c [coverage]\n\t-l [len] | -s [file] | -f [file]\tfragment sizes\n\t-minsize -maxsize\n" +
         "\t-matfile/-damage/-mapdamage f proto\t(endogenous + bacterial; suffix e/b/c for one source)\n\t--methyl -matfilenonmeth [prefix] -matfilemeth [prefix]\tlower-case c/g in the genomes are methylated cytosines\n\t-fa -sa -rl -se\tadapters, read length, single-end\n\t-ss [system] -qs [int] -qs2 [int]\tART sequencing system and quality shifts\n" +
         "\t--art [path]\tart_illumina to run on <prefix>_a.fa (default: ../art_src_MountRainier/art_illumina next to this binary, then $PATH)\n\t--noart\t\tstop after <prefix>_a.fa\n" +
