@@ -161,7 +161,7 @@ bool load_dnacomp(const std::string& path, int dist, CompTables& out, std::strin
         long long d, c[5];
         if (!to_i64(f[3], &d)) { err = "Parse error in composition file " + path + ": " + line; return false; }
         for (int k = 0; k < 5; k++) if (!to_i64(f[4 + k], &c[k])) { err = "Parse error in composition file " + path + ": " + line; return false; }
-        if (llabs(d) <= dist) {                                          // :837
+        if (d >= -(long long)dist && d <= (long long)dist) {             // abs(d) <= dist, :837 (without llabs: LLONG_MIN in a mangled file)
             const bool is3 = f[1] == "3p", is5 = f[1] == "5p", plus = f[2] == "+", minus = f[2] == "-";
             if (!(is3 || is5) || !(plus || minus)) continue;
             const int which = (is5 ? 0 : 2) + (plus ? 0 : 1);
